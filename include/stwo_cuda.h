@@ -1,0 +1,119 @@
+/* stwo_cuda.h — C ABI of libstwo_cuda.so, the B200 (sm_100a) backend for stwo-brainfuck's proving hot path.
+ *
+ * Every entry point replaces one method of Stwo's `Backend` trait family as the reference instantiates it at
+ * `SimdBackend` (stwo-prover 0.1.1 @ 31e8dbc, an un-vendored git dependency: /root/reference/Cargo.toml:41).  The
+ * reference has no FFI of its own (it selects the backend by type parameter, crates/brainfuck_prover/src/
+ * brainfuck_air/mod.rs:486-487,732), so each declaration cites the reference call site that reaches the trait method
+ * and the upstream trait it stands in for.  The Rust binding a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - all functions return 0 on success or a negative sc_status; sc_last_error() gives a thread-local message;
+ *  - no exceptions/panics cross the ABI; a sticky CUDA error makes the context unusable (SC_ECUDA from then on);
+ *  - handles are owned by the caller and freed exactly once; the library never keeps host pointers past a call;
+ *  - a column (`sc_col`) is a device buffer of 32-bit words: M31 values in [0, 2^31-1), or 8 words per Blake2s digest;
+ *  - circle evaluations are in bit-reversed circle-domain order on CanonicCoset(log).circle_domain();
+ *  - QM31 values cross the ABI as 4 words (a + bi) + (c + di)u -> {a,b,c,d}; secure columns are 4 coordinate columns;
+ *  - calls on one context are serialised on its stream and are asynchronous unless they return host data.
+ */
+#ifndef STWO_CUDA_H
+#define STWO_CUDA_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum { SC_OK = 0, SC_EINVAL = -1, SC_ECUDA = -2, SC_ENOMEM = -3, SC_EPROOF = -4, SC_EVERIFY = -5 } sc_status;
+
+typedef struct sc_ctx sc_ctx;             /* device + stream + scratch */
+typedef struct sc_col sc_col;             /* Backend::Column (BaseColumn / Col<B, Blake2sHash>) */
+typedef struct sc_twiddles sc_twiddles;   /* TwiddleTree<B> */
+
+const char* sc_last_error(void);
+int32_t sc_version(void);
+
+/* `stream` is a cudaStream_t to launch on (e.g. torch.cuda.current_stream().cuda_stream) or NULL for a private one. */
+int32_t sc_ctx_create(int32_t device, void* stream, sc_ctx** out);
+int32_t sc_ctx_destroy(sc_ctx* ctx);
+int32_t sc_ctx_sync(sc_ctx* ctx);
+/* Number of kernels launched through this context so far (bench.py's gpu_launches). */
+uint64_t sc_ctx_launch_count(const sc_ctx* ctx);
+
+/* ---- Column<T> (upstream core/backend/mod.rs `Column`: zeros, uninitialized, to_cpu, len, at, set, clone) ---- */
+int32_t sc_col_zeros(sc_ctx* ctx, uint64_t len, sc_col** out);
+int32_t sc_col_uninit(sc_ctx* ctx, uint64_t len, sc_col** out);
+int32_t sc_col_from_host(sc_ctx* ctx, const uint32_t* host, uint64_t len, sc_col** out);   /* FromIterator */
+int32_t sc_col_to_host(sc_ctx* ctx, const sc_col* col, uint32_t* host);                    /* to_cpu */
+int32_t sc_col_read(sc_ctx* ctx, const sc_col* col, uint64_t offset, uint64_t n, uint32_t* host);   /* at */
+int32_t sc_col_write(sc_ctx* ctx, sc_col* col, uint64_t offset, uint64_t n, const uint32_t* host);  /* set */
+int32_t sc_col_clone(sc_ctx* ctx, const sc_col* col, sc_col** out);
+int32_t sc_col_free(sc_ctx* ctx, sc_col* col);
+uint64_t sc_col_len(const sc_col* col);
+void* sc_col_device_ptr(sc_col* col);
+/* Expands `src` (len L) to len 16*L with every value repeated 16x — the reference's PackedBaseField broadcast
+ * (crates/brainfuck_prover/src/components/processor/table.rs:86-100), so only 1/16 of a trace column crosses PCIe. */
+int32_t sc_col_broadcast16(sc_ctx* ctx, const sc_col* src, sc_col** out);
+
+/* ---- ColumnOps::bit_reverse_column (upstream core/backend/simd/bit_reverse.rs) ---- */
+int32_t sc_bit_reverse(sc_ctx* ctx, sc_col* col);
+
+/* ---- FieldOps::batch_inverse for M31 and QM31 (LogupColGenerator::finalize_col, reached from e.g.
+ *      crates/brainfuck_prover/src/components/memory/table.rs:513) ---- */
+int32_t sc_batch_inverse_m31(sc_ctx* ctx, const sc_col* src, sc_col* dst);
+int32_t sc_batch_inverse_qm31(sc_ctx* ctx, sc_col* const src[4], sc_col* const dst[4]);
+
+/* ---- PolyOps (upstream core/poly/circle/ops.rs) ---- */
+/* precompute_twiddles(half_odds(root_log)) — crates/brainfuck_prover/src/brainfuck_air/mod.rs:480-484 (root_log 26). */
+int32_t sc_precompute_twiddles(sc_ctx* ctx, uint32_t root_log, sc_twiddles** out);
+int32_t sc_twiddles_free(sc_ctx* ctx, sc_twiddles* tw);
+int32_t sc_twiddles_to_host(sc_ctx* ctx, const sc_twiddles* tw, uint32_t* twiddles, uint32_t* itwiddles);
+/* interpolate_columns: in place, evaluations -> coefficients; columns may have mixed sizes (log >= 3).
+ * brainfuck_air/mod.rs:497,550-562,690-702 (tree_builder.extend_evals). */
+int32_t sc_interpolate(sc_ctx* ctx, sc_col* const* cols, uint32_t n, const sc_twiddles* tw);
+/* evaluate_polynomials: coefficients -> evaluations on CanonicCoset(log + log_blowup); allocates out[i].
+ * brainfuck_air/mod.rs:500,583,723 (tree_builder.commit). */
+int32_t sc_evaluate(sc_ctx* ctx, sc_col* const* coeffs, uint32_t n, uint32_t log_blowup, const sc_twiddles* tw, sc_col** out);
+/* eval_at_point for n (polynomial, point) pairs; points: n x 8 words {x[4], y[4]}; out: n x 4 words.
+ * Reached from prove_values inside prover::prove (brainfuck_air/mod.rs:732). */
+int32_t sc_eval_at_point(sc_ctx* ctx, sc_col* const* polys, uint32_t n, const uint32_t* points, uint32_t* out);
+
+/* ---- MerkleOps<Blake2sMerkleHasher>::commit_on_layer (upstream core/vcs/ops.rs, core/backend/simd/blake2s.rs) ----
+ * prev may be NULL; out receives a new 8*2^log_size-word column.  brainfuck_air/mod.rs:500,583,723 and every FRI layer. */
+int32_t sc_merkle_commit_layer(sc_ctx* ctx, uint32_t log_size, const sc_col* prev, sc_col* const* cols, uint32_t n, sc_col** out);
+/* MerkleProver::commit over mixed-size columns (stable by size, descending): layers_out[k] = layer of log size k,
+ * k = 0..max_log (caller provides max_log+1 slots); root (8 words) copied to root_out if not NULL. */
+int32_t sc_merkle_commit(sc_ctx* ctx, sc_col* const* cols, uint32_t n, sc_col** layers_out, uint32_t* max_log_out, uint32_t root_out[8]);
+
+/* ---- FriOps (upstream core/backend/simd/fri.rs) — inside prover::prove, brainfuck_air/mod.rs:732 ---- */
+/* src: 4 coordinate columns of a LineEvaluation on half_odds(log); dst: 4 new columns of length 2^(log-1). */
+int32_t sc_fold_line(sc_ctx* ctx, sc_col* const src[4], uint32_t log, const uint32_t alpha[4], const sc_twiddles* tw, sc_col* dst_out[4]);
+/* dst (length 2^(log-1), 4 coords) <- dst*alpha^2 + fold(src on CanonicCoset(log)). */
+int32_t sc_fold_circle_into_line(sc_ctx* ctx, sc_col* const src[4], uint32_t log, const uint32_t alpha[4], const sc_twiddles* tw, sc_col* const dst[4]);
+
+/* ---- QuotientOps::accumulate_quotients (upstream core/backend/simd/quotients.rs, core/pcs/quotients.rs) ----
+ * cols: the n columns of one LDE size 2^log; batches: nb sample batches; batch b has point batch_points[8b..8b+8) and
+ * batch_sizes[b] entries; entries (column index, value[4]) are concatenated in entry_cols / entry_vals.
+ * out: 4 new coordinate columns. */
+int32_t sc_accumulate_quotients(sc_ctx* ctx, uint32_t log, sc_col* const* cols, uint32_t n, const uint32_t random_coeff[4],
+                                const uint32_t* batch_points, const uint32_t* batch_sizes, const uint32_t* entry_cols,
+                                const uint32_t* entry_vals, uint32_t nb, sc_col* out[4]);
+
+/* ---- AccumulationOps (upstream core/backend/simd/accumulation.rs) ---- */
+int32_t sc_accumulate(sc_ctx* ctx, sc_col* const dst[4], sc_col* const src[4]);
+int32_t sc_secure_powers(const uint32_t felt[4], uint32_t n, uint32_t* out /* n x 4 */);
+
+/* ---- GrindOps<Blake2sChannel>::grind: smallest nonce with >= pow_bits trailing zeros (upstream simd/grind.rs) ---- */
+int32_t sc_grind(sc_ctx* ctx, const uint32_t digest[8], uint32_t pow_bits, uint64_t* nonce_out);
+
+/* ---- constraint_framework pieces the reference uses concretely at SimdBackend ---- */
+/* gen_is_first::<B>(log_size) — brainfuck_air/mod.rs:497. */
+int32_t sc_gen_is_first(sc_ctx* ctx, uint32_t log_size, sc_col** out);
+/* simd/prefix_sum.rs inclusive_prefix_sum: in-place inclusive prefix sum in trace-coset order of a bit-reversed
+ * column (LogupTraceGenerator::finalize_last, e.g. crates/brainfuck_prover/src/components/processor/table.rs:530). */
+int32_t sc_prefix_sum_bitrev(sc_ctx* ctx, sc_col* col);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STWO_CUDA_H */

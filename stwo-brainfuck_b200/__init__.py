@@ -1,0 +1,284 @@
+"""stwo-brainfuck B200 backend — host-side mirror of Stwo's ``Backend`` trait surface over libstwo_cuda.so.
+
+The reference selects its backend by type parameter (``SimdBackend``; crates/brainfuck_prover/src/brainfuck_air/
+mod.rs:56,399,480-497,732).  The Rust toolchain is absent from this image, so this module is the Python stand-in for
+the ``CudaBackend`` impl blocks: same method names, argument meaning and error behaviour (Stwo's ``assert!``s become
+``BackendError``), one C-ABI call per trait method (include/stwo_cuda.h).  There is NO CPU path here: importing works
+anywhere (so that the symbol table can be checked), but creating a backend without a CUDA device raises.
+
+The directory name carries a hyphen (task layout), so import it with
+``importlib.import_module("stwo-brainfuck_b200")``; tests/conftest.py aliases it as ``stwo_brainfuck_b200``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+P = (1 << 31) - 1
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libstwo_cuda.so")
+
+_u32p = ctypes.POINTER(ctypes.c_uint32)
+_vp = ctypes.c_void_p
+
+
+class BackendError(RuntimeError):
+    """A non-zero sc_status from the C ABI (mirrors a Stwo assert!/panic or a CUDA failure)."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"stwo_cuda error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+    """Loads libstwo_cuda.so (built in-tree by __graft_entry__.build()).  Fails loudly if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` first; "
+                          "there is no CPU fallback")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.sc_last_error.restype = ctypes.c_char_p
+    lib.sc_col_len.restype = ctypes.c_uint64
+    lib.sc_col_len.argtypes = [_vp]
+    lib.sc_col_device_ptr.restype = _vp
+    lib.sc_col_device_ptr.argtypes = [_vp]
+    lib.sc_ctx_launch_count.restype = ctypes.c_uint64
+    lib.sc_ctx_launch_count.argtypes = [_vp]
+    _lib = lib
+    return lib
+
+
+# Every symbol include/stwo_cuda.h declares (checked by tests/test_abi.py without a GPU).
+ABI_SYMBOLS = [
+    "sc_last_error", "sc_version", "sc_ctx_create", "sc_ctx_destroy", "sc_ctx_sync", "sc_ctx_launch_count",
+    "sc_col_zeros", "sc_col_uninit", "sc_col_from_host", "sc_col_to_host", "sc_col_read", "sc_col_write", "sc_col_clone",
+    "sc_col_free", "sc_col_len", "sc_col_device_ptr", "sc_col_broadcast16", "sc_bit_reverse", "sc_batch_inverse_m31",
+    "sc_batch_inverse_qm31", "sc_precompute_twiddles", "sc_twiddles_free", "sc_twiddles_to_host", "sc_interpolate",
+    "sc_evaluate", "sc_eval_at_point", "sc_merkle_commit_layer", "sc_merkle_commit", "sc_fold_line",
+    "sc_fold_circle_into_line", "sc_accumulate_quotients", "sc_accumulate", "sc_secure_powers", "sc_grind",
+    "sc_gen_is_first", "sc_prefix_sum_bitrev",
+]
+
+
+def _np_u32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(_u32p)
+
+
+class Column:
+    """Backend::Column — a device buffer of u32 words (BaseColumn, or 8 words per Blake2s hash)."""
+
+    def __init__(self, backend: "CudaBackend", handle):
+        self._b = backend
+        self._h = handle
+
+    def __len__(self) -> int:
+        return int(self._b._lib.sc_col_len(self._h))
+
+    def to_cpu(self) -> np.ndarray:
+        out = np.empty(len(self), dtype=np.uint32)
+        self._b._ck(self._b._lib.sc_col_to_host(self._b._ctx, self._h, _ptr(out)))
+        return out
+
+    def at(self, i: int) -> int:
+        out = np.empty(1, dtype=np.uint32)
+        self._b._ck(self._b._lib.sc_col_read(self._b._ctx, self._h, ctypes.c_uint64(i), ctypes.c_uint64(1), _ptr(out)))
+        return int(out[0])
+
+    def read(self, offset: int, n: int) -> np.ndarray:
+        out = np.empty(n, dtype=np.uint32)
+        self._b._ck(self._b._lib.sc_col_read(self._b._ctx, self._h, ctypes.c_uint64(offset), ctypes.c_uint64(n), _ptr(out)))
+        return out
+
+    def set(self, i: int, v: int) -> None:
+        a = np.array([v], dtype=np.uint32)
+        self._b._ck(self._b._lib.sc_col_write(self._b._ctx, self._h, ctypes.c_uint64(i), ctypes.c_uint64(1), _ptr(a)))
+
+    def clone(self) -> "Column":
+        h = _vp()
+        self._b._ck(self._b._lib.sc_col_clone(self._b._ctx, self._h, ctypes.byref(h)))
+        return Column(self._b, h)
+
+    def device_ptr(self) -> int:
+        return int(self._b._lib.sc_col_device_ptr(self._h))
+
+    def free(self) -> None:
+        if self._h is not None:
+            self._b._lib.sc_col_free(self._b._ctx, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            if self._h is not None and self._b._ctx is not None:
+                self.free()
+        except Exception:
+            pass
+
+
+class Twiddles:
+    """TwiddleTree<CudaBackend>: x-coordinate tree of half_odds(root_log) and its inverses, device resident."""
+
+    def __init__(self, backend: "CudaBackend", handle, root_log: int):
+        self._b, self._h, self.root_log = backend, handle, root_log
+
+    def to_cpu(self):
+        n = 1 << self.root_log
+        tw, itw = np.empty(n, dtype=np.uint32), np.empty(n, dtype=np.uint32)
+        self._b._ck(self._b._lib.sc_twiddles_to_host(self._b._ctx, self._h, _ptr(tw), _ptr(itw)))
+        return tw, itw
+
+
+class CudaBackend:
+    """The trait surface the reference needs from its backend, one method per trait method."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        self._lib = load_library()
+        self._ctx = None
+        ctx = _vp()
+        self._ck(self._lib.sc_ctx_create(ctypes.c_int32(device), _vp(stream) if stream else None, ctypes.byref(ctx)))
+        self._ctx = ctx
+
+    # -- plumbing
+    def _ck(self, code: int) -> None:
+        if code != 0:
+            raise BackendError(code, (self._lib.sc_last_error() or b"").decode())
+
+    def _arr(self, cols: Sequence[Column]):
+        return (_vp * max(1, len(cols)))(*[c._h for c in cols])
+
+    def sync(self) -> None:
+        self._ck(self._lib.sc_ctx_sync(self._ctx))
+
+    def launch_count(self) -> int:
+        return int(self._lib.sc_ctx_launch_count(self._ctx))
+
+    def close(self) -> None:
+        if self._ctx is not None:
+            self._lib.sc_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    # -- Column / ColumnOps
+    def column(self, values) -> Column:
+        a = _np_u32(values)
+        h = _vp()
+        self._ck(self._lib.sc_col_from_host(self._ctx, _ptr(a), ctypes.c_uint64(a.size), ctypes.byref(h)))
+        return Column(self, h)
+
+    def zeros(self, n: int) -> Column:
+        h = _vp()
+        self._ck(self._lib.sc_col_zeros(self._ctx, ctypes.c_uint64(n), ctypes.byref(h)))
+        return Column(self, h)
+
+    def broadcast16(self, col: Column) -> Column:
+        h = _vp()
+        self._ck(self._lib.sc_col_broadcast16(self._ctx, col._h, ctypes.byref(h)))
+        return Column(self, h)
+
+    def bit_reverse_column(self, col: Column) -> None:
+        self._ck(self._lib.sc_bit_reverse(self._ctx, col._h))
+
+    # -- FieldOps
+    def batch_inverse(self, src: Column, dst: Column) -> None:
+        self._ck(self._lib.sc_batch_inverse_m31(self._ctx, src._h, dst._h))
+
+    def batch_inverse_secure(self, src: Sequence[Column], dst: Sequence[Column]) -> None:
+        self._ck(self._lib.sc_batch_inverse_qm31(self._ctx, self._arr(src), self._arr(dst)))
+
+    # -- PolyOps
+    def precompute_twiddles(self, root_log: int) -> Twiddles:
+        h = _vp()
+        self._ck(self._lib.sc_precompute_twiddles(self._ctx, ctypes.c_uint32(root_log), ctypes.byref(h)))
+        return Twiddles(self, h, root_log)
+
+    def interpolate_columns(self, cols: Sequence[Column], twiddles: Twiddles) -> None:
+        """In place: bit-reversed evaluations on CanonicCoset(log).circle_domain() -> coefficients."""
+        self._ck(self._lib.sc_interpolate(self._ctx, self._arr(cols), ctypes.c_uint32(len(cols)), twiddles._h))
+
+    def evaluate_polynomials(self, polys: Sequence[Column], log_blowup: int, twiddles: Twiddles) -> List[Column]:
+        out = (_vp * max(1, len(polys)))()
+        self._ck(self._lib.sc_evaluate(self._ctx, self._arr(polys), ctypes.c_uint32(len(polys)), ctypes.c_uint32(log_blowup),
+                                       twiddles._h, out))
+        return [Column(self, _vp(out[i])) for i in range(len(polys))]
+
+    def eval_at_point(self, polys: Sequence[Column], points) -> np.ndarray:
+        """points: (n, 8) words {x[4], y[4]} -> (n, 4) QM31 values."""
+        pts = _np_u32(points).reshape(len(polys), 8)
+        out = np.empty((len(polys), 4), dtype=np.uint32)
+        self._ck(self._lib.sc_eval_at_point(self._ctx, self._arr(polys), ctypes.c_uint32(len(polys)), _ptr(pts), _ptr(out)))
+        return out
+
+    # -- MerkleOps<Blake2sMerkleHasher>
+    def commit_on_layer(self, log_size: int, prev_layer: Optional[Column], columns: Sequence[Column]) -> Column:
+        h = _vp()
+        self._ck(self._lib.sc_merkle_commit_layer(self._ctx, ctypes.c_uint32(log_size), prev_layer._h if prev_layer else None,
+                                                  self._arr(columns), ctypes.c_uint32(len(columns)), ctypes.byref(h)))
+        return Column(self, h)
+
+    def merkle_commit(self, columns: Sequence[Column]):
+        """MerkleProver::commit: returns (layers[k] = layer of log size k, root as 8 words)."""
+        max_log = max(int(np.log2(len(c))) for c in columns) if columns else 0
+        layers = (_vp * (max_log + 1))()
+        ml = ctypes.c_uint32()
+        root = np.empty(8, dtype=np.uint32)
+        self._ck(self._lib.sc_merkle_commit(self._ctx, self._arr(columns), ctypes.c_uint32(len(columns)), layers,
+                                            ctypes.byref(ml), _ptr(root)))
+        return [Column(self, _vp(layers[i])) for i in range(max_log + 1)], root
+
+    # -- FriOps
+    def fold_line(self, src: Sequence[Column], log: int, alpha, twiddles: Twiddles) -> List[Column]:
+        out = (_vp * 4)()
+        a = _np_u32(alpha)
+        self._ck(self._lib.sc_fold_line(self._ctx, self._arr(src), ctypes.c_uint32(log), _ptr(a), twiddles._h, out))
+        return [Column(self, _vp(out[i])) for i in range(4)]
+
+    def fold_circle_into_line(self, dst: Sequence[Column], src: Sequence[Column], log: int, alpha, twiddles: Twiddles) -> None:
+        a = _np_u32(alpha)
+        self._ck(self._lib.sc_fold_circle_into_line(self._ctx, self._arr(src), ctypes.c_uint32(log), _ptr(a), twiddles._h,
+                                                    self._arr(dst)))
+
+    # -- QuotientOps
+    def accumulate_quotients(self, log: int, columns: Sequence[Column], random_coeff, batch_points, batch_sizes, entry_cols,
+                             entry_vals) -> List[Column]:
+        out = (_vp * 4)()
+        rc, bp, bs = _np_u32(random_coeff), _np_u32(batch_points), _np_u32(batch_sizes)
+        ec, ev = _np_u32(entry_cols), _np_u32(entry_vals)
+        self._ck(self._lib.sc_accumulate_quotients(self._ctx, ctypes.c_uint32(log), self._arr(columns), ctypes.c_uint32(len(columns)),
+                                                   _ptr(rc), _ptr(bp), _ptr(bs), _ptr(ec), _ptr(ev), ctypes.c_uint32(bs.size), out))
+        return [Column(self, _vp(out[i])) for i in range(4)]
+
+    # -- AccumulationOps
+    def accumulate(self, dst: Sequence[Column], src: Sequence[Column]) -> None:
+        self._ck(self._lib.sc_accumulate(self._ctx, self._arr(dst), self._arr(src)))
+
+    def generate_secure_powers(self, felt, n: int) -> np.ndarray:
+        f = _np_u32(felt)
+        out = np.empty((n, 4), dtype=np.uint32)
+        self._ck(self._lib.sc_secure_powers(_ptr(f), ctypes.c_uint32(n), _ptr(out)))
+        return out
+
+    # -- GrindOps
+    def grind(self, digest, pow_bits: int) -> int:
+        d = _np_u32(digest)
+        nonce = ctypes.c_uint64()
+        self._ck(self._lib.sc_grind(self._ctx, _ptr(d), ctypes.c_uint32(pow_bits), ctypes.byref(nonce)))
+        return int(nonce.value)
+
+    # -- constraint_framework helpers
+    def gen_is_first(self, log_size: int) -> Column:
+        h = _vp()
+        self._ck(self._lib.sc_gen_is_first(self._ctx, ctypes.c_uint32(log_size), ctypes.byref(h)))
+        return Column(self, h)
+
+    def inclusive_prefix_sum(self, col: Column) -> None:
+        self._ck(self._lib.sc_prefix_sum_bitrev(self._ctx, col._h))

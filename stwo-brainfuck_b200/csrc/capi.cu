@@ -1,0 +1,501 @@
+// C ABI of libstwo_cuda.so (declared in include/stwo_cuda.h): context, columns, and one entry per Backend trait method.
+// Host-side glue only — argument checking, grouping by size, staging of small tables; all arithmetic is in the kernels.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/stwo_cuda.h"
+#include "kernels.cuh"
+
+using namespace sb;
+
+namespace sb { unsigned long long g_launch_count = 0; }
+
+struct sc_col {
+  uint32_t* d;
+  uint64_t len;
+};
+struct sc_twiddles {
+  uint32_t root_log;
+  uint32_t* tw;   // 2^root_log words
+  uint32_t* itw;  // 2^root_log words
+};
+struct sc_ctx {
+  int device;
+  cudaStream_t st;
+  bool own_stream;
+  bool poisoned;
+  // staging ring for small host->device tables (pointer arrays, task tables)
+  uint8_t* h_ring;
+  uint8_t* d_ring;
+  size_t ring_size, ring_off;
+};
+
+static thread_local std::string g_err;
+static int32_t fail(int32_t code, const std::string& m) { g_err = m; return code; }
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      if (ctx) ctx->poisoned = true;                                                               \
+      return fail(SC_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                   \
+    }                                                                                              \
+  } while (0)
+#define CKL(expr)                                                                                  \
+  do {                                                                                             \
+    int e_ = (expr);                                                                               \
+    if (e_ > 0) { ctx->poisoned = true; return fail(SC_ECUDA, std::string(#expr) + ": " + cudaGetErrorString((cudaError_t)e_)); } \
+    if (e_ < 0) return fail(SC_EINVAL, std::string(#expr) + ": invalid argument");                 \
+  } while (0)
+#define ENTER()                                                                                    \
+  if (!ctx) return fail(SC_EINVAL, "null context");                                                \
+  if (ctx->poisoned) return fail(SC_ECUDA, "context unusable after an earlier CUDA error");        \
+  CK(cudaSetDevice(ctx->device))
+
+static bool is_pow2(uint64_t x) { return x && !(x & (x - 1)); }
+static uint32_t ilog2(uint64_t x) { uint32_t l = 0; while ((1ull << l) < x) l++; return l; }
+
+// Copies a small host table to the device through the pinned ring; returns the device address.
+static int32_t stage(sc_ctx* ctx, const void* host, size_t bytes, void** dptr) {
+  size_t need = (bytes + 255) & ~(size_t)255;
+  if (need > ctx->ring_size) return fail(SC_ENOMEM, "staging table too large");
+  if (ctx->ring_off + need > ctx->ring_size) {
+    CK(cudaStreamSynchronize(ctx->st));
+    ctx->ring_off = 0;
+  }
+  memcpy(ctx->h_ring + ctx->ring_off, host, bytes);
+  CK(cudaMemcpyAsync(ctx->d_ring + ctx->ring_off, ctx->h_ring + ctx->ring_off, bytes, cudaMemcpyHostToDevice, ctx->st));
+  *dptr = ctx->d_ring + ctx->ring_off;
+  ctx->ring_off += need;
+  return SC_OK;
+}
+
+static int32_t new_col(sc_ctx* ctx, uint64_t len, sc_col** out) {
+  uint32_t* d = nullptr;
+  cudaError_t e = cudaMallocAsync((void**)&d, std::max<uint64_t>(len, 4) * 4, ctx->st);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(SC_ENOMEM, std::string("cudaMallocAsync: ") + cudaGetErrorString(e)); }
+  *out = new sc_col{d, len};
+  return SC_OK;
+}
+
+extern "C" {
+
+const char* sc_last_error(void) { return g_err.c_str(); }
+int32_t sc_version(void) { return 1; }
+
+int32_t sc_ctx_create(int32_t device, void* stream, sc_ctx** out) {
+  sc_ctx* ctx = nullptr;
+  if (!out) return fail(SC_EINVAL, "null out");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(SC_ECUDA, "no CUDA device available (this library has no CPU path)"); }
+  if (device < 0 || device >= ndev) return fail(SC_EINVAL, "bad device index");
+  CK(cudaSetDevice(device));
+  sc_ctx* c = new sc_ctx();
+  c->device = device; c->poisoned = false; c->ring_size = 4u << 20; c->ring_off = 0;
+  if (stream) { c->st = (cudaStream_t)stream; c->own_stream = false; }
+  else { CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking)); c->own_stream = true; }
+  CK(cudaMallocHost((void**)&c->h_ring, c->ring_size));
+  CK(cudaMalloc((void**)&c->d_ring, c->ring_size));
+  // keep freed blocks in the stream-ordered pool: column churn must not hit the driver allocator
+  cudaMemPool_t pool;
+  CK(cudaDeviceGetDefaultMemPool(&pool, device));
+  uint64_t thr = ~0ull;
+  CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  *out = c;
+  return SC_OK;
+}
+int32_t sc_ctx_destroy(sc_ctx* ctx) {
+  if (!ctx) return SC_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->st);
+  cudaFreeHost(ctx->h_ring);
+  cudaFree(ctx->d_ring);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->st);
+  delete ctx;
+  return SC_OK;
+}
+int32_t sc_ctx_sync(sc_ctx* ctx) { ENTER(); CK(cudaStreamSynchronize(ctx->st)); return SC_OK; }
+uint64_t sc_ctx_launch_count(const sc_ctx*) { return g_launch_count; }
+
+// ------------------------------------------------------------------ columns
+int32_t sc_col_uninit(sc_ctx* ctx, uint64_t len, sc_col** out) { ENTER(); if (!out) return fail(SC_EINVAL, "null out"); return new_col(ctx, len, out); }
+int32_t sc_col_zeros(sc_ctx* ctx, uint64_t len, sc_col** out) {
+  ENTER();
+  if (!out) return fail(SC_EINVAL, "null out");
+  int32_t r = new_col(ctx, len, out);
+  if (r) return r;
+  CK(cudaMemsetAsync((*out)->d, 0, len * 4, ctx->st));
+  return SC_OK;
+}
+int32_t sc_col_from_host(sc_ctx* ctx, const uint32_t* host, uint64_t len, sc_col** out) {
+  ENTER();
+  if (!out || (!host && len)) return fail(SC_EINVAL, "null argument");
+  int32_t r = new_col(ctx, len, out);
+  if (r) return r;
+  CK(cudaMemcpyAsync((*out)->d, host, len * 4, cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));  // host buffer may be pageable and is not retained
+  return SC_OK;
+}
+int32_t sc_col_to_host(sc_ctx* ctx, const sc_col* col, uint32_t* host) {
+  ENTER();
+  if (!col || !host) return fail(SC_EINVAL, "null argument");
+  CK(cudaMemcpyAsync(host, col->d, col->len * 4, cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  return SC_OK;
+}
+int32_t sc_col_read(sc_ctx* ctx, const sc_col* col, uint64_t offset, uint64_t n, uint32_t* host) {
+  ENTER();
+  if (!col || !host || offset + n > col->len) return fail(SC_EINVAL, "read out of range");
+  CK(cudaMemcpyAsync(host, col->d + offset, n * 4, cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  return SC_OK;
+}
+int32_t sc_col_write(sc_ctx* ctx, sc_col* col, uint64_t offset, uint64_t n, const uint32_t* host) {
+  ENTER();
+  if (!col || !host || offset + n > col->len) return fail(SC_EINVAL, "write out of range");
+  CK(cudaMemcpyAsync(col->d + offset, host, n * 4, cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  return SC_OK;
+}
+int32_t sc_col_clone(sc_ctx* ctx, const sc_col* col, sc_col** out) {
+  ENTER();
+  if (!col || !out) return fail(SC_EINVAL, "null argument");
+  int32_t r = new_col(ctx, col->len, out);
+  if (r) return r;
+  CK(cudaMemcpyAsync((*out)->d, col->d, col->len * 4, cudaMemcpyDeviceToDevice, ctx->st));
+  return SC_OK;
+}
+int32_t sc_col_free(sc_ctx* ctx, sc_col* col) {
+  if (!col) return SC_OK;
+  if (!ctx) return fail(SC_EINVAL, "null context");
+  cudaSetDevice(ctx->device);
+  cudaFreeAsync(col->d, ctx->st);
+  delete col;
+  return SC_OK;
+}
+uint64_t sc_col_len(const sc_col* col) { return col ? col->len : 0; }
+void* sc_col_device_ptr(sc_col* col) { return col ? col->d : nullptr; }
+
+int32_t sc_col_broadcast16(sc_ctx* ctx, const sc_col* src, sc_col** out) {
+  ENTER();
+  if (!src || !out) return fail(SC_EINVAL, "null argument");
+  int32_t r = new_col(ctx, src->len * 16, out);
+  if (r) return r;
+  CKL(launch_broadcast16(src->d, (*out)->d, src->len, ctx->st));
+  return SC_OK;
+}
+
+int32_t sc_bit_reverse(sc_ctx* ctx, sc_col* col) {
+  ENTER();
+  if (!col || !is_pow2(col->len)) return fail(SC_EINVAL, "bit_reverse: length must be a power of two");
+  CKL(launch_bit_reverse(col->d, ilog2(col->len), ctx->st));
+  return SC_OK;
+}
+
+int32_t sc_batch_inverse_m31(sc_ctx* ctx, const sc_col* src, sc_col* dst) {
+  ENTER();
+  if (!src || !dst || src->len != dst->len) return fail(SC_EINVAL, "batch_inverse: length mismatch");
+  CKL(launch_batch_inverse_m31(src->d, dst->d, src->len, ctx->st));
+  return SC_OK;
+}
+int32_t sc_batch_inverse_qm31(sc_ctx* ctx, sc_col* const src[4], sc_col* const dst[4]) {
+  ENTER();
+  const uint32_t* s[4]; uint32_t* d[4];
+  for (int k = 0; k < 4; k++) {
+    if (!src[k] || !dst[k] || src[k]->len != src[0]->len || dst[k]->len != src[0]->len) return fail(SC_EINVAL, "batch_inverse: bad columns");
+    s[k] = src[k]->d; d[k] = dst[k]->d;
+  }
+  CKL(launch_batch_inverse_qm31(s, d, src[0]->len, ctx->st));
+  return SC_OK;
+}
+
+// ------------------------------------------------------------------ twiddles / FFT
+int32_t sc_precompute_twiddles(sc_ctx* ctx, uint32_t root_log, sc_twiddles** out) {
+  ENTER();
+  if (!out || root_log < 2 || root_log > 29) return fail(SC_EINVAL, "precompute_twiddles: root_log must be in [2,29]");
+  sc_twiddles* t = new sc_twiddles{root_log, nullptr, nullptr};
+  CK(cudaMallocAsync((void**)&t->tw, (size_t)4 << root_log, ctx->st));
+  CK(cudaMallocAsync((void**)&t->itw, (size_t)4 << root_log, ctx->st));
+  CKL(launch_twiddle_tree(t->tw, t->itw, root_log, ctx->st));
+  *out = t;
+  return SC_OK;
+}
+int32_t sc_twiddles_free(sc_ctx* ctx, sc_twiddles* tw) {
+  if (!tw) return SC_OK;
+  if (!ctx) return fail(SC_EINVAL, "null context");
+  cudaSetDevice(ctx->device);
+  cudaFreeAsync(tw->tw, ctx->st);
+  cudaFreeAsync(tw->itw, ctx->st);
+  delete tw;
+  return SC_OK;
+}
+int32_t sc_twiddles_to_host(sc_ctx* ctx, const sc_twiddles* tw, uint32_t* twiddles, uint32_t* itwiddles) {
+  ENTER();
+  if (!tw) return fail(SC_EINVAL, "null twiddles");
+  if (twiddles) CK(cudaMemcpyAsync(twiddles, tw->tw, (size_t)4 << tw->root_log, cudaMemcpyDeviceToHost, ctx->st));
+  if (itwiddles) CK(cudaMemcpyAsync(itwiddles, tw->itw, (size_t)4 << tw->root_log, cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  return SC_OK;
+}
+
+int32_t sc_interpolate(sc_ctx* ctx, sc_col* const* cols, uint32_t n, const sc_twiddles* tw) {
+  ENTER();
+  if (!tw || (!cols && n)) return fail(SC_EINVAL, "null argument");
+  std::map<uint32_t, std::vector<uint32_t*>> by_log;
+  for (uint32_t i = 0; i < n; i++) {
+    if (!cols[i] || !is_pow2(cols[i]->len)) return fail(SC_EINVAL, "interpolate: column length must be a power of two");
+    uint32_t lg = ilog2(cols[i]->len);
+    if (lg < 3) return fail(SC_EINVAL, "interpolate: log size < 3 is not supported on the device");
+    if (lg > tw->root_log + 1) return fail(SC_EINVAL, "interpolate: twiddle tree too small for this domain");
+    by_log[lg].push_back(cols[i]->d);
+  }
+  for (auto& kv : by_log) {
+    void* dp;
+    int32_t r = stage(ctx, kv.second.data(), kv.second.size() * sizeof(void*), &dp);
+    if (r) return r;
+    CKL(launch_interpolate((uint32_t* const*)dp, (uint32_t)kv.second.size(), kv.first, tw->itw + ((size_t)1 << tw->root_log), ctx->st));
+  }
+  return SC_OK;
+}
+
+int32_t sc_evaluate(sc_ctx* ctx, sc_col* const* coeffs, uint32_t n, uint32_t log_blowup, const sc_twiddles* tw, sc_col** out) {
+  ENTER();
+  if (!tw || !out || (!coeffs && n)) return fail(SC_EINVAL, "null argument");
+  struct G { std::vector<const uint32_t*> src; std::vector<uint32_t*> dst; };
+  std::map<uint32_t, G> by_log;
+  for (uint32_t i = 0; i < n; i++) {
+    if (!coeffs[i] || !is_pow2(coeffs[i]->len)) return fail(SC_EINVAL, "evaluate: column length must be a power of two");
+    uint32_t lg = ilog2(coeffs[i]->len);
+    if (lg + log_blowup < 3) return fail(SC_EINVAL, "evaluate: domain log size < 3 is not supported on the device");
+    if (lg + log_blowup > tw->root_log + 1) return fail(SC_EINVAL, "evaluate: twiddle tree too small for this domain");
+    if (log_blowup > 3) return fail(SC_EINVAL, "evaluate: log_blowup > 3 not supported");
+  }
+  for (uint32_t i = 0; i < n; i++) {
+    uint32_t lg = ilog2(coeffs[i]->len);
+    int32_t r = new_col(ctx, coeffs[i]->len << log_blowup, &out[i]);
+    if (r) return r;
+    by_log[lg].src.push_back(coeffs[i]->d);
+    by_log[lg].dst.push_back(out[i]->d);
+  }
+  for (auto& kv : by_log) {
+    void *ds, *dd;
+    int32_t r = stage(ctx, kv.second.src.data(), kv.second.src.size() * sizeof(void*), &ds);
+    if (r) return r;
+    r = stage(ctx, kv.second.dst.data(), kv.second.dst.size() * sizeof(void*), &dd);
+    if (r) return r;
+    CKL(launch_evaluate((const uint32_t* const*)ds, (uint32_t* const*)dd, (uint32_t)kv.second.src.size(), kv.first,
+                        kv.first + log_blowup, tw->tw + ((size_t)1 << tw->root_log), ctx->st));
+  }
+  return SC_OK;
+}
+
+int32_t sc_eval_at_point(sc_ctx* ctx, sc_col* const* polys, uint32_t n, const uint32_t* points, uint32_t* out) {
+  ENTER();
+  if (!n) return SC_OK;
+  if (!polys || !points || !out) return fail(SC_EINVAL, "null argument");
+  std::vector<EvalTaskHost> tasks(n);
+  uint32_t blocks = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    if (!polys[i] || !is_pow2(polys[i]->len)) return fail(SC_EINVAL, "eval_at_point: length must be a power of two");
+    uint32_t lg = ilog2(polys[i]->len);
+    if (lg > 28) return fail(SC_EINVAL, "eval_at_point: polynomial too large");
+    const uint32_t* p = points + 8 * i;
+    QM31 x = q_make(p[0], p[1], p[2], p[3]), y = q_make(p[4], p[5], p[6], p[7]);
+    EvalTaskHost& t = tasks[i];
+    t.coeffs = polys[i]->d; t.log = lg; t.first_block = blocks;
+    for (int k = 0; k < 28; k++) t.f[k] = q_zero();
+    t.f[0] = y;
+    for (uint32_t k = 1; k < lg; k++) { t.f[k] = x; x = q_sub(q_mulm(q_sqr(x), 2), q_fromm(1)); }
+    blocks += lg > 11 ? (1u << (lg - 11)) : 1u;
+  }
+  void* dt;
+  int32_t r = stage(ctx, tasks.data(), tasks.size() * sizeof(EvalTaskHost), &dt);
+  if (r) return r;
+  QM31 *partials, *work, *dout;
+  CK(cudaMallocAsync((void**)&partials, (size_t)blocks * sizeof(QM31), ctx->st));
+  CK(cudaMallocAsync((void**)&work, (size_t)blocks * sizeof(QM31), ctx->st));
+  CK(cudaMallocAsync((void**)&dout, (size_t)n * sizeof(QM31), ctx->st));
+  CKL(launch_eval_at_point_tasks(dt, n, blocks, partials, work, dout, ctx->st));
+  CK(cudaMemcpyAsync(out, dout, (size_t)n * sizeof(QM31), cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  CK(cudaFreeAsync(partials, ctx->st));
+  CK(cudaFreeAsync(work, ctx->st));
+  CK(cudaFreeAsync(dout, ctx->st));
+  return SC_OK;
+}
+
+// ------------------------------------------------------------------ Merkle
+int32_t sc_merkle_commit_layer(sc_ctx* ctx, uint32_t log_size, const sc_col* prev, sc_col* const* cols, uint32_t n, sc_col** out) {
+  ENTER();
+  if (!out || (!cols && n) || log_size > 30) return fail(SC_EINVAL, "commit_on_layer: bad argument");
+  uint64_t rows = 1ull << log_size;
+  if (prev && prev->len != rows * 16) return fail(SC_EINVAL, "commit_on_layer: previous layer must have 2^(log_size+1) digests");
+  std::vector<const uint32_t*> p(n);
+  for (uint32_t i = 0; i < n; i++) {
+    if (!cols[i] || cols[i]->len != rows) return fail(SC_EINVAL, "commit_on_layer: column length != 2^log_size");
+    p[i] = cols[i]->d;
+  }
+  void* dp = nullptr;
+  if (n) { int32_t r = stage(ctx, p.data(), n * sizeof(void*), &dp); if (r) return r; }
+  int32_t r = new_col(ctx, rows * 8, out);
+  if (r) return r;
+  CKL(launch_commit_layer(log_size, prev ? prev->d : nullptr, (const uint32_t* const*)dp, n, (*out)->d, ctx->st));
+  return SC_OK;
+}
+
+int32_t sc_merkle_commit(sc_ctx* ctx, sc_col* const* cols, uint32_t n, sc_col** layers_out, uint32_t* max_log_out, uint32_t root_out[8]) {
+  ENTER();
+  if (!layers_out || (!cols && n)) return fail(SC_EINVAL, "null argument");
+  uint32_t max_log = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    if (!cols[i] || !is_pow2(cols[i]->len)) return fail(SC_EINVAL, "merkle_commit: column length must be a power of two");
+    max_log = std::max(max_log, ilog2(cols[i]->len));
+  }
+  for (int lg = (int)max_log; lg >= 0; lg--) {
+    std::vector<sc_col*> lc;
+    for (uint32_t i = 0; i < n; i++) if (ilog2(cols[i]->len) == (uint32_t)lg) lc.push_back(cols[i]);  // stable
+    int32_t r = sc_merkle_commit_layer(ctx, lg, lg == (int)max_log ? nullptr : layers_out[lg + 1], lc.data(), (uint32_t)lc.size(), &layers_out[lg]);
+    if (r) return r;
+  }
+  if (max_log_out) *max_log_out = max_log;
+  if (root_out) return sc_col_read(ctx, layers_out[0], 0, 8, root_out);
+  return SC_OK;
+}
+
+// ------------------------------------------------------------------ FRI
+int32_t sc_fold_line(sc_ctx* ctx, sc_col* const src[4], uint32_t log, const uint32_t alpha[4], const sc_twiddles* tw, sc_col* dst_out[4]) {
+  ENTER();
+  if (!tw || log < 1 || log > tw->root_log) return fail(SC_EINVAL, "fold_line: bad log size / twiddle tree too small");
+  const uint32_t* s[4]; uint32_t* d[4];
+  for (int k = 0; k < 4; k++) {
+    if (!src[k] || src[k]->len != (1ull << log)) return fail(SC_EINVAL, "fold_line: bad source column");
+    s[k] = src[k]->d;
+  }
+  for (int k = 0; k < 4; k++) { int32_t r = new_col(ctx, 1ull << (log - 1), &dst_out[k]); if (r) return r; d[k] = dst_out[k]->d; }
+  CKL(launch_fold_line(s, log, q_make(alpha[0], alpha[1], alpha[2], alpha[3]), d, tw->itw + ((size_t)1 << tw->root_log), ctx->st));
+  return SC_OK;
+}
+int32_t sc_fold_circle_into_line(sc_ctx* ctx, sc_col* const src[4], uint32_t log, const uint32_t alpha[4], const sc_twiddles* tw, sc_col* const dst[4]) {
+  ENTER();
+  if (!tw || log < 3 || log > tw->root_log + 1) return fail(SC_EINVAL, "fold_circle_into_line: bad log size / twiddle tree too small");
+  const uint32_t* s[4]; uint32_t* d[4];
+  for (int k = 0; k < 4; k++) {
+    if (!src[k] || !dst[k] || src[k]->len != (1ull << log) || dst[k]->len != (1ull << (log - 1))) return fail(SC_EINVAL, "fold_circle_into_line: bad columns");
+    s[k] = src[k]->d; d[k] = dst[k]->d;
+  }
+  CKL(launch_fold_circle_into_line(s, log, q_make(alpha[0], alpha[1], alpha[2], alpha[3]), d, tw->itw + ((size_t)1 << tw->root_log), ctx->st));
+  return SC_OK;
+}
+
+// ------------------------------------------------------------------ quotients
+int32_t sc_accumulate_quotients(sc_ctx* ctx, uint32_t log, sc_col* const* cols, uint32_t n, const uint32_t random_coeff[4],
+                                const uint32_t* batch_points, const uint32_t* batch_sizes, const uint32_t* entry_cols,
+                                const uint32_t* entry_vals, uint32_t nb, sc_col* out[4]) {
+  ENTER();
+  if (log < 2 || log > 30 || (!cols && n) || !out) return fail(SC_EINVAL, "accumulate_quotients: bad argument");
+  std::vector<const uint32_t*> p(n);
+  for (uint32_t i = 0; i < n; i++) {
+    if (!cols[i] || cols[i]->len != (1ull << log)) return fail(SC_EINVAL, "accumulate_quotients: column length != 2^log");
+    p[i] = cols[i]->d;
+  }
+  QM31 alpha = q_make(random_coeff[0], random_coeff[1], random_coeff[2], random_coeff[3]);
+  std::vector<QuotBatch> qb(nb);
+  std::vector<QuotEntry> qe;
+  size_t e = 0;
+  for (uint32_t b = 0; b < nb; b++) {
+    const uint32_t* q = batch_points + 8 * b;
+    QM31 sx = q_make(q[0], q[1], q[2], q[3]), sy = q_make(q[4], q[5], q[6], q[7]);
+    QuotBatch& B = qb[b];
+    B.prx = sx.a; B.pix = sx.b; B.pry = sy.a; B.piy = sy.b;
+    B.suma = q_zero(); B.sumb = q_zero(); B.first = (uint32_t)qe.size(); B.count = batch_sizes[b];
+    QM31 al = q_fromm(1);
+    QM31 c = q_sub(q_conj(sy), sy);
+    for (uint32_t j = 0; j < batch_sizes[b]; j++, e++) {
+      if (entry_cols[e] >= n) return fail(SC_EINVAL, "accumulate_quotients: column index out of range");
+      al = q_mul(al, alpha);
+      QM31 v = q_make(entry_vals[4 * e], entry_vals[4 * e + 1], entry_vals[4 * e + 2], entry_vals[4 * e + 3]);
+      QM31 a = q_sub(q_conj(v), v);
+      QM31 bb = q_sub(q_mul(v, c), q_mul(a, sy));
+      QM31 ac = q_mul(al, c);
+      B.suma = q_add(B.suma, q_mul(al, a));
+      B.sumb = q_add(B.sumb, q_mul(al, bb));
+      qe.push_back(QuotEntry{entry_cols[e], {ac.a.a, ac.a.b, ac.b.a, ac.b.b}});
+    }
+    B.coeff = q_pow(alpha, batch_sizes[b]);
+  }
+  uint32_t* d[4];
+  for (int k = 0; k < 4; k++) { int32_t r = new_col(ctx, 1ull << log, &out[k]); if (r) return r; d[k] = out[k]->d; }
+  if (nb == 0) {
+    for (int k = 0; k < 4; k++) CK(cudaMemsetAsync(d[k], 0, (size_t)4 << log, ctx->st));
+    return SC_OK;
+  }
+  void *dp = nullptr, *db, *de = nullptr;
+  int32_t r;
+  if (n) { r = stage(ctx, p.data(), n * sizeof(void*), &dp); if (r) return r; }
+  r = stage(ctx, qb.data(), qb.size() * sizeof(QuotBatch), &db); if (r) return r;
+  if (!qe.empty()) { r = stage(ctx, qe.data(), qe.size() * sizeof(QuotEntry), &de); if (r) return r; }
+  CKL(launch_accumulate_quotients(log, (const uint32_t* const*)dp, (const QuotBatch*)db, nb, (const QuotEntry*)de, d, ctx->st));
+  return SC_OK;
+}
+
+// ------------------------------------------------------------------ accumulation / grind / misc
+int32_t sc_accumulate(sc_ctx* ctx, sc_col* const dst[4], sc_col* const src[4]) {
+  ENTER();
+  uint32_t* d[4]; const uint32_t* s[4];
+  for (int k = 0; k < 4; k++) {
+    if (!dst[k] || !src[k] || dst[k]->len != dst[0]->len || src[k]->len != dst[0]->len) return fail(SC_EINVAL, "accumulate: bad columns");
+    d[k] = dst[k]->d; s[k] = src[k]->d;
+  }
+  CKL(launch_accumulate(d, s, dst[0]->len, ctx->st));
+  return SC_OK;
+}
+int32_t sc_secure_powers(const uint32_t felt[4], uint32_t n, uint32_t* out) {
+  if (!felt || (!out && n)) return fail(SC_EINVAL, "null argument");
+  QM31 f = q_make(felt[0], felt[1], felt[2], felt[3]), acc = q_fromm(1);
+  for (uint32_t i = 0; i < n; i++) {
+    out[4 * i] = acc.a.a; out[4 * i + 1] = acc.a.b; out[4 * i + 2] = acc.b.a; out[4 * i + 3] = acc.b.b;
+    acc = q_mul(acc, f);
+  }
+  return SC_OK;
+}
+int32_t sc_grind(sc_ctx* ctx, const uint32_t digest[8], uint32_t pow_bits, uint64_t* nonce_out) {
+  ENTER();
+  if (!digest || !nonce_out || pow_bits > 64) return fail(SC_EINVAL, "grind: bad argument");
+  unsigned long long* dres;
+  CK(cudaMallocAsync((void**)&dres, 8, ctx->st));
+  CK(cudaMemsetAsync(dres, 0xff, 8, ctx->st));
+  int e = launch_grind(digest, pow_bits, dres, ctx->st);
+  unsigned long long r = 0;
+  if (e == 0) CK(cudaMemcpyAsync(&r, dres, 8, cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  CK(cudaFreeAsync(dres, ctx->st));
+  if (e > 0) { ctx->poisoned = true; return fail(SC_ECUDA, "grind kernel failed"); }
+  if (e < 0) return fail(SC_EINVAL, "grind: no nonce found below 2^40");
+  *nonce_out = r;
+  return SC_OK;
+}
+int32_t sc_gen_is_first(sc_ctx* ctx, uint32_t log_size, sc_col** out) {
+  ENTER();
+  if (!out || log_size > 30) return fail(SC_EINVAL, "gen_is_first: bad argument");
+  int32_t r = new_col(ctx, 1ull << log_size, out);
+  if (r) return r;
+  CKL(launch_gen_is_first((*out)->d, log_size, ctx->st));
+  return SC_OK;
+}
+int32_t sc_prefix_sum_bitrev(sc_ctx* ctx, sc_col* col) {
+  ENTER();
+  if (!col || !is_pow2(col->len) || col->len < 2) return fail(SC_EINVAL, "prefix_sum: length must be a power of two >= 2");
+  uint32_t lg = ilog2(col->len);
+  uint32_t* scratch;
+  size_t words = col->len + 2 * ((col->len >> 11) + 2) + 8;
+  CK(cudaMallocAsync((void**)&scratch, words * 4, ctx->st));
+  CKL(launch_prefix_sum_bitrev(col->d, lg, scratch, ctx->st));
+  CK(cudaFreeAsync(scratch, ctx->st));
+  return SC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,51 @@
+// Internal launch interface between the C ABI (capi.cu) and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstddef>
+#include "m31.cuh"
+
+namespace sb {
+
+extern unsigned long long g_launch_count;  // kernels launched by this process (bench.py gpu_launches)
+
+// fft.cu
+int launch_twiddle_tree(uint32_t* tw, uint32_t* itw, uint32_t R, cudaStream_t st);
+int launch_interpolate(uint32_t* const* cols, uint32_t ncols, uint32_t n, const uint32_t* itw_end, cudaStream_t st);
+int launch_evaluate(const uint32_t* const* coeffs, uint32_t* const* out, uint32_t ncols, uint32_t src_log, uint32_t n,
+                    const uint32_t* tw_end, cudaStream_t st);
+
+// merkle.cu
+int launch_commit_layer(uint32_t log_size, const uint32_t* prev, const uint32_t* const* cols, uint32_t ncols,
+                        uint32_t* out, cudaStream_t st);
+int launch_grind(const uint32_t digest[8], uint32_t pow_bits, unsigned long long* d_result, cudaStream_t st);
+
+// ops.cu
+int launch_bit_reverse(uint32_t* v, uint32_t log, cudaStream_t st);
+int launch_batch_inverse_m31(const uint32_t* src, uint32_t* dst, size_t n, cudaStream_t st);
+int launch_batch_inverse_qm31(const uint32_t* const src[4], uint32_t* const dst[4], size_t n, cudaStream_t st);
+int launch_fold_line(const uint32_t* const src[4], uint32_t log, QM31 alpha, uint32_t* const dst[4], const uint32_t* itw_end,
+                     cudaStream_t st);
+int launch_fold_circle_into_line(const uint32_t* const src[4], uint32_t log, QM31 alpha, uint32_t* const dst[4],
+                                 const uint32_t* itw_end, cudaStream_t st);
+int launch_accumulate(uint32_t* const dst[4], const uint32_t* const src[4], size_t n, cudaStream_t st);
+int launch_fill(uint32_t* v, size_t n, uint32_t value, cudaStream_t st);
+int launch_gen_is_first(uint32_t* v, uint32_t log, cudaStream_t st);
+int launch_prefix_sum_bitrev(uint32_t* v, uint32_t log, uint32_t* scratch, cudaStream_t st);
+struct EvalTaskHost {  // mirrors ops.cu EvalTask
+  const uint32_t* coeffs;
+  uint32_t log;
+  uint32_t first_block;
+  QM31 f[28];
+};
+int launch_eval_at_point_tasks(const void* d_tasks, uint32_t ntasks, uint32_t total_blocks, QM31* d_partials, QM31* d_work,
+                               QM31* d_out, cudaStream_t st);
+int launch_broadcast16(const uint32_t* src, uint32_t* dst, size_t src_len, cudaStream_t st);
+
+// quotients.cu
+struct QuotEntry { uint32_t col; uint32_t c[4]; };
+struct QuotBatch { CM31 prx, pry, pix, piy; QM31 suma, sumb, coeff; uint32_t first, count; };
+int launch_accumulate_quotients(uint32_t log, const uint32_t* const* d_cols, const QuotBatch* d_batches, uint32_t nb,
+                                const QuotEntry* d_entries, uint32_t* const out[4], cudaStream_t st);
+
+}  // namespace sb

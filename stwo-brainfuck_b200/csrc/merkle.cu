@@ -1,0 +1,135 @@
+// Blake2s Merkle layer hashing and proof-of-work grinding for sm_100a.
+//
+// Replaces SimdBackend's MerkleOps<Blake2sMerkleHasher>::commit_on_layer and GrindOps<Blake2sChannel>::grind
+// (stwo-prover 0.1.1 @ 31e8dbc core/backend/simd/{blake2s.rs,grind.rs}, core/vcs/blake2_merkle.rs),
+// reached from tree_builder.commit at crates/brainfuck_prover/src/brainfuck_air/mod.rs:500,583,723 and from every FRI
+// layer commit / the grind inside prover::prove (:732).
+//
+// Node function: state = 0^8; if children: state = F(state, left||right); then F(state, 16 column words) per chunk
+// (zero padded), all counters/flags zero.  One thread per row: a warp covers 32 consecutive rows, so every column
+// load is one coalesced 128-byte line and the 32-byte digest store fills whole sectors.  The whole compression is
+// unrolled with compile-time sigma so message and state words live in registers (no local memory).
+#include "kernels.cuh"
+
+namespace sb {
+
+__device__ __forceinline__ uint32_t rotr16(uint32_t x) { return __byte_perm(x, x, 0x1032); }
+__device__ __forceinline__ uint32_t rotr8(uint32_t x) { return __byte_perm(x, x, 0x0321); }
+__device__ __forceinline__ uint32_t rotr12(uint32_t x) { return __funnelshift_r(x, x, 12); }
+__device__ __forceinline__ uint32_t rotr7(uint32_t x) { return __funnelshift_r(x, x, 7); }
+
+#define B2S_G(a, b, c, d, x, y)      \
+  do {                               \
+    a = a + b + (x);                 \
+    d = rotr16(d ^ a);               \
+    c = c + d;                       \
+    b = rotr12(b ^ c);               \
+    a = a + b + (y);                 \
+    d = rotr8(d ^ a);                \
+    c = c + d;                       \
+    b = rotr7(b ^ c);                \
+  } while (0)
+
+#define B2S_ROUND(s0, s1, s2, s3, s4, s5, s6, s7, s8, s9, s10, s11, s12, s13, s14, s15) \
+  B2S_G(v0, v4, v8, v12, m[s0], m[s1]);                                                  \
+  B2S_G(v1, v5, v9, v13, m[s2], m[s3]);                                                  \
+  B2S_G(v2, v6, v10, v14, m[s4], m[s5]);                                                 \
+  B2S_G(v3, v7, v11, v15, m[s6], m[s7]);                                                 \
+  B2S_G(v0, v5, v10, v15, m[s8], m[s9]);                                                 \
+  B2S_G(v1, v6, v11, v12, m[s10], m[s11]);                                               \
+  B2S_G(v2, v7, v8, v13, m[s12], m[s13]);                                                \
+  B2S_G(v3, v4, v9, v14, m[s14], m[s15]);
+
+// h <- F(h, m, 0, 0, 0, 0)
+__device__ __forceinline__ void b2s_compress(uint32_t h[8], const uint32_t m[16]) {
+  uint32_t v0 = h[0], v1 = h[1], v2 = h[2], v3 = h[3], v4 = h[4], v5 = h[5], v6 = h[6], v7 = h[7];
+  uint32_t v8 = 0x6A09E667u, v9 = 0xBB67AE85u, v10 = 0x3C6EF372u, v11 = 0xA54FF53Au;
+  uint32_t v12 = 0x510E527Fu, v13 = 0x9B05688Cu, v14 = 0x1F83D9ABu, v15 = 0x5BE0CD19u;
+  B2S_ROUND(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15)
+  B2S_ROUND(14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3)
+  B2S_ROUND(11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4)
+  B2S_ROUND(7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8)
+  B2S_ROUND(9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13)
+  B2S_ROUND(2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9)
+  B2S_ROUND(12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11)
+  B2S_ROUND(13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10)
+  B2S_ROUND(6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5)
+  B2S_ROUND(10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0)
+  h[0] ^= v0 ^ v8;  h[1] ^= v1 ^ v9;  h[2] ^= v2 ^ v10; h[3] ^= v3 ^ v11;
+  h[4] ^= v4 ^ v12; h[5] ^= v5 ^ v13; h[6] ^= v6 ^ v14; h[7] ^= v7 ^ v15;
+}
+
+template <bool HAS_PREV>
+__global__ void __launch_bounds__(256) commit_layer_kernel(uint32_t rows, const uint32_t* __restrict__ prev,
+                                                           const uint32_t* const* __restrict__ cols, uint32_t ncols,
+                                                           uint32_t* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  uint32_t h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint32_t m[16];
+  if (HAS_PREV) {
+    const uint4* pc = reinterpret_cast<const uint4*>(prev) + (size_t)i * 4;
+    uint4 a = __ldg(pc), b = __ldg(pc + 1), c = __ldg(pc + 2), d = __ldg(pc + 3);
+    m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w; m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
+    m[8] = c.x; m[9] = c.y; m[10] = c.z; m[11] = c.w; m[12] = d.x; m[13] = d.y; m[14] = d.z; m[15] = d.w;
+    b2s_compress(h, m);
+  }
+  for (uint32_t c0 = 0; c0 < ncols; c0 += 16) {
+#pragma unroll
+    for (uint32_t j = 0; j < 16; j++) m[j] = (c0 + j < ncols) ? __ldg(cols[c0 + j] + i) : 0u;
+    b2s_compress(h, m);
+  }
+  uint4* o = reinterpret_cast<uint4*>(out) + (size_t)i * 2;
+  o[0] = make_uint4(h[0], h[1], h[2], h[3]);
+  o[1] = make_uint4(h[4], h[5], h[6], h[7]);
+}
+
+int launch_commit_layer(uint32_t log_size, const uint32_t* prev, const uint32_t* const* cols, uint32_t ncols,
+                        uint32_t* out, cudaStream_t st) {
+  uint32_t rows = 1u << log_size;
+  uint32_t threads = rows < 256 ? (rows < 32 ? 32 : rows) : 256;
+  uint32_t blocks = (rows + threads - 1) / threads;
+  if (prev) commit_layer_kernel<true><<<blocks, threads, 0, st>>>(rows, prev, cols, ncols, out);
+  else commit_layer_kernel<false><<<blocks, threads, 0, st>>>(rows, prev, cols, ncols, out);
+  g_launch_count++;
+  return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- grind
+// Smallest nonce with trailing_zeros(F(digest, [nonce_lo, nonce_hi, 0...])) >= pow_bits (first 128 bits, LE).
+__global__ void grind_kernel(uint32_t d0, uint32_t d1, uint32_t d2, uint32_t d3, uint32_t d4, uint32_t d5, uint32_t d6,
+                             uint32_t d7, uint32_t pow_bits, unsigned long long base, unsigned long long* result) {
+  unsigned long long nonce = base + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t h[8] = {d0, d1, d2, d3, d4, d5, d6, d7};
+  uint32_t m[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  m[0] = (uint32_t)nonce; m[1] = (uint32_t)(nonce >> 32);
+  b2s_compress(h, m);
+  uint32_t tz;
+  if (h[0]) tz = __ffs(h[0]) - 1;
+  else if (h[1]) tz = 32 + __ffs(h[1]) - 1;
+  else if (h[2]) tz = 64 + __ffs(h[2]) - 1;
+  else if (h[3]) tz = 96 + __ffs(h[3]) - 1;
+  else tz = 128;
+  if (tz >= pow_bits) atomicMin(result, nonce);
+}
+
+// Searches [0, 2^40) in batches; *d_result must be initialised to ~0ull by the caller; returns after the first
+// batch that produced a hit (batches are scanned in increasing order, atomicMin keeps the smallest nonce).
+int launch_grind(const uint32_t digest[8], uint32_t pow_bits, unsigned long long* d_result, cudaStream_t st) {
+  const unsigned long long batch = 1ull << 22;
+  for (unsigned long long base = 0; base < (1ull << 40); base += batch) {
+    grind_kernel<<<(unsigned)(batch / 256), 256, 0, st>>>(digest[0], digest[1], digest[2], digest[3], digest[4], digest[5],
+                                                          digest[6], digest[7], pow_bits, base, d_result); g_launch_count++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    unsigned long long r;
+    e = cudaMemcpyAsync(&r, d_result, 8, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return (int)e;
+    if (r != ~0ull) return 0;
+  }
+  return -2;
+}
+
+}  // namespace sb

@@ -1,0 +1,338 @@
+// Row-local Backend ops for sm_100a: ColumnOps::bit_reverse_column, FieldOps::batch_inverse, FriOps::{fold_line,
+// fold_circle_into_line}, AccumulationOps::accumulate, gen_is_first, the LogUp coset-order prefix sum and
+// PolyOps::eval_at_point.  Definitions: stwo-prover 0.1.1 @ 31e8dbc core/backend/{cpu,simd}/{fri,accumulation,
+// bit_reverse,prefix_sum,circle}.rs; all are reached from prover::prove at
+// crates/brainfuck_prover/src/brainfuck_air/mod.rs:732 or from interaction_trace_evaluation (e.g.
+// crates/brainfuck_prover/src/components/processor/table.rs:456-533).
+// Every kernel here is HBM-bound: one coalesced read and one coalesced write per element, grid = multiple of 148 SMs.
+#include "kernels.cuh"
+
+namespace sb {
+
+static inline unsigned grid_for(size_t n, unsigned threads, unsigned per_thread = 1) {
+  size_t b = (n + (size_t)threads * per_thread - 1) / ((size_t)threads * per_thread);
+  size_t cap = 148u * 16u;
+  return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// ---------------------------------------------------------------- bit reverse (in place), 32x32 tiles through smem
+// Index = hi(5) | mid | lo(5): swap with rev(lo) | rev(mid) | rev(hi).  A CTA owns the pair of mid values (mid, rev(mid))
+// and moves both 32x32 tiles through shared memory so that global reads and writes are 128-byte rows.
+__global__ void bit_reverse_tiled_kernel(uint32_t* __restrict__ v, uint32_t log) {
+  __shared__ uint32_t ta[32][33], tb[32][33];
+  const uint32_t mlog = log - 10;
+  const uint32_t nmid = 1u << mlog;
+  const uint32_t tx = threadIdx.x & 31u, ty = threadIdx.x >> 5;  // 32 x 8
+  for (uint32_t mid = blockIdx.x; mid < nmid; mid += gridDim.x) {
+    uint32_t rmid = mlog ? (__brev(mid) >> (32 - mlog)) : 0;
+    if (rmid < mid) continue;
+    // tile(mid)[hi][lo] = v[hi<<(log-5) | mid<<5 | lo]
+    for (uint32_t r = ty; r < 32; r += 8) {
+      ta[r][tx] = v[((size_t)r << (log - 5)) | (mid << 5) | tx];
+      if (rmid != mid) tb[r][tx] = v[((size_t)r << (log - 5)) | (rmid << 5) | tx];
+    }
+    __syncthreads();
+    // element (hi,lo) of tile(mid) goes to index rev5(lo)<<(log-5) | rmid<<5 | rev5(hi): row rev5(lo) of tile(rmid), col rev5(hi)
+    for (uint32_t r = ty; r < 32; r += 8) {
+      uint32_t rr = __brev(r) >> 27, rc = __brev(tx) >> 27;
+      // write row r of tile(rmid): column tx takes source (hi = rev5(tx), lo = rev5(r)) of tile(mid)
+      v[((size_t)r << (log - 5)) | (rmid << 5) | tx] = ta[rc][rr];
+      if (rmid != mid) v[((size_t)r << (log - 5)) | (mid << 5) | tx] = tb[rc][rr];
+    }
+    __syncthreads();
+  }
+}
+__global__ void bit_reverse_small_kernel(uint32_t* __restrict__ v, uint32_t log) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (1u << log)) return;
+  uint32_t j = bitrev32(i, log);
+  if (i < j) { uint32_t a = v[i], b = v[j]; v[i] = b; v[j] = a; }
+}
+int launch_bit_reverse(uint32_t* v, uint32_t log, cudaStream_t st) {
+  if (log >= 10) {
+    uint32_t nmid = 1u << (log - 10);
+    bit_reverse_tiled_kernel<<<nmid < 148u * 8 ? nmid : 148u * 8, 256, 0, st>>>(v, log); g_launch_count++;
+  } else {
+    uint32_t n = 1u << log;
+    bit_reverse_small_kernel<<<(n + 255) / 256, 256, 0, st>>>(v, log); g_launch_count++;
+  }
+  return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- batch inverse (Fermat per lane; ALU is free next to HBM)
+__global__ void inv_m31_kernel(const uint32_t* __restrict__ s, uint32_t* __restrict__ d, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) d[i] = m_inv(s[i]);
+}
+struct Ptr4 { uint32_t* p[4]; };
+struct CPtr4 { const uint32_t* p[4]; };
+__global__ void inv_qm31_kernel(CPtr4 s, Ptr4 d, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    QM31 r = q_inv(q_make(s.p[0][i], s.p[1][i], s.p[2][i], s.p[3][i]));
+    d.p[0][i] = r.a.a; d.p[1][i] = r.a.b; d.p[2][i] = r.b.a; d.p[3][i] = r.b.b;
+  }
+}
+int launch_batch_inverse_m31(const uint32_t* src, uint32_t* dst, size_t n, cudaStream_t st) {
+  inv_m31_kernel<<<grid_for(n, 256), 256, 0, st>>>(src, dst, n); g_launch_count++;
+  return (int)cudaGetLastError();
+}
+int launch_batch_inverse_qm31(const uint32_t* const src[4], uint32_t* const dst[4], size_t n, cudaStream_t st) {
+  CPtr4 s{{src[0], src[1], src[2], src[3]}};
+  Ptr4 d{{dst[0], dst[1], dst[2], dst[3]}};
+  inv_qm31_kernel<<<grid_for(n, 256), 256, 0, st>>>(s, d, n); g_launch_count++;
+  return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- FRI folds
+// fold_line: out[i] = (e[2i]+e[2i+1]) + alpha * (e[2i]-e[2i+1]) / x_i ; 1/x_i = itw level of coset log `log`, index i.
+__global__ void fold_line_kernel(CPtr4 s, Ptr4 d, uint32_t log, QM31 alpha, const uint32_t* __restrict__ itw_end) {
+  const size_t half = (size_t)1 << (log - 1);
+  const uint32_t* itw = itw_end - ((size_t)1 << log);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += (size_t)gridDim.x * blockDim.x) {
+    uint2 c0 = reinterpret_cast<const uint2*>(s.p[0])[i], c1 = reinterpret_cast<const uint2*>(s.p[1])[i];
+    uint2 c2 = reinterpret_cast<const uint2*>(s.p[2])[i], c3 = reinterpret_cast<const uint2*>(s.p[3])[i];
+    QM31 a = q_make(c0.x, c1.x, c2.x, c3.x), b = q_make(c0.y, c1.y, c2.y, c3.y);
+    QM31 f0 = q_add(a, b), f1 = q_mulm(q_sub(a, b), __ldg(itw + i));
+    QM31 r = q_add(f0, q_mul(alpha, f1));
+    d.p[0][i] = r.a.a; d.p[1][i] = r.a.b; d.p[2][i] = r.b.a; d.p[3][i] = r.b.b;
+  }
+}
+int launch_fold_line(const uint32_t* const src[4], uint32_t log, QM31 alpha, uint32_t* const dst[4], const uint32_t* itw_end,
+                     cudaStream_t st) {
+  if (log < 1) return -1;
+  CPtr4 s{{src[0], src[1], src[2], src[3]}};
+  Ptr4 d{{dst[0], dst[1], dst[2], dst[3]}};
+  fold_line_kernel<<<grid_for((size_t)1 << (log - 1), 256), 256, 0, st>>>(s, d, log, alpha, itw_end); g_launch_count++;
+  return (int)cudaGetLastError();
+}
+
+// fold_circle_into_line: dst[i] = dst[i]*alpha^2 + (f0 + alpha*f1), (f0,f1) = ibutterfly(src[2i], src[2i+1], 1/p_i.y);
+// 1/p_i.y is the inverse circle-layer twiddle of the size-`log` FFT: from itw line layer 1, [x,y] -> [y,-y,-x,x].
+__global__ void fold_circle_kernel(CPtr4 s, Ptr4 d, uint32_t log, QM31 alpha, QM31 alpha_sq, const uint32_t* __restrict__ itw_end) {
+  const size_t half = (size_t)1 << (log - 1);
+  const uint32_t* l1 = itw_end - ((size_t)1 << (log - 1));
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += (size_t)gridDim.x * blockDim.x) {
+    size_t pair = (i >> 2) * 2;
+    uint32_t x = __ldg(l1 + pair), y = __ldg(l1 + pair + 1);
+    uint32_t sel = (uint32_t)i & 3u;
+    uint32_t t = sel < 2 ? y : x;
+    if (sel == 1 || sel == 2) t = P - t;
+    uint2 c0 = reinterpret_cast<const uint2*>(s.p[0])[i], c1 = reinterpret_cast<const uint2*>(s.p[1])[i];
+    uint2 c2 = reinterpret_cast<const uint2*>(s.p[2])[i], c3 = reinterpret_cast<const uint2*>(s.p[3])[i];
+    QM31 a = q_make(c0.x, c1.x, c2.x, c3.x), b = q_make(c0.y, c1.y, c2.y, c3.y);
+    QM31 f0 = q_add(a, b), f1 = q_mulm(q_sub(a, b), t);
+    QM31 acc = q_make(d.p[0][i], d.p[1][i], d.p[2][i], d.p[3][i]);
+    QM31 r = q_add(q_mul(acc, alpha_sq), q_add(f0, q_mul(alpha, f1)));
+    d.p[0][i] = r.a.a; d.p[1][i] = r.a.b; d.p[2][i] = r.b.a; d.p[3][i] = r.b.b;
+  }
+}
+int launch_fold_circle_into_line(const uint32_t* const src[4], uint32_t log, QM31 alpha, uint32_t* const dst[4],
+                                 const uint32_t* itw_end, cudaStream_t st) {
+  if (log < 3) return -1;
+  CPtr4 s{{src[0], src[1], src[2], src[3]}};
+  Ptr4 d{{dst[0], dst[1], dst[2], dst[3]}};
+  fold_circle_kernel<<<grid_for((size_t)1 << (log - 1), 256), 256, 0, st>>>(s, d, log, alpha, q_mul(alpha, alpha), itw_end); g_launch_count++;
+  return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- accumulate / fill / is_first
+__global__ void accumulate_kernel(Ptr4 d, CPtr4 s, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      uint4 a = reinterpret_cast<uint4*>(d.p[k])[i], b = reinterpret_cast<const uint4*>(s.p[k])[i];
+      a.x = m_add(a.x, b.x); a.y = m_add(a.y, b.y); a.z = m_add(a.z, b.z); a.w = m_add(a.w, b.w);
+      reinterpret_cast<uint4*>(d.p[k])[i] = a;
+    }
+  }
+}
+int launch_accumulate(uint32_t* const dst[4], const uint32_t* const src[4], size_t n, cudaStream_t st) {
+  if (n % 4) return -1;
+  Ptr4 d{{dst[0], dst[1], dst[2], dst[3]}};
+  CPtr4 s{{src[0], src[1], src[2], src[3]}};
+  accumulate_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(d, s, n / 4); g_launch_count++;
+  return (int)cudaGetLastError();
+}
+__global__ void fill_kernel(uint32_t* __restrict__ v, size_t n, uint32_t value, uint32_t first) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    v[i] = i == 0 ? first : value;
+}
+int launch_fill(uint32_t* v, size_t n, uint32_t value, cudaStream_t st) {
+  fill_kernel<<<grid_for(n, 256), 256, 0, st>>>(v, n, value, value); g_launch_count++;
+  return (int)cudaGetLastError();
+}
+int launch_gen_is_first(uint32_t* v, uint32_t log, cudaStream_t st) {
+  fill_kernel<<<grid_for((size_t)1 << log, 256), 256, 0, st>>>(v, (size_t)1 << log, 0u, 1u); g_launch_count++;
+  return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- LogUp prefix sum in trace-coset order
+// Storage index s <-> coset index i:  s = 2*brev(m) -> i = 2m ;  s = 2*brev(m)+1 -> i = 2^log - 1 - 2m   (m < 2^(log-1)).
+__device__ __forceinline__ uint32_t coset_to_storage(uint32_t i, uint32_t log) {
+  uint32_t m = (i & 1u) ? (((1u << log) - 1u - i) >> 1) : (i >> 1);
+  uint32_t r = (log > 1) ? (__brev(m) >> (33 - log)) : 0;
+  return 2u * r + (i & 1u);
+}
+constexpr uint32_t SCAN_CHUNK_LOG = 11;  // 256 threads x 8 elements
+
+__device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long long x, unsigned long long* total) {
+  __shared__ unsigned long long wsum[8];
+  const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  unsigned long long inc = x;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned long long y = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= (uint32_t)o) inc += y;
+  }
+  if (lane == 31) wsum[w] = inc;
+  __syncthreads();
+  unsigned long long base = 0, tot = 0;
+#pragma unroll
+  for (uint32_t k = 0; k < 8; k++) { if (k < w) base += wsum[k]; tot += wsum[k]; }
+  __syncthreads();
+  *total = tot;
+  return base + inc - x;
+}
+
+__global__ void __launch_bounds__(256) scan_gather_kernel(const uint32_t* __restrict__ v, uint32_t log, uint32_t* __restrict__ nat,
+                                                          unsigned long long* __restrict__ chunk_sums) {
+  const uint32_t n = 1u << log;
+  const uint32_t base = blockIdx.x << SCAN_CHUNK_LOG;
+  unsigned long long s = 0;
+#pragma unroll
+  for (uint32_t k = 0; k < 8; k++) {
+    uint32_t i = base + k * 256 + threadIdx.x;
+    if (i < n) { uint32_t x = v[coset_to_storage(i, log)]; nat[i] = x; s += x; }
+  }
+  unsigned long long tot;
+  block_exclusive_scan(s, &tot);
+  if (threadIdx.x == 0) chunk_sums[blockIdx.x] = tot % P;
+}
+__global__ void __launch_bounds__(256) scan_chunks_kernel(unsigned long long* __restrict__ chunk_sums, uint32_t nchunks) {
+  // single CTA: exclusive scan (mod P) of the chunk sums, sequential over 256-wide slabs
+  unsigned long long carry = 0;
+  for (uint32_t b = 0; b < nchunks; b += 256) {
+    uint32_t i = b + threadIdx.x;
+    unsigned long long x = i < nchunks ? chunk_sums[i] : 0, tot;
+    unsigned long long ex = block_exclusive_scan(x, &tot);
+    if (i < nchunks) chunk_sums[i] = (carry + ex) % P;
+    carry = (carry + tot) % P;
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(256) scan_scatter_kernel(uint32_t* __restrict__ v, uint32_t log, const uint32_t* __restrict__ nat,
+                                                           const unsigned long long* __restrict__ chunk_sums) {
+  const uint32_t n = 1u << log;
+  const uint32_t base = (blockIdx.x << SCAN_CHUNK_LOG) + threadIdx.x * 8;  // 8 consecutive coset rows per thread
+  unsigned long long x[8], s = 0;
+#pragma unroll
+  for (uint32_t k = 0; k < 8; k++) { x[k] = (base + k < n) ? nat[base + k] : 0; s += x[k]; }
+  unsigned long long tot;
+  unsigned long long run = block_exclusive_scan(s, &tot) + chunk_sums[blockIdx.x];
+#pragma unroll
+  for (uint32_t k = 0; k < 8; k++) {
+    run += x[k];
+    if (base + k < n) v[coset_to_storage(base + k, log)] = (uint32_t)(run % P);
+  }
+}
+// scratch: 2^log words for the natural-order copy + (2^log >> 11) + 1 u64 chunk sums (8-byte aligned, placed first).
+int launch_prefix_sum_bitrev(uint32_t* v, uint32_t log, uint32_t* scratch, cudaStream_t st) {
+  uint32_t n = 1u << log;
+  uint32_t nchunks = (n + (1u << SCAN_CHUNK_LOG) - 1) >> SCAN_CHUNK_LOG;
+  unsigned long long* sums = reinterpret_cast<unsigned long long*>(scratch);
+  uint32_t* nat = scratch + 2 * (size_t)((nchunks + 1) & ~1u) + 2;
+  scan_gather_kernel<<<nchunks, 256, 0, st>>>(v, log, nat, sums); g_launch_count++;
+  scan_chunks_kernel<<<1, 256, 0, st>>>(sums, nchunks); g_launch_count++;
+  scan_scatter_kernel<<<nchunks, 256, 0, st>>>(v, log, nat, sums); g_launch_count++;
+  return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- eval_at_point
+// value = sum_i c_i * prod_k f_k^{bit_k(i)},  f = [p.y, p.x, pi(p.x), pi^2(p.x), ...]   (CpuBackend fold()).
+// Stage 1: a CTA folds 2^11 base-field coefficients with f_0..f_10 -> one QM31 partial.  Stage 2: one CTA per task folds
+// the partials with the remaining factors.
+typedef EvalTaskHost EvalTask;  // {coeffs, log, first_block (prefix of stage-1 blocks), f[28]}
+constexpr uint32_t EV_CHUNK_LOG = 11;
+
+__global__ void __launch_bounds__(256) eval_stage1_kernel(const EvalTask* __restrict__ tasks, uint32_t ntasks, QM31* __restrict__ partials) {
+  // locate task by binary search over first_block
+  uint32_t lo = 0, hi = ntasks - 1;
+  while (lo < hi) { uint32_t mid = (lo + hi + 1) >> 1; if (tasks[mid].first_block <= blockIdx.x) lo = mid; else hi = mid - 1; }
+  const EvalTask& t = tasks[lo];
+  const uint32_t chunk = blockIdx.x - t.first_block;
+  const uint32_t clog = t.log < EV_CHUNK_LOG ? t.log : EV_CHUNK_LOG;
+  const uint32_t n = 1u << clog;
+  const uint32_t* c = t.coeffs + ((size_t)chunk << EV_CHUNK_LOG);
+  __shared__ QM31 sm[256];
+  // thread folds 8 consecutive coefficients (levels 0..2)
+  uint32_t i0 = threadIdx.x * 8;
+  QM31 acc = q_zero();
+  if (i0 < n) {
+    uint32_t x[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = (i0 + k < n) ? __ldg(c + i0 + k) : 0;
+    QM31 a0 = q_add(q_fromm(x[0]), q_mulm(t.f[0], x[1])), a1 = q_add(q_fromm(x[2]), q_mulm(t.f[0], x[3]));
+    QM31 a2 = q_add(q_fromm(x[4]), q_mulm(t.f[0], x[5])), a3 = q_add(q_fromm(x[6]), q_mulm(t.f[0], x[7]));
+    QM31 b0 = a0, b1 = a2;
+    if (clog > 1) { b0 = q_add(a0, q_mul(a1, t.f[1])); b1 = q_add(a2, q_mul(a3, t.f[1])); }
+    acc = b0;
+    if (clog > 2) acc = q_add(b0, q_mul(b1, t.f[2]));
+  }
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  // levels 3..clog-1 over the 2^(clog-3) thread partials
+  for (uint32_t lvl = 3; lvl < clog; lvl++) {
+    uint32_t cnt = 1u << (clog - lvl - 1);
+    QM31 r = q_zero();
+    if (threadIdx.x < cnt) r = q_add(sm[2 * threadIdx.x], q_mul(sm[2 * threadIdx.x + 1], t.f[lvl]));
+    __syncthreads();
+    if (threadIdx.x < cnt) sm[threadIdx.x] = r;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partials[blockIdx.x] = sm[0];
+}
+__global__ void __launch_bounds__(256) eval_stage2_kernel(const EvalTask* __restrict__ tasks, const QM31* __restrict__ partials,
+                                                          QM31* __restrict__ out, QM31* __restrict__ work) {
+  const EvalTask& t = tasks[blockIdx.x];
+  if (t.log <= EV_CHUNK_LOG) { if (threadIdx.x == 0) out[blockIdx.x] = partials[t.first_block]; return; }
+  const uint32_t levels = t.log - EV_CHUNK_LOG;
+  QM31* w = work + t.first_block;  // in-place tree over this task's partials (copied first)
+  uint32_t cnt = 1u << levels;
+  for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) w[i] = partials[t.first_block + i];
+  __syncthreads();
+  for (uint32_t lvl = 0; lvl < levels; lvl++) {
+    uint32_t half = cnt >> 1;
+    // read pairs, sync, write — strided so no in-place hazard: out index i < 2i
+    for (uint32_t base = 0; base < half; base += blockDim.x) {
+      uint32_t i = base + threadIdx.x;
+      QM31 r = q_zero();
+      if (i < half) r = q_add(w[2 * i], q_mul(w[2 * i + 1], t.f[EV_CHUNK_LOG + lvl]));
+      __syncthreads();
+      if (i < half) w[i] = r;
+      __syncthreads();
+    }
+    cnt = half;
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = w[0];
+}
+
+int launch_eval_at_point_tasks(const void* d_tasks, uint32_t ntasks, uint32_t total_blocks, QM31* d_partials, QM31* d_work,
+                               QM31* d_out, cudaStream_t st) {
+  if (!ntasks) return 0;
+  eval_stage1_kernel<<<total_blocks, 256, 0, st>>>(reinterpret_cast<const EvalTask*>(d_tasks), ntasks, d_partials); g_launch_count++;
+  eval_stage2_kernel<<<ntasks, 256, 0, st>>>(reinterpret_cast<const EvalTask*>(d_tasks), d_partials, d_out, d_work); g_launch_count++;
+  return (int)cudaGetLastError();
+}
+
+// 16x lane broadcast of a trace column (reference: PackedBaseField::broadcast in every table.rs trace_evaluation).
+__global__ void broadcast16_kernel(const uint32_t* __restrict__ s, uint4* __restrict__ d, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * 4; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t x = __ldg(s + (i >> 2));
+    d[i] = make_uint4(x, x, x, x);
+  }
+}
+int launch_broadcast16(const uint32_t* src, uint32_t* dst, size_t src_len, cudaStream_t st) {
+  broadcast16_kernel<<<grid_for(src_len * 4, 256), 256, 0, st>>>(src, reinterpret_cast<uint4*>(dst), src_len); g_launch_count++;
+  return (int)cudaGetLastError();
+}
+
+}  // namespace sb

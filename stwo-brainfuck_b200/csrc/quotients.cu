@@ -1,0 +1,119 @@
+// DEEP quotient accumulation for sm_100a.
+//
+// Replaces QuotientOps::accumulate_quotients (stwo-prover 0.1.1 @ 31e8dbc core/backend/{cpu,simd}/quotients.rs with the
+// helpers of core/pcs/quotients.rs), reached from compute_fri_quotients inside prover::prove at
+// crates/brainfuck_prover/src/brainfuck_air/mod.rs:732.
+//
+// Per row with domain point (px,py), for each sample batch (point S, entries j):
+//   numerator   = sum_j alpha^(j+1) * (c*col_j(row) - (a_j*py + b_j)),   (a,b,c) = (conj(v)-v, v*c - a*S.y, conj(S.y)-S.y)
+//   denominator = (Re(S.x)-px)*Im(S.y) - (Re(S.y)-py)*Im(S.x)    in CM31
+//   acc = acc * alpha^len(batch) + numerator / denominator
+// SimdBackend evaluates on a sub-domain and re-extends; the result is the same function on the same domain, so the
+// kernel evaluates directly.  HBM-bound: every column word is read once (128-bit loads, 4 consecutive rows per thread),
+// 16 bytes per row are written.  Four consecutive bit-reversed rows are (x,y),(x,-y),(-x,-y),(-x,y): one point per thread.
+// The numerator is split as sum_j C_j*col_j - (py*A + B) with A = sum a_j, B = sum b_j folded on the host, and the
+// sum of products is carried in 64-bit lanes with one partial reduction every two terms.
+#include "kernels.cuh"
+
+namespace sb {
+
+__constant__ Pt c_qgen_pow[31];
+
+__device__ __forceinline__ Pt q_point_at_index(uint32_t idx) {
+  Pt r = {1u, 0u};
+#pragma unroll 1
+  for (int k = 0; k < 31; k++)
+    if ((idx >> k) & 1u) r = p_add(r, c_qgen_pow[k]);
+  return r;
+}
+
+__device__ __forceinline__ uint64_t fold64(uint64_t v) { return (v >> 31) + (v & P); }
+__device__ __forceinline__ uint32_t red64(uint64_t v) {  // full reduction of any 64-bit value
+  v = (v >> 31) + (v & P);  // < 2^34
+  v = (v >> 31) + (v & P);  // < 2^31 + 8
+  uint32_t s = (uint32_t)v;
+  return s >= P ? s - P : s;
+}
+
+__global__ void __launch_bounds__(128) quotients_kernel(uint32_t log, const uint32_t* const* __restrict__ cols,
+                                                        const QuotBatch* __restrict__ batches, uint32_t nb,
+                                                        const QuotEntry* __restrict__ entries, uint32_t* o0, uint32_t* o1,
+                                                        uint32_t* o2, uint32_t* o3) {
+  const uint32_t nq = 1u << (log - 2);
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < nq; k += gridDim.x * blockDim.x) {
+    // base point: half_odds(log-1).at(bitrev(k, log-2)): index 2^(30-log) + j0 * 2^(32-log)
+    uint32_t j0 = (log > 2) ? (__brev(k) >> (34 - log)) : 0;
+    uint32_t idx = ((1u << (30 - log)) + (uint32_t)(((uint64_t)j0 << (32 - log)) & 0x7fffffffu)) & 0x7fffffffu;
+    Pt bp = q_point_at_index(idx);
+    const uint32_t px[4] = {bp.x, bp.x, m_neg(bp.x), m_neg(bp.x)};
+    const uint32_t py[4] = {bp.y, m_neg(bp.y), m_neg(bp.y), bp.y};
+    QM31 acc[4] = {q_zero(), q_zero(), q_zero(), q_zero()};
+    for (uint32_t b = 0; b < nb; b++) {
+      const QuotBatch qb = batches[b];
+      // denominators for the 4 rows, batch-inverted (CM31)
+      CM31 den[4], pre[4];
+      CM31 run = {1u, 0u};
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        CM31 dx = c_sub(qb.prx, CM31{px[r], 0u}), dy = c_sub(qb.pry, CM31{py[r], 0u});
+        den[r] = c_sub(c_mul(dx, qb.piy), c_mul(dy, qb.pix));
+        pre[r] = run;
+        run = c_mul(run, den[r]);
+      }
+      CM31 inv = c_inv(run);
+      CM31 dinv[4];
+#pragma unroll
+      for (int r = 3; r >= 0; r--) { dinv[r] = c_mul(inv, pre[r]); inv = c_mul(inv, den[r]); }
+      // sum_j C_j * col_j(row): 64-bit lanes
+      uint64_t s[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; r++) { s[r][0] = s[r][1] = s[r][2] = s[r][3] = 0; }
+      for (uint32_t e = qb.first; e < qb.first + qb.count; e++) {
+        const QuotEntry en = entries[e];
+        uint4 v = __ldg(reinterpret_cast<const uint4*>(cols[en.col]) + k);
+        const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+          s[r][0] += (uint64_t)en.c[0] * vv[r]; s[r][1] += (uint64_t)en.c[1] * vv[r];
+          s[r][2] += (uint64_t)en.c[2] * vv[r]; s[r][3] += (uint64_t)en.c[3] * vv[r];
+        }
+        if ((e - qb.first) & 1u) {
+#pragma unroll
+          for (int r = 0; r < 4; r++) { s[r][0] = fold64(s[r][0]); s[r][1] = fold64(s[r][1]); s[r][2] = fold64(s[r][2]); s[r][3] = fold64(s[r][3]); }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        QM31 num = q_make(red64(s[r][0]), red64(s[r][1]), red64(s[r][2]), red64(s[r][3]));
+        QM31 lin = q_add(q_mulm(qb.suma, py[r]), qb.sumb);
+        num = q_sub(num, lin);
+        acc[r] = q_add(q_mul(acc[r], qb.coeff), q_mulc(num, dinv[r]));
+      }
+    }
+    reinterpret_cast<uint4*>(o0)[k] = make_uint4(acc[0].a.a, acc[1].a.a, acc[2].a.a, acc[3].a.a);
+    reinterpret_cast<uint4*>(o1)[k] = make_uint4(acc[0].a.b, acc[1].a.b, acc[2].a.b, acc[3].a.b);
+    reinterpret_cast<uint4*>(o2)[k] = make_uint4(acc[0].b.a, acc[1].b.a, acc[2].b.a, acc[3].b.a);
+    reinterpret_cast<uint4*>(o3)[k] = make_uint4(acc[0].b.b, acc[1].b.b, acc[2].b.b, acc[3].b.b);
+  }
+}
+
+int launch_accumulate_quotients(uint32_t log, const uint32_t* const* d_cols, const QuotBatch* d_batches, uint32_t nb,
+                                const QuotEntry* d_entries, uint32_t* const out[4], cudaStream_t st) {
+  static bool init = false;
+  if (!init) {
+    Pt g[31];
+    g[0] = {GEN_X, GEN_Y};
+    for (int k = 1; k < 31; k++) g[k] = p_dbl(g[k - 1]);
+    cudaError_t e = cudaMemcpyToSymbol(c_qgen_pow, g, sizeof(g));
+    if (e != cudaSuccess) return (int)e;
+    init = true;
+  }
+  if (log < 2 || log > 30) return -1;
+  uint32_t nq = 1u << (log - 2);
+  uint32_t blocks = (nq + 127) / 128;
+  if (blocks > 148u * 16u) blocks = 148u * 16u;
+  quotients_kernel<<<blocks, 128, 0, st>>>(log, d_cols, d_batches, nb, d_entries, out[0], out[1], out[2], out[3]); g_launch_count++;
+  return (int)cudaGetLastError();
+}
+
+}  // namespace sb

@@ -1,0 +1,32 @@
+"""The C-ABI library loads and exports every symbol include/stwo_cuda.h declares (no compute calls: no GPU here)."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_exported(pkg):
+    hdr = open(os.path.join(ROOT, "include", "stwo_cuda.h")).read()
+    declared = set(re.findall(r"\b(sc_[a-z0-9_]+)\s*\(", hdr))
+    lib = pkg.load_library()
+    for sym in sorted(declared):
+        assert hasattr(lib, sym), f"{sym} declared in stwo_cuda.h but not exported"
+    assert declared <= set(pkg.ABI_SYMBOLS) | {"sc_status"}
+
+
+def test_no_cpu_fallback(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(pkg.BackendError):
+        pkg.CudaBackend(0)
+
+
+def test_product_does_not_import_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "stwo-brainfuck_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cc")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "liborc" not in src and "oracle/" not in src and "orc_" not in src, f

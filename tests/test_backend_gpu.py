@@ -1,0 +1,211 @@
+"""GPU parity: every Backend op through the C ABI vs the CPU oracle on the same seeded inputs (bit-exact)."""
+import numpy as np
+import pytest
+
+from oracle_lib import P
+
+pytestmark = pytest.mark.gpu
+ROOT_LOG = 20
+
+
+@pytest.fixture(scope="module")
+def tw(be):
+    return be.precompute_twiddles(ROOT_LOG)
+
+
+def rnd(seed, n):
+    return np.random.default_rng(seed).integers(0, P, size=n, dtype=np.uint32)
+
+
+def test_twiddles_match_oracle(be, orc, tw):
+    g_tw, g_itw = tw.to_cpu()
+    o_tw, o_itw = orc.twiddles(ROOT_LOG)
+    assert (g_tw == o_tw).all() and (g_itw == o_itw).all()
+
+
+@pytest.mark.parametrize("log", [3, 4, 5, 6, 8, 10, 12, 13, 14, 15, 17, 19, 21])
+def test_interpolate_evaluate(be, orc, tw, log):
+    kinds = {"random": rnd(0x5EED0000 + log, 1 << log),
+             "broadcast16": np.repeat(rnd(log, max(1, (1 << log) // 16)), 16)[: 1 << log],
+             "is_first": np.eye(1, 1 << log, 0, dtype=np.uint32)[0]}
+    cols = [be.column(v) for v in kinds.values()]
+    be.interpolate_columns(cols, tw)
+    refs = [orc.interpolate(v, ROOT_LOG) for v in kinds.values()]
+    for c, r, k in zip(cols, refs, kinds):
+        assert (c.to_cpu() == r).all(), f"interpolate {k} log {log}"
+    if log + 1 <= ROOT_LOG + 1:
+        ldes = be.evaluate_polynomials(cols, 1, tw)
+        for l, r, k in zip(ldes, refs, kinds):
+            assert (l.to_cpu() == orc.evaluate(r, 1, ROOT_LOG)).all(), f"evaluate {k} log {log}"
+    same = be.evaluate_polynomials(cols[:1], 0, tw)
+    assert (same[0].to_cpu() == list(kinds.values())[0]).all()
+
+
+def test_interpolate_mixed_sizes_and_errors(be, orc, tw, pkg):
+    logs = [4, 9, 4, 13, 16, 9]
+    host = [rnd(i, 1 << lg) for i, lg in enumerate(logs)]
+    cols = [be.column(h) for h in host]
+    be.interpolate_columns(cols, tw)
+    for c, h in zip(cols, host):
+        assert (c.to_cpu() == orc.interpolate(h, ROOT_LOG)).all()
+    with pytest.raises(pkg.BackendError):
+        be.interpolate_columns([be.column(np.zeros(12, dtype=np.uint32))], tw)      # not a power of two
+    with pytest.raises(pkg.BackendError):
+        be.interpolate_columns([be.zeros(1 << (ROOT_LOG + 2))], tw)                  # twiddle tree too small
+    be.interpolate_columns([], tw)                                                   # empty is fine
+
+
+@pytest.mark.parametrize("log", [0, 3, 5, 11, 12, 16, 20])
+def test_eval_at_point(be, orc, log):
+    c = rnd(log + 50, 1 << log)
+    pt = rnd(log + 51, 8)
+    got = be.eval_at_point([be.column(c)], pt)
+    assert (got[0] == orc.eval_at_point(c, pt)).all()
+
+
+def test_eval_at_point_batch(be, orc):
+    logs = [4, 13, 7, 18, 12]
+    cs = [rnd(i + 70, 1 << lg) for i, lg in enumerate(logs)]
+    pts = rnd(99, 8 * len(logs)).reshape(-1, 8)
+    got = be.eval_at_point([be.column(c) for c in cs], pts)
+    for g, c, p in zip(got, cs, pts):
+        assert (g == orc.eval_at_point(c, p)).all()
+
+
+@pytest.mark.parametrize("log,ncols,prev", [(0, 1, False), (0, 0, True), (3, 5, False), (5, 16, True), (8, 17, True),
+                                            (10, 0, True), (12, 33, False), (14, 60, True), (16, 4, True)])
+def test_commit_on_layer(be, orc, log, ncols, prev):
+    cols = [rnd(1000 + i, 1 << log) for i in range(ncols)]
+    pv = np.random.default_rng(log).integers(0, 2**32, size=16 << log, dtype=np.uint32) if prev else None
+    got = be.commit_on_layer(log, be.column(pv) if prev else None, [be.column(c) for c in cols])
+    assert (got.to_cpu() == orc.commit_on_layer(log, pv, cols)).all()
+
+
+def test_merkle_commit_mixed(be, orc):
+    logs = [12, 10, 12, 5, 10, 10, 4, 12, 7]
+    cols = [rnd(2000 + i, 1 << lg) for i, lg in enumerate(logs)]
+    layers, root = be.merkle_commit([be.column(c) for c in cols])
+    ref = orc.merkle_commit(cols)
+    assert len(layers) == len(ref) == 13
+    for k, (g, r) in enumerate(zip(layers, ref)):
+        assert (g.to_cpu() == r).all(), f"layer {k}"
+    assert (root == ref[0]).all()
+
+
+@pytest.mark.parametrize("log", [0, 1, 4, 9, 10, 11, 14, 17, 20])
+def test_bit_reverse(be, orc, log):
+    v = rnd(log, 1 << log)
+    c = be.column(v)
+    be.bit_reverse_column(c)
+    assert (c.to_cpu() == orc.bit_reverse(v)).all()
+
+
+def test_batch_inverse(be, orc):
+    v = rnd(1, 5000) | 1
+    d = be.zeros(5000)
+    be.batch_inverse(be.column(v), d)
+    assert (d.to_cpu() == orc.batch_inverse_m31(v)).all()
+    coords = [rnd(10 + k, 3000) for k in range(4)]
+    dst = [be.zeros(3000) for _ in range(4)]
+    be.batch_inverse_secure([be.column(c) for c in coords], dst)
+    for g, r in zip(dst, orc.batch_inverse_qm31(coords)):
+        assert (g.to_cpu() == r).all()
+
+
+@pytest.mark.parametrize("log", [1, 2, 5, 10, 16, 20])
+def test_fold_line(be, orc, tw, log):
+    coords = [rnd(300 + 4 * log + k, 1 << log) for k in range(4)]
+    alpha = [1, 2, 3, 4] if log % 2 else list(rnd(log, 4))
+    got = be.fold_line([be.column(c) for c in coords], log, alpha, tw)
+    for g, r in zip(got, orc.fold_line(coords, alpha)):
+        assert (g.to_cpu() == r).all()
+
+
+@pytest.mark.parametrize("log", [3, 4, 7, 12, 18, 21])
+def test_fold_circle_into_line(be, orc, tw, log):
+    coords = [rnd(400 + 4 * log + k, 1 << log) for k in range(4)]
+    dst = [rnd(500 + 4 * log + k, 1 << (log - 1)) for k in range(4)]
+    alpha = list(rnd(log + 1, 4))
+    gd = [be.column(d) for d in dst]
+    be.fold_circle_into_line(gd, [be.column(c) for c in coords], log, alpha, tw)
+    for g, r in zip(gd, orc.fold_circle_into_line(dst, coords, alpha)):
+        assert (g.to_cpu() == r).all()
+
+
+def test_fri_fold_to_constant(be, tw):
+    # size-independent property at a large size: folding the LDE of a low-degree secure poly ends on a constant layer
+    log = 20
+    coords = []
+    for k in range(4):
+        c = np.zeros(1 << (log - 1), dtype=np.uint32)
+        c[:] = rnd(600 + k, 1 << (log - 1))
+        col = be.column(c)
+        coords.append(be.evaluate_polynomials([col], 1, tw)[0])
+    alpha = [5, 6, 7, 8]
+    line = [be.zeros(1 << (log - 1)) for _ in range(4)]
+    be.fold_circle_into_line(line, coords, log, alpha, tw)
+    lg = log - 1
+    while lg > 1:
+        line = be.fold_line(line, lg, alpha, tw)
+        lg -= 1
+    for l in line:
+        v = l.to_cpu()
+        assert v[0] == v[1]
+
+
+@pytest.mark.parametrize("log", [1, 4, 10, 11, 12, 15, 20])
+def test_prefix_sum(be, orc, log):
+    v = rnd(700 + log, 1 << log)
+    c = be.column(v)
+    be.inclusive_prefix_sum(c)
+    assert (c.to_cpu() == orc.prefix_sum_bitrev(v)).all()
+
+
+def test_accumulate_and_powers(be, orc):
+    a = [rnd(800 + k, 1 << 12) for k in range(4)]
+    b = [rnd(810 + k, 1 << 12) for k in range(4)]
+    ga = [be.column(x) for x in a]
+    be.accumulate(ga, [be.column(x) for x in b])
+    for g, x, y in zip(ga, a, b):
+        assert (g.to_cpu() == (x.astype(np.uint64) + y) % P).all()
+    f = rnd(3, 4)
+    assert (be.generate_secure_powers(f, 103) == orc.secure_powers(f, 103)).all()
+
+
+def test_gen_is_first_and_broadcast(be):
+    c = be.gen_is_first(10).to_cpu()
+    assert c[0] == 1 and not c[1:].any()
+    v = rnd(9, 100)
+    assert (be.broadcast16(be.column(v)).to_cpu() == np.repeat(v, 16)).all()
+
+
+@pytest.mark.parametrize("log,ncols", [(4, 3), (9, 17), (14, 40)])
+def test_accumulate_quotients(be, orc, log, ncols):
+    cols = [rnd(900 + i, 1 << log) for i in range(ncols)]
+    alpha = rnd(1, 4)
+    # two batches: every column at point A, the last 4 columns also at point B
+    pts = rnd(2, 16)
+    bsizes = [ncols, min(4, ncols)]
+    ecols = list(range(ncols)) + list(range(ncols - bsizes[1], ncols))
+    evals = rnd(3, 4 * len(ecols))
+    got = be.accumulate_quotients(log, [be.column(c) for c in cols], alpha, pts, bsizes, ecols, evals)
+    ref = orc.accumulate_quotients(log, cols, alpha, pts, bsizes, ecols, evals)
+    for g, r in zip(got, ref):
+        assert (g.to_cpu() == r).all()
+    # no batches -> zero column
+    z = be.accumulate_quotients(log, [be.column(c) for c in cols], alpha, [], [], [], [])
+    assert not z[0].to_cpu().any()
+
+
+def test_grind(be, orc):
+    for seed in range(4):
+        d = np.random.default_rng(seed).integers(0, 2**32, size=8, dtype=np.uint32)
+        assert be.grind(d, 5) == orc.grind(d, 5)
+        assert be.grind(d, 12) == orc.grind(d, 12)
+
+
+def test_column_api(be):
+    c = be.zeros(64)
+    assert len(c) == 64 and c.at(5) == 0
+    c.set(5, 77)
+    assert c.at(5) == 77 and c.clone().at(5) == 77
