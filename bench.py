@@ -179,7 +179,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pkg = importlib.import_module("stwo-brainfuck_b200")
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # a real (non-default) stream: the library launches on this handle,
+    torch.cuda.set_stream(stream)         # and torch.cuda.Event records on the same one
+    assert stream.cuda_stream != 0
     be = pkg.CudaBackend(local, stream.cuda_stream)
     shape = tree_shape(args.scale_down)
     root_log = ROOT_LOG - args.scale_down
