@@ -1,0 +1,26 @@
+/* stwo_brainfuck.h — prove / verify entry points of libstwo_cuda.so: the host orchestrator that stands in for
+ * `brainfuck_prover prove|verify` (crates/brainfuck_prover/src/bin/brainfuck_prover.rs:79-152) and for
+ * prove_brainfuck / verify_brainfuck (crates/brainfuck_prover/src/brainfuck_air/mod.rs:471-797).
+ * The VM and the table builders run on the host; every Backend operation goes through the C ABI of stwo_cuda.h. */
+#ifndef STWO_BRAINFUCK_H
+#define STWO_BRAINFUCK_H
+#include "stwo_cuda.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+typedef struct sbf_proof sbf_proof; /* BrainfuckProof { claim, interaction_claim, proof } */
+const char* sbf_last_error(void);
+/* prove --code <code> with stdin bytes; log_max_rows = LOG_MAX_ROWS (24; 20 under cfg(test)), brainfuck_air/mod.rs:427-433 */
+int32_t sbf_prove(sc_ctx* ctx, const char* code, const uint8_t* input, size_t input_len, uint32_t log_max_rows, sbf_proof** out);
+/* verify_brainfuck: host only; 0 or SC_EVERIFY */
+int32_t sbf_verify(const sbf_proof* proof);
+char* sbf_proof_json(const sbf_proof* proof);    /* serde-shaped JSON of the proof; free with sbf_string_free */
+char* sbf_proof_report(const sbf_proof* proof);  /* steps, log sizes, per-stage milliseconds */
+size_t sbf_proof_output(const sbf_proof* proof, uint8_t* buf, size_t cap); /* program stdout */
+void sbf_string_free(char* s);
+void sbf_proof_free(sbf_proof* proof);
+int32_t sbf_proof_tamper(sbf_proof* proof, int32_t what); /* test hook: corrupt one field */
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -113,6 +113,23 @@ int32_t sc_gen_is_first(sc_ctx* ctx, uint32_t log_size, sc_col** out);
  * column (LogupTraceGenerator::finalize_last, e.g. crates/brainfuck_prover/src/components/processor/table.rs:530). */
 int32_t sc_prefix_sum_bitrev(sc_ctx* ctx, sc_col* col);
 
+/* ---- LogupTraceGenerator for one component: write_frac / finalize_col per relation entry, finalize_last.
+ * Stands in for the reference's interaction_trace_evaluation (e.g. crates/brainfuck_prover/src/components/processor/
+ * table.rs:456-533; memory/table.rs:485-518).  component: 0 memory, 1 instruction, 2 program, 3 processor, 4 `]`, 5 `[`,
+ * 6 `,`, 7 `<`, 8 `-`, 9 `.`, 10 `+`, 11 `>`, 12 end_of_execution (BrainfuckClaim order, brainfuck_air/mod.rs:79-93).
+ * main_cols: the component's main-trace evaluations, one value per 2^log_repeat rows (4 = the lane-compact form, 0 =
+ * full columns); elements: 3 x {z[4], alpha_powers[7][4]} for the memory,
+ * instruction and processor relations (brainfuck_air/mod.rs:149-165).  out: 4 x (#LogUp columns) new columns. ---- */
+int32_t sc_logup_generate(sc_ctx* ctx, int32_t component, sc_col* const* main_cols, uint32_t n_main, uint32_t log_repeat,
+                          const uint32_t* elements, sc_col** out, uint32_t claimed_sum[4]);
+/* ---- ComponentProver::evaluate_constraint_quotients_on_domain for one component (upstream constraint_framework/
+ * component.rs + simd_domain.rs; the `evaluate()` bodies are the reference's components/<name>/component.rs).
+ * Columns are the LDEs on CanonicCoset(log_size+1); coeffs: n_constraints x 4 words, coeffs[k] multiplies constraint k;
+ * accum (4 coordinate columns of the same length) += sum_k coeffs[k]*C_k / vanishing. ---- */
+int32_t sc_eval_constraints(sc_ctx* ctx, int32_t component, uint32_t log_size, sc_col* const* main_lde, uint32_t n_main,
+                            sc_col* const* inter_lde, uint32_t n_inter, const sc_col* is_first_lde, const uint32_t* elements,
+                            const uint32_t total_sum[4], const uint32_t* coeffs, sc_col* const accum[4]);
+
 #ifdef __cplusplus
 }
 #endif

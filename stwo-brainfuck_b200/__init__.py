@@ -64,8 +64,10 @@ ABI_SYMBOLS = [
     "sc_batch_inverse_qm31", "sc_precompute_twiddles", "sc_twiddles_free", "sc_twiddles_to_host", "sc_interpolate",
     "sc_evaluate", "sc_eval_at_point", "sc_merkle_commit_layer", "sc_merkle_commit", "sc_fold_line",
     "sc_fold_circle_into_line", "sc_accumulate_quotients", "sc_accumulate", "sc_secure_powers", "sc_grind",
-    "sc_gen_is_first", "sc_prefix_sum_bitrev",
+    "sc_gen_is_first", "sc_prefix_sum_bitrev", "sc_logup_generate", "sc_eval_constraints",
 ]
+PROVER_SYMBOLS = ["sbf_prove", "sbf_verify", "sbf_proof_json", "sbf_proof_report", "sbf_proof_output", "sbf_string_free",
+                  "sbf_proof_free", "sbf_proof_tamper", "sbf_last_error"]
 
 
 def _np_u32(a) -> np.ndarray:
@@ -282,3 +284,73 @@ class CudaBackend:
 
     def inclusive_prefix_sum(self, col: Column) -> None:
         self._ck(self._lib.sc_prefix_sum_bitrev(self._ctx, col._h))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# prove / verify — the stand-ins for `brainfuck_prover prove|verify` (crates/brainfuck_prover/src/bin/brainfuck_prover.rs)
+class VerificationError(RuntimeError):
+    pass
+
+
+class ProvingError(RuntimeError):
+    pass
+
+
+class Proof:
+    """BrainfuckProof handle (claim, interaction_claim, StarkProof) living on the C++ side."""
+
+    def __init__(self, lib, handle):
+        self._lib, self._h = lib, handle
+
+    def _str(self, fn) -> str:
+        fn.restype = _vp
+        p = fn(self._h)
+        s = ctypes.string_at(p).decode()
+        self._lib.sbf_string_free(_vp(p))
+        return s
+
+    def json(self) -> str:
+        return self._str(self._lib.sbf_proof_json)
+
+    def report(self) -> dict:
+        import json
+        return json.loads(self._str(self._lib.sbf_proof_report))
+
+    def output(self) -> bytes:
+        self._lib.sbf_proof_output.restype = ctypes.c_size_t
+        n = self._lib.sbf_proof_output(self._h, None, ctypes.c_size_t(0))
+        buf = (ctypes.c_uint8 * max(1, n))()
+        self._lib.sbf_proof_output(self._h, buf, ctypes.c_size_t(n))
+        return bytes(buf[:n])
+
+    def verify(self) -> None:
+        """verify_brainfuck (host only).  Raises VerificationError."""
+        if self._lib.sbf_verify(self._h) != 0:
+            self._lib.sbf_last_error.restype = ctypes.c_char_p
+            raise VerificationError(self._lib.sbf_last_error().decode())
+
+    def tamper(self, what: int) -> None:
+        if self._lib.sbf_proof_tamper(self._h, ctypes.c_int32(what)) != 0:
+            raise ValueError("bad tamper selector")
+
+    def __del__(self):
+        try:
+            if self._h is not None:
+                self._lib.sbf_proof_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+def prove_brainfuck(backend: CudaBackend, code: str, stdin: bytes = b"", log_max_rows: int = 24) -> Proof:
+    """prove_brainfuck(&Machine) of crates/brainfuck_prover/src/brainfuck_air/mod.rs:471-735: runs the VM on the host and the
+    whole proof on the device behind `backend`."""
+    lib = backend._lib
+    h = _vp()
+    code_b = code.encode() if isinstance(code, str) else code
+    rc = lib.sbf_prove(backend._ctx, ctypes.c_char_p(code_b), ctypes.c_char_p(stdin), ctypes.c_size_t(len(stdin)),
+                       ctypes.c_uint32(log_max_rows), ctypes.byref(h))
+    if rc != 0:
+        lib.sbf_last_error.restype = ctypes.c_char_p
+        raise ProvingError(lib.sbf_last_error().decode())
+    return Proof(lib, h)

@@ -9,6 +9,7 @@
 
 #include "../../include/stwo_cuda.h"
 #include "kernels.cuh"
+#include "air_params.cuh"
 
 using namespace sb;
 
@@ -272,15 +273,27 @@ int32_t sc_evaluate(sc_ctx* ctx, sc_col* const* coeffs, uint32_t n, uint32_t log
     uint32_t lg = ilog2(coeffs[i]->len);
     if (lg + log_blowup < 3) return fail(SC_EINVAL, "evaluate: domain log size < 3 is not supported on the device");
     if (lg + log_blowup > tw->root_log + 1) return fail(SC_EINVAL, "evaluate: twiddle tree too small for this domain");
-    if (log_blowup > 3) return fail(SC_EINVAL, "evaluate: log_blowup > 3 not supported");
   }
+  std::vector<uint32_t*> temps;  // zero-extended coefficient copies for log_blowup > 1 (PolyOps::extend)
   for (uint32_t i = 0; i < n; i++) {
     uint32_t lg = ilog2(coeffs[i]->len);
     int32_t r = new_col(ctx, coeffs[i]->len << log_blowup, &out[i]);
     if (r) return r;
-    by_log[lg].src.push_back(coeffs[i]->d);
+    const uint32_t* src = coeffs[i]->d;
+    if (log_blowup > 1) {
+      uint32_t* t;
+      size_t half = (size_t)coeffs[i]->len << (log_blowup - 1);
+      CK(cudaMallocAsync((void**)&t, half * 4, ctx->st));
+      CK(cudaMemsetAsync(t, 0, half * 4, ctx->st));
+      CK(cudaMemcpyAsync(t, src, coeffs[i]->len * 4, cudaMemcpyDeviceToDevice, ctx->st));
+      temps.push_back(t);
+      src = t;
+      lg += log_blowup - 1;
+    }
+    by_log[lg].src.push_back(src);
     by_log[lg].dst.push_back(out[i]->d);
   }
+  if (log_blowup > 1) log_blowup = 1;
   for (auto& kv : by_log) {
     void *ds, *dd;
     int32_t r = stage(ctx, kv.second.src.data(), kv.second.src.size() * sizeof(void*), &ds);
@@ -290,6 +303,7 @@ int32_t sc_evaluate(sc_ctx* ctx, sc_col* const* coeffs, uint32_t n, uint32_t log
     CKL(launch_evaluate((const uint32_t* const*)ds, (uint32_t* const*)dd, (uint32_t)kv.second.src.size(), kv.first,
                         kv.first + log_blowup, tw->tw + ((size_t)1 << tw->root_log), ctx->st));
   }
+  for (uint32_t* t : temps) CK(cudaFreeAsync(t, ctx->st));
   return SC_OK;
 }
 
@@ -495,6 +509,62 @@ int32_t sc_prefix_sum_bitrev(sc_ctx* ctx, sc_col* col) {
   CK(cudaMallocAsync((void**)&scratch, words * 4, ctx->st));
   CKL(launch_prefix_sum_bitrev(col->d, lg, scratch, ctx->st));
   CK(cudaFreeAsync(scratch, ctx->st));
+  return SC_OK;
+}
+
+// ------------------------------------------------------------------ AIR layer (air_kernels.cu)
+int32_t sc_logup_generate(sc_ctx* ctx, int32_t component, sc_col* const* main_cols, uint32_t n_main, uint32_t log_repeat,
+                          const uint32_t* elements, sc_col** out, uint32_t claimed_sum[4]) {
+  ENTER();
+  if (component < 0 || component >= sbf::N_COMPONENTS || !main_cols || !elements || !out || !claimed_sum) return fail(SC_EINVAL, "logup_generate: bad argument");
+  if ((int)n_main != sbf::N_MAIN_COLS[component]) return fail(SC_EINVAL, "logup_generate: wrong number of main columns");
+  if (!main_cols[0] || log_repeat > 8) return fail(SC_EINVAL, "logup_generate: bad argument");
+  uint64_t len = main_cols[0]->len << log_repeat;
+  if (!is_pow2(len) || len < 16) return fail(SC_EINVAL, "logup_generate: column length must be a power of two >= 16");
+  std::vector<const uint32_t*> mp(n_main);
+  for (uint32_t i = 0; i < n_main; i++) { if (!main_cols[i] || (main_cols[i]->len << log_repeat) != len) return fail(SC_EINVAL, "logup_generate: column length mismatch"); mp[i] = main_cols[i]->d; }
+  int nout = 4 * sbf::N_LOGUP_COLS[component];
+  std::vector<uint32_t*> op(nout);
+  for (int i = 0; i < nout; i++) { int32_t r = new_col(ctx, len, &out[i]); if (r) return r; op[i] = out[i]->d; }
+  void *dm, *dout;
+  int32_t r = stage(ctx, mp.data(), mp.size() * sizeof(void*), &dm); if (r) return r;
+  r = stage(ctx, op.data(), op.size() * sizeof(void*), &dout); if (r) return r;
+  AirParams p{};
+  p.main = (const uint32_t* const*)dm; p.out = (uint32_t* const*)dout; p.log_size = ilog2(len); p.main_shift = log_repeat;
+  memcpy(&p.el, elements, sizeof(p.el));
+  CKL(launch_air(false, component, p, ctx->st));
+  // LogupTraceGenerator::finalize_last: prefix-sum the last column's coordinates in coset order; claimed_sum = col.at(1)
+  for (int k = 0; k < 4; k++) { r = sc_prefix_sum_bitrev(ctx, out[nout - 4 + k]); if (r) return r; }
+  for (int k = 0; k < 4; k++) { r = sc_col_read(ctx, out[nout - 4 + k], 1, 1, &claimed_sum[k]); if (r) return r; }
+  return SC_OK;
+}
+
+int32_t sc_eval_constraints(sc_ctx* ctx, int32_t component, uint32_t log_size, sc_col* const* main_lde, uint32_t n_main,
+                            sc_col* const* inter_lde, uint32_t n_inter, const sc_col* is_first_lde, const uint32_t* elements,
+                            const uint32_t total_sum[4], const uint32_t* coeffs, sc_col* const accum[4]) {
+  ENTER();
+  if (component < 0 || component >= sbf::N_COMPONENTS || !main_lde || !inter_lde || !is_first_lde || !elements || !coeffs || !accum)
+    return fail(SC_EINVAL, "eval_constraints: bad argument");
+  if ((int)n_main != sbf::N_MAIN_COLS[component] || (int)n_inter != 4 * sbf::N_LOGUP_COLS[component])
+    return fail(SC_EINVAL, "eval_constraints: wrong number of columns");
+  uint64_t len = 2ull << log_size;
+  std::vector<const uint32_t*> mp(n_main), ip(n_inter);
+  for (uint32_t i = 0; i < n_main; i++) { if (!main_lde[i] || main_lde[i]->len != len) return fail(SC_EINVAL, "eval_constraints: main column length"); mp[i] = main_lde[i]->d; }
+  for (uint32_t i = 0; i < n_inter; i++) { if (!inter_lde[i] || inter_lde[i]->len != len) return fail(SC_EINVAL, "eval_constraints: interaction column length"); ip[i] = inter_lde[i]->d; }
+  if (is_first_lde->len != len) return fail(SC_EINVAL, "eval_constraints: is_first column length");
+  for (int k = 0; k < 4; k++) if (!accum[k] || accum[k]->len != len) return fail(SC_EINVAL, "eval_constraints: accumulator length");
+  void *dm, *di, *dc;
+  int32_t r = stage(ctx, mp.data(), mp.size() * sizeof(void*), &dm); if (r) return r;
+  r = stage(ctx, ip.data(), ip.size() * sizeof(void*), &di); if (r) return r;
+  r = stage(ctx, coeffs, (size_t)sbf::N_CONSTRAINTS[component] * 16, &dc); if (r) return r;
+  AirParams p{};
+  p.main = (const uint32_t* const*)dm; p.inter = (const uint32_t* const*)di; p.is_first = is_first_lde->d;
+  p.coeff = (const QM31*)dc; p.log_size = log_size;
+  memcpy(&p.el, elements, sizeof(p.el));
+  p.total_sum = q_make(total_sum[0], total_sum[1], total_sum[2], total_sum[3]);
+  vanishing_denom_inv(log_size, p.denom_inv);
+  for (int k = 0; k < 4; k++) p.acc[k] = accum[k]->d;
+  CKL(launch_air(true, component, p, ctx->st));
   return SC_OK;
 }
 

@@ -1,0 +1,180 @@
+// CudaBackend: the `Backend` the protocol driver runs on in the product — every method is one C-ABI call
+// (include/stwo_cuda.h), i.e. the host orchestrator dog-foods the drop-in boundary.  Also exports the prove / verify entry
+// points (`sbf_*`) that stand in for `brainfuck_prover prove|verify` (crates/brainfuck_prover/src/bin/brainfuck_prover.rs:79-152).
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "../../include/stwo_cuda.h"
+#include "host/verifier.hpp"
+
+using namespace sbf;
+
+namespace {
+
+struct CudaBackendImpl : Backend {
+  sc_ctx* ctx;
+  sc_twiddles* tw = nullptr;
+  explicit CudaBackendImpl(sc_ctx* c) : ctx(c) {}
+  ~CudaBackendImpl() override { if (tw) sc_twiddles_free(ctx, tw); }
+  static void ck(int32_t r) { if (r) throw std::runtime_error(std::string("stwo_cuda: ") + sc_last_error()); }
+  static sc_col* h(Col c) { return (sc_col*)c; }
+  const char* name() const override { return "cuda"; }
+
+  Col from_host(const uint32_t* v, size_t n) override { sc_col* c; ck(sc_col_from_host(ctx, v, n, &c)); return c; }
+  Col broadcast16(Col c) override { sc_col* o; ck(sc_col_broadcast16(ctx, h(c), &o)); return o; }
+  Col zeros(size_t n) override { sc_col* c; ck(sc_col_zeros(ctx, n, &c)); return c; }
+  size_t len(Col c) override { return sc_col_len(h(c)); }
+  void read(Col c, size_t off, size_t n, uint32_t* out) override { ck(sc_col_read(ctx, h(c), off, n, out)); }
+  void free_col(Col c) override { ck(sc_col_free(ctx, h(c))); }
+
+  void precompute_twiddles(uint32_t root_log) override {
+    if (tw) { sc_twiddles_free(ctx, tw); tw = nullptr; }
+    ck(sc_precompute_twiddles(ctx, root_log, &tw));
+  }
+  void interpolate(const std::vector<Col>& cols) override { ck(sc_interpolate(ctx, (sc_col* const*)cols.data(), (uint32_t)cols.size(), tw)); }
+  std::vector<Col> evaluate(const std::vector<Col>& coeffs, uint32_t log_blowup) override {
+    std::vector<Col> out(coeffs.size());
+    ck(sc_evaluate(ctx, (sc_col* const*)coeffs.data(), (uint32_t)coeffs.size(), log_blowup, tw, (sc_col**)out.data()));
+    return out;
+  }
+  std::vector<QM31> eval_at_point(const std::vector<Col>& polys, const std::vector<QPoint>& pts) override {
+    std::vector<QM31> out(polys.size());
+    static_assert(sizeof(QPoint) == 32 && sizeof(QM31) == 16, "layout");
+    ck(sc_eval_at_point(ctx, (sc_col* const*)polys.data(), (uint32_t)polys.size(), (const uint32_t*)pts.data(), (uint32_t*)out.data()));
+    return out;
+  }
+  std::vector<Col> merkle_commit(const std::vector<Col>& cols, Hash& root) override {
+    uint32_t max_log = 0;
+    for (Col c : cols) { uint32_t l = 0; while (((size_t)1 << l) < len(c)) l++; max_log = std::max(max_log, l); }
+    std::vector<Col> layers(max_log + 1);
+    ck(sc_merkle_commit(ctx, (sc_col* const*)cols.data(), (uint32_t)cols.size(), (sc_col**)layers.data(), nullptr, root.data()));
+    return layers;
+  }
+  std::array<Col, 4> fold_line(const std::array<Col, 4>& src, uint32_t log, QM31 alpha) override {
+    std::array<Col, 4> out;
+    ck(sc_fold_line(ctx, (sc_col* const*)src.data(), log, (const uint32_t*)&alpha, tw, (sc_col**)out.data()));
+    return out;
+  }
+  void fold_circle_into_line(const std::array<Col, 4>& dst, const std::array<Col, 4>& src, uint32_t log, QM31 alpha) override {
+    ck(sc_fold_circle_into_line(ctx, (sc_col* const*)src.data(), log, (const uint32_t*)&alpha, tw, (sc_col* const*)dst.data()));
+  }
+  std::array<Col, 4> accumulate_quotients(uint32_t log, const std::vector<Col>& cols, QM31 rc, const SampleBatchesFlat& b) override {
+    std::array<Col, 4> out;
+    ck(sc_accumulate_quotients(ctx, log, (sc_col* const*)cols.data(), (uint32_t)cols.size(), (const uint32_t*)&rc, b.points.data(),
+                               b.sizes.data(), b.entry_cols.data(), b.entry_vals.data(), (uint32_t)b.sizes.size(), (sc_col**)out.data()));
+    return out;
+  }
+  void accumulate(const std::array<Col, 4>& dst, const std::array<Col, 4>& src) override {
+    ck(sc_accumulate(ctx, (sc_col* const*)dst.data(), (sc_col* const*)src.data()));
+  }
+  uint64_t grind(const Hash& digest, uint32_t pow_bits) override { uint64_t n; ck(sc_grind(ctx, digest.data(), pow_bits, &n)); return n; }
+  Col gen_is_first(uint32_t log_size) override { sc_col* c; ck(sc_gen_is_first(ctx, log_size, &c)); return c; }
+  std::vector<Col> logup_generate(int comp, const std::vector<Col>& main, const InteractionElements& el, QM31& claimed) override {
+    std::vector<Col> out(4 * N_LOGUP_COLS[comp]);
+    ck(sc_logup_generate(ctx, comp, (sc_col* const*)main.data(), (uint32_t)main.size(), LOG_N_LANES, (const uint32_t*)&el,
+                         (sc_col**)out.data(), (uint32_t*)&claimed));
+    return out;
+  }
+  void eval_constraints(int comp, uint32_t log_size, const std::vector<Col>& m, const std::vector<Col>& it, Col is_first,
+                        const InteractionElements& el, QM31 total, const std::vector<QM31>& coeffs, const std::array<Col, 4>& acc) override {
+    ck(sc_eval_constraints(ctx, comp, log_size, (sc_col* const*)m.data(), (uint32_t)m.size(), (sc_col* const*)it.data(), (uint32_t)it.size(),
+                           h(is_first), (const uint32_t*)&el, (const uint32_t*)&total, (const uint32_t*)coeffs.data(), (sc_col* const*)acc.data()));
+  }
+};
+
+thread_local std::string g_sbf_err;
+char* dup_string(const std::string& s) {
+  char* p = (char*)malloc(s.size() + 1);
+  memcpy(p, s.c_str(), s.size() + 1);
+  return p;
+}
+
+}  // namespace
+
+struct sbf_proof {
+  BrainfuckProof proof;
+  ProverConfig cfg;
+  std::string report;  // JSON: steps, log sizes, per-stage host-clock milliseconds
+  std::vector<uint8_t> output;
+};
+
+extern "C" {
+
+const char* sbf_last_error(void) { return g_sbf_err.c_str(); }
+
+// `brainfuck_prover prove --code <code>` with stdin bytes `input`: run the VM on the host, prove on the device.
+// log_max_rows = LOG_MAX_ROWS (24; 20 in the reference's tests).  Returns 0 or SC_EPROOF.
+int32_t sbf_prove(sc_ctx* ctx, const char* code, const uint8_t* input, size_t input_len, uint32_t log_max_rows, sbf_proof** out) {
+  try {
+    if (!ctx || !code || !out) throw std::runtime_error("null argument");
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<uint32_t> program = compile(code);
+    Machine vm(program, std::vector<uint8_t>(input, input + input_len));
+    vm.execute();
+    double vm_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    CudaBackendImpl B(ctx);
+    ProverConfig cfg;
+    cfg.log_max_rows = log_max_rows;
+    auto t1 = std::chrono::steady_clock::now();
+    ProveResult r = prove_brainfuck(B, program, vm.trace, cfg, [&] { sc_ctx_sync(ctx); });
+    double prove_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
+    sbf_proof* p = new sbf_proof{std::move(r.proof), cfg, "", vm.output};
+    std::ostringstream o;
+    o << "{\"steps\":" << vm.trace.size() << ",\"vm_ms\":" << vm_ms << ",\"prove_ms\":" << prove_ms << ",\"log_sizes\":[";
+    for (int c = 0; c < N_COMPONENTS; c++) o << (c ? "," : "") << p->proof.log_size[c];
+    o << "],\"stages_ms\":{";
+    for (size_t i = 0; i < r.times.ms.size(); i++) o << (i ? "," : "") << "\"" << r.times.ms[i].first << "\":" << r.times.ms[i].second;
+    o << "}}";
+    p->report = o.str();
+    *out = p;
+    return SC_OK;
+  } catch (const std::exception& e) {
+    g_sbf_err = e.what();
+    return SC_EPROOF;
+  }
+}
+
+// `brainfuck_prover verify`: pure host code.  Returns 0 or SC_EVERIFY (message in sbf_last_error()).
+int32_t sbf_verify(const sbf_proof* p) {
+  try {
+    if (!p) throw std::runtime_error("null proof");
+    verify_brainfuck(p->proof, p->cfg);
+    return SC_OK;
+  } catch (const std::exception& e) {
+    g_sbf_err = e.what();
+    return SC_EVERIFY;
+  }
+}
+char* sbf_proof_json(const sbf_proof* p) { return p ? dup_string(proof_to_json(p->proof)) : nullptr; }
+char* sbf_proof_report(const sbf_proof* p) { return p ? dup_string(p->report) : nullptr; }
+size_t sbf_proof_output(const sbf_proof* p, uint8_t* buf, size_t cap) {
+  if (!p) return 0;
+  size_t n = std::min(cap, p->output.size());
+  if (buf && n) memcpy(buf, p->output.data(), n);
+  return p->output.size();
+}
+void sbf_string_free(char* s) { free(s); }
+void sbf_proof_free(sbf_proof* p) { delete p; }
+
+// Test hook: corrupt one field of a proof so that the verifier's rejection paths can be exercised.
+// what: 0 claimed_sum, 1 sampled value, 2 queried value, 3 FRI witness, 4 proof_of_work, 5 Merkle hash witness,
+//       6 last-layer polynomial, 7 commitment.
+int32_t sbf_proof_tamper(sbf_proof* p, int32_t what) {
+  if (!p) return SC_EINVAL;
+  CommitmentSchemeProof& s = p->proof.proof;
+  switch (what) {
+    case 0: p->proof.claimed_sum[0].a.a ^= 1; break;
+    case 1: s.sampled_values[1][0][0].a.a ^= 1; break;
+    case 2: s.queried_values[1][0][0] ^= 1; break;
+    case 3: s.fri_proof.first_layer.fri_witness[0].a.a ^= 1; break;
+    case 4: s.proof_of_work += 1; break;
+    case 5: s.decommitments[1].hash_witness[0][0] ^= 1; break;
+    case 6: s.fri_proof.last_layer_poly[0].a.a ^= 1; break;
+    case 7: s.commitments[2][0] ^= 1; break;
+    default: return SC_EINVAL;
+  }
+  return SC_OK;
+}
+
+}  // extern "C"

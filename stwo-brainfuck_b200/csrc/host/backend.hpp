@@ -1,0 +1,57 @@
+// The backend surface the protocol driver (prover.hpp) is written against — Stwo's `Backend` trait family plus the two
+// SimdBackend-only pieces (LogUp generation, constraint evaluation), SURVEY.md §8b.  The product implements it over the C
+// ABI (cuda_backend.cu); the CPU oracle implements it with scalar loops (oracle/orc_backend.cc, tests only).
+#pragma once
+#include <array>
+#include <vector>
+#include "air.hpp"
+#include "channel.hpp"
+
+namespace sbf {
+
+typedef void* Col;  // opaque column handle owned by the backend
+struct QPoint { QM31 x, y; };
+
+struct SampleBatchesFlat {   // ColumnSampleBatch list for one LDE size, flattened as the C ABI wants it
+  std::vector<uint32_t> points;      // nb x 8
+  std::vector<uint32_t> sizes;       // nb
+  std::vector<uint32_t> entry_cols;  // column index inside the size group
+  std::vector<uint32_t> entry_vals;  // 4 words per entry
+};
+
+struct Backend {
+  virtual ~Backend() {}
+  virtual const char* name() const = 0;
+  // Column<T>
+  virtual Col from_host(const uint32_t* v, size_t n) = 0;
+  virtual Col broadcast16(Col c) = 0;
+  virtual Col zeros(size_t n) = 0;
+  virtual size_t len(Col c) = 0;
+  virtual void read(Col c, size_t off, size_t n, uint32_t* out) = 0;
+  virtual void free_col(Col c) = 0;
+  // PolyOps
+  virtual void precompute_twiddles(uint32_t root_log) = 0;
+  virtual void interpolate(const std::vector<Col>& cols) = 0;                                  // in place
+  virtual std::vector<Col> evaluate(const std::vector<Col>& coeffs, uint32_t log_blowup) = 0;
+  virtual std::vector<QM31> eval_at_point(const std::vector<Col>& polys, const std::vector<QPoint>& pts) = 0;
+  // MerkleOps: layers[k] = layer of log size k
+  virtual std::vector<Col> merkle_commit(const std::vector<Col>& cols, Hash& root) = 0;
+  // FriOps
+  virtual std::array<Col, 4> fold_line(const std::array<Col, 4>& src, uint32_t log, QM31 alpha) = 0;
+  virtual void fold_circle_into_line(const std::array<Col, 4>& dst, const std::array<Col, 4>& src, uint32_t log, QM31 alpha) = 0;
+  // QuotientOps
+  virtual std::array<Col, 4> accumulate_quotients(uint32_t log, const std::vector<Col>& cols, QM31 random_coeff,
+                                                  const SampleBatchesFlat& b) = 0;
+  // AccumulationOps
+  virtual void accumulate(const std::array<Col, 4>& dst, const std::array<Col, 4>& src) = 0;
+  // GrindOps
+  virtual uint64_t grind(const Hash& digest, uint32_t pow_bits) = 0;
+  // constraint_framework
+  virtual Col gen_is_first(uint32_t log_size) = 0;
+  virtual std::vector<Col> logup_generate(int comp, const std::vector<Col>& main, const InteractionElements& el, QM31& claimed_sum) = 0;
+  virtual void eval_constraints(int comp, uint32_t log_size, const std::vector<Col>& main_lde, const std::vector<Col>& inter_lde,
+                                Col is_first_lde, const InteractionElements& el, QM31 total_sum, const std::vector<QM31>& coeffs,
+                                const std::array<Col, 4>& accum) = 0;
+};
+
+}  // namespace sbf

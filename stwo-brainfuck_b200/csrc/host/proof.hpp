@@ -1,0 +1,232 @@
+// Proof objects and shared protocol helpers (queries, sample batching, circle points over QM31, config).
+// Restates stwo-prover 0.1.1 @ 31e8dbc core/{pcs/mod.rs,pcs/quotients.rs,queries.rs,fri.rs,vcs/prover.rs} data shapes
+//  and the reference's BrainfuckProof (crates/brainfuck_prover/src/brainfuck_air/mod.rs:71-76).
+#pragma once
+#include <algorithm>
+#include <map>
+#include <set>
+#include <sstream>
+#include <string>
+#include "backend.hpp"
+
+namespace sbf {
+
+struct ProverConfig {          // PcsConfig::default() + LOG_MAX_ROWS (brainfuck_air/mod.rs:427-433,479)
+  uint32_t log_max_rows = 24;  // 20 under cfg(test) in the reference
+  uint32_t pow_bits = 5;
+  uint32_t log_blowup = 1;
+  uint32_t n_queries = 3;
+  uint32_t log_last_layer_degree_bound = 0;
+};
+
+struct MerkleDecommitment {
+  std::vector<Hash> hash_witness;
+  std::vector<uint32_t> column_witness;
+};
+struct FriLayerProof {
+  std::vector<QM31> fri_witness;
+  MerkleDecommitment decommitment;
+  Hash commitment;
+};
+struct FriProof {
+  FriLayerProof first_layer;
+  std::vector<FriLayerProof> inner_layers;
+  std::vector<QM31> last_layer_poly;
+};
+struct CommitmentSchemeProof {
+  std::vector<Hash> commitments;
+  std::vector<std::vector<std::vector<QM31>>> sampled_values;      // tree -> column -> sample
+  std::vector<MerkleDecommitment> decommitments;                   // per tree
+  std::vector<std::vector<std::vector<uint32_t>>> queried_values;  // tree -> column -> query
+  uint64_t proof_of_work = 0;
+  FriProof fri_proof;
+};
+struct BrainfuckProof {
+  uint32_t log_size[N_COMPONENTS];   // BrainfuckClaim
+  QM31 claimed_sum[N_COMPONENTS];    // BrainfuckInteractionClaim
+  CommitmentSchemeProof proof;       // StarkProof
+};
+
+// ---- circle points over QM31
+inline QPoint qp_add(QPoint p, QPoint q) {
+  return {q_sub(q_mul(p.x, q.x), q_mul(p.y, q.y)), q_add(q_mul(p.x, q.y), q_mul(p.y, q.x))};
+}
+inline Pt point_at_index(uint32_t idx) {
+  Pt r{1u, 0u}, b{GEN_X, GEN_Y};
+  idx &= 0x7fffffffu;
+  while (idx) { if (idx & 1u) r = p_add(r, b); b = p_dbl(b); idx >>= 1; }
+  return r;
+}
+inline QPoint to_qpoint(Pt p) { return {q_fromm(p.x), q_fromm(p.y)}; }
+// CanonicCoset(log).circle_domain().at(i)
+inline Pt canonic_domain_at(uint32_t log, uint32_t i) {
+  uint32_t half = 1u << (log - 1);
+  uint32_t init = 1u << (30 - log), step = 1u << (32 - log);
+  if (i < half) return point_at_index(init + (uint32_t)(((uint64_t)step * i) & 0x7fffffffu));
+  Pt p = point_at_index(init + (uint32_t)(((uint64_t)step * (i - half)) & 0x7fffffffu));
+  return p_conj(p);
+}
+// CirclePoint::get_random_point
+inline QPoint random_point(Channel& ch) {
+  QM31 t = ch.draw_felt();
+  QM31 t2 = q_sqr(t);
+  QM31 inv = q_inv(q_add(t2, q_fromm(1)));
+  return {q_mul(q_sub(q_fromm(1), t2), inv), q_mul(q_add(t, t), inv)};
+}
+inline bool qm31_less(const QM31& a, const QM31& b) {
+  uint32_t x[4] = {a.a.a, a.a.b, a.b.a, a.b.b}, y[4] = {b.a.a, b.a.b, b.b.a, b.b.b};
+  for (int i = 0; i < 4; i++) if (x[i] != y[i]) return x[i] < y[i];
+  return false;
+}
+struct QPointLess {
+  bool operator()(const QPoint& p, const QPoint& q) const {
+    if (!q_eq(p.x, q.x)) return qm31_less(p.x, q.x);
+    return qm31_less(p.y, q.y);
+  }
+};
+struct PointSample { QPoint point; QM31 value; };
+
+// ColumnSampleBatch::new_vec for the columns of one size group (BTreeMap keyed by point, stable inside a point)
+inline SampleBatchesFlat batch_samples(const std::vector<const std::vector<PointSample>*>& cols) {
+  std::map<QPoint, std::vector<std::pair<uint32_t, QM31>>, QPointLess> grouped;
+  for (uint32_t c = 0; c < cols.size(); c++)
+    for (const auto& s : *cols[c]) grouped[s.point].push_back({c, s.value});
+  SampleBatchesFlat f;
+  for (auto& kv : grouped) {
+    const QPoint& p = kv.first;
+    uint32_t w[8] = {p.x.a.a, p.x.a.b, p.x.b.a, p.x.b.b, p.y.a.a, p.y.a.b, p.y.b.a, p.y.b.b};
+    f.points.insert(f.points.end(), w, w + 8);
+    f.sizes.push_back((uint32_t)kv.second.size());
+    for (auto& e : kv.second) {
+      f.entry_cols.push_back(e.first);
+      uint32_t v[4] = {e.second.a.a, e.second.a.b, e.second.b.a, e.second.b.b};
+      f.entry_vals.insert(f.entry_vals.end(), v, v + 4);
+    }
+  }
+  return f;
+}
+
+// accumulate_row_quotients (core/pcs/quotients.rs) — verifier side, one row.
+inline QM31 row_quotient(const SampleBatchesFlat& f, const std::vector<uint32_t>& row_vals, QM31 alpha, Pt dp) {
+  QM31 acc = q_zero();
+  size_t e = 0;
+  for (size_t b = 0; b < f.sizes.size(); b++) {
+    const uint32_t* q = &f.points[8 * b];
+    QM31 sx = q_make(q[0], q[1], q[2], q[3]), sy = q_make(q[4], q[5], q[6], q[7]);
+    CM31 den = c_sub(c_mul(c_sub(sx.a, CM31{dp.x, 0}), sy.b), c_mul(c_sub(sy.a, CM31{dp.y, 0}), sx.b));
+    QM31 num = q_zero(), al = q_fromm(1);
+    QM31 c = q_sub(q_conj(sy), sy);
+    for (uint32_t j = 0; j < f.sizes[b]; j++, e++) {
+      al = q_mul(al, alpha);
+      QM31 v = q_make(f.entry_vals[4 * e], f.entry_vals[4 * e + 1], f.entry_vals[4 * e + 2], f.entry_vals[4 * e + 3]);
+      QM31 a = q_sub(q_conj(v), v);
+      QM31 bb = q_sub(q_mul(v, c), q_mul(a, sy));
+      QM31 value = q_mulm(q_mul(al, c), row_vals[f.entry_cols[e]]);
+      QM31 lin = q_add(q_mulm(q_mul(al, a), dp.y), q_mul(al, bb));
+      num = q_add(num, q_sub(value, lin));
+    }
+    acc = q_add(q_mul(acc, q_pow(alpha, f.sizes[b])), q_mulc(num, c_inv(den)));
+  }
+  return acc;
+}
+
+// ---- Queries (core/queries.rs)
+struct Queries {
+  std::vector<size_t> positions;
+  uint32_t log_domain_size;
+  static Queries generate(Channel& ch, uint32_t log_domain_size, uint32_t n_queries) {
+    std::set<size_t> s;
+    uint32_t cnt = 0;
+    size_t max_query = ((size_t)1 << log_domain_size) - 1;
+    for (;;) {
+      Hash w = ch.draw_random_bytes();
+      for (uint32_t x : w) {
+        s.insert((size_t)x & max_query);
+        if (++cnt == n_queries) return {std::vector<size_t>(s.begin(), s.end()), log_domain_size};
+      }
+    }
+  }
+  Queries fold(uint32_t n) const {
+    std::vector<size_t> p;
+    for (size_t q : positions) if (p.empty() || p.back() != (q >> n)) p.push_back(q >> n);
+    return {p, log_domain_size - n};
+  }
+};
+
+// compute_decommitment_positions (the fold cosets that contain a query), shared by prover and verifier
+inline std::vector<size_t> decommitment_positions(const std::vector<size_t>& queries, uint32_t fold_step) {
+  std::vector<size_t> out;
+  size_t i = 0;
+  while (i < queries.size()) {
+    size_t start = (queries[i] >> fold_step) << fold_step;
+    for (size_t p = start; p < start + ((size_t)1 << fold_step); p++) out.push_back(p);
+    while (i < queries.size() && (queries[i] >> fold_step) == (start >> fold_step)) i++;
+  }
+  return out;
+}
+
+// ---- JSON (serde shapes: M31 -> number, CM31 -> [a,b], QM31 -> [[a,b],[c,d]], hash -> hex string)
+inline std::string hex(const Hash& h) {
+  static const char* d = "0123456789abcdef";
+  std::string s;
+  const uint8_t* b = (const uint8_t*)h.data();
+  for (int i = 0; i < 32; i++) { s.push_back(d[b[i] >> 4]); s.push_back(d[b[i] & 15]); }
+  return s;
+}
+inline void jq(std::ostringstream& o, const QM31& q) { o << "[[" << q.a.a << "," << q.a.b << "],[" << q.b.a << "," << q.b.b << "]]"; }
+inline void jdec(std::ostringstream& o, const MerkleDecommitment& d) {
+  o << "{\"hash_witness\":[";
+  for (size_t i = 0; i < d.hash_witness.size(); i++) o << (i ? "," : "") << "\"" << hex(d.hash_witness[i]) << "\"";
+  o << "],\"column_witness\":[";
+  for (size_t i = 0; i < d.column_witness.size(); i++) o << (i ? "," : "") << d.column_witness[i];
+  o << "]}";
+}
+inline void jlayer(std::ostringstream& o, const FriLayerProof& l) {
+  o << "{\"fri_witness\":[";
+  for (size_t i = 0; i < l.fri_witness.size(); i++) { if (i) o << ","; jq(o, l.fri_witness[i]); }
+  o << "],\"decommitment\":";
+  jdec(o, l.decommitment);
+  o << ",\"commitment\":\"" << hex(l.commitment) << "\"}";
+}
+inline std::string proof_to_json(const BrainfuckProof& p) {
+  std::ostringstream o;
+  o << "{\"claim\":{";
+  for (int c = 0; c < N_COMPONENTS; c++) o << (c ? "," : "") << "\"" << COMPONENT_NAMES[c] << "\":{\"log_size\":" << p.log_size[c] << "}";
+  o << "},\"interaction_claim\":{";
+  for (int c = 0; c < N_COMPONENTS; c++) { o << (c ? "," : "") << "\"" << COMPONENT_NAMES[c] << "\":{\"claimed_sum\":"; jq(o, p.claimed_sum[c]); o << "}"; }
+  const CommitmentSchemeProof& s = p.proof;
+  o << "},\"proof\":{\"commitments\":[";
+  for (size_t i = 0; i < s.commitments.size(); i++) o << (i ? "," : "") << "\"" << hex(s.commitments[i]) << "\"";
+  o << "],\"sampled_values\":[";
+  for (size_t t = 0; t < s.sampled_values.size(); t++) {
+    o << (t ? "," : "") << "[";
+    for (size_t c = 0; c < s.sampled_values[t].size(); c++) {
+      o << (c ? "," : "") << "[";
+      for (size_t k = 0; k < s.sampled_values[t][c].size(); k++) { if (k) o << ","; jq(o, s.sampled_values[t][c][k]); }
+      o << "]";
+    }
+    o << "]";
+  }
+  o << "],\"decommitments\":[";
+  for (size_t t = 0; t < s.decommitments.size(); t++) { if (t) o << ","; jdec(o, s.decommitments[t]); }
+  o << "],\"queried_values\":[";
+  for (size_t t = 0; t < s.queried_values.size(); t++) {
+    o << (t ? "," : "") << "[";
+    for (size_t c = 0; c < s.queried_values[t].size(); c++) {
+      o << (c ? "," : "") << "[";
+      for (size_t k = 0; k < s.queried_values[t][c].size(); k++) o << (k ? "," : "") << s.queried_values[t][c][k];
+      o << "]";
+    }
+    o << "]";
+  }
+  o << "],\"proof_of_work\":" << s.proof_of_work << ",\"fri_proof\":{\"first_layer\":";
+  jlayer(o, s.fri_proof.first_layer);
+  o << ",\"inner_layers\":[";
+  for (size_t i = 0; i < s.fri_proof.inner_layers.size(); i++) { if (i) o << ","; jlayer(o, s.fri_proof.inner_layers[i]); }
+  o << "],\"last_layer_poly\":[";
+  for (size_t i = 0; i < s.fri_proof.last_layer_poly.size(); i++) { if (i) o << ","; jq(o, s.fri_proof.last_layer_poly[i]); }
+  o << "]}}}";
+  return o.str();
+}
+
+}  // namespace sbf

@@ -1,0 +1,68 @@
+"""End-to-end: prove on the GPU, verify on the host, and compare the proof byte for byte with the CPU oracle's proof
+(same protocol driver, every device op replaced by the scalar restatement).  Mirrors the reference's own end-to-end
+tests, crates/brainfuck_prover/src/brainfuck_air/mod.rs:799-859 (prove -> verify on four tiny programs)."""
+import ctypes
+import os
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PROGRAMS = os.path.join(ROOT, "tests", "golden", "programs")
+
+
+def oracle_proof(orc, code: bytes, stdin: bytes, log_max_rows: int) -> str:
+    lib = orc.lib
+    lib.orc_prove_json.restype = ctypes.c_void_p
+    lib.orc_last_error.restype = ctypes.c_char_p
+    p = lib.orc_prove_json(code, stdin, ctypes.c_size_t(len(stdin)), ctypes.c_uint32(log_max_rows), 1)
+    assert p, lib.orc_last_error()
+    s = ctypes.string_at(p).decode()
+    lib.orc_free(ctypes.c_void_p(p))
+    return s
+
+
+CASES = [  # the reference's four end-to-end programs (mod.rs:804-858) + the shipped examples that finish quickly
+    ("with_input", b"+>,<[>+.<-]", b"\x01", 10),
+    ("no_input", b"+++>++<[->+<]>.", b"", 10),
+    ("jump_mid", b"++[>+<-]>[-]<", b"", 10),
+    ("hello_kakarot", None, b"", 17),
+    ("collatz", None, b"7\n", 21),
+]
+
+
+@pytest.mark.parametrize("name,code,stdin,lmr", CASES)
+def test_prove_verify_matches_oracle(pkg, be, orc, name, code, stdin, lmr):
+    if code is None:
+        code = open(os.path.join(PROGRAMS, name + ".bf"), "rb").read()
+    proof = pkg.prove_brainfuck(be, code, stdin, lmr)
+    proof.verify()
+    want = oracle_proof(orc, code, stdin, lmr)
+    got = proof.json()
+    assert len(got) == len(want)
+    assert got == want, f"{name}: GPU proof differs from the oracle's proof"
+
+
+def test_hello_kakarot_at_reference_test_size(pkg, be):
+    # LOG_MAX_ROWS = 20 is what the reference uses under cfg(test) (brainfuck_air/mod.rs:430-433)
+    code = open(os.path.join(PROGRAMS, "hello_kakarot.bf"), "rb").read()
+    proof = pkg.prove_brainfuck(be, code, b"", 20)
+    proof.verify()
+    assert proof.output() == b"Hello Kakarot World!\n"
+    r = proof.report()
+    assert r["steps"] == 651 and r["log_sizes"] == [17, 14, 12, 14, 8, 4, 4, 10, 10, 9, 13, 11, 4]
+
+
+@pytest.mark.parametrize("what", range(8))
+def test_verifier_rejects_tampered_proof(pkg, be, what):
+    proof = pkg.prove_brainfuck(be, b"+>,<[>+.<-]", b"\x03", 10)
+    proof.verify()
+    proof.tamper(what)
+    with pytest.raises(pkg.VerificationError):
+        proof.verify()
+
+
+def test_component_too_large_is_an_error(pkg, be):
+    code = open(os.path.join(PROGRAMS, "hello_kakarot.bf"), "rb").read()
+    with pytest.raises(pkg.ProvingError):
+        pkg.prove_brainfuck(be, code, b"", 12)   # Memory needs log 17 > LOG_MAX_ROWS 12 (the reference panics likewise)
