@@ -1,14 +1,18 @@
 #!/usr/bin/env python
-"""bench.py — measures the proving hot path on B200 (see DESIGN.md §Measurement).
+"""bench.py — measures the proving hot path on B200 (DESIGN.md §4).
 
 Workloads (config.workload):
-  fib19_commit   the "LDE + commit" half of BASELINE.json's metric on fib19.bf's main-trace tree shape (128 columns,
-                 log sizes from SURVEY.md Table S): interpolate -> evaluate(blowup 2x) -> Blake2s Merkle commit.
-                 A step = one pass over one synthetic batch of that shape.  value = algorithmic GB/s.
-Contract: one JSON line on stdout from rank 0 (see task statement): metric/value/unit, e2e through the C ABI with host
-buffers, roofline of the dominant kernel group, cpu_baseline (oracle port timed on this box's cores), clocks.
-`--impl reference` times the CPU oracle port (the reference itself is Rust + an un-vendored git dependency and cannot be
-built in this image) on the same config.
+  fib19_prove   (default) BASELINE.json configs[1]: prove fib19.bf end to end on one B200, LOG_MAX_ROWS = 24, PcsConfig
+                default (pow 5, blowup 2x, 3 queries).  A step = one full proof.  metric = prove time (s), lower is better.
+                value = device path (tables already built on the host; includes the 63 MB compact-column upload);
+                e2e   = the whole `prove` call a user makes: VM run + host table building + uploads + proof + proof readback.
+  fib19_commit  the "LDE + commit GB/s" half of the metric on fib19's main-trace tree shape (128 columns): interpolate ->
+                evaluate(2x) -> Blake2s Merkle commit.  value = algorithmic GB/s.  (--workload commit)
+Contract: one JSON line on stdout from rank 0: metric/value/unit, e2e, roofline of the dominant kernel class (device time
+from CUDA events on the launch stream, recorded by the library's profiling scopes), cpu_baseline, clocks, gpu_launches.
+`--impl reference`: the reference is Rust + an un-vendored git dependency and cannot be built in this image, so this arm
+times the in-repo CPU oracle prover (OpenMP, all host cores) on a bounded sample and scales it to the workload (see
+`cpu_baseline.sample`).
 """
 import argparse
 import ctypes
@@ -25,42 +29,54 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 P = (1 << 31) - 1
+PROGRAMS = os.path.join(ROOT, "tests", "golden", "programs")
 
-# fib19.bf main-trace tree: (log_size, n_columns) per component, in commit order (col. fib19)
-FIB19_MAIN = [(24, 8), (22, 8), (11, 4), (22, 9), (19, 13), (11, 13), (4, 11), (20, 11), (19, 11), (4, 11), (20, 11),
-              (20, 11), (4, 7)]
+# fib19.bf: (log_size, main columns, LogUp columns) per component in commit order (column fib19)
+FIB19 = [(24, 8, 1), (22, 8, 1), (11, 4, 1), (22, 9, 3), (19, 13, 1), (11, 13, 1), (4, 11, 1), (20, 11, 1), (19, 11, 1),
+         (4, 11, 1), (20, 11, 1), (20, 11, 1), (4, 7, 1)]
+COLLATZ = [(21, 8, 1), (17, 8, 1), (13, 4, 1), (17, 9, 3), (14, 13, 1), (13, 13, 1), (5, 11, 1), (15, 11, 1), (14, 11, 1),
+           (6, 11, 1), (14, 11, 1), (15, 11, 1), (4, 7, 1)]
 ROOT_LOG = 26  # brainfuck_air/mod.rs:480-484: twiddles for CanonicCoset(24+1+2).circle_domain().half_coset
 
 
-def tree_shape(scale_down=0):
-    return [(max(4, lg - scale_down), n) for lg, n in FIB19_MAIN]
+def proof_columns(shape, log_max_rows):
+    """log sizes of every committed polynomial of a proof: preprocessed, main, interaction, composition."""
+    pre = list(range(log_max_rows, 3, -1))
+    main = [lg for lg, n, _ in shape for _ in range(n)]
+    inter = [lg for lg, _, k in shape for _ in range(4 * k)]
+    comp = [max(lg for lg, _, _ in shape) + 1] * 4
+    return pre, main, inter, comp
+
+
+def fft_bytes(logs):
+    """algorithmic bytes of interpolate (8N) + evaluate on the 2x domain (12N) per polynomial of 2^log words"""
+    return sum((8 + 12) * (1 << lg) for lg in logs)
+
+
+def proof_fft_bytes(shape, log_max_rows):
+    pre, main, inter, comp = proof_columns(shape, log_max_rows)
+    # composition polynomials are interpolated once (accumulator finalize) and evaluated once on the 2x domain; the lifts of
+    # the running polynomial between accumulator sizes are small and not counted
+    return fft_bytes(pre) + fft_bytes(main) + fft_bytes(inter) + fft_bytes(comp)
+
+
+def proof_lde_cells(shape, log_max_rows):
+    pre, main, inter, comp = proof_columns(shape, log_max_rows)
+    return sum(2 << lg for lg in pre + main + inter + comp)
 
 
 def commit_bytes(shape):
-    """Algorithmic bytes of one LDE+commit pass (DESIGN.md): per column of N words: iFFT 8N + LDE 12N;
-    Merkle: 4 B per LDE cell read + 32 B per node written + 64 B children read per non-leaf-layer node."""
-    fft = sum(n * (8 + 12) * (1 << lg) for lg, n in shape)
-    max_lde = max(lg for lg, _ in shape) + 1
-    merkle = sum(n * 4 * (2 << lg) for lg, n in shape)
+    cols = [(lg, n) for lg, n, _ in shape]
+    fft = sum(n * (8 + 12) * (1 << lg) for lg, n in cols)
+    max_lde = max(lg for lg, _ in cols) + 1
+    merkle = sum(n * 4 * (2 << lg) for lg, n in cols)
     merkle += sum((32 + (64 if k < max_lde else 0)) * (1 << k) for k in range(max_lde + 1))
     return fft, merkle
 
 
-def n_compressions(shape):
-    max_lde = max(lg for lg, _ in shape) + 1
-    per_layer = {}
-    for lg, n in shape:
-        per_layer[lg + 1] = per_layer.get(lg + 1, 0) + n
-    tot = 0
-    for k in range(max_lde + 1):
-        tot += (1 << k) * ((per_layer.get(k, 0) + 15) // 16 + (1 if k < max_lde else 0))
-    return tot
-
-
 class ClockSampler:
     def __init__(self, dev=0):
-        self.rows, self.stop = [], False
-        self.dev = dev
+        self.rows, self.stop, self.dev = [], False, dev
         self.t = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
@@ -74,7 +90,7 @@ class ClockSampler:
                     self.rows.append([x.strip() for x in o.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.1)
 
     def __enter__(self):
         self.t.start()
@@ -90,8 +106,7 @@ class ClockSampler:
         sm = sorted(int(float(r[0])) for r in self.rows)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.rows[0][1])), "reasons": reasons,
-                "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.rows[0][1])), "reasons": reasons, "samples": len(sm)}
 
 
 def peaks():
@@ -101,73 +116,50 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def oracle_lib():
+# ------------------------------------------------------------------------------------------------ CPU baseline (oracle port)
+def oracle():
     lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "liborc.so"))
+    lib.orc_prove_json.restype = ctypes.c_void_p
+    lib.orc_last_error.restype = ctypes.c_char_p
     return lib
 
 
-def cpu_commit_sample(scale_down, root_log):
-    """Oracle port of the same LDE+commit pass on a tree scaled down by 2^scale_down rows; returns (GB/s, seconds, threads)."""
-    lib = oracle_lib()
-    u32p = ctypes.POINTER(ctypes.c_uint32)
-    shape = tree_shape(scale_down)
-    rng = np.random.default_rng(1)
-    cols = [rng.integers(0, P, size=1 << lg, dtype=np.uint32) for lg, n in shape for _ in range(n)]
-    lib.orc_precompute_twiddles(root_log, np.empty(1 << root_log, dtype=np.uint32).ctypes.data_as(u32p),
-                                np.empty(1 << root_log, dtype=np.uint32).ctypes.data_as(u32p))  # warm the tree cache
+def cpu_prove_sample():
+    """CPU oracle prover (all host threads) on collatz.bf (stdin '7\\n') at LOG_MAX_ROWS 21, scaled to fib19 by committed LDE
+    cells.  Returns (scaled seconds, measured seconds, threads, description)."""
+    lib = oracle()
+    code = open(os.path.join(PROGRAMS, "collatz.bf"), "rb").read()
     t0 = time.perf_counter()
-    ldes = []
-    for c in cols:
-        lg = int(np.log2(c.size))
-        lib.orc_interpolate(c.ctypes.data_as(u32p), lg, 1, root_log)
-        o = np.empty(2 << lg, dtype=np.uint32)
-        lib.orc_evaluate(c.ctypes.data_as(u32p), lg, 1, 1, root_log, o.ctypes.data_as(u32p))
-        ldes.append(o)
-    logs = np.array([int(np.log2(o.size)) for o in ldes], dtype=np.uint32)
-    total = sum(8 << k for k in range(int(logs.max()) + 1))
-    buf = np.empty(total, dtype=np.uint32)
-    ptrs = (u32p * len(ldes))(*[o.ctypes.data_as(u32p) for o in ldes])
-    lib.orc_merkle_commit(ptrs, logs.ctypes.data_as(u32p), len(ldes), buf.ctypes.data_as(u32p))
+    p = lib.orc_prove_json(code, b"7\n", ctypes.c_size_t(2), ctypes.c_uint32(21), 0)
     dt = time.perf_counter() - t0
-    fft, merkle = commit_bytes(shape)
-    return (fft + merkle) / dt / 1e9, dt, int(lib.orc_num_threads())
+    if not p:
+        raise RuntimeError(lib.orc_last_error())
+    lib.orc_free(ctypes.c_void_p(p))
+    scale = proof_lde_cells(FIB19, 24) / proof_lde_cells(COLLATZ, 21)
+    return dt * scale, dt, int(lib.orc_num_threads()), \
+        f"CPU oracle prover (port; the Rust reference is not buildable here) on collatz.bf, LOG_MAX_ROWS 21: {dt:.2f} s measured, " \
+        f"scaled x{scale:.2f} by committed LDE cells to fib19.bf at LOG_MAX_ROWS 24"
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    sd = 6  # bounded sample: the same tree with 2^6 fewer rows per column (~15 M cells)
-    root_log = ROOT_LOG - sd
-    vals, secs = [], []
-    for i in range(args.warmup + args.steps):
-        v, dt, thr = cpu_commit_sample(sd, root_log)
-        if i >= args.warmup:
-            vals.append(v)
-            secs.append(dt)
+    vals = []
+    for i in range(max(1, min(args.steps, 2))):  # each sample is ~15-30 s of CPU work
+        scaled, dt, thr, desc = cpu_prove_sample()
+        vals.append(scaled)
     v = float(np.mean(vals))
-    line = {"impl": "reference", "metric": "LDE+commit throughput", "value": v, "unit": "GB/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u32 (M31)", "data": "synthetic",
-            "config": {"workload": "fib19_commit", "sample": f"fib19 main-trace tree shape with 2^{sd} fewer rows per column"},
-            "cpu_baseline": {"value": v, "unit": "GB/s", "cores": thr, "kind": "port",
-                             "sample": f"oracle port (reference is Rust, not buildable here), tree / 2^{sd}"},
-            "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    line = {"impl": "reference", "metric": "fib19.bf prove time", "value": v, "unit": "s", "n_gpus": args.gpus,
+            "steps": len(vals), "warmup": 0, "ms_per_step": 1e3 * v, "higher_is_better": False, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32 (M31)", "data": "fib19.bf (reference example program)",
+            "config": {"workload": "fib19_prove", "log_max_rows": 24, "pcs": "pow 5, blowup 2x, 3 queries"},
+            "cpu_baseline": {"value": v, "unit": "s", "cores": thr, "kind": "port", "sample": desc},
+            "e2e": {"value": v, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="cuda")
-    ap.add_argument("--scale-down", type=int, default=0, help="debug: shrink every column by 2^k rows")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
-
+# ------------------------------------------------------------------------------------------------ GPU arms
+def setup(args):
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -179,37 +171,109 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pkg = importlib.import_module("stwo-brainfuck_b200")
-    stream = torch.cuda.Stream()          # a real (non-default) stream: the library launches on this handle,
-    torch.cuda.set_stream(stream)         # and torch.cuda.Event records on the same one
-    assert stream.cuda_stream != 0
+    stream = torch.cuda.Stream()   # a real (non-default) stream: the library launches on this handle and
+    torch.cuda.set_stream(stream)  # torch.cuda.Event records on the same one
     be = pkg.CudaBackend(local, stream.cuda_stream)
-    shape = tree_shape(args.scale_down)
-    root_log = ROOT_LOG - args.scale_down
-    tw = be.precompute_twiddles(root_log)
+    return torch, dist, rank, world, local, pkg, stream, be
 
-    # synthetic trace columns: pinned host buffers (e2e) and resident device copies (value)
+
+def max_over_ranks(torch, dist, world, x):
+    if world == 1:
+        return x
+    t = torch.tensor([x], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def bench_prove(args):
+    torch, dist, rank, world, local, pkg, stream, be = setup(args)
+    code = open(os.path.join(PROGRAMS, "fib19.bf"), "rb").read()
+    lmr = 24
+
+    def step():
+        return pkg.prove_brainfuck(be, code, b"", lmr)
+
+    for _ in range(args.warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    be.profile(True)
+    be.profile_report()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = be.launch_count()
+    reports, proof_len = [], 0
+    with ClockSampler(local) as cs:
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(args.steps):
+            pr = step()
+            reports.append(pr.report())
+            proof_len = len(pr.json())      # proof readback (D2H of the result) is inside the timed region
+        e1.record(stream)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+    if world > 1:
+        dist.barrier()
+    launches = be.launch_count() - l0
+    prof = be.profile_report()
+    be.profile(False)
+    pr.verify()                              # the host verifier accepts the last proof
+    ev_s = e0.elapsed_time(e1) * 1e-3 / args.steps
+    e2e_s = max_over_ranks(torch, dist, world, max(wall / args.steps, ev_s))
+    host_tables = float(np.mean([r["stages_ms"]["tables(host)"] for r in reports])) * 1e-3
+    dev_s = max_over_ranks(torch, dist, world, float(np.mean([r["prove_ms"] for r in reports])) * 1e-3 - host_tables)
+    stages = {k: float(np.mean([r["stages_ms"][k] for r in reports])) for k in reports[0]["stages_ms"]}
+    kern = {k: v[0] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
+    peak, peak_src = peaks()
+    fft_ms = kern.get("fft_interpolate", 0) + kern.get("fft_evaluate", 0)
+    fb = proof_fft_bytes(FIB19, lmr)
+    roof = {"bound": "hbm", "kernel": "fft_pass_kernel (all interpolate + evaluate launches of one proof)",
+            "achieved": fb / (fft_ms * 1e-3) / 1e9 if fft_ms else None, "peak": peak, "unit": "GB/s", "traffic": None,
+            "peak_source": peak_src, "algorithmic_bytes": fb, "ms_per_proof": fft_ms}
+    roof["frac"] = roof["achieved"] / peak if roof["achieved"] else None
+    h2d = sum(n * (1 << (lg - 4)) * 4 for lg, n, _ in FIB19)
+    line = {"metric": "fib19.bf prove time", "value": dev_s, "unit": "s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_s * 1e3, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32 (M31)", "data": "fib19.bf (reference example program), 199246 VM steps",
+            "config": {"workload": "fib19_prove", "log_max_rows": lmr, "pcs": "pow 5, blowup 2x, 3 queries",
+                       "columns": 213, "lde_cells": proof_lde_cells(FIB19, lmr), "l2": "working set (>20 GB) exceeds L2",
+                       "parallelism": f"replicas x{world}", "proofs_per_s_all_gpus": world / dev_s},
+            "e2e": {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": proof_len,
+                    "includes": "VM run, host table building, uploads, proof, proof readback"},
+            "gpu_launches": int(launches), "stages_ms": stages, "kernel_ms_per_proof": kern, "roofline": roof,
+            "clocks": cs.summary(), "verified": True}
+    if rank == 0 and not args.no_cpu_baseline:
+        scaled, dt, thr, desc = cpu_prove_sample()
+        line["cpu_baseline"] = {"value": scaled, "unit": "s", "cores": thr, "kind": "port", "sample": desc}
+    if rank == 0:
+        print(json.dumps(line))
+    be.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_commit(args):
+    torch, dist, rank, world, local, pkg, stream, be = setup(args)
+    shape = [(max(4, lg - args.scale_down), n, k) for lg, n, k in FIB19]
+    tw = be.precompute_twiddles(ROOT_LOG - args.scale_down)
     rng = np.random.default_rng(0x5EED0000 + rank)
-    host = []
-    for lg, n in shape:
-        for _ in range(n):
-            t = torch.from_numpy(rng.integers(0, P, size=1 << lg, dtype=np.int64).astype(np.int32)).pin_memory()
-            host.append(t)
+    host = [torch.from_numpy(rng.integers(0, P, size=1 << lg, dtype=np.int64).astype(np.int32)).pin_memory()
+            for lg, n, _ in shape for _ in range(n)]
     h2d = sum(t.numel() * 4 for t in host)
     resident = [be.column(t.numpy().view(np.uint32)) for t in host]
 
     def step_resident():
-        cols = [c.clone() for c in resident]       # interpolate is in place; the clone is outside the algorithmic bytes
+        cols = [c.clone() for c in resident]   # interpolate is in place; the clone is outside the algorithmic bytes
         be.interpolate_columns(cols, tw)
         ldes = be.evaluate_polynomials(cols, 1, tw)
-        layers, root = be.merkle_commit(ldes)
-        return root
+        return be.merkle_commit(ldes)[1]
 
     def step_e2e():
         cols = [be.column(t.numpy().view(np.uint32)) for t in host]
         be.interpolate_columns(cols, tw)
         ldes = be.evaluate_polynomials(cols, 1, tw)
-        layers, root = be.merkle_commit(ldes)
-        return root
+        return be.merkle_commit(ldes)[1]
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -226,66 +290,54 @@ def main():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms / steps, be.launch_count() - l0, root
+        return max_over_ranks(torch, dist, world, e0.elapsed_time(e1) / steps), be.launch_count() - l0, root
 
     fft_b, merkle_b = commit_bytes(shape)
     alg = fft_b + merkle_b
     with ClockSampler(local) as cs:
+        be.profile(True)
+        be.profile_report()
         ms, launches, root = timed(step_resident, args.steps, args.warmup)
+        prof = be.profile_report()
+        be.profile(False)
         ms_e2e, _, root2 = timed(step_e2e, max(1, args.steps // 2), 1)
     assert (root == root2).all()
-    clocks = cs.summary()
-
-    # per-stage device times (CUDA events on the launch stream) for the roofline of the dominant stage
-    def stage_times():
-        cols = [c.clone() for c in resident]
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        torch.cuda.synchronize()
-        ev[0].record(stream)
-        be.interpolate_columns(cols, tw)
-        ev[1].record(stream)
-        ldes = be.evaluate_polynomials(cols, 1, tw)
-        ev[2].record(stream)
-        be.merkle_commit(ldes)
-        ev[3].record(stream)
-        torch.cuda.synchronize()
-        return [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
-
-    st = np.array([stage_times() for _ in range(3)]).min(axis=0)
+    kern = {k: v[0] / args.steps for k, v in prof.items()}
+    fft_ms = kern.get("fft_interpolate", 0) + kern.get("fft_evaluate", 0)
     peak, peak_src = peaks()
-    cells = sum(n << lg for lg, n in shape)
-    fft_ms = float(st[0] + st[1])
     roof = {"bound": "hbm", "kernel": "fft_pass_kernel (interpolate + evaluate, all passes)",
             "achieved": fft_b / (fft_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "traffic": None, "peak_source": peak_src}
     roof["frac"] = roof["achieved"] / peak
-
     line = {"metric": "LDE+commit throughput", "value": world * alg / (ms * 1e-3) / 1e9, "unit": "GB/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32 (M31)", "data": "synthetic",
-            "config": {"workload": "fib19_commit", "columns": sum(n for _, n in shape), "trace_cells": cells,
-                       "max_log_size": max(lg for lg, _ in shape), "log_blowup": 1, "scale_down": args.scale_down,
-                       "l2": "inputs (1 GB per step) exceed L2", "parallelism": f"replicas x{world}"},
-            "e2e": {"value": world * alg / (ms_e2e * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32},
-            "gpu_launches": int(launches),
-            "stages_ms": {"interpolate": float(st[0]), "evaluate": float(st[1]), "merkle_commit": float(st[2])},
-            "merkle": {"compressions": n_compressions(shape), "gcomp_per_s": n_compressions(shape) / (float(st[2]) * 1e-3) / 1e9},
-            "roofline": roof, "clocks": clocks}
-    if rank == 0 and not args.no_cpu_baseline:
-        sd = 6
-        v, dt, thr = cpu_commit_sample(sd, ROOT_LOG - sd)
-        line["cpu_baseline"] = {"value": v, "unit": "GB/s", "cores": thr, "kind": "port", "seconds": dt,
-                                "sample": f"oracle port of the same pass on the tree with 2^{sd} fewer rows per column"}
+            "config": {"workload": "fib19_commit", "columns": sum(n for _, n, _ in shape), "log_blowup": 1,
+                       "scale_down": args.scale_down, "l2": "inputs (1 GB per step) exceed L2", "parallelism": f"replicas x{world}"},
+            "e2e": {"value": world * alg / (ms_e2e * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 32},
+            "gpu_launches": int(launches), "kernel_ms_per_step": kern, "roofline": roof, "clocks": cs.summary()}
     if rank == 0:
         print(json.dumps(line))
     be.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda")
+    ap.add_argument("--workload", default="prove", choices=["prove", "commit"])
+    ap.add_argument("--scale-down", type=int, default=0, help="commit workload only: shrink every column by 2^k rows")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.workload == "commit":
+        return bench_commit(args)
+    return bench_prove(args)
 
 
 if __name__ == "__main__":

@@ -39,6 +39,10 @@ int32_t sc_ctx_destroy(sc_ctx* ctx);
 int32_t sc_ctx_sync(sc_ctx* ctx);
 /* Number of kernels launched through this context so far (bench.py's gpu_launches). */
 uint64_t sc_ctx_launch_count(const sc_ctx* ctx);
+/* Per-kernel-class device timing: when enabled every entry point brackets its launches with CUDA events on the launch
+ * stream; the report is "tag:milliseconds:count;..." (sum per tag since the last report) and clears the records. */
+int32_t sc_ctx_profile(sc_ctx* ctx, int32_t enable);
+size_t sc_ctx_profile_report(sc_ctx* ctx, char* buf, size_t cap);
 
 /* ---- Column<T> (upstream core/backend/mod.rs `Column`: zeros, uninitialized, to_cpu, len, at, set, clone) ---- */
 int32_t sc_col_zeros(sc_ctx* ctx, uint64_t len, sc_col** out);
@@ -112,6 +116,10 @@ int32_t sc_gen_is_first(sc_ctx* ctx, uint32_t log_size, sc_col** out);
 /* simd/prefix_sum.rs inclusive_prefix_sum: in-place inclusive prefix sum in trace-coset order of a bit-reversed
  * column (LogupTraceGenerator::finalize_last, e.g. crates/brainfuck_prover/src/components/processor/table.rs:530). */
 int32_t sc_prefix_sum_bitrev(sc_ctx* ctx, sc_col* col);
+
+/* ---- batched `Column::at` for decommitment (MerkleProver::decommit / FriProver::decommit read single elements):
+ * out_host[i*words .. +words) = cols[i][offsets[i] .. +words). ---- */
+int32_t sc_gather(sc_ctx* ctx, sc_col* const* cols, const uint64_t* offsets, uint32_t n, uint32_t words, uint32_t* out_host);
 
 /* ---- LogupTraceGenerator for one component: write_frac / finalize_col per relation entry, finalize_last.
  * Stands in for the reference's interaction_trace_evaluation (e.g. crates/brainfuck_prover/src/components/processor/

@@ -108,6 +108,11 @@ struct OrcBackend : Backend {
   size_t len(Col c) override { return H(c)->v.size(); }
   void read(Col c, size_t off, size_t n, uint32_t* out) override { memcpy(out, H(c)->v.data() + off, n * 4); }
   void free_col(Col c) override { delete H(c); }
+  std::vector<uint32_t> gather(const std::vector<Col>& cols, const std::vector<size_t>& offsets, uint32_t words) override {
+    std::vector<uint32_t> out(cols.size() * words);
+    for (size_t i = 0; i < cols.size(); i++) memcpy(&out[i * words], H(cols[i])->v.data() + offsets[i], words * 4);
+    return out;
+  }
 
   void precompute_twiddles(uint32_t root_log) override { orc::precompute_twiddles(orc::coset_half_odds(root_log), tw, itw); }
   void interpolate(const std::vector<Col>& cols) override {

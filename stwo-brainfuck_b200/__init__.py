@@ -64,7 +64,7 @@ ABI_SYMBOLS = [
     "sc_batch_inverse_qm31", "sc_precompute_twiddles", "sc_twiddles_free", "sc_twiddles_to_host", "sc_interpolate",
     "sc_evaluate", "sc_eval_at_point", "sc_merkle_commit_layer", "sc_merkle_commit", "sc_fold_line",
     "sc_fold_circle_into_line", "sc_accumulate_quotients", "sc_accumulate", "sc_secure_powers", "sc_grind",
-    "sc_gen_is_first", "sc_prefix_sum_bitrev", "sc_logup_generate", "sc_eval_constraints",
+    "sc_gen_is_first", "sc_prefix_sum_bitrev", "sc_logup_generate", "sc_eval_constraints", "sc_gather", "sc_ctx_profile", "sc_ctx_profile_report",
 ]
 PROVER_SYMBOLS = ["sbf_prove", "sbf_verify", "sbf_proof_json", "sbf_proof_report", "sbf_proof_output", "sbf_string_free",
                   "sbf_proof_free", "sbf_proof_tamper", "sbf_last_error"]
@@ -164,6 +164,23 @@ class CudaBackend:
 
     def launch_count(self) -> int:
         return int(self._lib.sc_ctx_launch_count(self._ctx))
+
+    def profile(self, enable: bool) -> None:
+        """Turns per-kernel-class CUDA-event timing on/off (sc_ctx_profile)."""
+        self._ck(self._lib.sc_ctx_profile(self._ctx, ctypes.c_int32(1 if enable else 0)))
+
+    def profile_report(self) -> dict:
+        """{tag: (milliseconds, scopes)} accumulated since the last report."""
+        self._lib.sc_ctx_profile_report.restype = ctypes.c_size_t
+        n = self._lib.sc_ctx_profile_report(self._ctx, None, ctypes.c_size_t(0))
+        buf = ctypes.create_string_buffer(1 << 16)
+        self._lib.sc_ctx_profile_report(self._ctx, buf, ctypes.c_size_t(len(buf)))
+        out = {}
+        for item in buf.value.decode().split(";"):
+            if item:
+                tag, ms, cnt = item.split(":")
+                out[tag] = (float(ms), int(cnt))
+        return out
 
     def close(self) -> None:
         if self._ctx is not None:

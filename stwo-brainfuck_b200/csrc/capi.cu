@@ -33,6 +33,24 @@ struct sc_ctx {
   uint8_t* h_ring;
   uint8_t* d_ring;
   size_t ring_size, ring_off;
+  // optional per-kernel-class timing (CUDA events on the launch stream), see sc_ctx_profile
+  bool profiling = false;
+  struct ProfRec { const char* tag; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;
+};
+
+// RAII: brackets the kernels launched in a scope with two events when profiling is on.
+struct ProfScope {
+  sc_ctx* c; cudaEvent_t a = nullptr, b = nullptr; const char* tag;
+  static cudaEvent_t get(sc_ctx* c) {
+    if (!c->ev_pool.empty()) { cudaEvent_t e = c->ev_pool.back(); c->ev_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+  ProfScope(sc_ctx* ctx, const char* t) : c(ctx), tag(t) {
+    if (c && c->profiling) { a = get(c); b = get(c); cudaEventRecord(a, c->st); }
+  }
+  ~ProfScope() { if (a) { cudaEventRecord(b, c->st); c->prof.push_back({tag, a, b}); } }
 };
 
 static thread_local std::string g_err;
@@ -121,6 +139,29 @@ int32_t sc_ctx_destroy(sc_ctx* ctx) {
 }
 int32_t sc_ctx_sync(sc_ctx* ctx) { ENTER(); CK(cudaStreamSynchronize(ctx->st)); return SC_OK; }
 uint64_t sc_ctx_launch_count(const sc_ctx*) { return g_launch_count; }
+int32_t sc_ctx_profile(sc_ctx* ctx, int32_t enable) {
+  ENTER();
+  ctx->profiling = enable != 0;
+  return SC_OK;
+}
+// Sums the recorded scopes per tag into "tag:ms:count;..." and clears them.  Returns the needed length.
+size_t sc_ctx_profile_report(sc_ctx* ctx, char* buf, size_t cap) {
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->st);
+  std::map<std::string, std::pair<double, int>> acc;
+  for (auto& r : ctx->prof) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    acc[r.tag].first += ms; acc[r.tag].second += 1;
+    ctx->ev_pool.push_back(r.a); ctx->ev_pool.push_back(r.b);
+  }
+  ctx->prof.clear();
+  std::string out;
+  for (auto& kv : acc) { char t[160]; snprintf(t, sizeof t, "%s:%.6f:%d;", kv.first.c_str(), kv.second.first, kv.second.second); out += t; }
+  if (buf && cap) { size_t n = std::min(cap - 1, out.size()); memcpy(buf, out.data(), n); buf[n] = 0; }
+  return out.size() + 1;
+}
 
 // ------------------------------------------------------------------ columns
 int32_t sc_col_uninit(sc_ctx* ctx, uint64_t len, sc_col** out) { ENTER(); if (!out) return fail(SC_EINVAL, "null out"); return new_col(ctx, len, out); }
@@ -186,21 +227,21 @@ int32_t sc_col_broadcast16(sc_ctx* ctx, const sc_col* src, sc_col** out) {
   if (!src || !out) return fail(SC_EINVAL, "null argument");
   int32_t r = new_col(ctx, src->len * 16, out);
   if (r) return r;
-  CKL(launch_broadcast16(src->d, (*out)->d, src->len, ctx->st));
+  { ProfScope ps_(ctx, "broadcast16"); CKL(launch_broadcast16(src->d, (*out)->d, src->len, ctx->st)); }
   return SC_OK;
 }
 
 int32_t sc_bit_reverse(sc_ctx* ctx, sc_col* col) {
   ENTER();
   if (!col || !is_pow2(col->len)) return fail(SC_EINVAL, "bit_reverse: length must be a power of two");
-  CKL(launch_bit_reverse(col->d, ilog2(col->len), ctx->st));
+  { ProfScope ps_(ctx, "bit_reverse"); CKL(launch_bit_reverse(col->d, ilog2(col->len), ctx->st)); }
   return SC_OK;
 }
 
 int32_t sc_batch_inverse_m31(sc_ctx* ctx, const sc_col* src, sc_col* dst) {
   ENTER();
   if (!src || !dst || src->len != dst->len) return fail(SC_EINVAL, "batch_inverse: length mismatch");
-  CKL(launch_batch_inverse_m31(src->d, dst->d, src->len, ctx->st));
+  { ProfScope ps_(ctx, "batch_inverse"); CKL(launch_batch_inverse_m31(src->d, dst->d, src->len, ctx->st)); }
   return SC_OK;
 }
 int32_t sc_batch_inverse_qm31(sc_ctx* ctx, sc_col* const src[4], sc_col* const dst[4]) {
@@ -210,7 +251,7 @@ int32_t sc_batch_inverse_qm31(sc_ctx* ctx, sc_col* const src[4], sc_col* const d
     if (!src[k] || !dst[k] || src[k]->len != src[0]->len || dst[k]->len != src[0]->len) return fail(SC_EINVAL, "batch_inverse: bad columns");
     s[k] = src[k]->d; d[k] = dst[k]->d;
   }
-  CKL(launch_batch_inverse_qm31(s, d, src[0]->len, ctx->st));
+  { ProfScope ps_(ctx, "batch_inverse"); CKL(launch_batch_inverse_qm31(s, d, src[0]->len, ctx->st)); }
   return SC_OK;
 }
 
@@ -221,7 +262,7 @@ int32_t sc_precompute_twiddles(sc_ctx* ctx, uint32_t root_log, sc_twiddles** out
   sc_twiddles* t = new sc_twiddles{root_log, nullptr, nullptr};
   CK(cudaMallocAsync((void**)&t->tw, (size_t)4 << root_log, ctx->st));
   CK(cudaMallocAsync((void**)&t->itw, (size_t)4 << root_log, ctx->st));
-  CKL(launch_twiddle_tree(t->tw, t->itw, root_log, ctx->st));
+  { ProfScope ps_(ctx, "twiddles"); CKL(launch_twiddle_tree(t->tw, t->itw, root_log, ctx->st)); }
   *out = t;
   return SC_OK;
 }
@@ -258,7 +299,7 @@ int32_t sc_interpolate(sc_ctx* ctx, sc_col* const* cols, uint32_t n, const sc_tw
     void* dp;
     int32_t r = stage(ctx, kv.second.data(), kv.second.size() * sizeof(void*), &dp);
     if (r) return r;
-    CKL(launch_interpolate((uint32_t* const*)dp, (uint32_t)kv.second.size(), kv.first, tw->itw + ((size_t)1 << tw->root_log), ctx->st));
+    { ProfScope ps_(ctx, "fft_interpolate"); CKL(launch_interpolate((uint32_t* const*)dp, (uint32_t)kv.second.size(), kv.first, tw->itw + ((size_t)1 << tw->root_log), ctx->st)); }
   }
   return SC_OK;
 }
@@ -300,8 +341,8 @@ int32_t sc_evaluate(sc_ctx* ctx, sc_col* const* coeffs, uint32_t n, uint32_t log
     if (r) return r;
     r = stage(ctx, kv.second.dst.data(), kv.second.dst.size() * sizeof(void*), &dd);
     if (r) return r;
-    CKL(launch_evaluate((const uint32_t* const*)ds, (uint32_t* const*)dd, (uint32_t)kv.second.src.size(), kv.first,
-                        kv.first + log_blowup, tw->tw + ((size_t)1 << tw->root_log), ctx->st));
+    { ProfScope ps_(ctx, "fft_evaluate"); CKL(launch_evaluate((const uint32_t* const*)ds, (uint32_t* const*)dd, (uint32_t)kv.second.src.size(), kv.first,
+                        kv.first + log_blowup, tw->tw + ((size_t)1 << tw->root_log), ctx->st)); }
   }
   for (uint32_t* t : temps) CK(cudaFreeAsync(t, ctx->st));
   return SC_OK;
@@ -333,7 +374,7 @@ int32_t sc_eval_at_point(sc_ctx* ctx, sc_col* const* polys, uint32_t n, const ui
   CK(cudaMallocAsync((void**)&partials, (size_t)blocks * sizeof(QM31), ctx->st));
   CK(cudaMallocAsync((void**)&work, (size_t)blocks * sizeof(QM31), ctx->st));
   CK(cudaMallocAsync((void**)&dout, (size_t)n * sizeof(QM31), ctx->st));
-  CKL(launch_eval_at_point_tasks(dt, n, blocks, partials, work, dout, ctx->st));
+  { ProfScope ps_(ctx, "eval_at_point"); CKL(launch_eval_at_point_tasks(dt, n, blocks, partials, work, dout, ctx->st)); }
   CK(cudaMemcpyAsync(out, dout, (size_t)n * sizeof(QM31), cudaMemcpyDeviceToHost, ctx->st));
   CK(cudaStreamSynchronize(ctx->st));
   CK(cudaFreeAsync(partials, ctx->st));
@@ -357,7 +398,7 @@ int32_t sc_merkle_commit_layer(sc_ctx* ctx, uint32_t log_size, const sc_col* pre
   if (n) { int32_t r = stage(ctx, p.data(), n * sizeof(void*), &dp); if (r) return r; }
   int32_t r = new_col(ctx, rows * 8, out);
   if (r) return r;
-  CKL(launch_commit_layer(log_size, prev ? prev->d : nullptr, (const uint32_t* const*)dp, n, (*out)->d, ctx->st));
+  { ProfScope ps_(ctx, "merkle_commit_layer"); CKL(launch_commit_layer(log_size, prev ? prev->d : nullptr, (const uint32_t* const*)dp, n, (*out)->d, ctx->st)); }
   return SC_OK;
 }
 
@@ -390,7 +431,7 @@ int32_t sc_fold_line(sc_ctx* ctx, sc_col* const src[4], uint32_t log, const uint
     s[k] = src[k]->d;
   }
   for (int k = 0; k < 4; k++) { int32_t r = new_col(ctx, 1ull << (log - 1), &dst_out[k]); if (r) return r; d[k] = dst_out[k]->d; }
-  CKL(launch_fold_line(s, log, q_make(alpha[0], alpha[1], alpha[2], alpha[3]), d, tw->itw + ((size_t)1 << tw->root_log), ctx->st));
+  { ProfScope ps_(ctx, "fold_line"); CKL(launch_fold_line(s, log, q_make(alpha[0], alpha[1], alpha[2], alpha[3]), d, tw->itw + ((size_t)1 << tw->root_log), ctx->st)); }
   return SC_OK;
 }
 int32_t sc_fold_circle_into_line(sc_ctx* ctx, sc_col* const src[4], uint32_t log, const uint32_t alpha[4], const sc_twiddles* tw, sc_col* const dst[4]) {
@@ -401,7 +442,7 @@ int32_t sc_fold_circle_into_line(sc_ctx* ctx, sc_col* const src[4], uint32_t log
     if (!src[k] || !dst[k] || src[k]->len != (1ull << log) || dst[k]->len != (1ull << (log - 1))) return fail(SC_EINVAL, "fold_circle_into_line: bad columns");
     s[k] = src[k]->d; d[k] = dst[k]->d;
   }
-  CKL(launch_fold_circle_into_line(s, log, q_make(alpha[0], alpha[1], alpha[2], alpha[3]), d, tw->itw + ((size_t)1 << tw->root_log), ctx->st));
+  { ProfScope ps_(ctx, "fold_circle_into_line"); CKL(launch_fold_circle_into_line(s, log, q_make(alpha[0], alpha[1], alpha[2], alpha[3]), d, tw->itw + ((size_t)1 << tw->root_log), ctx->st)); }
   return SC_OK;
 }
 
@@ -452,7 +493,7 @@ int32_t sc_accumulate_quotients(sc_ctx* ctx, uint32_t log, sc_col* const* cols, 
   if (n) { r = stage(ctx, p.data(), n * sizeof(void*), &dp); if (r) return r; }
   r = stage(ctx, qb.data(), qb.size() * sizeof(QuotBatch), &db); if (r) return r;
   if (!qe.empty()) { r = stage(ctx, qe.data(), qe.size() * sizeof(QuotEntry), &de); if (r) return r; }
-  CKL(launch_accumulate_quotients(log, (const uint32_t* const*)dp, (const QuotBatch*)db, nb, (const QuotEntry*)de, d, ctx->st));
+  { ProfScope ps_(ctx, "accumulate_quotients"); CKL(launch_accumulate_quotients(log, (const uint32_t* const*)dp, (const QuotBatch*)db, nb, (const QuotEntry*)de, d, ctx->st)); }
   return SC_OK;
 }
 
@@ -464,7 +505,7 @@ int32_t sc_accumulate(sc_ctx* ctx, sc_col* const dst[4], sc_col* const src[4]) {
     if (!dst[k] || !src[k] || dst[k]->len != dst[0]->len || src[k]->len != dst[0]->len) return fail(SC_EINVAL, "accumulate: bad columns");
     d[k] = dst[k]->d; s[k] = src[k]->d;
   }
-  CKL(launch_accumulate(d, s, dst[0]->len, ctx->st));
+  { ProfScope ps_(ctx, "accumulate"); CKL(launch_accumulate(d, s, dst[0]->len, ctx->st)); }
   return SC_OK;
 }
 int32_t sc_secure_powers(const uint32_t felt[4], uint32_t n, uint32_t* out) {
@@ -497,7 +538,7 @@ int32_t sc_gen_is_first(sc_ctx* ctx, uint32_t log_size, sc_col** out) {
   if (!out || log_size > 30) return fail(SC_EINVAL, "gen_is_first: bad argument");
   int32_t r = new_col(ctx, 1ull << log_size, out);
   if (r) return r;
-  CKL(launch_gen_is_first((*out)->d, log_size, ctx->st));
+  { ProfScope ps_(ctx, "gen_is_first"); CKL(launch_gen_is_first((*out)->d, log_size, ctx->st)); }
   return SC_OK;
 }
 int32_t sc_prefix_sum_bitrev(sc_ctx* ctx, sc_col* col) {
@@ -507,8 +548,30 @@ int32_t sc_prefix_sum_bitrev(sc_ctx* ctx, sc_col* col) {
   uint32_t* scratch;
   size_t words = col->len + 2 * ((col->len >> 11) + 2) + 8;
   CK(cudaMallocAsync((void**)&scratch, words * 4, ctx->st));
-  CKL(launch_prefix_sum_bitrev(col->d, lg, scratch, ctx->st));
+  { ProfScope ps_(ctx, "prefix_sum"); CKL(launch_prefix_sum_bitrev(col->d, lg, scratch, ctx->st)); }
   CK(cudaFreeAsync(scratch, ctx->st));
+  return SC_OK;
+}
+
+// Batched decommitment gather: out[i*words .. +words) = cols[i][offsets[i] .. +words).  One kernel + one D2H copy instead
+// of one tiny copy per queried value (MerkleProver::decommit walks Column::at element by element upstream).
+int32_t sc_gather(sc_ctx* ctx, sc_col* const* cols, const uint64_t* offsets, uint32_t n, uint32_t words, uint32_t* out_host) {
+  ENTER();
+  if (!n) return SC_OK;
+  if (!cols || !offsets || !out_host || !words) return fail(SC_EINVAL, "gather: bad argument");
+  std::vector<const uint32_t*> p(n);
+  for (uint32_t i = 0; i < n; i++) {
+    if (!cols[i] || offsets[i] + words > cols[i]->len) return fail(SC_EINVAL, "gather: out of range");
+    p[i] = cols[i]->d + offsets[i];
+  }
+  void* dp;
+  int32_t r = stage(ctx, p.data(), n * sizeof(void*), &dp); if (r) return r;
+  uint32_t* dout;
+  CK(cudaMallocAsync((void**)&dout, (size_t)n * words * 4, ctx->st));
+  { ProfScope ps_(ctx, "gather"); CKL(launch_gather((const uint32_t* const*)dp, n, words, dout, ctx->st)); }
+  CK(cudaMemcpyAsync(out_host, dout, (size_t)n * words * 4, cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  CK(cudaFreeAsync(dout, ctx->st));
   return SC_OK;
 }
 
@@ -532,7 +595,7 @@ int32_t sc_logup_generate(sc_ctx* ctx, int32_t component, sc_col* const* main_co
   AirParams p{};
   p.main = (const uint32_t* const*)dm; p.out = (uint32_t* const*)dout; p.log_size = ilog2(len); p.main_shift = log_repeat;
   memcpy(&p.el, elements, sizeof(p.el));
-  CKL(launch_air(false, component, p, ctx->st));
+  { ProfScope ps_(ctx, "logup_generate"); CKL(launch_air(false, component, p, ctx->st)); }
   // LogupTraceGenerator::finalize_last: prefix-sum the last column's coordinates in coset order; claimed_sum = col.at(1)
   for (int k = 0; k < 4; k++) { r = sc_prefix_sum_bitrev(ctx, out[nout - 4 + k]); if (r) return r; }
   for (int k = 0; k < 4; k++) { r = sc_col_read(ctx, out[nout - 4 + k], 1, 1, &claimed_sum[k]); if (r) return r; }
@@ -564,7 +627,7 @@ int32_t sc_eval_constraints(sc_ctx* ctx, int32_t component, uint32_t log_size, s
   p.total_sum = q_make(total_sum[0], total_sum[1], total_sum[2], total_sum[3]);
   vanishing_denom_inv(log_size, p.denom_inv);
   for (int k = 0; k < 4; k++) p.acc[k] = accum[k]->d;
-  CKL(launch_air(true, component, p, ctx->st));
+  { ProfScope ps_(ctx, "eval_constraints"); CKL(launch_air(true, component, p, ctx->st)); }
   return SC_OK;
 }
 

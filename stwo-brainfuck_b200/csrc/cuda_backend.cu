@@ -27,6 +27,12 @@ struct CudaBackendImpl : Backend {
   size_t len(Col c) override { return sc_col_len(h(c)); }
   void read(Col c, size_t off, size_t n, uint32_t* out) override { ck(sc_col_read(ctx, h(c), off, n, out)); }
   void free_col(Col c) override { ck(sc_col_free(ctx, h(c))); }
+  std::vector<uint32_t> gather(const std::vector<Col>& cols, const std::vector<size_t>& offsets, uint32_t words) override {
+    std::vector<uint32_t> out(cols.size() * words);
+    std::vector<uint64_t> off(offsets.begin(), offsets.end());
+    ck(sc_gather(ctx, (sc_col* const*)cols.data(), off.data(), (uint32_t)cols.size(), words, out.data()));
+    return out;
+  }
 
   void precompute_twiddles(uint32_t root_log) override {
     if (tw) { sc_twiddles_free(ctx, tw); tw = nullptr; }

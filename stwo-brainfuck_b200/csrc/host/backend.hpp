@@ -29,6 +29,8 @@ struct Backend {
   virtual size_t len(Col c) = 0;
   virtual void read(Col c, size_t off, size_t n, uint32_t* out) = 0;
   virtual void free_col(Col c) = 0;
+  // batched Column::at: out[i*words .. +words) = cols[i][offsets[i] .. +words)
+  virtual std::vector<uint32_t> gather(const std::vector<Col>& cols, const std::vector<size_t>& offsets, uint32_t words) = 0;
   // PolyOps
   virtual void precompute_twiddles(uint32_t root_log) = 0;
   virtual void interpolate(const std::vector<Col>& cols) = 0;                                  // in place

@@ -123,9 +123,15 @@ inline InteractionElements draw_elements(Channel& ch) {  // BrainfuckInteraction
 }
 
 // MerkleProver::decommit (core/vcs/prover.rs): values come back per column in the original column order.
+// The walk over the layers only needs indices, so it first records every element it would read (`Column::at` upstream) and
+// then fetches them with two batched gathers (hashes, column values) instead of thousands of 4..32-byte copies.
 inline void merkle_decommit(Backend& B, const CommitTree& t, const std::vector<Col>& columns, const std::map<uint32_t, std::vector<size_t>>& queries,
                             std::vector<std::vector<uint32_t>>& queried_values, MerkleDecommitment& d) {
   queried_values.assign(columns.size(), {});
+  std::vector<Col> hcols, vcols;
+  std::vector<size_t> hoff, voff;
+  struct VReq { size_t col; bool queried; };
+  std::vector<VReq> vreq;
   std::vector<size_t> last_queries;
   int n_layers = (int)t.layers.size();
   for (int lg = n_layers - 1; lg >= 0; lg--) {
@@ -142,23 +148,38 @@ inline void merkle_decommit(Backend& B, const CommitTree& t, const std::vector<C
       else if (pi < last_queries.size()) node = last_queries[pi] / 2;
       else node = colq[ci];
       if (lg + 1 < n_layers) {
-        Col prev = t.layers[lg + 1];
         for (size_t child = 2 * node; child <= 2 * node + 1; child++) {
           if (pi < last_queries.size() && last_queries[pi] == child) pi++;
-          else { Hash h; B.read(prev, 8 * child, 8, h.data()); d.hash_witness.push_back(h); }
+          else { hcols.push_back(t.layers[lg + 1]); hoff.push_back(8 * child); }
         }
       }
       bool queried = ci < colq.size() && colq[ci] == node;
       if (queried) ci++;
-      for (size_t c : lcols) {
-        uint32_t v;
-        B.read(columns[c], node, 1, &v);
-        if (queried) queried_values[c].push_back(v); else d.column_witness.push_back(v);
-      }
+      for (size_t c : lcols) { vcols.push_back(columns[c]); voff.push_back(node); vreq.push_back({c, queried}); }
       total.push_back(node);
     }
     last_queries = total;
   }
+  std::vector<uint32_t> hw = B.gather(hcols, hoff, 8), vw = B.gather(vcols, voff, 1);
+  for (size_t i = 0; i < hcols.size(); i++) { Hash h; memcpy(h.data(), &hw[8 * i], 32); d.hash_witness.push_back(h); }
+  for (size_t i = 0; i < vreq.size(); i++) {
+    if (vreq[i].queried) queried_values[vreq[i].col].push_back(vw[i]); else d.column_witness.push_back(vw[i]);
+  }
+}
+
+// FRI witness evaluations of one layer: the positions of each fold coset that are not themselves queried.
+inline void fri_witness(Backend& B, const std::array<Col, 4>& eval, const std::vector<size_t>& queries, const std::vector<size_t>& pos,
+                        std::vector<QM31>& out) {
+  std::vector<Col> cols;
+  std::vector<size_t> off;
+  size_t k = 0;
+  for (size_t p : pos) {
+    while (k < queries.size() && queries[k] < p) k++;
+    if (k < queries.size() && queries[k] == p) continue;
+    for (int c = 0; c < 4; c++) { cols.push_back(eval[c]); off.push_back(p); }
+  }
+  std::vector<uint32_t> w = B.gather(cols, off, 1);
+  for (size_t i = 0; i + 3 < w.size(); i += 4) out.push_back(q_make(w[i], w[i + 1], w[i + 2], w[i + 3]));
 }
 
 struct ProveResult {
@@ -384,14 +405,7 @@ inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code
       positions_by_log[q.first] = cq.positions;
       std::vector<size_t> pos = decommitment_positions(cq.positions, 1);
       fri_pos[q.first] = pos;
-      size_t k = 0;
-      for (size_t p : pos) {  // witness = the coset positions the verifier cannot compute itself
-        while (k < cq.positions.size() && cq.positions[k] < p) k++;
-        if (k < cq.positions.size() && cq.positions[k] == p) continue;
-        uint32_t w[4];
-        for (int c = 0; c < 4; c++) B.read(q.second[c], p, 1, &w[c]);
-        P.fri_proof.first_layer.fri_witness.push_back(q_make(w[0], w[1], w[2], w[3]));
-      }
+      fri_witness(B, q.second, cq.positions, pos, P.fri_proof.first_layer.fri_witness);
     }
     std::vector<std::vector<uint32_t>> unused;
     merkle_decommit(B, fri_first, first_cols, fri_pos, unused, P.fri_proof.first_layer.decommitment);
@@ -400,14 +414,7 @@ inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code
     for (auto& L : inner) {
       FriLayerProof lp;
       std::vector<size_t> pos = decommitment_positions(lq.positions, 1);
-      size_t k = 0;
-      for (size_t p : pos) {
-        while (k < lq.positions.size() && lq.positions[k] < p) k++;
-        if (k < lq.positions.size() && lq.positions[k] == p) continue;
-        uint32_t w[4];
-        for (int c = 0; c < 4; c++) B.read(L.eval[c], p, 1, &w[c]);
-        lp.fri_witness.push_back(q_make(w[0], w[1], w[2], w[3]));
-      }
+      fri_witness(B, L.eval, lq.positions, pos, lp.fri_witness);
       std::map<uint32_t, std::vector<size_t>> m{{L.log, pos}};
       std::vector<std::vector<uint32_t>> unused2;
       merkle_decommit(B, L.tree, {L.eval[0], L.eval[1], L.eval[2], L.eval[3]}, m, unused2, lp.decommitment);

@@ -40,6 +40,7 @@ struct EvalTaskHost {  // mirrors ops.cu EvalTask
 };
 int launch_eval_at_point_tasks(const void* d_tasks, uint32_t ntasks, uint32_t total_blocks, QM31* d_partials, QM31* d_work,
                                QM31* d_out, cudaStream_t st);
+int launch_gather(const uint32_t* const* d_src, uint32_t n, uint32_t words, uint32_t* d_out, cudaStream_t st);
 int launch_broadcast16(const uint32_t* src, uint32_t* dst, size_t src_len, cudaStream_t st);
 
 // quotients.cu

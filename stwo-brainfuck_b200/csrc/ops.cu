@@ -323,6 +323,16 @@ int launch_eval_at_point_tasks(const void* d_tasks, uint32_t ntasks, uint32_t to
   return (int)cudaGetLastError();
 }
 
+// decommitment gather: one thread per word
+__global__ void gather_kernel(const uint32_t* const* __restrict__ src, uint32_t n, uint32_t words, uint32_t* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n * words) out[i] = src[i / words][i % words];
+}
+int launch_gather(const uint32_t* const* d_src, uint32_t n, uint32_t words, uint32_t* d_out, cudaStream_t st) {
+  gather_kernel<<<(n * words + 255) / 256, 256, 0, st>>>(d_src, n, words, d_out); g_launch_count++;
+  return (int)cudaGetLastError();
+}
+
 // 16x lane broadcast of a trace column (reference: PackedBaseField::broadcast in every table.rs trace_evaluation).
 __global__ void broadcast16_kernel(const uint32_t* __restrict__ s, uint4* __restrict__ d, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * 4; i += (size_t)gridDim.x * blockDim.x) {
