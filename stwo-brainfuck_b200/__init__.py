@@ -172,8 +172,7 @@ class CudaBackend:
     def profile_report(self) -> dict:
         """{tag: (milliseconds, scopes)} accumulated since the last report."""
         self._lib.sc_ctx_profile_report.restype = ctypes.c_size_t
-        n = self._lib.sc_ctx_profile_report(self._ctx, None, ctypes.c_size_t(0))
-        buf = ctypes.create_string_buffer(1 << 16)
+        buf = ctypes.create_string_buffer(1 << 16)  # one call only: the report clears the records
         self._lib.sc_ctx_profile_report(self._ctx, buf, ctypes.c_size_t(len(buf)))
         out = {}
         for item in buf.value.decode().split(";"):

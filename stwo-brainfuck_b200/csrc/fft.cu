@@ -6,10 +6,16 @@
 // interpolate_columns) and :500,583,723 (commit → evaluate_polynomials).
 //
 // Design (B200-first, not SimdBackend's cache-blocked recursion):
-//  * a transform of log size n is cut into "passes"; a pass moves a tile of 2^K elements HBM→smem once, runs up to
-//    K butterfly layers on it out of registers (radix-16 groups: 4 layers per smem round trip) and writes it back;
-//  * the low pass owns the contiguous bits [0,K); a strided pass owns global bits [L0,L0+k) x 2^c contiguous
-//    elements, so every global access is a 2^c*4-byte run (>= 64 B) issued as 128-bit vector loads/stores;
+//  * a transform of log size n is cut into "passes"; a pass moves a tile of 2^K <= 2^13 elements HBM->smem once (128-bit
+//    loads), runs its butterfly layers out of registers in radix-32/16 rounds (5 or 4 layers per smem round trip) and
+//    writes the tile back;
+//  * the low pass owns the contiguous bits [0,K); a strided pass owns <= 9 higher bits x 16 contiguous words, so every
+//    global access is a 64-byte run;
+//  * everything that shapes addressing (K, round start, radix) is a template parameter: shared-memory accesses are
+//    [base + immediate], twiddles of a round are fetched with 128/64-bit loads (one load serves the circle layer and line
+//    layer 1), and ncu showed the round-1 version spending 13.9 instructions per element-layer against ~6 for the math;
+//  * butterflies are balanced across the two integer pipes: the 64-bit product and the plain additions go to the FMA
+//    pipe (IMAD), shifts/masks/min to the ALU pipe (ncu round 1: ALU 77 %, FMA 22 %);
 //  * columns of one size are batched through blockIdx.y, so concurrent CTAs share twiddle lines in L1/L2;
 //  * the blow-up layers of an LDE (zero high coefficients) are not computed: the first pass reads index & (2^src-1).
 // All values canonical in [0,P) at kernel boundaries.
@@ -39,14 +45,13 @@ __global__ void twiddle_tree_kernel(uint32_t* __restrict__ tw, uint32_t* __restr
   if (tid == total - 1) {
     v = 1u;
   } else {
-    // find level: offsets are total - 2^(R-j) for level j  (sum_{j'<j} 2^(R-j'-1)).
-    size_t rem = total - tid;                       // in (2^(R-j-1), 2^(R-j)]
-    uint32_t lg = 63 - __clzll((unsigned long long)(rem - 1));  // floor(log2(rem-1)), rem>=2
-    uint32_t j = R - 1 - lg;                        // level
-    uint32_t hl = R - j - 1;                        // log of level size
+    size_t rem = total - tid;                                   // in (2^(R-j-1), 2^(R-j)]
+    uint32_t lg = 63 - __clzll((unsigned long long)(rem - 1));  // floor(log2(rem-1)), rem >= 2
+    uint32_t j = R - 1 - lg;                                    // level
+    uint32_t hl = R - j - 1;                                    // log of level size
     uint32_t pos = (uint32_t)(tid - (total - ((size_t)2 << hl)));
     uint32_t i = bitrev32(pos, hl);
-    uint32_t cl = R - j;                            // coset log
+    uint32_t cl = R - j;                                        // coset log
     uint32_t idx = (1u << (29 - cl)) + (uint32_t)(((uint64_t)i << (31 - cl)) & 0x7fffffffu);
     v = point_at_index(idx & 0x7fffffffu).x;
   }
@@ -70,143 +75,208 @@ int launch_twiddle_tree(uint32_t* tw, uint32_t* itw, uint32_t R, cudaStream_t st
   return (int)cudaGetLastError();
 }
 
-// ---------------------------------------------------------------- butterflies
-__device__ __forceinline__ void bfly_fwd(uint32_t& a, uint32_t& b, uint32_t t) {
-  uint32_t m = m_reduce64((uint64_t)b * t);
-  uint32_t a0 = a;
-  a = m_add(a0, m);
-  b = m_sub(a0, m);
+// ---------------------------------------------------------------- butterflies (pipe-balanced)
+// x*1+y on the FMA pipe; `one` is a kernel argument so ptxas keeps the IMAD instead of folding it into an ALU-pipe IADD.
+__device__ __forceinline__ uint32_t fadd(uint32_t x, uint32_t y, uint32_t one) {
+  uint32_t r;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(one), "r"(y));
+  return r;
 }
-__device__ __forceinline__ void bfly_inv(uint32_t& a, uint32_t& b, uint32_t t) {
+// canonical reduction of s in [0, 2P): min(s, s-P)
+__device__ __forceinline__ uint32_t cred(uint32_t s, uint32_t one) { return min(s, fadd(s, 0x80000001u, one)); }  // s + (2^32 - P)
+// b*t mod P for b,t in [0,P): IMAD.WIDE, then (prod >> 31) + (prod & P) in [0, 2P)
+__device__ __forceinline__ uint32_t mulred(uint32_t b, uint32_t t, uint32_t one) {
+  uint64_t pr = (uint64_t)b * t;
+  uint32_t lo = (uint32_t)pr, hi = (uint32_t)(pr >> 32);
+  uint32_t s = fadd(__funnelshift_l(lo, hi, 1), lo & P, one);
+  return cred(s, one);
+}
+__device__ __forceinline__ void bfly_fwd(uint32_t& a, uint32_t& b, uint32_t t, uint32_t one) {
+  uint32_t m = mulred(b, t, one);
   uint32_t a0 = a;
-  a = m_add(a0, b);
-  b = m_reduce64((uint64_t)m_sub(a0, b) * t);
+  a = cred(fadd(a0, m, one), one);
+  uint32_t d = a0 - m;                                  // wraps when a0 < m
+  b = min(d, fadd(d, P, one));
+}
+__device__ __forceinline__ void bfly_inv(uint32_t& a, uint32_t& b, uint32_t t, uint32_t one) {
+  uint32_t a0 = a;
+  a = cred(fadd(a0, b, one), one);
+  uint32_t d = a0 - b;
+  b = mulred(min(d, fadd(d, P, one)), t, one);
 }
 
-__device__ __forceinline__ uint32_t smpad(uint32_t i) { return i + (i >> 5); }
+// ---------------------------------------------------------------- compile-time round partition
+// A pass processes `nbits` consecutive local bits in ceil(nbits/5) register rounds of 3..5 bits.
+__host__ __device__ constexpr int n_rounds(int nbits) { return (nbits + 4) / 5; }
+__host__ __device__ constexpr int round_size(int nbits, int i) { return nbits / n_rounds(nbits) + (i < nbits % n_rounds(nbits) ? 1 : 0); }
+__host__ __device__ constexpr int round_start(int nbits, int i) {
+  int s = 0;
+  for (int j = 0; j < i; j++) s += round_size(nbits, j);
+  return s;
+}
+constexpr int STRIDED_C = 4;  // contiguous words per row of a strided tile
 
-struct FftPass {
+struct FftArgs {
   const uint32_t* const* src;
   uint32_t* const* dst;
   const uint32_t* twend;  // one past the end of the (i)twiddle buffer
   uint32_t n;             // transform log size
-  uint32_t src_log;       // loads read index & (2^src_log - 1); forward layers >= src_log are identity-duplications
-  uint32_t K, c, L0;      // tile: 2^c contiguous x 2^(K-c) rows at stride 2^L0
-  uint32_t lb_lo;         // first local bit whose layer this pass computes
+  uint32_t src_log;       // loads read index & (2^src_log - 1); forward layers >= src_log are copies (zero-padded coeffs)
+  uint32_t L0;            // strided pass: global bit of local bit STRIDED_C
   uint32_t scale;         // multiply on store (inverse normalisation), 1 = none
+  uint32_t one;           // runtime 1 (see fadd)
 };
 
-// Twiddle of layer l (>=1) at index h / circle layer 0 derived from line layer 1: [x,y] -> [y,-y,-x,x].
-__device__ __forceinline__ uint32_t line_tw(const FftPass& p, uint32_t l, uint32_t h) {
-  return __ldg(p.twend - ((size_t)1 << (p.n - l)) + h);
-}
-__device__ __forceinline__ uint32_t circle_tw(const FftPass& p, uint32_t h) {
-  const uint32_t* l1 = p.twend - ((size_t)1 << (p.n - 1));
-  uint32_t pair = (h >> 2) * 2;
-  uint32_t x = __ldg(l1 + pair), y = __ldg(l1 + pair + 1);
-  uint32_t s = h & 3u;
-  uint32_t v = (s < 2) ? y : x;
-  return (s == 1 || s == 2) ? (P - v) : v;  // twiddles are never 0
-}
-
-template <bool INV, int R>
-__device__ __forceinline__ void radix_round(const FftPass& p, uint32_t* sm, uint32_t b, uint32_t gbase) {
-  const uint32_t K = p.K, c = p.c, L0 = p.L0;
-  const uint32_t gb0 = (b < c) ? b : L0 + (b - c);  // global bit of local bit b (round never straddles c unless L0==c)
-  constexpr uint32_t M = 1u << R;
-  for (uint32_t q = threadIdx.x; q < (1u << (K - R)); q += blockDim.x) {
-    uint32_t low = q & ((1u << b) - 1u), high = q >> b;
-    uint32_t li0 = low | (high << (b + R));
-    uint32_t g0 = gbase | (li0 & ((1u << c) - 1u)) | ((li0 >> c) << L0);
+// One register round over local bits [B, B+R) of a 2^K tile.  gb = global bit of local bit B; T = tile index bits above the tile.
+template <bool INV, int K, int B, int R, bool CIRCLE>
+__device__ __forceinline__ void fft_round(uint32_t* __restrict__ sm, const FftArgs& a, uint32_t T, uint32_t gb) {
+  constexpr int M = 1 << R;
+  constexpr int NG = 1 << (K - R);
+  const uint32_t one = a.one;
+  for (int q = threadIdx.x; q < NG; q += blockDim.x) {
+    const uint32_t low = q & ((1u << B) - 1u), high = (uint32_t)q >> B;
+    const uint32_t li0 = low | (high << (B + R));
+    uint32_t* p = sm + li0 + (li0 >> 5);
     uint32_t v[M];
 #pragma unroll
-    for (uint32_t m = 0; m < M; m++) v[m] = sm[smpad(li0 | (m << b))];
+    for (int m = 0; m < M; m++) v[m] = p[(m << B) + ((m << B) >> 5)];
+    const uint32_t H = (T << (K - B - R)) | high;
+    // CIRCLE (low pass, B == 0): line layer 1's 2^(R-2) twiddles also define the 2^(R-1) circle twiddles: [x,y] -> [y,-y,-x,x]
+    uint32_t w1[CIRCLE ? (M / 4) : 1];
+    if (CIRCLE) {
+      const uint32_t* l1 = a.twend - ((size_t)1 << (a.n - 1)) + ((size_t)H << (R - 2));
+      if (R >= 4) {
+#pragma unroll
+        for (int i = 0; i < M / 16; i++) {
+          uint4 x = __ldg(reinterpret_cast<const uint4*>(l1) + i);
+          w1[4 * i] = x.x; w1[4 * i + 1] = x.y; w1[4 * i + 2] = x.z; w1[4 * i + 3] = x.w;
+        }
+      } else {
+        uint2 x = __ldg(reinterpret_cast<const uint2*>(l1));
+        w1[0] = x.x; w1[1] = x.y;
+      }
+    }
 #pragma unroll
     for (int ss = 0; ss < R; ss++) {
       const int s = INV ? ss : (R - 1 - ss);
-      const uint32_t l = gb0 + s;
-      if (!INV && l >= p.src_log) continue;  // zero-padded coefficients: (v0, 0) -> (v0, v0), done by the load
-      const uint32_t hbase = g0 >> (l + 1);
+      const uint32_t l = gb + s;
+      if (!INV && l >= a.src_log) continue;  // (v0, 0) -> (v0, v0): already done by the masked load
+      constexpr int dummy = 0; (void)dummy;
+      const int NT = M >> (s + 1);           // distinct twiddles of this layer in the group
+      uint32_t tw[M / 2];
+      if (CIRCLE && s == 0) {
 #pragma unroll
-      for (uint32_t j = 0; j < (M >> (s + 1)); j++) {
-        uint32_t t = (l == 0) ? circle_tw(p, hbase + j) : line_tw(p, l, hbase + j);
+        for (int j = 0; j < M / 2; j++) {
+          uint32_t x = w1[2 * (j >> 2)], y = w1[2 * (j >> 2) + 1];
+          uint32_t t = ((j & 3) < 2) ? y : x;
+          tw[j] = ((j & 3) == 1 || (j & 3) == 2) ? (P - t) : t;
+        }
+      } else if (CIRCLE && s == 1) {
 #pragma unroll
-        for (uint32_t w = 0; w < (1u << s); w++) {
-          uint32_t m0 = (j << (s + 1)) | w, m1 = m0 | (1u << s);
-          if (INV) bfly_inv(v[m0], v[m1], t); else bfly_fwd(v[m0], v[m1], t);
+        for (int j = 0; j < M / 4; j++) tw[j] = w1[j];
+      } else {
+        const uint32_t* base = a.twend - ((size_t)1 << (a.n - l)) + ((size_t)H << (R - 1 - s));
+        if (NT >= 4) {
+#pragma unroll
+          for (int i = 0; i < NT / 4; i++) {
+            uint4 x = __ldg(reinterpret_cast<const uint4*>(base) + i);
+            tw[4 * i] = x.x; tw[4 * i + 1] = x.y; tw[4 * i + 2] = x.z; tw[4 * i + 3] = x.w;
+          }
+        } else if (NT == 2) {
+          uint2 x = __ldg(reinterpret_cast<const uint2*>(base));
+          tw[0] = x.x; tw[1] = x.y;
+        } else {
+          tw[0] = __ldg(base);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NT; j++) {
+#pragma unroll
+        for (int w = 0; w < (1 << s); w++) {
+          const int m0 = (j << (s + 1)) | w, m1 = m0 | (1 << s);
+          if (INV) bfly_inv(v[m0], v[m1], tw[j], one); else bfly_fwd(v[m0], v[m1], tw[j], one);
         }
       }
     }
 #pragma unroll
-    for (uint32_t m = 0; m < M; m++) sm[smpad(li0 | (m << b))] = v[m];
+    for (int m = 0; m < M; m++) p[(m << B) + ((m << B) >> 5)] = v[m];
   }
 }
 
-template <bool INV>
-__global__ void __launch_bounds__(256) fft_pass_kernel(FftPass p) {
+// Runs round I of the pass (ascending bit order); inverse walks I = 0..NR-1, forward NR-1..0.
+template <bool INV, int K, bool LOW, int I>
+__device__ __forceinline__ void run_round(uint32_t* sm, const FftArgs& a, uint32_t T) {
+  constexpr int C0 = LOW ? 0 : STRIDED_C;
+  constexpr int NB = K - C0;
+  constexpr int R = round_size(NB, I);
+  constexpr int B = C0 + round_start(NB, I);
+  const uint32_t gb = LOW ? (uint32_t)B : a.L0 + (uint32_t)(B - STRIDED_C);
+  fft_round<INV, K, B, R, (LOW && B == 0)>(sm, a, T, gb);
+  __syncthreads();
+}
+template <bool INV, int K, bool LOW, int I, int NR>
+struct Rounds {
+  static __device__ __forceinline__ void run(uint32_t* sm, const FftArgs& a, uint32_t T) {
+    run_round<INV, K, LOW, (INV ? I : NR - 1 - I)>(sm, a, T);
+    Rounds<INV, K, LOW, I + 1, NR>::run(sm, a, T);
+  }
+};
+template <bool INV, int K, bool LOW, int NR>
+struct Rounds<INV, K, LOW, NR, NR> {
+  static __device__ __forceinline__ void run(uint32_t*, const FftArgs&, uint32_t) {}
+};
+
+template <bool INV, int K, bool LOW>
+__global__ void __launch_bounds__(256) fft_kernel(FftArgs a) {
   extern __shared__ uint32_t sm[];
-  const uint32_t K = p.K, c = p.c, L0 = p.L0, k = K - c;
+  constexpr int C = LOW ? K : STRIDED_C;
+  const uint32_t L0 = LOW ? (uint32_t)K : a.L0;
   const uint32_t tile = blockIdx.x;
-  const uint32_t nlow = L0 - c;
-  const uint32_t gbase = ((tile & ((1u << nlow) - 1u)) << c) | ((tile >> nlow) << (L0 + k));
-  const uint32_t* __restrict__ src = p.src[blockIdx.y];
-  uint32_t* __restrict__ dst = p.dst[blockIdx.y];
-  const uint32_t smask = (p.src_log >= 32) ? 0xffffffffu : ((1u << p.src_log) - 1u);
-  const uint32_t cm = (1u << c) - 1u;
+  const uint32_t nlow = L0 - C;
+  const uint32_t T = tile >> nlow;
+  const uint32_t gbase = ((tile & ((1u << nlow) - 1u)) << C) | (T << (L0 + K - C));
+  const uint32_t* __restrict__ src = a.src[blockIdx.y];
+  uint32_t* __restrict__ dst = a.dst[blockIdx.y];
+  const uint32_t smask = (a.src_log >= 32) ? 0xffffffffu : ((1u << a.src_log) - 1u);
+  constexpr uint32_t cm = (1u << C) - 1u;
 
   for (uint32_t li = threadIdx.x * 4; li < (1u << K); li += blockDim.x * 4) {
-    uint32_t g = (gbase | (li & cm) | ((li >> c) << L0)) & smask;
+    uint32_t g = (gbase | (li & cm) | ((li >> C) << L0)) & smask;
     uint4 x = __ldg(reinterpret_cast<const uint4*>(src + g));
-    uint32_t o = smpad(li);
+    uint32_t o = li + (li >> 5);
     sm[o] = x.x; sm[o + 1] = x.y; sm[o + 2] = x.z; sm[o + 3] = x.w;
   }
   __syncthreads();
 
-  // rounds over local bits [lb_lo, K), 4 layers at a time; inverse ascends, forward descends.
-  const uint32_t nl = K - p.lb_lo;
-  const uint32_t nr = (nl + 3) / 4;
-  for (uint32_t r = 0; r < nr; r++) {
-    uint32_t b, w;
-    if (INV) { b = p.lb_lo + 4 * r; w = min(4u, K - b); }
-    else { uint32_t top = K - 4 * r; w = min(4u, top - p.lb_lo); b = top - w; }
-    switch (w) {
-      case 4: radix_round<INV, 4>(p, sm, b, gbase); break;
-      case 3: radix_round<INV, 3>(p, sm, b, gbase); break;
-      case 2: radix_round<INV, 2>(p, sm, b, gbase); break;
-      default: radix_round<INV, 1>(p, sm, b, gbase); break;
-    }
-    __syncthreads();
-  }
+  Rounds<INV, K, LOW, 0, n_rounds(LOW ? K : K - STRIDED_C)>::run(sm, a, T);
 
-  const uint32_t scale = p.scale;
+  const uint32_t scale = a.scale;
   for (uint32_t li = threadIdx.x * 4; li < (1u << K); li += blockDim.x * 4) {
-    uint32_t g = gbase | (li & cm) | ((li >> c) << L0);
-    uint32_t o = smpad(li);
+    uint32_t g = gbase | (li & cm) | ((li >> C) << L0);
+    uint32_t o = li + (li >> 5);
     uint4 x = make_uint4(sm[o], sm[o + 1], sm[o + 2], sm[o + 3]);
     if (scale != 1u) { x.x = m_mul(x.x, scale); x.y = m_mul(x.y, scale); x.z = m_mul(x.z, scale); x.w = m_mul(x.w, scale); }
-    else { x.x = x.x == P ? 0 : x.x; x.y = x.y == P ? 0 : x.y; x.z = x.z == P ? 0 : x.z; x.w = x.w == P ? 0 : x.w; }
     *reinterpret_cast<uint4*>(dst + g) = x;
   }
 }
 
 // ---------------------------------------------------------------- host-side pass planner
-static const uint32_t KMAX = 13;  // 2^13 words (+pad) = 33 KB smem per CTA
-static const uint32_t KSTRIDE_MAX = 9, CMIN = 4;
+static const uint32_t KMAX = 13;          // 2^13 words (+pad) = 33 KB smem per CTA
+static const uint32_t KSTRIDE_MAX = 9;    // layers per strided pass (tile 2^(9+4))
 
-struct PassDesc { uint32_t K, c, L0, lb_lo; };
+struct PassDesc { uint32_t K, L0; bool low; };
 
 static int plan_passes(uint32_t n, PassDesc* out) {  // ascending layer order
   int np = 0;
   uint32_t K0 = n < KMAX ? n : KMAX;
-  out[np++] = {K0, K0, K0, 0};
+  out[np++] = {K0, K0, true};
   uint32_t rem = n - K0;
   if (rem) {
     uint32_t ns = (rem + KSTRIDE_MAX - 1) / KSTRIDE_MAX;
     uint32_t L = K0;
     for (uint32_t i = 0; i < ns; i++) {
       uint32_t k = rem / ns + (i < rem % ns ? 1 : 0);
-      uint32_t c = KMAX - k; if (c > 5) c = 5; if (c < CMIN) c = CMIN;
-      out[np++] = {k + c, c, L, c};
+      out[np++] = {k + STRIDED_C, L, false};
       L += k;
     }
   }
@@ -216,18 +286,49 @@ static int plan_passes(uint32_t n, PassDesc* out) {  // ascending layer order
 static uint32_t threads_for(uint32_t K) {
   uint32_t t = K >= 12 ? 256u : (K >= 4 ? (1u << (K - 4)) : 1u);
   if (t < 32) t = 32;
-  if (t > 256) t = 256;
   return t;
+}
+
+template <bool INV, int K, bool LOW>
+static int launch_one(const FftArgs& a, dim3 grid, cudaStream_t st) {
+  size_t smem = ((size_t)(1u << K) + ((1u << K) >> 5) + 4) * 4;
+  fft_kernel<INV, K, LOW><<<grid, threads_for(K), smem, st>>>(a); g_launch_count++;
+  return (int)cudaGetLastError();
 }
 
 template <bool INV>
 static int run_pass(const PassDesc& d, const uint32_t* const* src, uint32_t* const* dst, uint32_t ncols, uint32_t n,
                     uint32_t src_log, const uint32_t* twend, uint32_t scale, cudaStream_t st) {
-  FftPass p{src, dst, twend, n, src_log, d.K, d.c, d.L0, d.lb_lo, scale};
+  FftArgs a{src, dst, twend, n, src_log, d.L0, scale, 1u};
   dim3 grid(1u << (n - d.K), ncols);
-  size_t smem = ((size_t)(1u << d.K) + ((1u << d.K) >> 5) + 4) * 4;
-  fft_pass_kernel<INV><<<grid, threads_for(d.K), smem, st>>>(p); g_launch_count++;
-  return (int)cudaGetLastError();
+  if (d.low) {
+    switch (d.K) {
+      case 3: return launch_one<INV, 3, true>(a, grid, st);
+      case 4: return launch_one<INV, 4, true>(a, grid, st);
+      case 5: return launch_one<INV, 5, true>(a, grid, st);
+      case 6: return launch_one<INV, 6, true>(a, grid, st);
+      case 7: return launch_one<INV, 7, true>(a, grid, st);
+      case 8: return launch_one<INV, 8, true>(a, grid, st);
+      case 9: return launch_one<INV, 9, true>(a, grid, st);
+      case 10: return launch_one<INV, 10, true>(a, grid, st);
+      case 11: return launch_one<INV, 11, true>(a, grid, st);
+      case 12: return launch_one<INV, 12, true>(a, grid, st);
+      case 13: return launch_one<INV, 13, true>(a, grid, st);
+    }
+  } else {
+    switch (d.K) {
+      case 5: return launch_one<INV, 5, false>(a, grid, st);
+      case 6: return launch_one<INV, 6, false>(a, grid, st);
+      case 7: return launch_one<INV, 7, false>(a, grid, st);
+      case 8: return launch_one<INV, 8, false>(a, grid, st);
+      case 9: return launch_one<INV, 9, false>(a, grid, st);
+      case 10: return launch_one<INV, 10, false>(a, grid, st);
+      case 11: return launch_one<INV, 11, false>(a, grid, st);
+      case 12: return launch_one<INV, 12, false>(a, grid, st);
+      case 13: return launch_one<INV, 13, false>(a, grid, st);
+    }
+  }
+  return -1;
 }
 
 // In-place interpolate of ncols columns of log size n (device pointer array `cols`).
@@ -243,10 +344,11 @@ int launch_interpolate(uint32_t* const* cols, uint32_t ncols, uint32_t n, const 
   return 0;
 }
 
-// coeffs (log src_log) -> evaluations on the canonic domain of log n = src_log + log_blowup, out of place.
+// coeffs (log src_log) -> evaluations on the canonic domain of log n = src_log + log_blowup (<= 1 here), out of place.
 int launch_evaluate(const uint32_t* const* coeffs, uint32_t* const* out, uint32_t ncols, uint32_t src_log, uint32_t n,
                     const uint32_t* tw_end, cudaStream_t st) {
   if (n < 3 || ncols == 0) return n < 3 ? -1 : 0;
+  if (n - src_log > 1) return -1;  // larger blow-ups are zero-extended by the caller (capi.cu)
   PassDesc pd[8];
   int np = plan_passes(n, pd);
   for (int i = np - 1; i >= 0; i--) {
