@@ -138,7 +138,7 @@ struct OrcBackend : Backend {
       out[i] = sq(orc::eval_at_point(H(polys[i])->v.data(), lg2(H(polys[i])->v.size()), orc::QPt{oq(pts[i].x), oq(pts[i].y)}));
     return out;
   }
-  std::vector<Col> merkle_commit(const std::vector<Col>& cols, Hash& root) override {
+  std::vector<Col> merkle_commit(const std::vector<Col>& cols, Hash* root) override {
     std::vector<const uint32_t*> p;
     std::vector<uint32_t> logs;
     for (Col c : cols) { p.push_back(H(c)->v.data()); logs.push_back(lg2(H(c)->v.size())); }
@@ -146,7 +146,7 @@ struct OrcBackend : Backend {
     orc::merkle_commit(p.data(), logs.data(), cols.size(), layers);
     std::vector<Col> out;
     for (auto& l : layers) out.push_back(new HCol{l});
-    memcpy(root.data(), layers[0].data(), 32);
+    if (root) memcpy(root->data(), layers[0].data(), 32);
     return out;
   }
   std::array<Col, 4> fold_line(const std::array<Col, 4>& src, uint32_t log, sb::QM31 alpha) override {

@@ -358,14 +358,15 @@ class Proof:
             pass
 
 
-def prove_brainfuck(backend: CudaBackend, code: str, stdin: bytes = b"", log_max_rows: int = 24) -> Proof:
+def prove_brainfuck(backend: CudaBackend, code: str, stdin: bytes = b"", log_max_rows: int = 24, overlap_host: bool = True) -> Proof:
     """prove_brainfuck(&Machine) of crates/brainfuck_prover/src/brainfuck_air/mod.rs:471-735: runs the VM on the host and the
-    whole proof on the device behind `backend`."""
+    whole proof on the device behind `backend`.  overlap_host=False builds the host tables before any device work (used by
+    bench.py to time the device path alone); the proof is identical either way."""
     lib = backend._lib
     h = _vp()
     code_b = code.encode() if isinstance(code, str) else code
     rc = lib.sbf_prove(backend._ctx, ctypes.c_char_p(code_b), ctypes.c_char_p(stdin), ctypes.c_size_t(len(stdin)),
-                       ctypes.c_uint32(log_max_rows), ctypes.byref(h))
+                       ctypes.c_uint32(log_max_rows), ctypes.c_uint32(0 if overlap_host else 1), ctypes.byref(h))
     if rc != 0:
         lib.sbf_last_error.restype = ctypes.c_char_p
         raise ProvingError(lib.sbf_last_error().decode())

@@ -50,11 +50,12 @@ struct CudaBackendImpl : Backend {
     ck(sc_eval_at_point(ctx, (sc_col* const*)polys.data(), (uint32_t)polys.size(), (const uint32_t*)pts.data(), (uint32_t*)out.data()));
     return out;
   }
-  std::vector<Col> merkle_commit(const std::vector<Col>& cols, Hash& root) override {
+  std::vector<Col> merkle_commit(const std::vector<Col>& cols, Hash* root) override {
     uint32_t max_log = 0;
     for (Col c : cols) { uint32_t l = 0; while (((size_t)1 << l) < len(c)) l++; max_log = std::max(max_log, l); }
     std::vector<Col> layers(max_log + 1);
-    ck(sc_merkle_commit(ctx, (sc_col* const*)cols.data(), (uint32_t)cols.size(), (sc_col**)layers.data(), nullptr, root.data()));
+    ck(sc_merkle_commit(ctx, (sc_col* const*)cols.data(), (uint32_t)cols.size(), (sc_col**)layers.data(), nullptr,
+                        root ? root->data() : nullptr));
     return layers;
   }
   std::array<Col, 4> fold_line(const std::array<Col, 4>& src, uint32_t log, QM31 alpha) override {
@@ -111,7 +112,8 @@ const char* sbf_last_error(void) { return g_sbf_err.c_str(); }
 
 // `brainfuck_prover prove --code <code>` with stdin bytes `input`: run the VM on the host, prove on the device.
 // log_max_rows = LOG_MAX_ROWS (24; 20 in the reference's tests).  Returns 0 or SC_EPROOF.
-int32_t sbf_prove(sc_ctx* ctx, const char* code, const uint8_t* input, size_t input_len, uint32_t log_max_rows, sbf_proof** out) {
+int32_t sbf_prove(sc_ctx* ctx, const char* code, const uint8_t* input, size_t input_len, uint32_t log_max_rows, uint32_t flags,
+                  sbf_proof** out) {
   try {
     if (!ctx || !code || !out) throw std::runtime_error("null argument");
     auto t0 = std::chrono::steady_clock::now();
@@ -122,6 +124,7 @@ int32_t sbf_prove(sc_ctx* ctx, const char* code, const uint8_t* input, size_t in
     CudaBackendImpl B(ctx);
     ProverConfig cfg;
     cfg.log_max_rows = log_max_rows;
+    cfg.overlap_host = !(flags & 1u);  // SBF_NO_OVERLAP: build the tables before any device work (bench.py's device-path timing)
     auto t1 = std::chrono::steady_clock::now();
     ProveResult r = prove_brainfuck(B, program, vm.trace, cfg, [&] { sc_ctx_sync(ctx); });
     double prove_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();

@@ -37,7 +37,8 @@ struct Backend {
   virtual std::vector<Col> evaluate(const std::vector<Col>& coeffs, uint32_t log_blowup) = 0;
   virtual std::vector<QM31> eval_at_point(const std::vector<Col>& polys, const std::vector<QPoint>& pts) = 0;
   // MerkleOps: layers[k] = layer of log size k
-  virtual std::vector<Col> merkle_commit(const std::vector<Col>& cols, Hash& root) = 0;
+  // root == nullptr: enqueue only (the caller reads layers[0] later), so the host can overlap other work
+  virtual std::vector<Col> merkle_commit(const std::vector<Col>& cols, Hash* root) = 0;
   // FriOps
   virtual std::array<Col, 4> fold_line(const std::array<Col, 4>& src, uint32_t log, QM31 alpha) = 0;
   virtual void fold_circle_into_line(const std::array<Col, 4>& dst, const std::array<Col, 4>& src, uint32_t log, QM31 alpha) = 0;

@@ -205,24 +205,30 @@ inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code
   std::vector<CommitTree> trees;
   auto commit_tree = [&](CommitTree& t) {  // TreeBuilder::commit -> CommitmentTreeProver::new
     t.evals = B.evaluate(t.polys, cfg.log_blowup);
-    t.layers = B.merkle_commit(t.evals, t.root);
+    t.layers = B.merkle_commit(t.evals, &t.root);
     ch.mix_root(t.root);
   };
   lap("twiddles");
 
-  // ---- phase 0: preprocessed trace (mod.rs:493-500)
+  // ---- phase 0: preprocessed trace (mod.rs:493-500).  With cfg.overlap_host the device work of this phase is only
+  // enqueued here; the host builds the 13 tables meanwhile and the root is read back (and mixed) afterwards — the
+  // transcript order is unchanged.
+  std::vector<Table> tables;
+  if (!cfg.overlap_host) { tables = build_tables(vm_trace, code); lap("tables(host)"); }
   {
     CommitTree t;
     for (uint32_t lg = cfg.log_max_rows; lg >= LOG_N_LANES; lg--) { t.polys.push_back(B.gen_is_first(lg)); t.logs.push_back(lg); }
     B.interpolate(t.polys);
-    commit_tree(t);
+    t.evals = B.evaluate(t.polys, cfg.log_blowup);
+    t.layers = B.merkle_commit(t.evals, nullptr);
+    if (cfg.overlap_host) { tables = build_tables(vm_trace, code); R.times.ms.push_back({"tables(host)", 0}); lap("tables(host)+preprocessed"); }
+    B.read(t.layers[0], 0, 8, t.root.data());
+    ch.mix_root(t.root);
     trees.push_back(std::move(t));
   }
   lap("preprocessed");
 
   // ---- phase 1: main trace (mod.rs:506-583).  Host builds the tables; one value per table row crosses to the device.
-  std::vector<Table> tables = build_tables(vm_trace, code);
-  lap("tables(host)");
   std::vector<std::vector<Col>> compact(N_COMPONENTS);
   {
     CommitTree t;
@@ -355,7 +361,7 @@ inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code
   CommitTree fri_first;
   std::vector<Col> first_cols;
   for (auto& q : quotients) for (Col x : q.second) first_cols.push_back(x);
-  fri_first.layers = B.merkle_commit(first_cols, fri_first.root);
+  fri_first.layers = B.merkle_commit(first_cols, &fri_first.root);
   ch.mix_root(fri_first.root);
   QM31 circle_alpha = ch.draw_felt();
   struct InnerLayer { std::array<Col, 4> eval; uint32_t log; CommitTree tree; };
@@ -367,7 +373,7 @@ inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code
   while (line_log > last_log) {
     while (qi < quotients.size() && quotients[qi].first - 1 == line_log) { B.fold_circle_into_line(layer, quotients[qi].second, quotients[qi].first, circle_alpha); qi++; }
     InnerLayer L{layer, line_log, {}};
-    L.tree.layers = B.merkle_commit({layer[0], layer[1], layer[2], layer[3]}, L.tree.root);
+    L.tree.layers = B.merkle_commit({layer[0], layer[1], layer[2], layer[3]}, &L.tree.root);
     ch.mix_root(L.tree.root);
     QM31 alpha = ch.draw_felt();
     layer = B.fold_line(layer, line_log, alpha);

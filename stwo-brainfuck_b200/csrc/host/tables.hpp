@@ -4,6 +4,8 @@
 // processor/instructions/{table.rs,jump/table.rs,end_of_execution/table.rs} — cited per function.
 #pragma once
 #include <algorithm>
+#include <string>
+#include <thread>
 #include "air_ids.hpp"
 #include "vm.hpp"
 
@@ -166,16 +168,30 @@ inline Table eoe_table(const std::vector<Registers>& regs) {
   return finish(std::move(c));
 }
 
+inline Table build_table(int k, const std::vector<Registers>& regs, const std::vector<uint32_t>& code) {
+  switch (k) {
+    case MEMORY: return memory_table(regs);
+    case INSTRUCTION: return instruction_table(regs, code);
+    case PROGRAM: return program_table(code);
+    case PROCESSOR: return processor_table(regs);
+    case JNZ: return jump_table(regs, ']');
+    case JZ: return jump_table(regs, '[');
+    case EOE: return eoe_table(regs);
+    default: return instruction_op_table(regs, opcode_of(k));
+  }
+}
+
+// The 13 tables are independent: one host thread each (the reference builds them one after the other, mod.rs:511-547).
 inline std::vector<Table> build_tables(const std::vector<Registers>& regs, const std::vector<uint32_t>& code) {
   std::vector<Table> t(N_COMPONENTS);
-  t[MEMORY] = memory_table(regs);
-  t[INSTRUCTION] = instruction_table(regs, code);
-  t[PROGRAM] = program_table(code);
-  t[PROCESSOR] = processor_table(regs);
-  t[JNZ] = jump_table(regs, ']');
-  t[JZ] = jump_table(regs, '[');
-  for (int k : {INPUT, LEFT, MINUS, OUTPUT, PLUS, RIGHT}) t[k] = instruction_op_table(regs, opcode_of(k));
-  t[EOE] = eoe_table(regs);
+  std::vector<std::string> err(N_COMPONENTS);
+  std::vector<std::thread> th;
+  for (int k = 0; k < N_COMPONENTS; k++)
+    th.emplace_back([&, k] {
+      try { t[k] = build_table(k, regs, code); } catch (const std::exception& e) { err[k] = e.what(); }
+    });
+  for (auto& x : th) x.join();
+  for (auto& e : err) if (!e.empty()) throw std::runtime_error(e);
   return t;
 }
 
