@@ -256,13 +256,68 @@ def bench_prove(args):
         dist.destroy_process_group()
 
 
+def bench_commit_sharded(args, torch, dist, rank, world, local, pkg, stream, be):
+    """N > 1: ONE fib19 main-trace tree split over the ranks (strong scaling): column-sharded LDE, NCCL all-to-all to row
+    ranges, row-sharded Merkle, sub-roots all-gathered (stwo-brainfuck_b200/sharded.py)."""
+    sharded = importlib.import_module("stwo-brainfuck_b200.sharded")
+    shape = [(max(4, lg - args.scale_down), n, k) for lg, n, k in FIB19]
+    logs = [lg for lg, n, _ in shape for _ in range(n)]
+    tw = be.precompute_twiddles(ROOT_LOG - args.scale_down)
+    owner = sharded.assign_columns(logs, world)
+    owned = {i: np.random.default_rng(0x5EED0000 + i).integers(0, P, size=1 << logs[i], dtype=np.uint32)
+             for i in range(len(logs)) if owner[i] == rank}
+    ops = sharded.CudaShardOps(pkg, be, tw, torch)
+    h2d = sum(v.nbytes for v in owned.values())
+
+    def step():
+        return sharded.sharded_commit(ops, dist, logs, owned, 1)
+
+    for _ in range(args.warmup):
+        root = step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = be.launch_count()
+    with ClockSampler(local) as cs:
+        e0.record(stream)
+        for _ in range(args.steps):
+            root = step()
+        e1.record(stream)
+        torch.cuda.synchronize()
+    dist.barrier()
+    ms = max_over_ranks(torch, dist, world, e0.elapsed_time(e1) / args.steps)
+    roots = [None] * world
+    dist.all_gather_object(roots, root.tolist())
+    assert all(r == roots[0] for r in roots), "ranks disagree on the root"
+    fft_b, merkle_b = commit_bytes(shape)
+    alg = fft_b + merkle_b
+    lde_bytes = sum(4 * (2 << lg) for lg in logs)
+    line = {"metric": "LDE+commit throughput", "value": alg / (ms * 1e-3) / 1e9, "unit": "GB/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u32 (M31)", "data": "synthetic",
+            "config": {"workload": "fib19_commit", "columns": len(logs), "log_blowup": 1, "scale_down": args.scale_down,
+                       "parallelism": f"column-sharded LDE -> all_to_all -> row-sharded Merkle x{world}",
+                       "all_to_all_bytes_per_rank": int(lde_bytes * (world - 1) / world / world),
+                       "note": "timed region includes the H2D upload of each rank's columns (host-resident inputs)"},
+            "e2e": {"value": alg / (ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 32},
+            "gpu_launches": int(be.launch_count() - l0), "root": bytes(np.array(root, dtype=np.uint32)).hex(),
+            "clocks": cs.summary()}
+    if rank == 0:
+        print(json.dumps(line))
+    be.close()
+    dist.destroy_process_group()
+
+
 def bench_commit(args):
     torch, dist, rank, world, local, pkg, stream, be = setup(args)
+    if world > 1:
+        return bench_commit_sharded(args, torch, dist, rank, world, local, pkg, stream, be)
     shape = [(max(4, lg - args.scale_down), n, k) for lg, n, k in FIB19]
     tw = be.precompute_twiddles(ROOT_LOG - args.scale_down)
-    rng = np.random.default_rng(0x5EED0000 + rank)
-    host = [torch.from_numpy(rng.integers(0, P, size=1 << lg, dtype=np.int64).astype(np.int32)).pin_memory()
-            for lg, n, _ in shape for _ in range(n)]
+    logs = [lg for lg, n, _ in shape for _ in range(n)]
+    host = [torch.from_numpy(np.random.default_rng(0x5EED0000 + i).integers(0, P, size=1 << lg, dtype=np.uint32).view(np.int32)).pin_memory()
+            for i, lg in enumerate(logs)]   # same per-column seeds as the sharded arm: the roots must agree
     h2d = sum(t.numel() * 4 for t in host)
     resident = [be.column(t.numpy().view(np.uint32)) for t in host]
 
@@ -318,7 +373,8 @@ def bench_commit(args):
                        "scale_down": args.scale_down, "l2": "inputs (1 GB per step) exceed L2", "parallelism": f"replicas x{world}"},
             "e2e": {"value": world * alg / (ms_e2e * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 32},
-            "gpu_launches": int(launches), "kernel_ms_per_step": kern, "roofline": roof, "clocks": cs.summary()}
+            "gpu_launches": int(launches), "kernel_ms_per_step": kern, "roofline": roof, "clocks": cs.summary(),
+            "root": bytes(np.array(root, dtype=np.uint32)).hex()}
     if rank == 0:
         print(json.dumps(line))
     be.close()

@@ -55,6 +55,9 @@ int32_t sc_col_clone(sc_ctx* ctx, const sc_col* col, sc_col** out);
 int32_t sc_col_free(sc_ctx* ctx, sc_col* col);
 uint64_t sc_col_len(const sc_col* col);
 void* sc_col_device_ptr(sc_col* col);
+/* Non-owning column over caller-owned device memory (a torch tensor, an NCCL receive buffer); sc_col_free only drops
+ * the handle.  Used by the multi-GPU path to hash row ranges received by all-to-all without another copy. */
+int32_t sc_col_wrap(sc_ctx* ctx, void* device_ptr, uint64_t len, sc_col** out);
 /* Expands `src` (len L) to len 16*L with every value repeated 16x — the reference's PackedBaseField broadcast
  * (crates/brainfuck_prover/src/components/processor/table.rs:86-100), so only 1/16 of a trace column crosses PCIe. */
 int32_t sc_col_broadcast16(sc_ctx* ctx, const sc_col* src, sc_col** out);

@@ -60,7 +60,7 @@ def load_library() -> ctypes.CDLL:
 ABI_SYMBOLS = [
     "sc_last_error", "sc_version", "sc_ctx_create", "sc_ctx_destroy", "sc_ctx_sync", "sc_ctx_launch_count",
     "sc_col_zeros", "sc_col_uninit", "sc_col_from_host", "sc_col_to_host", "sc_col_read", "sc_col_write", "sc_col_clone",
-    "sc_col_free", "sc_col_len", "sc_col_device_ptr", "sc_col_broadcast16", "sc_bit_reverse", "sc_batch_inverse_m31",
+    "sc_col_free", "sc_col_len", "sc_col_device_ptr", "sc_col_wrap", "sc_col_broadcast16", "sc_bit_reverse", "sc_batch_inverse_m31",
     "sc_batch_inverse_qm31", "sc_precompute_twiddles", "sc_twiddles_free", "sc_twiddles_to_host", "sc_interpolate",
     "sc_evaluate", "sc_eval_at_point", "sc_merkle_commit_layer", "sc_merkle_commit", "sc_fold_line",
     "sc_fold_circle_into_line", "sc_accumulate_quotients", "sc_accumulate", "sc_secure_powers", "sc_grind",
@@ -197,6 +197,14 @@ class CudaBackend:
         h = _vp()
         self._ck(self._lib.sc_col_zeros(self._ctx, ctypes.c_uint64(n), ctypes.byref(h)))
         return Column(self, h)
+
+    def wrap(self, device_ptr: int, n: int, keepalive=None) -> Column:
+        """Non-owning Column over device memory owned by someone else (torch tensor, NCCL buffer); sc_col_wrap."""
+        h = _vp()
+        self._ck(self._lib.sc_col_wrap(self._ctx, _vp(device_ptr), ctypes.c_uint64(n), ctypes.byref(h)))
+        c = Column(self, h)
+        c._keepalive = keepalive
+        return c
 
     def broadcast16(self, col: Column) -> Column:
         h = _vp()

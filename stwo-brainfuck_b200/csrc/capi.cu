@@ -18,6 +18,7 @@ namespace sb { unsigned long long g_launch_count = 0; }
 struct sc_col {
   uint32_t* d;
   uint64_t len;
+  bool owned = true;  // false: a view over caller-owned device memory (sc_col_wrap)
 };
 struct sc_twiddles {
   uint32_t root_log;
@@ -215,8 +216,17 @@ int32_t sc_col_free(sc_ctx* ctx, sc_col* col) {
   if (!col) return SC_OK;
   if (!ctx) return fail(SC_EINVAL, "null context");
   cudaSetDevice(ctx->device);
-  cudaFreeAsync(col->d, ctx->st);
+  if (col->owned) cudaFreeAsync(col->d, ctx->st);
   delete col;
+  return SC_OK;
+}
+// Non-owning column over caller-owned device memory (e.g. a torch tensor or an NCCL receive buffer); 16-byte aligned.
+int32_t sc_col_wrap(sc_ctx* ctx, void* device_ptr, uint64_t len, sc_col** out) {
+  ENTER();
+  if (!device_ptr || !out || ((uintptr_t)device_ptr & 15)) return fail(SC_EINVAL, "col_wrap: null or misaligned pointer");
+  sc_col* c = new sc_col{(uint32_t*)device_ptr, len};
+  c->owned = false;
+  *out = c;
   return SC_OK;
 }
 uint64_t sc_col_len(const sc_col* col) { return col ? col->len : 0; }

@@ -30,55 +30,82 @@ inline Table finish(std::vector<std::vector<uint32_t>> cols) {
 }
 
 // memory/table.rs:249-318 (sort by (mp,clk), fill clk gaps with dummies, pad) and :85-117 (pair with next, extra dummy)
+// Stable order of the trace by `key` then clk.  The VM emits rows in clk order, so a counting sort on the key is the
+// reference's `sort_by_key(|x| (x.key, x.clk))`; falls back to std::stable_sort for huge key ranges.
+template <class KeyFn>
+inline std::vector<uint32_t> order_by_key(size_t n, uint32_t max_key, KeyFn key) {
+  std::vector<uint32_t> idx(n);
+  if (max_key < (1u << 22)) {
+    std::vector<uint32_t> cnt((size_t)max_key + 2, 0);
+    for (size_t i = 0; i < n; i++) cnt[key(i) + 1]++;
+    for (size_t k = 1; k < cnt.size(); k++) cnt[k] += cnt[k - 1];
+    for (size_t i = 0; i < n; i++) idx[cnt[key(i)]++] = (uint32_t)i;
+  } else {
+    for (size_t i = 0; i < n; i++) idx[i] = (uint32_t)i;
+    std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return key(a) < key(b); });
+  }
+  return idx;
+}
+
 inline Table memory_table(const std::vector<Registers>& regs) {
-  struct E { uint32_t clk, mp, mv, d; };
-  std::vector<E> src;
-  for (auto& r : regs) src.push_back({r.clk, r.mp, r.mv, 0});
-  std::stable_sort(src.begin(), src.end(), [](const E& a, const E& b) { return a.mp != b.mp ? a.mp < b.mp : a.clk < b.clk; });
-  std::vector<E> t;
-  if (!src.empty()) {
-    const E* prev = &src[0];
-    for (auto& e : src) {
-      uint32_t next_clk = sb::m_add(prev->clk, 1);
-      if (e.mp == prev->mp && e.clk > next_clk)
-        for (uint32_t clk = next_clk; clk < e.clk; clk++) t.push_back({clk, prev->mp, prev->mv, 1});
-      t.push_back(e);
-      prev = &e;
-    }
+  if (regs.empty()) throw std::runtime_error("empty trace");
+  for (size_t i = 1; i < regs.size(); i++)
+    if (regs[i].clk <= regs[i - 1].clk) throw std::runtime_error("trace is not in clk order");
+  uint32_t max_mp = 0;
+  for (auto& r : regs) max_mp = std::max(max_mp, r.mp);
+  std::vector<uint32_t> ord = order_by_key(regs.size(), max_mp, [&](size_t i) { return regs[i].mp; });
+  // rows after gap filling: per mp run, last.clk - first.clk + 1
+  size_t rows = 0;
+  for (size_t k = 0; k < ord.size(); k++) {
+    const Registers& e = regs[ord[k]];
+    if (k && regs[ord[k - 1]].mp == e.mp) rows += e.clk - regs[ord[k - 1]].clk; else rows += 1;
   }
-  if (t.empty()) throw std::runtime_error("empty trace");
-  E last = t.back();
-  size_t pad = next_pow2(t.size()) - t.size();
-  for (uint32_t i = 1; i <= pad; i++) t.push_back({sb::m_add(last.clk, i), last.mp, last.mv, 1});
-  last = t.back();
-  t.push_back({sb::m_add(last.clk, 1), last.mp, last.mv, 1});
-  size_t n = t.size() - 1;
+  size_t n = next_pow2(rows);
   std::vector<std::vector<uint32_t>> c(8, std::vector<uint32_t>(n));
-  for (size_t i = 0; i < n; i++) {
-    c[0][i] = t[i].clk; c[1][i] = t[i].mp; c[2][i] = t[i].mv; c[3][i] = t[i].d;
-    c[4][i] = t[i + 1].clk; c[5][i] = t[i + 1].mp; c[6][i] = t[i + 1].mv; c[7][i] = t[i + 1].d;
+  uint32_t *clk = c[0].data(), *mp = c[1].data(), *mv = c[2].data(), *d = c[3].data();
+  size_t w = 0;
+  for (size_t k = 0; k < ord.size(); k++) {
+    const Registers& e = regs[ord[k]];
+    if (k) {
+      const Registers& p = regs[ord[k - 1]];
+      if (p.mp == e.mp)
+        for (uint32_t x = p.clk + 1; x < e.clk; x++) { clk[w] = x; mp[w] = p.mp; mv[w] = p.mv; d[w] = 1; w++; }
+    }
+    clk[w] = e.clk; mp[w] = e.mp; mv[w] = e.mv; d[w] = 0; w++;
   }
+  uint32_t last_clk = clk[w - 1], last_mp = mp[w - 1], last_mv = mv[w - 1];
+  for (uint32_t i = 1; w < n; i++, w++) { clk[w] = sb::m_add(last_clk, i); mp[w] = last_mp; mv[w] = last_mv; d[w] = 1; }
+  for (int k = 0; k < 4; k++) {  // next_* = the following entry; the last row pairs with one more dummy
+    std::copy(c[k].begin() + 1, c[k].end(), c[4 + k].begin());
+  }
+  c[4][n - 1] = sb::m_add(clk[n - 1], 1); c[5][n - 1] = mp[n - 1]; c[6][n - 1] = mv[n - 1]; c[7][n - 1] = 1;
   return finish(std::move(c));
 }
 
 // instruction/table.rs:250-281 (program rows ++ trace rows, stable sort by (ip,clk), pad with dummy(last.ip)) and :85-110
 inline Table instruction_table(const std::vector<Registers>& regs, const std::vector<uint32_t>& code) {
-  struct E { uint32_t ip, ci, ni, d, clk; };
-  std::vector<E> t;
-  for (size_t i = 0; i < code.size(); i++) t.push_back({(uint32_t)i, code[i], i + 1 == code.size() ? 0 : code[i + 1], 0, 0});
-  for (auto& r : regs) t.push_back({r.ip, r.ci, r.ni, 0, r.clk});
-  std::stable_sort(t.begin(), t.end(), [](const E& a, const E& b) { return a.ip != b.ip ? a.ip < b.ip : a.clk < b.clk; });
-  if (t.empty()) throw std::runtime_error("empty trace");
-  uint32_t last_ip = t.back().ip;
-  size_t pad = next_pow2(t.size()) - t.size();
-  for (size_t i = 0; i < pad; i++) t.push_back({last_ip, 0, 0, 1, 0});
-  t.push_back({t.back().ip, 0, 0, 1, 0});
-  size_t n = t.size() - 1;
+  // program rows (clk 0) come first in the concatenation and the trace is in clk order, so a stable sort on ip alone is
+  // the reference's stable sort on (ip, clk)
+  const size_t np = code.size(), total = np + regs.size();
+  if (total == 0) throw std::runtime_error("empty trace");
+  for (size_t i = 1; i < regs.size(); i++)
+    if (regs[i].clk <= regs[i - 1].clk) throw std::runtime_error("trace is not in clk order");
+  auto ip_of = [&](size_t i) { return i < np ? (uint32_t)i : regs[i - np].ip; };
+  uint32_t max_ip = 0;
+  for (size_t i = 0; i < total; i++) max_ip = std::max(max_ip, ip_of(i));
+  std::vector<uint32_t> ord = order_by_key(total, max_ip, ip_of);
+  size_t n = next_pow2(total);
   std::vector<std::vector<uint32_t>> c(8, std::vector<uint32_t>(n));
-  for (size_t i = 0; i < n; i++) {
-    c[0][i] = t[i].ip; c[1][i] = t[i].ci; c[2][i] = t[i].ni; c[3][i] = t[i].d;
-    c[4][i] = t[i + 1].ip; c[5][i] = t[i + 1].ci; c[6][i] = t[i + 1].ni; c[7][i] = t[i + 1].d;
+  for (size_t k = 0; k < total; k++) {
+    size_t i = ord[k];
+    if (i < np) { c[0][k] = (uint32_t)i; c[1][k] = code[i]; c[2][k] = i + 1 == np ? 0 : code[i + 1]; }
+    else { const Registers& r = regs[i - np]; c[0][k] = r.ip; c[1][k] = r.ci; c[2][k] = r.ni; }
+    c[3][k] = 0;
   }
+  uint32_t last_ip = c[0][total - 1];
+  for (size_t k = total; k < n; k++) { c[0][k] = last_ip; c[1][k] = 0; c[2][k] = 0; c[3][k] = 1; }
+  for (int k = 0; k < 4; k++) std::copy(c[k].begin() + 1, c[k].end(), c[4 + k].begin());
+  c[4][n - 1] = c[0][n - 1]; c[5][n - 1] = 0; c[6][n - 1] = 0; c[7][n - 1] = 1;
   return finish(std::move(c));
 }
 
