@@ -39,8 +39,9 @@ class CudaShardOps:
     def __init__(self, pkg, backend, twiddles, torch):
         self.pkg, self.be, self.tw, self.torch = pkg, backend, twiddles, torch
 
-    def lde(self, host_cols: List[np.ndarray], log_blowup: int):
-        cols = [self.be.column(h) for h in host_cols]
+    def lde(self, host_cols: List, log_blowup: int):
+        """host_cols: numpy arrays (uploaded here) or device-resident Columns (cloned: interpolate works in place)."""
+        cols = [h.clone() if isinstance(h, self.pkg.Column) else self.be.column(h) for h in host_cols]
         self.be.interpolate_columns(cols, self.tw)
         ldes = self.be.evaluate_polynomials(cols, log_blowup, self.tw)
         return [self.as_tensor(c) for c in ldes]
