@@ -48,6 +48,12 @@ size_t sc_ctx_profile_report(sc_ctx* ctx, char* buf, size_t cap);
 int32_t sc_col_zeros(sc_ctx* ctx, uint64_t len, sc_col** out);
 int32_t sc_col_uninit(sc_ctx* ctx, uint64_t len, sc_col** out);
 int32_t sc_col_from_host(sc_ctx* ctx, const uint32_t* host, uint64_t len, sc_col** out);   /* FromIterator */
+/* Upload without waiting: `host` must stay valid until the next synchronising call; pinned memory (sc_host_arena_alloc)
+ * makes it a true asynchronous DMA.  The reference fills its columns in ordinary host memory (e.g. processor/table.rs:
+ * 86-100); filling them in this arena instead removes the staged pageable copy from the upload. */
+int32_t sc_col_from_host_async(sc_ctx* ctx, const uint32_t* host, uint64_t len, sc_col** out);
+int32_t sc_host_arena_alloc(sc_ctx* ctx, uint64_t bytes, void** out);   /* thread-safe bump allocation, 64-byte aligned */
+int32_t sc_host_arena_reset(sc_ctx* ctx);                               /* releases every allocation, keeps the blocks */
 int32_t sc_col_to_host(sc_ctx* ctx, const sc_col* col, uint32_t* host);                    /* to_cpu */
 int32_t sc_col_read(sc_ctx* ctx, const sc_col* col, uint64_t offset, uint64_t n, uint32_t* host);   /* at */
 int32_t sc_col_write(sc_ctx* ctx, sc_col* col, uint64_t offset, uint64_t n, const uint32_t* host);  /* set */

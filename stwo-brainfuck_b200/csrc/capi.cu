@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -39,6 +40,10 @@ struct sc_ctx {
   struct ProfRec { const char* tag; cudaEvent_t a, b; };
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> ev_pool;
+  // pinned host arena (sc_host_arena_*): blocks are kept for the life of the context and reused after a reset
+  struct ArenaBlock { uint8_t* p; size_t size, used; };
+  std::vector<ArenaBlock> arena;
+  std::mutex arena_mu;
 };
 
 // RAII: brackets the kernels launched in a scope with two events when profiling is on.
@@ -133,6 +138,7 @@ int32_t sc_ctx_destroy(sc_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->st);
   cudaFreeHost(ctx->h_ring);
+  for (auto& b : ctx->arena) cudaFreeHost(b.p);
   cudaFree(ctx->d_ring);
   if (ctx->own_stream) cudaStreamDestroy(ctx->st);
   delete ctx;
@@ -181,6 +187,38 @@ int32_t sc_col_from_host(sc_ctx* ctx, const uint32_t* host, uint64_t len, sc_col
   if (r) return r;
   CK(cudaMemcpyAsync((*out)->d, host, len * 4, cudaMemcpyHostToDevice, ctx->st));
   CK(cudaStreamSynchronize(ctx->st));  // host buffer may be pageable and is not retained
+  return SC_OK;
+}
+// Same as sc_col_from_host but does not wait: `host` must stay valid (and should be pinned, e.g. from sc_host_arena_alloc,
+// for the copy to be a real asynchronous DMA) until the next synchronising call on this context.
+int32_t sc_col_from_host_async(sc_ctx* ctx, const uint32_t* host, uint64_t len, sc_col** out) {
+  ENTER();
+  if (!out || (!host && len)) return fail(SC_EINVAL, "null argument");
+  int32_t r = new_col(ctx, len, out);
+  if (r) return r;
+  CK(cudaMemcpyAsync((*out)->d, host, len * 4, cudaMemcpyHostToDevice, ctx->st));
+  return SC_OK;
+}
+// Pinned host arena owned by the context: thread-safe bump allocation (64-byte aligned); reset releases everything at once
+// but keeps the pinned blocks for the next proof.
+int32_t sc_host_arena_alloc(sc_ctx* ctx, uint64_t bytes, void** out) {
+  if (!ctx || !out) return fail(SC_EINVAL, "null argument");
+  std::lock_guard<std::mutex> lk(ctx->arena_mu);
+  size_t need = (bytes + 63) & ~(size_t)63;
+  for (auto& b : ctx->arena)
+    if (b.used + need <= b.size) { *out = b.p + b.used; b.used += need; return SC_OK; }
+  size_t sz = std::max<size_t>(need, (size_t)64 << 20);
+  uint8_t* p = nullptr;
+  cudaSetDevice(ctx->device);
+  if (cudaMallocHost((void**)&p, sz) != cudaSuccess) { cudaGetLastError(); return fail(SC_ENOMEM, "cudaMallocHost failed"); }
+  ctx->arena.push_back({p, sz, need});
+  *out = p;
+  return SC_OK;
+}
+int32_t sc_host_arena_reset(sc_ctx* ctx) {
+  if (!ctx) return fail(SC_EINVAL, "null context");
+  std::lock_guard<std::mutex> lk(ctx->arena_mu);
+  for (auto& b : ctx->arena) b.used = 0;
   return SC_OK;
 }
 int32_t sc_col_to_host(sc_ctx* ctx, const sc_col* col, uint32_t* host) {
@@ -375,7 +413,7 @@ int32_t sc_eval_at_point(sc_ctx* ctx, sc_col* const* polys, uint32_t n, const ui
     for (int k = 0; k < 28; k++) t.f[k] = q_zero();
     t.f[0] = y;
     for (uint32_t k = 1; k < lg; k++) { t.f[k] = x; x = q_sub(q_mulm(q_sqr(x), 2), q_fromm(1)); }
-    blocks += lg > 11 ? (1u << (lg - 11)) : 1u;
+    blocks += lg > 13 ? (1u << (lg - 13)) : 1u;  // EV_CHUNK_LOG (ops.cu)
   }
   void* dt;
   int32_t r = stage(ctx, tasks.data(), tasks.size() * sizeof(EvalTaskHost), &dt);

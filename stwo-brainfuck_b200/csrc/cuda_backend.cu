@@ -22,6 +22,16 @@ struct CudaBackendImpl : Backend {
   const char* name() const override { return "cuda"; }
 
   Col from_host(const uint32_t* v, size_t n) override { sc_col* c; ck(sc_col_from_host(ctx, v, n, &c)); return c; }
+  Col from_host_async(const uint32_t* v, size_t n) override { sc_col* c; ck(sc_col_from_host_async(ctx, v, n, &c)); return c; }
+  struct PinnedArena : HostArena {
+    sc_ctx* ctx;
+    void* alloc(size_t bytes) override {
+      void* p = nullptr;
+      if (sc_host_arena_alloc(ctx, bytes, &p)) throw std::bad_alloc();
+      return p;
+    }
+  } pinned;
+  HostArena* host_arena() override { pinned.ctx = ctx; sc_host_arena_reset(ctx); return &pinned; }
   Col broadcast16(Col c) override { sc_col* o; ck(sc_col_broadcast16(ctx, h(c), &o)); return o; }
   Col zeros(size_t n) override { sc_col* c; ck(sc_col_zeros(ctx, n, &c)); return c; }
   size_t len(Col c) override { return sc_col_len(h(c)); }

@@ -6,6 +6,7 @@
 #include <vector>
 #include "air.hpp"
 #include "channel.hpp"
+#include "tables.hpp"
 
 namespace sbf {
 
@@ -24,6 +25,10 @@ struct Backend {
   virtual const char* name() const = 0;
   // Column<T>
   virtual Col from_host(const uint32_t* v, size_t n) = 0;
+  // Optional fast upload path: a host arena whose memory the backend can DMA from directly, and an upload that does not
+  // wait (the caller keeps the memory alive until the next synchronising call).
+  virtual HostArena* host_arena() { return nullptr; }
+  virtual Col from_host_async(const uint32_t* v, size_t n) { return from_host(v, n); }
   virtual Col broadcast16(Col c) = 0;
   virtual Col zeros(size_t n) = 0;
   virtual size_t len(Col c) = 0;

@@ -213,6 +213,11 @@ inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code
   // ---- phase 0: preprocessed trace (mod.rs:493-500).  With cfg.overlap_host the device work of this phase is only
   // enqueued here; the host builds the 13 tables meanwhile and the root is read back (and mixed) afterwards — the
   // transcript order is unchanged.
+  struct ArenaGuard {  // tables are built into the backend's host arena (pinned memory on CUDA) and die before it is released
+    HostArena* prev;
+    explicit ArenaGuard(HostArena* a) : prev(current_arena()) { current_arena() = a; }
+    ~ArenaGuard() { current_arena() = prev; }
+  } arena_guard(B.host_arena());
   std::vector<Table> tables;
   if (!cfg.overlap_host) { tables = build_tables(vm_trace, code); lap("tables(host)"); }
   {
@@ -236,7 +241,7 @@ inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code
       proof.log_size[c] = tables[c].log_size;
       if (tables[c].log_size > cfg.log_max_rows) throw std::runtime_error(std::string("component too large: ") + COMPONENT_NAMES[c]);
       for (auto& col : tables[c].cols) {
-        Col cc = B.from_host(col.data(), col.size());
+        Col cc = B.from_host_async(col.data(), col.size());  // `tables` outlives the copies (synchronised by the root read-back)
         compact[c].push_back(cc);
         t.polys.push_back(B.broadcast16(cc));
         t.logs.push_back(tables[c].log_size);

@@ -11,16 +11,40 @@
 
 namespace sbf {
 
+// Table columns can live in a backend-provided host arena (pinned memory in the CUDA backend, so that the upload is a
+// true asynchronous DMA instead of a staged pageable copy).  The arena is installed by the prover around build_tables
+// and the tables' lifetime; without one the columns are ordinary heap vectors.
+struct HostArena {
+  virtual ~HostArena() {}
+  virtual void* alloc(size_t bytes) = 0;  // thread-safe, 64-byte aligned, released wholesale by the owner
+};
+inline HostArena*& current_arena() { static HostArena* a = nullptr; return a; }
+template <class T>
+struct ArenaAlloc {
+  typedef T value_type;
+  ArenaAlloc() = default;
+  template <class U> ArenaAlloc(const ArenaAlloc<U>&) {}
+  T* allocate(size_t n) {
+    if (HostArena* a = current_arena()) return static_cast<T*>(a->alloc(n * sizeof(T)));
+    return static_cast<T*>(::operator new(n * sizeof(T)));
+  }
+  void deallocate(T* p, size_t) { if (!current_arena()) ::operator delete(p); }
+  template <class U> bool operator==(const ArenaAlloc<U>&) const { return true; }
+  template <class U> bool operator!=(const ArenaAlloc<U>&) const { return false; }
+};
+typedef std::vector<uint32_t, ArenaAlloc<uint32_t>> ColVec;
+typedef std::vector<ColVec> ColVecs;
+
 struct Table {
   uint32_t log_size = 0;                    // column log size = log2(rows) + LOG_N_LANES
-  std::vector<std::vector<uint32_t>> cols;  // cols[c][row], rows = 2^(log_size - 4)
+  ColVecs cols;  // cols[c][row], rows = 2^(log_size - 4)
   size_t rows() const { return cols.empty() ? 0 : cols[0].size(); }
 };
 
 inline size_t next_pow2(size_t n) { size_t p = 1; while (p < n) p <<= 1; return p; }
 inline uint32_t ilog2_exact(size_t n) { uint32_t l = 0; while (((size_t)1 << l) < n) l++; return l; }
 
-inline Table finish(std::vector<std::vector<uint32_t>> cols) {
+inline Table finish(ColVecs cols) {
   Table t;
   size_t rows = cols[0].size();
   if (rows == 0 || (rows & (rows - 1))) throw std::runtime_error("table length must be a non-zero power of two");
@@ -61,7 +85,7 @@ inline Table memory_table(const std::vector<Registers>& regs) {
     if (k && regs[ord[k - 1]].mp == e.mp) rows += e.clk - regs[ord[k - 1]].clk; else rows += 1;
   }
   size_t n = next_pow2(rows);
-  std::vector<std::vector<uint32_t>> c(8, std::vector<uint32_t>(n));
+  ColVecs c(8, ColVec(n));
   uint32_t *clk = c[0].data(), *mp = c[1].data(), *mv = c[2].data(), *d = c[3].data();
   size_t w = 0;
   for (size_t k = 0; k < ord.size(); k++) {
@@ -95,7 +119,7 @@ inline Table instruction_table(const std::vector<Registers>& regs, const std::ve
   for (size_t i = 0; i < total; i++) max_ip = std::max(max_ip, ip_of(i));
   std::vector<uint32_t> ord = order_by_key(total, max_ip, ip_of);
   size_t n = next_pow2(total);
-  std::vector<std::vector<uint32_t>> c(8, std::vector<uint32_t>(n));
+  ColVecs c(8, ColVec(n));
   for (size_t k = 0; k < total; k++) {
     size_t i = ord[k];
     if (i < np) { c[0][k] = (uint32_t)i; c[1][k] = code[i]; c[2][k] = i + 1 == np ? 0 : code[i + 1]; }
@@ -114,7 +138,7 @@ inline Table program_table(const std::vector<uint32_t>& code) {
   size_t n0 = code.size();
   if (n0 == 0) throw std::runtime_error("empty program");
   size_t n = next_pow2(n0);
-  std::vector<std::vector<uint32_t>> c(4, std::vector<uint32_t>(n, 0));
+  ColVecs c(4, ColVec(n, 0));
   for (size_t i = 0; i < n; i++) {
     if (i < n0) { c[0][i] = (uint32_t)i; c[1][i] = code[i]; c[2][i] = i + 1 == n0 ? 0 : code[i + 1]; c[3][i] = 0; }
     else { c[0][i] = (uint32_t)(n0 - 1); c[3][i] = 1; }
@@ -134,7 +158,7 @@ inline Table processor_table(const std::vector<Registers>& regs) {
   last = t.back();
   t.push_back({sb::m_add(last.clk, 1), last.ip, 0, 0, 0, 0, 0, 1});
   size_t n = t.size() - 1;
-  std::vector<std::vector<uint32_t>> c(9, std::vector<uint32_t>(n));
+  ColVecs c(9, ColVec(n));
   for (size_t i = 0; i < n; i++) {
     c[0][i] = t[i].clk; c[1][i] = t[i].ip; c[2][i] = t[i].ci; c[3][i] = t[i].ni; c[4][i] = t[i].mp;
     c[5][i] = t[i].mv; c[6][i] = t[i].mvi; c[7][i] = t[i].d; c[8][i] = t[i + 1].clk;
@@ -164,7 +188,7 @@ inline std::vector<PairEntry> pair_entries(const std::vector<Registers>& regs, u
 inline Table instruction_op_table(const std::vector<Registers>& regs, uint32_t op) {
   auto t = pair_entries(regs, op);
   size_t n = t.size() / 2;
-  std::vector<std::vector<uint32_t>> c(11, std::vector<uint32_t>(n));
+  ColVecs c(11, ColVec(n));
   for (size_t i = 0; i < n; i++) {
     const PairEntry &a = t[2 * i], &b = t[2 * i + 1];
     c[0][i] = a.clk; c[1][i] = a.ip; c[2][i] = a.ci; c[3][i] = a.ni; c[4][i] = a.mp; c[5][i] = a.mv; c[6][i] = a.mvi;
@@ -176,7 +200,7 @@ inline Table instruction_op_table(const std::vector<Registers>& regs, uint32_t o
 inline Table jump_table(const std::vector<Registers>& regs, uint32_t op) {
   auto t = pair_entries(regs, op);
   size_t n = t.size() / 2;
-  std::vector<std::vector<uint32_t>> c(13, std::vector<uint32_t>(n));
+  ColVecs c(13, ColVec(n));
   for (size_t i = 0; i < n; i++) {
     const PairEntry &a = t[2 * i], &b = t[2 * i + 1];
     c[0][i] = a.clk; c[1][i] = a.ip; c[2][i] = a.ci; c[3][i] = a.ni; c[4][i] = a.mp; c[5][i] = a.mv; c[6][i] = a.mvi;
@@ -191,7 +215,7 @@ inline Table eoe_table(const std::vector<Registers>& regs) {
   for (auto& r : regs) if (r.ci == 0) rows.push_back(&r);
   if (rows.size() != 1) throw std::runtime_error("InvalidEndOfExecution");
   const Registers& r = *rows[0];
-  std::vector<std::vector<uint32_t>> c = {{r.clk}, {r.ip}, {r.ci}, {r.ni}, {r.mp}, {r.mv}, {r.mvi}};
+  ColVecs c = {{r.clk}, {r.ip}, {r.ci}, {r.ni}, {r.mp}, {r.mv}, {r.mvi}};
   return finish(std::move(c));
 }
 
