@@ -240,11 +240,12 @@ def bench_prove(args):
             "warmup": args.warmup, "ms_per_step": dev_s * 1e3, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 (M31)", "data": "fib19.bf (reference example program), 199246 VM steps",
             "config": {"workload": "fib19_prove", "log_max_rows": lmr, "pcs": "pow 5, blowup 2x, 3 queries",
+                       "twiddles": "tree of half_odds(26) cached per context (program-independent); preprocessed tree recomputed every proof",
                        "columns": 213, "lde_cells": proof_lde_cells(FIB19, lmr), "l2": "working set (>20 GB) exceeds L2",
                        "parallelism": f"replicas x{world}", "proofs_per_s_all_gpus": world / dev_s},
             "e2e": {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": proof_len,
                     "includes": "VM run, host table building, uploads, proof, proof readback"},
-            "gpu_launches": int(launches), "stages_ms": stages, "kernel_ms_per_proof": kern, "roofline": roof,
+            "gpu_launches": int(launches // args.steps), "stages_ms": stages, "kernel_ms_per_proof": kern, "roofline": roof,
             "clocks": cs.summary(), "verified": True}
     if rank == 0 and not args.no_cpu_baseline:
         scaled, dt, thr, desc = cpu_prove_sample()

@@ -80,6 +80,8 @@ int32_t sc_batch_inverse_qm31(sc_ctx* ctx, sc_col* const src[4], sc_col* const d
 /* precompute_twiddles(half_odds(root_log)) — crates/brainfuck_prover/src/brainfuck_air/mod.rs:480-484 (root_log 26). */
 int32_t sc_precompute_twiddles(sc_ctx* ctx, uint32_t root_log, sc_twiddles** out);
 int32_t sc_twiddles_free(sc_ctx* ctx, sc_twiddles* tw);
+/* The same tree, computed once per context and returned as a borrowed handle (never pass it to sc_twiddles_free). */
+int32_t sc_twiddles_cached(sc_ctx* ctx, uint32_t root_log, const sc_twiddles** out);
 int32_t sc_twiddles_to_host(sc_ctx* ctx, const sc_twiddles* tw, uint32_t* twiddles, uint32_t* itwiddles);
 /* interpolate_columns: in place, evaluations -> coefficients; columns may have mixed sizes (log >= 3).
  * brainfuck_air/mod.rs:497,550-562,690-702 (tree_builder.extend_evals). */

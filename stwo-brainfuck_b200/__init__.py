@@ -61,7 +61,7 @@ ABI_SYMBOLS = [
     "sc_last_error", "sc_version", "sc_ctx_create", "sc_ctx_destroy", "sc_ctx_sync", "sc_ctx_launch_count",
     "sc_col_zeros", "sc_col_uninit", "sc_col_from_host", "sc_col_from_host_async", "sc_host_arena_alloc", "sc_host_arena_reset", "sc_col_to_host", "sc_col_read", "sc_col_write", "sc_col_clone",
     "sc_col_free", "sc_col_len", "sc_col_device_ptr", "sc_col_wrap", "sc_col_broadcast16", "sc_bit_reverse", "sc_batch_inverse_m31",
-    "sc_batch_inverse_qm31", "sc_precompute_twiddles", "sc_twiddles_free", "sc_twiddles_to_host", "sc_interpolate",
+    "sc_batch_inverse_qm31", "sc_precompute_twiddles", "sc_twiddles_free", "sc_twiddles_cached", "sc_twiddles_to_host", "sc_interpolate",
     "sc_evaluate", "sc_eval_at_point", "sc_merkle_commit_layer", "sc_merkle_commit", "sc_fold_line",
     "sc_fold_circle_into_line", "sc_accumulate_quotients", "sc_accumulate", "sc_secure_powers", "sc_grind",
     "sc_gen_is_first", "sc_prefix_sum_bitrev", "sc_logup_generate", "sc_eval_constraints", "sc_gather", "sc_ctx_profile", "sc_ctx_profile_report",

@@ -44,6 +44,7 @@ struct sc_ctx {
   struct ArenaBlock { uint8_t* p; size_t size, used; };
   std::vector<ArenaBlock> arena;
   std::mutex arena_mu;
+  std::map<uint32_t, sc_twiddles*> tw_cache;  // sc_twiddles_cached
 };
 
 // RAII: brackets the kernels launched in a scope with two events when profiling is on.
@@ -139,6 +140,7 @@ int32_t sc_ctx_destroy(sc_ctx* ctx) {
   cudaStreamSynchronize(ctx->st);
   cudaFreeHost(ctx->h_ring);
   for (auto& b : ctx->arena) cudaFreeHost(b.p);
+  for (auto& kv : ctx->tw_cache) { cudaFree(kv.second->tw); cudaFree(kv.second->itw); delete kv.second; }
   cudaFree(ctx->d_ring);
   if (ctx->own_stream) cudaStreamDestroy(ctx->st);
   delete ctx;
@@ -312,6 +314,21 @@ int32_t sc_precompute_twiddles(sc_ctx* ctx, uint32_t root_log, sc_twiddles** out
   CK(cudaMallocAsync((void**)&t->itw, (size_t)4 << root_log, ctx->st));
   { ProfScope ps_(ctx, "twiddles"); CKL(launch_twiddle_tree(t->tw, t->itw, root_log, ctx->st)); }
   *out = t;
+  return SC_OK;
+}
+// Twiddle tree owned and cached by the context (the tree depends only on root_log): computed on first use, returned as a
+// borrowed handle afterwards, released by sc_ctx_destroy.  Do not pass the handle to sc_twiddles_free.
+int32_t sc_twiddles_cached(sc_ctx* ctx, uint32_t root_log, const sc_twiddles** out) {
+  ENTER();
+  if (!out) return fail(SC_EINVAL, "null out");
+  auto it = ctx->tw_cache.find(root_log);
+  if (it == ctx->tw_cache.end()) {
+    sc_twiddles* t = nullptr;
+    int32_t r = sc_precompute_twiddles(ctx, root_log, &t);
+    if (r) return r;
+    it = ctx->tw_cache.emplace(root_log, t).first;
+  }
+  *out = it->second;
   return SC_OK;
 }
 int32_t sc_twiddles_free(sc_ctx* ctx, sc_twiddles* tw) {

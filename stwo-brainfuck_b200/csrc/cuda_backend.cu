@@ -14,9 +14,9 @@ namespace {
 
 struct CudaBackendImpl : Backend {
   sc_ctx* ctx;
-  sc_twiddles* tw = nullptr;
+  const sc_twiddles* tw = nullptr;
   explicit CudaBackendImpl(sc_ctx* c) : ctx(c) {}
-  ~CudaBackendImpl() override { if (tw) sc_twiddles_free(ctx, tw); }
+  ~CudaBackendImpl() override { if (own_tw) sc_twiddles_free(ctx, own_tw); }
   static void ck(int32_t r) { if (r) throw std::runtime_error(std::string("stwo_cuda: ") + sc_last_error()); }
   static sc_col* h(Col c) { return (sc_col*)c; }
   const char* name() const override { return "cuda"; }
@@ -44,9 +44,15 @@ struct CudaBackendImpl : Backend {
     return out;
   }
 
+  // The tree depends only on root_log: the context computes it once and keeps it (the reference recomputes it per proof,
+  // brainfuck_air/mod.rs:480-484).  cache_twiddles = false restores that behaviour.
+  bool cache_twiddles = true;
+  sc_twiddles* own_tw = nullptr;
   void precompute_twiddles(uint32_t root_log) override {
-    if (tw) { sc_twiddles_free(ctx, tw); tw = nullptr; }
-    ck(sc_precompute_twiddles(ctx, root_log, &tw));
+    if (cache_twiddles) { ck(sc_twiddles_cached(ctx, root_log, &tw)); return; }
+    if (own_tw) sc_twiddles_free(ctx, own_tw);
+    ck(sc_precompute_twiddles(ctx, root_log, &own_tw));
+    tw = own_tw;
   }
   void interpolate(const std::vector<Col>& cols) override { ck(sc_interpolate(ctx, (sc_col* const*)cols.data(), (uint32_t)cols.size(), tw)); }
   std::vector<Col> evaluate(const std::vector<Col>& coeffs, uint32_t log_blowup) override {
@@ -135,6 +141,7 @@ int32_t sbf_prove(sc_ctx* ctx, const char* code, const uint8_t* input, size_t in
     ProverConfig cfg;
     cfg.log_max_rows = log_max_rows;
     cfg.overlap_host = !(flags & 1u);  // SBF_NO_OVERLAP: build the tables before any device work (bench.py's device-path timing)
+    B.cache_twiddles = !(flags & 2u);  // SBF_NO_TWIDDLE_CACHE: recompute the twiddle tree in every proof, as the reference does
     auto t1 = std::chrono::steady_clock::now();
     ProveResult r = prove_brainfuck(B, program, vm.trace, cfg, [&] { sc_ctx_sync(ctx); });
     double prove_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
