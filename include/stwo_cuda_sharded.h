@@ -1,0 +1,54 @@
+/* stwo_cuda_sharded.h — multi-GPU part of the C ABI of libstwo_cuda.so (one process per GPU, one sc_ctx per process).
+ *
+ * The reference is single-process (no collectives, no multi-GPU); these entry points are what the sharded
+ * prover (stwo-brainfuck_b200/csrc/host/prover_sharded.hpp) needs on top of stwo_cuda.h to split one proof over N GPUs the
+ * way BASELINE.json's north_star prescribes: columns for interpolation/extension, one all-to-all per commitment tree into
+ * bit-reversed row ranges, then row-local hashing, constraint evaluation, quotients and FRI folds.
+ * "Range" variants compute rows [row_off, row_off + n) of a domain; column handles passed to them cover exactly that range. */
+#ifndef STWO_CUDA_SHARDED_H
+#define STWO_CUDA_SHARDED_H
+#include "stwo_cuda.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sc_comm sc_comm; /* NCCL communicator (resolved with dlopen("libnccl.so.2")) */
+
+/* rank 0 creates the id, the launcher broadcasts its 128 bytes (e.g. torch.distributed), every rank calls sc_comm_init */
+int32_t sc_comm_unique_id(uint8_t out[128]);
+int32_t sc_comm_init(sc_ctx* ctx, int32_t rank, int32_t world, const uint8_t id[128], sc_comm** out);
+int32_t sc_comm_destroy(sc_ctx* ctx, sc_comm* comm);
+int32_t sc_comm_rank(const sc_comm* comm);
+int32_t sc_comm_world(const sc_comm* comm);
+/* column-shard -> row-shard exchange: per-peer counts in words, blocks laid out in rank order in both buffers */
+int32_t sc_all_to_all(sc_ctx* ctx, sc_comm* comm, const sc_col* send, const uint64_t* send_counts, sc_col* recv, const uint64_t* recv_counts);
+int32_t sc_all_gather(sc_ctx* ctx, sc_comm* comm, const sc_col* send, sc_col* recv, uint64_t n);   /* Merkle sub-roots */
+int32_t sc_allreduce_host_u32(sc_ctx* ctx, sc_comm* comm, uint32_t* buf, uint64_t n);              /* tiny host tables */
+
+int32_t sc_col_copy(sc_ctx* ctx, sc_col* dst, uint64_t dst_off, const sc_col* src, uint64_t src_off, uint64_t n);
+int32_t sc_col_view(sc_ctx* ctx, sc_col* col, uint64_t off, uint64_t n, sc_col** out);   /* non-owning slice, off % 4 == 0 */
+
+/* FriOps on a row range: outputs [out_off, out_off + n_out) of the folded layer; src covers inputs [2*out_off, 2*(out_off+n_out)) */
+int32_t sc_fold_line_range(sc_ctx* ctx, sc_col* const src[4], uint32_t log, uint64_t out_off, uint64_t n_out, const uint32_t alpha[4],
+                           const sc_twiddles* tw, sc_col* dst_out[4]);
+int32_t sc_fold_circle_into_line_range(sc_ctx* ctx, sc_col* const src[4], uint32_t log, uint64_t out_off, uint64_t n_out,
+                                       const uint32_t alpha[4], const sc_twiddles* tw, sc_col* const dst[4]);
+/* QuotientOps on a row range (row_off, n_rows multiples of 4) */
+int32_t sc_accumulate_quotients_range(sc_ctx* ctx, uint32_t log, uint64_t row_off, uint64_t n_rows, sc_col* const* cols, uint32_t n,
+                                      const uint32_t random_coeff[4], const uint32_t* batch_points, const uint32_t* batch_sizes,
+                                      const uint32_t* entry_cols, const uint32_t* entry_vals, uint32_t nb, sc_col* out[4]);
+/* the LDE of a LogUp cumulative column read at coset offset -1, as a column (so it can be re-sharded like the others) */
+int32_t sc_shift_prev(sc_ctx* ctx, const sc_col* col, uint32_t trace_log, sc_col** out);
+int32_t sc_accumulate_col(sc_ctx* ctx, sc_col* dst, const sc_col* src);
+/* LogUp generation materialising only the wanted coordinate columns (no prefix sum; use sc_prefix_sum_bitrev on the owner) */
+int32_t sc_logup_generate_sel(sc_ctx* ctx, int32_t component, sc_col* const* main_cols, uint32_t n_main, uint32_t log_repeat,
+                              const uint32_t* elements, const uint8_t* want, sc_col** out);
+int32_t sc_eval_constraints_range(sc_ctx* ctx, int32_t component, uint32_t log_size, uint64_t row_off, uint64_t n_rows,
+                                  sc_col* const* main_lde, uint32_t n_main, sc_col* const* inter_lde, uint32_t n_inter,
+                                  sc_col* const prev[4], const sc_col* is_first_lde, const uint32_t* elements,
+                                  const uint32_t total_sum[4], const uint32_t* coeffs, sc_col* const accum[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -2,11 +2,17 @@
 //
 // CPU `Backend` for the protocol driver: every device op of the product replaced by the scalar restatements in this
 // directory (own field arithmetic, own FFT/Merkle/quotient/fold loops, own row evaluators).  The driver itself
-// (stwo-brainfuck_b200/csrc/host/{prover,verifier}.hpp) and the AIR definition (host/air.hpp — the restatement of the
-// reference's components/<name>/component.rs `evaluate` bodies) are shared with the product on purpose: they are host
-// logic in the reference too; what this oracle checks is that the CUDA kernels compute the same field elements.
+// (stwo-brainfuck_b200/csrc/host/{prover,prover_sharded,verifier}.hpp) and the AIR definition (host/air.hpp — the
+// restatement of the reference's components/<name>/component.rs `evaluate` bodies) are shared with the product on purpose:
+// they are host logic in the reference too; what this oracle checks is that the CUDA kernels compute the same field elements.
 // Proof parity test: tests/test_prover_gpu.py compares the JSON of both provers byte for byte.
+// The multi-rank entry point (orc_prove_sharded_json) runs the sharded driver on `world` threads with an in-process
+// communicator, so that the N > 1 host logic is testable without GPUs.
+#include <condition_variable>
 #include <memory>
+#include <mutex>
+#include <thread>
+#include "../stwo-brainfuck_b200/csrc/host/prover_sharded.hpp"
 #include "../stwo-brainfuck_b200/csrc/host/verifier.hpp"
 #include "orc_ops.h"
 
@@ -14,7 +20,14 @@ using namespace sbf;
 
 namespace {
 
-struct HCol { std::vector<uint32_t> v; };
+struct HCol {  // host column: owns `store`, or is a view into another column's memory
+  uint32_t* d = nullptr;
+  size_t n = 0;
+  std::vector<uint32_t> store;
+  explicit HCol(size_t len) : n(len), store(len, 0) { d = store.data(); }
+  HCol(const uint32_t* v, size_t len) : n(len), store(v, v + len) { d = store.data(); }
+  HCol(uint32_t* view, size_t len, int) : d(view), n(len) {}
+};
 inline HCol* H(Col c) { return (HCol*)c; }
 inline orc::QM31 oq(const sb::QM31& q) { return orc::qfrom(q.a.a, q.a.b, q.b.a, q.b.b); }
 inline sb::QM31 sq(const orc::QM31& q) { return sb::q_make(q.a.a, q.a.b, q.b.a, q.b.b); }
@@ -40,12 +53,12 @@ struct OrcLogupGen {
   typedef OFm F;
   typedef OFq EF;
   const std::vector<Col>* main;
-  std::vector<HCol*>* out;
+  std::vector<HCol*>* out;  // null entries are not materialised
   const InteractionElements* el;
   size_t row, shift;
   int col = 0, batch = 0;
   orc::QM31 cum = orc::qfromm(0);
-  F next() { return {H((*main)[col++])->v[row >> shift]}; }
+  F next() { return {H((*main)[col++])->d[row >> shift]}; }
   F is_first() { return {0}; }
   F cst(uint32_t c) { return {c}; }
   EF ef(F x) { return {orc::qfromm(x.v)}; }
@@ -55,8 +68,8 @@ struct OrcLogupGen {
   void relation(int rel, EF num, const F* vals, int n) {
     OFq den = ocombine(el->rel[rel], vals, n);
     cum = orc::qadd(cum, orc::qmul(num.v, orc::qinv(den.v)));
-    (*out)[4 * batch]->v[row] = cum.a.a; (*out)[4 * batch + 1]->v[row] = cum.a.b;
-    (*out)[4 * batch + 2]->v[row] = cum.b.a; (*out)[4 * batch + 3]->v[row] = cum.b.b;
+    const uint32_t w[4] = {cum.a.a, cum.a.b, cum.b.a, cum.b.b};
+    for (int k = 0; k < 4; k++) if ((*out)[4 * batch + k]) (*out)[4 * batch + k]->d[row] = w[k];
     batch++;
   }
   void finalize_logup() {}
@@ -66,15 +79,16 @@ struct OrcDomainEval {
   typedef OFm F;
   typedef OFq EF;
   const std::vector<Col>*main, *inter;
+  const std::array<Col, 4>* prev = nullptr;  // pre-shifted last LogUp column (row-range evaluation), else index prev_row
   const uint32_t* is_first_col;
   const InteractionElements* el;
   const std::vector<sb::QM31>* coeff;
   orc::QM31 total;
-  size_t row, prev_row;
+  size_t row, prev_row;  // row indexes the (possibly partial) columns
   int col = 0, k = 0;
   orc::QM31 row_res = orc::qfromm(0);
   LogupState<OrcDomainEval> lg;
-  F next() { return {H((*main)[col++])->v[row]}; }
+  F next() { return {H((*main)[col++])->d[row]}; }
   F is_first() { return {is_first_col[row]}; }
   F cst(uint32_t c) { return {c}; }
   EF ef(F x) { return {orc::qfromm(x.v)}; }
@@ -85,48 +99,70 @@ struct OrcDomainEval {
   void add(EF c) { row_res = orc::qadd(row_res, orc::qmul(oq((*coeff)[k++]), c.v)); }
   void relation(int rel, EF num, const F* vals, int n) { lg.push(num, ocombine(el->rel[rel], vals, n)); }
   EF ext_at(int b, size_t r) {
-    return {orc::qfrom(H((*inter)[4 * b])->v[r], H((*inter)[4 * b + 1])->v[r], H((*inter)[4 * b + 2])->v[r], H((*inter)[4 * b + 3])->v[r])};
+    return {orc::qfrom(H((*inter)[4 * b])->d[r], H((*inter)[4 * b + 1])->d[r], H((*inter)[4 * b + 2])->d[r], H((*inter)[4 * b + 3])->d[r])};
   }
   EF ext_mask_cur(int b) { return ext_at(b, row); }
-  void ext_mask_last(EF& prev, EF& cur) { prev = ext_at(lg.n - 1, prev_row); cur = ext_at(lg.n - 1, row); }
+  void ext_mask_last(EF& pv, EF& cur) {
+    if (prev) pv = {orc::qfrom(H((*prev)[0])->d[row], H((*prev)[1])->d[row], H((*prev)[2])->d[row], H((*prev)[3])->d[row])};
+    else pv = ext_at(lg.n - 1, prev_row);
+    cur = ext_at(lg.n - 1, row);
+  }
   void finalize_logup() { lg.finalize(*this); }
+};
+
+// ---- in-process communicator for the multi-rank tests: `world` threads, one OrcBackend each
+struct ThreadComm {
+  int world;
+  std::mutex mu;
+  std::condition_variable cv;
+  int waiting = 0;
+  long generation = 0;
+  std::vector<const uint32_t*> ptr;
+  std::vector<const std::vector<size_t>*> counts;
+  explicit ThreadComm(int w) : world(w), ptr(w, nullptr), counts(w, nullptr) {}
+  void barrier() {
+    std::unique_lock<std::mutex> lk(mu);
+    long gen = generation;
+    if (++waiting == world) { waiting = 0; generation++; cv.notify_all(); }
+    else cv.wait(lk, [&] { return generation != gen; });
+  }
 };
 
 struct OrcBackend : Backend {
   std::vector<uint32_t> tw, itw;
+  ThreadComm* comm = nullptr;
+  int my_rank = 0;
   const char* name() const override { return "oracle"; }
   static uint32_t lg2(size_t n) { uint32_t l = 0; while (((size_t)1 << l) < n) l++; return l; }
 
-  Col from_host(const uint32_t* v, size_t n) override { return new HCol{std::vector<uint32_t>(v, v + n)}; }
+  Col from_host(const uint32_t* v, size_t n) override { return new HCol(v, n); }
   Col broadcast16(Col c) override {
-    HCol* o = new HCol;
-    o->v.resize(H(c)->v.size() * 16);
-    for (size_t i = 0; i < o->v.size(); i++) o->v[i] = H(c)->v[i >> 4];
+    HCol* o = new HCol(H(c)->n * 16);
+    for (size_t i = 0; i < o->n; i++) o->d[i] = H(c)->d[i >> 4];
     return o;
   }
-  Col zeros(size_t n) override { return new HCol{std::vector<uint32_t>(n, 0)}; }
-  size_t len(Col c) override { return H(c)->v.size(); }
-  void read(Col c, size_t off, size_t n, uint32_t* out) override { memcpy(out, H(c)->v.data() + off, n * 4); }
+  Col zeros(size_t n) override { return new HCol(n); }
+  size_t len(Col c) override { return H(c)->n; }
+  void read(Col c, size_t off, size_t n, uint32_t* out) override { memcpy(out, H(c)->d + off, n * 4); }
   void free_col(Col c) override { delete H(c); }
   std::vector<uint32_t> gather(const std::vector<Col>& cols, const std::vector<size_t>& offsets, uint32_t words) override {
     std::vector<uint32_t> out(cols.size() * words);
-    for (size_t i = 0; i < cols.size(); i++) memcpy(&out[i * words], H(cols[i])->v.data() + offsets[i], words * 4);
+    for (size_t i = 0; i < cols.size(); i++) memcpy(&out[i * words], H(cols[i])->d + offsets[i], words * 4);
     return out;
   }
 
   void precompute_twiddles(uint32_t root_log) override { orc::precompute_twiddles(orc::coset_half_odds(root_log), tw, itw); }
   void interpolate(const std::vector<Col>& cols) override {
 #pragma omp parallel for schedule(dynamic)
-    for (size_t i = 0; i < cols.size(); i++) orc::interpolate(H(cols[i])->v.data(), lg2(H(cols[i])->v.size()), itw);
+    for (size_t i = 0; i < cols.size(); i++) orc::interpolate(H(cols[i])->d, lg2(H(cols[i])->n), itw);
   }
   std::vector<Col> evaluate(const std::vector<Col>& coeffs, uint32_t log_blowup) override {
     std::vector<Col> out(coeffs.size());
 #pragma omp parallel for schedule(dynamic)
     for (size_t i = 0; i < coeffs.size(); i++) {
-      HCol* o = new HCol;
-      o->v = H(coeffs[i])->v;
-      o->v.resize(o->v.size() << log_blowup, 0);  // extend(): zero-pad at the end
-      orc::evaluate(o->v.data(), lg2(o->v.size()), tw);
+      HCol* o = new HCol(H(coeffs[i])->n << log_blowup);  // extend(): zero-pad at the end
+      memcpy(o->d, H(coeffs[i])->d, H(coeffs[i])->n * 4);
+      orc::evaluate(o->d, lg2(o->n), tw);
       out[i] = o;
     }
     return out;
@@ -135,70 +171,195 @@ struct OrcBackend : Backend {
     std::vector<sb::QM31> out(polys.size());
 #pragma omp parallel for schedule(dynamic)
     for (size_t i = 0; i < polys.size(); i++)
-      out[i] = sq(orc::eval_at_point(H(polys[i])->v.data(), lg2(H(polys[i])->v.size()), orc::QPt{oq(pts[i].x), oq(pts[i].y)}));
+      out[i] = sq(orc::eval_at_point(H(polys[i])->d, lg2(H(polys[i])->n), orc::QPt{oq(pts[i].x), oq(pts[i].y)}));
     return out;
   }
   std::vector<Col> merkle_commit(const std::vector<Col>& cols, Hash* root) override {
     std::vector<const uint32_t*> p;
     std::vector<uint32_t> logs;
-    for (Col c : cols) { p.push_back(H(c)->v.data()); logs.push_back(lg2(H(c)->v.size())); }
+    for (Col c : cols) { p.push_back(H(c)->d); logs.push_back(lg2(H(c)->n)); }
     std::vector<std::vector<uint32_t>> layers;
     orc::merkle_commit(p.data(), logs.data(), cols.size(), layers);
     std::vector<Col> out;
-    for (auto& l : layers) out.push_back(new HCol{l});
+    for (auto& l : layers) out.push_back(new HCol(l.data(), l.size()));
     if (root) memcpy(root->data(), layers[0].data(), 32);
     return out;
   }
+  Col commit_layer(uint32_t log, Col prev, const std::vector<Col>& cols) override {
+    std::vector<const uint32_t*> p;
+    for (Col c : cols) p.push_back(H(c)->d);
+    HCol* o = new HCol((size_t)8 << log);
+    orc::commit_on_layer(log, prev ? H(prev)->d : nullptr, p.data(), p.size(), o->d);
+    return o;
+  }
   std::array<Col, 4> fold_line(const std::array<Col, 4>& src, uint32_t log, sb::QM31 alpha) override {
-    std::array<Col, 4> out;
-    const uint32_t* s[4]; uint32_t* d[4];
-    for (int k = 0; k < 4; k++) { out[k] = zeros((size_t)1 << (log - 1)); s[k] = H(src[k])->v.data(); d[k] = H(out[k])->v.data(); }
-    orc::fold_line(s, log, oq(alpha), d);
-    return out;
+    return fold_line_range(src, log, 0, (size_t)1 << (log - 1), alpha);
   }
   void fold_circle_into_line(const std::array<Col, 4>& dst, const std::array<Col, 4>& src, uint32_t log, sb::QM31 alpha) override {
-    const uint32_t* s[4]; uint32_t* d[4];
-    for (int k = 0; k < 4; k++) { s[k] = H(src[k])->v.data(); d[k] = H(dst[k])->v.data(); }
-    orc::fold_circle_into_line(s, log, oq(alpha), d);
+    fold_circle_into_line_range(dst, src, log, 0, (size_t)1 << (log - 1), alpha);
   }
   std::array<Col, 4> accumulate_quotients(uint32_t log, const std::vector<Col>& cols, sb::QM31 rc, const SampleBatchesFlat& b) override {
-    std::array<Col, 4> out;
-    uint32_t* d[4];
-    for (int k = 0; k < 4; k++) { out[k] = zeros((size_t)1 << log); d[k] = H(out[k])->v.data(); }
-    std::vector<const uint32_t*> p;
-    for (Col c : cols) p.push_back(H(c)->v.data());
-    orc::accumulate_quotients(log, p.data(), (uint32_t)p.size(), oq(rc), b.points.data(), b.sizes.data(), b.entry_cols.data(),
-                              b.entry_vals.data(), (uint32_t)b.sizes.size(), d);
-    return out;
+    return accumulate_quotients_range(log, 0, (size_t)1 << log, cols, rc, b);
   }
   void accumulate(const std::array<Col, 4>& dst, const std::array<Col, 4>& src) override {
-    for (int k = 0; k < 4; k++)
-      for (size_t i = 0; i < H(dst[k])->v.size(); i++) H(dst[k])->v[i] = orc::madd(H(dst[k])->v[i], H(src[k])->v[i]);
+    for (int k = 0; k < 4; k++) accumulate_col(dst[k], src[k]);
   }
   uint64_t grind(const Hash& digest, uint32_t pow_bits) override { return orc::grind(digest.data(), pow_bits); }
-  Col gen_is_first(uint32_t log_size) override { HCol* c = (HCol*)zeros((size_t)1 << log_size); c->v[0] = 1; return c; }
+  Col gen_is_first(uint32_t log_size) override { HCol* c = new HCol((size_t)1 << log_size); c->d[0] = 1; return c; }
 
   std::vector<Col> logup_generate(int comp, const std::vector<Col>& main, const InteractionElements& el, sb::QM31& claimed) override {
-    size_t n = H(main[0])->v.size() << LOG_N_LANES;
-    uint32_t log = lg2(n);
-    std::vector<HCol*> out(4 * N_LOGUP_COLS[comp]);
-    for (auto& o : out) o = (HCol*)zeros(n);
+    std::vector<uint8_t> want(4 * N_LOGUP_COLS[comp], 1);
+    std::vector<Col> out = logup_generate_sel(comp, main, el, want);
+    for (int k = 0; k < 4; k++) prefix_sum(out[out.size() - 4 + k]);
+    size_t b = out.size() - 4;
+    claimed = sb::q_make(H(out[b])->d[1], H(out[b + 1])->d[1], H(out[b + 2])->d[1], H(out[b + 3])->d[1]);
+    return out;
+  }
+  void eval_constraints(int comp, uint32_t log_size, const std::vector<Col>& m, const std::vector<Col>& it, Col is_first,
+                        const InteractionElements& el, sb::QM31 total, const std::vector<sb::QM31>& coeffs,
+                        const std::array<Col, 4>& acc) override {
+    eval_rows(comp, log_size, 0, (size_t)2 << log_size, m, it, nullptr, is_first, el, total, coeffs, acc);
+  }
+
+  // ---- multi-rank extension
+  int rank() const override { return my_rank; }
+  int world() const override { return comm ? comm->world : 1; }
+  Col alloc(size_t n) override { return new HCol(n); }
+  Col view(Col c, size_t off, size_t n) override { return new HCol(H(c)->d + off, n, 0); }
+  void copy(Col dst, size_t dst_off, Col src, size_t src_off, size_t n) override { memcpy(H(dst)->d + dst_off, H(src)->d + src_off, n * 4); }
+  void all_to_all(Col send, const std::vector<size_t>& sc, Col recv, const std::vector<size_t>& rc) override {
+    if (!comm) { memcpy(H(recv)->d, H(send)->d, sc[0] * 4); return; }
+    comm->ptr[my_rank] = H(send)->d;
+    comm->counts[my_rank] = &sc;
+    comm->barrier();
+    size_t ro = 0;
+    for (int s = 0; s < comm->world; s++) {
+      size_t so = 0;
+      for (int d = 0; d < my_rank; d++) so += (*comm->counts[s])[d];
+      memcpy(H(recv)->d + ro, comm->ptr[s] + so, rc[s] * 4);
+      ro += rc[s];
+    }
+    comm->barrier();
+  }
+  void all_gather(Col send, Col recv, size_t n) override {
+    if (!comm) { memcpy(H(recv)->d, H(send)->d, n * 4); return; }
+    comm->ptr[my_rank] = H(send)->d;
+    comm->barrier();
+    for (int s = 0; s < comm->world; s++) memcpy(H(recv)->d + s * n, comm->ptr[s], n * 4);
+    comm->barrier();
+  }
+  void allreduce_host(uint32_t* buf, size_t n) override {
+    if (!comm) return;
+    comm->ptr[my_rank] = buf;
+    comm->barrier();
+    std::vector<uint32_t> sum(n, 0);
+    for (int s = 0; s < comm->world; s++) for (size_t i = 0; i < n; i++) sum[i] += comm->ptr[s][i];
+    comm->barrier();
+    memcpy(buf, sum.data(), n * 4);
+    comm->barrier();
+  }
+  // out[i] for i in [off, off+n): fold of inputs 2i, 2i+1 (src holds exactly those 2n inputs)
+  std::array<Col, 4> fold_line_range(const std::array<Col, 4>& src, uint32_t log, size_t off, size_t n_out, sb::QM31 alpha) override {
+    std::array<Col, 4> out;
+    for (int k = 0; k < 4; k++) out[k] = new HCol(n_out);
+    orc::Coset dom = orc::coset_half_odds(log);
+    orc::QM31 al = oq(alpha);
+    for (size_t i = 0; i < n_out; i++) {
+      uint32_t x = dom.at(orc::bit_reverse((uint32_t)(2 * (off + i)), log)).x;
+      orc::QM31 a = orc::qfrom(H(src[0])->d[2 * i], H(src[1])->d[2 * i], H(src[2])->d[2 * i], H(src[3])->d[2 * i]);
+      orc::QM31 b = orc::qfrom(H(src[0])->d[2 * i + 1], H(src[1])->d[2 * i + 1], H(src[2])->d[2 * i + 1], H(src[3])->d[2 * i + 1]);
+      orc::QM31 r = orc::qadd(orc::qadd(a, b), orc::qmul(al, orc::qmulm(orc::qsub(a, b), orc::minv(x))));
+      H(out[0])->d[i] = r.a.a; H(out[1])->d[i] = r.a.b; H(out[2])->d[i] = r.b.a; H(out[3])->d[i] = r.b.b;
+    }
+    return out;
+  }
+  void fold_circle_into_line_range(const std::array<Col, 4>& dst, const std::array<Col, 4>& src, uint32_t log, size_t off, size_t n_out,
+                                   sb::QM31 alpha) override {
+    orc::CircleDomain dom = orc::canonic_domain(log);
+    orc::QM31 al = oq(alpha), a2 = orc::qmul(al, al);
+    for (size_t i = 0; i < n_out; i++) {
+      orc::Pt p = dom.at(orc::bit_reverse((uint32_t)(2 * (off + i)), log));
+      orc::QM31 a = orc::qfrom(H(src[0])->d[2 * i], H(src[1])->d[2 * i], H(src[2])->d[2 * i], H(src[3])->d[2 * i]);
+      orc::QM31 b = orc::qfrom(H(src[0])->d[2 * i + 1], H(src[1])->d[2 * i + 1], H(src[2])->d[2 * i + 1], H(src[3])->d[2 * i + 1]);
+      orc::QM31 f = orc::qadd(orc::qadd(a, b), orc::qmul(al, orc::qmulm(orc::qsub(a, b), orc::minv(p.y))));
+      orc::QM31 d = orc::qfrom(H(dst[0])->d[i], H(dst[1])->d[i], H(dst[2])->d[i], H(dst[3])->d[i]);
+      orc::QM31 r = orc::qadd(orc::qmul(d, a2), f);
+      H(dst[0])->d[i] = r.a.a; H(dst[1])->d[i] = r.a.b; H(dst[2])->d[i] = r.b.a; H(dst[3])->d[i] = r.b.b;
+    }
+  }
+  std::array<Col, 4> accumulate_quotients_range(uint32_t log, size_t row_off, size_t n_rows, const std::vector<Col>& cols, sb::QM31 rc,
+                                                const SampleBatchesFlat& b) override {
+    std::array<Col, 4> out;
+    for (int k = 0; k < 4; k++) out[k] = new HCol(n_rows);
+#pragma omp parallel for schedule(static)
+    for (size_t r = 0; r < n_rows; r++) {
+      std::vector<uint32_t> rowv(cols.size());
+      for (size_t c = 0; c < cols.size(); c++) rowv[c] = H(cols[c])->d[r];
+      orc::Pt p = orc::canonic_domain(log).at(orc::bit_reverse((uint32_t)(row_off + r), log));
+      sb::QM31 v = orc_row_quotient(b, rowv, rc, p);
+      H(out[0])->d[r] = v.a.a; H(out[1])->d[r] = v.a.b; H(out[2])->d[r] = v.b.a; H(out[3])->d[r] = v.b.b;
+    }
+    return out;
+  }
+  // one row of accumulate_quotients with the oracle's own arithmetic (orc_ops.h accumulate_quotients, row form)
+  static sb::QM31 orc_row_quotient(const SampleBatchesFlat& f, const std::vector<uint32_t>& row, sb::QM31 alpha_s, orc::Pt p) {
+    orc::QM31 alpha = oq(alpha_s), acc = orc::qfromm(0);
+    size_t e = 0;
+    for (size_t b = 0; b < f.sizes.size(); b++) {
+      const uint32_t* q = &f.points[8 * b];
+      orc::QM31 sx = orc::qfrom(q[0], q[1], q[2], q[3]), sy = orc::qfrom(q[4], q[5], q[6], q[7]);
+      orc::CM31 den = orc::csub(orc::cmul(orc::csub(sx.a, orc::CM31{p.x, 0}), sy.b), orc::cmul(orc::csub(sy.a, orc::CM31{p.y, 0}), sx.b));
+      orc::QM31 num = orc::qfromm(0), al = orc::qfromm(1);
+      orc::QM31 c = orc::qsub(orc::qconj(sy), sy);
+      for (uint32_t j = 0; j < f.sizes[b]; j++, e++) {
+        al = orc::qmul(al, alpha);
+        orc::QM31 v = orc::qfrom(f.entry_vals[4 * e], f.entry_vals[4 * e + 1], f.entry_vals[4 * e + 2], f.entry_vals[4 * e + 3]);
+        orc::QM31 a = orc::qsub(orc::qconj(v), v);
+        orc::QM31 bb = orc::qsub(orc::qmul(v, c), orc::qmul(a, sy));
+        orc::QM31 value = orc::qmulm(orc::qmul(al, c), row[f.entry_cols[e]]);
+        orc::QM31 lin = orc::qadd(orc::qmulm(orc::qmul(al, a), p.y), orc::qmul(al, bb));
+        num = orc::qadd(num, orc::qsub(value, lin));
+      }
+      acc = orc::qadd(orc::qmul(acc, orc::qpow(alpha, f.sizes[b])), orc::qmulc(num, orc::cinv(den)));
+    }
+    return sq(acc);
+  }
+  Col shift_prev(Col c, uint32_t trace_log) override {
+    uint32_t e = trace_log + 1;
+    size_t n = (size_t)1 << e, half = n / 2;
+    HCol* o = new HCol(n);
+    for (size_t row = 0; row < n; row++) {
+      size_t idx = orc::bit_reverse((uint32_t)row, e);
+      size_t pidx = idx < half ? (idx + half - 1) % half : ((idx - half + 1) % half) + half;
+      o->d[row] = H(c)->d[orc::bit_reverse((uint32_t)pidx, e)];
+    }
+    return o;
+  }
+  void accumulate_col(Col dst, Col src) override { for (size_t i = 0; i < H(dst)->n; i++) H(dst)->d[i] = orc::madd(H(dst)->d[i], H(src)->d[i]); }
+  void prefix_sum(Col c) override { orc::prefix_sum_bitrev(H(c)->d, lg2(H(c)->n)); }
+  std::vector<Col> logup_generate_sel(int comp, const std::vector<Col>& main, const InteractionElements& el,
+                                      const std::vector<uint8_t>& want) override {
+    size_t n = H(main[0])->n << LOG_N_LANES;
+    std::vector<HCol*> out(4 * N_LOGUP_COLS[comp], nullptr);
+    for (size_t i = 0; i < out.size(); i++) if (want[i]) out[i] = new HCol(n);
 #pragma omp parallel for schedule(static)
     for (size_t row = 0; row < n; row++) {
       OrcLogupGen e;
       e.main = &main; e.out = &out; e.el = &el; e.row = row; e.shift = LOG_N_LANES;
       eval_component(comp, e);
     }
-    for (int k = 0; k < 4; k++) orc::prefix_sum_bitrev(out[out.size() - 4 + k]->v.data(), log);
-    size_t b = out.size() - 4;
-    claimed = sb::q_make(out[b]->v[1], out[b + 1]->v[1], out[b + 2]->v[1], out[b + 3]->v[1]);
     return std::vector<Col>(out.begin(), out.end());
   }
-  void eval_constraints(int comp, uint32_t log_size, const std::vector<Col>& m, const std::vector<Col>& it, Col is_first,
-                        const InteractionElements& el, sb::QM31 total, const std::vector<sb::QM31>& coeffs,
-                        const std::array<Col, 4>& acc) override {
+  void eval_constraints_range(int comp, uint32_t log_size, size_t row_off, size_t n_rows, const std::vector<Col>& m, const std::vector<Col>& it,
+                              const std::array<Col, 4>& prev, Col is_first, const InteractionElements& el, sb::QM31 total,
+                              const std::vector<sb::QM31>& coeffs, const std::array<Col, 4>& acc) override {
+    eval_rows(comp, log_size, row_off, n_rows, m, it, &prev, is_first, el, total, coeffs, acc);
+  }
+  void eval_rows(int comp, uint32_t log_size, size_t row_off, size_t n_rows, const std::vector<Col>& m, const std::vector<Col>& it,
+                 const std::array<Col, 4>* prev, Col is_first, const InteractionElements& el, sb::QM31 total,
+                 const std::vector<sb::QM31>& coeffs, const std::array<Col, 4>& acc) {
     uint32_t e = log_size + 1;
-    size_t n = (size_t)1 << e, half = n / 2;
+    size_t half = (size_t)1 << log_size;
     // 1 / coset_vanishing(CanonicCoset(log_size).coset, eval_domain.at(i)), i = 0,1 (the translation cancels for canonic cosets)
     uint32_t dinv[2];
     for (uint32_t i = 0; i < 2; i++) {
@@ -207,16 +368,17 @@ struct OrcBackend : Backend {
       dinv[i] = orc::minv(x);
     }
 #pragma omp parallel for schedule(static)
-    for (size_t row = 0; row < n; row++) {
-      size_t idx = orc::bit_reverse((uint32_t)row, e);
+    for (size_t row = 0; row < n_rows; row++) {
+      size_t grow = row + row_off;
+      size_t idx = orc::bit_reverse((uint32_t)grow, e);
       size_t pidx = idx < half ? (idx + half - 1) % half : ((idx - half + 1) % half) + half;
       OrcDomainEval ev;
-      ev.main = &m; ev.inter = &it; ev.is_first_col = H(is_first)->v.data(); ev.el = &el; ev.coeff = &coeffs; ev.total = oq(total);
+      ev.main = &m; ev.inter = &it; ev.prev = prev; ev.is_first_col = H(is_first)->d; ev.el = &el; ev.coeff = &coeffs; ev.total = oq(total);
       ev.row = row; ev.prev_row = orc::bit_reverse((uint32_t)pidx, e);
       eval_component(comp, ev);
-      orc::QM31 r = orc::qmulm(ev.row_res, dinv[row >> log_size]);
-      H(acc[0])->v[row] = orc::madd(H(acc[0])->v[row], r.a.a); H(acc[1])->v[row] = orc::madd(H(acc[1])->v[row], r.a.b);
-      H(acc[2])->v[row] = orc::madd(H(acc[2])->v[row], r.b.a); H(acc[3])->v[row] = orc::madd(H(acc[3])->v[row], r.b.b);
+      orc::QM31 r = orc::qmulm(ev.row_res, dinv[grow >> log_size]);
+      H(acc[0])->d[row] = orc::madd(H(acc[0])->d[row], r.a.a); H(acc[1])->d[row] = orc::madd(H(acc[1])->d[row], r.a.b);
+      H(acc[2])->d[row] = orc::madd(H(acc[2])->d[row], r.b.a); H(acc[3])->d[row] = orc::madd(H(acc[3])->d[row], r.b.b);
     }
   }
 };
@@ -232,18 +394,19 @@ struct OrcAssertEval : OrcDomainEval {
   }
   LogupState<OrcAssertEval> lg2s;
   void relation(int rel, EF num, const F* vals, int n) { lg2s.push(num, ocombine(el->rel[rel], vals, n)); }
-  void ext_mask_last(EF& prev, EF& cur) { prev = ext_at(lg2s.n - 1, prev_row); cur = ext_at(lg2s.n - 1, row); }
+  void ext_mask_last(EF& pv, EF& cur) { pv = ext_at(lg2s.n - 1, prev_row); cur = ext_at(lg2s.n - 1, row); }
   void finalize_logup() { lg2s.finalize(*this); }
 };
 
 char* dupstr(const std::string& s) { char* p = (char*)malloc(s.size() + 1); memcpy(p, s.c_str(), s.size() + 1); return p; }
 thread_local std::string g_err;
+std::string g_err_shared;
 
 }  // namespace
 
 extern "C" {
 
-const char* orc_last_error() { return g_err.c_str(); }
+const char* orc_last_error() { return g_err.empty() ? g_err_shared.c_str() : g_err.c_str(); }
 
 // Full CPU proof with the oracle backend; returns the proof JSON (malloc'd) or NULL.  verify != 0 also runs the verifier.
 char* orc_prove_json(const char* code, const uint8_t* input, size_t input_len, uint32_t log_max_rows, int verify) {
@@ -262,9 +425,49 @@ char* orc_prove_json(const char* code, const uint8_t* input, size_t input_len, u
     return nullptr;
   }
 }
+
+// The sharded driver on `world` in-process ranks (threads).  Every rank must produce the same proof; returns rank 0's JSON,
+// or NULL if any rank failed or the ranks disagree.
+char* orc_prove_sharded_json(const char* code, const uint8_t* input, size_t input_len, uint32_t log_max_rows, int world, int verify) {
+  try {
+    std::vector<uint32_t> program = compile(code);
+    Machine vm(program, std::vector<uint8_t>(input, input + input_len));
+    vm.execute();
+    ProverConfig cfg;
+    cfg.log_max_rows = log_max_rows;
+    ThreadComm comm(world);
+    std::vector<std::string> json(world), err(world);
+    std::vector<std::thread> th;
+    for (int r = 0; r < world; r++)
+      th.emplace_back([&, r] {
+        try {
+          OrcBackend B;
+          B.my_rank = r;
+          if (world > 1) B.comm = &comm;
+          ProveResult res = prove_brainfuck_sharded(B, program, vm.trace, cfg);
+          if (verify) verify_brainfuck(res.proof, cfg);
+          json[r] = proof_to_json(res.proof);
+        } catch (const std::exception& e) {
+          err[r] = e.what();
+          // a failed rank would dead-lock the others at the next barrier: make every later barrier a no-op
+          std::lock_guard<std::mutex> lk(comm.mu);
+          comm.world = 1 << 30;
+          comm.generation++;
+          comm.cv.notify_all();
+        }
+      });
+    for (auto& t : th) t.join();
+    for (int r = 0; r < world; r++) if (!err[r].empty()) { g_err_shared = "rank " + std::to_string(r) + ": " + err[r]; g_err.clear(); return nullptr; }
+    for (int r = 1; r < world; r++) if (json[r] != json[0]) { g_err_shared = "ranks disagree on the proof"; g_err.clear(); return nullptr; }
+    return dupstr(json[0]);
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return nullptr;
+  }
+}
 void orc_free(char* p) { free(p); }
 
-// VM + tables as JSON-ish text for the host-logic tests: "steps;output-hex;log_sizes;program"
+// VM + tables as text for the host-logic tests: "steps;output bytes;log_sizes;program;first memory cells"
 char* orc_vm_summary(const char* code, const uint8_t* input, size_t input_len) {
   try {
     std::vector<uint32_t> program = compile(code);
@@ -301,7 +504,7 @@ size_t orc_table_dump(const char* code, const uint8_t* input, size_t input_len, 
   return t.rows();
 }
 
-// assert_constraints for every component of a program, with dummy (all-ones) or seeded lookup elements.
+// assert_constraints for every component of a program, with shifted-dummy or channel-drawn lookup elements.
 // Returns NULL on success, else a malloc'd message.
 char* orc_assert_constraints(const char* code, const uint8_t* input, size_t input_len, int dummy_elements) {
   try {
@@ -312,9 +515,9 @@ char* orc_assert_constraints(const char* code, const uint8_t* input, size_t inpu
     InteractionElements el;
     Channel ch;
     if (dummy_elements) {
-      for (int r = 0; r < 3; r++) { el.rel[r].z = sb::q_fromm(1); for (int i = 0; i < 7; i++) el.rel[r].alpha_pow[i] = sb::q_fromm(1); }
-      // LookupElements::dummy() makes the (clk 0, ...) denominators vanish for some tables; use a shifted z instead
-      for (int r = 0; r < 3; r++) el.rel[r].z = sb::q_make(5, 6, 7, 8);
+      // LookupElements::dummy() (z = alpha^i = 1) makes some denominators vanish (memory/component.rs:225-227); keep the
+      // all-ones alpha powers but move z away
+      for (int r = 0; r < 3; r++) { el.rel[r].z = sb::q_make(5, 6, 7, 8); for (int i = 0; i < 7; i++) el.rel[r].alpha_pow[i] = sb::q_fromm(1); }
     } else {
       el = draw_elements(ch);
     }
@@ -331,15 +534,13 @@ char* orc_assert_constraints(const char* code, const uint8_t* input, size_t inpu
       std::vector<sb::QM31> coeffs(N_CONSTRAINTS[c], sb::q_fromm(1));
       std::string err;
       for (size_t row = 0; row < n; row++) {
-        // trace-domain offset -1: same index arithmetic with eval_log == log_size (step 2^-1 -> handled as half-domain walk)
         size_t idx = orc::bit_reverse((uint32_t)row, ls);
-        // coset order neighbour: convert circle-domain index -> coset index, subtract one, convert back
         size_t half = n / 2;
-        size_t ci = idx < half ? 2 * idx : 2 * n - 1 - 2 * idx;   // circle-domain -> coset index (inverse of coset_to_domain_index)
-        size_t pc = (ci + n - 1) % n;
+        size_t ci = idx < half ? 2 * idx : 2 * n - 1 - 2 * idx;   // circle-domain index -> coset index
+        size_t pc = (ci + n - 1) % n;                              // coset-order predecessor
         size_t pidx = orc::coset_to_domain_index(pc, ls);
         OrcAssertEval ev;
-        ev.main = &full; ev.inter = &inter; ev.is_first_col = H(isf)->v.data(); ev.el = &el; ev.coeff = &coeffs; ev.total = oq(claimed);
+        ev.main = &full; ev.inter = &inter; ev.is_first_col = H(isf)->d; ev.el = &el; ev.coeff = &coeffs; ev.total = oq(claimed);
         ev.row = row; ev.prev_row = orc::bit_reverse((uint32_t)pidx, ls); ev.err = &err;
         eval_component(c, ev);
         if (!err.empty()) return dupstr(std::string(COMPONENT_NAMES[c]) + ": " + err);

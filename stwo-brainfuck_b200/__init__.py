@@ -379,3 +379,56 @@ def prove_brainfuck(backend: CudaBackend, code: str, stdin: bytes = b"", log_max
         lib.sbf_last_error.restype = ctypes.c_char_p
         raise ProvingError(lib.sbf_last_error().decode())
     return Proof(lib, h)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# multi-GPU: one process per GPU, NCCL communicator created from an id that the launcher broadcasts (torch.distributed)
+SHARDED_SYMBOLS = ["sc_comm_unique_id", "sc_comm_init", "sc_comm_destroy", "sc_comm_rank", "sc_comm_world", "sc_all_to_all",
+                   "sc_all_gather", "sc_allreduce_host_u32", "sc_col_copy", "sc_col_view", "sc_fold_line_range",
+                   "sc_fold_circle_into_line_range", "sc_accumulate_quotients_range", "sc_shift_prev", "sc_accumulate_col",
+                   "sc_logup_generate_sel", "sc_eval_constraints_range", "sbf_prove_sharded"]
+
+
+class Comm:
+    """sc_comm: the NCCL communicator of the sharded prover (include/stwo_cuda_sharded.h)."""
+
+    def __init__(self, backend: CudaBackend, rank: int, world: int, unique_id: bytes):
+        self._b = backend
+        self._h = _vp()
+        backend._ck(backend._lib.sc_comm_init(backend._ctx, ctypes.c_int32(rank), ctypes.c_int32(world),
+                                              ctypes.c_char_p(unique_id), ctypes.byref(self._h)))
+        self.rank, self.world = rank, world
+
+    @staticmethod
+    def unique_id(backend: CudaBackend) -> bytes:
+        buf = ctypes.create_string_buffer(128)
+        backend._ck(backend._lib.sc_comm_unique_id(buf))
+        return buf.raw
+
+    @classmethod
+    def from_torch_distributed(cls, backend: CudaBackend, dist) -> "Comm":
+        """Rank 0 creates the NCCL id, torch.distributed broadcasts it, every rank joins."""
+        rank, world = dist.get_rank(), dist.get_world_size()
+        box = [cls.unique_id(backend) if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return cls(backend, rank, world, box[0])
+
+    def close(self) -> None:
+        if self._h is not None:
+            self._b._lib.sc_comm_destroy(self._b._ctx, self._h)
+            self._h = None
+
+
+def prove_brainfuck_sharded(backend: CudaBackend, comm: Optional[Comm], code, stdin: bytes = b"", log_max_rows: int = 24) -> Proof:
+    """One proof split over the ranks of `comm` (column-sharded FFTs, all-to-all, row-sharded hashing / constraints /
+    quotients / FRI — csrc/host/prover_sharded.hpp).  Every rank calls this with the same inputs and gets the same proof.
+    comm=None runs the sharded driver on one GPU."""
+    lib = backend._lib
+    h = _vp()
+    code_b = code.encode() if isinstance(code, str) else code
+    rc = lib.sbf_prove_sharded(backend._ctx, comm._h if comm else None, ctypes.c_char_p(code_b), ctypes.c_char_p(stdin),
+                               ctypes.c_size_t(len(stdin)), ctypes.c_uint32(log_max_rows), ctypes.c_uint32(0), ctypes.byref(h))
+    if rc != 0:
+        lib.sbf_last_error.restype = ctypes.c_char_p
+        raise ProvingError(lib.sbf_last_error().decode())
+    return Proof(lib, h)

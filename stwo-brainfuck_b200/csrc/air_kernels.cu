@@ -34,8 +34,13 @@ struct LogupGenEval {
   __device__ void relation(int rel, EF num, const F* vals, int n) {
     Fq den = combine_q(p.el.rel[rel], vals, n);
     cum = cum + num * Fq{q_inv(den.v)};
-    p.out[4 * batch + 0][row] = cum.v.a.a; p.out[4 * batch + 1][row] = cum.v.a.b;
-    p.out[4 * batch + 2][row] = cum.v.b.a; p.out[4 * batch + 3][row] = cum.v.b.b;
+    // a null output pointer means "not wanted here" (multi-GPU: a rank only materialises the coordinate columns it owns)
+    uint32_t* o0 = p.out[4 * batch + 0]; uint32_t* o1 = p.out[4 * batch + 1];
+    uint32_t* o2 = p.out[4 * batch + 2]; uint32_t* o3 = p.out[4 * batch + 3];
+    if (o0) o0[row] = cum.v.a.a;
+    if (o1) o1[row] = cum.v.a.b;
+    if (o2) o2[row] = cum.v.b.a;
+    if (o3) o3[row] = cum.v.b.b;
     batch++;
   }
   __device__ void finalize_logup() {}
@@ -73,22 +78,27 @@ struct DomainEval {
     return {q_make(__ldg(p.inter[4 * b] + r), __ldg(p.inter[4 * b + 1] + r), __ldg(p.inter[4 * b + 2] + r), __ldg(p.inter[4 * b + 3] + r))};
   }
   __device__ EF ext_mask_cur(int b) { return ext_at(b, row); }
-  __device__ void ext_mask_last(EF& prev, EF& cur) { prev = ext_at(lg.n - 1, prev_row); cur = ext_at(lg.n - 1, row); }
+  __device__ void ext_mask_last(EF& prev, EF& cur) {
+    if (p.prev[0]) prev = {q_make(__ldg(p.prev[0] + row), __ldg(p.prev[1] + row), __ldg(p.prev[2] + row), __ldg(p.prev[3] + row))};
+    else prev = ext_at(lg.n - 1, prev_row);
+    cur = ext_at(lg.n - 1, row);
+  }
   __device__ void finalize_logup() { lg.finalize(*this); }
 };
 
 template <int COMP>
 __global__ void __launch_bounds__(256) constraint_kernel(AirParams p) {
   const uint32_t e = p.log_size + 1;
-  uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= (1u << e)) return;
-  // offset_bit_reversed_circle_domain_index(row, log_size, log_size + 1, -1)
-  uint32_t idx = __brev(row) >> (32 - e), half = 1u << (e - 1);
+  uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;       // local row: index into the (possibly partial) columns
+  if (row >= (p.n_rows ? p.n_rows : (1u << e))) return;
+  const uint32_t grow = row + p.row_off;                       // row of the whole domain
+  // offset_bit_reversed_circle_domain_index(grow, log_size, log_size + 1, -1); only used when the columns are whole
+  uint32_t idx = __brev(grow) >> (32 - e), half = 1u << (e - 1);
   uint32_t pidx = idx < half ? ((idx + half - 1) & (half - 1)) : (((idx - half + 1) & (half - 1)) + half);
   uint32_t prev_row = __brev(pidx) >> (32 - e);
   DomainEval ev(p, row, prev_row);
   eval_component(COMP, ev);
-  Fq res = ev.row_res * Fm{p.denom_inv[row >> p.log_size]};
+  Fq res = ev.row_res * Fm{p.denom_inv[grow >> p.log_size]};
   p.acc[0][row] = m_add(p.acc[0][row], res.v.a.a);
   p.acc[1][row] = m_add(p.acc[1][row], res.v.a.b);
   p.acc[2][row] = m_add(p.acc[2][row], res.v.b.a);
@@ -97,7 +107,7 @@ __global__ void __launch_bounds__(256) constraint_kernel(AirParams p) {
 
 template <int COMP>
 static void launch_both(bool constraints, const AirParams& p, cudaStream_t st) {
-  uint32_t n = 1u << (p.log_size + (constraints ? 1 : 0));
+  uint32_t n = (constraints && p.n_rows) ? p.n_rows : (1u << (p.log_size + (constraints ? 1 : 0)));
   uint32_t threads = n < 256 ? n : 256;
   if (constraints) constraint_kernel<COMP><<<(n + threads - 1) / threads, threads, 0, st>>>(p);
   else logup_gen_kernel<COMP><<<(n + threads - 1) / threads, threads, 0, st>>>(p);

@@ -18,6 +18,10 @@ struct AirParams {
   uint32_t main_shift;           // LogUp generation: main columns hold one value per 2^main_shift rows (lane broadcast)
   uint32_t denom_inv[2];         // 1 / coset_vanishing on the two halves of the bit-reversed LDE
   uint32_t* acc[4];
+  // row-range evaluation (multi-GPU): the column pointers cover rows [row_off, row_off + n_rows) of the LDE; the value of
+  // the last LogUp column at coset offset -1 then comes from `prev` (that column pre-shifted by the owner, same rows).
+  uint32_t row_off, n_rows;      // n_rows == 0: the whole domain
+  const uint32_t* prev[4];       // nullable
 };
 
 int launch_air(bool constraints, int comp, const AirParams& p, cudaStream_t st);

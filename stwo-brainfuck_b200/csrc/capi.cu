@@ -15,101 +15,13 @@
 using namespace sb;
 
 namespace sb { unsigned long long g_launch_count = 0; }
+thread_local std::string g_sc_err;
 
-struct sc_col {
-  uint32_t* d;
-  uint64_t len;
-  bool owned = true;  // false: a view over caller-owned device memory (sc_col_wrap)
-};
-struct sc_twiddles {
-  uint32_t root_log;
-  uint32_t* tw;   // 2^root_log words
-  uint32_t* itw;  // 2^root_log words
-};
-struct sc_ctx {
-  int device;
-  cudaStream_t st;
-  bool own_stream;
-  bool poisoned;
-  // staging ring for small host->device tables (pointer arrays, task tables)
-  uint8_t* h_ring;
-  uint8_t* d_ring;
-  size_t ring_size, ring_off;
-  // optional per-kernel-class timing (CUDA events on the launch stream), see sc_ctx_profile
-  bool profiling = false;
-  struct ProfRec { const char* tag; cudaEvent_t a, b; };
-  std::vector<ProfRec> prof;
-  std::vector<cudaEvent_t> ev_pool;
-  // pinned host arena (sc_host_arena_*): blocks are kept for the life of the context and reused after a reset
-  struct ArenaBlock { uint8_t* p; size_t size, used; };
-  std::vector<ArenaBlock> arena;
-  std::mutex arena_mu;
-  std::map<uint32_t, sc_twiddles*> tw_cache;  // sc_twiddles_cached
-};
-
-// RAII: brackets the kernels launched in a scope with two events when profiling is on.
-struct ProfScope {
-  sc_ctx* c; cudaEvent_t a = nullptr, b = nullptr; const char* tag;
-  static cudaEvent_t get(sc_ctx* c) {
-    if (!c->ev_pool.empty()) { cudaEvent_t e = c->ev_pool.back(); c->ev_pool.pop_back(); return e; }
-    cudaEvent_t e; cudaEventCreate(&e); return e;
-  }
-  ProfScope(sc_ctx* ctx, const char* t) : c(ctx), tag(t) {
-    if (c && c->profiling) { a = get(c); b = get(c); cudaEventRecord(a, c->st); }
-  }
-  ~ProfScope() { if (a) { cudaEventRecord(b, c->st); c->prof.push_back({tag, a, b}); } }
-};
-
-static thread_local std::string g_err;
-static int32_t fail(int32_t code, const std::string& m) { g_err = m; return code; }
-#define CK(call)                                                                                   \
-  do {                                                                                             \
-    cudaError_t e_ = (call);                                                                       \
-    if (e_ != cudaSuccess) {                                                                       \
-      if (ctx) ctx->poisoned = true;                                                               \
-      return fail(SC_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                   \
-    }                                                                                              \
-  } while (0)
-#define CKL(expr)                                                                                  \
-  do {                                                                                             \
-    int e_ = (expr);                                                                               \
-    if (e_ > 0) { ctx->poisoned = true; return fail(SC_ECUDA, std::string(#expr) + ": " + cudaGetErrorString((cudaError_t)e_)); } \
-    if (e_ < 0) return fail(SC_EINVAL, std::string(#expr) + ": invalid argument");                 \
-  } while (0)
-#define ENTER()                                                                                    \
-  if (!ctx) return fail(SC_EINVAL, "null context");                                                \
-  if (ctx->poisoned) return fail(SC_ECUDA, "context unusable after an earlier CUDA error");        \
-  CK(cudaSetDevice(ctx->device))
-
-static bool is_pow2(uint64_t x) { return x && !(x & (x - 1)); }
-static uint32_t ilog2(uint64_t x) { uint32_t l = 0; while ((1ull << l) < x) l++; return l; }
-
-// Copies a small host table to the device through the pinned ring; returns the device address.
-static int32_t stage(sc_ctx* ctx, const void* host, size_t bytes, void** dptr) {
-  size_t need = (bytes + 255) & ~(size_t)255;
-  if (need > ctx->ring_size) return fail(SC_ENOMEM, "staging table too large");
-  if (ctx->ring_off + need > ctx->ring_size) {
-    CK(cudaStreamSynchronize(ctx->st));
-    ctx->ring_off = 0;
-  }
-  memcpy(ctx->h_ring + ctx->ring_off, host, bytes);
-  CK(cudaMemcpyAsync(ctx->d_ring + ctx->ring_off, ctx->h_ring + ctx->ring_off, bytes, cudaMemcpyHostToDevice, ctx->st));
-  *dptr = ctx->d_ring + ctx->ring_off;
-  ctx->ring_off += need;
-  return SC_OK;
-}
-
-static int32_t new_col(sc_ctx* ctx, uint64_t len, sc_col** out) {
-  uint32_t* d = nullptr;
-  cudaError_t e = cudaMallocAsync((void**)&d, std::max<uint64_t>(len, 4) * 4, ctx->st);
-  if (e != cudaSuccess) { cudaGetLastError(); return fail(SC_ENOMEM, std::string("cudaMallocAsync: ") + cudaGetErrorString(e)); }
-  *out = new sc_col{d, len};
-  return SC_OK;
-}
+#include "capi_internal.cuh"
 
 extern "C" {
 
-const char* sc_last_error(void) { return g_err.c_str(); }
+const char* sc_last_error(void) { return g_sc_err.c_str(); }
 int32_t sc_version(void) { return 1; }
 
 int32_t sc_ctx_create(int32_t device, void* stream, sc_ctx** out) {
@@ -512,14 +424,15 @@ int32_t sc_fold_circle_into_line(sc_ctx* ctx, sc_col* const src[4], uint32_t log
 }
 
 // ------------------------------------------------------------------ quotients
-int32_t sc_accumulate_quotients(sc_ctx* ctx, uint32_t log, sc_col* const* cols, uint32_t n, const uint32_t random_coeff[4],
-                                const uint32_t* batch_points, const uint32_t* batch_sizes, const uint32_t* entry_cols,
-                                const uint32_t* entry_vals, uint32_t nb, sc_col* out[4]) {
+int32_t sc_accumulate_quotients_range(sc_ctx* ctx, uint32_t log, uint64_t row_off, uint64_t n_rows, sc_col* const* cols, uint32_t n,
+                                      const uint32_t random_coeff[4], const uint32_t* batch_points, const uint32_t* batch_sizes,
+                                      const uint32_t* entry_cols, const uint32_t* entry_vals, uint32_t nb, sc_col* out[4]) {
   ENTER();
-  if (log < 2 || log > 30 || (!cols && n) || !out) return fail(SC_EINVAL, "accumulate_quotients: bad argument");
+  if (log < 2 || log > 30 || (!cols && n) || !out || (row_off & 3) || (n_rows & 3) || row_off + n_rows > (1ull << log))
+    return fail(SC_EINVAL, "accumulate_quotients: bad argument");
   std::vector<const uint32_t*> p(n);
   for (uint32_t i = 0; i < n; i++) {
-    if (!cols[i] || cols[i]->len != (1ull << log)) return fail(SC_EINVAL, "accumulate_quotients: column length != 2^log");
+    if (!cols[i] || cols[i]->len != n_rows) return fail(SC_EINVAL, "accumulate_quotients: column length != number of rows");
     p[i] = cols[i]->d;
   }
   QM31 alpha = q_make(random_coeff[0], random_coeff[1], random_coeff[2], random_coeff[3]);
@@ -548,9 +461,9 @@ int32_t sc_accumulate_quotients(sc_ctx* ctx, uint32_t log, sc_col* const* cols, 
     B.coeff = q_pow(alpha, batch_sizes[b]);
   }
   uint32_t* d[4];
-  for (int k = 0; k < 4; k++) { int32_t r = new_col(ctx, 1ull << log, &out[k]); if (r) return r; d[k] = out[k]->d; }
+  for (int k = 0; k < 4; k++) { int32_t r = new_col(ctx, n_rows, &out[k]); if (r) return r; d[k] = out[k]->d; }
   if (nb == 0) {
-    for (int k = 0; k < 4; k++) CK(cudaMemsetAsync(d[k], 0, (size_t)4 << log, ctx->st));
+    for (int k = 0; k < 4; k++) CK(cudaMemsetAsync(d[k], 0, n_rows * 4, ctx->st));
     return SC_OK;
   }
   void *dp = nullptr, *db, *de = nullptr;
@@ -558,8 +471,15 @@ int32_t sc_accumulate_quotients(sc_ctx* ctx, uint32_t log, sc_col* const* cols, 
   if (n) { r = stage(ctx, p.data(), n * sizeof(void*), &dp); if (r) return r; }
   r = stage(ctx, qb.data(), qb.size() * sizeof(QuotBatch), &db); if (r) return r;
   if (!qe.empty()) { r = stage(ctx, qe.data(), qe.size() * sizeof(QuotEntry), &de); if (r) return r; }
-  { ProfScope ps_(ctx, "accumulate_quotients"); CKL(launch_accumulate_quotients(log, (const uint32_t* const*)dp, (const QuotBatch*)db, nb, (const QuotEntry*)de, d, ctx->st)); }
+  { ProfScope ps_(ctx, "accumulate_quotients"); CKL(launch_accumulate_quotients(log, row_off, n_rows, (const uint32_t* const*)dp, (const QuotBatch*)db, nb, (const QuotEntry*)de, d, ctx->st)); }
   return SC_OK;
+}
+int32_t sc_accumulate_quotients(sc_ctx* ctx, uint32_t log, sc_col* const* cols, uint32_t n, const uint32_t random_coeff[4],
+                                const uint32_t* batch_points, const uint32_t* batch_sizes, const uint32_t* entry_cols,
+                                const uint32_t* entry_vals, uint32_t nb, sc_col* out[4]) {
+  if (log > 30) return fail(SC_EINVAL, "accumulate_quotients: bad argument");
+  return sc_accumulate_quotients_range(ctx, log, 0, 1ull << log, cols, n, random_coeff, batch_points, batch_sizes, entry_cols,
+                                       entry_vals, nb, out);
 }
 
 // ------------------------------------------------------------------ accumulation / grind / misc

@@ -1,0 +1,106 @@
+// Internals shared by the translation units that implement the C ABI (capi.cu, sharded.cu): handle layouts, error
+// plumbing, the small-table staging ring and the profiling scope.
+#pragma once
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/stwo_cuda.h"
+#include "kernels.cuh"
+
+using namespace sb;
+
+struct sc_col {
+  uint32_t* d;
+  uint64_t len;
+  bool owned = true;  // false: a view over caller-owned device memory (sc_col_wrap)
+};
+struct sc_twiddles {
+  uint32_t root_log;
+  uint32_t* tw;   // 2^root_log words
+  uint32_t* itw;  // 2^root_log words
+};
+struct sc_ctx {
+  int device;
+  cudaStream_t st;
+  bool own_stream;
+  bool poisoned;
+  // staging ring for small host->device tables (pointer arrays, task tables)
+  uint8_t* h_ring;
+  uint8_t* d_ring;
+  size_t ring_size, ring_off;
+  // optional per-kernel-class timing (CUDA events on the launch stream), see sc_ctx_profile
+  bool profiling = false;
+  struct ProfRec { const char* tag; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;
+  // pinned host arena (sc_host_arena_*): blocks are kept for the life of the context and reused after a reset
+  struct ArenaBlock { uint8_t* p; size_t size, used; };
+  std::vector<ArenaBlock> arena;
+  std::mutex arena_mu;
+  std::map<uint32_t, sc_twiddles*> tw_cache;  // sc_twiddles_cached
+};
+
+// RAII: brackets the kernels launched in a scope with two events when profiling is on.
+struct ProfScope {
+  sc_ctx* c; cudaEvent_t a = nullptr, b = nullptr; const char* tag;
+  static cudaEvent_t get(sc_ctx* c) {
+    if (!c->ev_pool.empty()) { cudaEvent_t e = c->ev_pool.back(); c->ev_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+  ProfScope(sc_ctx* ctx, const char* t) : c(ctx), tag(t) {
+    if (c && c->profiling) { a = get(c); b = get(c); cudaEventRecord(a, c->st); }
+  }
+  ~ProfScope() { if (a) { cudaEventRecord(b, c->st); c->prof.push_back({tag, a, b}); } }
+};
+
+extern thread_local std::string g_sc_err;
+static inline int32_t fail(int32_t code, const std::string& m) { g_sc_err = m; return code; }
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      if (ctx) ctx->poisoned = true;                                                               \
+      return fail(SC_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                   \
+    }                                                                                              \
+  } while (0)
+#define CKL(expr)                                                                                  \
+  do {                                                                                             \
+    int e_ = (expr);                                                                               \
+    if (e_ > 0) { ctx->poisoned = true; return fail(SC_ECUDA, std::string(#expr) + ": " + cudaGetErrorString((cudaError_t)e_)); } \
+    if (e_ < 0) return fail(SC_EINVAL, std::string(#expr) + ": invalid argument");                 \
+  } while (0)
+#define ENTER()                                                                                    \
+  if (!ctx) return fail(SC_EINVAL, "null context");                                                \
+  if (ctx->poisoned) return fail(SC_ECUDA, "context unusable after an earlier CUDA error");        \
+  CK(cudaSetDevice(ctx->device))
+
+static inline bool is_pow2(uint64_t x) { return x && !(x & (x - 1)); }
+static inline uint32_t ilog2(uint64_t x) { uint32_t l = 0; while ((1ull << l) < x) l++; return l; }
+
+// Copies a small host table to the device through the pinned ring; returns the device address.
+static inline int32_t stage(sc_ctx* ctx, const void* host, size_t bytes, void** dptr) {
+  size_t need = (bytes + 255) & ~(size_t)255;
+  if (need > ctx->ring_size) return fail(SC_ENOMEM, "staging table too large");
+  if (ctx->ring_off + need > ctx->ring_size) {
+    CK(cudaStreamSynchronize(ctx->st));
+    ctx->ring_off = 0;
+  }
+  memcpy(ctx->h_ring + ctx->ring_off, host, bytes);
+  CK(cudaMemcpyAsync(ctx->d_ring + ctx->ring_off, ctx->h_ring + ctx->ring_off, bytes, cudaMemcpyHostToDevice, ctx->st));
+  *dptr = ctx->d_ring + ctx->ring_off;
+  ctx->ring_off += need;
+  return SC_OK;
+}
+
+static inline int32_t new_col(sc_ctx* ctx, uint64_t len, sc_col** out) {
+  uint32_t* d = nullptr;
+  cudaError_t e = cudaMallocAsync((void**)&d, std::max<uint64_t>(len, 4) * 4, ctx->st);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(SC_ENOMEM, std::string("cudaMallocAsync: ") + cudaGetErrorString(e)); }
+  *out = new sc_col{d, len};
+  return SC_OK;
+}
+

@@ -5,7 +5,8 @@
 #include <cstring>
 #include <string>
 
-#include "../../include/stwo_cuda.h"
+#include "../../include/stwo_cuda_sharded.h"
+#include "host/prover_sharded.hpp"
 #include "host/verifier.hpp"
 
 using namespace sbf;
@@ -57,6 +58,7 @@ struct CudaBackendImpl : Backend {
   void interpolate(const std::vector<Col>& cols) override { ck(sc_interpolate(ctx, (sc_col* const*)cols.data(), (uint32_t)cols.size(), tw)); }
   std::vector<Col> evaluate(const std::vector<Col>& coeffs, uint32_t log_blowup) override {
     std::vector<Col> out(coeffs.size());
+    if (coeffs.empty()) return out;
     ck(sc_evaluate(ctx, (sc_col* const*)coeffs.data(), (uint32_t)coeffs.size(), log_blowup, tw, (sc_col**)out.data()));
     return out;
   }
@@ -104,6 +106,63 @@ struct CudaBackendImpl : Backend {
     ck(sc_eval_constraints(ctx, comp, log_size, (sc_col* const*)m.data(), (uint32_t)m.size(), (sc_col* const*)it.data(), (uint32_t)it.size(),
                            h(is_first), (const uint32_t*)&el, (const uint32_t*)&total, (const uint32_t*)coeffs.data(), (sc_col* const*)acc.data()));
   }
+
+  // ---- multi-GPU extension (include/stwo_cuda_sharded.h)
+  sc_comm* comm = nullptr;
+  int rank() const override { return comm ? sc_comm_rank(comm) : 0; }
+  int world() const override { return comm ? sc_comm_world(comm) : 1; }
+  Col alloc(size_t n) override { sc_col* c; ck(sc_col_uninit(ctx, n, &c)); return c; }
+  Col view(Col c, size_t off, size_t n) override { sc_col* o; ck(sc_col_view(ctx, h(c), off, n, &o)); return o; }
+  void copy(Col dst, size_t dst_off, Col src, size_t src_off, size_t n) override { ck(sc_col_copy(ctx, h(dst), dst_off, h(src), src_off, n)); }
+  Col commit_layer(uint32_t log, Col prev, const std::vector<Col>& cols) override {
+    sc_col* o;
+    ck(sc_merkle_commit_layer(ctx, log, h(prev), (sc_col* const*)cols.data(), (uint32_t)cols.size(), &o));
+    return o;
+  }
+  void all_to_all(Col send, const std::vector<size_t>& sc, Col recv, const std::vector<size_t>& rc) override {
+    if (!comm) { copy(recv, 0, send, 0, sc[0]); return; }
+    std::vector<uint64_t> s(sc.begin(), sc.end()), r(rc.begin(), rc.end());
+    ck(sc_all_to_all(ctx, comm, h(send), s.data(), h(recv), r.data()));
+  }
+  void all_gather(Col send, Col recv, size_t n) override {
+    if (!comm) { copy(recv, 0, send, 0, n); return; }
+    ck(sc_all_gather(ctx, comm, h(send), h(recv), n));
+  }
+  void allreduce_host(uint32_t* buf, size_t n) override { if (comm) ck(sc_allreduce_host_u32(ctx, comm, buf, n)); }
+  std::array<Col, 4> fold_line_range(const std::array<Col, 4>& src, uint32_t log, size_t off, size_t n_out, QM31 alpha) override {
+    std::array<Col, 4> out;
+    ck(sc_fold_line_range(ctx, (sc_col* const*)src.data(), log, off, n_out, (const uint32_t*)&alpha, tw, (sc_col**)out.data()));
+    return out;
+  }
+  void fold_circle_into_line_range(const std::array<Col, 4>& dst, const std::array<Col, 4>& src, uint32_t log, size_t off, size_t n_out,
+                                   QM31 alpha) override {
+    ck(sc_fold_circle_into_line_range(ctx, (sc_col* const*)src.data(), log, off, n_out, (const uint32_t*)&alpha, tw, (sc_col* const*)dst.data()));
+  }
+  std::array<Col, 4> accumulate_quotients_range(uint32_t log, size_t row_off, size_t n_rows, const std::vector<Col>& cols, QM31 rc,
+                                                const SampleBatchesFlat& b) override {
+    std::array<Col, 4> out;
+    ck(sc_accumulate_quotients_range(ctx, log, row_off, n_rows, (sc_col* const*)cols.data(), (uint32_t)cols.size(), (const uint32_t*)&rc,
+                                     b.points.data(), b.sizes.data(), b.entry_cols.data(), b.entry_vals.data(), (uint32_t)b.sizes.size(),
+                                     (sc_col**)out.data()));
+    return out;
+  }
+  Col shift_prev(Col c, uint32_t trace_log) override { sc_col* o; ck(sc_shift_prev(ctx, h(c), trace_log, &o)); return o; }
+  void accumulate_col(Col dst, Col src) override { ck(sc_accumulate_col(ctx, h(dst), h(src))); }
+  void prefix_sum(Col c) override { ck(sc_prefix_sum_bitrev(ctx, h(c))); }
+  std::vector<Col> logup_generate_sel(int comp, const std::vector<Col>& main, const InteractionElements& el,
+                                      const std::vector<uint8_t>& want) override {
+    std::vector<Col> out(4 * N_LOGUP_COLS[comp], nullptr);
+    ck(sc_logup_generate_sel(ctx, comp, (sc_col* const*)main.data(), (uint32_t)main.size(), LOG_N_LANES, (const uint32_t*)&el, want.data(),
+                             (sc_col**)out.data()));
+    return out;
+  }
+  void eval_constraints_range(int comp, uint32_t log_size, size_t row_off, size_t n_rows, const std::vector<Col>& m, const std::vector<Col>& it,
+                              const std::array<Col, 4>& prev, Col is_first, const InteractionElements& el, QM31 total,
+                              const std::vector<QM31>& coeffs, const std::array<Col, 4>& acc) override {
+    ck(sc_eval_constraints_range(ctx, comp, log_size, row_off, n_rows, (sc_col* const*)m.data(), (uint32_t)m.size(), (sc_col* const*)it.data(),
+                                 (uint32_t)it.size(), (sc_col* const*)prev.data(), h(is_first), (const uint32_t*)&el, (const uint32_t*)&total,
+                                 (const uint32_t*)coeffs.data(), (sc_col* const*)acc.data()));
+  }
 };
 
 thread_local std::string g_sbf_err;
@@ -128,8 +187,11 @@ const char* sbf_last_error(void) { return g_sbf_err.c_str(); }
 
 // `brainfuck_prover prove --code <code>` with stdin bytes `input`: run the VM on the host, prove on the device.
 // log_max_rows = LOG_MAX_ROWS (24; 20 in the reference's tests).  Returns 0 or SC_EPROOF.
+int32_t sbf_prove_sharded(sc_ctx* ctx, sc_comm* comm, const char* code, const uint8_t* input, size_t input_len, uint32_t log_max_rows,
+                          uint32_t flags, sbf_proof** out);
 int32_t sbf_prove(sc_ctx* ctx, const char* code, const uint8_t* input, size_t input_len, uint32_t log_max_rows, uint32_t flags,
                   sbf_proof** out) {
+  if (flags & 4u) return sbf_prove_sharded(ctx, nullptr, code, input, input_len, log_max_rows, flags, out);  // SBF_SHARDED_DRIVER
   try {
     if (!ctx || !code || !out) throw std::runtime_error("null argument");
     auto t0 = std::chrono::steady_clock::now();
@@ -148,6 +210,41 @@ int32_t sbf_prove(sc_ctx* ctx, const char* code, const uint8_t* input, size_t in
     sbf_proof* p = new sbf_proof{std::move(r.proof), cfg, "", vm.output};
     std::ostringstream o;
     o << "{\"steps\":" << vm.trace.size() << ",\"vm_ms\":" << vm_ms << ",\"prove_ms\":" << prove_ms << ",\"log_sizes\":[";
+    for (int c = 0; c < N_COMPONENTS; c++) o << (c ? "," : "") << p->proof.log_size[c];
+    o << "],\"stages_ms\":{";
+    for (size_t i = 0; i < r.times.ms.size(); i++) o << (i ? "," : "") << "\"" << r.times.ms[i].first << "\":" << r.times.ms[i].second;
+    o << "}}";
+    p->report = o.str();
+    *out = p;
+    return SC_OK;
+  } catch (const std::exception& e) {
+    g_sbf_err = e.what();
+    return SC_EPROOF;
+  }
+}
+
+// One proof over the ranks of `comm` (one process per GPU; every rank calls this with the same program and gets the same
+// proof).  comm == NULL runs the sharded driver on a single GPU (world 1): same proof as sbf_prove.
+int32_t sbf_prove_sharded(sc_ctx* ctx, sc_comm* comm, const char* code, const uint8_t* input, size_t input_len, uint32_t log_max_rows,
+                          uint32_t flags, sbf_proof** out) {
+  try {
+    if (!ctx || !code || !out) throw std::runtime_error("null argument");
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<uint32_t> program = compile(code);
+    Machine vm(program, std::vector<uint8_t>(input, input + input_len));
+    vm.execute();
+    double vm_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    CudaBackendImpl B(ctx);
+    B.comm = comm;
+    ProverConfig cfg;
+    cfg.log_max_rows = log_max_rows;
+    B.cache_twiddles = !(flags & 2u);
+    auto t1 = std::chrono::steady_clock::now();
+    ProveResult r = prove_brainfuck_sharded(B, program, vm.trace, cfg, [&] { sc_ctx_sync(ctx); });
+    double prove_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
+    sbf_proof* p = new sbf_proof{std::move(r.proof), cfg, "", vm.output};
+    std::ostringstream o;
+    o << "{\"steps\":" << vm.trace.size() << ",\"vm_ms\":" << vm_ms << ",\"prove_ms\":" << prove_ms << ",\"world\":" << B.world() << ",\"log_sizes\":[";
     for (int c = 0; c < N_COMPONENTS; c++) o << (c ? "," : "") << p->proof.log_size[c];
     o << "],\"stages_ms\":{";
     for (size_t i = 0; i < r.times.ms.size(); i++) o << (i ? "," : "") << "\"" << r.times.ms[i].first << "\":" << r.times.ms[i].second;

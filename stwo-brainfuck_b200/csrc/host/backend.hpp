@@ -44,6 +44,8 @@ struct Backend {
   // MerkleOps: layers[k] = layer of log size k
   // root == nullptr: enqueue only (the caller reads layers[0] later), so the host can overlap other work
   virtual std::vector<Col> merkle_commit(const std::vector<Col>& cols, Hash* root) = 0;
+  // MerkleOps::commit_on_layer on 2^log rows (also used on row ranges: the node function is local to a row)
+  virtual Col commit_layer(uint32_t log, Col prev, const std::vector<Col>& cols) = 0;
   // FriOps
   virtual std::array<Col, 4> fold_line(const std::array<Col, 4>& src, uint32_t log, QM31 alpha) = 0;
   virtual void fold_circle_into_line(const std::array<Col, 4>& dst, const std::array<Col, 4>& src, uint32_t log, QM31 alpha) = 0;
@@ -60,6 +62,30 @@ struct Backend {
   virtual void eval_constraints(int comp, uint32_t log_size, const std::vector<Col>& main_lde, const std::vector<Col>& inter_lde,
                                 Col is_first_lde, const InteractionElements& el, QM31 total_sum, const std::vector<QM31>& coeffs,
                                 const std::array<Col, 4>& accum) = 0;
+
+  // ---- multi-GPU extension (prover_sharded.hpp): one rank of `world`; row-range variants and collectives
+  virtual int rank() const { return 0; }
+  virtual int world() const { return 1; }
+  virtual Col alloc(size_t n) = 0;                                            // uninitialised
+  virtual Col view(Col c, size_t off, size_t n) = 0;                          // non-owning slice (free_col drops the handle)
+  virtual void copy(Col dst, size_t dst_off, Col src, size_t src_off, size_t n) = 0;
+  virtual void all_to_all(Col send, const std::vector<size_t>& send_counts, Col recv, const std::vector<size_t>& recv_counts) = 0;
+  virtual void all_gather(Col send, Col recv, size_t n) = 0;
+  virtual void allreduce_host(uint32_t* buf, size_t n) = 0;                   // sum; exactly one contributor per slot
+  virtual std::array<Col, 4> fold_line_range(const std::array<Col, 4>& src, uint32_t log, size_t out_off, size_t n_out, QM31 alpha) = 0;
+  virtual void fold_circle_into_line_range(const std::array<Col, 4>& dst, const std::array<Col, 4>& src, uint32_t log, size_t out_off,
+                                           size_t n_out, QM31 alpha) = 0;
+  virtual std::array<Col, 4> accumulate_quotients_range(uint32_t log, size_t row_off, size_t n_rows, const std::vector<Col>& cols,
+                                                        QM31 random_coeff, const SampleBatchesFlat& b) = 0;
+  virtual Col shift_prev(Col lde_col, uint32_t trace_log) = 0;
+  virtual void accumulate_col(Col dst, Col src) = 0;
+  virtual void prefix_sum(Col c) = 0;
+  virtual std::vector<Col> logup_generate_sel(int comp, const std::vector<Col>& main, const InteractionElements& el,
+                                              const std::vector<uint8_t>& want) = 0;   // null for unwanted outputs
+  virtual void eval_constraints_range(int comp, uint32_t log_size, size_t row_off, size_t n_rows, const std::vector<Col>& main_lde,
+                                      const std::vector<Col>& inter_lde, const std::array<Col, 4>& prev, Col is_first_lde,
+                                      const InteractionElements& el, QM31 total_sum, const std::vector<QM31>& coeffs,
+                                      const std::array<Col, 4>& accum) = 0;
 };
 
 }  // namespace sbf

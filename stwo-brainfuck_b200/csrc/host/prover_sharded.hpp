@@ -1,0 +1,670 @@
+// One proof split over N = 2^w ranks (one GPU each) — the multi-GPU form of prover.hpp, same transcript, same proof bytes.
+//
+// Partitioning (BASELINE.json north_star):
+//   * polynomials are COLUMN-sharded: each committed column has one owner rank that interpolates it, extends it and
+//     evaluates it at the OODS points (columns are independent: no communication);
+//   * every low-degree extension is then RE-SHARDED BY ROWS with one all-to-all per commitment tree: rank r ends up with
+//     rows [r*R/N, (r+1)*R/N) (bit-reversed order) of every column of that size; Merkle hashing, constraint evaluation,
+//     DEEP quotients and FRI folds are local to such a range (children 2i, 2i+1 and fold partners are adjacent);
+//   * per tree / FRI layer the N sub-roots are all-gathered (N x 32 bytes) and the top log2 N layers are hashed by every rank;
+//   * tiny things (columns below 32 rows per rank, the FRI tail, the channel, the grind) are replicated;
+//   * the only non-local mask, the LogUp cumulative column at coset offset -1, travels as an extra pre-shifted column in
+//     the interaction tree's all-to-all;
+//   * composition accumulators are row-sharded; their four coordinate columns are gathered to four owners for the
+//     interpolate/lift chain (FFTs need whole columns), then committed like any other tree.
+// With world = 1 this driver degenerates to the single-GPU prover and produces the identical proof (tested).
+#pragma once
+#include "prover.hpp"
+
+namespace sbf {
+
+struct ShardLayout {
+  int w = 0, rank = 0, world = 1;
+  bool circle_sharded(uint32_t L) const { return L >= (uint32_t)w + 5; }  // LDE / circle-domain columns of log L
+  bool line_sharded(uint32_t l) const { return l >= (uint32_t)w + 4; }    // FRI line layers of log l
+};
+
+// A column as this rank sees it after re-sharding: its rows [rank*seg, (rank+1)*seg) if sharded, else the whole column.
+struct RowCol {
+  Col rows = nullptr;
+  uint32_t L = 0;
+  bool sharded = false;
+  size_t seg() const { return rows_len; }
+  size_t rows_len = 0;
+};
+struct Loc { Col col; size_t off; bool mine; };
+inline Loc locate(const RowCol& c, size_t row, const ShardLayout& sl) {
+  if (c.sharded) return {c.rows, row % c.rows_len, (int)(row / c.rows_len) == sl.rank};
+  return {c.rows, row, sl.rank == 0};
+}
+// Values that live on different ranks, delivered to every rank: each rank gathers what it owns, the rest arrives by all-reduce.
+inline std::vector<uint32_t> fetch(Backend& B, const std::vector<Loc>& req, uint32_t words) {
+  std::vector<uint32_t> buf(req.size() * words, 0);
+  std::vector<Col> cols;
+  std::vector<size_t> offs, slot;
+  for (size_t i = 0; i < req.size(); i++)
+    if (req[i].mine) { cols.push_back(req[i].col); offs.push_back(req[i].off); slot.push_back(i); }
+  std::vector<uint32_t> got = B.gather(cols, offs, words);
+  for (size_t j = 0; j < slot.size(); j++) memcpy(&buf[slot[j] * words], &got[j * words], words * 4);
+  if (B.world() > 1) B.allreduce_host(buf.data(), buf.size());
+  return buf;
+}
+
+inline std::vector<int> assign_owners(const std::vector<uint32_t>& logs, int world) {
+  std::vector<size_t> order(logs.size());
+  for (size_t i = 0; i < order.size(); i++) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return logs[a] > logs[b]; });
+  std::vector<int> owner(logs.size());
+  for (size_t k = 0; k < order.size(); k++) owner[order[k]] = (int)(k % world);
+  return owner;
+}
+
+struct SMerkle {
+  std::vector<Col> layers;  // [k]: k > w: this rank's sub-layer (2^(k-w) nodes); k <= w: the whole layer (replicated)
+  Hash root;
+};
+// Row-sharded MerkleProver::commit over columns that are either row ranges (sharded) or whole (replicated).
+inline SMerkle merkle_sharded(Backend& B, const ShardLayout& sl, const std::vector<RowCol>& cols) {
+  SMerkle m;
+  uint32_t maxL = 0;
+  for (auto& c : cols) maxL = std::max(maxL, c.L);
+  m.layers.assign(maxL + 1, nullptr);
+  const uint32_t w = (uint32_t)sl.w;
+  Col prev = nullptr;
+  int k = (int)maxL;
+  for (; k >= (int)w; k--) {
+    std::vector<Col> lc, tmp;
+    size_t n = (size_t)1 << (k - w);
+    for (auto& c : cols) {
+      if (c.L != (uint32_t)k) continue;
+      if (c.sharded) lc.push_back(c.rows);
+      else { Col v = B.view(c.rows, (size_t)sl.rank * n, n); tmp.push_back(v); lc.push_back(v); }
+    }
+    Col layer = B.commit_layer((uint32_t)(k - w), prev, lc);
+    for (Col v : tmp) B.free_col(v);
+    m.layers[k] = layer;
+    prev = layer;
+  }
+  if (maxL >= w) {  // N sub-roots -> every rank
+    Col full = B.alloc((size_t)8 << w);
+    B.all_gather(prev, full, 8);
+    B.free_col(m.layers[w]);
+    m.layers[w] = full;
+    prev = full;
+  }
+  for (; k >= 0; k--) {
+    std::vector<Col> lc;
+    for (auto& c : cols) if (c.L == (uint32_t)k) lc.push_back(c.rows);  // always replicated at these sizes
+    Col layer = B.commit_layer((uint32_t)k, prev, lc);
+    m.layers[k] = layer;
+    prev = layer;
+  }
+  B.read(m.layers[0], 0, 8, m.root.data());
+  return m;
+}
+
+struct STree {
+  std::vector<uint32_t> logs;  // polynomial log size per column
+  std::vector<int> owner;
+  std::vector<Col> polys;      // coefficient column on the owner, nullptr elsewhere
+  std::vector<RowCol> rows;    // LDE as seen by this rank
+  std::vector<Col> bufs;       // buffers behind `rows`
+  SMerkle merkle;
+};
+struct ExtraCol { Col full; uint32_t L; int owner; };  // non-committed column riding in a tree's all-to-all
+
+// Column-shard -> row-shard exchange of the LDEs (`lde[c]` on owners) + extras, then the row-sharded Merkle commit.
+inline void exchange_and_commit(Backend& B, const ShardLayout& sl, uint32_t log_blowup, STree& t, std::vector<Col>& lde,
+                                const std::vector<ExtraCol>& extras, std::vector<RowCol>* extra_rows) {
+  const int N = sl.world, me = sl.rank;
+  struct E { uint32_t L; int owner; bool sharded; size_t seg; Col full; };
+  std::vector<E> es;
+  for (size_t c = 0; c < t.logs.size(); c++) {
+    uint32_t L = t.logs[c] + log_blowup;
+    bool sh = sl.circle_sharded(L);
+    es.push_back({L, t.owner[c], sh, sh ? ((size_t)1 << (L - sl.w)) : ((size_t)1 << L), lde[c]});
+  }
+  for (auto& x : extras) {
+    bool sh = sl.circle_sharded(x.L);
+    es.push_back({x.L, x.owner, sh, sh ? ((size_t)1 << (x.L - sl.w)) : ((size_t)1 << x.L), x.full});
+  }
+  std::vector<RowCol> out(es.size());
+  if (N == 1) {  // nothing to exchange: the LDE columns are the row ranges
+    for (size_t i = 0; i < es.size(); i++) { out[i] = {es[i].full, es[i].L, es[i].sharded, es[i].seg}; t.bufs.push_back(es[i].full); }
+  } else {
+    std::vector<size_t> scount(N, 0), rcount(N, 0);
+    for (auto& e : es) { rcount[e.owner] += e.seg; if (e.owner == me) for (int d = 0; d < N; d++) scount[d] += e.seg; }
+    size_t stot = 0, rtot = 0;
+    for (int d = 0; d < N; d++) { stot += scount[d]; rtot += rcount[d]; }
+    Col send = B.alloc(std::max<size_t>(stot, 4)), recv = B.alloc(std::max<size_t>(rtot, 4));
+    size_t so = 0;
+    for (int d = 0; d < N; d++)
+      for (auto& e : es)
+        if (e.owner == me) { B.copy(send, so, e.full, e.sharded ? (size_t)d * e.seg : 0, e.seg); so += e.seg; }
+    B.all_to_all(send, scount, recv, rcount);
+    B.free_col(send);
+    for (auto& e : es) if (e.owner == me) B.free_col(e.full);
+    std::vector<size_t> roff(N, 0);
+    { size_t o = 0; for (int s = 0; s < N; s++) { roff[s] = o; o += rcount[s]; } }
+    for (size_t i = 0; i < es.size(); i++) {
+      out[i] = {B.view(recv, roff[es[i].owner], es[i].seg), es[i].L, es[i].sharded, es[i].seg};
+      roff[es[i].owner] += es[i].seg;
+      t.bufs.push_back(out[i].rows);
+    }
+    t.bufs.push_back(recv);
+  }
+  t.rows.assign(out.begin(), out.begin() + t.logs.size());
+  if (extra_rows) extra_rows->assign(out.begin() + t.logs.size(), out.end());
+  t.merkle = merkle_sharded(B, sl, t.rows);
+}
+
+// MerkleProver::decommit over a sharded tree: same walk as merkle_decommit, values and hashes fetched across ranks.
+inline void merkle_decommit_sharded(Backend& B, const ShardLayout& sl, const SMerkle& m, const std::vector<RowCol>& columns,
+                                    const std::map<uint32_t, std::vector<size_t>>& queries,
+                                    std::vector<std::vector<uint32_t>>& queried_values, MerkleDecommitment& d) {
+  queried_values.assign(columns.size(), {});
+  std::vector<Loc> hreq, vreq;
+  struct VReq { size_t col; bool queried; };
+  std::vector<VReq> vinfo;
+  std::vector<size_t> last_queries;
+  int n_layers = (int)m.layers.size();
+  for (int lg = n_layers - 1; lg >= 0; lg--) {
+    std::vector<size_t> lcols;
+    for (size_t c = 0; c < columns.size(); c++) if (columns[c].L == (uint32_t)lg) lcols.push_back(c);
+    static const std::vector<size_t> none;
+    auto it = queries.find((uint32_t)lg);
+    const std::vector<size_t>& colq = it == queries.end() ? none : it->second;
+    size_t pi = 0, ci = 0;
+    std::vector<size_t> total;
+    while (pi < last_queries.size() || ci < colq.size()) {
+      size_t node;
+      if (pi < last_queries.size() && ci < colq.size()) node = std::min(last_queries[pi] / 2, colq[ci]);
+      else if (pi < last_queries.size()) node = last_queries[pi] / 2;
+      else node = colq[ci];
+      if (lg + 1 < n_layers) {
+        int k = lg + 1;
+        for (size_t child = 2 * node; child <= 2 * node + 1; child++) {
+          if (pi < last_queries.size() && last_queries[pi] == child) { pi++; continue; }
+          if (k > sl.w) {
+            size_t n = (size_t)1 << (k - sl.w);
+            hreq.push_back({m.layers[k], 8 * (child % n), (int)(child / n) == sl.rank});
+          } else {
+            hreq.push_back({m.layers[k], 8 * child, sl.rank == 0});
+          }
+        }
+      }
+      bool queried = ci < colq.size() && colq[ci] == node;
+      if (queried) ci++;
+      for (size_t c : lcols) { vreq.push_back(locate(columns[c], node, sl)); vinfo.push_back({c, queried}); }
+      total.push_back(node);
+    }
+    last_queries = total;
+  }
+  std::vector<uint32_t> hw = fetch(B, hreq, 8), vw = fetch(B, vreq, 1);
+  for (size_t i = 0; i < hreq.size(); i++) { Hash h; memcpy(h.data(), &hw[8 * i], 32); d.hash_witness.push_back(h); }
+  for (size_t i = 0; i < vinfo.size(); i++) {
+    if (vinfo[i].queried) queried_values[vinfo[i].col].push_back(vw[i]); else d.column_witness.push_back(vw[i]);
+  }
+}
+inline void fri_witness_sharded(Backend& B, const ShardLayout& sl, const std::array<RowCol, 4>& eval, const std::vector<size_t>& queries,
+                                const std::vector<size_t>& pos, std::vector<QM31>& out) {
+  std::vector<Loc> req;
+  size_t k = 0;
+  for (size_t p : pos) {
+    while (k < queries.size() && queries[k] < p) k++;
+    if (k < queries.size() && queries[k] == p) continue;
+    for (int c = 0; c < 4; c++) req.push_back(locate(eval[c], p, sl));
+  }
+  std::vector<uint32_t> w = fetch(B, req, 1);
+  for (size_t i = 0; i + 3 < w.size(); i += 4) out.push_back(q_make(w[i], w[i + 1], w[i + 2], w[i + 3]));
+}
+
+inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_t>& code, const std::vector<Registers>& vm_trace,
+                                           const ProverConfig& cfg, const std::function<void()>& sync = nullptr) {
+  ProveResult R;
+  BrainfuckProof& proof = R.proof;
+  ShardLayout sl;
+  sl.rank = B.rank(); sl.world = B.world();
+  while ((1 << sl.w) < sl.world) sl.w++;
+  if ((1 << sl.w) != sl.world) throw std::runtime_error("world size must be a power of two");
+  const int N = sl.world, me = sl.rank;
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char* name) {
+    if (sync) sync();
+    auto now = std::chrono::steady_clock::now();
+    R.times.ms.push_back({name, std::chrono::duration<double, std::milli>(now - t_last).count()});
+    t_last = now;
+  };
+  auto row_off = [&](const RowCol& c) { return c.sharded ? (size_t)me * c.rows_len : (size_t)0; };
+
+  B.precompute_twiddles(cfg.log_max_rows + cfg.log_blowup + 1);
+  Channel ch;
+  std::vector<STree> trees;
+  lap("twiddles");
+
+  struct ArenaGuard {
+    HostArena* prev;
+    explicit ArenaGuard(HostArena* a) : prev(current_arena()) { current_arena() = a; }
+    ~ArenaGuard() { current_arena() = prev; }
+  } arena_guard(B.host_arena());
+
+  // owned polynomials of a tree: interpolate in place, extend, exchange, commit
+  auto lde_owned = [&](STree& t) {
+    std::vector<Col> owned;
+    std::vector<size_t> idx;
+    for (size_t c = 0; c < t.polys.size(); c++) if (t.polys[c]) { owned.push_back(t.polys[c]); idx.push_back(c); }
+    std::vector<Col> ev = B.evaluate(owned, cfg.log_blowup);
+    std::vector<Col> lde(t.polys.size(), nullptr);
+    for (size_t j = 0; j < idx.size(); j++) lde[idx[j]] = ev[j];
+    return lde;
+  };
+  auto interpolate_owned = [&](STree& t) {
+    std::vector<Col> owned;
+    for (Col p : t.polys) if (p) owned.push_back(p);
+    B.interpolate(owned);
+  };
+
+  // ---- phase 0: preprocessed trace
+  {
+    STree t;
+    for (uint32_t lg = cfg.log_max_rows; lg >= LOG_N_LANES; lg--) t.logs.push_back(lg);
+    t.owner = assign_owners(t.logs, N);
+    for (size_t c = 0; c < t.logs.size(); c++) t.polys.push_back(t.owner[c] == me ? B.gen_is_first(t.logs[c]) : nullptr);
+    interpolate_owned(t);
+    std::vector<Col> lde = lde_owned(t);
+    exchange_and_commit(B, sl, cfg.log_blowup, t, lde, {}, nullptr);
+    ch.mix_root(t.merkle.root);
+    trees.push_back(std::move(t));
+  }
+  lap("preprocessed");
+
+  // ---- phase 1: main trace.  Every rank builds the (small) compact tables; only owned columns are expanded and transformed.
+  std::vector<Table> tables = build_tables(vm_trace, code);
+  lap("tables(host)");
+  std::vector<std::vector<Col>> compact(N_COMPONENTS);
+  {
+    STree t;
+    for (int c = 0; c < N_COMPONENTS; c++) {
+      proof.log_size[c] = tables[c].log_size;
+      if (tables[c].log_size > cfg.log_max_rows) throw std::runtime_error(std::string("component too large: ") + COMPONENT_NAMES[c]);
+      for (size_t j = 0; j < tables[c].cols.size(); j++) t.logs.push_back(tables[c].log_size);
+    }
+    t.owner = assign_owners(t.logs, N);
+    size_t k = 0;
+    for (int c = 0; c < N_COMPONENTS; c++)
+      for (auto& col : tables[c].cols) {
+        Col cc = B.from_host_async(col.data(), col.size());
+        compact[c].push_back(cc);
+        t.polys.push_back(t.owner[k] == me ? B.broadcast16(cc) : nullptr);
+        k++;
+      }
+    interpolate_owned(t);
+    for (int c = 0; c < N_COMPONENTS; c++) ch.mix_u64(proof.log_size[c]);
+    std::vector<Col> lde = lde_owned(t);
+    exchange_and_commit(B, sl, cfg.log_blowup, t, lde, {}, nullptr);
+    ch.mix_root(t.merkle.root);
+    trees.push_back(std::move(t));
+  }
+  lap("main_trace");
+
+  // ---- phase 2: interaction trace.  Ownership is per coordinate column; an owner recomputes the (cheap) fractions itself.
+  InteractionElements el = draw_elements(ch);
+  std::vector<std::array<RowCol, 4>> prev_rows(N_COMPONENTS);  // last LogUp column at coset offset -1, row-sharded
+  {
+    STree t;
+    std::vector<int> col_comp;
+    for (int c = 0; c < N_COMPONENTS; c++)
+      for (int j = 0; j < 4 * N_LOGUP_COLS[c]; j++) { t.logs.push_back(proof.log_size[c]); col_comp.push_back(c); }
+    t.owner = assign_owners(t.logs, N);
+    t.polys.assign(t.logs.size(), nullptr);
+    std::vector<uint32_t> claimed(4 * N_COMPONENTS, 0);
+    size_t base = 0;
+    for (int c = 0; c < N_COMPONENTS; c++) {
+      int nout = 4 * N_LOGUP_COLS[c];
+      std::vector<uint8_t> want(nout, 0);
+      bool any = false;
+      for (int j = 0; j < nout; j++) if (t.owner[base + j] == me) { want[j] = 1; any = true; }
+      if (any) {
+        std::vector<Col> outs = B.logup_generate_sel(c, compact[c], el, want);
+        for (int j = 0; j < nout; j++) {
+          if (!outs[j]) continue;
+          if (j >= nout - 4) {  // LogupTraceGenerator::finalize_last: coset-order prefix sum, claimed_sum = col.at(1)
+            B.prefix_sum(outs[j]);
+            B.read(outs[j], 1, 1, &claimed[4 * c + (j - (nout - 4))]);
+          }
+          t.polys[base + j] = outs[j];
+        }
+      }
+      for (Col cc : compact[c]) B.free_col(cc);
+      base += nout;
+    }
+    if (N > 1) B.allreduce_host(claimed.data(), claimed.size());
+    for (int c = 0; c < N_COMPONENTS; c++) proof.claimed_sum[c] = q_make(claimed[4 * c], claimed[4 * c + 1], claimed[4 * c + 2], claimed[4 * c + 3]);
+    interpolate_owned(t);
+    for (int c = 0; c < N_COMPONENTS; c++) ch.mix_felts({proof.claimed_sum[c]});
+    std::vector<Col> lde = lde_owned(t);
+    // extras: the last LogUp column of every component, shifted to coset offset -1, one column per coordinate
+    std::vector<ExtraCol> extras;
+    base = 0;
+    for (int c = 0; c < N_COMPONENTS; c++) {
+      int nout = 4 * N_LOGUP_COLS[c];
+      for (int k = 0; k < 4; k++) {
+        size_t ci = base + nout - 4 + k;
+        Col sh = t.owner[ci] == me ? B.shift_prev(lde[ci], proof.log_size[c]) : nullptr;
+        extras.push_back({sh, proof.log_size[c] + cfg.log_blowup, t.owner[ci]});
+      }
+      base += nout;
+    }
+    std::vector<RowCol> extra_rows;
+    exchange_and_commit(B, sl, cfg.log_blowup, t, lde, extras, &extra_rows);
+    for (int c = 0; c < N_COMPONENTS; c++) for (int k = 0; k < 4; k++) prev_rows[c][k] = extra_rows[4 * c + k];
+    ch.mix_root(t.merkle.root);
+    trees.push_back(std::move(t));
+  }
+  lap("interaction_trace");
+
+  // ---- composition: constraint quotients on this rank's rows
+  QM31 random_coeff = ch.draw_felt();
+  int total_constraints = 0;
+  for (int c = 0; c < N_COMPONENTS; c++) total_constraints += N_CONSTRAINTS[c];
+  std::vector<QM31> powers(total_constraints);
+  { QM31 a = q_fromm(1); for (auto& p : powers) { p = a; a = q_mul(a, random_coeff); } }
+  struct Sub { std::array<Col, 4> cols; bool sharded; size_t len; };
+  std::map<uint32_t, Sub> sub;
+  {
+    size_t main_off = 0, inter_off = 0;
+    int g = 0;
+    for (int c = 0; c < N_COMPONENTS; c++) {
+      uint32_t ls = proof.log_size[c], L = ls + 1;
+      bool sh = sl.circle_sharded(L);
+      size_t len = sh ? ((size_t)1 << (L - sl.w)) : ((size_t)1 << L);
+      if (!sub.count(L)) sub[L] = {{B.zeros(len), B.zeros(len), B.zeros(len), B.zeros(len)}, sh, len};
+      std::vector<QM31> coeffs(N_CONSTRAINTS[c]);
+      for (int k = 0; k < N_CONSTRAINTS[c]; k++) coeffs[k] = powers[total_constraints - 1 - (g + k)];
+      g += N_CONSTRAINTS[c];
+      std::vector<Col> m, it;
+      for (int j = 0; j < N_MAIN_COLS[c]; j++) m.push_back(trees[1].rows[main_off + j].rows);
+      for (int j = 0; j < 4 * N_LOGUP_COLS[c]; j++) it.push_back(trees[2].rows[inter_off + j].rows);
+      Col isf = trees[0].rows[cfg.log_max_rows - ls].rows;
+      if (sh) {
+        std::array<Col, 4> pv = {prev_rows[c][0].rows, prev_rows[c][1].rows, prev_rows[c][2].rows, prev_rows[c][3].rows};
+        B.eval_constraints_range(c, ls, (size_t)me * len, len, m, it, pv, isf, el, proof.claimed_sum[c], coeffs, sub[L].cols);
+      } else {
+        B.eval_constraints(c, ls, m, it, isf, el, proof.claimed_sum[c], coeffs, sub[L].cols);
+      }
+      main_off += N_MAIN_COLS[c];
+      inter_off += 4 * N_LOGUP_COLS[c];
+    }
+  }
+  for (auto& pr : prev_rows) for (auto& rc : pr) if (N > 1 && rc.rows) { /* views into the tree's recv buffer: freed with it */ }
+  lap("constraints");
+
+  // ---- accumulator finalize: coordinate k of every size goes to rank k % N (one all-to-all), which runs the FFT chain
+  STree comp_tree;
+  {
+    auto owner_of = [&](int k) { return k % N; };
+    std::map<uint32_t, std::array<Col, 4>> full;  // whole accumulator columns on their coordinate owner
+    if (N == 1) {
+      for (auto& kv : sub) full[kv.first] = kv.second.cols;
+    } else {
+      std::vector<size_t> scount(N, 0), rcount(N, 0);
+      for (auto& kv : sub) {
+        if (!kv.second.sharded) continue;
+        for (int k = 0; k < 4; k++) { scount[owner_of(k)] += kv.second.len; if (owner_of(k) == me) for (int s = 0; s < N; s++) rcount[s] += kv.second.len; }
+      }
+      size_t stot = 0, rtot = 0;
+      for (int d = 0; d < N; d++) { stot += scount[d]; rtot += rcount[d]; }
+      Col send = B.alloc(std::max<size_t>(stot, 4)), recv = B.alloc(std::max<size_t>(rtot, 4));
+      size_t so = 0;
+      for (int d = 0; d < N; d++)
+        for (auto& kv : sub)
+          if (kv.second.sharded)
+            for (int k = 0; k < 4; k++)
+              if (owner_of(k) == d) { B.copy(send, so, kv.second.cols[k], 0, kv.second.len); so += kv.second.len; }
+      B.all_to_all(send, scount, recv, rcount);
+      B.free_col(send);
+      size_t ro = 0;
+      for (auto& kv : sub) full[kv.first] = {nullptr, nullptr, nullptr, nullptr};
+      for (int s = 0; s < N; s++)
+        for (auto& kv : sub)
+          if (kv.second.sharded)
+            for (int k = 0; k < 4; k++)
+              if (owner_of(k) == me) {
+                Col& dst = full[kv.first][k];
+                if (!dst) dst = B.alloc(kv.second.len * N);
+                B.copy(dst, (size_t)s * kv.second.len, recv, ro, kv.second.len);
+                ro += kv.second.len;
+              }
+      B.free_col(recv);
+      for (auto& kv : sub)
+        for (int k = 0; k < 4; k++) {
+          if (kv.second.sharded) B.free_col(kv.second.cols[k]);
+          else if (owner_of(k) == me) full[kv.first][k] = kv.second.cols[k];   // replicated: the owner keeps its copy
+          else B.free_col(kv.second.cols[k]);
+        }
+    }
+    uint32_t comp_log = sub.rbegin()->first;
+    comp_tree.logs.assign(4, comp_log);
+    for (int k = 0; k < 4; k++) comp_tree.owner.push_back(owner_of(k));
+    comp_tree.polys.assign(4, nullptr);
+    for (int k = 0; k < 4; k++) {
+      if (owner_of(k) != me) continue;
+      Col cur = nullptr;
+      uint32_t cur_log = 0;
+      for (auto& kv : full) {   // ascending sizes: lift the running polynomial, accumulate, interpolate
+        Col vals = kv.second[k];
+        if (cur) {
+          std::vector<Col> ev = B.evaluate({cur}, kv.first - cur_log);
+          B.accumulate_col(vals, ev[0]);
+          B.free_col(ev[0]);
+          B.free_col(cur);
+        }
+        B.interpolate({vals});
+        cur = vals;
+        cur_log = kv.first;
+      }
+      comp_tree.polys[k] = cur;
+    }
+    std::vector<Col> lde = lde_owned(comp_tree);
+    exchange_and_commit(B, sl, cfg.log_blowup, comp_tree, lde, {}, nullptr);
+    ch.mix_root(comp_tree.merkle.root);
+    trees.push_back(std::move(comp_tree));
+  }
+  lap("composition");
+
+  // ---- OODS sampling: owners evaluate their polynomials, the table is completed by all-reduce
+  QPoint oods = random_point(ch);
+  MaskLayout mask = mask_points(cfg, proof.log_size, oods);
+  CommitmentSchemeProof& P = proof.proof;
+  {
+    std::vector<Col> polys;
+    std::vector<QPoint> pts;
+    std::vector<size_t> slots;
+    size_t n_slots = 0;
+    for (size_t t = 0; t < trees.size(); t++)
+      for (size_t c = 0; c < trees[t].polys.size(); c++)
+        for (auto& p : mask.points[t][c]) {
+          if (trees[t].polys[c]) { polys.push_back(trees[t].polys[c]); pts.push_back(p); slots.push_back(n_slots); }
+          n_slots++;
+        }
+    std::vector<QM31> vals = B.eval_at_point(polys, pts);
+    std::vector<uint32_t> table(4 * n_slots, 0);
+    for (size_t j = 0; j < slots.size(); j++) memcpy(&table[4 * slots[j]], &vals[j], 16);
+    if (N > 1) B.allreduce_host(table.data(), table.size());
+    size_t k = 0;
+    P.sampled_values.resize(trees.size());
+    std::vector<QM31> flat;
+    for (size_t t = 0; t < trees.size(); t++) {
+      P.sampled_values[t].resize(trees[t].polys.size());
+      for (size_t c = 0; c < trees[t].polys.size(); c++)
+        for (size_t s = 0; s < mask.points[t][c].size(); s++) {
+          QM31 v = q_make(table[4 * k], table[4 * k + 1], table[4 * k + 2], table[4 * k + 3]);
+          P.sampled_values[t][c].push_back(v);
+          flat.push_back(v);
+          k++;
+        }
+    }
+    ch.mix_felts(flat);
+  }
+  lap("oods_eval");
+
+  // ---- DEEP quotients on this rank's rows
+  QM31 quot_coeff = ch.draw_felt();
+  struct FlatCol { RowCol rc; std::vector<PointSample> samples; };
+  std::vector<FlatCol> flat_cols;
+  for (size_t t = 0; t < trees.size(); t++)
+    for (size_t c = 0; c < trees[t].rows.size(); c++) {
+      FlatCol f{trees[t].rows[c], {}};
+      for (size_t s = 0; s < mask.points[t][c].size(); s++) f.samples.push_back({mask.points[t][c][s], P.sampled_values[t][c][s]});
+      flat_cols.push_back(std::move(f));
+    }
+  std::map<uint32_t, std::vector<const FlatCol*>, std::greater<uint32_t>> groups;
+  for (auto& f : flat_cols) groups[f.rc.L].push_back(&f);
+  std::vector<std::pair<uint32_t, std::array<RowCol, 4>>> quotients;  // descending log size
+  for (auto& kv : groups) {
+    std::vector<Col> cols;
+    std::vector<const std::vector<PointSample>*> samples;
+    for (auto* f : kv.second) { cols.push_back(f->rc.rows); samples.push_back(&f->samples); }
+    const RowCol& r0 = kv.second[0]->rc;
+    std::array<Col, 4> q = r0.sharded ? B.accumulate_quotients_range(kv.first, row_off(r0), r0.rows_len, cols, quot_coeff, batch_samples(samples))
+                                      : B.accumulate_quotients(kv.first, cols, quot_coeff, batch_samples(samples));
+    std::array<RowCol, 4> rq;
+    for (int k = 0; k < 4; k++) rq[k] = {q[k], kv.first, r0.sharded, r0.rows_len};
+    quotients.push_back({kv.first, rq});
+  }
+  lap("quotients");
+
+  // ---- FRI commit
+  std::vector<RowCol> first_cols;
+  for (auto& q : quotients) for (auto& x : q.second) first_cols.push_back(x);
+  SMerkle fri_first = merkle_sharded(B, sl, first_cols);
+  ch.mix_root(fri_first.root);
+  QM31 circle_alpha = ch.draw_felt();
+  struct InnerLayer { std::array<RowCol, 4> eval; uint32_t log; SMerkle tree; };
+  std::vector<InnerLayer> inner;
+  uint32_t line_log = quotients[0].first - 1;
+  auto line_cols = [&](uint32_t l, std::array<Col, 4> c) {
+    bool sh = sl.line_sharded(l);
+    size_t len = sh ? ((size_t)1 << (l - sl.w)) : ((size_t)1 << l);
+    std::array<RowCol, 4> r;
+    for (int k = 0; k < 4; k++) r[k] = {c[k], l, sh, len};
+    return r;
+  };
+  std::array<RowCol, 4> layer;
+  {
+    bool sh = sl.line_sharded(line_log);
+    size_t len = sh ? ((size_t)1 << (line_log - sl.w)) : ((size_t)1 << line_log);
+    layer = line_cols(line_log, {B.zeros(len), B.zeros(len), B.zeros(len), B.zeros(len)});
+  }
+  size_t qi = 0;
+  const uint32_t last_log = cfg.log_last_layer_degree_bound + cfg.log_blowup;
+  auto cols_of = [](const std::array<RowCol, 4>& r) { return std::array<Col, 4>{r[0].rows, r[1].rows, r[2].rows, r[3].rows}; };
+  while (line_log > last_log) {
+    while (qi < quotients.size() && quotients[qi].first - 1 == line_log) {
+      if (layer[0].sharded) B.fold_circle_into_line_range(cols_of(layer), cols_of(quotients[qi].second), quotients[qi].first,
+                                                          (size_t)me * layer[0].rows_len, layer[0].rows_len, circle_alpha);
+      else B.fold_circle_into_line(cols_of(layer), cols_of(quotients[qi].second), quotients[qi].first, circle_alpha);
+      qi++;
+    }
+    InnerLayer Lr{layer, line_log, {}};
+    Lr.tree = merkle_sharded(B, sl, std::vector<RowCol>(layer.begin(), layer.end()));
+    ch.mix_root(Lr.tree.root);
+    QM31 alpha = ch.draw_felt();
+    std::array<Col, 4> next;
+    if (layer[0].sharded) {
+      size_t n_out = layer[0].rows_len / 2;
+      next = B.fold_line_range(cols_of(layer), line_log, (size_t)me * n_out, n_out, alpha);
+      if (!sl.line_sharded(line_log - 1)) {  // the layer becomes too small to shard: replicate it
+        for (int k = 0; k < 4; k++) {
+          Col fullc = B.alloc((size_t)1 << (line_log - 1));
+          B.all_gather(next[k], fullc, n_out);
+          B.free_col(next[k]);
+          next[k] = fullc;
+        }
+      }
+    } else {
+      next = B.fold_line(cols_of(layer), line_log, alpha);
+    }
+    line_log--;
+    layer = line_cols(line_log, next);
+    inner.push_back(std::move(Lr));
+  }
+  if (qi != quotients.size()) throw std::runtime_error("FRI: not all columns consumed");
+  {
+    size_t n = (size_t)1 << line_log;
+    std::vector<std::vector<uint32_t>> cv(4, std::vector<uint32_t>(n));
+    for (int k = 0; k < 4; k++) B.read(layer[k].rows, 0, n, cv[k].data());
+    if (cfg.log_last_layer_degree_bound != 0) throw std::runtime_error("only log_last_layer_degree_bound = 0 is supported");
+    QM31 v0 = q_make(cv[0][0], cv[1][0], cv[2][0], cv[3][0]);
+    for (size_t i = 1; i < n; i++)
+      if (!q_eq(v0, q_make(cv[0][i], cv[1][i], cv[2][i], cv[3][i]))) throw std::runtime_error("FRI: invalid degree (last layer not constant)");
+    P.fri_proof.last_layer_poly = {v0};
+    ch.mix_felts(P.fri_proof.last_layer_poly);
+  }
+  lap("fri_commit");
+
+  P.proof_of_work = B.grind(ch.digest, cfg.pow_bits);
+  ch.mix_u64(P.proof_of_work);
+  lap("grind");
+
+  // ---- decommit
+  uint32_t max_log = quotients[0].first;
+  Queries queries = Queries::generate(ch, max_log, cfg.n_queries);
+  std::map<uint32_t, std::vector<size_t>> positions_by_log;
+  {
+    std::map<uint32_t, std::vector<size_t>> fri_pos;
+    for (auto& q : quotients) {
+      Queries cq = queries.fold(max_log - q.first);
+      positions_by_log[q.first] = cq.positions;
+      std::vector<size_t> pos = decommitment_positions(cq.positions, 1);
+      fri_pos[q.first] = pos;
+      fri_witness_sharded(B, sl, q.second, cq.positions, pos, P.fri_proof.first_layer.fri_witness);
+    }
+    std::vector<std::vector<uint32_t>> unused;
+    merkle_decommit_sharded(B, sl, fri_first, first_cols, fri_pos, unused, P.fri_proof.first_layer.decommitment);
+    P.fri_proof.first_layer.commitment = fri_first.root;
+    Queries lq = queries.fold(1);
+    for (auto& L : inner) {
+      FriLayerProof lp;
+      std::vector<size_t> pos = decommitment_positions(lq.positions, 1);
+      fri_witness_sharded(B, sl, L.eval, lq.positions, pos, lp.fri_witness);
+      std::map<uint32_t, std::vector<size_t>> m{{L.log, pos}};
+      std::vector<std::vector<uint32_t>> unused2;
+      merkle_decommit_sharded(B, sl, L.tree, std::vector<RowCol>(L.eval.begin(), L.eval.end()), m, unused2, lp.decommitment);
+      lp.commitment = L.tree.root;
+      P.fri_proof.inner_layers.push_back(std::move(lp));
+      lq = lq.fold(1);
+    }
+  }
+  P.queried_values.resize(trees.size());
+  P.decommitments.resize(trees.size());
+  for (size_t t = 0; t < trees.size(); t++) {
+    P.commitments.push_back(trees[t].merkle.root);
+    merkle_decommit_sharded(B, sl, trees[t].merkle, trees[t].rows, positions_by_log, P.queried_values[t], P.decommitments[t]);
+  }
+  lap("decommit");
+
+  {
+    const auto& cs = P.sampled_values[3];
+    QM31 comp = cs[0][0];
+    comp = q_add(comp, q_mul(cs[1][0], q_make(0, 1, 0, 0)));
+    comp = q_add(comp, q_mul(cs[2][0], q_make(0, 0, 1, 0)));
+    comp = q_add(comp, q_mul(cs[3][0], q_make(0, 0, 0, 1)));
+    QM31 want = eval_composition_at_point(cfg, proof.log_size, proof.claimed_sum, el, oods, P.sampled_values, random_coeff);
+    if (!q_eq(comp, want)) throw std::runtime_error("ConstraintsNotSatisfied");
+  }
+  // ---- release
+  for (auto& t : trees) {
+    for (Col x : t.polys) if (x) B.free_col(x);
+    for (Col x : t.bufs) B.free_col(x);
+    for (Col x : t.merkle.layers) if (x) B.free_col(x);
+  }
+  for (auto& q : quotients) for (auto& x : q.second) B.free_col(x.rows);
+  for (Col x : fri_first.layers) if (x) B.free_col(x);
+  for (auto& L : inner) { for (auto& x : L.eval) B.free_col(x.rows); for (Col x : L.tree.layers) if (x) B.free_col(x); }
+  for (auto& x : layer) B.free_col(x.rows);
+  lap("check+free");
+  return R;
+}
+
+}  // namespace sbf

@@ -46,7 +46,8 @@ int launch_broadcast16(const uint32_t* src, uint32_t* dst, size_t src_len, cudaS
 // quotients.cu
 struct QuotEntry { uint32_t col; uint32_t c[4]; };
 struct QuotBatch { CM31 prx, pry, pix, piy; QM31 suma, sumb, coeff; uint32_t first, count; };
-int launch_accumulate_quotients(uint32_t log, const uint32_t* const* d_cols, const QuotBatch* d_batches, uint32_t nb,
-                                const QuotEntry* d_entries, uint32_t* const out[4], cudaStream_t st);
+int launch_accumulate_quotients(uint32_t log, uint64_t row_off, uint64_t nrows, const uint32_t* const* d_cols,
+                                const QuotBatch* d_batches, uint32_t nb, const QuotEntry* d_entries, uint32_t* const out[4],
+                                cudaStream_t st);
 
 }  // namespace sb

@@ -38,11 +38,12 @@ __device__ __forceinline__ uint32_t red64(uint64_t v) {  // full reduction of an
 __global__ void __launch_bounds__(128) quotients_kernel(uint32_t log, const uint32_t* const* __restrict__ cols,
                                                         const QuotBatch* __restrict__ batches, uint32_t nb,
                                                         const QuotEntry* __restrict__ entries, uint32_t* o0, uint32_t* o1,
-                                                        uint32_t* o2, uint32_t* o3) {
-  const uint32_t nq = 1u << (log - 2);
+                                                        uint32_t* o2, uint32_t* o3, uint32_t k_off, uint32_t nq) {
+  // rows [4*k_off, 4*(k_off+nq)) of the domain; columns and outputs are indexed by the LOCAL quad index k
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < nq; k += gridDim.x * blockDim.x) {
-    // base point: half_odds(log-1).at(bitrev(k, log-2)): index 2^(30-log) + j0 * 2^(32-log)
-    uint32_t j0 = (log > 2) ? (__brev(k) >> (34 - log)) : 0;
+    // base point: half_odds(log-1).at(bitrev(kg, log-2)): index 2^(30-log) + j0 * 2^(32-log)
+    const uint32_t kg = k + k_off;
+    uint32_t j0 = (log > 2) ? (__brev(kg) >> (34 - log)) : 0;
     uint32_t idx = ((1u << (30 - log)) + (uint32_t)(((uint64_t)j0 << (32 - log)) & 0x7fffffffu)) & 0x7fffffffu;
     Pt bp = q_point_at_index(idx);
     const uint32_t px[4] = {bp.x, bp.x, m_neg(bp.x), m_neg(bp.x)};
@@ -97,8 +98,9 @@ __global__ void __launch_bounds__(128) quotients_kernel(uint32_t log, const uint
   }
 }
 
-int launch_accumulate_quotients(uint32_t log, const uint32_t* const* d_cols, const QuotBatch* d_batches, uint32_t nb,
-                                const QuotEntry* d_entries, uint32_t* const out[4], cudaStream_t st) {
+int launch_accumulate_quotients(uint32_t log, uint64_t row_off, uint64_t nrows, const uint32_t* const* d_cols,
+                                const QuotBatch* d_batches, uint32_t nb, const QuotEntry* d_entries, uint32_t* const out[4],
+                                cudaStream_t st) {
   static bool init = false;
   if (!init) {
     Pt g[31];
@@ -108,11 +110,12 @@ int launch_accumulate_quotients(uint32_t log, const uint32_t* const* d_cols, con
     if (e != cudaSuccess) return (int)e;
     init = true;
   }
-  if (log < 2 || log > 30) return -1;
-  uint32_t nq = 1u << (log - 2);
+  if (log < 2 || log > 30 || (row_off & 3) || (nrows & 3) || row_off + nrows > ((uint64_t)1 << log)) return -1;
+  uint32_t nq = (uint32_t)(nrows >> 2);
   uint32_t blocks = (nq + 127) / 128;
   if (blocks > 148u * 16u) blocks = 148u * 16u;
-  quotients_kernel<<<blocks, 128, 0, st>>>(log, d_cols, d_batches, nb, d_entries, out[0], out[1], out[2], out[3]); g_launch_count++;
+  quotients_kernel<<<blocks, 128, 0, st>>>(log, d_cols, d_batches, nb, d_entries, out[0], out[1], out[2], out[3],
+                                           (uint32_t)(row_off >> 2), nq); g_launch_count++;
   return (int)cudaGetLastError();
 }
 
