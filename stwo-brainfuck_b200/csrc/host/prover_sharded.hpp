@@ -14,6 +14,7 @@
 //     interpolate/lift chain (FFTs need whole columns), then committed like any other tree.
 // With world = 1 this driver degenerates to the single-GPU prover and produces the identical proof (tested).
 #pragma once
+#include <memory>
 #include "prover.hpp"
 
 namespace sbf {
@@ -49,6 +50,21 @@ inline std::vector<uint32_t> fetch(Backend& B, const std::vector<Loc>& req, uint
   if (B.world() > 1) B.allreduce_host(buf.data(), buf.size());
   return buf;
 }
+
+// Batched form: requests are registered while walking the trees, resolved with ONE gather + ONE all-reduce per word size,
+// then the registered finishers distribute the values (MerkleProver::decommit touches ~100 scattered nodes per tree).
+struct FetchBatch {
+  std::vector<Loc> req[2];             // [0]: 1-word values, [1]: 8-word hashes
+  std::vector<uint32_t> data[2];
+  std::vector<std::function<void()>> finish;
+  size_t add_value(const Loc& l) { req[0].push_back(l); return req[0].size() - 1; }
+  size_t add_hash(const Loc& l) { req[1].push_back(l); return req[1].size() - 1; }
+  void run(Backend& B) {
+    data[0] = fetch(B, req[0], 1);
+    data[1] = fetch(B, req[1], 8);
+    for (auto& f : finish) f();
+  }
+};
 
 inline std::vector<int> assign_owners(const std::vector<uint32_t>& logs, int world) {
   std::vector<size_t> order(logs.size());
@@ -158,14 +174,15 @@ inline void exchange_and_commit(Backend& B, const ShardLayout& sl, uint32_t log_
   t.merkle = merkle_sharded(B, sl, t.rows);
 }
 
-// MerkleProver::decommit over a sharded tree: same walk as merkle_decommit, values and hashes fetched across ranks.
-inline void merkle_decommit_sharded(Backend& B, const ShardLayout& sl, const SMerkle& m, const std::vector<RowCol>& columns,
+// MerkleProver::decommit over a sharded tree: same walk as merkle_decommit; the reads are registered in `fb` and the outputs
+// are filled by a finisher once the batch has run.
+inline void merkle_decommit_sharded(FetchBatch& fb, const ShardLayout& sl, const SMerkle& m, const std::vector<RowCol>& columns,
                                     const std::map<uint32_t, std::vector<size_t>>& queries,
-                                    std::vector<std::vector<uint32_t>>& queried_values, MerkleDecommitment& d) {
-  queried_values.assign(columns.size(), {});
-  std::vector<Loc> hreq, vreq;
-  struct VReq { size_t col; bool queried; };
-  std::vector<VReq> vinfo;
+                                    std::vector<std::vector<uint32_t>>* queried_values, MerkleDecommitment* d) {
+  if (queried_values) queried_values->assign(columns.size(), {});
+  struct VReq { size_t slot, col; bool queried; };
+  auto hslots = std::make_shared<std::vector<size_t>>();
+  auto vinfo = std::make_shared<std::vector<VReq>>();
   std::vector<size_t> last_queries;
   int n_layers = (int)m.layers.size();
   for (int lg = n_layers - 1; lg >= 0; lg--) {
@@ -187,36 +204,43 @@ inline void merkle_decommit_sharded(Backend& B, const ShardLayout& sl, const SMe
           if (pi < last_queries.size() && last_queries[pi] == child) { pi++; continue; }
           if (k > sl.w) {
             size_t n = (size_t)1 << (k - sl.w);
-            hreq.push_back({m.layers[k], 8 * (child % n), (int)(child / n) == sl.rank});
+            hslots->push_back(fb.add_hash({m.layers[k], 8 * (child % n), (int)(child / n) == sl.rank}));
           } else {
-            hreq.push_back({m.layers[k], 8 * child, sl.rank == 0});
+            hslots->push_back(fb.add_hash({m.layers[k], 8 * child, sl.rank == 0}));
           }
         }
       }
       bool queried = ci < colq.size() && colq[ci] == node;
       if (queried) ci++;
-      for (size_t c : lcols) { vreq.push_back(locate(columns[c], node, sl)); vinfo.push_back({c, queried}); }
+      for (size_t c : lcols) vinfo->push_back({fb.add_value(locate(columns[c], node, sl)), c, queried});
       total.push_back(node);
     }
     last_queries = total;
   }
-  std::vector<uint32_t> hw = fetch(B, hreq, 8), vw = fetch(B, vreq, 1);
-  for (size_t i = 0; i < hreq.size(); i++) { Hash h; memcpy(h.data(), &hw[8 * i], 32); d.hash_witness.push_back(h); }
-  for (size_t i = 0; i < vinfo.size(); i++) {
-    if (vinfo[i].queried) queried_values[vinfo[i].col].push_back(vw[i]); else d.column_witness.push_back(vw[i]);
-  }
+  FetchBatch* pfb = &fb;
+  fb.finish.push_back([pfb, hslots, vinfo, queried_values, d] {
+    for (size_t s : *hslots) { Hash h; memcpy(h.data(), &pfb->data[1][8 * s], 32); d->hash_witness.push_back(h); }
+    for (auto& v : *vinfo) {
+      uint32_t x = pfb->data[0][v.slot];
+      if (v.queried) { if (queried_values) (*queried_values)[v.col].push_back(x); } else d->column_witness.push_back(x);
+    }
+  });
 }
-inline void fri_witness_sharded(Backend& B, const ShardLayout& sl, const std::array<RowCol, 4>& eval, const std::vector<size_t>& queries,
-                                const std::vector<size_t>& pos, std::vector<QM31>& out) {
-  std::vector<Loc> req;
+inline void fri_witness_sharded(FetchBatch& fb, const ShardLayout& sl, const std::array<RowCol, 4>& eval, const std::vector<size_t>& queries,
+                                const std::vector<size_t>& pos, std::vector<QM31>* out) {
+  auto slots = std::make_shared<std::vector<size_t>>();
   size_t k = 0;
   for (size_t p : pos) {
     while (k < queries.size() && queries[k] < p) k++;
     if (k < queries.size() && queries[k] == p) continue;
-    for (int c = 0; c < 4; c++) req.push_back(locate(eval[c], p, sl));
+    for (int c = 0; c < 4; c++) slots->push_back(fb.add_value(locate(eval[c], p, sl)));
   }
-  std::vector<uint32_t> w = fetch(B, req, 1);
-  for (size_t i = 0; i + 3 < w.size(); i += 4) out.push_back(q_make(w[i], w[i + 1], w[i + 2], w[i + 3]));
+  FetchBatch* pfb = &fb;
+  fb.finish.push_back([pfb, slots, out] {
+    const auto& w = pfb->data[0];
+    for (size_t i = 0; i + 3 < slots->size(); i += 4)
+      out->push_back(q_make(w[(*slots)[i]], w[(*slots)[i + 1]], w[(*slots)[i + 2]], w[(*slots)[i + 3]]));
+  });
 }
 
 inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_t>& code, const std::vector<Registers>& vm_trace,
@@ -607,40 +631,43 @@ inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_
   ch.mix_u64(P.proof_of_work);
   lap("grind");
 
-  // ---- decommit
+  // ---- decommit: every read of every tree and FRI layer goes into one batch (one gather + one all-reduce per word size)
   uint32_t max_log = quotients[0].first;
   Queries queries = Queries::generate(ch, max_log, cfg.n_queries);
   std::map<uint32_t, std::vector<size_t>> positions_by_log;
   {
+    FetchBatch fb;
     std::map<uint32_t, std::vector<size_t>> fri_pos;
     for (auto& q : quotients) {
       Queries cq = queries.fold(max_log - q.first);
       positions_by_log[q.first] = cq.positions;
       std::vector<size_t> pos = decommitment_positions(cq.positions, 1);
       fri_pos[q.first] = pos;
-      fri_witness_sharded(B, sl, q.second, cq.positions, pos, P.fri_proof.first_layer.fri_witness);
+      fri_witness_sharded(fb, sl, q.second, cq.positions, pos, &P.fri_proof.first_layer.fri_witness);
     }
-    std::vector<std::vector<uint32_t>> unused;
-    merkle_decommit_sharded(B, sl, fri_first, first_cols, fri_pos, unused, P.fri_proof.first_layer.decommitment);
+    merkle_decommit_sharded(fb, sl, fri_first, first_cols, fri_pos, nullptr, &P.fri_proof.first_layer.decommitment);
     P.fri_proof.first_layer.commitment = fri_first.root;
+    P.fri_proof.inner_layers.resize(inner.size());
     Queries lq = queries.fold(1);
-    for (auto& L : inner) {
-      FriLayerProof lp;
+    std::vector<std::vector<RowCol>> inner_cols(inner.size());
+    for (size_t i = 0; i < inner.size(); i++) {
+      InnerLayer& L = inner[i];
+      FriLayerProof& lp = P.fri_proof.inner_layers[i];
       std::vector<size_t> pos = decommitment_positions(lq.positions, 1);
-      fri_witness_sharded(B, sl, L.eval, lq.positions, pos, lp.fri_witness);
+      fri_witness_sharded(fb, sl, L.eval, lq.positions, pos, &lp.fri_witness);
       std::map<uint32_t, std::vector<size_t>> m{{L.log, pos}};
-      std::vector<std::vector<uint32_t>> unused2;
-      merkle_decommit_sharded(B, sl, L.tree, std::vector<RowCol>(L.eval.begin(), L.eval.end()), m, unused2, lp.decommitment);
+      inner_cols[i].assign(L.eval.begin(), L.eval.end());
+      merkle_decommit_sharded(fb, sl, L.tree, inner_cols[i], m, nullptr, &lp.decommitment);
       lp.commitment = L.tree.root;
-      P.fri_proof.inner_layers.push_back(std::move(lp));
       lq = lq.fold(1);
     }
-  }
-  P.queried_values.resize(trees.size());
-  P.decommitments.resize(trees.size());
-  for (size_t t = 0; t < trees.size(); t++) {
-    P.commitments.push_back(trees[t].merkle.root);
-    merkle_decommit_sharded(B, sl, trees[t].merkle, trees[t].rows, positions_by_log, P.queried_values[t], P.decommitments[t]);
+    P.queried_values.resize(trees.size());
+    P.decommitments.resize(trees.size());
+    for (size_t t = 0; t < trees.size(); t++) {
+      P.commitments.push_back(trees[t].merkle.root);
+      merkle_decommit_sharded(fb, sl, trees[t].merkle, trees[t].rows, positions_by_log, &P.queried_values[t], &P.decommitments[t]);
+    }
+    fb.run(B);
   }
   lap("decommit");
 
