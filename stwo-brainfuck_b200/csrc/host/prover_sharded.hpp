@@ -302,26 +302,69 @@ inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_
   }
   lap("preprocessed");
 
-  // ---- phase 1: main trace.  Every rank builds the (small) compact tables; only owned columns are expanded and transformed.
-  std::vector<Table> tables = build_tables(vm_trace, code);
+  // ---- phase 1: main trace.  Table k is built by rank k % N only (host work and PCIe traffic are divided by N); the compact
+  // columns (one word per table row, 63 MB in total for fib19) are then replicated over NVLink, because LogUp generation and
+  // the 16x expansion of owned columns need them everywhere.  Only owned columns are expanded and transformed.
+  std::vector<Table> tables(N_COMPONENTS);
+  {
+    std::vector<std::string> err(N_COMPONENTS);
+    std::vector<std::thread> th;
+    for (int k = 0; k < N_COMPONENTS; k++)
+      if (k % N == me)
+        th.emplace_back([&, k] { try { tables[k] = build_table(k, vm_trace, code); } catch (const std::exception& e) { err[k] = e.what(); } });
+    for (auto& x : th) x.join();
+    for (auto& e : err) if (!e.empty()) throw std::runtime_error(e);
+  }
   lap("tables(host)");
   std::vector<std::vector<Col>> compact(N_COMPONENTS);
+  Col compact_recv = nullptr;
   {
     STree t;
+    std::vector<uint32_t> ls(N_COMPONENTS, 0);
+    for (int c = 0; c < N_COMPONENTS; c++) if (c % N == me) ls[c] = tables[c].log_size;
+    if (N > 1) B.allreduce_host(ls.data(), ls.size());
     for (int c = 0; c < N_COMPONENTS; c++) {
-      proof.log_size[c] = tables[c].log_size;
-      if (tables[c].log_size > cfg.log_max_rows) throw std::runtime_error(std::string("component too large: ") + COMPONENT_NAMES[c]);
-      for (size_t j = 0; j < tables[c].cols.size(); j++) t.logs.push_back(tables[c].log_size);
+      proof.log_size[c] = ls[c];
+      if (ls[c] > cfg.log_max_rows) throw std::runtime_error(std::string("component too large: ") + COMPONENT_NAMES[c]);
+      if (ls[c] < LOG_N_LANES) throw std::runtime_error("bad table size");
+      for (int j = 0; j < N_MAIN_COLS[c]; j++) t.logs.push_back(ls[c]);
     }
     t.owner = assign_owners(t.logs, N);
+    if (N == 1) {
+      for (int c = 0; c < N_COMPONENTS; c++)
+        for (auto& col : tables[c].cols) compact[c].push_back(B.from_host_async(col.data(), col.size()));
+    } else {
+      auto rows_of = [&](int c) { return (size_t)1 << (ls[c] - LOG_N_LANES); };
+      std::vector<size_t> scount(N, 0), rcount(N, 0);
+      for (int c = 0; c < N_COMPONENTS; c++) {
+        rcount[c % N] += rows_of(c) * N_MAIN_COLS[c];
+        if (c % N == me) for (int d = 0; d < N; d++) scount[d] += rows_of(c) * N_MAIN_COLS[c];
+      }
+      size_t mine = scount[0], rtot = 0;
+      for (int s2 = 0; s2 < N; s2++) rtot += rcount[s2];
+      Col send = B.alloc(std::max<size_t>(mine * N, 4));
+      compact_recv = B.alloc(std::max<size_t>(rtot, 4));
+      size_t so = 0;
+      std::vector<Col> up;
+      for (int c = 0; c < N_COMPONENTS; c++)
+        if (c % N == me)
+          for (auto& col : tables[c].cols) {
+            Col u = B.from_host_async(col.data(), col.size());
+            up.push_back(u);
+            for (int d = 0; d < N; d++) B.copy(send, (size_t)d * mine + so, u, 0, col.size());
+            so += col.size();
+          }
+      B.all_to_all(send, scount, compact_recv, rcount);
+      B.free_col(send);
+      for (Col u : up) B.free_col(u);
+      std::vector<size_t> roff(N, 0);
+      { size_t o = 0; for (int s2 = 0; s2 < N; s2++) { roff[s2] = o; o += rcount[s2]; } }
+      for (int c = 0; c < N_COMPONENTS; c++)
+        for (int j = 0; j < N_MAIN_COLS[c]; j++) { compact[c].push_back(B.view(compact_recv, roff[c % N], rows_of(c))); roff[c % N] += rows_of(c); }
+    }
     size_t k = 0;
     for (int c = 0; c < N_COMPONENTS; c++)
-      for (auto& col : tables[c].cols) {
-        Col cc = B.from_host_async(col.data(), col.size());
-        compact[c].push_back(cc);
-        t.polys.push_back(t.owner[k] == me ? B.broadcast16(cc) : nullptr);
-        k++;
-      }
+      for (Col cc : compact[c]) { t.polys.push_back(t.owner[k] == me ? B.broadcast16(cc) : nullptr); k++; }
     interpolate_owned(t);
     for (int c = 0; c < N_COMPONENTS; c++) ch.mix_u64(proof.log_size[c]);
     std::vector<Col> lde = lde_owned(t);
@@ -362,6 +405,7 @@ inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_
       for (Col cc : compact[c]) B.free_col(cc);
       base += nout;
     }
+    if (compact_recv) B.free_col(compact_recv);
     if (N > 1) B.allreduce_host(claimed.data(), claimed.size());
     for (int c = 0; c < N_COMPONENTS; c++) proof.claimed_sum[c] = q_make(claimed[4 * c], claimed[4 * c + 1], claimed[4 * c + 2], claimed[4 * c + 3]);
     interpolate_owned(t);
@@ -667,6 +711,7 @@ inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_
       P.commitments.push_back(trees[t].merkle.root);
       merkle_decommit_sharded(fb, sl, trees[t].merkle, trees[t].rows, positions_by_log, &P.queried_values[t], &P.decommitments[t]);
     }
+    lap("decommit:walk");
     fb.run(B);
   }
   lap("decommit");
