@@ -221,8 +221,10 @@ def bench_prove_sharded(args, torch, dist, rank, world, local, pkg, stream, be):
     dist.all_gather_object(digests, digest)
     assert len(set(digests)) == 1, "ranks disagree on the proof"
     e2e_s = max_over_ranks(torch, dist, world, max(wall / args.steps, e0.elapsed_time(e1) * 1e-3 / args.steps))
-    host_tables = float(np.mean([r["stages_ms"]["tables(host)"] for r in reports])) * 1e-3
-    dev_s = max_over_ranks(torch, dist, world, float(np.mean([r["prove_ms"] for r in reports])) * 1e-3 - host_tables)
+    # each table is built by one rank; the others wait for the slowest builder at the first collective, so the host share of
+    # a proof is the MAX over ranks of the table-building time (rank 0 builds the Memory table, the longest one)
+    host_tables = max_over_ranks(torch, dist, world, float(np.mean([r["stages_ms"]["tables(host)"] for r in reports])) * 1e-3)
+    dev_s = max_over_ranks(torch, dist, world, float(np.mean([r["prove_ms"] for r in reports])) * 1e-3) - host_tables
     stages = {k: float(np.mean([r["stages_ms"][k] for r in reports])) for k in reports[0]["stages_ms"]}
     kern = {k: v[0] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
     peak, peak_src = peaks()
