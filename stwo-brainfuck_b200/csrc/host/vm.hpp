@@ -77,7 +77,7 @@ struct Machine {
       }
       if (!early) {
         r.mv = at(r.mp);
-        r.mvi = r.mv ? sb::m_inv(r.mv) : 0;
+        r.mvi = inverse(r.mv);
       }
       r.clk += 1;
       r.ip += 1;
@@ -88,6 +88,16 @@ struct Machine {
   }
 
  private:
+  // mv.inverse() is needed at every step (machine.rs:224-228); cell values are small in practice, so remember them
+  std::vector<uint32_t> inv_cache = std::vector<uint32_t>(1 << 16, 0);
+  uint32_t inverse(uint32_t v) {
+    if (v == 0) return 0;
+    if (v < inv_cache.size()) {
+      if (!inv_cache[v]) inv_cache[v] = sb::m_inv(v);
+      return inv_cache[v];
+    }
+    return sb::m_inv(v);
+  }
   uint32_t& at(uint32_t mp) {
     if (mp >= ram.size()) throw std::runtime_error("memory pointer out of range");
     return ram[mp];
