@@ -43,6 +43,7 @@ uint64_t sc_ctx_launch_count(const sc_ctx* ctx);
  * stream; the report is "tag:milliseconds:count;..." (sum per tag since the last report) and clears the records. */
 int32_t sc_ctx_profile(sc_ctx* ctx, int32_t enable);
 size_t sc_ctx_profile_report(sc_ctx* ctx, char* buf, size_t cap);
+size_t sc_ctx_profile_timeline(sc_ctx* ctx, char* buf, size_t cap);  /* "tag:start_ms:dur_ms;" per scope, not cleared */
 
 /* ---- Column<T> (upstream core/backend/mod.rs `Column`: zeros, uninitialized, to_cpu, len, at, set, clone) ---- */
 int32_t sc_col_zeros(sc_ctx* ctx, uint64_t len, sc_col** out);
@@ -138,7 +139,8 @@ int32_t sc_gather(sc_ctx* ctx, sc_col* const* cols, const uint64_t* offsets, uin
  * 6 `,`, 7 `<`, 8 `-`, 9 `.`, 10 `+`, 11 `>`, 12 end_of_execution (BrainfuckClaim order, brainfuck_air/mod.rs:79-93).
  * main_cols: the component's main-trace evaluations, one value per 2^log_repeat rows (4 = the lane-compact form, 0 =
  * full columns); elements: 3 x {z[4], alpha_powers[7][4]} for the memory,
- * instruction and processor relations (brainfuck_air/mod.rs:149-165).  out: 4 x (#LogUp columns) new columns. ---- */
+ * instruction and processor relations (brainfuck_air/mod.rs:149-165).  out: 4 x (#LogUp columns) new columns.
+ * claimed_sum may be NULL: it is element 1 of each of the last four columns and can be fetched later (sc_gather). ---- */
 int32_t sc_logup_generate(sc_ctx* ctx, int32_t component, sc_col* const* main_cols, uint32_t n_main, uint32_t log_repeat,
                           const uint32_t* elements, sc_col** out, uint32_t claimed_sum[4]);
 /* ---- ComponentProver::evaluate_constraint_quotients_on_domain for one component (upstream constraint_framework/

@@ -64,7 +64,7 @@ ABI_SYMBOLS = [
     "sc_batch_inverse_qm31", "sc_precompute_twiddles", "sc_twiddles_free", "sc_twiddles_cached", "sc_twiddles_to_host", "sc_interpolate",
     "sc_evaluate", "sc_eval_at_point", "sc_merkle_commit_layer", "sc_merkle_commit", "sc_fold_line",
     "sc_fold_circle_into_line", "sc_accumulate_quotients", "sc_accumulate", "sc_secure_powers", "sc_grind",
-    "sc_gen_is_first", "sc_prefix_sum_bitrev", "sc_logup_generate", "sc_eval_constraints", "sc_gather", "sc_ctx_profile", "sc_ctx_profile_report",
+    "sc_gen_is_first", "sc_prefix_sum_bitrev", "sc_logup_generate", "sc_eval_constraints", "sc_gather", "sc_ctx_profile", "sc_ctx_profile_report", "sc_ctx_profile_timeline",
 ]
 PROVER_SYMBOLS = ["sbf_prove", "sbf_verify", "sbf_proof_json", "sbf_proof_report", "sbf_proof_output", "sbf_string_free",
                   "sbf_proof_free", "sbf_proof_tamper", "sbf_last_error"]
@@ -179,6 +179,19 @@ class CudaBackend:
             if item:
                 tag, ms, cnt = item.split(":")
                 out[tag] = (float(ms), int(cnt))
+        return out
+
+    def profile_timeline(self) -> list:
+        """[(tag, start_ms, dur_ms)] of every scope since the last report, in launch order (call before profile_report)."""
+        self._lib.sc_ctx_profile_timeline.restype = ctypes.c_size_t
+        need = self._lib.sc_ctx_profile_timeline(self._ctx, None, ctypes.c_size_t(0))
+        buf = ctypes.create_string_buffer(int(need) + 1)
+        self._lib.sc_ctx_profile_timeline(self._ctx, buf, ctypes.c_size_t(len(buf)))
+        out = []
+        for item in buf.value.decode().split(";"):
+            if item:
+                tag, t0, ms = item.split(":")
+                out.append((tag, float(t0), float(ms)))
         return out
 
     def close(self) -> None:

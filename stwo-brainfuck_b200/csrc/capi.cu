@@ -84,6 +84,23 @@ size_t sc_ctx_profile_report(sc_ctx* ctx, char* buf, size_t cap) {
   return out.size() + 1;
 }
 
+// Per-scope GPU timeline of the records collected so far ("tag:start_ms:dur_ms;" relative to the first record); does not
+// clear them, so call it before sc_ctx_profile_report.  Holes between consecutive records are time the GPU sat idle.
+size_t sc_ctx_profile_timeline(sc_ctx* ctx, char* buf, size_t cap) {
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->st);
+  std::string out;
+  for (auto& r : ctx->prof) {
+    float t0 = 0, ms = 0;
+    cudaEventElapsedTime(&t0, ctx->prof.front().a, r.a);
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    char t[160]; snprintf(t, sizeof t, "%s:%.6f:%.6f;", r.tag, t0, ms); out += t;
+  }
+  if (buf && cap) { size_t n = std::min(cap - 1, out.size()); memcpy(buf, out.data(), n); buf[n] = 0; }
+  return out.size() + 1;
+}
+
 // ------------------------------------------------------------------ columns
 int32_t sc_col_uninit(sc_ctx* ctx, uint64_t len, sc_col** out) { ENTER(); if (!out) return fail(SC_EINVAL, "null out"); return new_col(ctx, len, out); }
 int32_t sc_col_zeros(sc_ctx* ctx, uint64_t len, sc_col** out) {
@@ -526,12 +543,13 @@ int32_t sc_gen_is_first(sc_ctx* ctx, uint32_t log_size, sc_col** out) {
   { ProfScope ps_(ctx, "gen_is_first"); CKL(launch_gen_is_first((*out)->d, log_size, ctx->st)); }
   return SC_OK;
 }
+static inline size_t prefix_scratch_words(uint64_t len) { return ((len + 2 * ((len >> 11) + 2) + 8) + 3) & ~(size_t)3; }
 int32_t sc_prefix_sum_bitrev(sc_ctx* ctx, sc_col* col) {
   ENTER();
   if (!col || !is_pow2(col->len) || col->len < 2) return fail(SC_EINVAL, "prefix_sum: length must be a power of two >= 2");
   uint32_t lg = ilog2(col->len);
   uint32_t* scratch;
-  size_t words = col->len + 2 * ((col->len >> 11) + 2) + 8;
+  size_t words = prefix_scratch_words(col->len);
   CK(cudaMallocAsync((void**)&scratch, words * 4, ctx->st));
   { ProfScope ps_(ctx, "prefix_sum"); CKL(launch_prefix_sum_bitrev(col->d, lg, scratch, ctx->st)); }
   CK(cudaFreeAsync(scratch, ctx->st));
@@ -564,7 +582,7 @@ int32_t sc_gather(sc_ctx* ctx, sc_col* const* cols, const uint64_t* offsets, uin
 int32_t sc_logup_generate(sc_ctx* ctx, int32_t component, sc_col* const* main_cols, uint32_t n_main, uint32_t log_repeat,
                           const uint32_t* elements, sc_col** out, uint32_t claimed_sum[4]) {
   ENTER();
-  if (component < 0 || component >= sbf::N_COMPONENTS || !main_cols || !elements || !out || !claimed_sum) return fail(SC_EINVAL, "logup_generate: bad argument");
+  if (component < 0 || component >= sbf::N_COMPONENTS || !main_cols || !elements || !out) return fail(SC_EINVAL, "logup_generate: bad argument");
   if ((int)n_main != sbf::N_MAIN_COLS[component]) return fail(SC_EINVAL, "logup_generate: wrong number of main columns");
   if (!main_cols[0] || log_repeat > 8) return fail(SC_EINVAL, "logup_generate: bad argument");
   uint64_t len = main_cols[0]->len << log_repeat;
@@ -582,8 +600,16 @@ int32_t sc_logup_generate(sc_ctx* ctx, int32_t component, sc_col* const* main_co
   memcpy(&p.el, elements, sizeof(p.el));
   { ProfScope ps_(ctx, "logup_generate"); CKL(launch_air(false, component, p, ctx->st)); }
   // LogupTraceGenerator::finalize_last: prefix-sum the last column's coordinates in coset order; claimed_sum = col.at(1)
-  for (int k = 0; k < 4; k++) { r = sc_prefix_sum_bitrev(ctx, out[nout - 4 + k]); if (r) return r; }
-  for (int k = 0; k < 4; k++) { r = sc_col_read(ctx, out[nout - 4 + k], 1, 1, &claimed_sum[k]); if (r) return r; }
+  {
+    uint32_t* scratch;
+    size_t words = prefix_scratch_words(len);
+    CK(cudaMallocAsync((void**)&scratch, 4 * words * 4, ctx->st));
+    uint32_t* v4[4] = {op[nout - 4], op[nout - 3], op[nout - 2], op[nout - 1]};
+    { ProfScope ps_(ctx, "prefix_sum"); CKL(launch_prefix_sum_bitrev4(v4, p.log_size, scratch, words, ctx->st)); }
+    CK(cudaFreeAsync(scratch, ctx->st));
+  }
+  // claimed_sum == NULL: the caller reads element 1 of the last four columns itself (e.g. one sc_gather for all components)
+  if (claimed_sum) for (int k = 0; k < 4; k++) { r = sc_col_read(ctx, out[nout - 4 + k], 1, 1, &claimed_sum[k]); if (r) return r; }
   return SC_OK;
 }
 

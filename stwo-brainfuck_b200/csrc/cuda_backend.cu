@@ -101,6 +101,12 @@ struct CudaBackendImpl : Backend {
                          (sc_col**)out.data(), (uint32_t*)&claimed));
     return out;
   }
+  std::vector<Col> logup_generate_deferred(int comp, const std::vector<Col>& main, const InteractionElements& el) override {
+    std::vector<Col> out(4 * N_LOGUP_COLS[comp]);
+    ck(sc_logup_generate(ctx, comp, (sc_col* const*)main.data(), (uint32_t)main.size(), LOG_N_LANES, (const uint32_t*)&el,
+                         (sc_col**)out.data(), nullptr));
+    return out;
+  }
   void eval_constraints(int comp, uint32_t log_size, const std::vector<Col>& m, const std::vector<Col>& it, Col is_first,
                         const InteractionElements& el, QM31 total, const std::vector<QM31>& coeffs, const std::array<Col, 4>& acc) override {
     ck(sc_eval_constraints(ctx, comp, log_size, (sc_col* const*)m.data(), (uint32_t)m.size(), (sc_col* const*)it.data(), (uint32_t)it.size(),

@@ -59,6 +59,11 @@ struct Backend {
   // constraint_framework
   virtual Col gen_is_first(uint32_t log_size) = 0;
   virtual std::vector<Col> logup_generate(int comp, const std::vector<Col>& main, const InteractionElements& el, QM31& claimed_sum) = 0;
+  // same without the read-back: the claimed sum is element 1 of each of the last four returned columns (fetch them with one gather)
+  virtual std::vector<Col> logup_generate_deferred(int comp, const std::vector<Col>& main, const InteractionElements& el) {
+    QM31 s;
+    return logup_generate(comp, main, el, s);
+  }
   virtual void eval_constraints(int comp, uint32_t log_size, const std::vector<Col>& main_lde, const std::vector<Col>& inter_lde,
                                 Col is_first_lde, const InteractionElements& el, QM31 total_sum, const std::vector<QM31>& coeffs,
                                 const std::array<Col, 4>& accum) = 0;

@@ -122,16 +122,30 @@ inline InteractionElements draw_elements(Channel& ch) {  // BrainfuckInteraction
   return el;
 }
 
-// MerkleProver::decommit (core/vcs/prover.rs): values come back per column in the original column order.
-// The walk over the layers only needs indices, so it first records every element it would read (`Column::at` upstream) and
-// then fetches them with two batched gathers (hashes, column values) instead of thousands of 4..32-byte copies.
-inline void merkle_decommit(Backend& B, const CommitTree& t, const std::vector<Col>& columns, const std::map<uint32_t, std::vector<size_t>>& queries,
-                            std::vector<std::vector<uint32_t>>& queried_values, MerkleDecommitment& d) {
-  queried_values.assign(columns.size(), {});
+// Every element the decommit phase reads (`Column::at` upstream) is known from the query positions alone, so the walks
+// below only record what they need; one flush then fetches everything with two batched gathers (32-byte hashes, 4-byte
+// values) and hands each walk its slice.  Output references passed to the walks must stay valid until flush().
+struct GatherQueue {
+  Backend& B;
   std::vector<Col> hcols, vcols;
   std::vector<size_t> hoff, voff;
+  std::vector<std::function<void(const uint32_t*, const uint32_t*)>> done;
+  explicit GatherQueue(Backend& b) : B(b) {}
+  void flush() {
+    std::vector<uint32_t> hw = B.gather(hcols, hoff, 8), vw = B.gather(vcols, voff, 1);
+    for (auto& f : done) f(hw.data(), vw.data());
+    hcols.clear(); vcols.clear(); hoff.clear(); voff.clear(); done.clear();
+  }
+};
+
+// MerkleProver::decommit (core/vcs/prover.rs): values come back per column in the original column order.
+inline void merkle_decommit(GatherQueue& G, const CommitTree& t, const std::vector<Col>& columns, const std::map<uint32_t, std::vector<size_t>>& queries,
+                            std::vector<std::vector<uint32_t>>* queried_values, MerkleDecommitment& d) {
+  Backend& B = G.B;
+  if (queried_values) queried_values->assign(columns.size(), {});
   struct VReq { size_t col; bool queried; };
   std::vector<VReq> vreq;
+  const size_t hbase = G.hcols.size(), vbase = G.vcols.size();
   std::vector<size_t> last_queries;
   int n_layers = (int)t.layers.size();
   for (int lg = n_layers - 1; lg >= 0; lg--) {
@@ -150,36 +164,42 @@ inline void merkle_decommit(Backend& B, const CommitTree& t, const std::vector<C
       if (lg + 1 < n_layers) {
         for (size_t child = 2 * node; child <= 2 * node + 1; child++) {
           if (pi < last_queries.size() && last_queries[pi] == child) pi++;
-          else { hcols.push_back(t.layers[lg + 1]); hoff.push_back(8 * child); }
+          else { G.hcols.push_back(t.layers[lg + 1]); G.hoff.push_back(8 * child); }
         }
       }
       bool queried = ci < colq.size() && colq[ci] == node;
       if (queried) ci++;
-      for (size_t c : lcols) { vcols.push_back(columns[c]); voff.push_back(node); vreq.push_back({c, queried}); }
+      for (size_t c : lcols) { G.vcols.push_back(columns[c]); G.voff.push_back(node); vreq.push_back({c, queried}); }
       total.push_back(node);
     }
     last_queries = total;
   }
-  std::vector<uint32_t> hw = B.gather(hcols, hoff, 8), vw = B.gather(vcols, voff, 1);
-  for (size_t i = 0; i < hcols.size(); i++) { Hash h; memcpy(h.data(), &hw[8 * i], 32); d.hash_witness.push_back(h); }
-  for (size_t i = 0; i < vreq.size(); i++) {
-    if (vreq[i].queried) queried_values[vreq[i].col].push_back(vw[i]); else d.column_witness.push_back(vw[i]);
-  }
+  const size_t nh = G.hcols.size() - hbase;
+  G.done.push_back([hbase, vbase, nh, vreq = std::move(vreq), queried_values, &d](const uint32_t* hw, const uint32_t* vw) {
+    for (size_t i = 0; i < nh; i++) { Hash h; memcpy(h.data(), hw + 8 * (hbase + i), 32); d.hash_witness.push_back(h); }
+    for (size_t i = 0; i < vreq.size(); i++) {
+      uint32_t v = vw[vbase + i];
+      if (!vreq[i].queried) d.column_witness.push_back(v);
+      else if (queried_values) (*queried_values)[vreq[i].col].push_back(v);
+    }
+  });
 }
 
 // FRI witness evaluations of one layer: the positions of each fold coset that are not themselves queried.
-inline void fri_witness(Backend& B, const std::array<Col, 4>& eval, const std::vector<size_t>& queries, const std::vector<size_t>& pos,
+inline void fri_witness(GatherQueue& G, const std::array<Col, 4>& eval, const std::vector<size_t>& queries, const std::vector<size_t>& pos,
                         std::vector<QM31>& out) {
-  std::vector<Col> cols;
-  std::vector<size_t> off;
+  const size_t vbase = G.vcols.size();
   size_t k = 0;
   for (size_t p : pos) {
     while (k < queries.size() && queries[k] < p) k++;
     if (k < queries.size() && queries[k] == p) continue;
-    for (int c = 0; c < 4; c++) { cols.push_back(eval[c]); off.push_back(p); }
+    for (int c = 0; c < 4; c++) { G.vcols.push_back(eval[c]); G.voff.push_back(p); }
   }
-  std::vector<uint32_t> w = B.gather(cols, off, 1);
-  for (size_t i = 0; i + 3 < w.size(); i += 4) out.push_back(q_make(w[i], w[i + 1], w[i + 2], w[i + 3]));
+  const size_t n = G.vcols.size() - vbase;
+  G.done.push_back([vbase, n, &out](const uint32_t*, const uint32_t* vw) {
+    const uint32_t* w = vw + vbase;
+    for (size_t i = 0; i + 3 < n; i += 4) out.push_back(q_make(w[i], w[i + 1], w[i + 2], w[i + 3]));
+  });
 }
 
 struct ProveResult {
@@ -258,10 +278,16 @@ inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code
   InteractionElements el = draw_elements(ch);
   {
     CommitTree t;
+    std::vector<Col> sum_cols;
     for (int c = 0; c < N_COMPONENTS; c++) {
-      std::vector<Col> cols = B.logup_generate(c, compact[c], el, proof.claimed_sum[c]);
+      std::vector<Col> cols = B.logup_generate_deferred(c, compact[c], el);
       for (Col cc : compact[c]) B.free_col(cc);
       for (Col x : cols) { t.polys.push_back(x); t.logs.push_back(proof.log_size[c]); }
+      sum_cols.insert(sum_cols.end(), cols.end() - 4, cols.end());
+    }
+    {  // claimed sums (LogupTraceGenerator::finalize_last: the cumulative column at index 1), one read-back for all components
+      std::vector<uint32_t> w = B.gather(sum_cols, std::vector<size_t>(sum_cols.size(), 1), 1);
+      for (int c = 0; c < N_COMPONENTS; c++) proof.claimed_sum[c] = q_make(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
     }
     B.interpolate(t.polys);
     for (int c = 0; c < N_COMPONENTS; c++) ch.mix_felts({proof.claimed_sum[c]});
@@ -409,6 +435,8 @@ inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code
   uint32_t max_log = quotients[0].first;
   Queries queries = Queries::generate(ch, max_log, cfg.n_queries);
   std::map<uint32_t, std::vector<size_t>> positions_by_log;
+  GatherQueue G(B);
+  P.fri_proof.inner_layers.resize(inner.size());  // the queued walks keep references into these
   {
     std::map<uint32_t, std::vector<size_t>> fri_pos;
     for (auto& q : quotients) {
@@ -416,21 +444,19 @@ inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code
       positions_by_log[q.first] = cq.positions;
       std::vector<size_t> pos = decommitment_positions(cq.positions, 1);
       fri_pos[q.first] = pos;
-      fri_witness(B, q.second, cq.positions, pos, P.fri_proof.first_layer.fri_witness);
+      fri_witness(G, q.second, cq.positions, pos, P.fri_proof.first_layer.fri_witness);
     }
-    std::vector<std::vector<uint32_t>> unused;
-    merkle_decommit(B, fri_first, first_cols, fri_pos, unused, P.fri_proof.first_layer.decommitment);
+    merkle_decommit(G, fri_first, first_cols, fri_pos, nullptr, P.fri_proof.first_layer.decommitment);
     P.fri_proof.first_layer.commitment = fri_first.root;
     Queries lq = queries.fold(1);
-    for (auto& L : inner) {
-      FriLayerProof lp;
+    for (size_t li = 0; li < inner.size(); li++) {
+      auto& L = inner[li];
+      FriLayerProof& lp = P.fri_proof.inner_layers[li];
       std::vector<size_t> pos = decommitment_positions(lq.positions, 1);
-      fri_witness(B, L.eval, lq.positions, pos, lp.fri_witness);
+      fri_witness(G, L.eval, lq.positions, pos, lp.fri_witness);
       std::map<uint32_t, std::vector<size_t>> m{{L.log, pos}};
-      std::vector<std::vector<uint32_t>> unused2;
-      merkle_decommit(B, L.tree, {L.eval[0], L.eval[1], L.eval[2], L.eval[3]}, m, unused2, lp.decommitment);
+      merkle_decommit(G, L.tree, {L.eval[0], L.eval[1], L.eval[2], L.eval[3]}, m, nullptr, lp.decommitment);
       lp.commitment = L.tree.root;
-      P.fri_proof.inner_layers.push_back(std::move(lp));
       lq = lq.fold(1);
     }
   }
@@ -439,8 +465,9 @@ inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code
   P.decommitments.resize(trees.size());
   for (size_t t = 0; t < trees.size(); t++) {
     P.commitments.push_back(trees[t].root);
-    merkle_decommit(B, trees[t], trees[t].evals, positions_by_log, P.queried_values[t], P.decommitments[t]);
+    merkle_decommit(G, trees[t], trees[t].evals, positions_by_log, &P.queried_values[t], P.decommitments[t]);
   }
+  G.flush();
   lap("decommit");
 
   // ---- sanity check (ProvingError::ConstraintsNotSatisfied)

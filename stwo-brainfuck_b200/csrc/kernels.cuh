@@ -32,6 +32,7 @@ int launch_accumulate(uint32_t* const dst[4], const uint32_t* const src[4], size
 int launch_fill(uint32_t* v, size_t n, uint32_t value, cudaStream_t st);
 int launch_gen_is_first(uint32_t* v, uint32_t log, cudaStream_t st);
 int launch_prefix_sum_bitrev(uint32_t* v, uint32_t log, uint32_t* scratch, cudaStream_t st);
+int launch_prefix_sum_bitrev4(uint32_t* const v[4], uint32_t log, uint32_t* scratch, size_t words, cudaStream_t st);
 struct EvalTaskHost {  // mirrors ops.cu EvalTask
   const uint32_t* coeffs;
   uint32_t log;

@@ -246,6 +246,68 @@ int launch_prefix_sum_bitrev(uint32_t* v, uint32_t log, uint32_t* scratch, cudaS
   return (int)cudaGetLastError();
 }
 
+// The four coordinate columns of one LogUp batch in one launch set (grid.y = coordinate); scratch holds four regions of
+// `words` words laid out as above.
+struct Scan4 { uint32_t* v[4]; uint32_t* nat[4]; unsigned long long* sums[4]; };
+__global__ void __launch_bounds__(256) scan_gather4_kernel(Scan4 a, uint32_t log) {
+  const uint32_t n = 1u << log;
+  const uint32_t base = blockIdx.x << SCAN_CHUNK_LOG;
+  const uint32_t* __restrict__ v = a.v[blockIdx.y];
+  uint32_t* __restrict__ nat = a.nat[blockIdx.y];
+  unsigned long long s = 0;
+#pragma unroll
+  for (uint32_t k = 0; k < 8; k++) {
+    uint32_t i = base + k * 256 + threadIdx.x;
+    if (i < n) { uint32_t x = v[coset_to_storage(i, log)]; nat[i] = x; s += x; }
+  }
+  unsigned long long tot;
+  block_exclusive_scan(s, &tot);
+  if (threadIdx.x == 0) a.sums[blockIdx.y][blockIdx.x] = tot % P;
+}
+__global__ void __launch_bounds__(256) scan_chunks4_kernel(Scan4 a, uint32_t nchunks) {
+  unsigned long long* __restrict__ chunk_sums = a.sums[blockIdx.x];
+  unsigned long long carry = 0;
+  for (uint32_t b = 0; b < nchunks; b += 256) {
+    uint32_t i = b + threadIdx.x;
+    unsigned long long x = i < nchunks ? chunk_sums[i] : 0, tot;
+    unsigned long long ex = block_exclusive_scan(x, &tot);
+    if (i < nchunks) chunk_sums[i] = (carry + ex) % P;
+    carry = (carry + tot) % P;
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(256) scan_scatter4_kernel(Scan4 a, uint32_t log) {
+  const uint32_t n = 1u << log;
+  const uint32_t base = (blockIdx.x << SCAN_CHUNK_LOG) + threadIdx.x * 8;
+  uint32_t* __restrict__ v = a.v[blockIdx.y];
+  const uint32_t* __restrict__ nat = a.nat[blockIdx.y];
+  unsigned long long x[8], s = 0;
+#pragma unroll
+  for (uint32_t k = 0; k < 8; k++) { x[k] = (base + k < n) ? nat[base + k] : 0; s += x[k]; }
+  unsigned long long tot;
+  unsigned long long run = block_exclusive_scan(s, &tot) + a.sums[blockIdx.y][blockIdx.x];
+#pragma unroll
+  for (uint32_t k = 0; k < 8; k++) {
+    run += x[k];
+    if (base + k < n) v[coset_to_storage(base + k, log)] = (uint32_t)(run % P);
+  }
+}
+int launch_prefix_sum_bitrev4(uint32_t* const v[4], uint32_t log, uint32_t* scratch, size_t words, cudaStream_t st) {
+  uint32_t n = 1u << log;
+  uint32_t nchunks = (n + (1u << SCAN_CHUNK_LOG) - 1) >> SCAN_CHUNK_LOG;
+  Scan4 a;
+  for (int k = 0; k < 4; k++) {
+    uint32_t* s = scratch + (size_t)k * words;
+    a.v[k] = v[k];
+    a.sums[k] = reinterpret_cast<unsigned long long*>(s);
+    a.nat[k] = s + 2 * (size_t)((nchunks + 1) & ~1u) + 2;
+  }
+  scan_gather4_kernel<<<dim3(nchunks, 4), 256, 0, st>>>(a, log); g_launch_count++;
+  scan_chunks4_kernel<<<4, 256, 0, st>>>(a, nchunks); g_launch_count++;
+  scan_scatter4_kernel<<<dim3(nchunks, 4), 256, 0, st>>>(a, log); g_launch_count++;
+  return (int)cudaGetLastError();
+}
+
 // ---------------------------------------------------------------- eval_at_point
 // value = sum_i c_i * prod_k f_k^{bit_k(i)},  f = [p.y, p.x, pi(p.x), pi^2(p.x), ...]   (CpuBackend fold()).
 // Stage 1: a CTA folds 2^13 base-field coefficients -> one QM31 partial.  A thread owns 32 consecutive coefficients and
