@@ -51,7 +51,9 @@ int32_t sc_col_uninit(sc_ctx* ctx, uint64_t len, sc_col** out);
 int32_t sc_col_from_host(sc_ctx* ctx, const uint32_t* host, uint64_t len, sc_col** out);   /* FromIterator */
 /* Upload without waiting: `host` must stay valid until the next synchronising call; pinned memory (sc_host_arena_alloc)
  * makes it a true asynchronous DMA.  The reference fills its columns in ordinary host memory (e.g. processor/table.rs:
- * 86-100); filling them in this arena instead removes the staged pageable copy from the upload. */
+ * 86-100); filling them in this arena instead removes the staged pageable copy from the upload.  The copy runs on a
+ * second stream owned by the context, beside kernels already queued; every other entry point first makes the compute
+ * stream wait for the uploads issued so far. */
 int32_t sc_col_from_host_async(sc_ctx* ctx, const uint32_t* host, uint64_t len, sc_col** out);
 int32_t sc_host_arena_alloc(sc_ctx* ctx, uint64_t bytes, void** out);   /* thread-safe bump allocation, 64-byte aligned */
 int32_t sc_host_arena_reset(sc_ctx* ctx);                               /* releases every allocation, keeps the blocks */
@@ -132,6 +134,24 @@ int32_t sc_prefix_sum_bitrev(sc_ctx* ctx, sc_col* col);
 /* ---- batched `Column::at` for decommitment (MerkleProver::decommit / FriProver::decommit read single elements):
  * out_host[i*words .. +words) = cols[i][offsets[i] .. +words). ---- */
 int32_t sc_gather(sc_ctx* ctx, sc_col* const* cols, const uint64_t* offsets, uint32_t n, uint32_t words, uint32_t* out_host);
+
+/* ---- Lane-repeated columns.  The reference writes every table row into all 16 SIMD lanes of a trace column
+ * (components/processor/table.rs:86-100 and the six other table.rs files: `data[vec_row] = value.into()`), so a main-trace
+ * evaluation of log size m+4 holds 2^m distinct values, each filling 16 consecutive (bit-reversed-order) rows.  Such a
+ * column's polynomial has one non-zero coefficient in 16 and the first four FFT layers only scale / replicate, so
+ * PolyOps::interpolate_columns / evaluate_polynomials / eval_at_point and MerkleOps::commit_on_layer can work on the 2^m
+ * values.  A column passed here stores the distinct values (or compact coefficients: coefficient j = coefficient j<<r of the
+ * full vector).  sc_evaluate_repeated returns ordinary full-length columns, bit-identical to sc_evaluate of the expanded
+ * input.  The *_repeated Merkle calls take ordinary full columns and rely on the caller's promise that they repeat. ---- */
+int32_t sc_interpolate_repeated(sc_ctx* ctx, sc_col* const* cols, uint32_t n, uint32_t log_repeat, const sc_twiddles* tw);
+int32_t sc_evaluate_repeated(sc_ctx* ctx, sc_col* const* coeffs, uint32_t n, uint32_t log_repeat, uint32_t log_blowup,
+                             const sc_twiddles* tw, sc_col** out);
+int32_t sc_eval_at_point_repeated(sc_ctx* ctx, sc_col* const* polys, const uint32_t* log_repeats, uint32_t n,
+                                  const uint32_t* points, uint32_t* out);
+int32_t sc_merkle_commit_layer_repeated(sc_ctx* ctx, uint32_t log_size, const sc_col* prev, sc_col* const* cols, uint32_t n,
+                                        uint32_t log_repeat, sc_col** out);
+int32_t sc_merkle_commit_repeated(sc_ctx* ctx, sc_col* const* cols, uint32_t n, uint32_t log_repeat, sc_col** layers_out,
+                                  uint32_t* max_log_out, uint32_t root_out[8]);
 
 /* ---- LogupTraceGenerator for one component: write_frac / finalize_col per relation entry, finalize_last.
  * Stands in for the reference's interaction_trace_evaluation (e.g. crates/brainfuck_prover/src/components/processor/

@@ -174,6 +174,52 @@ struct OrcBackend : Backend {
       out[i] = sq(orc::eval_at_point(H(polys[i])->d, lg2(H(polys[i])->n), orc::QPt{oq(pts[i].x), oq(pts[i].y)}));
     return out;
   }
+  // Lane-repeated columns the slow, obvious way: expand, run the plain transform, check the claimed structure, compact.
+  static HCol* expand_values(const HCol* c, uint32_t rep) {
+    HCol* o = new HCol(c->n << rep);
+    for (size_t i = 0; i < o->n; i++) o->d[i] = c->d[i >> rep];
+    return o;
+  }
+  static HCol* expand_coeffs(const HCol* c, uint32_t rep, uint32_t log_blowup) {
+    HCol* o = new HCol((c->n << rep) << log_blowup);  // HCol(n) is zero-filled
+    for (size_t i = 0; i < c->n; i++) o->d[i << rep] = c->d[i];
+    return o;
+  }
+  void interpolate_repeated(const std::vector<Col>& cols, uint32_t rep) override {
+    bool bad = false;
+#pragma omp parallel for schedule(dynamic)
+    for (size_t i = 0; i < cols.size(); i++) {
+      HCol* full = expand_values(H(cols[i]), rep);
+      orc::interpolate(full->d, lg2(full->n), itw);
+      for (size_t j = 0; j < full->n; j++) {
+        if ((j & (((size_t)1 << rep) - 1)) == 0) H(cols[i])->d[j >> rep] = full->d[j];
+        else if (full->d[j] != 0) bad = true;
+      }
+      delete full;
+    }
+    if (bad) throw std::runtime_error("oracle: a repeated column has a non-zero coefficient off the 2^rep grid");
+  }
+  std::vector<Col> evaluate_repeated(const std::vector<Col>& coeffs, uint32_t rep, uint32_t log_blowup) override {
+    std::vector<Col> out(coeffs.size());
+#pragma omp parallel for schedule(dynamic)
+    for (size_t i = 0; i < coeffs.size(); i++) {
+      HCol* o = expand_coeffs(H(coeffs[i]), rep, log_blowup);
+      orc::evaluate(o->d, lg2(o->n), tw);
+      out[i] = o;
+    }
+    return out;
+  }
+  std::vector<sb::QM31> eval_at_point_repeated(const std::vector<Col>& polys, const std::vector<uint32_t>& reps, const std::vector<QPoint>& pts) override {
+    std::vector<sb::QM31> out(polys.size());
+#pragma omp parallel for schedule(dynamic)
+    for (size_t i = 0; i < polys.size(); i++) {
+      HCol* full = expand_coeffs(H(polys[i]), reps[i], 0);
+      out[i] = sq(orc::eval_at_point(full->d, lg2(full->n), orc::QPt{oq(pts[i].x), oq(pts[i].y)}));
+      delete full;
+    }
+    return out;
+  }
+  std::vector<Col> merkle_commit_repeated(const std::vector<Col>& cols, uint32_t, Hash* root) override { return merkle_commit(cols, root); }
   std::vector<Col> merkle_commit(const std::vector<Col>& cols, Hash* root) override {
     std::vector<const uint32_t*> p;
     std::vector<uint32_t> logs;

@@ -64,7 +64,8 @@ ABI_SYMBOLS = [
     "sc_batch_inverse_qm31", "sc_precompute_twiddles", "sc_twiddles_free", "sc_twiddles_cached", "sc_twiddles_to_host", "sc_interpolate",
     "sc_evaluate", "sc_eval_at_point", "sc_merkle_commit_layer", "sc_merkle_commit", "sc_fold_line",
     "sc_fold_circle_into_line", "sc_accumulate_quotients", "sc_accumulate", "sc_secure_powers", "sc_grind",
-    "sc_gen_is_first", "sc_prefix_sum_bitrev", "sc_logup_generate", "sc_eval_constraints", "sc_gather", "sc_ctx_profile", "sc_ctx_profile_report", "sc_ctx_profile_timeline",
+    "sc_gen_is_first", "sc_prefix_sum_bitrev", "sc_logup_generate", "sc_eval_constraints", "sc_gather", "sc_ctx_profile", "sc_ctx_profile_report", "sc_ctx_profile_timeline", "sc_interpolate_repeated", "sc_evaluate_repeated", "sc_eval_at_point_repeated",
+    "sc_merkle_commit_layer_repeated", "sc_merkle_commit_repeated",
 ]
 PROVER_SYMBOLS = ["sbf_prove", "sbf_verify", "sbf_proof_json", "sbf_proof_report", "sbf_proof_output", "sbf_string_free",
                   "sbf_proof_free", "sbf_proof_tamper", "sbf_last_error"]
@@ -256,6 +257,37 @@ class CudaBackend:
         out = np.empty((len(polys), 4), dtype=np.uint32)
         self._ck(self._lib.sc_eval_at_point(self._ctx, self._arr(polys), ctypes.c_uint32(len(polys)), _ptr(pts), _ptr(out)))
         return out
+
+    # -- lane-repeated columns (include/stwo_cuda.h: every stored value stands for 2^log_repeat consecutive rows)
+    def interpolate_repeated(self, cols: Sequence[Column], log_repeat: int, twiddles: Twiddles) -> None:
+        """In place: the distinct values -> the non-zero coefficients (coefficient j = coefficient j << log_repeat)."""
+        self._ck(self._lib.sc_interpolate_repeated(self._ctx, self._arr(cols), ctypes.c_uint32(len(cols)), ctypes.c_uint32(log_repeat),
+                                                   twiddles._h))
+
+    def evaluate_repeated(self, coeffs: Sequence[Column], log_repeat: int, log_blowup: int, twiddles: Twiddles) -> List[Column]:
+        """Compact coefficients -> ordinary full-length evaluations on the (blown-up) domain."""
+        out = (_vp * max(1, len(coeffs)))()
+        self._ck(self._lib.sc_evaluate_repeated(self._ctx, self._arr(coeffs), ctypes.c_uint32(len(coeffs)), ctypes.c_uint32(log_repeat),
+                                                ctypes.c_uint32(log_blowup), twiddles._h, out))
+        return [Column(self, _vp(out[i])) for i in range(len(coeffs))]
+
+    def eval_at_point_repeated(self, polys: Sequence[Column], log_repeats, points) -> np.ndarray:
+        pts = _np_u32(points).reshape(len(polys), 8)
+        reps = _np_u32(log_repeats)
+        out = np.empty((len(polys), 4), dtype=np.uint32)
+        self._ck(self._lib.sc_eval_at_point_repeated(self._ctx, self._arr(polys), _ptr(reps), ctypes.c_uint32(len(polys)), _ptr(pts),
+                                                     _ptr(out)))
+        return out
+
+    def merkle_commit_repeated(self, columns: Sequence[Column], log_repeat: int):
+        """merkle_commit for full-length columns that all repeat each value 2^log_repeat times."""
+        max_log = max(int(np.log2(len(c))) for c in columns) if columns else 0
+        layers = (_vp * (max_log + 1))()
+        ml = ctypes.c_uint32()
+        root = np.empty(8, dtype=np.uint32)
+        self._ck(self._lib.sc_merkle_commit_repeated(self._ctx, self._arr(columns), ctypes.c_uint32(len(columns)),
+                                                     ctypes.c_uint32(log_repeat), layers, ctypes.byref(ml), _ptr(root)))
+        return [Column(self, _vp(layers[i])) for i in range(max_log + 1)], root
 
     # -- MerkleOps<Blake2sMerkleHasher>
     def commit_on_layer(self, log_size: int, prev_layer: Optional[Column], columns: Sequence[Column]) -> Column:

@@ -54,6 +54,7 @@ int32_t sc_ctx_destroy(sc_ctx* ctx) {
   for (auto& b : ctx->arena) cudaFreeHost(b.p);
   for (auto& kv : ctx->tw_cache) { cudaFree(kv.second->tw); cudaFree(kv.second->itw); delete kv.second; }
   cudaFree(ctx->d_ring);
+  if (ctx->copy_st) { cudaStreamSynchronize(ctx->copy_st); cudaStreamDestroy(ctx->copy_st); cudaEventDestroy(ctx->copy_ev); }
   if (ctx->own_stream) cudaStreamDestroy(ctx->st);
   delete ctx;
   return SC_OK;
@@ -123,11 +124,19 @@ int32_t sc_col_from_host(sc_ctx* ctx, const uint32_t* host, uint64_t len, sc_col
 // Same as sc_col_from_host but does not wait: `host` must stay valid (and should be pinned, e.g. from sc_host_arena_alloc,
 // for the copy to be a real asynchronous DMA) until the next synchronising call on this context.
 int32_t sc_col_from_host_async(sc_ctx* ctx, const uint32_t* host, uint64_t len, sc_col** out) {
-  ENTER();
+  ENTER_NOJOIN();
   if (!out || (!host && len)) return fail(SC_EINVAL, "null argument");
-  int32_t r = new_col(ctx, len, out);
-  if (r) return r;
-  CK(cudaMemcpyAsync((*out)->d, host, len * 4, cudaMemcpyHostToDevice, ctx->st));
+  if (!ctx->copy_st) {
+    CK(cudaStreamCreateWithFlags(&ctx->copy_st, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->copy_ev, cudaEventDisableTiming));
+  }
+  // allocated and filled on the copy stream: independent of whatever is queued on the compute stream
+  uint32_t* d = nullptr;
+  cudaError_t e = cudaMallocAsync((void**)&d, std::max<uint64_t>(len, 4) * 4, ctx->copy_st);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(SC_ENOMEM, std::string("cudaMallocAsync: ") + cudaGetErrorString(e)); }
+  *out = new sc_col{d, len};
+  CK(cudaMemcpyAsync(d, host, len * 4, cudaMemcpyHostToDevice, ctx->copy_st));
+  ctx->uploads_pending = true;
   return SC_OK;
 }
 // Pinned host arena owned by the context: thread-safe bump allocation (64-byte aligned); reset releases everything at once
@@ -342,7 +351,81 @@ int32_t sc_evaluate(sc_ctx* ctx, sc_col* const* coeffs, uint32_t n, uint32_t log
   return SC_OK;
 }
 
+// ---- lane-repeated columns.  A column of 2^m stored values stands for an evaluation of log size m + log_repeat in which
+// every value fills 2^log_repeat consecutive rows (the reference writes one table row into all 16 SIMD lanes:
+// components/processor/table.rs:86-100).  Its polynomial has a single non-zero coefficient per 2^log_repeat, and the first
+// log_repeat FFT layers only scale or replicate, so both transforms run on the 2^m distinct values (fft.cu, LINE).
+int32_t sc_interpolate_repeated(sc_ctx* ctx, sc_col* const* cols, uint32_t n, uint32_t log_repeat, const sc_twiddles* tw) {
+  ENTER();
+  if (!tw || (!cols && n)) return fail(SC_EINVAL, "null argument");
+  std::map<uint32_t, std::vector<uint32_t*>> by_log;
+  for (uint32_t i = 0; i < n; i++) {
+    if (!cols[i] || !is_pow2(cols[i]->len)) return fail(SC_EINVAL, "interpolate_repeated: column length must be a power of two");
+    uint32_t lg = ilog2(cols[i]->len);
+    if (lg + log_repeat > tw->root_log + 1 || lg > tw->root_log) return fail(SC_EINVAL, "interpolate_repeated: twiddle tree too small for this domain");
+    by_log[lg].push_back(cols[i]->d);
+  }
+  for (auto& kv : by_log) {
+    void* dp;
+    int32_t r = stage(ctx, kv.second.data(), kv.second.size() * sizeof(void*), &dp);
+    if (r) return r;
+    { ProfScope ps_(ctx, "fft_interpolate"); CKL(launch_interpolate_repeated((uint32_t* const*)dp, (uint32_t)kv.second.size(), kv.first, tw->itw + ((size_t)1 << tw->root_log), ctx->st)); }
+  }
+  return SC_OK;
+}
+
+// coeffs: compact coefficients (sc_interpolate_repeated).  out: new FULL columns of length (len << log_repeat) << log_blowup.
+int32_t sc_evaluate_repeated(sc_ctx* ctx, sc_col* const* coeffs, uint32_t n, uint32_t log_repeat, uint32_t log_blowup, const sc_twiddles* tw, sc_col** out) {
+  ENTER();
+  if (!tw || !out || (!coeffs && n)) return fail(SC_EINVAL, "null argument");
+  if (log_blowup > 1) return fail(SC_EINVAL, "evaluate_repeated: log_blowup > 1 is not supported");
+  if (log_repeat < 2 || log_repeat > 8) return fail(SC_EINVAL, "evaluate_repeated: log_repeat must be in [2, 8]");
+  struct G { std::vector<const uint32_t*> src; std::vector<uint32_t*> tmp, dst; };
+  std::map<uint32_t, G> by_log;
+  for (uint32_t i = 0; i < n; i++) {
+    if (!coeffs[i] || !is_pow2(coeffs[i]->len)) return fail(SC_EINVAL, "evaluate_repeated: column length must be a power of two");
+    uint32_t lg = ilog2(coeffs[i]->len);
+    if (lg + log_blowup + log_repeat > tw->root_log + 1 || lg + log_blowup > tw->root_log) return fail(SC_EINVAL, "evaluate_repeated: twiddle tree too small for this domain");
+  }
+  std::vector<uint32_t*> temps;
+  for (uint32_t i = 0; i < n; i++) {
+    uint32_t lg = ilog2(coeffs[i]->len);
+    int32_t r = new_col(ctx, (coeffs[i]->len << log_repeat) << log_blowup, &out[i]);
+    if (r) return r;
+    uint32_t* t;
+    CK(cudaMallocAsync((void**)&t, (coeffs[i]->len << log_blowup) * 4, ctx->st));
+    temps.push_back(t);
+    G& g = by_log[lg];
+    g.src.push_back(coeffs[i]->d); g.tmp.push_back(t); g.dst.push_back(out[i]->d);
+  }
+  for (auto& kv : by_log) {
+    void *ds, *dt, *dd;
+    size_t nc = kv.second.src.size();
+    int32_t r = stage(ctx, kv.second.src.data(), nc * sizeof(void*), &ds); if (r) return r;
+    r = stage(ctx, kv.second.tmp.data(), nc * sizeof(void*), &dt); if (r) return r;
+    r = stage(ctx, kv.second.dst.data(), nc * sizeof(void*), &dd); if (r) return r;
+    {
+      ProfScope ps_(ctx, "fft_evaluate");
+      CKL(launch_evaluate_repeated((const uint32_t* const*)ds, (uint32_t* const*)dt, (uint32_t)nc, kv.first, kv.first + log_blowup,
+                                   tw->tw + ((size_t)1 << tw->root_log), ctx->st));
+    }
+    { ProfScope ps_(ctx, "broadcast16"); CKL(launch_broadcast_cols((const uint32_t* const*)dt, (uint32_t* const*)dd, (uint32_t)nc, (size_t)1 << (kv.first + log_blowup), log_repeat, ctx->st)); }
+  }
+  for (uint32_t* t : temps) CK(cudaFreeAsync(t, ctx->st));
+  return SC_OK;
+}
+
+static int32_t eval_at_point_impl(sc_ctx* ctx, sc_col* const* polys, const uint32_t* log_repeats, uint32_t n, const uint32_t* points, uint32_t* out);
 int32_t sc_eval_at_point(sc_ctx* ctx, sc_col* const* polys, uint32_t n, const uint32_t* points, uint32_t* out) {
+  return eval_at_point_impl(ctx, polys, nullptr, n, points, out);
+}
+int32_t sc_eval_at_point_repeated(sc_ctx* ctx, sc_col* const* polys, const uint32_t* log_repeats, uint32_t n, const uint32_t* points, uint32_t* out) {
+  if (!log_repeats && n) return fail(SC_EINVAL, "null argument");
+  return eval_at_point_impl(ctx, polys, log_repeats, n, points, out);
+}
+// log_repeats[i] = r > 0: polys[i] holds the compact coefficients of sc_interpolate_repeated, i.e. coefficient j stands at
+// index j << r of the full vector, whose basis monomial is the product of f_k over the set bits k >= r of that index.
+static int32_t eval_at_point_impl(sc_ctx* ctx, sc_col* const* polys, const uint32_t* log_repeats, uint32_t n, const uint32_t* points, uint32_t* out) {
   ENTER();
   if (!n) return SC_OK;
   if (!polys || !points || !out) return fail(SC_EINVAL, "null argument");
@@ -351,14 +434,15 @@ int32_t sc_eval_at_point(sc_ctx* ctx, sc_col* const* polys, uint32_t n, const ui
   for (uint32_t i = 0; i < n; i++) {
     if (!polys[i] || !is_pow2(polys[i]->len)) return fail(SC_EINVAL, "eval_at_point: length must be a power of two");
     uint32_t lg = ilog2(polys[i]->len);
-    if (lg > 28) return fail(SC_EINVAL, "eval_at_point: polynomial too large");
+    const uint32_t rep = log_repeats ? log_repeats[i] : 0;
+    if (lg + rep > 28) return fail(SC_EINVAL, "eval_at_point: polynomial too large");
     const uint32_t* p = points + 8 * i;
     QM31 x = q_make(p[0], p[1], p[2], p[3]), y = q_make(p[4], p[5], p[6], p[7]);
     EvalTaskHost& t = tasks[i];
     t.coeffs = polys[i]->d; t.log = lg; t.first_block = blocks;
     for (int k = 0; k < 28; k++) t.f[k] = q_zero();
-    t.f[0] = y;
-    for (uint32_t k = 1; k < lg; k++) { t.f[k] = x; x = q_sub(q_mulm(q_sqr(x), 2), q_fromm(1)); }
+    if (rep == 0) t.f[0] = y;
+    for (uint32_t k = 1; k < lg + rep; k++) { if (k >= rep) t.f[k - rep] = x; x = q_sub(q_mulm(q_sqr(x), 2), q_fromm(1)); }
     blocks += lg > 13 ? (1u << (lg - 13)) : 1u;  // EV_CHUNK_LOG (ops.cu)
   }
   void* dt;
@@ -378,7 +462,17 @@ int32_t sc_eval_at_point(sc_ctx* ctx, sc_col* const* polys, uint32_t n, const ui
 }
 
 // ------------------------------------------------------------------ Merkle
+static int32_t commit_layer_impl(sc_ctx* ctx, uint32_t log_size, const sc_col* prev, sc_col* const* cols, uint32_t n, uint32_t log_repeat, sc_col** out);
 int32_t sc_merkle_commit_layer(sc_ctx* ctx, uint32_t log_size, const sc_col* prev, sc_col* const* cols, uint32_t n, sc_col** out) {
+  return commit_layer_impl(ctx, log_size, prev, cols, n, 0, out);
+}
+// As sc_merkle_commit_layer when every column (and therefore every child pair) repeats each value 2^log_repeat times:
+// one node per group is hashed and its digest stored 2^log_repeat times.  The caller guarantees the repetition.
+int32_t sc_merkle_commit_layer_repeated(sc_ctx* ctx, uint32_t log_size, const sc_col* prev, sc_col* const* cols, uint32_t n, uint32_t log_repeat, sc_col** out) {
+  if (log_repeat > 8) return fail(SC_EINVAL, "commit_on_layer: log_repeat > 8");
+  return commit_layer_impl(ctx, log_size, prev, cols, n, log_repeat, out);
+}
+static int32_t commit_layer_impl(sc_ctx* ctx, uint32_t log_size, const sc_col* prev, sc_col* const* cols, uint32_t n, uint32_t log_repeat, sc_col** out) {
   ENTER();
   if (!out || (!cols && n) || log_size > 30) return fail(SC_EINVAL, "commit_on_layer: bad argument");
   uint64_t rows = 1ull << log_size;
@@ -392,11 +486,21 @@ int32_t sc_merkle_commit_layer(sc_ctx* ctx, uint32_t log_size, const sc_col* pre
   if (n) { int32_t r = stage(ctx, p.data(), n * sizeof(void*), &dp); if (r) return r; }
   int32_t r = new_col(ctx, rows * 8, out);
   if (r) return r;
-  { ProfScope ps_(ctx, "merkle_commit_layer"); CKL(launch_commit_layer(log_size, prev ? prev->d : nullptr, (const uint32_t* const*)dp, n, (*out)->d, ctx->st)); }
+  { ProfScope ps_(ctx, "merkle_commit_layer"); CKL(launch_commit_layer(log_size, prev ? prev->d : nullptr, (const uint32_t* const*)dp, n, (*out)->d, ctx->st, log_repeat)); }
   return SC_OK;
 }
 
+static int32_t merkle_commit_impl(sc_ctx* ctx, sc_col* const* cols, uint32_t n, uint32_t log_repeat, sc_col** layers_out, uint32_t* max_log_out, uint32_t root_out[8]);
 int32_t sc_merkle_commit(sc_ctx* ctx, sc_col* const* cols, uint32_t n, sc_col** layers_out, uint32_t* max_log_out, uint32_t root_out[8]) {
+  return merkle_commit_impl(ctx, cols, n, 0, layers_out, max_log_out, root_out);
+}
+// Tree over columns that ALL repeat each value 2^log_repeat times: the nodes of the deepest layer then repeat 2^log_repeat
+// times, those of the layer above half as often, and so on; the first log_repeat layers hash one node per group.
+int32_t sc_merkle_commit_repeated(sc_ctx* ctx, sc_col* const* cols, uint32_t n, uint32_t log_repeat, sc_col** layers_out, uint32_t* max_log_out, uint32_t root_out[8]) {
+  if (log_repeat > 8) return fail(SC_EINVAL, "merkle_commit: log_repeat > 8");
+  return merkle_commit_impl(ctx, cols, n, log_repeat, layers_out, max_log_out, root_out);
+}
+static int32_t merkle_commit_impl(sc_ctx* ctx, sc_col* const* cols, uint32_t n, uint32_t log_repeat, sc_col** layers_out, uint32_t* max_log_out, uint32_t root_out[8]) {
   ENTER();
   if (!layers_out || (!cols && n)) return fail(SC_EINVAL, "null argument");
   uint32_t max_log = 0;
@@ -407,7 +511,8 @@ int32_t sc_merkle_commit(sc_ctx* ctx, sc_col* const* cols, uint32_t n, sc_col** 
   for (int lg = (int)max_log; lg >= 0; lg--) {
     std::vector<sc_col*> lc;
     for (uint32_t i = 0; i < n; i++) if (ilog2(cols[i]->len) == (uint32_t)lg) lc.push_back(cols[i]);  // stable
-    int32_t r = sc_merkle_commit_layer(ctx, lg, lg == (int)max_log ? nullptr : layers_out[lg + 1], lc.data(), (uint32_t)lc.size(), &layers_out[lg]);
+    uint32_t depth = max_log - (uint32_t)lg, rep = log_repeat > depth ? log_repeat - depth : 0;
+    int32_t r = commit_layer_impl(ctx, lg, lg == (int)max_log ? nullptr : layers_out[lg + 1], lc.data(), (uint32_t)lc.size(), rep, &layers_out[lg]);
     if (r) return r;
   }
   if (max_log_out) *max_log_out = max_log;

@@ -42,6 +42,11 @@ struct sc_ctx {
   std::vector<ArenaBlock> arena;
   std::mutex arena_mu;
   std::map<uint32_t, sc_twiddles*> tw_cache;  // sc_twiddles_cached
+  // sc_col_from_host_async copies on a second stream so that uploads overlap kernels already queued on `st`; the next
+  // call of any other entry point makes `st` wait for them (join_uploads)
+  cudaStream_t copy_st = nullptr;
+  cudaEvent_t copy_ev = nullptr;
+  bool uploads_pending = false;
 };
 
 // RAII: brackets the kernels launched in a scope with two events when profiling is on.
@@ -73,10 +78,17 @@ static inline int32_t fail(int32_t code, const std::string& m) { g_sc_err = m; r
     if (e_ > 0) { ctx->poisoned = true; return fail(SC_ECUDA, std::string(#expr) + ": " + cudaGetErrorString((cudaError_t)e_)); } \
     if (e_ < 0) return fail(SC_EINVAL, std::string(#expr) + ": invalid argument");                 \
   } while (0)
-#define ENTER()                                                                                    \
+#define ENTER_NOJOIN()                                                                             \
   if (!ctx) return fail(SC_EINVAL, "null context");                                                \
   if (ctx->poisoned) return fail(SC_ECUDA, "context unusable after an earlier CUDA error");        \
   CK(cudaSetDevice(ctx->device))
+#define ENTER()                                                                                    \
+  ENTER_NOJOIN();                                                                                  \
+  if (ctx->uploads_pending) {                                                                      \
+    CK(cudaEventRecord(ctx->copy_ev, ctx->copy_st));                                               \
+    CK(cudaStreamWaitEvent(ctx->st, ctx->copy_ev, 0));                                             \
+    ctx->uploads_pending = false;                                                                  \
+  }
 
 static inline bool is_pow2(uint64_t x) { return x && !(x & (x - 1)); }
 static inline uint32_t ilog2(uint64_t x) { uint32_t l = 0; while ((1ull << l) < x) l++; return l; }

@@ -204,29 +204,32 @@ __device__ __forceinline__ void fft_round(uint32_t* __restrict__ sm, const FftAr
 }
 
 // Runs round I of the pass (ascending bit order); inverse walks I = 0..NR-1, forward NR-1..0.
-template <bool INV, int K, bool LOW, int I>
+template <bool INV, int K, bool LOW, bool LINE, int I>
 __device__ __forceinline__ void run_round(uint32_t* sm, const FftArgs& a, uint32_t T) {
   constexpr int C0 = LOW ? 0 : STRIDED_C;
   constexpr int NB = K - C0;
   constexpr int R = round_size(NB, I);
   constexpr int B = C0 + round_start(NB, I);
   const uint32_t gb = LOW ? (uint32_t)B : a.L0 + (uint32_t)(B - STRIDED_C);
-  fft_round<INV, K, B, R, (LOW && B == 0)>(sm, a, T, gb);
+  fft_round<INV, K, B, R, (LOW && B == 0 && !LINE)>(sm, a, T, gb);
   __syncthreads();
 }
-template <bool INV, int K, bool LOW, int I, int NR>
+template <bool INV, int K, bool LOW, bool LINE, int I, int NR>
 struct Rounds {
   static __device__ __forceinline__ void run(uint32_t* sm, const FftArgs& a, uint32_t T) {
-    run_round<INV, K, LOW, (INV ? I : NR - 1 - I)>(sm, a, T);
-    Rounds<INV, K, LOW, I + 1, NR>::run(sm, a, T);
+    run_round<INV, K, LOW, LINE, (INV ? I : NR - 1 - I)>(sm, a, T);
+    Rounds<INV, K, LOW, LINE, I + 1, NR>::run(sm, a, T);
   }
 };
-template <bool INV, int K, bool LOW, int NR>
-struct Rounds<INV, K, LOW, NR, NR> {
+template <bool INV, int K, bool LOW, bool LINE, int NR>
+struct Rounds<INV, K, LOW, LINE, NR, NR> {
   static __device__ __forceinline__ void run(uint32_t*, const FftArgs&, uint32_t) {}
 };
 
-template <bool INV, int K, bool LOW>
+// LINE: every layer is a line layer (layer l uses the 2^(n-1-l) twiddles at twend - 2^(n-l), l = 0 included).  That is the
+// transform of a column whose evaluations repeat each value 2^r times, restricted to its 2^n distinct values: the first r
+// layers of the circle transform of log n+r only scale (inverse) or replicate (forward), see launch_interpolate_repeated.
+template <bool INV, int K, bool LOW, bool LINE = false>
 __global__ void __launch_bounds__(256) fft_kernel(FftArgs a) {
   extern __shared__ uint32_t sm[];
   constexpr int C = LOW ? K : STRIDED_C;
@@ -248,7 +251,7 @@ __global__ void __launch_bounds__(256) fft_kernel(FftArgs a) {
   }
   __syncthreads();
 
-  Rounds<INV, K, LOW, 0, n_rounds(LOW ? K : K - STRIDED_C)>::run(sm, a, T);
+  Rounds<INV, K, LOW, LINE, 0, n_rounds(LOW ? K : K - STRIDED_C)>::run(sm, a, T);
 
   const uint32_t scale = a.scale;
   for (uint32_t li = threadIdx.x * 4; li < (1u << K); li += blockDim.x * 4) {
@@ -289,18 +292,34 @@ static uint32_t threads_for(uint32_t K) {
   return t;
 }
 
-template <bool INV, int K, bool LOW>
+template <bool INV, int K, bool LOW, bool LINE = false>
 static int launch_one(const FftArgs& a, dim3 grid, cudaStream_t st) {
   size_t smem = ((size_t)(1u << K) + ((1u << K) >> 5) + 4) * 4;
-  fft_kernel<INV, K, LOW><<<grid, threads_for(K), smem, st>>>(a); g_launch_count++;
+  fft_kernel<INV, K, LOW, LINE><<<grid, threads_for(K), smem, st>>>(a); g_launch_count++;
   return (int)cudaGetLastError();
 }
 
 template <bool INV>
 static int run_pass(const PassDesc& d, const uint32_t* const* src, uint32_t* const* dst, uint32_t ncols, uint32_t n,
-                    uint32_t src_log, const uint32_t* twend, uint32_t scale, cudaStream_t st) {
+                    uint32_t src_log, const uint32_t* twend, uint32_t scale, cudaStream_t st, bool line = false) {
   FftArgs a{src, dst, twend, n, src_log, d.L0, scale, 1u};
   dim3 grid(1u << (n - d.K), ncols);
+  if (d.low && line) {
+    switch (d.K) {
+      case 3: return launch_one<INV, 3, true, true>(a, grid, st);
+      case 4: return launch_one<INV, 4, true, true>(a, grid, st);
+      case 5: return launch_one<INV, 5, true, true>(a, grid, st);
+      case 6: return launch_one<INV, 6, true, true>(a, grid, st);
+      case 7: return launch_one<INV, 7, true, true>(a, grid, st);
+      case 8: return launch_one<INV, 8, true, true>(a, grid, st);
+      case 9: return launch_one<INV, 9, true, true>(a, grid, st);
+      case 10: return launch_one<INV, 10, true, true>(a, grid, st);
+      case 11: return launch_one<INV, 11, true, true>(a, grid, st);
+      case 12: return launch_one<INV, 12, true, true>(a, grid, st);
+      case 13: return launch_one<INV, 13, true, true>(a, grid, st);
+    }
+    return -1;
+  }
   if (d.low) {
     switch (d.K) {
       case 3: return launch_one<INV, 3, true>(a, grid, st);
@@ -354,6 +373,69 @@ int launch_evaluate(const uint32_t* const* coeffs, uint32_t* const* out, uint32_
   for (int i = np - 1; i >= 0; i--) {
     bool first = (i == np - 1);
     int e = run_pass<false>(pd[i], first ? coeffs : (const uint32_t* const*)out, out, ncols, n, first ? src_log : 32, tw_end, 1u, st);
+    if (e) return e;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------- lane-repeated columns (line transforms)
+// log size < 3: one thread per column does the few butterflies serially
+template <bool INV>
+__global__ void line_fft_small_kernel(FftArgs a, uint32_t ncols) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncols) return;
+  const uint32_t n = a.n, size = 1u << n;
+  const uint32_t smask = (a.src_log >= 32) ? 0xffffffffu : ((1u << a.src_log) - 1u);
+  uint32_t v[4];
+  for (uint32_t i = 0; i < size; i++) v[i] = a.src[c][i & smask];
+  for (uint32_t ss = 0; ss < n; ss++) {
+    const uint32_t s = INV ? ss : n - 1 - ss;
+    if (!INV && s >= a.src_log) continue;
+    const uint32_t* tw = a.twend - ((size_t)1 << (n - s));
+    for (uint32_t i = 0; i < size; i++) {
+      if ((i >> s) & 1u) continue;
+      if (INV) bfly_inv(v[i], v[i + (1u << s)], tw[i >> (s + 1)], a.one); else bfly_fwd(v[i], v[i + (1u << s)], tw[i >> (s + 1)], a.one);
+    }
+  }
+  for (uint32_t i = 0; i < size; i++) a.dst[c][i] = a.scale != 1u ? m_mul(v[i], a.scale) : v[i];
+}
+
+// In place: the 2^n distinct values of each column -> the non-zero coefficients of the polynomial interpolating the
+// column with every value repeated 2^r times (any r: the r skipped layers contribute the factor 2^r that turns the
+// 1/2^(n+r) normalisation into 1/2^n).  Coefficient i of the result is coefficient i << r of the full vector.
+int launch_interpolate_repeated(uint32_t* const* cols, uint32_t ncols, uint32_t n, const uint32_t* itw_end, cudaStream_t st) {
+  if (ncols == 0 || n == 0) return 0;
+  uint32_t ninv = m_inv(m_pow(2, n));
+  if (n < 3) {
+    FftArgs a{cols, cols, itw_end, n, 32, 0, ninv, 1u};
+    line_fft_small_kernel<true><<<(ncols + 63) / 64, 64, 0, st>>>(a, ncols); g_launch_count++;
+    return (int)cudaGetLastError();
+  }
+  PassDesc pd[8];
+  int np = plan_passes(n, pd);
+  for (int i = 0; i < np; i++) {
+    int e = run_pass<true>(pd[i], cols, cols, ncols, n, 32, itw_end, i == np - 1 ? ninv : 1u, st, true);
+    if (e) return e;
+  }
+  return 0;
+}
+
+// Compact coefficients (log src_log) -> the 2^n distinct evaluations (n = src_log + log_blowup, log_blowup <= 1) of the
+// repeated column on the larger domain; the caller replicates each 2^r times.
+int launch_evaluate_repeated(const uint32_t* const* coeffs, uint32_t* const* out, uint32_t ncols, uint32_t src_log, uint32_t n,
+                             const uint32_t* tw_end, cudaStream_t st) {
+  if (ncols == 0) return 0;
+  if (n - src_log > 1) return -1;
+  if (n < 3) {
+    FftArgs a{coeffs, out, tw_end, n, src_log, 0, 1u, 1u};
+    line_fft_small_kernel<false><<<(ncols + 63) / 64, 64, 0, st>>>(a, ncols); g_launch_count++;
+    return (int)cudaGetLastError();
+  }
+  PassDesc pd[8];
+  int np = plan_passes(n, pd);
+  for (int i = np - 1; i >= 0; i--) {
+    bool first = (i == np - 1);
+    int e = run_pass<false>(pd[i], first ? coeffs : (const uint32_t* const*)out, out, ncols, n, first ? src_log : 32, tw_end, 1u, st, true);
     if (e) return e;
   }
   return 0;

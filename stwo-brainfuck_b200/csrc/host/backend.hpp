@@ -41,6 +41,16 @@ struct Backend {
   virtual void interpolate(const std::vector<Col>& cols) = 0;                                  // in place
   virtual std::vector<Col> evaluate(const std::vector<Col>& coeffs, uint32_t log_blowup) = 0;
   virtual std::vector<QM31> eval_at_point(const std::vector<Col>& polys, const std::vector<QPoint>& pts) = 0;
+  // ---- lane-repeated columns: a stored value stands for 2^rep consecutive rows of the evaluation (rep = LOG_N_LANES for
+  // the main trace, whose table rows are written into all 16 SIMD lanes: components/<name>/table.rs trace_evaluation).
+  // The polynomial of such a column has one non-zero coefficient in 2^rep; `interpolate_repeated` leaves those in the
+  // column (coefficient j = coefficient j << rep of the full vector) and the two evaluators take that compact form.
+  virtual void interpolate_repeated(const std::vector<Col>& cols, uint32_t rep) = 0;                                     // in place
+  virtual std::vector<Col> evaluate_repeated(const std::vector<Col>& coeffs, uint32_t rep, uint32_t log_blowup) = 0;     // full-length evaluations
+  virtual std::vector<QM31> eval_at_point_repeated(const std::vector<Col>& polys, const std::vector<uint32_t>& reps,
+                                                   const std::vector<QPoint>& pts) = 0;
+  // merkle_commit of full-length columns that all repeat each value 2^rep times (the deepest `rep` layers then repeat too)
+  virtual std::vector<Col> merkle_commit_repeated(const std::vector<Col>& cols, uint32_t rep, Hash* root) = 0;
   // MerkleOps: layers[k] = layer of log size k
   // root == nullptr: enqueue only (the caller reads layers[0] later), so the host can overlap other work
   virtual std::vector<Col> merkle_commit(const std::vector<Col>& cols, Hash* root) = 0;

@@ -14,7 +14,8 @@ namespace sbf {
 struct StageTimes { std::vector<std::pair<std::string, double>> ms; };
 
 struct CommitTree {
-  std::vector<Col> polys;      // coefficient columns
+  std::vector<Col> polys;      // coefficient columns (compact when rep > 0: coefficient j stands for j << rep, backend.hpp)
+  uint32_t rep = 0;            // every evaluation column repeats each value 2^rep times
   std::vector<uint32_t> logs;  // log size of each polynomial
   std::vector<Col> evals;      // LDE columns (log + blowup)
   std::vector<Col> layers;     // Merkle layers by log size
@@ -207,7 +208,10 @@ struct ProveResult {
   StageTimes times;
 };
 
-inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code, const std::vector<Registers>& vm_trace,
+// `run_vm` yields the execution trace.  With cfg.overlap_host it is called only after the (program-independent)
+// preprocessed phase has been enqueued, so the VM run as well as the table building hide behind that device work.
+typedef std::function<const std::vector<Registers>&()> TraceSource;
+inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code, const TraceSource& run_vm,
                                    const ProverConfig& cfg, const std::function<void()>& sync = nullptr) {
   ProveResult R;
   BrainfuckProof& proof = R.proof;
@@ -224,8 +228,13 @@ inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code
   Channel ch;
   std::vector<CommitTree> trees;
   auto commit_tree = [&](CommitTree& t) {  // TreeBuilder::commit -> CommitmentTreeProver::new
-    t.evals = B.evaluate(t.polys, cfg.log_blowup);
-    t.layers = B.merkle_commit(t.evals, &t.root);
+    if (t.rep) {
+      t.evals = B.evaluate_repeated(t.polys, t.rep, cfg.log_blowup);
+      t.layers = B.merkle_commit_repeated(t.evals, t.rep, &t.root);
+    } else {
+      t.evals = B.evaluate(t.polys, cfg.log_blowup);
+      t.layers = B.merkle_commit(t.evals, &t.root);
+    }
     ch.mix_root(t.root);
   };
   lap("twiddles");
@@ -239,35 +248,46 @@ inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code
     ~ArenaGuard() { current_arena() = prev; }
   } arena_guard(B.host_arena());
   std::vector<Table> tables;
-  if (!cfg.overlap_host) { tables = build_tables(vm_trace, code); lap("tables(host)"); }
+  std::vector<std::vector<Col>> compact(N_COMPONENTS);
+  // One value per table row crosses to the device.  The copies are queued as soon as the tables exist: the backend runs
+  // them beside the preprocessed phase (CUDA: a copy stream), and `tables` outlives them (they are complete by the first
+  // read-back after this point).
+  auto upload_tables = [&] {
+    for (int c = 0; c < N_COMPONENTS; c++) {
+      proof.log_size[c] = tables[c].log_size;
+      if (tables[c].log_size > cfg.log_max_rows) throw std::runtime_error(std::string("component too large: ") + COMPONENT_NAMES[c]);
+      for (auto& col : tables[c].cols) compact[c].push_back(B.from_host_async(col.data(), col.size()));
+    }
+  };
+  if (!cfg.overlap_host) { tables = build_tables(run_vm(), code); lap("tables(host)"); upload_tables(); }
   {
     CommitTree t;
     for (uint32_t lg = cfg.log_max_rows; lg >= LOG_N_LANES; lg--) { t.polys.push_back(B.gen_is_first(lg)); t.logs.push_back(lg); }
     B.interpolate(t.polys);
     t.evals = B.evaluate(t.polys, cfg.log_blowup);
     t.layers = B.merkle_commit(t.evals, nullptr);
-    if (cfg.overlap_host) { tables = build_tables(vm_trace, code); R.times.ms.push_back({"tables(host)", 0}); lap("tables(host)+preprocessed"); }
+    if (cfg.overlap_host) { tables = build_tables(run_vm(), code); upload_tables(); R.times.ms.push_back({"tables(host)", 0}); lap("tables(host)+preprocessed"); }
     B.read(t.layers[0], 0, 8, t.root.data());
     ch.mix_root(t.root);
     trees.push_back(std::move(t));
   }
   lap("preprocessed");
 
-  // ---- phase 1: main trace (mod.rs:506-583).  Host builds the tables; one value per table row crosses to the device.
-  std::vector<std::vector<Col>> compact(N_COMPONENTS);
+  // ---- phase 1: main trace (mod.rs:506-583)
   {
     CommitTree t;
     for (int c = 0; c < N_COMPONENTS; c++) {
-      proof.log_size[c] = tables[c].log_size;
-      if (tables[c].log_size > cfg.log_max_rows) throw std::runtime_error(std::string("component too large: ") + COMPONENT_NAMES[c]);
-      for (auto& col : tables[c].cols) {
-        Col cc = B.from_host_async(col.data(), col.size());  // `tables` outlives the copies (synchronised by the root read-back)
-        compact[c].push_back(cc);
-        t.polys.push_back(B.broadcast16(cc));
+      for (Col cc : compact[c]) {
+        size_t n = B.len(cc);
+        Col pc = B.alloc(n);
+        B.copy(pc, 0, cc, 0, n);
+        t.polys.push_back(pc);
         t.logs.push_back(tables[c].log_size);
       }
     }
-    B.interpolate(t.polys);
+    // a table row fills all 16 lanes of its column (table.rs trace_evaluation): interpolate / extend / hash the distinct values only
+    t.rep = LOG_N_LANES;
+    B.interpolate_repeated(t.polys, t.rep);
     for (int c = 0; c < N_COMPONENTS; c++) ch.mix_u64(proof.log_size[c]);
     commit_tree(t);
     trees.push_back(std::move(t));
@@ -351,10 +371,11 @@ inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code
   {
     std::vector<Col> polys;
     std::vector<QPoint> pts;
+    std::vector<uint32_t> reps;
     for (size_t t = 0; t < trees.size(); t++)
       for (size_t c = 0; c < trees[t].polys.size(); c++)
-        for (auto& p : mask.points[t][c]) { polys.push_back(trees[t].polys[c]); pts.push_back(p); }
-    std::vector<QM31> vals = B.eval_at_point(polys, pts);
+        for (auto& p : mask.points[t][c]) { polys.push_back(trees[t].polys[c]); pts.push_back(p); reps.push_back(trees[t].rep); }
+    std::vector<QM31> vals = B.eval_at_point_repeated(polys, reps, pts);
     size_t k = 0;
     P.sampled_values.resize(trees.size());
     std::vector<QM31> flat;
@@ -488,6 +509,11 @@ inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code
   for (Col x : layer) B.free_col(x);
   lap("check+free");
   return R;
+}
+
+inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code, const std::vector<Registers>& vm_trace,
+                                   const ProverConfig& cfg, const std::function<void()>& sync = nullptr) {
+  return prove_brainfuck(B, code, TraceSource([&]() -> const std::vector<Registers>& { return vm_trace; }), cfg, sync);
 }
 
 }  // namespace sbf

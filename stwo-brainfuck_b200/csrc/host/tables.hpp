@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <string>
 #include <thread>
+#include <utility>
 #include "air_ids.hpp"
 #include "vm.hpp"
 
@@ -29,10 +30,15 @@ struct ArenaAlloc {
     return static_cast<T*>(::operator new(n * sizeof(T)));
   }
   void deallocate(T* p, size_t) { if (!current_arena()) ::operator delete(p); }
+  // `ColVec(n)` leaves its words uninitialised (every builder writes every row of every column); `ColVec(n, v)` fills
+  template <class U> void construct(U*) noexcept {}
+  template <class U, class A0, class... A> void construct(U* p, A0&& a0, A&&... a) { ::new ((void*)p) U(std::forward<A0>(a0), std::forward<A>(a)...); }
   template <class U> bool operator==(const ArenaAlloc<U>&) const { return true; }
   template <class U> bool operator!=(const ArenaAlloc<U>&) const { return false; }
 };
 typedef std::vector<uint32_t, ArenaAlloc<uint32_t>> ColVec;
+// builder scratch: large heap vectors are mmap'ed and page-faulted afresh on every proof, the arena's pages are not
+template <class T> using Scratch = std::vector<T, ArenaAlloc<T>>;
 typedef std::vector<ColVec> ColVecs;
 
 struct Table {
@@ -40,6 +46,27 @@ struct Table {
   ColVecs cols;  // cols[c][row], rows = 2^(log_size - 4)
   size_t rows() const { return cols.empty() ? 0 : cols[0].size(); }
 };
+
+inline ColVecs make_cols(size_t ncols, size_t rows) {  // uninitialised, no prototype copies
+  ColVecs c;
+  c.reserve(ncols);
+  for (size_t k = 0; k < ncols; k++) c.emplace_back(rows);
+  return c;
+}
+// fn(lo, hi) over [0, n) on `threads` host threads (the caller's included); small ranges stay on the caller
+template <class Fn>
+inline void parallel_ranges(size_t n, unsigned threads, Fn fn) {
+  if (threads <= 1 || n < ((size_t)1 << 14)) { fn((size_t)0, n); return; }
+  std::vector<std::thread> th;
+  size_t per = (n + threads - 1) / threads;
+  for (unsigned t = 1; t < threads; t++) {
+    size_t lo = std::min(n, t * per), hi = std::min(n, lo + per);
+    if (lo < hi) th.emplace_back([=] { fn(lo, hi); });
+  }
+  fn((size_t)0, std::min(n, per));
+  for (auto& x : th) x.join();
+}
+constexpr unsigned TABLE_THREADS = 4;  // extra host threads inside the three big builders
 
 inline size_t next_pow2(size_t n) { size_t p = 1; while (p < n) p <<= 1; return p; }
 inline uint32_t ilog2_exact(size_t n) { uint32_t l = 0; while (((size_t)1 << l) < n) l++; return l; }
@@ -57,8 +84,8 @@ inline Table finish(ColVecs cols) {
 // Stable order of the trace by `key` then clk.  The VM emits rows in clk order, so a counting sort on the key is the
 // reference's `sort_by_key(|x| (x.key, x.clk))`; falls back to std::stable_sort for huge key ranges.
 template <class KeyFn>
-inline std::vector<uint32_t> order_by_key(size_t n, uint32_t max_key, KeyFn key) {
-  std::vector<uint32_t> idx(n);
+inline Scratch<uint32_t> order_by_key(size_t n, uint32_t max_key, KeyFn key) {
+  Scratch<uint32_t> idx(n);
   if (max_key < (1u << 22)) {
     std::vector<uint32_t> cnt((size_t)max_key + 2, 0);
     for (size_t i = 0; i < n; i++) cnt[key(i) + 1]++;
@@ -73,36 +100,53 @@ inline std::vector<uint32_t> order_by_key(size_t n, uint32_t max_key, KeyFn key)
 
 inline Table memory_table(const std::vector<Registers>& regs) {
   if (regs.empty()) throw std::runtime_error("empty trace");
-  for (size_t i = 1; i < regs.size(); i++)
-    if (regs[i].clk <= regs[i - 1].clk) throw std::runtime_error("trace is not in clk order");
+  const size_t m = regs.size();
   uint32_t max_mp = 0;
-  for (auto& r : regs) max_mp = std::max(max_mp, r.mp);
-  std::vector<uint32_t> ord = order_by_key(regs.size(), max_mp, [&](size_t i) { return regs[i].mp; });
-  // rows after gap filling: per mp run, last.clk - first.clk + 1
+  for (size_t i = 0; i < m; i++) {
+    if (i && regs[i].clk <= regs[i - 1].clk) throw std::runtime_error("trace is not in clk order");
+    max_mp = std::max(max_mp, regs[i].mp);
+  }
+  // the (mp, clk)-sorted entries as three dense arrays: the passes below then read memory in order
+  struct S { uint32_t clk, mp, mv; };
+  Scratch<S> e(m);
+  {
+    Scratch<uint32_t> ord = order_by_key(m, max_mp, [&](size_t i) { return regs[i].mp; });
+    parallel_ranges(m, TABLE_THREADS, [&](size_t lo, size_t hi) {
+      for (size_t k = lo; k < hi; k++) { const Registers& r = regs[ord[k]]; e[k] = {r.clk, r.mp, r.mv}; }
+    });
+  }
+  // row offset of every real entry after gap filling (per mp run: last.clk - first.clk + 1 rows)
+  Scratch<size_t> off(m);
   size_t rows = 0;
-  for (size_t k = 0; k < ord.size(); k++) {
-    const Registers& e = regs[ord[k]];
-    if (k && regs[ord[k - 1]].mp == e.mp) rows += e.clk - regs[ord[k - 1]].clk; else rows += 1;
+  for (size_t k = 0; k < m; k++) {
+    if (k && e[k - 1].mp == e[k].mp) rows += e[k].clk - e[k - 1].clk; else rows += 1;
+    off[k] = rows - 1;
   }
   size_t n = next_pow2(rows);
-  ColVecs c(8, ColVec(n));
+  ColVecs c = make_cols(8, n);
   uint32_t *clk = c[0].data(), *mp = c[1].data(), *mv = c[2].data(), *d = c[3].data();
-  size_t w = 0;
-  for (size_t k = 0; k < ord.size(); k++) {
-    const Registers& e = regs[ord[k]];
-    if (k) {
-      const Registers& p = regs[ord[k - 1]];
-      if (p.mp == e.mp)
-        for (uint32_t x = p.clk + 1; x < e.clk; x++) { clk[w] = x; mp[w] = p.mp; mv[w] = p.mv; d[w] = 1; w++; }
+  parallel_ranges(m, TABLE_THREADS, [&](size_t lo, size_t hi) {
+    for (size_t k = lo; k < hi; k++) {
+      size_t w = off[k];
+      if (k && e[k - 1].mp == e[k].mp) {
+        const S& p = e[k - 1];
+        size_t g = w - (e[k].clk - p.clk - 1);
+        for (uint32_t x = p.clk + 1; x < e[k].clk; x++, g++) { clk[g] = x; mp[g] = p.mp; mv[g] = p.mv; d[g] = 1; }
+      }
+      clk[w] = e[k].clk; mp[w] = e[k].mp; mv[w] = e[k].mv; d[w] = 0;
     }
-    clk[w] = e.clk; mp[w] = e.mp; mv[w] = e.mv; d[w] = 0; w++;
-  }
-  uint32_t last_clk = clk[w - 1], last_mp = mp[w - 1], last_mv = mv[w - 1];
-  for (uint32_t i = 1; w < n; i++, w++) { clk[w] = sb::m_add(last_clk, i); mp[w] = last_mp; mv[w] = last_mv; d[w] = 1; }
-  for (int k = 0; k < 4; k++) {  // next_* = the following entry; the last row pairs with one more dummy
-    std::copy(c[k].begin() + 1, c[k].end(), c[4 + k].begin());
-  }
-  c[4][n - 1] = sb::m_add(clk[n - 1], 1); c[5][n - 1] = mp[n - 1]; c[6][n - 1] = mv[n - 1]; c[7][n - 1] = 1;
+  });
+  const uint32_t last_clk = clk[rows - 1], last_mp = mp[rows - 1], last_mv = mv[rows - 1];
+  parallel_ranges(n - rows, TABLE_THREADS, [&](size_t lo, size_t hi) {
+    for (size_t i = lo; i < hi; i++) {
+      size_t w = rows + i;
+      clk[w] = (uint32_t)(((uint64_t)last_clk + i + 1) % P); mp[w] = last_mp; mv[w] = last_mv; d[w] = 1;
+    }
+  });
+  parallel_ranges(n - 1, TABLE_THREADS, [&](size_t lo, size_t hi) {  // next_* = the following entry
+    for (int k = 0; k < 4; k++) std::copy(c[k].begin() + 1 + lo, c[k].begin() + 1 + hi, c[4 + k].begin() + lo);
+  });
+  c[4][n - 1] = sb::m_add(clk[n - 1], 1); c[5][n - 1] = mp[n - 1]; c[6][n - 1] = mv[n - 1]; c[7][n - 1] = 1;  // one more dummy
   return finish(std::move(c));
 }
 
@@ -117,18 +161,22 @@ inline Table instruction_table(const std::vector<Registers>& regs, const std::ve
   auto ip_of = [&](size_t i) { return i < np ? (uint32_t)i : regs[i - np].ip; };
   uint32_t max_ip = 0;
   for (size_t i = 0; i < total; i++) max_ip = std::max(max_ip, ip_of(i));
-  std::vector<uint32_t> ord = order_by_key(total, max_ip, ip_of);
+  Scratch<uint32_t> ord = order_by_key(total, max_ip, ip_of);
   size_t n = next_pow2(total);
-  ColVecs c(8, ColVec(n));
-  for (size_t k = 0; k < total; k++) {
-    size_t i = ord[k];
-    if (i < np) { c[0][k] = (uint32_t)i; c[1][k] = code[i]; c[2][k] = i + 1 == np ? 0 : code[i + 1]; }
-    else { const Registers& r = regs[i - np]; c[0][k] = r.ip; c[1][k] = r.ci; c[2][k] = r.ni; }
-    c[3][k] = 0;
-  }
+  ColVecs c = make_cols(8, n);
+  parallel_ranges(total, TABLE_THREADS, [&](size_t lo, size_t hi) {
+    for (size_t k = lo; k < hi; k++) {
+      size_t i = ord[k];
+      if (i < np) { c[0][k] = (uint32_t)i; c[1][k] = code[i]; c[2][k] = i + 1 == np ? 0 : code[i + 1]; }
+      else { const Registers& r = regs[i - np]; c[0][k] = r.ip; c[1][k] = r.ci; c[2][k] = r.ni; }
+      c[3][k] = 0;
+    }
+  });
   uint32_t last_ip = c[0][total - 1];
   for (size_t k = total; k < n; k++) { c[0][k] = last_ip; c[1][k] = 0; c[2][k] = 0; c[3][k] = 1; }
-  for (int k = 0; k < 4; k++) std::copy(c[k].begin() + 1, c[k].end(), c[4 + k].begin());
+  parallel_ranges(n - 1, TABLE_THREADS, [&](size_t lo, size_t hi) {
+    for (int k = 0; k < 4; k++) std::copy(c[k].begin() + 1 + lo, c[k].begin() + 1 + hi, c[4 + k].begin() + lo);
+  });
   c[4][n - 1] = c[0][n - 1]; c[5][n - 1] = 0; c[6][n - 1] = 0; c[7][n - 1] = 1;
   return finish(std::move(c));
 }
@@ -148,49 +196,53 @@ inline Table program_table(const std::vector<uint32_t>& code) {
 
 // processor/table.rs:117-142 (pair with next + extra dummy), :195-207 (pad with dummy(last.clk+i, last.ip))
 inline Table processor_table(const std::vector<Registers>& regs) {
-  struct E { uint32_t clk, ip, ci, ni, mp, mv, mvi, d; };
-  std::vector<E> t;
-  for (auto& r : regs) t.push_back({r.clk, r.ip, r.ci, r.ni, r.mp, r.mv, r.mvi, 0});
-  if (t.empty()) throw std::runtime_error("empty trace");
-  E last = t.back();
-  size_t pad = next_pow2(t.size()) - t.size();
-  for (uint32_t i = 1; i <= pad; i++) t.push_back({sb::m_add(last.clk, i), last.ip, 0, 0, 0, 0, 0, 1});
-  last = t.back();
-  t.push_back({sb::m_add(last.clk, 1), last.ip, 0, 0, 0, 0, 0, 1});
-  size_t n = t.size() - 1;
-  ColVecs c(9, ColVec(n));
-  for (size_t i = 0; i < n; i++) {
-    c[0][i] = t[i].clk; c[1][i] = t[i].ip; c[2][i] = t[i].ci; c[3][i] = t[i].ni; c[4][i] = t[i].mp;
-    c[5][i] = t[i].mv; c[6][i] = t[i].mvi; c[7][i] = t[i].d; c[8][i] = t[i + 1].clk;
-  }
+  const size_t m = regs.size();
+  if (m == 0) throw std::runtime_error("empty trace");
+  const size_t n = next_pow2(m);
+  const Registers last = regs.back();
+  ColVecs c = make_cols(9, n);
+  // row i < m: the step itself; row i >= m: dummy(last.clk + (i - m + 1), last.ip); next_clk pairs with row i + 1 (or one more dummy)
+  auto clk_of = [&](size_t i) { return i < m ? regs[i].clk : (uint32_t)(((uint64_t)last.clk + (i - m + 1)) % P); };
+  parallel_ranges(n, TABLE_THREADS, [&](size_t lo, size_t hi) {
+    for (size_t i = lo; i < hi; i++) {
+      if (i < m) {
+        const Registers& r = regs[i];
+        c[0][i] = r.clk; c[1][i] = r.ip; c[2][i] = r.ci; c[3][i] = r.ni; c[4][i] = r.mp; c[5][i] = r.mv; c[6][i] = r.mvi; c[7][i] = 0;
+      } else {
+        c[0][i] = clk_of(i); c[1][i] = last.ip; c[2][i] = 0; c[3][i] = 0; c[4][i] = 0; c[5][i] = 0; c[6][i] = 0; c[7][i] = 1;
+      }
+      c[8][i] = clk_of(i + 1);
+    }
+  });
   return finish(std::move(c));
 }
 
 // processor/instructions/table.rs:293-328 and jump/table.rs:264-297: for every step with ci == op the pair (step, next step),
 // padded in ENTRIES with dummy(last_clk + i, last_ip), i from 0, then chunked in twos; an empty table is one dummy row.
 struct PairEntry { uint32_t clk, ip, ci, ni, mp, mv, mvi, d; };
-inline std::vector<PairEntry> pair_entries(const std::vector<Registers>& regs, uint32_t op) {
-  std::vector<PairEntry> t;
-  for (size_t i = 0; i + 1 < regs.size(); i++)
-    if (regs[i].ci == op)
-      for (int k = 0; k < 2; k++) {
-        const Registers& r = regs[i + k];
-        t.push_back({r.clk, r.ip, r.ci, r.ni, r.mp, r.mv, r.mvi, 0});
-      }
-  uint32_t last_clk = t.empty() ? 0 : t.back().clk, last_ip = t.empty() ? 0 : t.back().ip;
-  size_t len = t.size();
-  size_t pad = (len == 0 ? 1 : next_pow2(len)) - len;
-  for (uint32_t i = 0; i < pad; i++) t.push_back({sb::m_add(last_clk, i), last_ip, 0, 0, 0, 0, 0, 1});
-  if (t.size() == 1) t.push_back({sb::m_add(t[0].clk, 1), t[0].ip, 0, 0, 0, 0, 0, 1});
-  return t;
-}
+struct PairRows {
+  const std::vector<Registers>& regs;
+  Scratch<uint32_t> steps;           // i with regs[i].ci == op (and a following step)
+  uint32_t last_clk = 0, last_ip = 0;  // of the last real entry
+  size_t n = 1;                       // table rows
+  PairRows(const std::vector<Registers>& r, uint32_t op) : regs(r) {
+    size_t cnt = 0;
+    for (size_t i = 0; i + 1 < regs.size(); i++) cnt += regs[i].ci == op;
+    steps.reserve(cnt);
+    for (size_t i = 0; i + 1 < regs.size(); i++) if (regs[i].ci == op) steps.push_back((uint32_t)i);
+    if (cnt) { const Registers& l = regs[steps.back() + 1]; last_clk = l.clk; last_ip = l.ip; n = next_pow2(2 * cnt) / 2; }
+  }
+  PairEntry dummy(size_t j) const { return {(uint32_t)(((uint64_t)last_clk + j) % P), last_ip, 0, 0, 0, 0, 0, 1}; }
+  static PairEntry real(const Registers& r) { return {r.clk, r.ip, r.ci, r.ni, r.mp, r.mv, r.mvi, 0}; }
+  PairEntry first(size_t row) const { return row < steps.size() ? real(regs[steps[row]]) : dummy(2 * (row - steps.size())); }
+  PairEntry second(size_t row) const { return row < steps.size() ? real(regs[steps[row] + 1]) : dummy(2 * (row - steps.size()) + 1); }
+};
 // columns: clk ip ci ni mp mv mvi d next_ip next_mp next_mv  (ProcessorInstructionColumn)
 inline Table instruction_op_table(const std::vector<Registers>& regs, uint32_t op) {
-  auto t = pair_entries(regs, op);
-  size_t n = t.size() / 2;
-  ColVecs c(11, ColVec(n));
-  for (size_t i = 0; i < n; i++) {
-    const PairEntry &a = t[2 * i], &b = t[2 * i + 1];
+  PairRows t(regs, op);
+  ColVecs c = make_cols(11, t.n);
+  for (size_t i = 0; i < t.n; i++) {
+    const PairEntry a = t.first(i), b = t.second(i);
     c[0][i] = a.clk; c[1][i] = a.ip; c[2][i] = a.ci; c[3][i] = a.ni; c[4][i] = a.mp; c[5][i] = a.mv; c[6][i] = a.mvi;
     c[7][i] = a.d; c[8][i] = b.ip; c[9][i] = b.mp; c[10][i] = b.mv;
   }
@@ -198,11 +250,10 @@ inline Table instruction_op_table(const std::vector<Registers>& regs, uint32_t o
 }
 // columns: clk ip ci ni mp mv mvi next_clk next_ip next_mp next_mv d is_mv_zero  (JumpColumn)
 inline Table jump_table(const std::vector<Registers>& regs, uint32_t op) {
-  auto t = pair_entries(regs, op);
-  size_t n = t.size() / 2;
-  ColVecs c(13, ColVec(n));
-  for (size_t i = 0; i < n; i++) {
-    const PairEntry &a = t[2 * i], &b = t[2 * i + 1];
+  PairRows t(regs, op);
+  ColVecs c = make_cols(13, t.n);
+  for (size_t i = 0; i < t.n; i++) {
+    const PairEntry a = t.first(i), b = t.second(i);
     c[0][i] = a.clk; c[1][i] = a.ip; c[2][i] = a.ci; c[3][i] = a.ni; c[4][i] = a.mp; c[5][i] = a.mv; c[6][i] = a.mvi;
     c[7][i] = b.clk; c[8][i] = b.ip; c[9][i] = b.mp; c[10][i] = b.mv; c[11][i] = a.d;
     c[12][i] = sb::m_sub(1, sb::m_mul(a.mv, a.mvi));

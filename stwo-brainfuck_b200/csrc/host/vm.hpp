@@ -48,6 +48,7 @@ struct Machine {
 
   void execute() {
     const size_t n = program.size();
+    trace.reserve((size_t)1 << 18);  // growing from empty costs more than the run itself (reallocation + page faults)
     while (r.ip < n) {
       r.ci = program[r.ip];
       r.ni = (r.ip == n - 1) ? 0 : program[r.ip + 1];

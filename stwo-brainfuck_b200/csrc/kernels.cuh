@@ -12,12 +12,15 @@ extern unsigned long long g_launch_count;  // kernels launched by this process (
 // fft.cu
 int launch_twiddle_tree(uint32_t* tw, uint32_t* itw, uint32_t R, cudaStream_t st);
 int launch_interpolate(uint32_t* const* cols, uint32_t ncols, uint32_t n, const uint32_t* itw_end, cudaStream_t st);
+int launch_interpolate_repeated(uint32_t* const* cols, uint32_t ncols, uint32_t n, const uint32_t* itw_end, cudaStream_t st);
+int launch_evaluate_repeated(const uint32_t* const* coeffs, uint32_t* const* out, uint32_t ncols, uint32_t src_log, uint32_t n,
+                             const uint32_t* tw_end, cudaStream_t st);
 int launch_evaluate(const uint32_t* const* coeffs, uint32_t* const* out, uint32_t ncols, uint32_t src_log, uint32_t n,
                     const uint32_t* tw_end, cudaStream_t st);
 
 // merkle.cu
 int launch_commit_layer(uint32_t log_size, const uint32_t* prev, const uint32_t* const* cols, uint32_t ncols,
-                        uint32_t* out, cudaStream_t st);
+                        uint32_t* out, cudaStream_t st, uint32_t rep_log = 0);
 int launch_grind(const uint32_t digest[8], uint32_t pow_bits, unsigned long long* d_result, cudaStream_t st);
 
 // ops.cu
@@ -43,6 +46,8 @@ int launch_eval_at_point_tasks(const void* d_tasks, uint32_t ntasks, uint32_t to
                                QM31* d_out, cudaStream_t st);
 int launch_gather(const uint32_t* const* d_src, uint32_t n, uint32_t words, uint32_t* d_out, cudaStream_t st);
 int launch_broadcast16(const uint32_t* src, uint32_t* dst, size_t src_len, cudaStream_t st);
+// dst[c][i] = src[c][i >> rep_log] for ncols columns of src_len values (device pointer arrays), 2 <= rep_log <= 8
+int launch_broadcast_cols(const uint32_t* const* src, uint32_t* const* dst, uint32_t ncols, size_t src_len, uint32_t rep_log, cudaStream_t st);
 
 // quotients.cu
 struct QuotEntry { uint32_t col; uint32_t c[4]; };

@@ -69,12 +69,15 @@ __device__ __forceinline__ void b2s_compress(uint32_t h[8], const uint32_t m[16]
   h[4] ^= v4 ^ v12; h[5] ^= v5 ^ v13; h[6] ^= v6 ^ v14; h[7] ^= v7 ^ v15;
 }
 
+// rep_log > 0: every column repeats each value 2^rep_log times and so do the children, hence so do the nodes of this layer;
+// a thread hashes the first node of its group and stores the digest 2^rep_log times (rows = number of groups).
 template <bool HAS_PREV>
 __global__ void __launch_bounds__(256) commit_layer_kernel(uint32_t rows, const uint32_t* __restrict__ prev,
                                                            const uint32_t* const* __restrict__ cols, uint32_t ncols,
-                                                           uint32_t* __restrict__ out, uint32_t one) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows) return;
+                                                           uint32_t* __restrict__ out, uint32_t one, uint32_t rep_log) {
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= rows) return;
+  const uint32_t i = g << rep_log;
   uint32_t h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   uint32_t m[16];
   if (HAS_PREV) {
@@ -90,17 +93,18 @@ __global__ void __launch_bounds__(256) commit_layer_kernel(uint32_t rows, const 
     b2s_compress(h, m, one);
   }
   uint4* o = reinterpret_cast<uint4*>(out) + (size_t)i * 2;
-  o[0] = make_uint4(h[0], h[1], h[2], h[3]);
-  o[1] = make_uint4(h[4], h[5], h[6], h[7]);
+  const uint4 lo = make_uint4(h[0], h[1], h[2], h[3]), hi = make_uint4(h[4], h[5], h[6], h[7]);
+  for (uint32_t k = 0; k < (1u << rep_log); k++) { o[2 * k] = lo; o[2 * k + 1] = hi; }
 }
 
 int launch_commit_layer(uint32_t log_size, const uint32_t* prev, const uint32_t* const* cols, uint32_t ncols,
-                        uint32_t* out, cudaStream_t st) {
-  uint32_t rows = 1u << log_size;
+                        uint32_t* out, cudaStream_t st, uint32_t rep_log) {
+  if (rep_log > log_size) rep_log = log_size;
+  uint32_t rows = 1u << (log_size - rep_log);
   uint32_t threads = rows < 256 ? (rows < 32 ? 32 : rows) : 256;
   uint32_t blocks = (rows + threads - 1) / threads;
-  if (prev) commit_layer_kernel<true><<<blocks, threads, 0, st>>>(rows, prev, cols, ncols, out, 1u);
-  else commit_layer_kernel<false><<<blocks, threads, 0, st>>>(rows, prev, cols, ncols, out, 1u);
+  if (prev) commit_layer_kernel<true><<<blocks, threads, 0, st>>>(rows, prev, cols, ncols, out, 1u, rep_log);
+  else commit_layer_kernel<false><<<blocks, threads, 0, st>>>(rows, prev, cols, ncols, out, 1u, rep_log);
   g_launch_count++;
   return (int)cudaGetLastError();
 }

@@ -5,6 +5,7 @@
 // crates/brainfuck_prover/src/brainfuck_air/mod.rs:732 or from interaction_trace_evaluation (e.g.
 // crates/brainfuck_prover/src/components/processor/table.rs:456-533).
 // Every kernel here is HBM-bound: one coalesced read and one coalesced write per element, grid = multiple of 148 SMs.
+#include <algorithm>
 #include "kernels.cuh"
 
 namespace sb {
@@ -435,6 +436,21 @@ __global__ void broadcast16_kernel(const uint32_t* __restrict__ s, uint4* __rest
     uint32_t x = __ldg(s + (i >> 2));
     d[i] = make_uint4(x, x, x, x);
   }
+}
+__global__ void broadcast_cols_kernel(const uint32_t* const* __restrict__ src, uint32_t* const* __restrict__ dst, size_t n, uint32_t sh) {
+  const uint32_t* __restrict__ s = src[blockIdx.y];
+  uint4* __restrict__ d = reinterpret_cast<uint4*>(dst[blockIdx.y]);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (n << sh); i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t x = __ldg(s + (i >> sh));
+    d[i] = make_uint4(x, x, x, x);
+  }
+}
+int launch_broadcast_cols(const uint32_t* const* src, uint32_t* const* dst, uint32_t ncols, size_t src_len, uint32_t rep_log, cudaStream_t st) {
+  if (rep_log < 2 || rep_log > 8) return -1;
+  size_t vecs = src_len << (rep_log - 2);
+  unsigned bx = (unsigned)std::min<size_t>((vecs + 255) / 256, 4096);
+  broadcast_cols_kernel<<<dim3(bx, ncols), 256, 0, st>>>(src, dst, src_len, rep_log - 2); g_launch_count++;
+  return (int)cudaGetLastError();
 }
 int launch_broadcast16(const uint32_t* src, uint32_t* dst, size_t src_len, cudaStream_t st) {
   broadcast16_kernel<<<grid_for(src_len * 4, 256), 256, 0, st>>>(src, reinterpret_cast<uint4*>(dst), src_len); g_launch_count++;
