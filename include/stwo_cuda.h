@@ -143,7 +143,9 @@ int32_t sc_gather(sc_ctx* ctx, sc_col* const* cols, const uint64_t* offsets, uin
  * values.  A column passed here stores the distinct values (or compact coefficients: coefficient j = coefficient j<<r of the
  * full vector).  sc_evaluate_repeated returns ordinary full-length columns, bit-identical to sc_evaluate of the expanded
  * input.  The *_repeated Merkle calls take ordinary full columns and rely on the caller's promise that they repeat. ---- */
-int32_t sc_interpolate_repeated(sc_ctx* ctx, sc_col* const* cols, uint32_t n, uint32_t log_repeat, const sc_twiddles* tw);
+/* out == NULL: in place.  Otherwise the inputs are left untouched and out[i] receives a new column with the coefficients. */
+int32_t sc_interpolate_repeated(sc_ctx* ctx, sc_col* const* cols, uint32_t n, uint32_t log_repeat, const sc_twiddles* tw,
+                                sc_col** out);
 int32_t sc_evaluate_repeated(sc_ctx* ctx, sc_col* const* coeffs, uint32_t n, uint32_t log_repeat, uint32_t log_blowup,
                              const sc_twiddles* tw, sc_col** out);
 int32_t sc_eval_at_point_repeated(sc_ctx* ctx, sc_col* const* polys, const uint32_t* log_repeats, uint32_t n,

@@ -185,19 +185,23 @@ struct OrcBackend : Backend {
     for (size_t i = 0; i < c->n; i++) o->d[i << rep] = c->d[i];
     return o;
   }
-  void interpolate_repeated(const std::vector<Col>& cols, uint32_t rep) override {
+  std::vector<Col> interpolate_repeated(const std::vector<Col>& cols, uint32_t rep) override {
     bool bad = false;
+    std::vector<Col> out(cols.size());
 #pragma omp parallel for schedule(dynamic)
     for (size_t i = 0; i < cols.size(); i++) {
       HCol* full = expand_values(H(cols[i]), rep);
       orc::interpolate(full->d, lg2(full->n), itw);
+      HCol* o = new HCol(H(cols[i])->n);
       for (size_t j = 0; j < full->n; j++) {
-        if ((j & (((size_t)1 << rep) - 1)) == 0) H(cols[i])->d[j >> rep] = full->d[j];
+        if ((j & (((size_t)1 << rep) - 1)) == 0) o->d[j >> rep] = full->d[j];
         else if (full->d[j] != 0) bad = true;
       }
       delete full;
+      out[i] = o;
     }
     if (bad) throw std::runtime_error("oracle: a repeated column has a non-zero coefficient off the 2^rep grid");
+    return out;
   }
   std::vector<Col> evaluate_repeated(const std::vector<Col>& coeffs, uint32_t rep, uint32_t log_blowup) override {
     std::vector<Col> out(coeffs.size());

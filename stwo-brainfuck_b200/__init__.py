@@ -19,7 +19,7 @@ import numpy as np
 
 P = (1 << 31) - 1
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libstwo_cuda.so")
+LIB_PATH = os.environ.get("STWO_CUDA_LIB") or os.path.join(_HERE, "libstwo_cuda.so")  # override: kernel A/B experiments only
 
 _u32p = ctypes.POINTER(ctypes.c_uint32)
 _vp = ctypes.c_void_p
@@ -259,10 +259,13 @@ class CudaBackend:
         return out
 
     # -- lane-repeated columns (include/stwo_cuda.h: every stored value stands for 2^log_repeat consecutive rows)
-    def interpolate_repeated(self, cols: Sequence[Column], log_repeat: int, twiddles: Twiddles) -> None:
-        """In place: the distinct values -> the non-zero coefficients (coefficient j = coefficient j << log_repeat)."""
+    def interpolate_repeated(self, cols: Sequence[Column], log_repeat: int, twiddles: Twiddles, in_place: bool = True):
+        """The distinct values -> the non-zero coefficients (coefficient j = coefficient j << log_repeat); in place, or into
+        new columns (returned) when in_place is False."""
+        out = None if in_place else (_vp * max(1, len(cols)))()
         self._ck(self._lib.sc_interpolate_repeated(self._ctx, self._arr(cols), ctypes.c_uint32(len(cols)), ctypes.c_uint32(log_repeat),
-                                                   twiddles._h))
+                                                   twiddles._h, out))
+        return None if in_place else [Column(self, _vp(out[i])) for i in range(len(cols))]
 
     def evaluate_repeated(self, coeffs: Sequence[Column], log_repeat: int, log_blowup: int, twiddles: Twiddles) -> List[Column]:
         """Compact coefficients -> ordinary full-length evaluations on the (blown-up) domain."""

@@ -54,7 +54,8 @@ int32_t sc_ctx_destroy(sc_ctx* ctx) {
   for (auto& b : ctx->arena) cudaFreeHost(b.p);
   for (auto& kv : ctx->tw_cache) { cudaFree(kv.second->tw); cudaFree(kv.second->itw); delete kv.second; }
   cudaFree(ctx->d_ring);
-  if (ctx->copy_st) { cudaStreamSynchronize(ctx->copy_st); cudaStreamDestroy(ctx->copy_st); cudaEventDestroy(ctx->copy_ev); }
+  if (ctx->copy_st) { cudaStreamSynchronize(ctx->copy_st); cudaStreamDestroy(ctx->copy_st); cudaEventDestroy(ctx->copy_ev); cudaEventDestroy(ctx->slab_ev); }
+  if (ctx->slab) cudaFree(ctx->slab);
   if (ctx->own_stream) cudaStreamDestroy(ctx->st);
   delete ctx;
   return SC_OK;
@@ -129,12 +130,39 @@ int32_t sc_col_from_host_async(sc_ctx* ctx, const uint32_t* host, uint64_t len, 
   if (!ctx->copy_st) {
     CK(cudaStreamCreateWithFlags(&ctx->copy_st, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ctx->copy_ev, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->slab_ev, cudaEventDisableTiming));
   }
-  // allocated and filled on the copy stream: independent of whatever is queued on the compute stream
-  uint32_t* d = nullptr;
-  cudaError_t e = cudaMallocAsync((void**)&d, std::max<uint64_t>(len, 4) * 4, ctx->copy_st);
-  if (e != cudaSuccess) { cudaGetLastError(); return fail(SC_ENOMEM, std::string("cudaMallocAsync: ") + cudaGetErrorString(e)); }
-  *out = new sc_col{d, len};
+  const size_t bytes = ((std::max<uint64_t>(len, 4) * 4) + 255) & ~(size_t)255;
+  if (ctx->slab_live == 0 && ctx->slab_used == 0 && ctx->slab_high > ctx->slab_cap) {
+    // the previous round of uploads did not fit: grow once, while nothing lives in the slab (cudaFree/cudaMalloc synchronise)
+    if (ctx->slab) CK(cudaFree(ctx->slab));
+    ctx->slab = nullptr; ctx->slab_cap = 0;
+    size_t want = ctx->slab_high + (ctx->slab_high >> 2);
+    CK(cudaMalloc((void**)&ctx->slab, want));
+    ctx->slab_cap = want;
+  }
+  ctx->slab_high = std::max(ctx->slab_high, ctx->slab_used + bytes);
+  if (ctx->slab_used + bytes > ctx->slab_cap) {
+    // no room (first proof on this context, or a larger program): ordinary pool column, copied on the compute stream
+    ctx->slab_used += bytes;  // keep counting so that slab_high sees the whole round
+    ctx->slab_live++;
+    int32_t r = new_col(ctx, len, out);
+    if (r) return r;
+    (*out)->slab = true;      // only for the live count; `owned` stays true, so the memory goes back to the pool
+    CK(cudaMemcpyAsync((*out)->d, host, len * 4, cudaMemcpyHostToDevice, ctx->st));
+    return SC_OK;
+  }
+  if (ctx->slab_fence) {  // the slab was rewound: do not overwrite what kernels already queued on `st` may still read
+    CK(cudaEventRecord(ctx->slab_ev, ctx->st));
+    CK(cudaStreamWaitEvent(ctx->copy_st, ctx->slab_ev, 0));
+    ctx->slab_fence = false;
+  }
+  uint32_t* d = reinterpret_cast<uint32_t*>(ctx->slab + ctx->slab_used);
+  ctx->slab_used += bytes;
+  ctx->slab_live++;
+  sc_col* c = new sc_col{d, len};
+  c->owned = false; c->slab = true;
+  *out = c;
   CK(cudaMemcpyAsync(d, host, len * 4, cudaMemcpyHostToDevice, ctx->copy_st));
   ctx->uploads_pending = true;
   return SC_OK;
@@ -195,6 +223,7 @@ int32_t sc_col_free(sc_ctx* ctx, sc_col* col) {
   if (!ctx) return fail(SC_EINVAL, "null context");
   cudaSetDevice(ctx->device);
   if (col->owned) cudaFreeAsync(col->d, ctx->st);
+  if (col->slab && --ctx->slab_live == 0) { ctx->slab_used = 0; ctx->slab_fence = true; }
   delete col;
   return SC_OK;
 }
@@ -248,8 +277,9 @@ int32_t sc_precompute_twiddles(sc_ctx* ctx, uint32_t root_log, sc_twiddles** out
   ENTER();
   if (!out || root_log < 2 || root_log > 29) return fail(SC_EINVAL, "precompute_twiddles: root_log must be in [2,29]");
   sc_twiddles* t = new sc_twiddles{root_log, nullptr, nullptr};
-  CK(cudaMallocAsync((void**)&t->tw, (size_t)4 << root_log, ctx->st));
-  CK(cudaMallocAsync((void**)&t->itw, (size_t)4 << root_log, ctx->st));
+  // 2 x 2^root_log words each: the tree, then the same tree doubled for the FFT butterflies (fft.cu mulred)
+  CK(cudaMallocAsync((void**)&t->tw, (size_t)8 << root_log, ctx->st));
+  CK(cudaMallocAsync((void**)&t->itw, (size_t)8 << root_log, ctx->st));
   { ProfScope ps_(ctx, "twiddles"); CKL(launch_twiddle_tree(t->tw, t->itw, root_log, ctx->st)); }
   *out = t;
   return SC_OK;
@@ -302,7 +332,7 @@ int32_t sc_interpolate(sc_ctx* ctx, sc_col* const* cols, uint32_t n, const sc_tw
     void* dp;
     int32_t r = stage(ctx, kv.second.data(), kv.second.size() * sizeof(void*), &dp);
     if (r) return r;
-    { ProfScope ps_(ctx, "fft_interpolate"); CKL(launch_interpolate((uint32_t* const*)dp, (uint32_t)kv.second.size(), kv.first, tw->itw + ((size_t)1 << tw->root_log), ctx->st)); }
+    { ProfScope ps_(ctx, "fft_interpolate"); CKL(launch_interpolate((uint32_t* const*)dp, (uint32_t)kv.second.size(), kv.first, tw->itw + ((size_t)2 << tw->root_log), ctx->st)); }
   }
   return SC_OK;
 }
@@ -345,7 +375,7 @@ int32_t sc_evaluate(sc_ctx* ctx, sc_col* const* coeffs, uint32_t n, uint32_t log
     r = stage(ctx, kv.second.dst.data(), kv.second.dst.size() * sizeof(void*), &dd);
     if (r) return r;
     { ProfScope ps_(ctx, "fft_evaluate"); CKL(launch_evaluate((const uint32_t* const*)ds, (uint32_t* const*)dd, (uint32_t)kv.second.src.size(), kv.first,
-                        kv.first + log_blowup, tw->tw + ((size_t)1 << tw->root_log), ctx->st)); }
+                        kv.first + log_blowup, tw->tw + ((size_t)2 << tw->root_log), ctx->st)); }
   }
   for (uint32_t* t : temps) CK(cudaFreeAsync(t, ctx->st));
   return SC_OK;
@@ -355,21 +385,27 @@ int32_t sc_evaluate(sc_ctx* ctx, sc_col* const* coeffs, uint32_t n, uint32_t log
 // every value fills 2^log_repeat consecutive rows (the reference writes one table row into all 16 SIMD lanes:
 // components/processor/table.rs:86-100).  Its polynomial has a single non-zero coefficient per 2^log_repeat, and the first
 // log_repeat FFT layers only scale or replicate, so both transforms run on the 2^m distinct values (fft.cu, LINE).
-int32_t sc_interpolate_repeated(sc_ctx* ctx, sc_col* const* cols, uint32_t n, uint32_t log_repeat, const sc_twiddles* tw) {
+int32_t sc_interpolate_repeated(sc_ctx* ctx, sc_col* const* cols, uint32_t n, uint32_t log_repeat, const sc_twiddles* tw, sc_col** out) {
   ENTER();
   if (!tw || (!cols && n)) return fail(SC_EINVAL, "null argument");
-  std::map<uint32_t, std::vector<uint32_t*>> by_log;
+  struct G { std::vector<const uint32_t*> src; std::vector<uint32_t*> dst; };
+  std::map<uint32_t, G> by_log;
   for (uint32_t i = 0; i < n; i++) {
     if (!cols[i] || !is_pow2(cols[i]->len)) return fail(SC_EINVAL, "interpolate_repeated: column length must be a power of two");
     uint32_t lg = ilog2(cols[i]->len);
     if (lg + log_repeat > tw->root_log + 1 || lg > tw->root_log) return fail(SC_EINVAL, "interpolate_repeated: twiddle tree too small for this domain");
-    by_log[lg].push_back(cols[i]->d);
+  }
+  for (uint32_t i = 0; i < n; i++) {
+    uint32_t* dst = cols[i]->d;
+    if (out) { int32_t r = new_col(ctx, cols[i]->len, &out[i]); if (r) return r; dst = out[i]->d; }
+    G& g = by_log[ilog2(cols[i]->len)];
+    g.src.push_back(cols[i]->d); g.dst.push_back(dst);
   }
   for (auto& kv : by_log) {
-    void* dp;
-    int32_t r = stage(ctx, kv.second.data(), kv.second.size() * sizeof(void*), &dp);
-    if (r) return r;
-    { ProfScope ps_(ctx, "fft_interpolate"); CKL(launch_interpolate_repeated((uint32_t* const*)dp, (uint32_t)kv.second.size(), kv.first, tw->itw + ((size_t)1 << tw->root_log), ctx->st)); }
+    void *ds, *dd;
+    int32_t r = stage(ctx, kv.second.src.data(), kv.second.src.size() * sizeof(void*), &ds); if (r) return r;
+    r = stage(ctx, kv.second.dst.data(), kv.second.dst.size() * sizeof(void*), &dd); if (r) return r;
+    { ProfScope ps_(ctx, "fft_interpolate"); CKL(launch_interpolate_repeated((const uint32_t* const*)ds, (uint32_t* const*)dd, (uint32_t)kv.second.src.size(), kv.first, tw->itw + ((size_t)2 << tw->root_log), ctx->st)); }
   }
   return SC_OK;
 }
@@ -407,7 +443,7 @@ int32_t sc_evaluate_repeated(sc_ctx* ctx, sc_col* const* coeffs, uint32_t n, uin
     {
       ProfScope ps_(ctx, "fft_evaluate");
       CKL(launch_evaluate_repeated((const uint32_t* const*)ds, (uint32_t* const*)dt, (uint32_t)nc, kv.first, kv.first + log_blowup,
-                                   tw->tw + ((size_t)1 << tw->root_log), ctx->st));
+                                   tw->tw + ((size_t)2 << tw->root_log), ctx->st));
     }
     { ProfScope ps_(ctx, "broadcast16"); CKL(launch_broadcast_cols((const uint32_t* const*)dt, (uint32_t* const*)dd, (uint32_t)nc, (size_t)1 << (kv.first + log_blowup), log_repeat, ctx->st)); }
   }
@@ -508,12 +544,33 @@ static int32_t merkle_commit_impl(sc_ctx* ctx, sc_col* const* cols, uint32_t n, 
     if (!cols[i] || !is_pow2(cols[i]->len)) return fail(SC_EINVAL, "merkle_commit: column length must be a power of two");
     max_log = std::max(max_log, ilog2(cols[i]->len));
   }
-  for (int lg = (int)max_log; lg >= 0; lg--) {
+  // layers above `top` one launch each; the remaining small ones (no repetition left there) in a single launch
+  int top = (int)std::min<uint32_t>(max_log, MERKLE_TOP_LOG);
+  if (log_repeat && (uint32_t)top + log_repeat > max_log) top = (int)max_log - (int)log_repeat;  // may become < 0: nothing fused
+  for (int lg = (int)max_log; lg > top; lg--) {
     std::vector<sc_col*> lc;
     for (uint32_t i = 0; i < n; i++) if (ilog2(cols[i]->len) == (uint32_t)lg) lc.push_back(cols[i]);  // stable
     uint32_t depth = max_log - (uint32_t)lg, rep = log_repeat > depth ? log_repeat - depth : 0;
     int32_t r = commit_layer_impl(ctx, lg, lg == (int)max_log ? nullptr : layers_out[lg + 1], lc.data(), (uint32_t)lc.size(), rep, &layers_out[lg]);
     if (r) return r;
+  }
+  if (top >= 0) {
+    std::vector<const uint32_t*> cp;
+    uint32_t col_off[MERKLE_TOP_LOG + 2];
+    uint32_t* outp[MERKLE_TOP_LOG + 1];
+    for (int k = 0; k <= top; k++) {
+      int lg = top - k;
+      col_off[k] = (uint32_t)cp.size();
+      for (uint32_t i = 0; i < n; i++) if (ilog2(cols[i]->len) == (uint32_t)lg) cp.push_back(cols[i]->d);  // stable
+      int32_t r = new_col(ctx, 8ull << lg, &layers_out[lg]);
+      if (r) return r;
+      outp[k] = layers_out[lg]->d;
+    }
+    col_off[top + 1] = (uint32_t)cp.size();
+    void* dp = nullptr;
+    if (!cp.empty()) { int32_t r = stage(ctx, cp.data(), cp.size() * sizeof(void*), &dp); if (r) return r; }
+    ProfScope ps_(ctx, "merkle_commit_layer");
+    CKL(launch_commit_top((uint32_t)top, top == (int)max_log ? nullptr : layers_out[top + 1]->d, (const uint32_t* const*)dp, col_off, outp, ctx->st));
   }
   if (max_log_out) *max_log_out = max_log;
   if (root_out) return sc_col_read(ctx, layers_out[0], 0, 8, root_out);

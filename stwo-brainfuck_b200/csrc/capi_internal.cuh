@@ -17,6 +17,7 @@ struct sc_col {
   uint32_t* d;
   uint64_t len;
   bool owned = true;  // false: a view over caller-owned device memory (sc_col_wrap)
+  bool slab = false;  // lives in the context's upload slab (sc_col_from_host_async)
 };
 struct sc_twiddles {
   uint32_t root_log;
@@ -45,8 +46,16 @@ struct sc_ctx {
   // sc_col_from_host_async copies on a second stream so that uploads overlap kernels already queued on `st`; the next
   // call of any other entry point makes `st` wait for them (join_uploads)
   cudaStream_t copy_st = nullptr;
-  cudaEvent_t copy_ev = nullptr;
+  cudaEvent_t copy_ev = nullptr, slab_ev = nullptr;
   bool uploads_pending = false;
+  // Upload targets come from a persistent slab, not from the stream-ordered pool: a pool allocation on the copy stream
+  // either inherits a dependency on the compute stream or maps fresh memory, and both stall the kernels it should overlap.
+  // Bump allocation; the slab rewinds when its last column is freed (the copy stream then waits for the compute stream's
+  // position at that moment before it overwrites anything).
+  uint8_t* slab = nullptr;
+  size_t slab_cap = 0, slab_used = 0, slab_high = 0;
+  int slab_live = 0;
+  bool slab_fence = false;
 };
 
 // RAII: brackets the kernels launched in a scope with two events when profiling is on.

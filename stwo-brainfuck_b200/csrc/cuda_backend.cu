@@ -68,8 +68,11 @@ struct CudaBackendImpl : Backend {
     ck(sc_eval_at_point(ctx, (sc_col* const*)polys.data(), (uint32_t)polys.size(), (const uint32_t*)pts.data(), (uint32_t*)out.data()));
     return out;
   }
-  void interpolate_repeated(const std::vector<Col>& cols, uint32_t rep) override {
-    ck(sc_interpolate_repeated(ctx, (sc_col* const*)cols.data(), (uint32_t)cols.size(), rep, tw));
+  std::vector<Col> interpolate_repeated(const std::vector<Col>& cols, uint32_t rep) override {
+    std::vector<Col> out(cols.size());
+    if (cols.empty()) return out;
+    ck(sc_interpolate_repeated(ctx, (sc_col* const*)cols.data(), (uint32_t)cols.size(), rep, tw, (sc_col**)out.data()));
+    return out;
   }
   std::vector<Col> evaluate_repeated(const std::vector<Col>& coeffs, uint32_t rep, uint32_t log_blowup) override {
     std::vector<Col> out(coeffs.size());

@@ -55,8 +55,12 @@ __global__ void twiddle_tree_kernel(uint32_t* __restrict__ tw, uint32_t* __restr
     uint32_t idx = (1u << (29 - cl)) + (uint32_t)(((uint64_t)i << (31 - cl)) & 0x7fffffffu);
     v = point_at_index(idx & 0x7fffffffu).x;
   }
+  const uint32_t iv = m_inv(v);
   tw[tid] = v;
-  itw[tid] = m_inv(v);
+  itw[tid] = iv;
+  // second half of both buffers: the same tree doubled (2t < 2^32), which is what the butterflies multiply by (mulred)
+  tw[total + tid] = 2u * v;
+  itw[total + tid] = 2u * iv;
 }
 
 int launch_twiddle_tree(uint32_t* tw, uint32_t* itw, uint32_t R, cudaStream_t st) {
@@ -82,27 +86,41 @@ __device__ __forceinline__ uint32_t fadd(uint32_t x, uint32_t y, uint32_t one) {
   asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(one), "r"(y));
   return r;
 }
+// y - x as x*(-1)+y, again on the FMA pipe (mone = 0 - one)
+__device__ __forceinline__ uint32_t fsub(uint32_t y, uint32_t x, uint32_t mone) {
+  uint32_t r;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(mone), "r"(y));
+  return r;
+}
 // canonical reduction of s in [0, 2P): min(s, s-P)
 __device__ __forceinline__ uint32_t cred(uint32_t s, uint32_t one) { return min(s, fadd(s, 0x80000001u, one)); }  // s + (2^32 - P)
-// b*t mod P for b,t in [0,P): IMAD.WIDE, then (prod >> 31) + (prod & P) in [0, 2P)
-__device__ __forceinline__ uint32_t mulred(uint32_t b, uint32_t t, uint32_t one) {
-  uint64_t pr = (uint64_t)b * t;
-  uint32_t lo = (uint32_t)pr, hi = (uint32_t)(pr >> 32);
-  uint32_t s = fadd(__funnelshift_l(lo, hi, 1), lo & P, one);
+// b*t mod P for b in [0,P], t in [0,P) given as t2 = 2t: the 64-bit product 2bt has (bt >> 31) in its high word and
+// (bt & P) << 1 in its low word, so bt = hi + (lo >> 1) (mod P) — one IMAD.WIDE and one IMAD.HI, no shifts or masks.
+__device__ __forceinline__ uint32_t mulred(uint32_t b, uint32_t t2, uint32_t one) {
+  const uint64_t pr = (uint64_t)b * t2;
+  const uint32_t lo = (uint32_t)pr, hi = (uint32_t)(pr >> 32);
+  uint32_t s;
+#ifdef SB_FFT_IMADHI
+  asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(s) : "r"(lo), "r"(one << 31), "r"(hi));   // runtime 2^31: stays an IMAD.HI (FMA pipe)
+#else
+  asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(s) : "r"(lo), "r"(0x80000000u), "r"(hi));  // ptxas turns this into LEA.HI (ALU pipe)
+#endif
   return cred(s, one);
 }
-__device__ __forceinline__ void bfly_fwd(uint32_t& a, uint32_t& b, uint32_t t, uint32_t one) {
-  uint32_t m = mulred(b, t, one);
+__device__ __forceinline__ void bfly_fwd(uint32_t& a, uint32_t& b, uint32_t t2, uint32_t one) {
+  const uint32_t mone = 0u - one;
+  uint32_t m = mulred(b, t2, one);
   uint32_t a0 = a;
   a = cred(fadd(a0, m, one), one);
-  uint32_t d = a0 - m;                                  // wraps when a0 < m
+  uint32_t d = fsub(a0, m, mone);                       // wraps when a0 < m
   b = min(d, fadd(d, P, one));
 }
-__device__ __forceinline__ void bfly_inv(uint32_t& a, uint32_t& b, uint32_t t, uint32_t one) {
+__device__ __forceinline__ void bfly_inv(uint32_t& a, uint32_t& b, uint32_t t2, uint32_t one) {
+  const uint32_t mone = 0u - one;
   uint32_t a0 = a;
   a = cred(fadd(a0, b, one), one);
-  uint32_t d = a0 - b;
-  b = mulred(min(d, fadd(d, P, one)), t, one);
+  uint32_t d = fsub(a0, b, mone);
+  b = mulred(min(d, fadd(d, P, one)), t2, one);
 }
 
 // ---------------------------------------------------------------- compile-time round partition
@@ -119,7 +137,7 @@ constexpr int STRIDED_C = 4;  // contiguous words per row of a strided tile
 struct FftArgs {
   const uint32_t* const* src;
   uint32_t* const* dst;
-  const uint32_t* twend;  // one past the end of the (i)twiddle buffer
+  const uint32_t* twend;  // one past the end of the DOUBLED (i)twiddle tree (second half of the buffer)
   uint32_t n;             // transform log size
   uint32_t src_log;       // loads read index & (2^src_log - 1); forward layers >= src_log are copies (zero-padded coeffs)
   uint32_t L0;            // strided pass: global bit of local bit STRIDED_C
@@ -169,7 +187,7 @@ __device__ __forceinline__ void fft_round(uint32_t* __restrict__ sm, const FftAr
         for (int j = 0; j < M / 2; j++) {
           uint32_t x = w1[2 * (j >> 2)], y = w1[2 * (j >> 2) + 1];
           uint32_t t = ((j & 3) < 2) ? y : x;
-          tw[j] = ((j & 3) == 1 || (j & 3) == 2) ? (P - t) : t;
+          tw[j] = ((j & 3) == 1 || (j & 3) == 2) ? (2u * P - t) : t;   // doubled twiddles: -t is 2P - 2t
         }
       } else if (CIRCLE && s == 1) {
 #pragma unroll
@@ -400,21 +418,22 @@ __global__ void line_fft_small_kernel(FftArgs a, uint32_t ncols) {
   for (uint32_t i = 0; i < size; i++) a.dst[c][i] = a.scale != 1u ? m_mul(v[i], a.scale) : v[i];
 }
 
-// In place: the 2^n distinct values of each column -> the non-zero coefficients of the polynomial interpolating the
+// src -> cols (may be the same arrays): the 2^n distinct values of each column -> the non-zero coefficients of the polynomial interpolating the
 // column with every value repeated 2^r times (any r: the r skipped layers contribute the factor 2^r that turns the
 // 1/2^(n+r) normalisation into 1/2^n).  Coefficient i of the result is coefficient i << r of the full vector.
-int launch_interpolate_repeated(uint32_t* const* cols, uint32_t ncols, uint32_t n, const uint32_t* itw_end, cudaStream_t st) {
-  if (ncols == 0 || n == 0) return 0;
+int launch_interpolate_repeated(const uint32_t* const* src, uint32_t* const* cols, uint32_t ncols, uint32_t n, const uint32_t* itw_end,
+                                cudaStream_t st) {
+  if (ncols == 0) return 0;
   uint32_t ninv = m_inv(m_pow(2, n));
   if (n < 3) {
-    FftArgs a{cols, cols, itw_end, n, 32, 0, ninv, 1u};
+    FftArgs a{src, cols, itw_end, n, 32, 0, ninv, 1u};
     line_fft_small_kernel<true><<<(ncols + 63) / 64, 64, 0, st>>>(a, ncols); g_launch_count++;
     return (int)cudaGetLastError();
   }
   PassDesc pd[8];
   int np = plan_passes(n, pd);
   for (int i = 0; i < np; i++) {
-    int e = run_pass<true>(pd[i], cols, cols, ncols, n, 32, itw_end, i == np - 1 ? ninv : 1u, st, true);
+    int e = run_pass<true>(pd[i], i == 0 ? src : (const uint32_t* const*)cols, cols, ncols, n, 32, itw_end, i == np - 1 ? ninv : 1u, st, true);
     if (e) return e;
   }
   return 0;

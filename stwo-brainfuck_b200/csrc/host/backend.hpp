@@ -45,7 +45,7 @@ struct Backend {
   // the main trace, whose table rows are written into all 16 SIMD lanes: components/<name>/table.rs trace_evaluation).
   // The polynomial of such a column has one non-zero coefficient in 2^rep; `interpolate_repeated` leaves those in the
   // column (coefficient j = coefficient j << rep of the full vector) and the two evaluators take that compact form.
-  virtual void interpolate_repeated(const std::vector<Col>& cols, uint32_t rep) = 0;                                     // in place
+  virtual std::vector<Col> interpolate_repeated(const std::vector<Col>& values, uint32_t rep) = 0;                       // new columns; inputs kept
   virtual std::vector<Col> evaluate_repeated(const std::vector<Col>& coeffs, uint32_t rep, uint32_t log_blowup) = 0;     // full-length evaluations
   virtual std::vector<QM31> eval_at_point_repeated(const std::vector<Col>& polys, const std::vector<uint32_t>& reps,
                                                    const std::vector<QPoint>& pts) = 0;

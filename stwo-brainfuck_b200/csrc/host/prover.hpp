@@ -259,14 +259,16 @@ inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code
       for (auto& col : tables[c].cols) compact[c].push_back(B.from_host_async(col.data(), col.size()));
     }
   };
-  if (!cfg.overlap_host) { tables = build_tables(run_vm(), code); lap("tables(host)"); upload_tables(); }
+  if (!cfg.overlap_host) { tables = build_tables(run_vm(), code); lap("tables(host)"); }
   {
     CommitTree t;
     for (uint32_t lg = cfg.log_max_rows; lg >= LOG_N_LANES; lg--) { t.polys.push_back(B.gen_is_first(lg)); t.logs.push_back(lg); }
     B.interpolate(t.polys);
     t.evals = B.evaluate(t.polys, cfg.log_blowup);
     t.layers = B.merkle_commit(t.evals, nullptr);
-    if (cfg.overlap_host) { tables = build_tables(run_vm(), code); upload_tables(); R.times.ms.push_back({"tables(host)", 0}); lap("tables(host)+preprocessed"); }
+    if (cfg.overlap_host) tables = build_tables(run_vm(), code);
+    upload_tables();  // queued behind nothing: the copies run while the device is still busy with the phase above
+    if (cfg.overlap_host) { R.times.ms.push_back({"tables(host)", 0}); lap("tables(host)+preprocessed"); }
     B.read(t.layers[0], 0, 8, t.root.data());
     ch.mix_root(t.root);
     trees.push_back(std::move(t));
@@ -276,18 +278,12 @@ inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code
   // ---- phase 1: main trace (mod.rs:506-583)
   {
     CommitTree t;
-    for (int c = 0; c < N_COMPONENTS; c++) {
-      for (Col cc : compact[c]) {
-        size_t n = B.len(cc);
-        Col pc = B.alloc(n);
-        B.copy(pc, 0, cc, 0, n);
-        t.polys.push_back(pc);
-        t.logs.push_back(tables[c].log_size);
-      }
-    }
+    std::vector<Col> values;
+    for (int c = 0; c < N_COMPONENTS; c++)
+      for (Col cc : compact[c]) { values.push_back(cc); t.logs.push_back(tables[c].log_size); }
     // a table row fills all 16 lanes of its column (table.rs trace_evaluation): interpolate / extend / hash the distinct values only
     t.rep = LOG_N_LANES;
-    B.interpolate_repeated(t.polys, t.rep);
+    t.polys = B.interpolate_repeated(values, t.rep);   // the values themselves are kept for the LogUp generation below
     for (int c = 0; c < N_COMPONENTS; c++) ch.mix_u64(proof.log_size[c]);
     commit_tree(t);
     trees.push_back(std::move(t));

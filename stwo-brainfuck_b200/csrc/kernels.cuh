@@ -12,13 +12,17 @@ extern unsigned long long g_launch_count;  // kernels launched by this process (
 // fft.cu
 int launch_twiddle_tree(uint32_t* tw, uint32_t* itw, uint32_t R, cudaStream_t st);
 int launch_interpolate(uint32_t* const* cols, uint32_t ncols, uint32_t n, const uint32_t* itw_end, cudaStream_t st);
-int launch_interpolate_repeated(uint32_t* const* cols, uint32_t ncols, uint32_t n, const uint32_t* itw_end, cudaStream_t st);
+int launch_interpolate_repeated(const uint32_t* const* src, uint32_t* const* cols, uint32_t ncols, uint32_t n, const uint32_t* itw_end,
+                                cudaStream_t st);
 int launch_evaluate_repeated(const uint32_t* const* coeffs, uint32_t* const* out, uint32_t ncols, uint32_t src_log, uint32_t n,
                              const uint32_t* tw_end, cudaStream_t st);
 int launch_evaluate(const uint32_t* const* coeffs, uint32_t* const* out, uint32_t ncols, uint32_t src_log, uint32_t n,
                     const uint32_t* tw_end, cudaStream_t st);
 
 // merkle.cu
+constexpr uint32_t MERKLE_TOP_LOG = 9;  // layers of <= 2^9 nodes are hashed by one CTA in a single launch (merkle.cu)
+int launch_commit_top(uint32_t top_log, const uint32_t* prev, const uint32_t* const* cols, const uint32_t* col_off,
+                      uint32_t* const* out, cudaStream_t st);
 int launch_commit_layer(uint32_t log_size, const uint32_t* prev, const uint32_t* const* cols, uint32_t ncols,
                         uint32_t* out, cudaStream_t st, uint32_t rep_log = 0);
 int launch_grind(const uint32_t digest[8], uint32_t pow_bits, unsigned long long* d_result, cudaStream_t st);

@@ -109,6 +109,61 @@ int launch_commit_layer(uint32_t log_size, const uint32_t* prev, const uint32_t*
   return (int)cudaGetLastError();
 }
 
+// The top of a tree in one launch.  Layers of <= 2^TOP_LOG nodes take 2-3 us each and as long again to launch; a tree has
+// TOP_LOG + 1 of them and a proof about thirty trees (four commitments + one per FRI layer).  One CTA walks the layers
+// from `top_log` down to the root, a thread per node, __syncthreads between layers (the children were written by this CTA,
+// so they are re-read with ordinary loads, not through the read-only path).
+struct TopArgs {
+  const uint32_t* prev;            // layer top_log + 1 (NULL when top_log is the deepest layer)
+  const uint32_t* const* cols;     // column pointers of layers top_log, top_log-1, ..., 0, concatenated
+  uint32_t col_off[MERKLE_TOP_LOG + 2];  // cols of layer top_log - k are cols[col_off[k] .. col_off[k+1])
+  uint32_t* out[MERKLE_TOP_LOG + 1];     // out[k] = layer top_log - k
+  uint32_t top_log;
+  uint32_t one;
+};
+__global__ void __launch_bounds__(1 << MERKLE_TOP_LOG) commit_top_kernel(TopArgs a) {
+  const uint32_t i = threadIdx.x;
+  const uint32_t* prev = a.prev;
+  for (uint32_t k = 0; k <= a.top_log; k++) {
+    const uint32_t lg = a.top_log - k;
+    if (i < (1u << lg)) {
+      uint32_t h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      uint32_t m[16];
+      if (prev) {
+        const uint4* pc = reinterpret_cast<const uint4*>(prev) + (size_t)i * 4;
+        uint4 x = pc[0], y = pc[1], z = pc[2], w = pc[3];
+        m[0] = x.x; m[1] = x.y; m[2] = x.z; m[3] = x.w; m[4] = y.x; m[5] = y.y; m[6] = y.z; m[7] = y.w;
+        m[8] = z.x; m[9] = z.y; m[10] = z.z; m[11] = z.w; m[12] = w.x; m[13] = w.y; m[14] = w.z; m[15] = w.w;
+        b2s_compress(h, m, a.one);
+      }
+      const uint32_t c_lo = a.col_off[k], c_hi = a.col_off[k + 1];
+      for (uint32_t c0 = c_lo; c0 < c_hi; c0 += 16) {
+#pragma unroll
+        for (uint32_t j = 0; j < 16; j++) m[j] = (c0 + j < c_hi) ? __ldg(a.cols[c0 + j] + i) : 0u;
+        b2s_compress(h, m, a.one);
+      }
+      uint4* o = reinterpret_cast<uint4*>(a.out[k]) + (size_t)i * 2;
+      o[0] = make_uint4(h[0], h[1], h[2], h[3]);
+      o[1] = make_uint4(h[4], h[5], h[6], h[7]);
+    }
+    __syncthreads();
+    prev = a.out[k];
+  }
+}
+// cols: device array of the column pointers (layer top_log first); col_off / out as in TopArgs (host arrays).
+int launch_commit_top(uint32_t top_log, const uint32_t* prev, const uint32_t* const* cols, const uint32_t* col_off,
+                      uint32_t* const* out, cudaStream_t st) {
+  if (top_log > MERKLE_TOP_LOG) return -1;
+  TopArgs a;
+  a.prev = prev; a.cols = cols; a.top_log = top_log; a.one = 1u;
+  for (uint32_t k = 0; k <= top_log + 1; k++) a.col_off[k] = col_off[k];
+  for (uint32_t k = 0; k <= top_log; k++) a.out[k] = out[k];
+  uint32_t threads = 1u << top_log;
+  if (threads < 32) threads = 32;
+  commit_top_kernel<<<1, threads, 0, st>>>(a); g_launch_count++;
+  return (int)cudaGetLastError();
+}
+
 // ---------------------------------------------------------------- grind
 // Smallest nonce with trailing_zeros(F(digest, [nonce_lo, nonce_hi, 0...])) >= pow_bits (first 128 bits, LE).
 __global__ void grind_kernel(uint32_t d0, uint32_t d1, uint32_t d2, uint32_t d3, uint32_t d4, uint32_t d5, uint32_t d6,

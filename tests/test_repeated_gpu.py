@@ -22,8 +22,13 @@ def rnd(seed, n):
 @pytest.mark.parametrize("m", [0, 1, 2, 3, 4, 7, 10, 13, 14, 16])
 def test_interpolate_and_evaluate_repeated(be, orc, tw, m):
     vals = [rnd(31 * m + k, 1 << m) for k in range(3)]
-    cols = [be.column(v) for v in vals]
-    be.interpolate_repeated(cols, REP, tw)
+    src = [be.column(v) for v in vals]
+    cols = be.interpolate_repeated(src, REP, tw, in_place=False)
+    for c, v in zip(src, vals):
+        assert (c.to_cpu() == v).all(), "out-of-place interpolate must leave its input alone"
+    be.interpolate_repeated(src, REP, tw)
+    for c, d in zip(src, cols):
+        assert (c.to_cpu() == d.to_cpu()).all(), "in-place and out-of-place interpolate agree"
     full = [orc.interpolate(np.repeat(v, 1 << REP), ROOT_LOG) for v in vals]
     for c, f in zip(cols, full):
         assert not f.reshape(-1, 1 << REP)[:, 1:].any(), "oracle: coefficients off the 16-grid must vanish"
