@@ -152,8 +152,7 @@ int32_t sc_col_from_host_async(sc_ctx* ctx, const uint32_t* host, uint64_t len, 
     CK(cudaMemcpyAsync((*out)->d, host, len * 4, cudaMemcpyHostToDevice, ctx->st));
     return SC_OK;
   }
-  if (ctx->slab_fence) {  // the slab was rewound: do not overwrite what kernels already queued on `st` may still read
-    CK(cudaEventRecord(ctx->slab_ev, ctx->st));
+  if (ctx->slab_fence) {  // the slab was rewound: wait for the compute stream's position at that moment (sc_col_free)
     CK(cudaStreamWaitEvent(ctx->copy_st, ctx->slab_ev, 0));
     ctx->slab_fence = false;
   }
@@ -163,7 +162,12 @@ int32_t sc_col_from_host_async(sc_ctx* ctx, const uint32_t* host, uint64_t len, 
   sc_col* c = new sc_col{d, len};
   c->owned = false; c->slab = true;
   *out = c;
-  CK(cudaMemcpyAsync(d, host, len * 4, cudaMemcpyHostToDevice, ctx->copy_st));
+  // In pieces: the small host->device copies of the compute stream (pointer tables, stage()) share the one H2D copy
+  // engine with these uploads and would otherwise sit behind a whole 16 MB column, idling the kernels that wait for them.
+  const size_t piece = (size_t)512 << 10;
+  for (size_t off = 0; off < len * 4; off += piece)
+    CK(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(d) + off, reinterpret_cast<const uint8_t*>(host) + off, std::min(piece, (size_t)(len * 4 - off)),
+                       cudaMemcpyHostToDevice, ctx->copy_st));
   ctx->uploads_pending = true;
   return SC_OK;
 }
@@ -223,7 +227,11 @@ int32_t sc_col_free(sc_ctx* ctx, sc_col* col) {
   if (!ctx) return fail(SC_EINVAL, "null context");
   cudaSetDevice(ctx->device);
   if (col->owned) cudaFreeAsync(col->d, ctx->st);
-  if (col->slab && --ctx->slab_live == 0) { ctx->slab_used = 0; ctx->slab_fence = true; }
+  if (col->slab && --ctx->slab_live == 0) {
+    // rewind; whatever is queued on `st` up to here may still read the slab, later uploads must not overtake it
+    ctx->slab_used = 0;
+    if (ctx->slab_ev) { cudaEventRecord(ctx->slab_ev, ctx->st); ctx->slab_fence = true; }
+  }
   delete col;
   return SC_OK;
 }
@@ -623,6 +631,7 @@ int32_t sc_accumulate_quotients_range(sc_ctx* ctx, uint32_t log, uint64_t row_of
     QM31 sx = q_make(q[0], q[1], q[2], q[3]), sy = q_make(q[4], q[5], q[6], q[7]);
     QuotBatch& B = qb[b];
     B.prx = sx.a; B.pix = sx.b; B.pry = sy.a; B.piy = sy.b;
+    B.c0 = c_sub(c_mul(B.prx, B.piy), c_mul(B.pry, B.pix));
     B.suma = q_zero(); B.sumb = q_zero(); B.first = (uint32_t)qe.size(); B.count = batch_sizes[b];
     QM31 al = q_fromm(1);
     QM31 c = q_sub(q_conj(sy), sy);
@@ -650,7 +659,11 @@ int32_t sc_accumulate_quotients_range(sc_ctx* ctx, uint32_t log, uint64_t row_of
   if (n) { r = stage(ctx, p.data(), n * sizeof(void*), &dp); if (r) return r; }
   r = stage(ctx, qb.data(), qb.size() * sizeof(QuotBatch), &db); if (r) return r;
   if (!qe.empty()) { r = stage(ctx, qe.data(), qe.size() * sizeof(QuotEntry), &de); if (r) return r; }
-  { ProfScope ps_(ctx, "accumulate_quotients"); CKL(launch_accumulate_quotients(log, row_off, n_rows, (const uint32_t* const*)dp, (const QuotBatch*)db, nb, (const QuotEntry*)de, d, ctx->st)); }
+  uint32_t* scratch = nullptr;
+  size_t sw = quotients_scratch_words(log, row_off, n_rows);
+  if (sw) CK(cudaMallocAsync((void**)&scratch, sw * 4, ctx->st));
+  { ProfScope ps_(ctx, "accumulate_quotients"); CKL(launch_accumulate_quotients(log, row_off, n_rows, (const uint32_t* const*)dp, (const QuotBatch*)db, nb, (const QuotEntry*)de, d, ctx->st, scratch)); }
+  if (scratch) CK(cudaFreeAsync(scratch, ctx->st));
   return SC_OK;
 }
 int32_t sc_accumulate_quotients(sc_ctx* ctx, uint32_t log, sc_col* const* cols, uint32_t n, const uint32_t random_coeff[4],
@@ -711,9 +724,15 @@ int32_t sc_prefix_sum_bitrev(sc_ctx* ctx, sc_col* col) {
   if (!col || !is_pow2(col->len) || col->len < 2) return fail(SC_EINVAL, "prefix_sum: length must be a power of two >= 2");
   uint32_t lg = ilog2(col->len);
   uint32_t* scratch;
-  size_t words = prefix_scratch_words(col->len);
-  CK(cudaMallocAsync((void**)&scratch, words * 4, ctx->st));
-  { ProfScope ps_(ctx, "prefix_sum"); CKL(launch_prefix_sum_bitrev(col->d, lg, scratch, ctx->st)); }
+  if (lg >= 12) {
+    CK(cudaMallocAsync((void**)&scratch, prefix_sum_tiled_words(lg) * 4, ctx->st));
+    uint32_t* v1[1] = {col->d};
+    { ProfScope ps_(ctx, "prefix_sum"); CKL(launch_prefix_sum_bitrev_tiled(v1, 1, lg, scratch, ctx->st)); }
+  } else {
+    size_t words = prefix_scratch_words(col->len);
+    CK(cudaMallocAsync((void**)&scratch, words * 4, ctx->st));
+    { ProfScope ps_(ctx, "prefix_sum"); CKL(launch_prefix_sum_bitrev(col->d, lg, scratch, ctx->st)); }
+  }
   CK(cudaFreeAsync(scratch, ctx->st));
   return SC_OK;
 }
@@ -764,10 +783,15 @@ int32_t sc_logup_generate(sc_ctx* ctx, int32_t component, sc_col* const* main_co
   // LogupTraceGenerator::finalize_last: prefix-sum the last column's coordinates in coset order; claimed_sum = col.at(1)
   {
     uint32_t* scratch;
-    size_t words = prefix_scratch_words(len);
-    CK(cudaMallocAsync((void**)&scratch, 4 * words * 4, ctx->st));
     uint32_t* v4[4] = {op[nout - 4], op[nout - 3], op[nout - 2], op[nout - 1]};
-    { ProfScope ps_(ctx, "prefix_sum"); CKL(launch_prefix_sum_bitrev4(v4, p.log_size, scratch, words, ctx->st)); }
+    if (p.log_size >= 12) {
+      CK(cudaMallocAsync((void**)&scratch, 4 * prefix_sum_tiled_words(p.log_size) * 4, ctx->st));
+      { ProfScope ps_(ctx, "prefix_sum"); CKL(launch_prefix_sum_bitrev_tiled(v4, 4, p.log_size, scratch, ctx->st)); }
+    } else {
+      size_t words = prefix_scratch_words(len);
+      CK(cudaMallocAsync((void**)&scratch, 4 * words * 4, ctx->st));
+      { ProfScope ps_(ctx, "prefix_sum"); CKL(launch_prefix_sum_bitrev4(v4, p.log_size, scratch, words, ctx->st)); }
+    }
     CK(cudaFreeAsync(scratch, ctx->st));
   }
   // claimed_sum == NULL: the caller reads element 1 of the last four columns itself (e.g. one sc_gather for all components)

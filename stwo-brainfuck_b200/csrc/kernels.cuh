@@ -39,6 +39,8 @@ int launch_accumulate(uint32_t* const dst[4], const uint32_t* const src[4], size
 int launch_fill(uint32_t* v, size_t n, uint32_t value, cudaStream_t st);
 int launch_gen_is_first(uint32_t* v, uint32_t log, cudaStream_t st);
 int launch_prefix_sum_bitrev(uint32_t* v, uint32_t log, uint32_t* scratch, cudaStream_t st);
+size_t prefix_sum_tiled_words(uint32_t log);
+int launch_prefix_sum_bitrev_tiled(uint32_t* const* v, uint32_t ncols, uint32_t log, uint32_t* scratch, cudaStream_t st);
 int launch_prefix_sum_bitrev4(uint32_t* const v[4], uint32_t log, uint32_t* scratch, size_t words, cudaStream_t st);
 struct EvalTaskHost {  // mirrors ops.cu EvalTask
   const uint32_t* coeffs;
@@ -55,9 +57,10 @@ int launch_broadcast_cols(const uint32_t* const* src, uint32_t* const* dst, uint
 
 // quotients.cu
 struct QuotEntry { uint32_t col; uint32_t c[4]; };
-struct QuotBatch { CM31 prx, pry, pix, piy; QM31 suma, sumb, coeff; uint32_t first, count; };
+struct QuotBatch { CM31 prx, pry, pix, piy, c0; QM31 suma, sumb, coeff; uint32_t first, count; };  // c0 = prx*piy - pry*pix
 int launch_accumulate_quotients(uint32_t log, uint64_t row_off, uint64_t nrows, const uint32_t* const* d_cols,
                                 const QuotBatch* d_batches, uint32_t nb, const QuotEntry* d_entries, uint32_t* const out[4],
-                                cudaStream_t st);
+                                cudaStream_t st, uint32_t* d_scratch = nullptr);
+size_t quotients_scratch_words(uint32_t log, uint64_t row_off, uint64_t nrows);
 
 }  // namespace sb

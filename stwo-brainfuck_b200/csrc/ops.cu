@@ -309,6 +309,142 @@ int launch_prefix_sum_bitrev4(uint32_t* const v[4], uint32_t log, uint32_t* scra
   return (int)cudaGetLastError();
 }
 
+// ---- tiled variant (log >= 12): every global access is a full 256-byte run.
+// Coset position i = 2m is stored at 2*brev(m), i = 2m+1 at 2*(~brev(m))+1 (m over log-1 bits).  Split m = (a | mid | b)
+// with 5-bit a (top) and b (bottom): brev(m) = (brev5(b) | brev(mid) | brev5(a)), so for fixed (b, mid) the 32 values of a
+// together with both parities are 64 consecutive storage words, and for fixed (a, mid) the 32 values of b are 64
+// consecutive coset positions — once the odd positions are taken from the mirrored tile (~mid), which is why a CTA owns
+// the tile pair {mid, ~mid}.  Pass A un-permutes into `nat` and records the sum of every 64-position run; two small
+// kernels turn run sums into exclusive offsets (64 runs per super-run, then one CTA over the super-runs); pass C scans
+// each run in a warp, adds its offset and permutes back through the same tiles.
+struct PsArgs {
+  uint32_t* v[4];
+  uint32_t* nat[4];
+  uint32_t* run[4];   // 2^(log-6) run sums -> exclusive offsets within their super-run
+  uint32_t* sup[4];   // 2^(log-12) super-run sums -> exclusive offsets
+};
+__device__ __forceinline__ uint32_t brev5(uint32_t x) { return __brev(x) >> 27; }
+__device__ __forceinline__ uint32_t ps_mod(unsigned long long v) {  // v < 2^40
+  uint32_t s = (uint32_t)(v >> 31) + ((uint32_t)v & P);
+  return s >= P ? s - P : s;
+}
+template <bool BACK>
+__global__ void __launch_bounds__(256) ps_tile_kernel(PsArgs a, uint32_t log) {
+  __shared__ uint32_t T[2][32][65];
+  const uint32_t Lp = log - 1, mb = Lp - 10;                 // bits of mid
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t mid[2] = {blockIdx.x, (~blockIdx.x) & ((1u << mb) - 1u)};
+  uint32_t* __restrict__ v = a.v[blockIdx.y];
+  uint32_t* __restrict__ nat = a.nat[blockIdx.y];
+  uint32_t rowbase[2];
+#pragma unroll
+  for (int tt = 0; tt < 2; tt++) rowbase[tt] = (__brev(mid[tt]) >> (32 - mb)) << 6;
+  if (!BACK) {
+#pragma unroll
+    for (int tt = 0; tt < 2; tt++)
+      for (uint32_t b = warp; b < 32; b += 8) {
+        const uint32_t* row = v + ((brev5(b) << (Lp - 4)) | rowbase[tt]);
+        T[tt][b][lane] = row[lane];
+        T[tt][b][lane + 32] = row[lane + 32];
+      }
+    __syncthreads();
+  }
+  for (uint32_t r = warp; r < 64; r += 8) {
+    const uint32_t tt = r >> 5, aa = r & 31u, b = lane;
+    const uint32_t m0 = (aa << (Lp - 5)) | (mid[tt] << 5);
+    const uint32_t ce = 2u * brev5(aa), co = 2u * brev5((~aa) & 31u) + 1u, bo = (~b) & 31u;
+    uint2* np = reinterpret_cast<uint2*>(nat + 2u * (size_t)m0) + b;
+    if (!BACK) {
+      const uint32_t e = T[tt][b][ce], o = T[tt ^ 1u][bo][co];
+      *np = make_uint2(e, o);
+      unsigned long long sum = (unsigned long long)e + o;
+#pragma unroll
+      for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+      if (lane == 0) a.run[blockIdx.y][m0 >> 5] = ps_mod(sum);
+    } else {
+      const uint2 x = *np;
+      const unsigned long long loc = (unsigned long long)x.x + x.y;
+      unsigned long long inc = loc;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        unsigned long long y = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= (uint32_t)d) inc += y;
+      }
+      const uint32_t run = m0 >> 5;
+      const unsigned long long off = (unsigned long long)a.run[blockIdx.y][run] + a.sup[blockIdx.y][run >> 6];
+      T[tt][b][ce] = ps_mod(off + inc - x.y);
+      T[tt ^ 1u][bo][co] = ps_mod(off + inc);
+    }
+  }
+  if (BACK) {
+    __syncthreads();
+#pragma unroll
+    for (int tt = 0; tt < 2; tt++)
+      for (uint32_t b = warp; b < 32; b += 8) {
+        uint32_t* row = v + ((brev5(b) << (Lp - 4)) | rowbase[tt]);
+        row[lane] = T[tt][b][lane];
+        row[lane + 32] = T[tt][b][lane + 32];
+      }
+  }
+}
+// 64 run sums per CTA (one warp, two runs per lane) -> exclusive offsets in place, total to sup
+__global__ void __launch_bounds__(32) ps_runs_kernel(PsArgs a) {
+  uint32_t* run = a.run[blockIdx.y] + (size_t)blockIdx.x * 64;
+  const uint32_t lane = threadIdx.x;
+  const uint2 x = reinterpret_cast<const uint2*>(run)[lane];
+  unsigned long long inc = (unsigned long long)x.x + x.y;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    unsigned long long y = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= (uint32_t)d) inc += y;
+  }
+  const unsigned long long ex = inc - x.x - x.y;
+  reinterpret_cast<uint2*>(run)[lane] = make_uint2(ps_mod(ex), ps_mod(ex + x.x));
+  if (lane == 31) a.sup[blockIdx.y][blockIdx.x] = ps_mod(inc);
+}
+// one CTA per column: exclusive scan of the super-run sums
+__global__ void __launch_bounds__(1024) ps_super_kernel(PsArgs a, uint32_t nsup) {
+  __shared__ unsigned long long wsum[32];
+  uint32_t* sup = a.sup[blockIdx.x];
+  const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  unsigned long long carry = 0;
+  for (uint32_t base = 0; base < nsup; base += 1024) {
+    const uint32_t i = base + threadIdx.x;
+    const unsigned long long x = i < nsup ? sup[i] : 0;
+    unsigned long long inc = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      unsigned long long y = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= (uint32_t)d) inc += y;
+    }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    unsigned long long wb = 0, tot = 0;
+    for (uint32_t k = 0; k < 32; k++) { if (k < w) wb += wsum[k]; tot += wsum[k]; }
+    if (i < nsup) sup[i] = ps_mod(carry + wb + inc - x);
+    carry = ps_mod(carry + tot);
+    __syncthreads();
+  }
+}
+size_t prefix_sum_tiled_words(uint32_t log) { return (((size_t)1 << log) + ((size_t)1 << (log - 6)) + ((size_t)1 << (log - 12)) + 3) & ~(size_t)3; }
+// ncols <= 4 columns of one size (log >= 12); scratch: ncols * prefix_sum_tiled_words(log) words
+int launch_prefix_sum_bitrev_tiled(uint32_t* const* v, uint32_t ncols, uint32_t log, uint32_t* scratch, cudaStream_t st) {
+  if (log < 12 || ncols == 0 || ncols > 4) return -1;
+  const size_t words = prefix_sum_tiled_words(log);
+  PsArgs a;
+  for (uint32_t k = 0; k < 4; k++) {
+    uint32_t* s = scratch + (size_t)(k < ncols ? k : 0) * words;
+    a.v[k] = v[k < ncols ? k : 0];
+    a.nat[k] = s; a.run[k] = s + ((size_t)1 << log); a.sup[k] = a.run[k] + ((size_t)1 << (log - 6));
+  }
+  const uint32_t pairs = 1u << (log - 12);
+  ps_tile_kernel<false><<<dim3(pairs, ncols), 256, 0, st>>>(a, log); g_launch_count++;
+  ps_runs_kernel<<<dim3(1u << (log - 12), ncols), 32, 0, st>>>(a); g_launch_count++;
+  ps_super_kernel<<<ncols, 1024, 0, st>>>(a, 1u << (log - 12)); g_launch_count++;
+  ps_tile_kernel<true><<<dim3(pairs, ncols), 256, 0, st>>>(a, log); g_launch_count++;
+  return (int)cudaGetLastError();
+}
+
 // ---------------------------------------------------------------- eval_at_point
 // value = sum_i c_i * prod_k f_k^{bit_k(i)},  f = [p.y, p.x, pi(p.x), pi^2(p.x), ...]   (CpuBackend fold()).
 // Stage 1: a CTA folds 2^13 base-field coefficients -> one QM31 partial.  A thread owns 32 consecutive coefficients and

@@ -98,9 +98,125 @@ __global__ void __launch_bounds__(128) quotients_kernel(uint32_t log, const uint
   }
 }
 
+// ---------------------------------------------------------------- v2: table-driven points, one inversion per thread
+// The per-thread fixed cost of the kernel above (a 31-step point ladder and one CM31 inversion per sample batch) is several
+// times the useful work when a size has few columns (the 2^26-row launch carries the four composition columns only).
+//  * points: quad kg = (kb << 7) | t has domain index base + brev(kg)*step, and brev splits, so its point is Q[t] + R[kb]
+//    with Q (128 entries) and R (one per 128 quads) written by a small pre-kernel: one group addition per thread;
+//  * denominators: den_r = c0 -/+ piy*x +/- pix*y with c0 = prx*piy - pry*pix folded on the host; the four rows of a quad
+//    and up to QV2_NB batches share ONE base-field inversion (Montgomery's trick on the norms re^2 + im^2);
+//  * the first batch skips the acc*coeff product, and py*suma is formed once per batch.
+constexpr int QV2_NB = 2;
+constexpr uint32_t QV2_TLOG = 7;
+
+__global__ void quot_points_kernel(uint32_t log, uint32_t kb0, uint32_t nkb, Pt* __restrict__ Q, Pt* __restrict__ Rt) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (1u << QV2_TLOG)) {
+    // base + brev7(t) << 23   (the top 7 bits of brev(kg) times the step 2^(32-log))
+    uint32_t idx = ((1u << (30 - log)) + ((__brev(i) >> (32 - QV2_TLOG)) << (31 - QV2_TLOG - 1))) & 0x7fffffffu;
+    Q[i] = q_point_at_index(idx);
+  } else if (i - (1u << QV2_TLOG) < nkb) {
+    const uint32_t kb = kb0 + (i - (1u << QV2_TLOG));
+    const uint32_t hb = log - 2 - QV2_TLOG;                       // bits of kb
+    uint32_t j = hb ? (__brev(kb) >> (32 - hb)) : 0;
+    uint32_t idx = (uint32_t)(((uint64_t)j << (32 - log)) & 0x7fffffffu);
+    Rt[i - (1u << QV2_TLOG)] = q_point_at_index(idx);
+  }
+}
+
+__global__ void __launch_bounds__(128) quotients_kernel2(const uint32_t* const* __restrict__ cols, const QuotBatch* __restrict__ batches,
+                                                         uint32_t nb, const QuotEntry* __restrict__ entries, uint32_t* o0, uint32_t* o1,
+                                                         uint32_t* o2, uint32_t* o3, uint32_t k_off, uint32_t nq,
+                                                         const Pt* __restrict__ Q, const Pt* __restrict__ Rt, uint32_t kb0) {
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < nq; k += gridDim.x * blockDim.x) {
+    const uint32_t kg = k + k_off;
+    const Pt bp = p_add(Q[kg & ((1u << QV2_TLOG) - 1u)], Rt[(kg >> QV2_TLOG) - kb0]);
+    const uint32_t x = bp.x, y = bp.y;                    // rows: (x,y) (x,-y) (-x,-y) (-x,y)
+    QM31 acc[4];
+    for (uint32_t b0 = 0; b0 < nb; b0 += QV2_NB) {
+      const uint32_t nbc = nb - b0 < (uint32_t)QV2_NB ? nb - b0 : (uint32_t)QV2_NB;
+      CM31 den[QV2_NB][4];
+      uint32_t pre[QV2_NB][4];
+      uint32_t run = 1u;
+#pragma unroll
+      for (int bb = 0; bb < QV2_NB; bb++) {
+        if ((uint32_t)bb < nbc) {
+          const QuotBatch& qb = batches[b0 + bb];
+          const CM31 u = c_mulm(qb.piy, x), v = c_mulm(qb.pix, y);
+          const CM31 lo = c_sub(qb.c0, u), hi = c_add(qb.c0, u);
+          den[bb][0] = c_add(lo, v); den[bb][1] = c_sub(lo, v); den[bb][2] = c_sub(hi, v); den[bb][3] = c_add(hi, v);
+#pragma unroll
+          for (int r = 0; r < 4; r++) {
+            pre[bb][r] = run;
+            run = m_mul(run, m_add(m_sqr(den[bb][r].a), m_sqr(den[bb][r].b)));
+          }
+        }
+      }
+      uint32_t inv = m_inv(run);
+      CM31 dinv[QV2_NB][4];
+#pragma unroll
+      for (int bb = QV2_NB - 1; bb >= 0; bb--) {
+        if ((uint32_t)bb < nbc) {
+#pragma unroll
+          for (int r = 3; r >= 0; r--) {
+            const uint32_t ninv = m_mul(inv, pre[bb][r]);                     // 1 / norm
+            inv = m_mul(inv, m_add(m_sqr(den[bb][r].a), m_sqr(den[bb][r].b)));
+            dinv[bb][r] = CM31{m_mul(den[bb][r].a, ninv), m_mul(m_neg(den[bb][r].b), ninv)};   // conj / norm
+          }
+        }
+      }
+#pragma unroll
+      for (int bb = 0; bb < QV2_NB; bb++) {
+        if ((uint32_t)bb < nbc) {
+          const QuotBatch& qb = batches[b0 + bb];
+          uint64_t s[4][4];
+#pragma unroll
+          for (int r = 0; r < 4; r++) { s[r][0] = s[r][1] = s[r][2] = s[r][3] = 0; }
+          const uint32_t e0 = qb.first, e1 = qb.first + qb.count;
+          for (uint32_t e = e0; e < e1; e++) {
+            const QuotEntry en = entries[e];
+            uint4 v = __ldg(reinterpret_cast<const uint4*>(cols[en.col]) + k);
+            const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+              s[r][0] += (uint64_t)en.c[0] * vv[r]; s[r][1] += (uint64_t)en.c[1] * vv[r];
+              s[r][2] += (uint64_t)en.c[2] * vv[r]; s[r][3] += (uint64_t)en.c[3] * vv[r];
+            }
+            if ((e - e0) & 1u) {
+#pragma unroll
+              for (int r = 0; r < 4; r++) { s[r][0] = fold64(s[r][0]); s[r][1] = fold64(s[r][1]); s[r][2] = fold64(s[r][2]); s[r][3] = fold64(s[r][3]); }
+            }
+          }
+          const QM31 ya = q_mulm(qb.suma, y);
+          const QM31 linp = q_add(qb.sumb, ya), linm = q_sub(qb.sumb, ya);   // py = +y rows 0,3 ; -y rows 1,2
+#pragma unroll
+          for (int r = 0; r < 4; r++) {
+            QM31 num = q_make(red64(s[r][0]), red64(s[r][1]), red64(s[r][2]), red64(s[r][3]));
+            num = q_sub(num, (r == 0 || r == 3) ? linp : linm);
+            const QM31 term = q_mulc(num, dinv[bb][r]);
+            acc[r] = (b0 + bb == 0) ? term : q_add(q_mul(acc[r], qb.coeff), term);
+          }
+        }
+      }
+    }
+    reinterpret_cast<uint4*>(o0)[k] = make_uint4(acc[0].a.a, acc[1].a.a, acc[2].a.a, acc[3].a.a);
+    reinterpret_cast<uint4*>(o1)[k] = make_uint4(acc[0].a.b, acc[1].a.b, acc[2].a.b, acc[3].a.b);
+    reinterpret_cast<uint4*>(o2)[k] = make_uint4(acc[0].b.a, acc[1].b.a, acc[2].b.a, acc[3].b.a);
+    reinterpret_cast<uint4*>(o3)[k] = make_uint4(acc[0].b.b, acc[1].b.b, acc[2].b.b, acc[3].b.b);
+  }
+}
+
+// words of device scratch launch_accumulate_quotients needs for its point tables (0: the small-domain kernel is used)
+size_t quotients_scratch_words(uint32_t log, uint64_t row_off, uint64_t nrows) {
+  if (log < 2 + QV2_TLOG + 1 || nrows == 0) return 0;
+  uint64_t k0 = row_off >> 2, k1 = (row_off + nrows) >> 2;
+  uint64_t nkb = ((k1 + 127) >> QV2_TLOG) - (k0 >> QV2_TLOG);
+  return (size_t)(128 + nkb) * (sizeof(Pt) / 4);
+}
+
 int launch_accumulate_quotients(uint32_t log, uint64_t row_off, uint64_t nrows, const uint32_t* const* d_cols,
                                 const QuotBatch* d_batches, uint32_t nb, const QuotEntry* d_entries, uint32_t* const out[4],
-                                cudaStream_t st) {
+                                cudaStream_t st, uint32_t* d_scratch) {
   static bool init = false;
   if (!init) {
     Pt g[31];
@@ -114,6 +230,15 @@ int launch_accumulate_quotients(uint32_t log, uint64_t row_off, uint64_t nrows, 
   uint32_t nq = (uint32_t)(nrows >> 2);
   uint32_t blocks = (nq + 127) / 128;
   if (blocks > 148u * 16u) blocks = 148u * 16u;
+  if (d_scratch && quotients_scratch_words(log, row_off, nrows)) {
+    const uint32_t k0 = (uint32_t)(row_off >> 2), kb0 = k0 >> QV2_TLOG;
+    const uint32_t nkb = ((k0 + nq + 127) >> QV2_TLOG) - kb0;
+    Pt* Q = reinterpret_cast<Pt*>(d_scratch);
+    Pt* Rt = Q + 128;
+    quot_points_kernel<<<(128 + nkb + 127) / 128, 128, 0, st>>>(log, kb0, nkb, Q, Rt); g_launch_count++;
+    quotients_kernel2<<<blocks, 128, 0, st>>>(d_cols, d_batches, nb, d_entries, out[0], out[1], out[2], out[3], k0, nq, Q, Rt, kb0); g_launch_count++;
+    return (int)cudaGetLastError();
+  }
   quotients_kernel<<<blocks, 128, 0, st>>>(log, d_cols, d_batches, nb, d_entries, out[0], out[1], out[2], out[3],
                                            (uint32_t)(row_off >> 2), nq); g_launch_count++;
   return (int)cudaGetLastError();

@@ -197,6 +197,37 @@ def test_accumulate_quotients(be, orc, log, ncols):
     assert not z[0].to_cpu().any()
 
 
+@pytest.mark.parametrize("log,ncols,nbatch", [(10, 5, 1), (11, 9, 3), (12, 4, 5), (16, 24, 2), (17, 6, 4)])
+def test_accumulate_quotients_many_batches(be, orc, pkg, log, ncols, nbatch):
+    """Domains of >= 2^10 rows take the table-driven kernel; batch counts around its chunk size (2), row ranges included."""
+    import ctypes
+    cols = [rnd(1900 + i, 1 << log) for i in range(ncols)]
+    alpha = rnd(11, 4)
+    pts = rnd(12, 8 * nbatch)
+    bsizes = [max(1, ncols - b) for b in range(nbatch)]
+    ecols = [c for b in range(nbatch) for c in range(ncols - bsizes[b], ncols)]
+    evals = rnd(13, 4 * len(ecols))
+    dcols = [be.column(c) for c in cols]
+    got = be.accumulate_quotients(log, dcols, alpha, pts, bsizes, ecols, evals)
+    ref = orc.accumulate_quotients(log, cols, alpha, pts, bsizes, ecols, evals)
+    for g, r in zip(got, ref):
+        assert (g.to_cpu() == r).all()
+    # a row range that starts and ends off the 512-row table granularity (sharded prover's call)
+    off, n = (1 << log) // 4 + 4 * 37, (1 << log) // 2 + 4 * 5
+    views = [be.column(c[off:off + n]) for c in cols]
+    out = (ctypes.c_void_p * 4)()
+    rc, bp, bs = (np.ascontiguousarray(a, dtype=np.uint32) for a in (alpha, pts, bsizes))
+    ec, ev = (np.ascontiguousarray(a, dtype=np.uint32) for a in (ecols, evals))
+    u32p = ctypes.POINTER(ctypes.c_uint32)
+    be._ck(be._lib.sc_accumulate_quotients_range(be._ctx, ctypes.c_uint32(log), ctypes.c_uint64(off), ctypes.c_uint64(n), be._arr(views),
+                                                 ctypes.c_uint32(len(views)), rc.ctypes.data_as(u32p), bp.ctypes.data_as(u32p),
+                                                 bs.ctypes.data_as(u32p), ec.ctypes.data_as(u32p), ev.ctypes.data_as(u32p),
+                                                 ctypes.c_uint32(bs.size), out))
+    for k in range(4):
+        part = pkg.Column(be, ctypes.c_void_p(out[k])).to_cpu()
+        assert (part == ref[k][off:off + n]).all(), f"range coordinate {k}"
+
+
 def test_grind(be, orc):
     for seed in range(4):
         d = np.random.default_rng(seed).integers(0, 2**32, size=8, dtype=np.uint32)
