@@ -40,6 +40,12 @@ int32_t sc_accumulate_quotients_range(sc_ctx* ctx, uint32_t log, uint64_t row_of
 /* the LDE of a LogUp cumulative column read at coset offset -1, as a column (so it can be re-sharded like the others) */
 int32_t sc_shift_prev(sc_ctx* ctx, const sc_col* col, uint32_t trace_log, sc_col** out);
 int32_t sc_accumulate_col(sc_ctx* ctx, sc_col* dst, const sc_col* src);
+/* sc_evaluate_repeated (stwo_cuda.h) restricted to rows [row_off[i], row_off[i]+row_cnt[i]) of column i, both multiples of
+ * 2^log_repeat.  The main-trace values are replicated on every rank and their transforms cost 1/16 of a full column, so a
+ * rank computes all of them and keeps only its row range: the main tree needs no LDE exchange. */
+int32_t sc_evaluate_repeated_range(sc_ctx* ctx, sc_col* const* coeffs, uint32_t n, uint32_t log_repeat, uint32_t log_blowup,
+                                   const sc_twiddles* tw, const uint64_t* row_off, const uint64_t* row_cnt, sc_col** out);
+
 /* LogUp generation materialising only the wanted coordinate columns (no prefix sum; use sc_prefix_sum_bitrev on the owner) */
 int32_t sc_logup_generate_sel(sc_ctx* ctx, int32_t component, sc_col* const* main_cols, uint32_t n_main, uint32_t log_repeat,
                               const uint32_t* elements, const uint8_t* want, sc_col** out);

@@ -213,6 +213,12 @@ struct OrcBackend : Backend {
     }
     return out;
   }
+  std::vector<Col> evaluate_repeated_range(const std::vector<Col>& coeffs, uint32_t rep, uint32_t log_blowup, const std::vector<size_t>& offs,
+                                           const std::vector<size_t>& cnts) override {
+    std::vector<Col> full = evaluate_repeated(coeffs, rep, log_blowup), out(coeffs.size());
+    for (size_t i = 0; i < coeffs.size(); i++) { out[i] = new HCol(H(full[i])->d + offs[i], cnts[i]); delete H(full[i]); }
+    return out;
+  }
   std::vector<sb::QM31> eval_at_point_repeated(const std::vector<Col>& polys, const std::vector<uint32_t>& reps, const std::vector<QPoint>& pts) override {
     std::vector<sb::QM31> out(polys.size());
 #pragma omp parallel for schedule(dynamic)
@@ -494,7 +500,7 @@ char* orc_prove_sharded_json(const char* code, const uint8_t* input, size_t inpu
           OrcBackend B;
           B.my_rank = r;
           if (world > 1) B.comm = &comm;
-          ProveResult res = prove_brainfuck_sharded(B, program, vm.trace, cfg);
+          ProveResult res = prove_brainfuck_sharded(B, program, TraceSource([&]() -> const std::vector<Registers>& { return vm.trace; }), cfg);
           if (verify) verify_brainfuck(res.proof, cfg);
           json[r] = proof_to_json(res.proof);
         } catch (const std::exception& e) {

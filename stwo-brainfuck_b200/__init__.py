@@ -434,7 +434,7 @@ def prove_brainfuck(backend: CudaBackend, code: str, stdin: bytes = b"", log_max
 SHARDED_SYMBOLS = ["sc_comm_unique_id", "sc_comm_init", "sc_comm_destroy", "sc_comm_rank", "sc_comm_world", "sc_all_to_all",
                    "sc_all_gather", "sc_allreduce_host_u32", "sc_col_copy", "sc_col_view", "sc_fold_line_range",
                    "sc_fold_circle_into_line_range", "sc_accumulate_quotients_range", "sc_shift_prev", "sc_accumulate_col",
-                   "sc_logup_generate_sel", "sc_eval_constraints_range", "sbf_prove_sharded"]
+                   "sc_logup_generate_sel", "sc_eval_constraints_range", "sc_evaluate_repeated_range", "sbf_prove_sharded"]
 
 
 class Comm:

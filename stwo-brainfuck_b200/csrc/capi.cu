@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <tuple>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -419,44 +420,64 @@ int32_t sc_interpolate_repeated(sc_ctx* ctx, sc_col* const* cols, uint32_t n, ui
 }
 
 // coeffs: compact coefficients (sc_interpolate_repeated).  out: new FULL columns of length (len << log_repeat) << log_blowup.
-int32_t sc_evaluate_repeated(sc_ctx* ctx, sc_col* const* coeffs, uint32_t n, uint32_t log_repeat, uint32_t log_blowup, const sc_twiddles* tw, sc_col** out) {
+static int32_t evaluate_repeated_impl(sc_ctx* ctx, sc_col* const* coeffs, uint32_t n, uint32_t log_repeat, uint32_t log_blowup, const sc_twiddles* tw,
+                                      const uint64_t* row_off, const uint64_t* row_cnt, sc_col** out) {
   ENTER();
   if (!tw || !out || (!coeffs && n)) return fail(SC_EINVAL, "null argument");
   if (log_blowup > 1) return fail(SC_EINVAL, "evaluate_repeated: log_blowup > 1 is not supported");
   if (log_repeat < 2 || log_repeat > 8) return fail(SC_EINVAL, "evaluate_repeated: log_repeat must be in [2, 8]");
-  struct G { std::vector<const uint32_t*> src; std::vector<uint32_t*> tmp, dst; };
-  std::map<uint32_t, G> by_log;
+  struct G { std::vector<const uint32_t*> src; std::vector<uint32_t*> tmp, dst; std::vector<const uint32_t*> part; };
+  struct Key { uint32_t lg; uint64_t off, cnt; bool operator<(const Key& o) const { return std::tie(lg, off, cnt) < std::tie(o.lg, o.off, o.cnt); } };
+  std::map<Key, G> groups;
+  const uint64_t rmask = (1ull << log_repeat) - 1;
   for (uint32_t i = 0; i < n; i++) {
     if (!coeffs[i] || !is_pow2(coeffs[i]->len)) return fail(SC_EINVAL, "evaluate_repeated: column length must be a power of two");
     uint32_t lg = ilog2(coeffs[i]->len);
     if (lg + log_blowup + log_repeat > tw->root_log + 1 || lg + log_blowup > tw->root_log) return fail(SC_EINVAL, "evaluate_repeated: twiddle tree too small for this domain");
+    if (row_off) {
+      uint64_t full = (coeffs[i]->len << log_repeat) << log_blowup;
+      if ((row_off[i] & rmask) || (row_cnt[i] & rmask) || row_off[i] + row_cnt[i] > full) return fail(SC_EINVAL, "evaluate_repeated: row range must be aligned to the repetition and inside the domain");
+    }
   }
   std::vector<uint32_t*> temps;
   for (uint32_t i = 0; i < n; i++) {
     uint32_t lg = ilog2(coeffs[i]->len);
-    int32_t r = new_col(ctx, (coeffs[i]->len << log_repeat) << log_blowup, &out[i]);
+    uint64_t full = (coeffs[i]->len << log_repeat) << log_blowup;
+    uint64_t off = row_off ? row_off[i] : 0, cnt = row_off ? row_cnt[i] : full;
+    int32_t r = new_col(ctx, cnt, &out[i]);
     if (r) return r;
     uint32_t* t;
     CK(cudaMallocAsync((void**)&t, (coeffs[i]->len << log_blowup) * 4, ctx->st));
     temps.push_back(t);
-    G& g = by_log[lg];
-    g.src.push_back(coeffs[i]->d); g.tmp.push_back(t); g.dst.push_back(out[i]->d);
+    G& g = groups[Key{lg, off, cnt}];
+    g.src.push_back(coeffs[i]->d); g.tmp.push_back(t); g.dst.push_back(out[i]->d); g.part.push_back(t + (off >> log_repeat));
   }
-  for (auto& kv : by_log) {
-    void *ds, *dt, *dd;
+  for (auto& kv : groups) {
+    void *ds, *dt, *dd, *dpart;
     size_t nc = kv.second.src.size();
     int32_t r = stage(ctx, kv.second.src.data(), nc * sizeof(void*), &ds); if (r) return r;
     r = stage(ctx, kv.second.tmp.data(), nc * sizeof(void*), &dt); if (r) return r;
     r = stage(ctx, kv.second.dst.data(), nc * sizeof(void*), &dd); if (r) return r;
+    r = stage(ctx, kv.second.part.data(), nc * sizeof(void*), &dpart); if (r) return r;
     {
       ProfScope ps_(ctx, "fft_evaluate");
-      CKL(launch_evaluate_repeated((const uint32_t* const*)ds, (uint32_t* const*)dt, (uint32_t)nc, kv.first, kv.first + log_blowup,
+      CKL(launch_evaluate_repeated((const uint32_t* const*)ds, (uint32_t* const*)dt, (uint32_t)nc, kv.first.lg, kv.first.lg + log_blowup,
                                    tw->tw + ((size_t)2 << tw->root_log), ctx->st));
     }
-    { ProfScope ps_(ctx, "broadcast16"); CKL(launch_broadcast_cols((const uint32_t* const*)dt, (uint32_t* const*)dd, (uint32_t)nc, (size_t)1 << (kv.first + log_blowup), log_repeat, ctx->st)); }
+    if (kv.first.cnt) { ProfScope ps_(ctx, "broadcast16"); CKL(launch_broadcast_cols((const uint32_t* const*)dpart, (uint32_t* const*)dd, (uint32_t)nc, (size_t)(kv.first.cnt >> log_repeat), log_repeat, ctx->st)); }
   }
   for (uint32_t* t : temps) CK(cudaFreeAsync(t, ctx->st));
   return SC_OK;
+}
+int32_t sc_evaluate_repeated(sc_ctx* ctx, sc_col* const* coeffs, uint32_t n, uint32_t log_repeat, uint32_t log_blowup, const sc_twiddles* tw, sc_col** out) {
+  return evaluate_repeated_impl(ctx, coeffs, n, log_repeat, log_blowup, tw, nullptr, nullptr, out);
+}
+// Rows [row_off[i], row_off[i] + row_cnt[i]) of the evaluation only (both multiples of 2^log_repeat): what one rank of the
+// sharded prover keeps of a main-trace column — every rank transforms the distinct values itself instead of exchanging LDEs.
+int32_t sc_evaluate_repeated_range(sc_ctx* ctx, sc_col* const* coeffs, uint32_t n, uint32_t log_repeat, uint32_t log_blowup, const sc_twiddles* tw,
+                                   const uint64_t* row_off, const uint64_t* row_cnt, sc_col** out) {
+  if (n && (!row_off || !row_cnt)) return fail(SC_EINVAL, "null argument");
+  return evaluate_repeated_impl(ctx, coeffs, n, log_repeat, log_blowup, tw, row_off, row_cnt, out);
 }
 
 static int32_t eval_at_point_impl(sc_ctx* ctx, sc_col* const* polys, const uint32_t* log_repeats, uint32_t n, const uint32_t* points, uint32_t* out);

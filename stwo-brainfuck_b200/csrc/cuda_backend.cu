@@ -80,6 +80,15 @@ struct CudaBackendImpl : Backend {
     ck(sc_evaluate_repeated(ctx, (sc_col* const*)coeffs.data(), (uint32_t)coeffs.size(), rep, log_blowup, tw, (sc_col**)out.data()));
     return out;
   }
+  std::vector<Col> evaluate_repeated_range(const std::vector<Col>& coeffs, uint32_t rep, uint32_t log_blowup, const std::vector<size_t>& offs,
+                                           const std::vector<size_t>& cnts) override {
+    std::vector<Col> out(coeffs.size());
+    if (coeffs.empty()) return out;
+    std::vector<uint64_t> o(offs.begin(), offs.end()), c(cnts.begin(), cnts.end());
+    ck(sc_evaluate_repeated_range(ctx, (sc_col* const*)coeffs.data(), (uint32_t)coeffs.size(), rep, log_blowup, tw, o.data(), c.data(),
+                                  (sc_col**)out.data()));
+    return out;
+  }
   std::vector<QM31> eval_at_point_repeated(const std::vector<Col>& polys, const std::vector<uint32_t>& reps, const std::vector<QPoint>& pts) override {
     std::vector<QM31> out(polys.size());
     if (polys.empty()) return out;
@@ -266,18 +275,22 @@ int32_t sbf_prove_sharded(sc_ctx* ctx, sc_comm* comm, const char* code, const ui
                           uint32_t flags, sbf_proof** out) {
   try {
     if (!ctx || !code || !out) throw std::runtime_error("null argument");
-    auto t0 = std::chrono::steady_clock::now();
     std::vector<uint32_t> program = compile(code);
     Machine vm(program, std::vector<uint8_t>(input, input + input_len));
-    vm.execute();
-    double vm_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    double vm_ms = 0;
+    TraceSource run_vm = [&]() -> const std::vector<Registers>& {  // called on the prover's host thread, beside the preprocessed phase
+      auto t0 = std::chrono::steady_clock::now();
+      vm.execute();
+      vm_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      return vm.trace;
+    };
     CudaBackendImpl B(ctx);
     B.comm = comm;
     ProverConfig cfg;
     cfg.log_max_rows = log_max_rows;
     B.cache_twiddles = !(flags & 2u);
     auto t1 = std::chrono::steady_clock::now();
-    ProveResult r = prove_brainfuck_sharded(B, program, vm.trace, cfg, [&] { sc_ctx_sync(ctx); });
+    ProveResult r = prove_brainfuck_sharded(B, program, run_vm, cfg, [&] { sc_ctx_sync(ctx); });
     double prove_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
     sbf_proof* p = new sbf_proof{std::move(r.proof), cfg, "", vm.output};
     std::ostringstream o;

@@ -47,6 +47,9 @@ struct Backend {
   // column (coefficient j = coefficient j << rep of the full vector) and the two evaluators take that compact form.
   virtual std::vector<Col> interpolate_repeated(const std::vector<Col>& values, uint32_t rep) = 0;                       // new columns; inputs kept
   virtual std::vector<Col> evaluate_repeated(const std::vector<Col>& coeffs, uint32_t rep, uint32_t log_blowup) = 0;     // full-length evaluations
+  // rows [offs[i], offs[i] + cnts[i]) of evaluate_repeated's column i (multiples of 2^rep): a rank's share in the sharded prover
+  virtual std::vector<Col> evaluate_repeated_range(const std::vector<Col>& coeffs, uint32_t rep, uint32_t log_blowup,
+                                                   const std::vector<size_t>& offs, const std::vector<size_t>& cnts) = 0;
   virtual std::vector<QM31> eval_at_point_repeated(const std::vector<Col>& polys, const std::vector<uint32_t>& reps,
                                                    const std::vector<QPoint>& pts) = 0;
   // merkle_commit of full-length columns that all repeat each value 2^rep times (the deepest `rep` layers then repeat too)

@@ -122,7 +122,8 @@ inline SMerkle merkle_sharded(Backend& B, const ShardLayout& sl, const std::vect
 struct STree {
   std::vector<uint32_t> logs;  // polynomial log size per column
   std::vector<int> owner;
-  std::vector<Col> polys;      // coefficient column on the owner, nullptr elsewhere
+  std::vector<Col> polys;      // coefficient column on the owner, nullptr elsewhere (every rank when `rep`)
+  uint32_t rep = 0;            // main trace: compact coefficients of lane-repeated columns (backend.hpp), held by every rank
   std::vector<RowCol> rows;    // LDE as seen by this rank
   std::vector<Col> bufs;       // buffers behind `rows`
   SMerkle merkle;
@@ -243,7 +244,7 @@ inline void fri_witness_sharded(FetchBatch& fb, const ShardLayout& sl, const std
   });
 }
 
-inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_t>& code, const std::vector<Registers>& vm_trace,
+inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_t>& code, const TraceSource& run_vm,
                                            const ProverConfig& cfg, const std::function<void()>& sync = nullptr) {
   ProveResult R;
   BrainfuckProof& proof = R.proof;
@@ -288,6 +289,24 @@ inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_
     B.interpolate(owned);
   };
 
+  // The VM run and this rank's tables (table k is built by rank k % N only: host work and PCIe traffic are divided by N)
+  // proceed on a host thread while the program-independent preprocessed phase below keeps the device and this thread busy.
+  std::vector<Table> tables(N_COMPONENTS);
+  std::string host_err;
+  struct Joiner { std::thread t; ~Joiner() { if (t.joinable()) t.join(); } } host;
+  host.t = std::thread([&] {
+    try {
+      const std::vector<Registers>& vm_trace = run_vm();
+      std::vector<std::string> err(N_COMPONENTS);
+      std::vector<std::thread> th;
+      for (int k = 0; k < N_COMPONENTS; k++)
+        if (k % N == me)
+          th.emplace_back([&, k] { try { tables[k] = build_table(k, vm_trace, code); } catch (const std::exception& e) { err[k] = e.what(); } });
+      for (auto& x : th) x.join();
+      for (auto& e : err) if (!e.empty()) { host_err = e; break; }
+    } catch (const std::exception& e) { host_err = e.what(); }
+  });
+
   // ---- phase 0: preprocessed trace
   {
     STree t;
@@ -302,20 +321,11 @@ inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_
   }
   lap("preprocessed");
 
-  // ---- phase 1: main trace.  Table k is built by rank k % N only (host work and PCIe traffic are divided by N); the compact
-  // columns (one word per table row, 63 MB in total for fib19) are then replicated over NVLink, because LogUp generation and
-  // the 16x expansion of owned columns need them everywhere.  Only owned columns are expanded and transformed.
-  std::vector<Table> tables(N_COMPONENTS);
-  {
-    std::vector<std::string> err(N_COMPONENTS);
-    std::vector<std::thread> th;
-    for (int k = 0; k < N_COMPONENTS; k++)
-      if (k % N == me)
-        th.emplace_back([&, k] { try { tables[k] = build_table(k, vm_trace, code); } catch (const std::exception& e) { err[k] = e.what(); } });
-    for (auto& x : th) x.join();
-    for (auto& e : err) if (!e.empty()) throw std::runtime_error(e);
-  }
-  lap("tables(host)");
+  // ---- phase 1: main trace.  The compact columns (one word per table row, 63 MB in total for fib19) are replicated over
+  // NVLink, because LogUp generation and the transforms below need them on every rank.
+  host.t.join();
+  if (!host_err.empty()) throw std::runtime_error(host_err);
+  lap("tables(host)");  // only the part of the host work the preprocessed phase did not hide
   std::vector<std::vector<Col>> compact(N_COMPONENTS);
   Col compact_recv = nullptr;
   {
@@ -362,13 +372,31 @@ inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_
       for (int c = 0; c < N_COMPONENTS; c++)
         for (int j = 0; j < N_MAIN_COLS[c]; j++) { compact[c].push_back(B.view(compact_recv, roff[c % N], rows_of(c))); roff[c % N] += rows_of(c); }
     }
-    size_t k = 0;
-    for (int c = 0; c < N_COMPONENTS; c++)
-      for (Col cc : compact[c]) { t.polys.push_back(t.owner[k] == me ? B.broadcast16(cc) : nullptr); k++; }
-    interpolate_owned(t);
+    // Every table row fills 16 lanes, so a column's transforms run on its distinct values at 1/16 of the cost; the values
+    // are on every rank already, so each rank transforms ALL main columns and expands only its own row range of the LDE:
+    // the main tree needs no column->row exchange at all.
+    std::vector<Col> values;
+    for (int c = 0; c < N_COMPONENTS; c++) for (Col cc : compact[c]) values.push_back(cc);
+    t.rep = LOG_N_LANES;
+    t.polys = B.interpolate_repeated(values, t.rep);
     for (int c = 0; c < N_COMPONENTS; c++) ch.mix_u64(proof.log_size[c]);
-    std::vector<Col> lde = lde_owned(t);
-    exchange_and_commit(B, sl, cfg.log_blowup, t, lde, {}, nullptr);
+    {
+      std::vector<size_t> offs, cnts;
+      for (size_t c = 0; c < t.logs.size(); c++) {
+        uint32_t L = t.logs[c] + cfg.log_blowup;
+        bool sh = sl.circle_sharded(L);
+        size_t seg = sh ? ((size_t)1 << (L - sl.w)) : ((size_t)1 << L);
+        offs.push_back(sh ? (size_t)me * seg : 0);
+        cnts.push_back(seg);
+      }
+      std::vector<Col> rows = B.evaluate_repeated_range(t.polys, t.rep, cfg.log_blowup, offs, cnts);
+      for (size_t c = 0; c < t.logs.size(); c++) {
+        uint32_t L = t.logs[c] + cfg.log_blowup;
+        t.rows.push_back({rows[c], L, sl.circle_sharded(L), cnts[c]});
+        t.bufs.push_back(rows[c]);
+      }
+      t.merkle = merkle_sharded(B, sl, t.rows);
+    }
     ch.mix_root(t.merkle.root);
     trees.push_back(std::move(t));
   }
@@ -548,14 +576,17 @@ inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_
     std::vector<Col> polys;
     std::vector<QPoint> pts;
     std::vector<size_t> slots;
+    std::vector<uint32_t> reps;
     size_t n_slots = 0;
     for (size_t t = 0; t < trees.size(); t++)
       for (size_t c = 0; c < trees[t].polys.size(); c++)
         for (auto& p : mask.points[t][c]) {
-          if (trees[t].polys[c]) { polys.push_back(trees[t].polys[c]); pts.push_back(p); slots.push_back(n_slots); }
+          if (trees[t].polys[c] && (!trees[t].rep || trees[t].owner[c] == me)) {
+            polys.push_back(trees[t].polys[c]); pts.push_back(p); reps.push_back(trees[t].rep); slots.push_back(n_slots);
+          }
           n_slots++;
         }
-    std::vector<QM31> vals = B.eval_at_point(polys, pts);
+    std::vector<QM31> vals = B.eval_at_point_repeated(polys, reps, pts);
     std::vector<uint32_t> table(4 * n_slots, 0);
     for (size_t j = 0; j < slots.size(); j++) memcpy(&table[4 * slots[j]], &vals[j], 16);
     if (N > 1) B.allreduce_host(table.data(), table.size());

@@ -26,6 +26,8 @@ __device__ __forceinline__ uint32_t fadd(uint32_t x, uint32_t y, uint32_t one) {
   asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(one), "r"(y));
   return r;
 }
+// Tried and rejected (tools/merkle_bench.py, B200): rotating by 16 on the FMA pipe as x*2^16 -> lo+hi (IMAD.WIDE + IMAD) to take
+// one of the eight ALU ops per G off the ALU pipe: 17.8-20.0 G compressions/s against 19.8-22.3 with the PRMT below.
 #define B2S_G(a, b, c, d, x, y)      \
   do {                               \
     a = fadd(b, a, one);             \
