@@ -160,6 +160,11 @@ struct CudaBackendImpl : Backend {
     ck(sc_merkle_commit_layer(ctx, log, h(prev), (sc_col* const*)cols.data(), (uint32_t)cols.size(), &o));
     return o;
   }
+  Col commit_layer_repeated(uint32_t log, Col prev, const std::vector<Col>& cols, uint32_t rep) override {
+    sc_col* o;
+    ck(sc_merkle_commit_layer_repeated(ctx, log, h(prev), (sc_col* const*)cols.data(), (uint32_t)cols.size(), rep, &o));
+    return o;
+  }
   void all_to_all(Col send, const std::vector<size_t>& sc, Col recv, const std::vector<size_t>& rc) override {
     if (!comm) { copy(recv, 0, send, 0, sc[0]); return; }
     std::vector<uint64_t> s(sc.begin(), sc.end()), r(rc.begin(), rc.end());

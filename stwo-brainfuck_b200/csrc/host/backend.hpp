@@ -59,6 +59,8 @@ struct Backend {
   virtual std::vector<Col> merkle_commit(const std::vector<Col>& cols, Hash* root) = 0;
   // MerkleOps::commit_on_layer on 2^log rows (also used on row ranges: the node function is local to a row)
   virtual Col commit_layer(uint32_t log, Col prev, const std::vector<Col>& cols) = 0;
+  // same when every column (hence every node) of these 2^log rows repeats 2^rep times: backends may hash one node per group
+  virtual Col commit_layer_repeated(uint32_t log, Col prev, const std::vector<Col>& cols, uint32_t rep) { (void)rep; return commit_layer(log, prev, cols); }
   // FriOps
   virtual std::array<Col, 4> fold_line(const std::array<Col, 4>& src, uint32_t log, QM31 alpha) = 0;
   virtual void fold_circle_into_line(const std::array<Col, 4>& dst, const std::array<Col, 4>& src, uint32_t log, QM31 alpha) = 0;

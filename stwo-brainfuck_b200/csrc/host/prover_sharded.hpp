@@ -80,7 +80,8 @@ struct SMerkle {
   Hash root;
 };
 // Row-sharded MerkleProver::commit over columns that are either row ranges (sharded) or whole (replicated).
-inline SMerkle merkle_sharded(Backend& B, const ShardLayout& sl, const std::vector<RowCol>& cols) {
+// rep: every column repeats each value 2^rep times (main trace); the deepest `rep` layers then hash one node per group.
+inline SMerkle merkle_sharded(Backend& B, const ShardLayout& sl, const std::vector<RowCol>& cols, uint32_t rep = 0) {
   SMerkle m;
   uint32_t maxL = 0;
   for (auto& c : cols) maxL = std::max(maxL, c.L);
@@ -96,7 +97,8 @@ inline SMerkle merkle_sharded(Backend& B, const ShardLayout& sl, const std::vect
       if (c.sharded) lc.push_back(c.rows);
       else { Col v = B.view(c.rows, (size_t)sl.rank * n, n); tmp.push_back(v); lc.push_back(v); }
     }
-    Col layer = B.commit_layer((uint32_t)(k - w), prev, lc);
+    const uint32_t depth = maxL - (uint32_t)k, lrep = rep > depth ? rep - depth : 0;
+    Col layer = lrep && (uint32_t)(k - w) >= lrep ? B.commit_layer_repeated((uint32_t)(k - w), prev, lc, lrep) : B.commit_layer((uint32_t)(k - w), prev, lc);
     for (Col v : tmp) B.free_col(v);
     m.layers[k] = layer;
     prev = layer;
@@ -345,10 +347,11 @@ inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_
         for (auto& col : tables[c].cols) compact[c].push_back(B.from_host_async(col.data(), col.size()));
     } else {
       auto rows_of = [&](int c) { return (size_t)1 << (ls[c] - LOG_N_LANES); };
+      auto seg_of = [&](int c) { return std::max<size_t>(rows_of(c), 4); };  // 16-byte aligned slots: the views feed vector loads
       std::vector<size_t> scount(N, 0), rcount(N, 0);
       for (int c = 0; c < N_COMPONENTS; c++) {
-        rcount[c % N] += rows_of(c) * N_MAIN_COLS[c];
-        if (c % N == me) for (int d = 0; d < N; d++) scount[d] += rows_of(c) * N_MAIN_COLS[c];
+        rcount[c % N] += seg_of(c) * N_MAIN_COLS[c];
+        if (c % N == me) for (int d = 0; d < N; d++) scount[d] += seg_of(c) * N_MAIN_COLS[c];
       }
       size_t mine = scount[0], rtot = 0;
       for (int s2 = 0; s2 < N; s2++) rtot += rcount[s2];
@@ -362,7 +365,7 @@ inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_
             Col u = B.from_host_async(col.data(), col.size());
             up.push_back(u);
             for (int d = 0; d < N; d++) B.copy(send, (size_t)d * mine + so, u, 0, col.size());
-            so += col.size();
+            so += seg_of(c);
           }
       B.all_to_all(send, scount, compact_recv, rcount);
       B.free_col(send);
@@ -370,7 +373,7 @@ inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_
       std::vector<size_t> roff(N, 0);
       { size_t o = 0; for (int s2 = 0; s2 < N; s2++) { roff[s2] = o; o += rcount[s2]; } }
       for (int c = 0; c < N_COMPONENTS; c++)
-        for (int j = 0; j < N_MAIN_COLS[c]; j++) { compact[c].push_back(B.view(compact_recv, roff[c % N], rows_of(c))); roff[c % N] += rows_of(c); }
+        for (int j = 0; j < N_MAIN_COLS[c]; j++) { compact[c].push_back(B.view(compact_recv, roff[c % N], rows_of(c))); roff[c % N] += seg_of(c); }
     }
     // Every table row fills 16 lanes, so a column's transforms run on its distinct values at 1/16 of the cost; the values
     // are on every rank already, so each rank transforms ALL main columns and expands only its own row range of the LDE:
@@ -395,7 +398,7 @@ inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_
         t.rows.push_back({rows[c], L, sl.circle_sharded(L), cnts[c]});
         t.bufs.push_back(rows[c]);
       }
-      t.merkle = merkle_sharded(B, sl, t.rows);
+      t.merkle = merkle_sharded(B, sl, t.rows, t.rep);
     }
     ch.mix_root(t.merkle.root);
     trees.push_back(std::move(t));
