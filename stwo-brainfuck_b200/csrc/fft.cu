@@ -132,7 +132,7 @@ __host__ __device__ constexpr int round_start(int nbits, int i) {
   for (int j = 0; j < i; j++) s += round_size(nbits, j);
   return s;
 }
-constexpr int STRIDED_C = 4;  // contiguous words per row of a strided tile
+constexpr int STRIDED_C = 4;  // log2 of the contiguous words per row of a strided tile (64-byte runs); 3 for the 10-layer pass
 
 struct FftArgs {
   const uint32_t* const* src;
@@ -222,35 +222,36 @@ __device__ __forceinline__ void fft_round(uint32_t* __restrict__ sm, const FftAr
 }
 
 // Runs round I of the pass (ascending bit order); inverse walks I = 0..NR-1, forward NR-1..0.
-template <bool INV, int K, bool LOW, bool LINE, int I>
+template <bool INV, int K, bool LOW, bool LINE, int SC, int I>
 __device__ __forceinline__ void run_round(uint32_t* sm, const FftArgs& a, uint32_t T) {
-  constexpr int C0 = LOW ? 0 : STRIDED_C;
+  constexpr int C0 = LOW ? 0 : SC;
   constexpr int NB = K - C0;
   constexpr int R = round_size(NB, I);
   constexpr int B = C0 + round_start(NB, I);
-  const uint32_t gb = LOW ? (uint32_t)B : a.L0 + (uint32_t)(B - STRIDED_C);
+  const uint32_t gb = LOW ? (uint32_t)B : a.L0 + (uint32_t)(B - SC);
   fft_round<INV, K, B, R, (LOW && B == 0 && !LINE)>(sm, a, T, gb);
   __syncthreads();
 }
-template <bool INV, int K, bool LOW, bool LINE, int I, int NR>
+template <bool INV, int K, bool LOW, bool LINE, int SC, int I, int NR>
 struct Rounds {
   static __device__ __forceinline__ void run(uint32_t* sm, const FftArgs& a, uint32_t T) {
-    run_round<INV, K, LOW, LINE, (INV ? I : NR - 1 - I)>(sm, a, T);
-    Rounds<INV, K, LOW, LINE, I + 1, NR>::run(sm, a, T);
+    run_round<INV, K, LOW, LINE, SC, (INV ? I : NR - 1 - I)>(sm, a, T);
+    Rounds<INV, K, LOW, LINE, SC, I + 1, NR>::run(sm, a, T);
   }
 };
-template <bool INV, int K, bool LOW, bool LINE, int NR>
-struct Rounds<INV, K, LOW, LINE, NR, NR> {
+template <bool INV, int K, bool LOW, bool LINE, int SC, int NR>
+struct Rounds<INV, K, LOW, LINE, SC, NR, NR> {
   static __device__ __forceinline__ void run(uint32_t*, const FftArgs&, uint32_t) {}
 };
 
 // LINE: every layer is a line layer (layer l uses the 2^(n-1-l) twiddles at twend - 2^(n-l), l = 0 included).  That is the
 // transform of a column whose evaluations repeat each value 2^r times, restricted to its 2^n distinct values: the first r
 // layers of the circle transform of log n+r only scale (inverse) or replicate (forward), see launch_interpolate_repeated.
-template <bool INV, int K, bool LOW, bool LINE = false>
-__global__ void __launch_bounds__(256) fft_kernel(FftArgs a) {
+// (256, 4): 64 registers, four CTAs per SM; the forward low pass otherwise takes 80 and runs three (LDE 6-7 % slower, measured)
+template <bool INV, int K, bool LOW, bool LINE = false, int SC = STRIDED_C>
+__global__ void __launch_bounds__(256, 4) fft_kernel(FftArgs a) {
   extern __shared__ uint32_t sm[];
-  constexpr int C = LOW ? K : STRIDED_C;
+  constexpr int C = LOW ? K : SC;
   const uint32_t L0 = LOW ? (uint32_t)K : a.L0;
   const uint32_t tile = blockIdx.x;
   const uint32_t nlow = L0 - C;
@@ -269,7 +270,7 @@ __global__ void __launch_bounds__(256) fft_kernel(FftArgs a) {
   }
   __syncthreads();
 
-  Rounds<INV, K, LOW, LINE, 0, n_rounds(LOW ? K : K - STRIDED_C)>::run(sm, a, T);
+  Rounds<INV, K, LOW, LINE, SC, 0, n_rounds(LOW ? K : K - SC)>::run(sm, a, T);
 
   const uint32_t scale = a.scale;
   for (uint32_t li = threadIdx.x * 4; li < (1u << K); li += blockDim.x * 4) {
@@ -285,19 +286,22 @@ __global__ void __launch_bounds__(256) fft_kernel(FftArgs a) {
 static const uint32_t KMAX = 13;          // 2^13 words (+pad) = 33 KB smem per CTA
 static const uint32_t KSTRIDE_MAX = 9;    // layers per strided pass (tile 2^(9+4))
 
-struct PassDesc { uint32_t K, L0; bool low; };
+struct PassDesc { uint32_t K, L0; bool low; uint32_t sc; };
 
 static int plan_passes(uint32_t n, PassDesc* out) {  // ascending layer order
   int np = 0;
   uint32_t K0 = n < KMAX ? n : KMAX;
-  out[np++] = {K0, K0, true};
+  out[np++] = {K0, K0, true, 0};
   uint32_t rem = n - K0;
-  if (rem) {
+  if (rem == KSTRIDE_MAX + 1) {
+    // ten layers left (log 23): one strided pass of 2^10 rows x 8 words instead of two passes of 16-word rows
+    out[np++] = {rem + 3, K0, false, 3};
+  } else if (rem) {
     uint32_t ns = (rem + KSTRIDE_MAX - 1) / KSTRIDE_MAX;
     uint32_t L = K0;
     for (uint32_t i = 0; i < ns; i++) {
       uint32_t k = rem / ns + (i < rem % ns ? 1 : 0);
-      out[np++] = {k + STRIDED_C, L, false};
+      out[np++] = {k + STRIDED_C, L, false, (uint32_t)STRIDED_C};
       L += k;
     }
   }
@@ -310,10 +314,10 @@ static uint32_t threads_for(uint32_t K) {
   return t;
 }
 
-template <bool INV, int K, bool LOW, bool LINE = false>
+template <bool INV, int K, bool LOW, bool LINE = false, int SC = STRIDED_C>
 static int launch_one(const FftArgs& a, dim3 grid, cudaStream_t st) {
   size_t smem = ((size_t)(1u << K) + ((1u << K) >> 5) + 4) * 4;
-  fft_kernel<INV, K, LOW, LINE><<<grid, threads_for(K), smem, st>>>(a); g_launch_count++;
+  fft_kernel<INV, K, LOW, LINE, SC><<<grid, threads_for(K), smem, st>>>(a); g_launch_count++;
   return (int)cudaGetLastError();
 }
 
@@ -338,6 +342,7 @@ static int run_pass(const PassDesc& d, const uint32_t* const* src, uint32_t* con
     }
     return -1;
   }
+  if (!d.low && d.sc == 3) return d.K == 13 ? launch_one<INV, 13, false, false, 3>(a, grid, st) : -1;
   if (d.low) {
     switch (d.K) {
       case 3: return launch_one<INV, 3, true>(a, grid, st);

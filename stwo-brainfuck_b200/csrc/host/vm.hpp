@@ -48,7 +48,9 @@ struct Machine {
 
   void execute() {
     const size_t n = program.size();
-    trace.reserve((size_t)1 << 18);  // growing from empty costs more than the run itself (reallocation + page faults)
+    // growing from empty costs more than the run itself (reallocation + page faults); 2^20 + 1 rows is the most the AIR can
+    // take at LOG_MAX_ROWS 24 (the processor table holds one row per step), untouched pages cost nothing
+    trace.reserve(((size_t)1 << 20) + 1);
     while (r.ip < n) {
       r.ci = program[r.ip];
       r.ni = (r.ip == n - 1) ? 0 : program[r.ip + 1];

@@ -41,6 +41,21 @@ def test_interpolate_evaluate(be, orc, tw, log):
     assert (same[0].to_cpu() == list(kinds.values())[0]).all()
 
 
+def test_interpolate_evaluate_log23(be, orc):
+    """log 23 = 13 low layers + ONE strided pass of ten layers (8-word rows); log 22 still takes two 16-word passes."""
+    root = 22
+    tw23 = be.precompute_twiddles(root)
+    v22, v23 = rnd(2201, 1 << 22), rnd(2301, 1 << 23)
+    c22, c23 = be.column(v22), be.column(v23)
+    be.interpolate_columns([c22, c23], tw23)
+    r22, r23 = orc.interpolate(v22, root), orc.interpolate(v23, root)
+    assert (c22.to_cpu() == r22).all() and (c23.to_cpu() == r23).all()
+    lde = be.evaluate_polynomials([c22], 1, tw23)[0]
+    assert (lde.to_cpu() == orc.evaluate(r22, 1, root)).all()
+    back = be.evaluate_polynomials([c23], 0, tw23)[0]
+    assert (back.to_cpu() == v23).all()
+
+
 def test_interpolate_mixed_sizes_and_errors(be, orc, tw, pkg):
     logs = [4, 9, 4, 13, 16, 9]
     host = [rnd(i, 1 << lg) for i, lg in enumerate(logs)]
