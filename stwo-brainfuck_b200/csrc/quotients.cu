@@ -124,7 +124,8 @@ __global__ void quot_points_kernel(uint32_t log, uint32_t kb0, uint32_t nkb, Pt*
   }
 }
 
-__global__ void __launch_bounds__(128) quotients_kernel2(const uint32_t* const* __restrict__ cols, const QuotBatch* __restrict__ batches,
+// (128, 8): 64 registers with ~300 B of spills measured 5 % faster than the unconstrained 127-register build
+__global__ void __launch_bounds__(128, 8) quotients_kernel2(const uint32_t* const* __restrict__ cols, const QuotBatch* __restrict__ batches,
                                                          uint32_t nb, const QuotEntry* __restrict__ entries, uint32_t* o0, uint32_t* o1,
                                                          uint32_t* o2, uint32_t* o3, uint32_t k_off, uint32_t nq,
                                                          const Pt* __restrict__ Q, const Pt* __restrict__ Rt, uint32_t kb0) {
