@@ -60,8 +60,10 @@ struct DomainEval {
   typedef Fq EF;
   const AirParams& p;
   uint32_t row, prev_row;
-  int col = 0, k = 0;
-  Fq row_res{q_zero()};
+  int col = 0, k = 0, pending = 0;
+  // sum_k coeff_k * constraint_k in four 64-bit lanes: one IMAD.WIDE per coordinate and base-field constraint, a partial
+  // fold after every second product (2 * 2^62 + the folded rest stays below 2^64), one full reduction at the end
+  unsigned long long acc[4] = {0, 0, 0, 0};
   LogupState<DomainEval> lg;
   __device__ DomainEval(const AirParams& pp, uint32_t r, uint32_t pr) : p(pp), row(r), prev_row(pr) {}
   __device__ F next() { return {__ldg(p.main[col++] + row)}; }
@@ -71,8 +73,21 @@ struct DomainEval {
   __device__ EF ef_zero() { return {q_zero()}; }
   __device__ EF ef_neg_one() { return {q_fromm(P - 1)}; }
   __device__ EF total_sum() { return {p.total_sum}; }
-  __device__ void add(F c) { row_res = row_res + Fq{p.coeff[k++]} * c; }
-  __device__ void add(EF c) { row_res = row_res + Fq{p.coeff[k++]} * c; }
+  __device__ void add(F c) {
+    const QM31 q = p.coeff[k++];
+    acc[0] += (unsigned long long)q.a.a * c.v; acc[1] += (unsigned long long)q.a.b * c.v;
+    acc[2] += (unsigned long long)q.b.a * c.v; acc[3] += (unsigned long long)q.b.b * c.v;
+    if (++pending == 2) {
+      pending = 0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) acc[j] = (acc[j] >> 31) + (acc[j] & P);
+    }
+  }
+  __device__ void add(EF c) {
+    const QM31 t = q_mul(p.coeff[k++], c.v);
+    acc[0] += t.a.a; acc[1] += t.a.b; acc[2] += t.b.a; acc[3] += t.b.b;
+  }
+  __device__ Fq row_result() const { return {q_make(m_red_wide(acc[0]), m_red_wide(acc[1]), m_red_wide(acc[2]), m_red_wide(acc[3]))}; }
   __device__ void relation(int rel, EF num, const F* vals, int n) { lg.push(num, combine_q(p.el.rel[rel], vals, n)); }
   __device__ EF ext_at(int b, uint32_t r) {
     return {q_make(__ldg(p.inter[4 * b] + r), __ldg(p.inter[4 * b + 1] + r), __ldg(p.inter[4 * b + 2] + r), __ldg(p.inter[4 * b + 3] + r))};
@@ -98,7 +113,7 @@ __global__ void __launch_bounds__(256) constraint_kernel(AirParams p) {
   uint32_t prev_row = __brev(pidx) >> (32 - e);
   DomainEval ev(p, row, prev_row);
   eval_component(COMP, ev);
-  Fq res = ev.row_res * Fm{p.denom_inv[grow >> p.log_size]};
+  Fq res = ev.row_result() * Fm{p.denom_inv[grow >> p.log_size]};
   p.acc[0][row] = m_add(p.acc[0][row], res.v.a.a);
   p.acc[1][row] = m_add(p.acc[1][row], res.v.a.b);
   p.acc[2][row] = m_add(p.acc[2][row], res.v.b.a);

@@ -68,9 +68,17 @@ struct CM31 {
 SB_HD CM31 c_add(CM31 x, CM31 y) { return {m_add(x.a, y.a), m_add(x.b, y.b)}; }
 SB_HD CM31 c_sub(CM31 x, CM31 y) { return {m_sub(x.a, y.a), m_sub(x.b, y.b)}; }
 SB_HD CM31 c_neg(CM31 x) { return {m_neg(x.a), m_neg(x.b)}; }
+// Any 64-bit value -> canonical [0,P): two folds by 2^31 == 1 (mod P) and one conditional subtraction.
+SB_HD uint32_t m_red_wide(uint64_t v) {
+  v = (v >> 31) + (v & P);                               // < 2^33 + 2^31
+  uint32_t s = (uint32_t)(v >> 31) + ((uint32_t)v & P);  // < P + 8
+  return s >= P ? s - P : s;
+}
 SB_HD CM31 c_mul(CM31 x, CM31 y) {
-  // (a+bi)(c+di) = (ac - bd) + (ad + bc)i
-  return {m_sub(m_mul(x.a, y.a), m_mul(x.b, y.b)), m_add(m_mul(x.a, y.b), m_mul(x.b, y.a))};
+  // (a+bi)(c+di) = (ac - bd) + (ad + bc)i; each coordinate is ONE 64-bit sum of two products (-bd as b(P-d)), reduced once
+  uint64_t re = (uint64_t)x.a * y.a + (uint64_t)x.b * (P - y.b);
+  uint64_t im = (uint64_t)x.a * y.b + (uint64_t)x.b * y.a;
+  return {m_red_wide(re), m_red_wide(im)};
 }
 SB_HD CM31 c_mulm(CM31 x, uint32_t m) { return {m_mul(x.a, m), m_mul(x.b, m)}; }
 SB_HD CM31 c_inv(CM31 x) {
@@ -91,7 +99,14 @@ SB_HD CM31 c_mulR(CM31 x) {  // * (2 + i)
   return {m_sub(m_add(x.a, x.a), x.b), m_add(m_add(x.b, x.b), x.a)};
 }
 SB_HD QM31 q_mul(QM31 x, QM31 y) {
-  return {c_add(c_mul(x.a, y.a), c_mulR(c_mul(x.b, y.b))), c_add(c_mul(x.a, y.b), c_mul(x.b, y.a))};
+  // x = A + Bu, y = C + Du, u^2 = 2 + i:  (AC + (2+i)BD) + (AD + BC)u.  BD is reduced first; every other coordinate is one
+  // 64-bit sum (at most four products, 4P^2 < 2^64) and one reduction: 16 multiplications and 6 reductions in all.
+  const CM31 bd = c_mul(x.b, y.b);
+  uint64_t re = (uint64_t)x.a.a * y.a.a + (uint64_t)x.a.b * (P - y.a.b) + 2ull * bd.a + (P - bd.b);
+  uint64_t im = (uint64_t)x.a.a * y.a.b + (uint64_t)x.a.b * y.a.a + bd.a + 2ull * bd.b;
+  uint64_t ure = (uint64_t)x.a.a * y.b.a + (uint64_t)x.a.b * (P - y.b.b) + (uint64_t)x.b.a * y.a.a + (uint64_t)x.b.b * (P - y.a.b);
+  uint64_t uim = (uint64_t)x.a.a * y.b.b + (uint64_t)x.a.b * y.b.a + (uint64_t)x.b.a * y.a.b + (uint64_t)x.b.b * y.a.a;
+  return {{m_red_wide(re), m_red_wide(im)}, {m_red_wide(ure), m_red_wide(uim)}};
 }
 SB_HD QM31 q_mulm(QM31 x, uint32_t m) { return {c_mulm(x.a, m), c_mulm(x.b, m)}; }
 SB_HD QM31 q_mulc(QM31 x, CM31 c) { return {c_mul(x.a, c), c_mul(x.b, c)}; }
