@@ -167,10 +167,12 @@ def rooflines(kern, shape, lmr, world, clocks):
     roof = {"bound": "hbm", "kernel": "commit_layer_kernel + commit_top_kernel (every Merkle launch of one proof, this rank's share)",
             "achieved": mb / world / (m_ms * 1e-3) / 1e9 if m_ms else None, "peak": peak, "unit": "GB/s", "traffic": None,
             "peak_source": peak_src, "algorithmic_bytes": mb / world, "ms_per_proof": m_ms, "share_of_kernel_time": share,
+            "traffic_note": "ncu --set full on seven launches of a fib19 proof: dram read+write = 0.96-1.00 x the algorithmic bytes "
+                            "of the launch (profiles/r1_final_ncu_full_merkle_*.csv); not summed over the ~170 launches, hence null",
             "alu_pipe": {"algorithmic_compressions": mc / world, "executed_compressions": mx / world,
                          "achieved_Gcomp_s": mx / world / (m_ms * 1e-3) / 1e9 if m_ms else None, "bound_Gcomp_s": bound / 1e9,
                          "frac": (mx / world / (m_ms * 1e-3)) / bound if m_ms else None,
-                         "alu_ops_per_compression": ALU_OPS_PER_COMPRESSION,
+                         "alu_ops_per_compression": ALU_OPS_PER_COMPRESSION, "ncu_alu_pipe_active_pct": "77-82 (profiles/r1_final_ncu_full_merkle_*.csv)",
                          "note": "the binding roofline: XOR/rotate run on the 16-lane ALU pipe; executed < algorithmic because "
                                  "the main-trace tree hashes one node per 16 repeated rows in its four deepest layers"}}
     roof["frac"] = roof["achieved"] / peak if roof["achieved"] else None
