@@ -3,7 +3,9 @@
 #pragma once
 #include <cstdint>
 #include <stdexcept>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 #include "../m31.cuh"
 
@@ -78,29 +80,44 @@ struct Machine {
         }
         default: throw std::runtime_error("invalid instruction");
       }
-      if (!early) {
-        r.mv = at(r.mp);
-        r.mvi = inverse(r.mv);
-      }
+      if (!early) r.mv = at(r.mp);  // mvi is filled in afterwards (fill_inverses): it does not influence execution
       r.clk += 1;
       r.ip += 1;
     }
     r.ci = 0;
     r.ni = 0;
     trace.push_back(r);
+    fill_inverses();
+  }
+
+  // mvi = mv^-1 (0 for 0) for every row (machine.rs:224-228 computes it per step).  A jump keeps the previous mv/mvi pair,
+  // which the pass below reproduces because it inverts whatever mv the row recorded.  Montgomery's trick over chunks of the
+  // trace (3 multiplications per row and one inversion per chunk), chunks on a few host threads.
+  void fill_inverses() {
+    const size_t n = trace.size(), chunk = (size_t)1 << 14;
+    auto work = [&](size_t lo, size_t hi) {
+      std::vector<uint32_t> pre(chunk);
+      for (size_t c0 = lo; c0 < hi; c0 += chunk) {
+        const size_t c1 = c0 + chunk < hi ? c0 + chunk : hi;
+        uint32_t run = 1;
+        for (size_t i = c0; i < c1; i++) { pre[i - c0] = run; if (trace[i].mv) run = sb::m_mul(run, trace[i].mv); }
+        uint32_t inv = sb::m_inv(run);
+        for (size_t i = c1; i-- > c0;) {
+          const uint32_t v = trace[i].mv;
+          if (v) { trace[i].mvi = sb::m_mul(inv, pre[i - c0]); inv = sb::m_mul(inv, v); } else trace[i].mvi = 0;
+        }
+      }
+    };
+    const unsigned T = n >= ((size_t)1 << 17) ? 4 : 1;
+    if (T == 1) { work(0, n); return; }
+    std::vector<std::thread> th;
+    const size_t per = ((n + T - 1) / T + chunk - 1) / chunk * chunk;
+    for (unsigned t = 1; t < T; t++) { size_t lo = std::min(n, t * per), hi = std::min(n, lo + per); if (lo < hi) th.emplace_back(work, lo, hi); }
+    work(0, std::min(n, per));
+    for (auto& x : th) x.join();
   }
 
  private:
-  // mv.inverse() is needed at every step (machine.rs:224-228); cell values are small in practice, so remember them
-  std::vector<uint32_t> inv_cache = std::vector<uint32_t>(1 << 16, 0);
-  uint32_t inverse(uint32_t v) {
-    if (v == 0) return 0;
-    if (v < inv_cache.size()) {
-      if (!inv_cache[v]) inv_cache[v] = sb::m_inv(v);
-      return inv_cache[v];
-    }
-    return sb::m_inv(v);
-  }
   uint32_t& at(uint32_t mp) {
     if (mp >= ram.size()) throw std::runtime_error("memory pointer out of range");
     return ram[mp];
