@@ -560,6 +560,27 @@ size_t orc_table_dump(const char* code, const uint8_t* input, size_t input_len, 
   return t.rows();
 }
 
+// One component table built from an explicit register list (n rows of clk, ip, ci, ni, mp, mv, mvi, in clk order) and program
+// words: the shape of the reference's table.rs unit tests, which start from hand-written `Registers`.  Returns the number of
+// rows (0 and a message in orc_last_error on failure).
+size_t orc_table_from_registers(const uint32_t* regs, size_t n, const uint32_t* program, size_t n_program, int comp, uint32_t* out,
+                                uint32_t* n_cols) {
+  try {
+    std::vector<Registers> tr(n);
+    for (size_t i = 0; i < n; i++) { const uint32_t* r = regs + 7 * i; tr[i].clk = r[0]; tr[i].ip = r[1]; tr[i].ci = r[2]; tr[i].ni = r[3]; tr[i].mp = r[4]; tr[i].mv = r[5]; tr[i].mvi = r[6]; }
+    std::vector<uint32_t> prog(program, program + n_program);
+    Table t = build_table(comp, tr, prog);
+    *n_cols = (uint32_t)t.cols.size();
+    if (out)
+      for (size_t r = 0; r < t.rows(); r++)
+        for (size_t c = 0; c < t.cols.size(); c++) out[r * t.cols.size() + c] = t.cols[c][r];
+    return t.rows();
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 0;
+  }
+}
+
 // assert_constraints for every component of a program, with shifted-dummy or channel-drawn lookup elements.
 // Returns NULL on success, else a malloc'd message.
 char* orc_assert_constraints(const char* code, const uint8_t* input, size_t input_len, int dummy_elements) {

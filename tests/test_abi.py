@@ -16,6 +16,20 @@ def test_header_symbols_exported(pkg):
     assert declared <= set(pkg.ABI_SYMBOLS) | {"sc_status"}
 
 
+def test_sharded_and_prover_header_symbols_exported(pkg):
+    """include/stwo_cuda_sharded.h and include/stwo_brainfuck.h: every declared entry point is exported too."""
+    lib = pkg.load_library()
+    for hdr_name, prefix, listed in (("stwo_cuda_sharded.h", "sc_", pkg.SHARDED_SYMBOLS), ("stwo_brainfuck.h", "sbf_", pkg.PROVER_SYMBOLS)):
+        hdr = open(os.path.join(ROOT, "include", hdr_name)).read()
+        hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)                       # prose in comments may mention other calls
+        declared = set(re.findall(r"\b(%s[a-z0-9_]+)\s*\(" % prefix, hdr))
+        assert declared, hdr_name
+        for sym in sorted(declared):
+            assert hasattr(lib, sym), f"{sym} declared in {hdr_name} but not exported"
+        missing = declared - set(listed) - set(pkg.ABI_SYMBOLS)
+        assert not missing, f"{hdr_name}: {sorted(missing)} not listed in the Python mirror"
+
+
 def test_no_cpu_fallback(pkg):
     import torch
     if torch.cuda.is_available():
