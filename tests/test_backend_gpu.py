@@ -255,3 +255,31 @@ def test_column_api(be):
     assert len(c) == 64 and c.at(5) == 0
     c.set(5, 77)
     assert c.at(5) == 77 and c.clone().at(5) == 77
+
+
+def test_error_paths_return_status_not_crash(be, tw, pkg):
+    """Precondition violations come back as BackendError (Stwo asserts / panics there); the context stays usable."""
+    import ctypes
+    a, b = be.column(rnd(1, 1 << 8)), be.column(rnd(2, 1 << 9))
+    with pytest.raises(pkg.BackendError):
+        be.commit_on_layer(8, None, [a, b])                                   # column length != 2^log_size
+    with pytest.raises(pkg.BackendError):
+        be.commit_on_layer(8, a, [a])                                         # previous layer of the wrong size
+    with pytest.raises(pkg.BackendError):
+        be.evaluate_polynomials([be.zeros(1 << (ROOT_LOG + 1))], 1, tw)       # domain exceeds the twiddle tree
+    with pytest.raises(pkg.BackendError):
+        be.fold_line([a, a, a, b], 8, rnd(3, 4), tw)                          # ragged coordinate columns
+    with pytest.raises(pkg.BackendError):
+        be.accumulate_quotients(8, [a], rnd(4, 4), rnd(5, 8), [1], [3], rnd(6, 4))   # column index out of range
+    with pytest.raises(pkg.BackendError):
+        be.accumulate([a, a, a, a], [b, b, b, b])                             # length mismatch
+    with pytest.raises(pkg.BackendError):
+        be.merkle_commit_repeated([a], 9)                                     # log_repeat out of range
+    with pytest.raises(pkg.BackendError):
+        be.eval_at_point_repeated([be.zeros(1 << 20)], [12], rnd(7, 8))       # logical size beyond 2^28
+    assert be._lib.sc_col_free(be._ctx, None) == 0                            # freeing NULL is a no-op
+    assert be._lib.sc_interpolate(be._ctx, None, ctypes.c_uint32(0), tw._h) == 0   # empty batch
+    # the context still works
+    c = be.column(rnd(8, 1 << 8))
+    be.interpolate_columns([c], tw)
+    assert len(c.to_cpu()) == 256
