@@ -86,15 +86,28 @@ inline Table finish(ColVecs cols) {
 template <class KeyFn>
 inline Scratch<uint32_t> order_by_key(size_t n, uint32_t max_key, KeyFn key) {
   Scratch<uint32_t> idx(n);
-  if (max_key < (1u << 22)) {
-    std::vector<uint32_t> cnt((size_t)max_key + 2, 0);
-    for (size_t i = 0; i < n; i++) cnt[key(i) + 1]++;
-    for (size_t k = 1; k < cnt.size(); k++) cnt[k] += cnt[k - 1];
-    for (size_t i = 0; i < n; i++) idx[cnt[key(i)]++] = (uint32_t)i;
-  } else {
+  if (max_key >= (1u << 22)) {
     for (size_t i = 0; i < n; i++) idx[i] = (uint32_t)i;
     std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return key(a) < key(b); });
+    return idx;
   }
+  // counting sort; large inputs on TABLE_THREADS threads: per-thread histograms of contiguous chunks, offsets taken in
+  // (key, thread) order so that equal keys keep their input order
+  const size_t K = (size_t)max_key + 1;
+  const unsigned T = (n >= ((size_t)1 << 16) && K * TABLE_THREADS <= n) ? TABLE_THREADS : 1;
+  const size_t per = (n + T - 1) / T;
+  std::vector<uint32_t> cnt(K * T, 0);
+  auto run = [&](auto fn) {
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < T; t++) th.emplace_back([=] { fn(t, std::min(n, t * per), std::min(n, (t + 1) * per)); });
+    fn(0u, (size_t)0, std::min(n, per));
+    for (auto& x : th) x.join();
+  };
+  run([&](unsigned t, size_t lo, size_t hi) { uint32_t* c = cnt.data() + (size_t)t * K; for (size_t i = lo; i < hi; i++) c[key(i)]++; });
+  uint32_t acc = 0;
+  for (size_t k = 0; k < K; k++)
+    for (unsigned t = 0; t < T; t++) { uint32_t c = cnt[(size_t)t * K + k]; cnt[(size_t)t * K + k] = acc; acc += c; }
+  run([&](unsigned t, size_t lo, size_t hi) { uint32_t* c = cnt.data() + (size_t)t * K; for (size_t i = lo; i < hi; i++) idx[c[key(i)]++] = (uint32_t)i; });
   return idx;
 }
 
