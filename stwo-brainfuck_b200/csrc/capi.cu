@@ -337,11 +337,16 @@ int32_t sc_interpolate(sc_ctx* ctx, sc_col* const* cols, uint32_t n, const sc_tw
     if (lg > tw->root_log + 1) return fail(SC_EINVAL, "interpolate: twiddle tree too small for this domain");
     by_log[lg].push_back(cols[i]->d);
   }
+  std::vector<uint32_t*> all;
+  for (auto& kv : by_log) all.insert(all.end(), kv.second.begin(), kv.second.end());
+  if (all.empty()) return SC_OK;
+  void* dp;
+  int32_t r = stage(ctx, all.data(), all.size() * sizeof(void*), &dp);   // one pointer table for every size class
+  if (r) return r;
+  size_t off = 0;
   for (auto& kv : by_log) {
-    void* dp;
-    int32_t r = stage(ctx, kv.second.data(), kv.second.size() * sizeof(void*), &dp);
-    if (r) return r;
-    { ProfScope ps_(ctx, "fft_interpolate"); CKL(launch_interpolate((uint32_t* const*)dp, (uint32_t)kv.second.size(), kv.first, tw->itw + ((size_t)2 << tw->root_log), ctx->st)); }
+    { ProfScope ps_(ctx, "fft_interpolate"); CKL(launch_interpolate((uint32_t* const*)dp + off, (uint32_t)kv.second.size(), kv.first, tw->itw + ((size_t)2 << tw->root_log), ctx->st)); }
+    off += kv.second.size();
   }
   return SC_OK;
 }
@@ -377,14 +382,21 @@ int32_t sc_evaluate(sc_ctx* ctx, sc_col* const* coeffs, uint32_t n, uint32_t log
     by_log[lg].dst.push_back(out[i]->d);
   }
   if (log_blowup > 1) log_blowup = 1;
-  for (auto& kv : by_log) {
-    void *ds, *dd;
-    int32_t r = stage(ctx, kv.second.src.data(), kv.second.src.size() * sizeof(void*), &ds);
-    if (r) return r;
-    r = stage(ctx, kv.second.dst.data(), kv.second.dst.size() * sizeof(void*), &dd);
-    if (r) return r;
-    { ProfScope ps_(ctx, "fft_evaluate"); CKL(launch_evaluate((const uint32_t* const*)ds, (uint32_t* const*)dd, (uint32_t)kv.second.src.size(), kv.first,
-                        kv.first + log_blowup, tw->tw + ((size_t)2 << tw->root_log), ctx->st)); }
+  {
+    std::vector<const void*> all;   // every group's sources, then every group's destinations: one staged table
+    for (auto& kv : by_log) all.insert(all.end(), kv.second.src.begin(), kv.second.src.end());
+    const size_t ndst0 = all.size();
+    for (auto& kv : by_log) all.insert(all.end(), kv.second.dst.begin(), kv.second.dst.end());
+    void* dall = nullptr;
+    if (!all.empty()) { int32_t r = stage(ctx, all.data(), all.size() * sizeof(void*), &dall); if (r) return r; }
+    size_t off = 0;
+    for (auto& kv : by_log) {
+      const uint32_t* const* ds = (const uint32_t* const*)dall + off;
+      uint32_t* const* dd = (uint32_t* const*)dall + ndst0 + off;
+      { ProfScope ps_(ctx, "fft_evaluate"); CKL(launch_evaluate(ds, dd, (uint32_t)kv.second.src.size(), kv.first,
+                          kv.first + log_blowup, tw->tw + ((size_t)2 << tw->root_log), ctx->st)); }
+      off += kv.second.src.size();
+    }
   }
   for (uint32_t* t : temps) CK(cudaFreeAsync(t, ctx->st));
   return SC_OK;
@@ -576,30 +588,38 @@ static int32_t merkle_commit_impl(sc_ctx* ctx, sc_col* const* cols, uint32_t n, 
   // layers above `top` one launch each; the remaining small ones (no repetition left there) in a single launch
   int top = (int)std::min<uint32_t>(max_log, MERKLE_TOP_LOG);
   if (log_repeat && (uint32_t)top + log_repeat > max_log) top = (int)max_log - (int)log_repeat;  // may become < 0: nothing fused
+  // one pointer table for the whole tree (columns by layer, deepest first, input order within a layer), staged once: a
+  // per-layer table would put a small host->device copy in front of every launch
+  std::vector<const uint32_t*> cp;
+  std::vector<uint32_t> first(max_log + 2, 0);   // columns of layer lg are cp[first[lg+1] .. first[lg]) in this numbering
+  for (int lg = (int)max_log; lg >= 0; lg--) {
+    first[lg + 1] = (uint32_t)cp.size();
+    for (uint32_t i = 0; i < n; i++) if (ilog2(cols[i]->len) == (uint32_t)lg) cp.push_back(cols[i]->d);  // stable
+  }
+  first[0] = (uint32_t)cp.size();
+  const uint32_t* const* dp = nullptr;
+  if (!cp.empty()) { void* d; int32_t r = stage(ctx, cp.data(), cp.size() * sizeof(void*), &d); if (r) return r; dp = (const uint32_t* const*)d; }
   for (int lg = (int)max_log; lg > top; lg--) {
-    std::vector<sc_col*> lc;
-    for (uint32_t i = 0; i < n; i++) if (ilog2(cols[i]->len) == (uint32_t)lg) lc.push_back(cols[i]);  // stable
     uint32_t depth = max_log - (uint32_t)lg, rep = log_repeat > depth ? log_repeat - depth : 0;
-    int32_t r = commit_layer_impl(ctx, lg, lg == (int)max_log ? nullptr : layers_out[lg + 1], lc.data(), (uint32_t)lc.size(), rep, &layers_out[lg]);
+    int32_t r = new_col(ctx, 8ull << lg, &layers_out[lg]);
     if (r) return r;
+    ProfScope ps_(ctx, "merkle_commit_layer");
+    CKL(launch_commit_layer(lg, lg == (int)max_log ? nullptr : layers_out[lg + 1]->d, dp + first[lg + 1], first[lg] - first[lg + 1],
+                            layers_out[lg]->d, ctx->st, rep));
   }
   if (top >= 0) {
-    std::vector<const uint32_t*> cp;
     uint32_t col_off[MERKLE_TOP_LOG + 2];
     uint32_t* outp[MERKLE_TOP_LOG + 1];
     for (int k = 0; k <= top; k++) {
       int lg = top - k;
-      col_off[k] = (uint32_t)cp.size();
-      for (uint32_t i = 0; i < n; i++) if (ilog2(cols[i]->len) == (uint32_t)lg) cp.push_back(cols[i]->d);  // stable
+      col_off[k] = first[lg + 1] - first[top + 1];
       int32_t r = new_col(ctx, 8ull << lg, &layers_out[lg]);
       if (r) return r;
       outp[k] = layers_out[lg]->d;
     }
-    col_off[top + 1] = (uint32_t)cp.size();
-    void* dp = nullptr;
-    if (!cp.empty()) { int32_t r = stage(ctx, cp.data(), cp.size() * sizeof(void*), &dp); if (r) return r; }
+    col_off[top + 1] = first[0] - first[top + 1];
     ProfScope ps_(ctx, "merkle_commit_layer");
-    CKL(launch_commit_top((uint32_t)top, top == (int)max_log ? nullptr : layers_out[top + 1]->d, (const uint32_t* const*)dp, col_off, outp, ctx->st));
+    CKL(launch_commit_top((uint32_t)top, top == (int)max_log ? nullptr : layers_out[top + 1]->d, dp + first[top + 1], col_off, outp, ctx->st));
   }
   if (max_log_out) *max_log_out = max_log;
   if (root_out) return sc_col_read(ctx, layers_out[0], 0, 8, root_out);
