@@ -42,6 +42,11 @@ uint64_t sc_ctx_launch_count(const sc_ctx* ctx);
 /* Per-kernel-class device timing: when enabled every entry point brackets its launches with CUDA events on the launch
  * stream; the report is "tag:milliseconds:count;..." (sum per tag since the last report) and clears the records. */
 int32_t sc_ctx_profile(sc_ctx* ctx, int32_t enable);
+/* sc_ctx_mark: a token; sc_ctx_release_since frees every column created on the context after the token that is still alive
+ * (a Rust caller unwinding from a panic inside `prove` has no other way to find them). */
+uint64_t sc_ctx_mark(sc_ctx* ctx);
+int32_t sc_ctx_release_since(sc_ctx* ctx, uint64_t mark);
+uint64_t sc_ctx_live_columns(sc_ctx* ctx);   /* number of column handles currently alive on the context */
 size_t sc_ctx_profile_report(sc_ctx* ctx, char* buf, size_t cap);
 size_t sc_ctx_profile_timeline(sc_ctx* ctx, char* buf, size_t cap);  /* "tag:start_ms:dur_ms;" per scope, not cleared */
 

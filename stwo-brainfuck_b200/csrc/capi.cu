@@ -162,6 +162,7 @@ int32_t sc_col_from_host_async(sc_ctx* ctx, const uint32_t* host, uint64_t len, 
   ctx->slab_live++;
   sc_col* c = new sc_col{d, len};
   c->owned = false; c->slab = true;
+  track(ctx, c);
   *out = c;
   // In pieces: the small host->device copies of the compute stream (pointer tables, stage()) share the one H2D copy
   // engine with these uploads and would otherwise sit behind a whole 16 MB column, idling the kernels that wait for them.
@@ -227,6 +228,7 @@ int32_t sc_col_free(sc_ctx* ctx, sc_col* col) {
   if (!col) return SC_OK;
   if (!ctx) return fail(SC_EINVAL, "null context");
   cudaSetDevice(ctx->device);
+  ctx->live.erase(col->id);
   if (col->owned) cudaFreeAsync(col->d, ctx->st);
   if (col->slab && --ctx->slab_live == 0) {
     // rewind; whatever is queued on `st` up to here may still read the slab, later uploads must not overtake it
@@ -236,12 +238,24 @@ int32_t sc_col_free(sc_ctx* ctx, sc_col* col) {
   delete col;
   return SC_OK;
 }
+// sc_ctx_mark returns a token; sc_ctx_release_since frees every column created on this context after that token that is
+// still alive (views included).  For callers that unwind from a failure and no longer know what they allocated.
+uint64_t sc_ctx_mark(sc_ctx* ctx) { return ctx ? ctx->next_id : 0; }
+uint64_t sc_ctx_live_columns(sc_ctx* ctx) { return ctx ? ctx->live.size() : 0; }
+int32_t sc_ctx_release_since(sc_ctx* ctx, uint64_t mark) {
+  if (!ctx) return fail(SC_EINVAL, "null context");
+  std::vector<sc_col*> victims;
+  for (auto it = ctx->live.lower_bound(mark); it != ctx->live.end(); ++it) victims.push_back(it->second);
+  for (sc_col* c : victims) sc_col_free(ctx, c);
+  return SC_OK;
+}
 // Non-owning column over caller-owned device memory (e.g. a torch tensor or an NCCL receive buffer); 16-byte aligned.
 int32_t sc_col_wrap(sc_ctx* ctx, void* device_ptr, uint64_t len, sc_col** out) {
   ENTER();
   if (!device_ptr || !out || ((uintptr_t)device_ptr & 15)) return fail(SC_EINVAL, "col_wrap: null or misaligned pointer");
   sc_col* c = new sc_col{(uint32_t*)device_ptr, len};
   c->owned = false;
+  track(ctx, c);
   *out = c;
   return SC_OK;
 }

@@ -18,6 +18,7 @@ struct sc_col {
   uint64_t len;
   bool owned = true;  // false: a view over caller-owned device memory (sc_col_wrap)
   bool slab = false;  // lives in the context's upload slab (sc_col_from_host_async)
+  uint64_t id = 0;    // creation order within the context (sc_ctx_mark / sc_ctx_release_since)
 };
 struct sc_twiddles {
   uint32_t root_log;
@@ -43,6 +44,10 @@ struct sc_ctx {
   std::vector<ArenaBlock> arena;
   std::mutex arena_mu;
   std::map<uint32_t, sc_twiddles*> tw_cache;  // sc_twiddles_cached
+  // every live column handle by creation id: lets a caller that failed half-way (an exception inside the prover) release
+  // what it created since a mark instead of leaking gigabytes of device memory
+  std::map<uint64_t, sc_col*> live;
+  uint64_t next_id = 1;
   // sc_col_from_host_async copies on a second stream so that uploads overlap kernels already queued on `st`; the next
   // call of any other entry point makes `st` wait for them (join_uploads)
   cudaStream_t copy_st = nullptr;
@@ -117,11 +122,13 @@ static inline int32_t stage(sc_ctx* ctx, const void* host, size_t bytes, void** 
   return SC_OK;
 }
 
+static inline void track(sc_ctx* ctx, sc_col* c) { c->id = ctx->next_id++; ctx->live[c->id] = c; }
 static inline int32_t new_col(sc_ctx* ctx, uint64_t len, sc_col** out) {
   uint32_t* d = nullptr;
   cudaError_t e = cudaMallocAsync((void**)&d, std::max<uint64_t>(len, 4) * 4, ctx->st);
   if (e != cudaSuccess) { cudaGetLastError(); return fail(SC_ENOMEM, std::string("cudaMallocAsync: ") + cudaGetErrorString(e)); }
   *out = new sc_col{d, len};
+  track(ctx, *out);
   return SC_OK;
 }
 

@@ -238,6 +238,7 @@ int32_t sbf_prove_sharded(sc_ctx* ctx, sc_comm* comm, const char* code, const ui
 int32_t sbf_prove(sc_ctx* ctx, const char* code, const uint8_t* input, size_t input_len, uint32_t log_max_rows, uint32_t flags,
                   sbf_proof** out) {
   if (flags & 4u) return sbf_prove_sharded(ctx, nullptr, code, input, input_len, log_max_rows, flags, out);  // SBF_SHARDED_DRIVER
+  const uint64_t mark = sc_ctx_mark(ctx);
   try {
     if (!ctx || !code || !out) throw std::runtime_error("null argument");
     std::vector<uint32_t> program = compile(code);
@@ -270,6 +271,7 @@ int32_t sbf_prove(sc_ctx* ctx, const char* code, const uint8_t* input, size_t in
     return SC_OK;
   } catch (const std::exception& e) {
     g_sbf_err = e.what();
+    if (ctx) { sc_ctx_sync(ctx); sc_ctx_release_since(ctx, mark); }  // nothing the failed proof allocated stays on the device
     return SC_EPROOF;
   }
 }
@@ -278,6 +280,7 @@ int32_t sbf_prove(sc_ctx* ctx, const char* code, const uint8_t* input, size_t in
 // proof).  comm == NULL runs the sharded driver on a single GPU (world 1): same proof as sbf_prove.
 int32_t sbf_prove_sharded(sc_ctx* ctx, sc_comm* comm, const char* code, const uint8_t* input, size_t input_len, uint32_t log_max_rows,
                           uint32_t flags, sbf_proof** out) {
+  const uint64_t mark = sc_ctx_mark(ctx);
   try {
     if (!ctx || !code || !out) throw std::runtime_error("null argument");
     std::vector<uint32_t> program = compile(code);
@@ -309,6 +312,7 @@ int32_t sbf_prove_sharded(sc_ctx* ctx, sc_comm* comm, const char* code, const ui
     return SC_OK;
   } catch (const std::exception& e) {
     g_sbf_err = e.what();
+    if (ctx) { sc_ctx_sync(ctx); sc_ctx_release_since(ctx, mark); }  // nothing the failed proof allocated stays on the device
     return SC_EPROOF;
   }
 }

@@ -121,6 +121,7 @@ int32_t sc_col_view(sc_ctx* ctx, sc_col* col, uint64_t off, uint64_t n, sc_col**
   if (!col || !out || off + n > col->len) return fail(SC_EINVAL, "col_view: out of range");
   sc_col* c = new sc_col{col->d + off, n};
   c->owned = false;
+  track(ctx, c);
   *out = c;
   return SC_OK;
 }

@@ -63,6 +63,19 @@ def test_verifier_rejects_tampered_proof(pkg, be, what):
 
 
 def test_component_too_large_is_an_error(pkg, be):
+    import gc
+    gc.collect()
     code = open(os.path.join(PROGRAMS, "hello_kakarot.bf"), "rb").read()
+    before = be.live_columns()
     with pytest.raises(pkg.ProvingError):
         pkg.prove_brainfuck(be, code, b"", 12)   # Memory needs log 17 > LOG_MAX_ROWS 12 (the reference panics likewise)
+    assert be.live_columns() == before            # the failed proof released the preprocessed tree it had already built
+    pkg.prove_brainfuck(be, code, b"", 17).verify()   # and the context is still usable
+    gc.collect()
+    assert be.live_columns() == before            # a finished proof leaves nothing behind either
+
+
+def test_vm_errors_surface_as_proving_errors(pkg, be):
+    for code, stdin in ((b"+]", b""), (b",", b""), (b"<+", b""), (b"", b"")):
+        with pytest.raises(pkg.ProvingError):
+            pkg.prove_brainfuck(be, code, stdin, 10)
