@@ -68,6 +68,23 @@ inline void parallel_ranges(size_t n, unsigned threads, Fn fn) {
 }
 constexpr unsigned TABLE_THREADS = 4;  // extra host threads inside the three big builders
 
+// max of key(i) over [0, n) and a check that ok(i) holds everywhere, on TABLE_THREADS threads
+template <class KeyFn, class OkFn>
+inline uint32_t scan_max(size_t n, KeyFn key, OkFn ok, const char* what) {
+  uint32_t mx[TABLE_THREADS] = {0, 0, 0, 0};
+  bool bad[TABLE_THREADS] = {false, false, false, false};
+  const size_t per = (n + TABLE_THREADS - 1) / TABLE_THREADS;
+  parallel_ranges(n, TABLE_THREADS, [&](size_t lo, size_t hi) {
+    const size_t t = per ? std::min<size_t>(lo / per, TABLE_THREADS - 1) : 0;
+    uint32_t m = 0;
+    bool b = false;
+    for (size_t i = lo; i < hi; i++) { m = std::max(m, key(i)); b |= !ok(i); }
+    mx[t] = std::max(mx[t], m); bad[t] |= b;
+  });
+  for (unsigned t = 0; t < TABLE_THREADS; t++) if (bad[t]) throw std::runtime_error(what);
+  return *std::max_element(mx, mx + TABLE_THREADS);
+}
+
 inline size_t next_pow2(size_t n) { size_t p = 1; while (p < n) p <<= 1; return p; }
 inline uint32_t ilog2_exact(size_t n) { uint32_t l = 0; while (((size_t)1 << l) < n) l++; return l; }
 
@@ -114,11 +131,8 @@ inline Scratch<uint32_t> order_by_key(size_t n, uint32_t max_key, KeyFn key) {
 inline Table memory_table(const std::vector<Registers>& regs) {
   if (regs.empty()) throw std::runtime_error("empty trace");
   const size_t m = regs.size();
-  uint32_t max_mp = 0;
-  for (size_t i = 0; i < m; i++) {
-    if (i && regs[i].clk <= regs[i - 1].clk) throw std::runtime_error("trace is not in clk order");
-    max_mp = std::max(max_mp, regs[i].mp);
-  }
+  const uint32_t max_mp = scan_max(m, [&](size_t i) { return regs[i].mp; }, [&](size_t i) { return !i || regs[i].clk > regs[i - 1].clk; },
+                                   "trace is not in clk order");
   // the (mp, clk)-sorted entries as three dense arrays: the passes below then read memory in order
   struct S { uint32_t clk, mp, mv; };
   Scratch<S> e(m);
@@ -169,11 +183,9 @@ inline Table instruction_table(const std::vector<Registers>& regs, const std::ve
   // the reference's stable sort on (ip, clk)
   const size_t np = code.size(), total = np + regs.size();
   if (total == 0) throw std::runtime_error("empty trace");
-  for (size_t i = 1; i < regs.size(); i++)
-    if (regs[i].clk <= regs[i - 1].clk) throw std::runtime_error("trace is not in clk order");
   auto ip_of = [&](size_t i) { return i < np ? (uint32_t)i : regs[i - np].ip; };
-  uint32_t max_ip = 0;
-  for (size_t i = 0; i < total; i++) max_ip = std::max(max_ip, ip_of(i));
+  const uint32_t max_ip = scan_max(total, ip_of, [&](size_t i) { return i <= np || regs[i - np].clk > regs[i - np - 1].clk; },
+                                   "trace is not in clk order");
   Scratch<uint32_t> ord = order_by_key(total, max_ip, ip_of);
   size_t n = next_pow2(total);
   ColVecs c = make_cols(8, n);
@@ -233,16 +245,36 @@ inline Table processor_table(const std::vector<Registers>& regs) {
 // processor/instructions/table.rs:293-328 and jump/table.rs:264-297: for every step with ci == op the pair (step, next step),
 // padded in ENTRIES with dummy(last_clk + i, last_ip), i from 0, then chunked in twos; an empty table is one dummy row.
 struct PairEntry { uint32_t clk, ip, ci, ni, mp, mv, mvi, d; };
+// Step indices by opcode, found in ONE pass over the trace and shared by the eight instruction / jump tables (each of them
+// scanning the 28-byte registers twice costs more than building the table once the trace is large).
+inline int op_slot(uint32_t ci) {
+  switch (ci) { case ']': return 0; case '[': return 1; case ',': return 2; case '<': return 3; case '-': return 4; case '.': return 5;
+                case '+': return 6; case '>': return 7; default: return -1; }
+}
+struct TraceIndex {
+  Scratch<uint32_t> steps[8];
+  explicit TraceIndex(const std::vector<Registers>& regs) {
+    size_t cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const size_t m = regs.empty() ? 0 : regs.size() - 1;   // a step needs a successor to be paired with
+    for (size_t i = 0; i < m; i++) { int sl = op_slot(regs[i].ci); if (sl >= 0) cnt[sl]++; }
+    for (int sl = 0; sl < 8; sl++) steps[sl].reserve(cnt[sl]);
+    for (size_t i = 0; i < m; i++) { int sl = op_slot(regs[i].ci); if (sl >= 0) steps[sl].push_back((uint32_t)i); }
+  }
+};
 struct PairRows {
   const std::vector<Registers>& regs;
-  Scratch<uint32_t> steps;           // i with regs[i].ci == op (and a following step)
+  Scratch<uint32_t> own;             // i with regs[i].ci == op (and a following step), when no shared index was given
+  const Scratch<uint32_t>& steps;
   uint32_t last_clk = 0, last_ip = 0;  // of the last real entry
   size_t n = 1;                       // table rows
-  PairRows(const std::vector<Registers>& r, uint32_t op) : regs(r) {
-    size_t cnt = 0;
-    for (size_t i = 0; i + 1 < regs.size(); i++) cnt += regs[i].ci == op;
-    steps.reserve(cnt);
-    for (size_t i = 0; i + 1 < regs.size(); i++) if (regs[i].ci == op) steps.push_back((uint32_t)i);
+  PairRows(const std::vector<Registers>& r, uint32_t op, const TraceIndex* ix) : regs(r), steps(ix ? ix->steps[op_slot(op)] : own) {
+    if (!ix) {
+      size_t cnt = 0;
+      for (size_t i = 0; i + 1 < regs.size(); i++) cnt += regs[i].ci == op;
+      own.reserve(cnt);
+      for (size_t i = 0; i + 1 < regs.size(); i++) if (regs[i].ci == op) own.push_back((uint32_t)i);
+    }
+    const size_t cnt = steps.size();
     if (cnt) { const Registers& l = regs[steps.back() + 1]; last_clk = l.clk; last_ip = l.ip; n = next_pow2(2 * cnt) / 2; }
   }
   PairEntry dummy(size_t j) const { return {(uint32_t)(((uint64_t)last_clk + j) % P), last_ip, 0, 0, 0, 0, 0, 1}; }
@@ -251,8 +283,8 @@ struct PairRows {
   PairEntry second(size_t row) const { return row < steps.size() ? real(regs[steps[row] + 1]) : dummy(2 * (row - steps.size()) + 1); }
 };
 // columns: clk ip ci ni mp mv mvi d next_ip next_mp next_mv  (ProcessorInstructionColumn)
-inline Table instruction_op_table(const std::vector<Registers>& regs, uint32_t op) {
-  PairRows t(regs, op);
+inline Table instruction_op_table(const std::vector<Registers>& regs, uint32_t op, const TraceIndex* ix = nullptr) {
+  PairRows t(regs, op, ix);
   ColVecs c = make_cols(11, t.n);
   for (size_t i = 0; i < t.n; i++) {
     const PairEntry a = t.first(i), b = t.second(i);
@@ -262,8 +294,8 @@ inline Table instruction_op_table(const std::vector<Registers>& regs, uint32_t o
   return finish(std::move(c));
 }
 // columns: clk ip ci ni mp mv mvi next_clk next_ip next_mp next_mv d is_mv_zero  (JumpColumn)
-inline Table jump_table(const std::vector<Registers>& regs, uint32_t op) {
-  PairRows t(regs, op);
+inline Table jump_table(const std::vector<Registers>& regs, uint32_t op, const TraceIndex* ix = nullptr) {
+  PairRows t(regs, op, ix);
   ColVecs c = make_cols(13, t.n);
   for (size_t i = 0; i < t.n; i++) {
     const PairEntry a = t.first(i), b = t.second(i);
@@ -283,16 +315,16 @@ inline Table eoe_table(const std::vector<Registers>& regs) {
   return finish(std::move(c));
 }
 
-inline Table build_table(int k, const std::vector<Registers>& regs, const std::vector<uint32_t>& code) {
+inline Table build_table(int k, const std::vector<Registers>& regs, const std::vector<uint32_t>& code, const TraceIndex* ix = nullptr) {
   switch (k) {
     case MEMORY: return memory_table(regs);
     case INSTRUCTION: return instruction_table(regs, code);
     case PROGRAM: return program_table(code);
     case PROCESSOR: return processor_table(regs);
-    case JNZ: return jump_table(regs, ']');
-    case JZ: return jump_table(regs, '[');
+    case JNZ: return jump_table(regs, ']', ix);
+    case JZ: return jump_table(regs, '[', ix);
     case EOE: return eoe_table(regs);
-    default: return instruction_op_table(regs, opcode_of(k));
+    default: return instruction_op_table(regs, opcode_of(k), ix);
   }
 }
 
@@ -301,10 +333,16 @@ inline std::vector<Table> build_tables(const std::vector<Registers>& regs, const
   std::vector<Table> t(N_COMPONENTS);
   std::vector<std::string> err(N_COMPONENTS);
   std::vector<std::thread> th;
-  for (int k = 0; k < N_COMPONENTS; k++)
-    th.emplace_back([&, k] {
-      try { t[k] = build_table(k, regs, code); } catch (const std::exception& e) { err[k] = e.what(); }
+  auto spawn = [&](int k, const TraceIndex* ix) {
+    th.emplace_back([&, k, ix] {
+      try { t[k] = build_table(k, regs, code, ix); } catch (const std::exception& e) { err[k] = e.what(); }
     });
+  };
+  // the four tables that do not need the opcode index start first; this thread indexes the trace meanwhile
+  for (int k : {(int)MEMORY, (int)INSTRUCTION, (int)PROCESSOR, (int)PROGRAM}) spawn(k, nullptr);
+  TraceIndex ix(regs);
+  for (int k = 0; k < N_COMPONENTS; k++)
+    if (k != MEMORY && k != INSTRUCTION && k != PROCESSOR && k != PROGRAM) spawn(k, &ix);
   for (auto& x : th) x.join();
   for (auto& e : err) if (!e.empty()) throw std::runtime_error(e);
   return t;
