@@ -182,7 +182,9 @@ def rooflines(kern, shape, lmr, world, clocks):
                 "achieved": fb / (fft_ms * 1e-3) / 1e9 if fft_ms else None, "peak": peak, "unit": "GB/s", "traffic": None,
                 "algorithmic_bytes": fb, "ms_per_proof": fft_ms,
                 "note": "algorithmic bytes count every column at full length (8N + 12N); main-trace columns are transformed on "
-                        "their 2^-4 distinct values"}
+                        "their 2^-4 distinct values",
+                "binding_limit": "integer issue: ncu smsp__issue_active 59-72 %, ALU pipe 47-61 %, DRAM 11-39 % on the passes of a "
+                                 "fib19 proof (profiles/r1_final_ncu_full_fft_a.csv); >= 10 integer instructions per butterfly"}
     roof_fft["frac"] = roof_fft["achieved"] / peak if roof_fft["achieved"] else None
     return roof, roof_fft
 
