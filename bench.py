@@ -316,6 +316,14 @@ def bench_prove_sharded(args, torch, dist, rank, world, local, pkg, stream, be):
                     "includes": "VM run and host table building on every rank, uploads, proof, proof readback"},
             "gpu_launches": int(launches // args.steps), "stages_ms": stages, "kernel_ms_per_proof": kern, "roofline": roof,
             "roofline_fft": roof_fft, "clocks": clocks, "verified": True}
+    if args.timeline:  # one more proof with the scopes kept in launch order: where this rank's device sits idle
+        dist.barrier()
+        be.profile(True); be.profile_report()
+        pr = pkg.prove_brainfuck_sharded(be, comm, code, b"", lmr)
+        tl = be.profile_timeline()
+        be.profile_report(); be.profile(False)
+        json.dump({"rank": rank, "world": world, "timeline": tl, "stages_ms": pr.report()["stages_ms"]},
+                  open(f"{args.timeline}.rank{rank}.json", "w"))
     if rank == 0:
         print(json.dumps(line))
     comm.close()
@@ -532,6 +540,7 @@ def main():
     ap.add_argument("--workload", default="prove", choices=["prove", "commit"])
     ap.add_argument("--scale-down", type=int, default=0, help="commit workload only: shrink every column by 2^k rows")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--timeline", default=None, help="N > 1 prove workload: also dump every rank's profiling-scope timeline to <path>.rank<r>.json")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -42,6 +42,11 @@ uint64_t sc_ctx_launch_count(const sc_ctx* ctx);
 /* Per-kernel-class device timing: when enabled every entry point brackets its launches with CUDA events on the launch
  * stream; the report is "tag:milliseconds:count;..." (sum per tag since the last report) and clears the records. */
 int32_t sc_ctx_profile(sc_ctx* ctx, int32_t enable);
+/* Device-side stopwatch on the compute stream: sc_event_elapsed waits for `b` and returns the milliseconds between the marks. */
+typedef struct sc_event sc_event;
+int32_t sc_event_record(sc_ctx* ctx, sc_event** out);
+int32_t sc_event_elapsed(sc_ctx* ctx, const sc_event* a, const sc_event* b, float* ms);
+int32_t sc_event_free(sc_ctx* ctx, sc_event* e);
 /* sc_ctx_mark: a token; sc_ctx_release_since frees every column created on the context after the token that is still alive
  * (a Rust caller unwinding from a panic inside `prove` has no other way to find them). */
 uint64_t sc_ctx_mark(sc_ctx* ctx);

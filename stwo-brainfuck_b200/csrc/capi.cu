@@ -203,8 +203,15 @@ int32_t sc_col_to_host(sc_ctx* ctx, const sc_col* col, uint32_t* host) {
   return SC_OK;
 }
 int32_t sc_col_read(sc_ctx* ctx, const sc_col* col, uint64_t offset, uint64_t n, uint32_t* host) {
-  ENTER();
+  ENTER_NOJOIN();
   if (!col || !host || offset + n > col->len) return fail(SC_EINVAL, "read out of range");
+  // a read of an ordinary column does not wait for uploads still in flight on the copy stream (a Merkle root can be read
+  // back while the next phase's inputs are being copied); only a column that lives in the upload slab needs them
+  if (col->slab && ctx->uploads_pending) {
+    CK(cudaEventRecord(ctx->copy_ev, ctx->copy_st));
+    CK(cudaStreamWaitEvent(ctx->st, ctx->copy_ev, 0));
+    ctx->uploads_pending = false;
+  }
   CK(cudaMemcpyAsync(host, col->d + offset, n * 4, cudaMemcpyDeviceToHost, ctx->st));
   CK(cudaStreamSynchronize(ctx->st));
   return SC_OK;
@@ -236,6 +243,33 @@ int32_t sc_col_free(sc_ctx* ctx, sc_col* col) {
     if (ctx->slab_ev) { cudaEventRecord(ctx->slab_ev, ctx->st); ctx->slab_fence = true; }
   }
   delete col;
+  return SC_OK;
+}
+// GPU-side stopwatch for callers that overlap host work with queued kernels: sc_event_record marks a point on the compute
+// stream; sc_event_elapsed(a, b) waits for b and returns the device time between the two marks (the idle gap when b was
+// recorded after the host finished something the device had to wait for).
+struct sc_event { cudaEvent_t ev; };
+int32_t sc_event_record(sc_ctx* ctx, sc_event** out) {
+  ENTER_NOJOIN();
+  if (!out) return fail(SC_EINVAL, "null out");
+  sc_event* e = new sc_event;
+  CK(cudaEventCreate(&e->ev));
+  CK(cudaEventRecord(e->ev, ctx->st));
+  *out = e;
+  return SC_OK;
+}
+int32_t sc_event_elapsed(sc_ctx* ctx, const sc_event* a, const sc_event* b, float* ms) {
+  ENTER_NOJOIN();
+  if (!a || !b || !ms) return fail(SC_EINVAL, "null argument");
+  CK(cudaEventSynchronize(b->ev));
+  CK(cudaEventElapsedTime(ms, a->ev, b->ev));
+  return SC_OK;
+}
+int32_t sc_event_free(sc_ctx* ctx, sc_event* e) {
+  if (!e) return SC_OK;
+  if (ctx) cudaSetDevice(ctx->device);
+  cudaEventDestroy(e->ev);
+  delete e;
   return SC_OK;
 }
 // sc_ctx_mark returns a token; sc_ctx_release_since frees every column created on this context after that token that is

@@ -160,6 +160,13 @@ struct CudaBackendImpl : Backend {
     ck(sc_merkle_commit_layer(ctx, log, h(prev), (sc_col* const*)cols.data(), (uint32_t)cols.size(), &o));
     return o;
   }
+  void* mark() override { sc_event* e; ck(sc_event_record(ctx, &e)); return e; }
+  double gap_ms(void* a, void* b) override {
+    float ms = 0;
+    ck(sc_event_elapsed(ctx, (sc_event*)a, (sc_event*)b, &ms));
+    sc_event_free(ctx, (sc_event*)a); sc_event_free(ctx, (sc_event*)b);
+    return ms;
+  }
   Col commit_layer_repeated(uint32_t log, Col prev, const std::vector<Col>& cols, uint32_t rep) override {
     sc_col* o;
     ck(sc_merkle_commit_layer_repeated(ctx, log, h(prev), (sc_col* const*)cols.data(), (uint32_t)cols.size(), rep, &o));

@@ -83,6 +83,10 @@ struct Backend {
                                 Col is_first_lde, const InteractionElements& el, QM31 total_sum, const std::vector<QM31>& coeffs,
                                 const std::array<Col, 4>& accum) = 0;
 
+  // device-side stopwatch: mark() a point in the queued work; gap_ms(a, b) = device time between two marks (consumes both)
+  virtual void* mark() { return nullptr; }
+  virtual double gap_ms(void* a, void* b) { (void)a; (void)b; return 0; }
+
   // ---- multi-GPU extension (prover_sharded.hpp): one rank of `world`; row-range variants and collectives
   virtual int rank() const { return 0; }
   virtual int world() const { return 1; }

@@ -79,9 +79,14 @@ struct SMerkle {
   std::vector<Col> layers;  // [k]: k > w: this rank's sub-layer (2^(k-w) nodes); k <= w: the whole layer (replicated)
   Hash root;
 };
-// Row-sharded MerkleProver::commit over columns that are either row ranges (sharded) or whole (replicated).
+// Row-sharded MerkleProver::commit over columns that are either row ranges (sharded) or whole (replicated).  The node
+// function is local to a row, so the layers with more than `world` nodes are an ordinary Merkle tree over this rank's row
+// ranges (log sizes L - w): one backend call, which fuses the small layers and stages one pointer table.  The `world`
+// sub-roots are all-gathered and the top w layers hashed by every rank.
 // rep: every column repeats each value 2^rep times (main trace); the deepest `rep` layers then hash one node per group.
-inline SMerkle merkle_sharded(Backend& B, const ShardLayout& sl, const std::vector<RowCol>& cols, uint32_t rep = 0) {
+// before_root_read: called when all device work is queued, just before the blocking read of the root.
+inline SMerkle merkle_sharded(Backend& B, const ShardLayout& sl, const std::vector<RowCol>& cols, uint32_t rep = 0,
+                              const std::function<void()>& before_root_read = nullptr) {
   SMerkle m;
   uint32_t maxL = 0;
   for (auto& c : cols) maxL = std::max(maxL, c.L);
@@ -89,26 +94,23 @@ inline SMerkle merkle_sharded(Backend& B, const ShardLayout& sl, const std::vect
   const uint32_t w = (uint32_t)sl.w;
   Col prev = nullptr;
   int k = (int)maxL;
-  for (; k >= (int)w; k--) {
-    std::vector<Col> lc, tmp;
-    size_t n = (size_t)1 << (k - w);
+  if (maxL >= w) {
+    std::vector<Col> local, tmp;
     for (auto& c : cols) {
-      if (c.L != (uint32_t)k) continue;
-      if (c.sharded) lc.push_back(c.rows);
-      else { Col v = B.view(c.rows, (size_t)sl.rank * n, n); tmp.push_back(v); lc.push_back(v); }
+      if (c.L < w) continue;
+      size_t n = (size_t)1 << (c.L - w);
+      if (c.sharded) local.push_back(c.rows);
+      else { Col v = B.view(c.rows, (size_t)sl.rank * n, n); tmp.push_back(v); local.push_back(v); }
     }
-    const uint32_t depth = maxL - (uint32_t)k, lrep = rep > depth ? rep - depth : 0;
-    Col layer = lrep && (uint32_t)(k - w) >= lrep ? B.commit_layer_repeated((uint32_t)(k - w), prev, lc, lrep) : B.commit_layer((uint32_t)(k - w), prev, lc);
+    std::vector<Col> ll = rep ? B.merkle_commit_repeated(local, rep, nullptr) : B.merkle_commit(local, nullptr);
     for (Col v : tmp) B.free_col(v);
-    m.layers[k] = layer;
-    prev = layer;
-  }
-  if (maxL >= w) {  // N sub-roots -> every rank
-    Col full = B.alloc((size_t)8 << w);
-    B.all_gather(prev, full, 8);
-    B.free_col(m.layers[w]);
+    for (size_t j = 0; j < ll.size(); j++) m.layers[j + w] = ll[j];
+    Col full = B.alloc((size_t)8 << w);   // N sub-roots -> every rank
+    B.all_gather(ll[0], full, 8);
+    B.free_col(ll[0]);
     m.layers[w] = full;
     prev = full;
+    k = (int)w - 1;
   }
   for (; k >= 0; k--) {
     std::vector<Col> lc;
@@ -117,6 +119,7 @@ inline SMerkle merkle_sharded(Backend& B, const ShardLayout& sl, const std::vect
     m.layers[k] = layer;
     prev = layer;
   }
+  if (before_root_read) before_root_read();
   B.read(m.layers[0], 0, 8, m.root.data());
   return m;
 }
@@ -134,7 +137,8 @@ struct ExtraCol { Col full; uint32_t L; int owner; };  // non-committed column r
 
 // Column-shard -> row-shard exchange of the LDEs (`lde[c]` on owners) + extras, then the row-sharded Merkle commit.
 inline void exchange_and_commit(Backend& B, const ShardLayout& sl, uint32_t log_blowup, STree& t, std::vector<Col>& lde,
-                                const std::vector<ExtraCol>& extras, std::vector<RowCol>* extra_rows) {
+                                const std::vector<ExtraCol>& extras, std::vector<RowCol>* extra_rows,
+                                const std::function<void()>& before_root_read = nullptr) {
   const int N = sl.world, me = sl.rank;
   struct E { uint32_t L; int owner; bool sharded; size_t seg; Col full; };
   std::vector<E> es;
@@ -174,7 +178,7 @@ inline void exchange_and_commit(Backend& B, const ShardLayout& sl, uint32_t log_
   }
   t.rows.assign(out.begin(), out.begin() + t.logs.size());
   if (extra_rows) extra_rows->assign(out.begin() + t.logs.size(), out.end());
-  t.merkle = merkle_sharded(B, sl, t.rows);
+  t.merkle = merkle_sharded(B, sl, t.rows, 0, before_root_read);
 }
 
 // MerkleProver::decommit over a sharded tree: same walk as merkle_decommit; the reads are registered in `fb` and the outputs
@@ -295,6 +299,8 @@ inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_
   // proceed on a host thread while the program-independent preprocessed phase below keeps the device and this thread busy.
   std::vector<Table> tables(N_COMPONENTS);
   std::string host_err;
+  double host_wait_ms = 0;
+  std::vector<Col> uploaded;   // this rank's compact columns, in (component, column) order
   struct Joiner { std::thread t; ~Joiner() { if (t.joinable()) t.join(); } } host;
   host.t = std::thread([&] {
     try {
@@ -317,17 +323,28 @@ inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_
     for (size_t c = 0; c < t.logs.size(); c++) t.polys.push_back(t.owner[c] == me ? B.gen_is_first(t.logs[c]) : nullptr);
     interpolate_owned(t);
     std::vector<Col> lde = lde_owned(t);
-    exchange_and_commit(B, sl, cfg.log_blowup, t, lde, {}, nullptr);
+    // With every kernel of this phase queued, wait for the host thread and queue the uploads of this rank's tables: they
+    // run on the copy stream beside the tail of the phase instead of in front of the main-trace exchange.
+    void *ev_queued = nullptr, *ev_host = nullptr;
+    exchange_and_commit(B, sl, cfg.log_blowup, t, lde, {}, nullptr, [&] {
+      ev_queued = B.mark();   // end of this phase's kernels
+      host.t.join();
+      ev_host = B.mark();     // first moment the device could be given the next phase: the gap is what the host cost it
+      if (!host_err.empty()) return;
+      for (int c = 0; c < N_COMPONENTS; c++)
+        if (c % N == me) for (auto& col : tables[c].cols) uploaded.push_back(B.from_host_async(col.data(), col.size()));
+    });
+    if (ev_queued && ev_host) host_wait_ms = B.gap_ms(ev_queued, ev_host);
+    if (!host_err.empty()) throw std::runtime_error(host_err);
     ch.mix_root(t.merkle.root);
     trees.push_back(std::move(t));
   }
   lap("preprocessed");
+  // the part of the VM + table time the DEVICE waited for (the rest hid behind the preprocessed phase)
+  R.times.ms.push_back({"tables(host)", host_wait_ms});
 
   // ---- phase 1: main trace.  The compact columns (one word per table row, 63 MB in total for fib19) are replicated over
   // NVLink, because LogUp generation and the transforms below need them on every rank.
-  host.t.join();
-  if (!host_err.empty()) throw std::runtime_error(host_err);
-  lap("tables(host)");  // only the part of the host work the preprocessed phase did not hide
   std::vector<std::vector<Col>> compact(N_COMPONENTS);
   Col compact_recv = nullptr;
   {
@@ -343,8 +360,9 @@ inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_
     }
     t.owner = assign_owners(t.logs, N);
     if (N == 1) {
+      size_t u = 0;
       for (int c = 0; c < N_COMPONENTS; c++)
-        for (auto& col : tables[c].cols) compact[c].push_back(B.from_host_async(col.data(), col.size()));
+        for (size_t j = 0; j < tables[c].cols.size(); j++) compact[c].push_back(uploaded[u++]);
     } else {
       auto rows_of = [&](int c) { return (size_t)1 << (ls[c] - LOG_N_LANES); };
       auto seg_of = [&](int c) { return std::max<size_t>(rows_of(c), 4); };  // 16-byte aligned slots: the views feed vector loads
@@ -357,19 +375,17 @@ inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_
       for (int s2 = 0; s2 < N; s2++) rtot += rcount[s2];
       Col send = B.alloc(std::max<size_t>(mine * N, 4));
       compact_recv = B.alloc(std::max<size_t>(rtot, 4));
-      size_t so = 0;
-      std::vector<Col> up;
+      size_t so = 0, ui = 0;
       for (int c = 0; c < N_COMPONENTS; c++)
         if (c % N == me)
           for (auto& col : tables[c].cols) {
-            Col u = B.from_host_async(col.data(), col.size());
-            up.push_back(u);
+            Col u = uploaded[ui++];
             for (int d = 0; d < N; d++) B.copy(send, (size_t)d * mine + so, u, 0, col.size());
             so += seg_of(c);
           }
       B.all_to_all(send, scount, compact_recv, rcount);
       B.free_col(send);
-      for (Col u : up) B.free_col(u);
+      for (Col u : uploaded) B.free_col(u);
       std::vector<size_t> roff(N, 0);
       { size_t o = 0; for (int s2 = 0; s2 < N; s2++) { roff[s2] = o; o += rcount[s2]; } }
       for (int c = 0; c < N_COMPONENTS; c++)
@@ -416,6 +432,8 @@ inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_
     t.owner = assign_owners(t.logs, N);
     t.polys.assign(t.logs.size(), nullptr);
     std::vector<uint32_t> claimed(4 * N_COMPONENTS, 0);
+    std::vector<Col> sum_cols;
+    std::vector<size_t> sum_slots;
     size_t base = 0;
     for (int c = 0; c < N_COMPONENTS; c++) {
       int nout = 4 * N_LOGUP_COLS[c];
@@ -428,7 +446,8 @@ inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_
           if (!outs[j]) continue;
           if (j >= nout - 4) {  // LogupTraceGenerator::finalize_last: coset-order prefix sum, claimed_sum = col.at(1)
             B.prefix_sum(outs[j]);
-            B.read(outs[j], 1, 1, &claimed[4 * c + (j - (nout - 4))]);
+            sum_cols.push_back(outs[j]);
+            sum_slots.push_back(4 * c + (j - (nout - 4)));
           }
           t.polys[base + j] = outs[j];
         }
@@ -437,6 +456,10 @@ inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_
       base += nout;
     }
     if (compact_recv) B.free_col(compact_recv);
+    if (!sum_cols.empty()) {  // one read-back for every cumulative column this rank owns
+      std::vector<uint32_t> wv = B.gather(sum_cols, std::vector<size_t>(sum_cols.size(), 1), 1);
+      for (size_t i = 0; i < sum_slots.size(); i++) claimed[sum_slots[i]] = wv[i];
+    }
     if (N > 1) B.allreduce_host(claimed.data(), claimed.size());
     for (int c = 0; c < N_COMPONENTS; c++) proof.claimed_sum[c] = q_make(claimed[4 * c], claimed[4 * c + 1], claimed[4 * c + 2], claimed[4 * c + 3]);
     interpolate_owned(t);
