@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <stdexcept>
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -48,39 +49,49 @@ struct Machine {
   Machine(std::vector<uint32_t> code, std::vector<uint8_t> in, size_t ram_size = 30000)
       : program(std::move(code)), ram(ram_size, 0), input(std::move(in)) {}
 
+  ~Machine() { recycle(trace); }
+
   void execute() {
     const size_t n = program.size();
-    // growing from empty costs more than the run itself (reallocation + page faults); 2^20 + 1 rows is the most the AIR can
-    // take at LOG_MAX_ROWS 24 (the processor table holds one row per step), untouched pages cost nothing
+    // Growing the trace from empty costs more than the run itself (reallocation + a page fault per 4 KB), so the buffer of
+    // the previous proof is taken over when there is one; 2^20 + 1 rows is the most the AIR can take at LOG_MAX_ROWS 24
+    // (the processor table holds one row per step) and untouched pages cost nothing.
+    recycle(trace, /*take=*/true);
+    trace.clear();
     trace.reserve(((size_t)1 << 20) + 1);
+    const uint32_t* prog = program.data();
+    uint32_t* cells = ram.data();
+    const uint32_t ram_size = (uint32_t)ram.size();
+    if (r.mp >= ram_size) throw std::runtime_error("memory pointer out of range");
+    // the pointer is range-checked when it moves; every access in between is to a checked cell
     while (r.ip < n) {
-      r.ci = program[r.ip];
-      r.ni = (r.ip == n - 1) ? 0 : program[r.ip + 1];
+      r.ci = prog[r.ip];
+      r.ni = (r.ip == n - 1) ? 0 : prog[r.ip + 1];
       trace.push_back(r);
       bool early = false;
       switch (r.ci) {
-        case '>': r.mp = sb::m_add(r.mp, 1); break;
-        case '<': r.mp = sb::m_sub(r.mp, 1); break;
-        case '+': at(r.mp) = sb::m_add(at(r.mp), 1); break;
-        case '-': at(r.mp) = sb::m_sub(at(r.mp), 1); break;
+        case '>': r.mp = sb::m_add(r.mp, 1); if (r.mp >= ram_size) throw std::runtime_error("memory pointer out of range"); break;
+        case '<': r.mp = sb::m_sub(r.mp, 1); if (r.mp >= ram_size) throw std::runtime_error("memory pointer out of range"); break;
+        case '+': cells[r.mp] = sb::m_add(cells[r.mp], 1); break;
+        case '-': cells[r.mp] = sb::m_sub(cells[r.mp], 1); break;
         case ',':
           if (in_pos >= input.size()) throw std::runtime_error("input exhausted");
-          at(r.mp) = input[in_pos++];
+          cells[r.mp] = input[in_pos++];
           break;
-        case '.': output.push_back((uint8_t)at(r.mp)); break;
+        case '.': output.push_back((uint8_t)cells[r.mp]); break;
         case '[': {
           uint32_t arg = program.at(r.ip + 1);
-          if (at(r.mp) == 0) { r.ip = arg; early = true; } else r.ip += 1;
+          if (cells[r.mp] == 0) { r.ip = arg; early = true; } else r.ip += 1;
           break;
         }
         case ']': {
           uint32_t arg = program.at(r.ip + 1);
-          if (at(r.mp) != 0) { r.ip = arg - 1; early = true; } else r.ip += 1;
+          if (cells[r.mp] != 0) { r.ip = arg - 1; early = true; } else r.ip += 1;
           break;
         }
         default: throw std::runtime_error("invalid instruction");
       }
-      if (!early) r.mv = at(r.mp);  // mvi is filled in afterwards (fill_inverses): it does not influence execution
+      if (!early) r.mv = cells[r.mp];  // mvi is filled in afterwards (fill_inverses): it does not influence execution
       r.clk += 1;
       r.ip += 1;
     }
@@ -88,6 +99,15 @@ struct Machine {
     r.ni = 0;
     trace.push_back(r);
     fill_inverses();
+  }
+
+  // One spare trace buffer per process: a finished machine leaves its (already faulted-in) buffer for the next one.
+  static void recycle(std::vector<Registers>& v, bool take = false) {
+    static std::mutex mu;
+    static std::vector<Registers> spare;
+    std::lock_guard<std::mutex> lk(mu);
+    if (take) { if (spare.capacity() > v.capacity()) v.swap(spare); }
+    else if (v.capacity() > spare.capacity()) { v.clear(); spare.swap(v); }
   }
 
   // mvi = mv^-1 (0 for 0) for every row (machine.rs:224-228 computes it per step).  A jump keeps the previous mv/mvi pair,
