@@ -9,13 +9,17 @@
 //  * a transform of log size n is cut into "passes"; a pass moves a tile of 2^K <= 2^13 elements HBM->smem once (128-bit
 //    loads), runs its butterfly layers out of registers in radix-32/16 rounds (5 or 4 layers per smem round trip) and
 //    writes the tile back;
-//  * the low pass owns the contiguous bits [0,K); a strided pass owns <= 9 higher bits x 16 contiguous words, so every
-//    global access is a 64-byte run;
+//  * the low pass owns the contiguous bits [0,K); a strided pass owns <= 9 higher bits x 16 contiguous words (64-byte
+//    runs), or exactly 10 bits x 8 words when that saves a whole pass (log 23);
 //  * everything that shapes addressing (K, round start, radix) is a template parameter: shared-memory accesses are
 //    [base + immediate], twiddles of a round are fetched with 128/64-bit loads (one load serves the circle layer and line
 //    layer 1), and ncu showed the round-1 version spending 13.9 instructions per element-layer against ~6 for the math;
-//  * butterflies are balanced across the two integer pipes: the 64-bit product and the plain additions go to the FMA
-//    pipe (IMAD), shifts/masks/min to the ALU pipe (ncu round 1: ALU 77 %, FMA 22 %);
+//  * butterflies are balanced across the two integer pipes: twiddles are stored doubled so that the 64-bit product 2bt
+//    splits into (bt >> 31, (bt & P) << 1) without a mask, additions and subtractions are IMADs with a runtime +-1 (FMA
+//    pipe), only LEA.HI and the three min() of the conditional subtractions stay on the ALU pipe: 10 integer instructions
+//    per butterfly (ncu: first version ALU 77 % / FMA 22 %, now 47-61 % / 31-38 %, issue 59-72 %);
+//  * columns that repeat every value 2^r times (the whole main trace, r = 4) are transformed on their distinct values: the
+//    LINE variants at the end of this file;
 //  * columns of one size are batched through blockIdx.y, so concurrent CTAs share twiddle lines in L1/L2;
 //  * the blow-up layers of an LDE (zero high coefficients) are not computed: the first pass reads index & (2^src-1).
 // All values canonical in [0,P) at kernel boundaries.

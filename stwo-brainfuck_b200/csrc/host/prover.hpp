@@ -336,21 +336,27 @@ inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code
     }
   }
   lap("constraints");
-  // DomainEvaluationAccumulator::finalize: ascending sizes; lift the running poly, accumulate, interpolate
+  // DomainEvaluationAccumulator::finalize.  Upstream walks the sizes upwards: evaluate the running polynomial on the next
+  // domain, add the values, interpolate.  interpolate(values + evaluate(p)) = interpolate(values) + p exactly (p has lower
+  // degree than the domain), so the same coefficients come from interpolating every size once — one batched call — and
+  // adding each running polynomial into the low coefficients of the next: no lifting transforms at all.
   CommitTree comp_tree;
   {
+    std::vector<Col> all;
+    for (auto& kv : sub) for (Col x : kv.second) all.push_back(x);
+    B.interpolate(all);
     std::vector<Col> cur;
     uint32_t cur_log = 0;
     for (auto& kv : sub) {
       std::array<Col, 4> vals = kv.second;
       if (!cur.empty()) {
-        std::vector<Col> ev = B.evaluate(cur, kv.first - cur_log);
-        B.accumulate(vals, {ev[0], ev[1], ev[2], ev[3]});
-        for (Col x : ev) B.free_col(x);
+        std::array<Col, 4> low;
+        for (int k = 0; k < 4; k++) low[k] = B.view(vals[k], 0, (size_t)1 << cur_log);
+        B.accumulate(low, {cur[0], cur[1], cur[2], cur[3]});
+        for (Col x : low) B.free_col(x);
         for (Col x : cur) B.free_col(x);
       }
       cur = {vals[0], vals[1], vals[2], vals[3]};
-      B.interpolate(cur);
       cur_log = kv.first;
     }
     comp_tree.polys = cur;

@@ -569,19 +569,24 @@ inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_
     comp_tree.logs.assign(4, comp_log);
     for (int k = 0; k < 4; k++) comp_tree.owner.push_back(owner_of(k));
     comp_tree.polys.assign(4, nullptr);
+    {  // finalize in coefficient space (prover.hpp): interpolate every size once, add each running polynomial into the low
+       // coefficients of the next size
+      std::vector<Col> mine;
+      for (auto& kv : full) for (int k = 0; k < 4; k++) if (owner_of(k) == me) mine.push_back(kv.second[k]);
+      B.interpolate(mine);
+    }
     for (int k = 0; k < 4; k++) {
       if (owner_of(k) != me) continue;
       Col cur = nullptr;
       uint32_t cur_log = 0;
-      for (auto& kv : full) {   // ascending sizes: lift the running polynomial, accumulate, interpolate
+      for (auto& kv : full) {
         Col vals = kv.second[k];
         if (cur) {
-          std::vector<Col> ev = B.evaluate({cur}, kv.first - cur_log);
-          B.accumulate_col(vals, ev[0]);
-          B.free_col(ev[0]);
+          Col low = B.view(vals, 0, (size_t)1 << cur_log);
+          B.accumulate_col(low, cur);
+          B.free_col(low);
           B.free_col(cur);
         }
-        B.interpolate({vals});
         cur = vals;
         cur_log = kv.first;
       }
