@@ -137,6 +137,8 @@ int32_t sc_grind(sc_ctx* ctx, const uint32_t digest[8], uint32_t pow_bits, uint6
 /* ---- constraint_framework pieces the reference uses concretely at SimdBackend ---- */
 /* gen_is_first::<B>(log_size) — brainfuck_air/mod.rs:497. */
 int32_t sc_gen_is_first(sc_ctx* ctx, uint32_t log_size, sc_col** out);
+/* coefficients of that column's polynomial in closed form (= sc_gen_is_first + sc_interpolate, without the transform) */
+int32_t sc_is_first_coeffs(sc_ctx* ctx, uint32_t log_size, const sc_twiddles* tw, sc_col** out);
 /* simd/prefix_sum.rs inclusive_prefix_sum: in-place inclusive prefix sum in trace-coset order of a bit-reversed
  * column (LogupTraceGenerator::finalize_last, e.g. crates/brainfuck_prover/src/components/processor/table.rs:530). */
 int32_t sc_prefix_sum_bitrev(sc_ctx* ctx, sc_col* col);

@@ -64,7 +64,7 @@ ABI_SYMBOLS = [
     "sc_batch_inverse_qm31", "sc_precompute_twiddles", "sc_twiddles_free", "sc_twiddles_cached", "sc_twiddles_to_host", "sc_interpolate",
     "sc_evaluate", "sc_eval_at_point", "sc_merkle_commit_layer", "sc_merkle_commit", "sc_fold_line",
     "sc_fold_circle_into_line", "sc_accumulate_quotients", "sc_accumulate", "sc_secure_powers", "sc_grind",
-    "sc_gen_is_first", "sc_prefix_sum_bitrev", "sc_logup_generate", "sc_eval_constraints", "sc_gather", "sc_ctx_profile", "sc_ctx_profile_report", "sc_ctx_profile_timeline", "sc_ctx_mark", "sc_ctx_release_since", "sc_ctx_live_columns", "sc_event_record", "sc_event_elapsed", "sc_event_free", "sc_interpolate_repeated", "sc_evaluate_repeated", "sc_eval_at_point_repeated",
+    "sc_gen_is_first", "sc_is_first_coeffs", "sc_prefix_sum_bitrev", "sc_logup_generate", "sc_eval_constraints", "sc_gather", "sc_ctx_profile", "sc_ctx_profile_report", "sc_ctx_profile_timeline", "sc_ctx_mark", "sc_ctx_release_since", "sc_ctx_live_columns", "sc_event_record", "sc_event_elapsed", "sc_event_free", "sc_interpolate_repeated", "sc_evaluate_repeated", "sc_eval_at_point_repeated",
     "sc_merkle_commit_layer_repeated", "sc_merkle_commit_repeated",
 ]
 PROVER_SYMBOLS = ["sbf_prove", "sbf_verify", "sbf_proof_json", "sbf_proof_report", "sbf_proof_output", "sbf_string_free",
@@ -357,6 +357,12 @@ class CudaBackend:
     def gen_is_first(self, log_size: int) -> Column:
         h = _vp()
         self._ck(self._lib.sc_gen_is_first(self._ctx, ctypes.c_uint32(log_size), ctypes.byref(h)))
+        return Column(self, h)
+
+    def is_first_coeffs(self, log_size: int, twiddles: Twiddles) -> Column:
+        """The polynomial of gen_is_first(log_size) (interpolated), in closed form."""
+        h = _vp()
+        self._ck(self._lib.sc_is_first_coeffs(self._ctx, ctypes.c_uint32(log_size), twiddles._h, ctypes.byref(h)))
         return Column(self, h)
 
     def inclusive_prefix_sum(self, col: Column) -> None:

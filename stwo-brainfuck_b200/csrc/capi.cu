@@ -807,6 +807,16 @@ int32_t sc_gen_is_first(sc_ctx* ctx, uint32_t log_size, sc_col** out) {
   { ProfScope ps_(ctx, "gen_is_first"); CKL(launch_gen_is_first((*out)->d, log_size, ctx->st)); }
   return SC_OK;
 }
+// The polynomial of gen_is_first(log_size), i.e. sc_gen_is_first followed by sc_interpolate, computed in closed form.
+int32_t sc_is_first_coeffs(sc_ctx* ctx, uint32_t log_size, const sc_twiddles* tw, sc_col** out) {
+  ENTER();
+  if (!out || !tw || log_size < 3) return fail(SC_EINVAL, "is_first_coeffs: bad argument");
+  if (log_size > tw->root_log + 1) return fail(SC_EINVAL, "is_first_coeffs: twiddle tree too small for this domain");
+  int32_t r = new_col(ctx, 1ull << log_size, out);
+  if (r) return r;
+  { ProfScope ps_(ctx, "gen_is_first"); CKL(launch_is_first_coeffs((*out)->d, log_size, tw->itw + ((size_t)1 << tw->root_log), ctx->st)); }
+  return SC_OK;
+}
 static inline size_t prefix_scratch_words(uint64_t len) { return ((len + 2 * ((len >> 11) + 2) + 8) + 3) & ~(size_t)3; }
 int32_t sc_prefix_sum_bitrev(sc_ctx* ctx, sc_col* col) {
   ENTER();

@@ -73,6 +73,8 @@ struct Backend {
   virtual uint64_t grind(const Hash& digest, uint32_t pow_bits) = 0;
   // constraint_framework
   virtual Col gen_is_first(uint32_t log_size) = 0;
+  // the interpolated IsFirst column (backends may have a closed form)
+  virtual Col is_first_poly(uint32_t log_size) { Col c = gen_is_first(log_size); interpolate({c}); return c; }
   virtual std::vector<Col> logup_generate(int comp, const std::vector<Col>& main, const InteractionElements& el, QM31& claimed_sum) = 0;
   // same without the read-back: the claimed sum is element 1 of each of the last four returned columns (fetch them with one gather)
   virtual std::vector<Col> logup_generate_deferred(int comp, const std::vector<Col>& main, const InteractionElements& el) {

@@ -262,8 +262,7 @@ inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code
   if (!cfg.overlap_host) { tables = build_tables(run_vm(), code); lap("tables(host)"); }
   {
     CommitTree t;
-    for (uint32_t lg = cfg.log_max_rows; lg >= LOG_N_LANES; lg--) { t.polys.push_back(B.gen_is_first(lg)); t.logs.push_back(lg); }
-    B.interpolate(t.polys);
+    for (uint32_t lg = cfg.log_max_rows; lg >= LOG_N_LANES; lg--) { t.polys.push_back(B.is_first_poly(lg)); t.logs.push_back(lg); }
     t.evals = B.evaluate(t.polys, cfg.log_blowup);
     t.layers = B.merkle_commit(t.evals, nullptr);
     if (cfg.overlap_host) tables = build_tables(run_vm(), code);

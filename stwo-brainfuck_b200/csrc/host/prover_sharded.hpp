@@ -320,8 +320,7 @@ inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_
     STree t;
     for (uint32_t lg = cfg.log_max_rows; lg >= LOG_N_LANES; lg--) t.logs.push_back(lg);
     t.owner = assign_owners(t.logs, N);
-    for (size_t c = 0; c < t.logs.size(); c++) t.polys.push_back(t.owner[c] == me ? B.gen_is_first(t.logs[c]) : nullptr);
-    interpolate_owned(t);
+    for (size_t c = 0; c < t.logs.size(); c++) t.polys.push_back(t.owner[c] == me ? B.is_first_poly(t.logs[c]) : nullptr);
     std::vector<Col> lde = lde_owned(t);
     // With every kernel of this phase queued, wait for the host thread and queue the uploads of this rank's tables: they
     // run on the copy stream beside the tail of the phase instead of in front of the main-trace exchange.

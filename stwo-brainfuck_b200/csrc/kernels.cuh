@@ -38,6 +38,7 @@ int launch_fold_circle_into_line(const uint32_t* const src[4], uint32_t log, QM3
 int launch_accumulate(uint32_t* const dst[4], const uint32_t* const src[4], size_t n, cudaStream_t st);
 int launch_fill(uint32_t* v, size_t n, uint32_t value, cudaStream_t st);
 int launch_gen_is_first(uint32_t* v, uint32_t log, cudaStream_t st);
+int launch_is_first_coeffs(uint32_t* out, uint32_t log, const uint32_t* itw_plain_end, cudaStream_t st);
 int launch_prefix_sum_bitrev(uint32_t* v, uint32_t log, uint32_t* scratch, cudaStream_t st);
 size_t prefix_sum_tiled_words(uint32_t log);
 int launch_prefix_sum_bitrev_tiled(uint32_t* const* v, uint32_t ncols, uint32_t log, uint32_t* scratch, cudaStream_t st);

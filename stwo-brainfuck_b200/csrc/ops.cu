@@ -161,6 +161,30 @@ int launch_fill(uint32_t* v, size_t n, uint32_t value, cudaStream_t st) {
   fill_kernel<<<grid_for(n, 256), 256, 0, st>>>(v, n, value, value); g_launch_count++;
   return (int)cudaGetLastError();
 }
+// Coefficients of the IsFirst column (1 at row 0, else 0) in closed form.  The inverse transform of e_0 only ever meets
+// twiddle index 0 (entry i of a layer is non-zero only below 2^(l+1), i.e. in group 0), so coefficient i is the product of
+// t_l over the set bits l of i, times 1/2^log, with t_0 the first circle twiddle (y of the first layer-1 pair), t_1 the
+// first layer-1 twiddle and t_l the first twiddle of line layer l: a write-only kernel instead of a fill and 1-2 FFT passes.
+__global__ void is_first_coeffs_kernel(uint32_t* __restrict__ out, uint32_t log, const uint32_t* __restrict__ itw_end, uint32_t ninv) {
+  __shared__ uint32_t t[32];
+  if (threadIdx.x < log) {
+    const uint32_t l = threadIdx.x;
+    const uint32_t* l1 = itw_end - ((size_t)1 << (log - 1));
+    t[l] = l == 0 ? l1[1] : (l == 1 ? l1[0] : *(itw_end - ((size_t)1 << (log - l))));
+  }
+  __syncthreads();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < ((size_t)1 << log); i += (size_t)gridDim.x * blockDim.x) {  // capped grid
+    uint32_t v = ninv;
+    for (uint32_t l = 0; l < log; l++) if ((i >> l) & 1u) v = m_mul(v, t[l]);
+    out[i] = v;
+  }
+}
+int launch_is_first_coeffs(uint32_t* out, uint32_t log, const uint32_t* itw_plain_end, cudaStream_t st) {
+  if (log < 3 || log > 31) return -1;
+  uint32_t ninv = m_inv(m_pow(2, log));
+  is_first_coeffs_kernel<<<grid_for((size_t)1 << log, 256), 256, 0, st>>>(out, log, itw_plain_end, ninv); g_launch_count++;
+  return (int)cudaGetLastError();
+}
 int launch_gen_is_first(uint32_t* v, uint32_t log, cudaStream_t st) {
   fill_kernel<<<grid_for((size_t)1 << log, 256), 256, 0, st>>>(v, (size_t)1 << log, 0u, 1u); g_launch_count++;
   return (int)cudaGetLastError();

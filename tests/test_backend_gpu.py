@@ -257,6 +257,15 @@ def test_column_api(be):
     assert c.at(5) == 77 and c.clone().at(5) == 77
 
 
+@pytest.mark.parametrize("log", [3, 4, 5, 9, 13, 14, 17, 20, 21])
+def test_is_first_coeffs_closed_form(be, orc, tw, log):
+    got = be.is_first_coeffs(log, tw).to_cpu()
+    c = be.gen_is_first(log)
+    be.interpolate_columns([c], tw)
+    assert (got == c.to_cpu()).all()
+    assert (got == orc.interpolate(np.eye(1, 1 << log, 0, dtype=np.uint32)[0], ROOT_LOG)).all()
+
+
 def test_error_paths_return_status_not_crash(be, tw, pkg):
     """Precondition violations come back as BackendError (Stwo asserts / panics there); the context stays usable."""
     import ctypes
