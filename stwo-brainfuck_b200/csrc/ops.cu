@@ -165,18 +165,30 @@ int launch_fill(uint32_t* v, size_t n, uint32_t value, cudaStream_t st) {
 // twiddle index 0 (entry i of a layer is non-zero only below 2^(l+1), i.e. in group 0), so coefficient i is the product of
 // t_l over the set bits l of i, times 1/2^log, with t_0 the first circle twiddle (y of the first layer-1 pair), t_1 the
 // first layer-1 twiddle and t_l the first twiddle of line layer l: a write-only kernel instead of a fill and 1-2 FFT passes.
-__global__ void is_first_coeffs_kernel(uint32_t* __restrict__ out, uint32_t log, const uint32_t* __restrict__ itw_end, uint32_t ninv) {
+__global__ void __launch_bounds__(256) is_first_coeffs_kernel(uint32_t* __restrict__ out, uint32_t log, const uint32_t* __restrict__ itw_end,
+                                                              uint32_t ninv) {
   __shared__ uint32_t t[32];
+  __shared__ uint32_t hp;
   if (threadIdx.x < log) {
     const uint32_t l = threadIdx.x;
     const uint32_t* l1 = itw_end - ((size_t)1 << (log - 1));
     t[l] = l == 0 ? l1[1] : (l == 1 ? l1[0] : *(itw_end - ((size_t)1 << (log - l))));
   }
   __syncthreads();
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < ((size_t)1 << log); i += (size_t)gridDim.x * blockDim.x) {  // capped grid
-    uint32_t v = ninv;
-    for (uint32_t l = 0; l < log; l++) if ((i >> l) & 1u) v = m_mul(v, t[l]);
-    out[i] = v;
+  // the 256 coefficients of a block share their high bits: one product for those (thread 0), one table entry per thread for
+  // the low eight bits, one multiplication per coefficient
+  uint32_t low = 1u;
+  for (uint32_t l = 0; l < 8 && l < log; l++) if ((threadIdx.x >> l) & 1u) low = m_mul(low, t[l]);
+  const size_t n = (size_t)1 << log;
+  for (size_t base = (size_t)blockIdx.x * 256; base < n; base += (size_t)gridDim.x * 256) {  // capped grid
+    if (threadIdx.x == 0) {
+      uint32_t v = ninv;
+      for (uint32_t l = 8; l < log; l++) if ((base >> l) & 1u) v = m_mul(v, t[l]);
+      hp = v;
+    }
+    __syncthreads();
+    if (base + threadIdx.x < n) out[base + threadIdx.x] = m_mul(hp, low);
+    __syncthreads();
   }
 }
 int launch_is_first_coeffs(uint32_t* out, uint32_t log, const uint32_t* itw_plain_end, cudaStream_t st) {
