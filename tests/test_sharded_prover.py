@@ -1,5 +1,5 @@
 """The sharded prover (csrc/host/prover_sharded.hpp) must produce the very same proof as the single-rank prover.
-CPU: the driver on 1, 2 and 4 in-process ranks (threads) over the oracle backend vs the golden proofs.
+CPU: the driver on 1, 2, 4 and 8 in-process ranks (threads) over the oracle backend vs the golden proofs.
 GPU: the driver at world 1 through the CUDA backend (row-range kernels, views, gathers) vs the golden proofs; the multi-rank
 NCCL path is exercised by tools/run_sharded_prove.py under torchrun (see profiles/)."""
 import ctypes
@@ -26,6 +26,20 @@ def test_sharded_driver_on_thread_ranks(orc, name, world):
     lib.orc_last_error.restype = ctypes.c_char_p
     stdin = bytes.fromhex(g["stdin_hex"])
     p = lib.orc_prove_sharded_json(source(name, g), stdin, ctypes.c_size_t(len(stdin)), ctypes.c_uint32(g["log_max_rows"]), world, 1)
+    assert p, lib.orc_last_error()
+    js = ctypes.string_at(p)
+    lib.orc_free(ctypes.c_void_p(p))
+    assert hashlib.sha256(js).hexdigest() == g["sha256"]
+
+
+def test_sharded_driver_eight_thread_ranks(orc):
+    """World 8 (w = 3): more ranks than tables of some sizes, 13 tables dealt over 8 ranks, replicated FRI tail from log 6."""
+    g = GOLD["a-bc"]
+    lib = orc.lib
+    lib.orc_prove_sharded_json.restype = ctypes.c_void_p
+    lib.orc_last_error.restype = ctypes.c_char_p
+    stdin = bytes.fromhex(g["stdin_hex"])
+    p = lib.orc_prove_sharded_json(source("a-bc", g), stdin, ctypes.c_size_t(len(stdin)), ctypes.c_uint32(g["log_max_rows"]), 8, 1)
     assert p, lib.orc_last_error()
     js = ctypes.string_at(p)
     lib.orc_free(ctypes.c_void_p(p))
