@@ -23,6 +23,7 @@
 //  * columns of one size are batched through blockIdx.y, so concurrent CTAs share twiddle lines in L1/L2;
 //  * the blow-up layers of an LDE (zero high coefficients) are not computed: the first pass reads index & (2^src-1).
 // All values canonical in [0,P) at kernel boundaries.
+#include <mutex>
 #include "kernels.cuh"
 
 namespace sb {
@@ -68,14 +69,22 @@ __global__ void twiddle_tree_kernel(uint32_t* __restrict__ tw, uint32_t* __restr
 }
 
 int launch_twiddle_tree(uint32_t* tw, uint32_t* itw, uint32_t R, cudaStream_t st) {
-  static bool init = false;
-  if (!init) {
-    Pt g[31];
-    g[0] = {GEN_X, GEN_Y};
-    for (int k = 1; k < 31; k++) g[k] = p_dbl(g[k - 1]);
-    cudaError_t e = cudaMemcpyToSymbol(c_gen_pow, g, sizeof(g));
-    if (e != cudaSuccess) return (int)e;
-    init = true;
+  // __constant__ memory is per device: initialise it once for every device this process uses (one flag per ordinal;
+  // the mutex covers contexts of different devices created from different host threads)
+  {
+    static std::mutex mu;
+    static bool init[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev >= 0 && dev < 64 && !init[dev]) {
+      Pt g[31];
+      g[0] = {GEN_X, GEN_Y};
+      for (int k = 1; k < 31; k++) g[k] = p_dbl(g[k - 1]);
+      cudaError_t e = cudaMemcpyToSymbol(c_gen_pow, g, sizeof(g));
+      if (e != cudaSuccess) return (int)e;
+      init[dev] = true;
+    }
   }
   size_t total = (size_t)1 << R;
   unsigned blocks = (unsigned)((total + 255) / 256);

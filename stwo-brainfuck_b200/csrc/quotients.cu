@@ -13,6 +13,7 @@
 // 16 bytes per row are written.  Four consecutive bit-reversed rows are (x,y),(x,-y),(-x,-y),(-x,y): one point per thread.
 // The numerator is split as sum_j C_j*col_j - (py*A + B) with A = sum a_j, B = sum b_j folded on the host, and the
 // sum of products is carried in 64-bit lanes with one partial reduction every two terms.
+#include <mutex>
 #include "kernels.cuh"
 
 namespace sb {
@@ -218,14 +219,22 @@ size_t quotients_scratch_words(uint32_t log, uint64_t row_off, uint64_t nrows) {
 int launch_accumulate_quotients(uint32_t log, uint64_t row_off, uint64_t nrows, const uint32_t* const* d_cols,
                                 const QuotBatch* d_batches, uint32_t nb, const QuotEntry* d_entries, uint32_t* const out[4],
                                 cudaStream_t st, uint32_t* d_scratch) {
-  static bool init = false;
-  if (!init) {
-    Pt g[31];
-    g[0] = {GEN_X, GEN_Y};
-    for (int k = 1; k < 31; k++) g[k] = p_dbl(g[k - 1]);
-    cudaError_t e = cudaMemcpyToSymbol(c_qgen_pow, g, sizeof(g));
-    if (e != cudaSuccess) return (int)e;
-    init = true;
+  // __constant__ memory is per device: initialise it once for every device this process uses (one flag per ordinal;
+  // the mutex covers contexts of different devices created from different host threads)
+  {
+    static std::mutex mu;
+    static bool init[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev >= 0 && dev < 64 && !init[dev]) {
+      Pt g[31];
+      g[0] = {GEN_X, GEN_Y};
+      for (int k = 1; k < 31; k++) g[k] = p_dbl(g[k - 1]);
+      cudaError_t e = cudaMemcpyToSymbol(c_qgen_pow, g, sizeof(g));
+      if (e != cudaSuccess) return (int)e;
+      init[dev] = true;
+    }
   }
   if (log < 2 || log > 30 || (row_off & 3) || (nrows & 3) || row_off + nrows > ((uint64_t)1 << log)) return -1;
   uint32_t nq = (uint32_t)(nrows >> 2);
