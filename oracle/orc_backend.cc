@@ -443,16 +443,52 @@ struct OrcBackend : Backend {
 // the reference's 13 `test_*_constraints` tests, e.g. components/processor/component.rs:178-236).
 struct OrcAssertEval : OrcDomainEval {
   std::string* err;
-  void add(F c) { if (c.v != 0 && err->empty()) *err = "constraint " + std::to_string(k) + " row " + std::to_string(row); k++; }
-  void add(EF c) {
-    if (!orc::qeq(c.v, orc::qfromm(0)) && err->empty()) *err = "constraint " + std::to_string(k) + " row " + std::to_string(row);
-    k++;
+  // message: "constraint K row R left (a + bi) + (c + di)u" — the value as QM31's Display prints it upstream (pinned by the
+  // should_panic strings of the reference's memory/component.rs tests)
+  static std::string show(orc::QM31 v) {
+    return "(" + std::to_string(v.a.a) + " + " + std::to_string(v.a.b) + "i) + (" + std::to_string(v.b.a) + " + " + std::to_string(v.b.b) + "i)u";
   }
+  size_t report_row = 0;
+  void fail(orc::QM31 v) { if (err->empty()) *err = "constraint " + std::to_string(k) + " row " + std::to_string(report_row) + " left " + show(v); }
+  void add(F c) { if (c.v != 0) fail(orc::qfromm(c.v)); k++; }
+  void add(EF c) { if (!orc::qeq(c.v, orc::qfromm(0))) fail(c.v); k++; }
   LogupState<OrcAssertEval> lg2s;
   void relation(int rel, EF num, const F* vals, int n) { lg2s.push(num, ocombine(el->rel[rel], vals, n)); }
   void ext_mask_last(EF& pv, EF& cur) { pv = ext_at(lg2s.n - 1, prev_row); cur = ext_at(lg2s.n - 1, row); }
   void finalize_logup() { lg2s.finalize(*this); }
 };
+
+// constraint_framework::assert_constraints for one component: every constraint must vanish on every row of the trace domain.
+// Upstream evaluates the polynomials back on the trace domain, bit-reverses to NATURAL order and walks `row` over that, so
+// the first failure it reports is the first in natural order; the same walk here ("row" in the message is that index).
+static std::string assert_component(OrcBackend& B, int c, const Table& table, const InteractionElements& el) {
+  std::vector<Col> compact, full;
+  for (auto& col : table.cols) { compact.push_back(B.from_host(col.data(), col.size())); full.push_back(B.broadcast16(compact.back())); }
+  sb::QM31 claimed;
+  std::vector<Col> inter = B.logup_generate(c, compact, el, claimed);
+  uint32_t ls = table.log_size;
+  size_t n = (size_t)1 << ls;
+  Col isf = B.gen_is_first(ls);
+  std::vector<sb::QM31> coeffs(N_CONSTRAINTS[c], sb::q_fromm(1));
+  std::string err;
+  for (size_t nat = 0; nat < n && err.empty(); nat++) {
+    size_t row = orc::bit_reverse((uint32_t)nat, ls);   // storage index of natural row `nat`
+    size_t idx = nat;
+    size_t half = n / 2;
+    size_t ci = idx < half ? 2 * idx : 2 * n - 1 - 2 * idx;   // circle-domain index -> coset index
+    size_t pc = (ci + n - 1) % n;                              // coset-order predecessor
+    size_t pidx = orc::coset_to_domain_index(pc, ls);
+    OrcAssertEval ev;
+    ev.main = &full; ev.inter = &inter; ev.is_first_col = H(isf)->d; ev.el = &el; ev.coeff = &coeffs; ev.total = oq(claimed);
+    ev.row = row; ev.prev_row = orc::bit_reverse((uint32_t)pidx, ls); ev.err = &err; ev.report_row = nat;
+    eval_component(c, ev);
+  }
+  for (Col x : compact) B.free_col(x);
+  for (Col x : full) B.free_col(x);
+  for (Col x : inter) B.free_col(x);
+  B.free_col(isf);
+  return err;
+}
 
 char* dupstr(const std::string& s) { char* p = (char*)malloc(s.size() + 1); memcpy(p, s.c_str(), s.size() + 1); return p; }
 thread_local std::string g_err;
@@ -601,33 +637,36 @@ char* orc_assert_constraints(const char* code, const uint8_t* input, size_t inpu
     OrcBackend B;
     B.precompute_twiddles(8);
     for (int c = 0; c < N_COMPONENTS; c++) {
-      std::vector<Col> compact, full;
-      for (auto& col : tables[c].cols) { compact.push_back(B.from_host(col.data(), col.size())); full.push_back(B.broadcast16(compact.back())); }
-      sb::QM31 claimed;
-      std::vector<Col> inter = B.logup_generate(c, compact, el, claimed);
-      uint32_t ls = tables[c].log_size;
-      size_t n = (size_t)1 << ls;
-      Col isf = B.gen_is_first(ls);
-      std::vector<sb::QM31> coeffs(N_CONSTRAINTS[c], sb::q_fromm(1));
-      std::string err;
-      for (size_t row = 0; row < n; row++) {
-        size_t idx = orc::bit_reverse((uint32_t)row, ls);
-        size_t half = n / 2;
-        size_t ci = idx < half ? 2 * idx : 2 * n - 1 - 2 * idx;   // circle-domain index -> coset index
-        size_t pc = (ci + n - 1) % n;                              // coset-order predecessor
-        size_t pidx = orc::coset_to_domain_index(pc, ls);
-        OrcAssertEval ev;
-        ev.main = &full; ev.inter = &inter; ev.is_first_col = H(isf)->d; ev.el = &el; ev.coeff = &coeffs; ev.total = oq(claimed);
-        ev.row = row; ev.prev_row = orc::bit_reverse((uint32_t)pidx, ls); ev.err = &err;
-        eval_component(c, ev);
-        if (!err.empty()) return dupstr(std::string(COMPONENT_NAMES[c]) + ": " + err);
-      }
-      for (Col x : compact) B.free_col(x);
-      for (Col x : full) B.free_col(x);
-      for (Col x : inter) B.free_col(x);
-      B.free_col(isf);
+      std::string err = assert_component(B, c, tables[c], el);
+      if (!err.empty()) return dupstr(std::string(COMPONENT_NAMES[c]) + ": " + err);
     }
     return nullptr;
+  } catch (const std::exception& e) {
+    return dupstr(std::string("exception: ") + e.what());
+  }
+}
+
+// assert_constraints on ONE component given its table explicitly (rows x cols, row-major): the shape of the reference's
+// negative component tests, which corrupt a table by hand.  elements: 0 = drawn from a fresh channel (MemoryElements::draw
+// on Blake2sChannel::default()), 2 = LookupElements::dummy() (z = 1, every alpha power = 1).  NULL = all constraints hold.
+char* orc_assert_table(int comp, const uint32_t* rows, size_t n_rows, size_t n_cols, int elements) {
+  try {
+    if (comp < 0 || comp >= N_COMPONENTS || (int)n_cols != N_MAIN_COLS[comp]) return dupstr("bad component / column count");
+    Table t;
+    t.cols.assign(n_cols, ColVec(n_rows));
+    for (size_t r = 0; r < n_rows; r++) for (size_t c = 0; c < n_cols; c++) t.cols[c][r] = rows[r * n_cols + c];
+    t.log_size = OrcBackend::lg2(n_rows) + LOG_N_LANES;
+    InteractionElements el;
+    if (elements == 2) {
+      for (int r = 0; r < 3; r++) { el.rel[r].z = sb::q_fromm(1); for (int i = 0; i < 7; i++) el.rel[r].alpha_pow[i] = sb::q_fromm(1); }
+    } else {
+      Channel ch;
+      el = draw_elements(ch);
+    }
+    OrcBackend B;
+    B.precompute_twiddles(8);
+    std::string err = assert_component(B, comp, t, el);
+    return err.empty() ? nullptr : dupstr(err);
   } catch (const std::exception& e) {
     return dupstr(std::string("exception: ") + e.what());
   }

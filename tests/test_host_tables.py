@@ -180,3 +180,51 @@ def test_assert_constraints_all_components(orc, code, stdin, dummy):
         msg = ctypes.string_at(p).decode()
         lib.orc_free(ctypes.c_void_p(p))
         pytest.fail(msg)
+
+
+# ------------------------------------------------------------------------------------------------ negative vectors
+# components/memory/component.rs:211-609: ten corrupted Memory tables with the row and value of the first constraint that
+# `assert_constraints` reports (`#[should_panic = "... row: R\n  left: (v + 0i) + (0 + 0i)u ..."]`).  Tables are written out
+# as the reference builds them: entries sorted by (mp, clk), each row paired with the next entry, one more dummy at the end.
+# columns: clk mp mv d | next_clk next_mp next_mv next_d;  elements: 0 = drawn from a fresh channel, 2 = LookupElements::dummy()
+def _mem(entries, last_dummy):
+    e = list(entries) + [last_dummy]
+    return [list(e[i]) + list(e[i + 1]) for i in range(len(entries))]
+
+
+NEGATIVE = {
+    "boundary_clk": (_mem([(1, 0, 0, 0)], (2, 0, 0, 1)), 0, 0, 1),
+    "boundary_mp": (_mem([(0, 1, 0, 0)], (1, 1, 0, 1)), 0, 0, 1),
+    "boundary_mv": (_mem([(0, 0, 1, 0)], (1, 0, 1, 1)), 0, 0, 1),
+    "boundary_d": (_mem([(0, 0, 0, 1)], (1, 0, 0, 1)), 0, 0, 1),
+    "transition_mp_increase": (_mem([(0, 0, 0, 0), (0, 2, 0, 0)], (1, 2, 0, 1)), 2, 0, 2),
+    "transition_clk_increase": (_mem([(0, 0, 0, 0), (0, 0, 0, 0)], (1, 0, 0, 1)), 0, 0, 1),
+    "transition_mp_increase_next_mv": (_mem([(0, 0, 0, 0), (0, 1, 1, 0)], (1, 1, 1, 1)), 0, 0, 1),
+}
+_t = _mem([(0, 0, 0, 0), (0, 1, 0, 0)], (1, 1, 0, 1))
+_a = [list(r) for r in _t]; _a[0][7] = 2
+NEGATIVE["transition_next_dummy"] = (_a, 0, 0, 2)
+_b = [list(r) for r in _t]; _b[1][3] = 1; _b[1][5] = 2
+NEGATIVE["transition_d_mp"] = (_b, 0, 1, 1)
+_c = [list(r) for r in _t]; _c[1][3] = 1; _c[1][6] = 1
+NEGATIVE["transition_d_mv"] = (_c, 0, 1, 1)
+
+
+@pytest.mark.parametrize("name", sorted(NEGATIVE))
+def test_memory_component_negative_vectors(orc, name):
+    rows, elements, want_row, want_value = NEGATIVE[name]
+    lib = orc.lib
+    lib.orc_assert_table.restype = ctypes.c_void_p
+    flat = np.ascontiguousarray(rows, dtype=np.uint32)
+    p = lib.orc_assert_table(MEMORY, flat.ctypes.data_as(u32p), ctypes.c_size_t(len(rows)), ctypes.c_size_t(8), elements)
+    assert p, f"{name}: the corrupted table passed"
+    msg = ctypes.string_at(p).decode()
+    lib.orc_free(ctypes.c_void_p(p))
+    assert f" row {want_row} left ({want_value} + 0i) + (0 + 0i)u" in msg, msg
+
+
+def test_memory_component_valid_table_passes(orc):
+    lib = orc.lib
+    lib.orc_assert_table.restype = ctypes.c_void_p
+    flat = np.ascontiguousarray(_t, dtype=np.uint32)
+    assert not lib.orc_assert_table(MEMORY, flat.ctypes.data_as(u32p), ctypes.c_size_t(2), ctypes.c_size_t(8), 0)
