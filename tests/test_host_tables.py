@@ -7,6 +7,8 @@
 * components/processor/instructions/table.rs:653-728           `<` table of "+>,<[>+.<-]"
 * components/processor/instructions/jump/table.rs:665-746      `]` table of "++>,<[>+.<-]"
 * components/memory/table.rs:713-744                           memory table from three hand-written registers
+* components/program/table.rs:357-381, end_of_execution/table.rs:339-371   program and end-of-execution tables
+* components/memory/component.rs:211-609                       ten corrupted Memory tables: row and value of the first violation
 * SURVEY.md Table S / the reference's component tests           log sizes of the shipped programs
 
 `assert_constraints` (constraint_framework::assert_constraints, used by all 13 component tests of the reference) runs on the
@@ -143,6 +145,16 @@ def test_jump_if_not_zero_table_example_program(orc):
     # clk ip ci ni mp mv mvi | next_clk next_ip next_mp next_mv | d is_mv_zero   (jump/table.rs:688-727)
     want = [[11, 12, JNZ_C, 7, 0, 1, 1, 12, 7, 0, 1, 0, 0], [17, 12, JNZ_C, 7, 0, 0, 0, 18, 14, 0, 0, 0, 1]]
     assert table(orc, b"++>,<[>+.<-]", b"\x01", JNZ) == want
+
+
+def test_program_table_example(orc):
+    # program/table.rs:357-381: "+>-" -> rows (ip, ci, ni, d) padded with dummy(last ip)
+    assert table(orc, b"+>-", b"", PROGRAM) == [[0, PLUS_C, RIGHT_C, 0], [1, RIGHT_C, MINUS_C, 0], [2, MINUS_C, 0, 0], [2, 0, 0, 1]]
+
+
+def test_end_of_execution_table_example_program(orc):
+    # end_of_execution/table.rs:339-371: the single row with ci == 0 of "+>,<[>+.<-]" (clk 11, ip 13, everything else 0)
+    assert table(orc, b"+>,<[>+.<-]", b"\x01", EOE) == [[11, 13, 0, 0, 0, 0, 0]]
 
 
 def test_empty_instruction_tables_are_one_dummy_row(orc):
