@@ -16,6 +16,12 @@ const char* sbf_last_error(void);
 int32_t sbf_prove(sc_ctx* ctx, const char* code, const uint8_t* input, size_t input_len, uint32_t log_max_rows, uint32_t flags,
                   sbf_proof** out);
 /* verify_brainfuck: host only; 0 or SC_EVERIFY */
+/* The same proof split over the ranks of `comm` (include/stwo_cuda_sharded.h: one process per GPU, every rank calls this with
+ * the same program and ends with the same proof bytes).  comm == NULL runs the sharded driver on one GPU. */
+#define SBF_SHARDED_DRIVER 4u /* flags for sbf_prove: take the sharded driver with world size 1 */
+struct sc_comm;
+int32_t sbf_prove_sharded(sc_ctx* ctx, struct sc_comm* comm, const char* code, const uint8_t* input, size_t input_len,
+                          uint32_t log_max_rows, uint32_t flags, sbf_proof** out);
 int32_t sbf_verify(const sbf_proof* proof);
 char* sbf_proof_json(const sbf_proof* proof);    /* serde-shaped JSON of the proof; free with sbf_string_free */
 char* sbf_proof_report(const sbf_proof* proof);  /* steps, log sizes, per-stage milliseconds */

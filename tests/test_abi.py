@@ -26,7 +26,7 @@ def test_sharded_and_prover_header_symbols_exported(pkg):
         assert declared, hdr_name
         for sym in sorted(declared):
             assert hasattr(lib, sym), f"{sym} declared in {hdr_name} but not exported"
-        missing = declared - set(listed) - set(pkg.ABI_SYMBOLS)
+        missing = declared - set(listed) - set(pkg.ABI_SYMBOLS) - set(pkg.SHARDED_SYMBOLS)
         assert not missing, f"{hdr_name}: {sorted(missing)} not listed in the Python mirror"
 
 
@@ -47,3 +47,89 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 m = bad.search(src)
                 assert not m, f"{f}: {m.group(0)}"
+
+
+def _declared_in_headers():
+    out = set()
+    for hdr_name in ("stwo_cuda.h", "stwo_cuda_sharded.h", "stwo_brainfuck.h"):
+        hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", hdr_name)).read(), flags=re.S)
+        out |= set(re.findall(r"\b((?:sc|sbf)_[a-z0-9_]+)\s*\(", hdr))
+    return out
+
+
+def test_every_export_is_declared(pkg):
+    """The reverse direction: libstwo_cuda.so exports no sc_* / sbf_* entry point that the headers do not declare."""
+    import subprocess
+    so = os.path.join(ROOT, "stwo-brainfuck_b200", "libstwo_cuda.so")
+    nm = subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True, check=True).stdout
+    exported = {ln.split()[-1] for ln in nm.splitlines() if re.search(r" T (sc|sbf)_[a-z0-9_]+$", ln)}
+    assert exported, "no exports found"
+    assert exported == _declared_in_headers()
+
+
+RUST_CRATE = os.path.join(ROOT, "bindings", "rust", "stwo-cuda-backend")
+
+
+def test_rust_ffi_is_generated_from_the_headers():
+    """bindings/rust/stwo-cuda-backend/src/ffi.rs is exactly what tools/gen_rust_ffi.py makes of include/*.h today, and
+    declares every entry point of the three headers (the crate itself cannot be compiled in this image: no rustc)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_rust_ffi", os.path.join(ROOT, "tools", "gen_rust_ffi.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    text = open(os.path.join(RUST_CRATE, "src", "ffi.rs")).read()
+    assert text == gen.generate(), "ffi.rs is stale: run python tools/gen_rust_ffi.py"
+    assert set(re.findall(r"pub fn ((?:sc|sbf)_[a-z0-9_]+)\(", text)) == _declared_in_headers()
+
+
+def test_rust_crate_calls_only_declared_entry_points():
+    """Every `ffi::name` the hand-written Rust modules use exists in ffi.rs with the same number of arguments as the call
+    passes — a consistency check that stands in for the compiler this image lacks."""
+    ffi = open(os.path.join(RUST_CRATE, "src", "ffi.rs")).read()
+    arity = {m.group(1): (0 if not m.group(2).strip() else m.group(2).count(":"))
+             for m in re.finditer(r"pub fn ((?:sc|sbf)_[a-z0-9_]+)\(([^)]*)\)", ffi)}
+    consts = set(re.findall(r"pub const ([A-Z_]+):", ffi))
+    types = set(re.findall(r"pub struct ([A-Za-z]+)", ffi))
+    used = 0
+    for f in sorted(os.listdir(os.path.join(RUST_CRATE, "src"))):
+        if f == "ffi.rs" or not f.endswith(".rs"):
+            continue
+        src = open(os.path.join(RUST_CRATE, "src", f)).read()
+        src = re.sub(r"//[^\n]*", "", src)
+        mods = re.findall(r"^(?:pub )?mod ([a-z_]+);", src, flags=re.M)
+        for m in mods:
+            assert os.path.exists(os.path.join(RUST_CRATE, "src", m + ".rs")), f"{f}: mod {m} has no file"
+        for m in re.finditer(r"(?<!std::)(?<!core::)\bffi::([A-Za-z_0-9]+)", src):
+            name = m.group(1)
+            assert name in arity or name in consts or name in types, f"{f}: ffi::{name} is not declared"
+            if name in arity and src[m.end():m.end() + 1] == "(":
+                depth, i, commas, nonempty = 0, m.end(), 0, False
+                while True:                                   # count top-level commas of the call's argument list
+                    c = src[i]
+                    if c in "([{":
+                        depth += 1
+                    elif c in ")]}":
+                        depth -= 1
+                        if depth == 0:
+                            break
+                    elif c == "," and depth == 1:
+                        commas += 1
+                    elif depth >= 1 and not c.isspace():
+                        nonempty = True
+                    i += 1
+                tail = src[m.end():i].rstrip()
+                n_args = 0 if not nonempty else commas + (0 if tail.endswith(",") else 1)
+                assert n_args == arity[name], f"{f}: {name} called with {n_args} arguments, declared with {arity[name]}"
+                used += 1
+    assert used >= 30
+
+
+def test_reference_patch_applies():
+    """bindings/rust/reference-cuda-feature.patch applies cleanly to the reference tree (only where that tree exists)."""
+    import shutil, subprocess
+    ref = "/root/reference"
+    if not os.path.isdir(ref) or not shutil.which("patch"):
+        pytest.skip("reference tree or patch(1) not available")
+    patch = os.path.join(ROOT, "bindings", "rust", "reference-cuda-feature.patch")
+    r = subprocess.run(["patch", "-p1", "--dry-run", "--batch", "-F0", "-d", ref, "-o", "/dev/null", "-i", patch], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
