@@ -367,6 +367,23 @@ def bench_prove(args):
         e1.record(stream)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
+        # (C) not the headline: the same end-to-end call with the program-independent preprocessed tree kept on the context
+        # between proofs (SBF_CACHE_PREPROCESSED).  The reference rebuilds that tree in every proof,
+        # so `value` and `e2e` above do too; this leg only reports what a server proving many programs would see.
+        cached = None
+        try:
+            pkg.prove_brainfuck(be, code, b"", lmr, cache_preprocessed=True)   # fills the cache
+            torch.cuda.synchronize()
+            t0c = time.perf_counter()
+            for _ in range(args.steps):
+                prc = pkg.prove_brainfuck(be, code, b"", lmr, cache_preprocessed=True)
+                same = prc.json() == pr.json()
+            torch.cuda.synchronize()
+            cached = {"value": (time.perf_counter() - t0c) / args.steps, "unit": "s", "proof_identical": bool(same),
+                      "note": "end to end as e2e, preprocessed tree reused across proofs; not the headline"}
+            pkg.clear_preprocessed_cache(be)
+        except Exception as e:  # reported, never hidden: the headline legs above do not depend on this one
+            cached = {"error": repr(e)}
     if world > 1:
         dist.barrier()
     pr.verify()                              # the host verifier accepts the last proof
@@ -391,7 +408,7 @@ def bench_prove(args):
             "e2e": {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": proof_len,
                     "includes": "VM run, host table building, uploads, proof, proof readback"},
             "gpu_launches": int(launches // args.steps), "stages_ms": stages, "kernel_ms_per_proof": kern, "roofline": roof,
-            "roofline_fft": roof_fft, "clocks": clocks, "verified": True}
+            "roofline_fft": roof_fft, "clocks": clocks, "verified": True, "e2e_preprocessed_cache": cached}
     if rank == 0 and not args.no_cpu_baseline:
         scaled, dt, thr, desc = cpu_prove_sample()
         line["cpu_baseline"] = {"value": scaled, "unit": "s", "cores": thr, "kind": "port", "sample": desc}

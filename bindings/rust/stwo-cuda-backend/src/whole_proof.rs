@@ -38,7 +38,8 @@ impl Drop for CudaProof {
 }
 
 /// `log_max_rows` = the reference's `LOG_MAX_ROWS` (24; brainfuck_air/mod.rs:427-428).  `flags`: `ffi::SBF_NO_OVERLAP`,
-/// `ffi::SBF_NO_TWIDDLE_CACHE` (recompute the twiddle tree in every proof, as the reference does), `ffi::SBF_SHARDED_DRIVER`.
+/// `ffi::SBF_NO_TWIDDLE_CACHE` (recompute the twiddle tree in every proof, as the reference does), `ffi::SBF_SHARDED_DRIVER`,
+/// `ffi::SBF_CACHE_PREPROCESSED` (keep the program-independent preprocessed tree on the context between proofs).
 pub fn prove(code: &str, input: &[u8], log_max_rows: u32, flags: u32) -> Result<CudaProof, ProofError> {
     let code = CString::new(code).map_err(|_| ProofError(ffi::SC_EINVAL, "program text contains a NUL byte".into()))?;
     let mut out = ptr::null_mut();
@@ -47,6 +48,14 @@ pub fn prove(code: &str, input: &[u8], log_max_rows: u32, flags: u32) -> Result<
         return Err(last_error(rc));
     }
     Ok(CudaProof(out))
+}
+
+/// Drops the tree kept by `SBF_CACHE_PREPROCESSED` (destroying the context does too).
+pub fn clear_preprocessed_cache() -> Result<(), ProofError> {
+    match unsafe { ffi::sbf_preprocessed_cache_clear(ctx()) } {
+        ffi::SC_OK => Ok(()),
+        rc => Err(last_error(rc)),
+    }
 }
 
 impl CudaProof {

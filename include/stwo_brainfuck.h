@@ -13,6 +13,11 @@ const char* sbf_last_error(void);
 /* prove --code <code> with stdin bytes; log_max_rows = LOG_MAX_ROWS (24; 20 under cfg(test)), brainfuck_air/mod.rs:427-433 */
 #define SBF_NO_OVERLAP 1u /* flags: build the host tables before any device work instead of overlapping them with phase 0 */
 #define SBF_NO_TWIDDLE_CACHE 2u /* flags: recompute the twiddle tree in every proof (the reference does, mod.rs:480-484) */
+/* flags: keep the preprocessed tree (the IsFirst columns of log size log_max_rows..4, their LDEs and Merkle layers — the
+ * same for every program, brainfuck_air/mod.rs:453-464,493-500) on the context between proofs.  The reference rebuilds it
+ * in every proof; the proof bytes are the same either way.  sbf_preprocessed_cache_clear drops it (sc_ctx_destroy does too). */
+#define SBF_CACHE_PREPROCESSED 8u
+int32_t sbf_preprocessed_cache_clear(sc_ctx* ctx);
 int32_t sbf_prove(sc_ctx* ctx, const char* code, const uint8_t* input, size_t input_len, uint32_t log_max_rows, uint32_t flags,
                   sbf_proof** out);
 /* verify_brainfuck: host only; 0 or SC_EVERIFY */

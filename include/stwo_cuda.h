@@ -52,6 +52,11 @@ int32_t sc_event_free(sc_ctx* ctx, sc_event* e);
 uint64_t sc_ctx_mark(sc_ctx* ctx);
 int32_t sc_ctx_release_since(sc_ctx* ctx, uint64_t mark);
 uint64_t sc_ctx_live_columns(sc_ctx* ctx);   /* number of column handles currently alive on the context */
+/* Ties a caller-owned object to the context: `dtor(ctx, p)` runs inside sc_ctx_destroy while the context can still free
+ * columns (and when the slot is overwritten).  slot < 4; slot 0 is used by sbf_prove for its preprocessed-tree cache. */
+typedef void (*sc_attach_dtor)(sc_ctx* ctx, void* p);
+int32_t sc_ctx_attach(sc_ctx* ctx, uint32_t slot, void* p, sc_attach_dtor dtor);
+void* sc_ctx_attached(sc_ctx* ctx, uint32_t slot);
 size_t sc_ctx_profile_report(sc_ctx* ctx, char* buf, size_t cap);
 size_t sc_ctx_profile_timeline(sc_ctx* ctx, char* buf, size_t cap);  /* "tag:start_ms:dur_ms;" per scope, not cleared */
 

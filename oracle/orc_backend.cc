@@ -518,6 +518,33 @@ char* orc_prove_json(const char* code, const uint8_t* input, size_t input_len, u
   }
 }
 
+// The same driver with a PreprocessedCache kept across `n` proofs on one backend (prover.hpp: the preprocessed tree is
+// program-independent).  Returns the proofs' JSON, one per line, then a last line "fills hits"; NULL on failure.
+char* orc_prove_sequence_cached_json(int n, const char* const* codes, const uint8_t* const* inputs, const size_t* input_lens,
+                                     const uint32_t* log_max_rows, int verify) {
+  try {
+    OrcBackend B;
+    PreprocessedCache cache;
+    std::string out;
+    for (int i = 0; i < n; i++) {
+      std::vector<uint32_t> program = compile(codes[i]);
+      Machine vm(program, std::vector<uint8_t>(inputs[i], inputs[i] + input_lens[i]));
+      vm.execute();
+      ProverConfig cfg;
+      cfg.log_max_rows = log_max_rows[i];
+      ProveResult r = prove_brainfuck(B, program, vm.trace, cfg, nullptr, &cache);
+      if (verify) verify_brainfuck(r.proof, cfg);
+      out += proof_to_json(r.proof) + "\n";
+    }
+    out += std::to_string(cache.fills) + " " + std::to_string(cache.hits);
+    cache.release(B);
+    return dupstr(out);
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return nullptr;
+  }
+}
+
 // The sharded driver on `world` in-process ranks (threads).  Every rank must produce the same proof; returns rank 0's JSON,
 // or NULL if any rank failed or the ranks disagree.
 char* orc_prove_sharded_json(const char* code, const uint8_t* input, size_t input_len, uint32_t log_max_rows, int world, int verify) {

@@ -65,10 +65,10 @@ ABI_SYMBOLS = [
     "sc_evaluate", "sc_eval_at_point", "sc_merkle_commit_layer", "sc_merkle_commit", "sc_fold_line",
     "sc_fold_circle_into_line", "sc_accumulate_quotients", "sc_accumulate", "sc_secure_powers", "sc_grind",
     "sc_gen_is_first", "sc_is_first_coeffs", "sc_prefix_sum_bitrev", "sc_logup_generate", "sc_eval_constraints", "sc_gather", "sc_ctx_profile", "sc_ctx_profile_report", "sc_ctx_profile_timeline", "sc_ctx_mark", "sc_ctx_release_since", "sc_ctx_live_columns", "sc_event_record", "sc_event_elapsed", "sc_event_free", "sc_interpolate_repeated", "sc_evaluate_repeated", "sc_eval_at_point_repeated",
-    "sc_merkle_commit_layer_repeated", "sc_merkle_commit_repeated",
+    "sc_merkle_commit_layer_repeated", "sc_merkle_commit_repeated", "sc_ctx_attach", "sc_ctx_attached",
 ]
 PROVER_SYMBOLS = ["sbf_prove", "sbf_verify", "sbf_proof_json", "sbf_proof_report", "sbf_proof_output", "sbf_string_free",
-                  "sbf_proof_free", "sbf_proof_tamper", "sbf_last_error"]
+                  "sbf_proof_free", "sbf_proof_tamper", "sbf_last_error", "sbf_preprocessed_cache_clear"]
 
 
 def _np_u32(a) -> np.ndarray:
@@ -425,19 +425,28 @@ class Proof:
             pass
 
 
-def prove_brainfuck(backend: CudaBackend, code: str, stdin: bytes = b"", log_max_rows: int = 24, overlap_host: bool = True) -> Proof:
+def prove_brainfuck(backend: CudaBackend, code: str, stdin: bytes = b"", log_max_rows: int = 24, overlap_host: bool = True,
+                    cache_preprocessed: bool = False) -> Proof:
     """prove_brainfuck(&Machine) of crates/brainfuck_prover/src/brainfuck_air/mod.rs:471-735: runs the VM on the host and the
     whole proof on the device behind `backend`.  overlap_host=False builds the host tables before any device work (used by
-    bench.py to time the device path alone); the proof is identical either way."""
+    bench.py to time the device path alone); cache_preprocessed=True keeps the program-independent preprocessed tree on
+    the backend's context between proofs (SBF_CACHE_PREPROCESSED; the reference rebuilds it every time).  The proof is
+    identical in every case."""
     lib = backend._lib
     h = _vp()
     code_b = code.encode() if isinstance(code, str) else code
+    flags = (0 if overlap_host else 1) | (8 if cache_preprocessed else 0)
     rc = lib.sbf_prove(backend._ctx, ctypes.c_char_p(code_b), ctypes.c_char_p(stdin), ctypes.c_size_t(len(stdin)),
-                       ctypes.c_uint32(log_max_rows), ctypes.c_uint32(0 if overlap_host else 1), ctypes.byref(h))
+                       ctypes.c_uint32(log_max_rows), ctypes.c_uint32(flags), ctypes.byref(h))
     if rc != 0:
         lib.sbf_last_error.restype = ctypes.c_char_p
         raise ProvingError(lib.sbf_last_error().decode())
     return Proof(lib, h)
+
+
+def clear_preprocessed_cache(backend: CudaBackend) -> None:
+    """Drops the tree kept by cache_preprocessed=True (sbf_preprocessed_cache_clear); destroying the context does too."""
+    backend._ck(backend._lib.sbf_preprocessed_cache_clear(backend._ctx))
 
 
 # ---------------------------------------------------------------------------------------------------------------------

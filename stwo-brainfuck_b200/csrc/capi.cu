@@ -51,6 +51,8 @@ int32_t sc_ctx_destroy(sc_ctx* ctx) {
   if (!ctx) return SC_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->st);
+  for (auto& a : ctx->attached) if (a.p && a.dtor) { a.dtor(ctx, a.p); a.p = nullptr; }  // may free columns: the context is still whole
+  cudaStreamSynchronize(ctx->st);
   cudaFreeHost(ctx->h_ring);
   for (auto& b : ctx->arena) cudaFreeHost(b.p);
   for (auto& kv : ctx->tw_cache) { cudaFree(kv.second->tw); cudaFree(kv.second->itw); delete kv.second; }
@@ -62,6 +64,15 @@ int32_t sc_ctx_destroy(sc_ctx* ctx) {
   return SC_OK;
 }
 int32_t sc_ctx_sync(sc_ctx* ctx) { ENTER(); CK(cudaStreamSynchronize(ctx->st)); return SC_OK; }
+int32_t sc_ctx_attach(sc_ctx* ctx, uint32_t slot, void* p, sc_attach_dtor dtor) {
+  if (!ctx || slot >= 4) return fail(SC_EINVAL, "ctx_attach: bad argument");
+  auto& a = ctx->attached[slot];
+  if (a.p && a.dtor && a.p != p) a.dtor(ctx, a.p);
+  a.p = p;
+  a.dtor = dtor;
+  return SC_OK;
+}
+void* sc_ctx_attached(sc_ctx* ctx, uint32_t slot) { return ctx && slot < 4 ? ctx->attached[slot].p : nullptr; }
 uint64_t sc_ctx_launch_count(const sc_ctx*) { return g_launch_count; }
 int32_t sc_ctx_profile(sc_ctx* ctx, int32_t enable) {
   ENTER();

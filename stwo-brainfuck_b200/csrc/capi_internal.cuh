@@ -61,6 +61,8 @@ struct sc_ctx {
   size_t slab_cap = 0, slab_used = 0, slab_high = 0;
   int slab_live = 0;
   bool slab_fence = false;
+  // sc_ctx_attach: caller-owned objects whose life ends with the context (e.g. the prover's preprocessed-tree cache)
+  struct Attached { void* p = nullptr; void (*dtor)(sc_ctx*, void*) = nullptr; } attached[4];
 };
 
 // RAII: brackets the kernels launched in a scope with two events when profiling is on.

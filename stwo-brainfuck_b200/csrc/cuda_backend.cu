@@ -239,6 +239,27 @@ extern "C" {
 
 const char* sbf_last_error(void) { return g_sbf_err.c_str(); }
 
+// SBF_CACHE_PREPROCESSED: the cache lives in slot 0 of the context and dies with it
+static void drop_preprocessed_cache(sc_ctx* ctx, void* p) {
+  PreprocessedCache* c = (PreprocessedCache*)p;
+  try { CudaBackendImpl B(ctx); c->release(B); } catch (...) {}
+  delete c;
+}
+static PreprocessedCache* preprocessed_cache(sc_ctx* ctx) {
+  PreprocessedCache* c = (PreprocessedCache*)sc_ctx_attached(ctx, 0);
+  if (!c) {
+    c = new PreprocessedCache;
+    if (sc_ctx_attach(ctx, 0, c, drop_preprocessed_cache)) { delete c; throw std::runtime_error(sc_last_error()); }
+  }
+  return c;
+}
+int32_t sbf_preprocessed_cache_clear(sc_ctx* ctx) {
+  if (!ctx) return SC_EINVAL;
+  PreprocessedCache* c = (PreprocessedCache*)sc_ctx_attached(ctx, 0);
+  if (c) { try { CudaBackendImpl B(ctx); c->release(B); } catch (const std::exception& e) { g_sbf_err = e.what(); return SC_ECUDA; } }
+  return SC_OK;
+}
+
 // `brainfuck_prover prove --code <code>` with stdin bytes `input`: run the VM on the host, prove on the device.
 // log_max_rows = LOG_MAX_ROWS (24; 20 in the reference's tests).  Returns 0 or SC_EPROOF.
 int32_t sbf_prove_sharded(sc_ctx* ctx, sc_comm* comm, const char* code, const uint8_t* input, size_t input_len, uint32_t log_max_rows,
@@ -247,8 +268,11 @@ int32_t sbf_prove(sc_ctx* ctx, const char* code, const uint8_t* input, size_t in
                   sbf_proof** out) {
   if (flags & 4u) return sbf_prove_sharded(ctx, nullptr, code, input, input_len, log_max_rows, flags, out);  // SBF_SHARDED_DRIVER
   const uint64_t mark = sc_ctx_mark(ctx);
+  PreprocessedCache* pp = nullptr;
+  uint64_t pp_fills = 0;
   try {
     if (!ctx || !code || !out) throw std::runtime_error("null argument");
+    if (flags & 8u) { pp = preprocessed_cache(ctx); pp_fills = pp->fills; }  // SBF_CACHE_PREPROCESSED
     std::vector<uint32_t> program = compile(code);
     Machine vm(program, std::vector<uint8_t>(input, input + input_len));
     double vm_ms = 0;
@@ -265,7 +289,7 @@ int32_t sbf_prove(sc_ctx* ctx, const char* code, const uint8_t* input, size_t in
     cfg.overlap_host = !(flags & 1u);  // SBF_NO_OVERLAP: VM run and tables before any device work (bench.py's device-path timing)
     B.cache_twiddles = !(flags & 2u);  // SBF_NO_TWIDDLE_CACHE: recompute the twiddle tree in every proof, as the reference does
     auto t1 = std::chrono::steady_clock::now();
-    ProveResult r = prove_brainfuck(B, program, run_vm, cfg, [&] { sc_ctx_sync(ctx); });
+    ProveResult r = prove_brainfuck(B, program, run_vm, cfg, [&] { sc_ctx_sync(ctx); }, pp);
     double prove_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
     sbf_proof* p = new sbf_proof{std::move(r.proof), cfg, "", vm.output};
     std::ostringstream o;
@@ -280,6 +304,7 @@ int32_t sbf_prove(sc_ctx* ctx, const char* code, const uint8_t* input, size_t in
   } catch (const std::exception& e) {
     g_sbf_err = e.what();
     if (ctx) { sc_ctx_sync(ctx); sc_ctx_release_since(ctx, mark); }  // nothing the failed proof allocated stays on the device
+    if (pp && pp->fills != pp_fills) pp->forget();  // a tree cached by this very call went with the release above
     return SC_EPROOF;
   }
 }

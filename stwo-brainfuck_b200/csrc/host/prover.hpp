@@ -20,6 +20,26 @@ struct CommitTree {
   std::vector<Col> evals;      // LDE columns (log + blowup)
   std::vector<Col> layers;     // Merkle layers by log size
   Hash root;
+  bool borrowed = false;       // the columns belong to a PreprocessedCache: the proof does not free them
+};
+
+// The preprocessed tree is program-independent: the IsFirst columns of log size LOG_MAX_ROWS .. 4, whatever the program
+// (brainfuck_air/mod.rs:453-464,493-500).  A caller that proves many programs on one backend may keep the tree (its
+// polynomials, their LDEs, the Merkle layers and the root) between proofs.  The transcript is
+// unchanged: the cached root is mixed where the computed one would be.  Off unless a cache object is passed.
+struct PreprocessedCache {
+  bool valid = false;
+  uint32_t log_max_rows = 0, log_blowup = 0;
+  CommitTree tree;
+  uint64_t fills = 0, hits = 0;  // (re)builds and reuses so far
+  bool matches(const ProverConfig& cfg) const { return valid && log_max_rows == cfg.log_max_rows && log_blowup == cfg.log_blowup; }
+  void release(Backend& B) {
+    for (Col x : tree.polys) B.free_col(x);
+    for (Col x : tree.evals) B.free_col(x);
+    for (Col x : tree.layers) B.free_col(x);
+    forget();
+  }
+  void forget() { tree = CommitTree(); valid = false; }  // the columns are already gone (e.g. released with a failed proof)
 };
 
 // Mask points of every committed column: tree -> column -> points (Components::mask_points + composition, prover/mod.rs)
@@ -212,7 +232,8 @@ struct ProveResult {
 // preprocessed phase has been enqueued, so the VM run as well as the table building hide behind that device work.
 typedef std::function<const std::vector<Registers>&()> TraceSource;
 inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code, const TraceSource& run_vm,
-                                   const ProverConfig& cfg, const std::function<void()>& sync = nullptr) {
+                                   const ProverConfig& cfg, const std::function<void()>& sync = nullptr,
+                                   PreprocessedCache* pp_cache = nullptr) {
   ProveResult R;
   BrainfuckProof& proof = R.proof;
   auto t_last = std::chrono::steady_clock::now();
@@ -262,14 +283,29 @@ inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code
   if (!cfg.overlap_host) { tables = build_tables(run_vm(), code); lap("tables(host)"); }
   {
     CommitTree t;
-    for (uint32_t lg = cfg.log_max_rows; lg >= LOG_N_LANES; lg--) { t.polys.push_back(B.is_first_poly(lg)); t.logs.push_back(lg); }
-    t.evals = B.evaluate(t.polys, cfg.log_blowup);
-    t.layers = B.merkle_commit(t.evals, nullptr);
+    const bool hit = pp_cache && pp_cache->matches(cfg);
+    if (hit) {
+      t = pp_cache->tree;  // handles only; `borrowed` is set
+      pp_cache->hits++;
+    } else {
+      if (pp_cache && pp_cache->valid) pp_cache->release(B);  // built for another LOG_MAX_ROWS / blowup
+      for (uint32_t lg = cfg.log_max_rows; lg >= LOG_N_LANES; lg--) { t.polys.push_back(B.is_first_poly(lg)); t.logs.push_back(lg); }
+      t.evals = B.evaluate(t.polys, cfg.log_blowup);
+      t.layers = B.merkle_commit(t.evals, nullptr);
+    }
     if (cfg.overlap_host) tables = build_tables(run_vm(), code);
     upload_tables();  // queued behind nothing: the copies run while the device is still busy with the phase above
     if (cfg.overlap_host) { R.times.ms.push_back({"tables(host)", 0}); lap("tables(host)+preprocessed"); }
-    B.read(t.layers[0], 0, 8, t.root.data());
+    if (!hit) B.read(t.layers[0], 0, 8, t.root.data());
     ch.mix_root(t.root);
+    if (pp_cache && !hit) {
+      t.borrowed = true;
+      pp_cache->tree = t;
+      pp_cache->log_max_rows = cfg.log_max_rows;
+      pp_cache->log_blowup = cfg.log_blowup;
+      pp_cache->valid = true;
+      pp_cache->fills++;
+    }
     trees.push_back(std::move(t));
   }
   lap("preprocessed");
@@ -503,7 +539,12 @@ inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code
     if (!q_eq(comp, want)) throw std::runtime_error("ConstraintsNotSatisfied");
   }
   // ---- release device memory
-  for (auto& t : trees) { for (Col x : t.polys) B.free_col(x); for (Col x : t.evals) B.free_col(x); for (Col x : t.layers) B.free_col(x); }
+  for (auto& t : trees) {
+    if (t.borrowed) continue;  // the preprocessed tree stays with its cache
+    for (Col x : t.polys) B.free_col(x);
+    for (Col x : t.evals) B.free_col(x);
+    for (Col x : t.layers) B.free_col(x);
+  }
   for (auto& q : quotients) for (Col x : q.second) B.free_col(x);
   for (Col x : fri_first.layers) B.free_col(x);
   for (auto& L : inner) { for (Col x : L.eval) B.free_col(x); for (Col x : L.tree.layers) B.free_col(x); }
@@ -513,8 +554,9 @@ inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code
 }
 
 inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code, const std::vector<Registers>& vm_trace,
-                                   const ProverConfig& cfg, const std::function<void()>& sync = nullptr) {
-  return prove_brainfuck(B, code, TraceSource([&]() -> const std::vector<Registers>& { return vm_trace; }), cfg, sync);
+                                   const ProverConfig& cfg, const std::function<void()>& sync = nullptr,
+                                   PreprocessedCache* pp_cache = nullptr) {
+  return prove_brainfuck(B, code, TraceSource([&]() -> const std::vector<Registers>& { return vm_trace; }), cfg, sync, pp_cache);
 }
 
 }  // namespace sbf
