@@ -280,7 +280,7 @@ inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code
       for (auto& col : tables[c].cols) compact[c].push_back(B.from_host_async(col.data(), col.size()));
     }
   };
-  if (!cfg.overlap_host) { tables = build_tables(run_vm(), code); lap("tables(host)"); }
+  if (!cfg.overlap_host) { tables = build_tables(run_vm(), code, cfg.log_max_rows); lap("tables(host)"); }
   {
     CommitTree t;
     const bool hit = pp_cache && pp_cache->matches(cfg);
@@ -293,7 +293,7 @@ inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code
       t.evals = B.evaluate(t.polys, cfg.log_blowup);
       t.layers = B.merkle_commit(t.evals, nullptr);
     }
-    if (cfg.overlap_host) tables = build_tables(run_vm(), code);
+    if (cfg.overlap_host) tables = build_tables(run_vm(), code, cfg.log_max_rows);
     upload_tables();  // queued behind nothing: the copies run while the device is still busy with the phase above
     if (cfg.overlap_host) { R.times.ms.push_back({"tables(host)", 0}); lap("tables(host)+preprocessed"); }
     if (!hit) B.read(t.layers[0], 0, 8, t.root.data());

@@ -128,7 +128,9 @@ inline Scratch<uint32_t> order_by_key(size_t n, uint32_t max_key, KeyFn key) {
   return idx;
 }
 
-inline Table memory_table(const std::vector<Registers>& regs) {
+// log_max_rows < 32: fail before the columns are allocated when the table cannot fit (sierpinski.bf needs log size 29:
+// 2^25 rows x 8 columns = 1 GiB of host memory that would be thrown away by the size check of the driver)
+inline Table memory_table(const std::vector<Registers>& regs, uint32_t log_max_rows = 32) {
   if (regs.empty()) throw std::runtime_error("empty trace");
   const size_t m = regs.size();
   const uint32_t max_mp = scan_max(m, [&](size_t i) { return regs[i].mp; }, [&](size_t i) { return !i || regs[i].clk > regs[i - 1].clk; },
@@ -150,6 +152,8 @@ inline Table memory_table(const std::vector<Registers>& regs) {
     off[k] = rows - 1;
   }
   size_t n = next_pow2(rows);
+  if (log_max_rows < 32 && log_max_rows >= LOG_N_LANES && n > ((size_t)1 << (log_max_rows - LOG_N_LANES)))
+    throw std::runtime_error("component too large: memory (" + std::to_string(rows) + " rows after filling the clk gaps)");
   ColVecs c = make_cols(8, n);
   uint32_t *clk = c[0].data(), *mp = c[1].data(), *mv = c[2].data(), *d = c[3].data();
   parallel_ranges(m, TABLE_THREADS, [&](size_t lo, size_t hi) {
@@ -315,9 +319,10 @@ inline Table eoe_table(const std::vector<Registers>& regs) {
   return finish(std::move(c));
 }
 
-inline Table build_table(int k, const std::vector<Registers>& regs, const std::vector<uint32_t>& code, const TraceIndex* ix = nullptr) {
+inline Table build_table(int k, const std::vector<Registers>& regs, const std::vector<uint32_t>& code, const TraceIndex* ix = nullptr,
+                         uint32_t log_max_rows = 32) {
   switch (k) {
-    case MEMORY: return memory_table(regs);
+    case MEMORY: return memory_table(regs, log_max_rows);
     case INSTRUCTION: return instruction_table(regs, code);
     case PROGRAM: return program_table(code);
     case PROCESSOR: return processor_table(regs);
@@ -329,13 +334,13 @@ inline Table build_table(int k, const std::vector<Registers>& regs, const std::v
 }
 
 // The 13 tables are independent: one host thread each (the reference builds them one after the other, mod.rs:511-547).
-inline std::vector<Table> build_tables(const std::vector<Registers>& regs, const std::vector<uint32_t>& code) {
+inline std::vector<Table> build_tables(const std::vector<Registers>& regs, const std::vector<uint32_t>& code, uint32_t log_max_rows = 32) {
   std::vector<Table> t(N_COMPONENTS);
   std::vector<std::string> err(N_COMPONENTS);
   std::vector<std::thread> th;
   auto spawn = [&](int k, const TraceIndex* ix) {
     th.emplace_back([&, k, ix] {
-      try { t[k] = build_table(k, regs, code, ix); } catch (const std::exception& e) { err[k] = e.what(); }
+      try { t[k] = build_table(k, regs, code, ix, log_max_rows); } catch (const std::exception& e) { err[k] = e.what(); }
     });
   };
   // the four tables that do not need the opcode index start first; this thread indexes the trace meanwhile

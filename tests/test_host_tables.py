@@ -90,6 +90,21 @@ def test_component_log_sizes(orc):
     assert vm_summary(orc, load("collatz.bf"), b"7\n")[2] == [21, 17, 13, 17, 14, 13, 5, 15, 14, 6, 14, 15, 4]
 
 
+def test_sierpinski_exceeds_log_max_rows(orc):
+    """BASELINE.json configs[2]: sierpinski.bf runs (257 750 trace rows) but its Memory table has 26 258 214 rows after the clk
+    gaps are filled -> 2^25 rows -> log size 29 > LOG_MAX_ROWS 24 (brainfuck_air/mod.rs:427-428).  The reference
+    cannot prove it; the prover reports the component instead of building the 1 GiB table."""
+    steps, out, logs, prog, ram = vm_summary(orc, load("sierpinski.bf"))
+    assert steps == 257750 and logs == [29, 22, 12, 22, 20, 17, 4, 19, 20, 15, 20, 19, 4]
+    assert out.startswith(b" " * 31 + b"*\n") and out.count(b"\n") == 32
+    lib = orc.lib
+    lib.orc_prove_json.restype = ctypes.c_void_p
+    lib.orc_last_error.restype = ctypes.c_char_p
+    # LOG_MAX_ROWS 12 here only to keep the oracle's preprocessed phase short; the GPU test uses 24
+    assert not lib.orc_prove_json(load("sierpinski.bf"), b"", ctypes.c_size_t(0), ctypes.c_uint32(12), 0)
+    assert b"component too large: memory" in lib.orc_last_error()
+
+
 def test_compiler_jump_targets(orc):
     # compiler.rs:13-37: `[` is followed by the index after the matching `]`'s slot, `]` by the index after the `[`'s slot
     assert vm_summary(orc, b"+>,<[>+.<-]", b"\x01")[3] == [43, 62, 44, 60, 91, 12, 62, 43, 46, 60, 45, 93, 6]

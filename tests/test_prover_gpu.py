@@ -75,6 +75,20 @@ def test_component_too_large_is_an_error(pkg, be):
     assert be.live_columns() == before            # a finished proof leaves nothing behind either
 
 
+def test_sierpinski_is_outside_the_reference_envelope(pkg, be):
+    """BASELINE.json configs[2] lists sierpinski.bf; its Memory table needs log size 29 > LOG_MAX_ROWS 24:
+    the reference cannot prove it (no IsFirst(29) column, twiddles too small, brainfuck_air/mod.rs:427-428,480-484) and neither
+    may the CUDA path pretend to — a ProvingError naming the component, raised before 1 GiB of table is built, nothing leaked."""
+    import gc
+    gc.collect()
+    code = open(os.path.join(PROGRAMS, "sierpinski.bf"), "rb").read()
+    before = be.live_columns()
+    for overlap in (True, False):
+        with pytest.raises(pkg.ProvingError, match="component too large: memory"):
+            pkg.prove_brainfuck(be, code, b"", 24, overlap_host=overlap)
+        assert be.live_columns() == before
+
+
 def test_vm_errors_surface_as_proving_errors(pkg, be):
     for code, stdin in ((b"+]", b""), (b",", b""), (b"<+", b""), (b"", b"")):
         with pytest.raises(pkg.ProvingError):
