@@ -673,6 +673,82 @@ char* orc_assert_constraints(const char* code, const uint8_t* input, size_t inpu
   }
 }
 
+// LogupTraceGenerator output for ONE component given its table (rows x cols, row-major) and explicit lookup elements
+// (96 words: 3 x {z[4], alpha_powers[7][4]}, the C ABI's layout): out receives 4 * N_LOGUP_COLS columns of 16 * n_rows
+// words each, concatenated; claimed[4] the claimed sum.  Returns the number of columns written, 0 on error.
+size_t orc_logup_table(int comp, const uint32_t* rows, size_t n_rows, size_t n_cols, const uint32_t* elements, uint32_t* out,
+                       uint32_t* claimed) {
+  try {
+    if (comp < 0 || comp >= N_COMPONENTS || (int)n_cols != N_MAIN_COLS[comp]) throw std::runtime_error("bad component / column count");
+    InteractionElements el;
+    static_assert(sizeof(InteractionElements) == 96 * 4, "elements layout");
+    memcpy(&el, elements, sizeof(el));
+    OrcBackend B;
+    std::vector<Col> compact;
+    for (size_t c = 0; c < n_cols; c++) {
+      std::vector<uint32_t> col(n_rows);
+      for (size_t r = 0; r < n_rows; r++) col[r] = rows[r * n_cols + c];
+      compact.push_back(B.from_host(col.data(), col.size()));
+    }
+    sb::QM31 sum;
+    std::vector<Col> inter = B.logup_generate(comp, compact, el, sum);
+    const size_t len = 16 * n_rows;
+    for (size_t k = 0; k < inter.size(); k++) B.read(inter[k], 0, len, out + k * len);
+    claimed[0] = sum.a.a; claimed[1] = sum.a.b; claimed[2] = sum.b.a; claimed[3] = sum.b.b;
+    for (Col x : compact) B.free_col(x);
+    for (Col x : inter) B.free_col(x);
+    return inter.size();
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 0;
+  }
+}
+
+// ComponentProver::evaluate_constraint_quotients_on_domain for ONE component given its table: interpolate the main trace,
+// generate and interpolate the LogUp columns, extend everything (and IsFirst) to CanonicCoset(log_size + 1), evaluate the
+// constraints with the given per-constraint coefficients (n_constraints x 4 words) into a zeroed accumulator.
+// out: 4 coordinate columns of 32 * n_rows words.  Returns the claimed sum through claimed[4]; 0 on error, else 4.
+size_t orc_constraints_table(int comp, const uint32_t* rows, size_t n_rows, size_t n_cols, const uint32_t* elements,
+                             const uint32_t* coeffs, uint32_t* out, uint32_t* claimed) {
+  try {
+    if (comp < 0 || comp >= N_COMPONENTS || (int)n_cols != N_MAIN_COLS[comp]) throw std::runtime_error("bad component / column count");
+    InteractionElements el;
+    memcpy(&el, elements, sizeof(el));
+    OrcBackend B;
+    const uint32_t ls = OrcBackend::lg2(n_rows) + LOG_N_LANES;
+    B.precompute_twiddles(ls + 2);
+    std::vector<Col> compact, full;
+    for (size_t c = 0; c < n_cols; c++) {
+      std::vector<uint32_t> col(n_rows);
+      for (size_t r = 0; r < n_rows; r++) col[r] = rows[r * n_cols + c];
+      compact.push_back(B.from_host(col.data(), col.size()));
+      full.push_back(B.broadcast16(compact.back()));
+    }
+    sb::QM31 sum;
+    std::vector<Col> inter = B.logup_generate(comp, compact, el, sum);
+    Col isf = B.gen_is_first(ls);
+    B.interpolate(full);
+    B.interpolate(inter);
+    B.interpolate({isf});
+    std::vector<Col> main_lde = B.evaluate(full, 1), inter_lde = B.evaluate(inter, 1), isf_lde = B.evaluate({isf}, 1);
+    std::vector<sb::QM31> cf(N_CONSTRAINTS[comp]);
+    for (int k = 0; k < N_CONSTRAINTS[comp]; k++) cf[k] = sb::q_make(coeffs[4 * k], coeffs[4 * k + 1], coeffs[4 * k + 2], coeffs[4 * k + 3]);
+    const size_t len = (size_t)2 << ls;
+    std::array<Col, 4> acc;
+    for (int k = 0; k < 4; k++) acc[k] = B.zeros(len);
+    B.eval_constraints(comp, ls, main_lde, inter_lde, isf_lde[0], el, sum, cf, acc);
+    for (int k = 0; k < 4; k++) B.read(acc[k], 0, len, out + k * len);
+    claimed[0] = sum.a.a; claimed[1] = sum.a.b; claimed[2] = sum.b.a; claimed[3] = sum.b.b;
+    for (auto* v : {&compact, &full, &inter, &main_lde, &inter_lde, &isf_lde}) for (Col x : *v) B.free_col(x);
+    B.free_col(isf);
+    for (Col x : acc) B.free_col(x);
+    return 4;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 0;
+  }
+}
+
 // assert_constraints on ONE component given its table explicitly (rows x cols, row-major): the shape of the reference's
 // negative component tests, which corrupt a table by hand.  elements: 0 = drawn from a fresh channel (MemoryElements::draw
 // on Blake2sChannel::default()), 2 = LookupElements::dummy() (z = 1, every alpha power = 1).  NULL = all constraints hold.

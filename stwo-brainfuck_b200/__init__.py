@@ -368,6 +368,32 @@ class CudaBackend:
     def inclusive_prefix_sum(self, col: Column) -> None:
         self._ck(self._lib.sc_prefix_sum_bitrev(self._ctx, col._h))
 
+    # -- the two constraint-framework pieces Stwo writes concretely against SimdBackend
+    COMPONENT_COLUMNS = [(8, 1), (8, 1), (4, 1), (9, 3), (13, 1), (13, 1)] + [(11, 1)] * 6 + [(7, 1)]  # (main, LogUp) per component
+
+    def logup_generate(self, component: int, main_cols: Sequence[Column], elements, log_repeat: int = 0):
+        """interaction_trace_evaluation of one component (e.g. components/memory/table.rs:485-518): LogupTraceGenerator's
+        write_frac / finalize_col per relation entry and finalize_last.  component: BrainfuckClaim order (0 memory … 12
+        end_of_execution); elements: 96 words, 3 x {z[4], alpha_powers[7][4]} for the memory, instruction and processor
+        relations; log_repeat=4 takes one value per table row.  Returns (4 * #LogUp columns, claimed_sum[4])."""
+        el = _np_u32(elements)
+        assert el.size == 96
+        n_out = 4 * self.COMPONENT_COLUMNS[component][1]
+        out = (_vp * n_out)()
+        claimed = np.zeros(4, dtype=np.uint32)
+        self._ck(self._lib.sc_logup_generate(self._ctx, ctypes.c_int32(component), self._arr(main_cols), ctypes.c_uint32(len(main_cols)),
+                                             ctypes.c_uint32(log_repeat), _ptr(el), out, _ptr(claimed)))
+        return [Column(self, _vp(out[i])) for i in range(n_out)], claimed
+
+    def eval_constraints(self, component: int, log_size: int, main_lde: Sequence[Column], inter_lde: Sequence[Column], is_first_lde: Column,
+                         elements, total_sum, coeffs, accum: Sequence[Column]) -> None:
+        """ComponentProver::evaluate_constraint_quotients_on_domain of one component: accum (4 coordinate columns on
+        CanonicCoset(log_size + 1)) += sum_k coeffs[k] * C_k / vanishing.  coeffs: n_constraints x 4 words."""
+        el, ts, cf = _np_u32(elements), _np_u32(total_sum), _np_u32(coeffs)
+        self._ck(self._lib.sc_eval_constraints(self._ctx, ctypes.c_int32(component), ctypes.c_uint32(log_size), self._arr(main_lde),
+                                               ctypes.c_uint32(len(main_lde)), self._arr(inter_lde), ctypes.c_uint32(len(inter_lde)),
+                                               is_first_lde._h, _ptr(el), _ptr(ts), _ptr(cf), self._arr(accum)))
+
 
 # ---------------------------------------------------------------------------------------------------------------------
 # prove / verify — the stand-ins for `brainfuck_prover prove|verify` (crates/brainfuck_prover/src/bin/brainfuck_prover.rs)
