@@ -749,6 +749,39 @@ size_t orc_constraints_table(int comp, const uint32_t* rows, size_t n_rows, size
   }
 }
 
+// The Fiat–Shamir channel (csrc/host/channel.hpp, host logic shared by the product and the oracle) driven by a script, so
+// that a test can pin it against an independent model.  Ops: 'R' + 32 bytes mix_root; 'F' + u32 n + 16 n bytes mix_felts;
+// 'U' + 8 bytes mix_u64; 'D' draw_felt (emits 16 bytes); 'S' + u32 n draw_felts(n) (emits 16 n bytes); 'B' draw_random_bytes
+// (emits 32 bytes); 'Z' trailing_zeros (emits 4 bytes).  The final digest (32 bytes) is appended.  Returns bytes written.
+size_t orc_channel_script(const uint8_t* script, size_t len, uint8_t* out, size_t cap) {
+  Channel ch;
+  size_t w = 0;
+  auto emit = [&](const void* p, size_t n) { if (w + n <= cap) memcpy(out + w, p, n); w += n; };
+  auto rd32 = [&](size_t at) { uint32_t v; memcpy(&v, script + at, 4); return v; };
+  size_t i = 0;
+  while (i < len) {
+    const uint8_t op = script[i++];
+    if (op == 'R') { Hash h; memcpy(h.data(), script + i, 32); i += 32; ch.mix_root(h); }
+    else if (op == 'F') {
+      uint32_t n = rd32(i); i += 4;
+      std::vector<sb::QM31> f(n);
+      for (uint32_t k = 0; k < n; k++, i += 16) f[k] = sb::q_make(rd32(i), rd32(i + 4), rd32(i + 8), rd32(i + 12));
+      ch.mix_felts(f);
+    }
+    else if (op == 'U') { uint64_t v; memcpy(&v, script + i, 8); i += 8; ch.mix_u64(v); }
+    else if (op == 'D') { sb::QM31 q = ch.draw_felt(); uint32_t v[4] = {q.a.a, q.a.b, q.b.a, q.b.b}; emit(v, 16); }
+    else if (op == 'S') {
+      uint32_t n = rd32(i); i += 4;
+      for (sb::QM31 q : ch.draw_felts(n)) { uint32_t v[4] = {q.a.a, q.a.b, q.b.a, q.b.b}; emit(v, 16); }
+    }
+    else if (op == 'B') { Hash h = ch.draw_random_bytes(); emit(h.data(), 32); }
+    else if (op == 'Z') { uint32_t z = ch.trailing_zeros(); emit(&z, 4); }
+    else return 0;
+  }
+  emit(ch.digest.data(), 32);
+  return w;
+}
+
 // assert_constraints on ONE component given its table explicitly (rows x cols, row-major): the shape of the reference's
 // negative component tests, which corrupt a table by hand.  elements: 0 = drawn from a fresh channel (MemoryElements::draw
 // on Blake2sChannel::default()), 2 = LookupElements::dummy() (z = 1, every alpha power = 1).  NULL = all constraints hold.
