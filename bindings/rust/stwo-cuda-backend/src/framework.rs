@@ -68,6 +68,9 @@ impl ComponentId {
 pub struct RelationElements(pub [u32; 96]);
 
 impl RelationElements {
+    /// The reference wraps each `LookupElements<N>` in a tuple struct with a private field (`MemoryElements`,
+    /// `InstructionElements`, `ProcessorElements`: components/memory/table.rs:425-426 and siblings); the trait-level patch
+    /// gives those wrappers a `pub fn lookup_elements(&self) -> &LookupElements<N>` accessor to call this with.
     pub fn new(memory: &LookupElements<3>, instruction: &LookupElements<3>, processor: &LookupElements<7>) -> Self {
         fn put<const N: usize>(dst: &mut [u32], e: &LookupElements<N>) {
             dst[..4].copy_from_slice(&words::qm31(e.z));

@@ -59,8 +59,15 @@ impl FriOps for CudaBackend {
         let a: SecureField = v[..half].iter().fold(SecureField::zero(), |s, x| s + *x);
         let b: SecureField = v[half..].iter().fold(SecureField::zero(), |s, x| s + *x);
         let lambda = (a - b) / BaseField::from_u32_unchecked(n as u32);
-        let g: SecureColumnByCoords<Self> =
-            v.iter().enumerate().map(|(i, x)| if i < half { *x - lambda } else { *x + lambda }).collect();
-        (SecureEvaluation::new(eval.domain, g), lambda)
+        // upstream implements FromIterator<SecureField> for the CPU column only: split the coordinates by hand
+        let mut coords: [Vec<BaseField>; 4] = Default::default();
+        for (i, x) in v.iter().enumerate() {
+            let g = if i < half { *x - lambda } else { *x + lambda };
+            for (k, c) in g.to_m31_array().into_iter().enumerate() {
+                coords[k].push(c);
+            }
+        }
+        let columns = coords.map(|c| c.into_iter().collect::<CudaBaseColumn>());
+        (SecureEvaluation::new(eval.domain, SecureColumnByCoords { columns }), lambda)
     }
 }
