@@ -95,7 +95,7 @@ impl CudaLogup {
     /// `±(1 − d) / (Σ vᵢ·αⁱ − z)`, batched per column, inverted, accumulated, and the last column prefix-summed in
     /// coset order.  Returns the 4·k base columns of the k LogUp columns and the claimed sum.
     ///
-    /// `log_repeat = 4` takes the lane-compact form of the main trace (one value per 16 rows, `lanes::CompactTrace`),
+    /// `log_repeat = 4` takes the lane-compact form of the main trace (one value per 16 rows, `lanes::upload`),
     /// `0` the full columns.
     pub fn generate(
         component: ComponentId,
