@@ -458,6 +458,18 @@ struct OrcAssertEval : OrcDomainEval {
   void finalize_logup() { lg2s.finalize(*this); }
 };
 
+// Same walk, but the value of every constraint at one row is recorded instead of asserted (tests/air_model.py compares
+// them with a Python transcription of the reference's evaluate() bodies on tables that do NOT satisfy the AIR).
+struct OrcRecordEval : OrcDomainEval {
+  std::vector<orc::QM31>* rec;
+  void add(F c) { rec->push_back(orc::qfromm(c.v)); k++; }
+  void add(EF c) { rec->push_back(c.v); k++; }
+  LogupState<OrcRecordEval> lg2s;
+  void relation(int rel, EF num, const F* vals, int n) { lg2s.push(num, ocombine(el->rel[rel], vals, n)); }
+  void ext_mask_last(EF& pv, EF& cur) { pv = ext_at(lg2s.n - 1, prev_row); cur = ext_at(lg2s.n - 1, row); }
+  void finalize_logup() { lg2s.finalize(*this); }
+};
+
 // constraint_framework::assert_constraints for one component: every constraint must vanish on every row of the trace domain.
 // Upstream evaluates the polynomials back on the trace domain, bit-reverses to NATURAL order and walks `row` over that, so
 // the first failure it reports is the first in natural order; the same walk here ("row" in the message is that index).
@@ -780,6 +792,47 @@ size_t orc_channel_script(const uint8_t* script, size_t len, uint8_t* out, size_
   }
   emit(ch.digest.data(), 32);
   return w;
+}
+
+// Values of all constraints of ONE component at natural trace-domain row `nat`, for an explicit table and explicit lookup
+// elements; the LogUp columns and the claimed sum are generated from the table.  out: N_CONSTRAINTS x 4 words.  Returns the
+// number of constraints, 0 on error.
+size_t orc_constraint_values(int comp, const uint32_t* rows, size_t n_rows, size_t n_cols, const uint32_t* elements, size_t nat,
+                             uint32_t* out) {
+  try {
+    if (comp < 0 || comp >= N_COMPONENTS || (int)n_cols != N_MAIN_COLS[comp]) throw std::runtime_error("bad component / column count");
+    InteractionElements el;
+    memcpy(&el, elements, sizeof(el));
+    OrcBackend B;
+    std::vector<Col> compact, full;
+    for (size_t c = 0; c < n_cols; c++) {
+      std::vector<uint32_t> col(n_rows);
+      for (size_t r = 0; r < n_rows; r++) col[r] = rows[r * n_cols + c];
+      compact.push_back(B.from_host(col.data(), col.size()));
+      full.push_back(B.broadcast16(compact.back()));
+    }
+    sb::QM31 claimed;
+    std::vector<Col> inter = B.logup_generate(comp, compact, el, claimed);
+    const uint32_t ls = OrcBackend::lg2(n_rows) + LOG_N_LANES;
+    const size_t n = (size_t)1 << ls, half = n / 2;
+    if (nat >= n) throw std::runtime_error("row out of range");
+    Col isf = B.gen_is_first(ls);
+    std::vector<sb::QM31> coeffs(N_CONSTRAINTS[comp], sb::q_fromm(1));
+    std::vector<orc::QM31> rec;
+    const size_t ci = nat < half ? 2 * nat : 2 * n - 1 - 2 * nat;   // circle-domain index -> coset index
+    const size_t pidx = orc::coset_to_domain_index((ci + n - 1) % n, ls);
+    OrcRecordEval ev;
+    ev.main = &full; ev.inter = &inter; ev.is_first_col = H(isf)->d; ev.el = &el; ev.coeff = &coeffs; ev.total = oq(claimed);
+    ev.row = orc::bit_reverse((uint32_t)nat, ls); ev.prev_row = orc::bit_reverse((uint32_t)pidx, ls); ev.rec = &rec;
+    eval_component(comp, ev);
+    for (size_t k = 0; k < rec.size(); k++) { out[4 * k] = rec[k].a.a; out[4 * k + 1] = rec[k].a.b; out[4 * k + 2] = rec[k].b.a; out[4 * k + 3] = rec[k].b.b; }
+    for (auto* v : {&compact, &full, &inter}) for (Col x : *v) B.free_col(x);
+    B.free_col(isf);
+    return rec.size();
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 0;
+  }
 }
 
 // assert_constraints on ONE component given its table explicitly (rows x cols, row-major): the shape of the reference's

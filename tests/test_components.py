@@ -172,3 +172,49 @@ def test_cuda_eval_constraints_matches_oracle(be, orc, prog):
         assert np.array_equal(np.stack([c.to_cpu() for c in acc]), twice), comp
         for c in full + inter + [isf, isf_lde] + main_lde + inter_lde + acc:
             c.free()
+
+
+# ------------------------------------------------------------------------------------------------ the AIR itself
+def oracle_constraint_values(orc, comp, rows, el, nat):
+    lib = orc.lib
+    lib.orc_constraint_values.restype = ctypes.c_size_t
+    a = np.ascontiguousarray(rows, dtype=np.uint32)
+    e = np.ascontiguousarray(el, dtype=np.uint32)
+    out = np.zeros((N_CONSTRAINTS[comp], 4), dtype=np.uint32)
+    got = lib.orc_constraint_values(comp, a.ctypes.data_as(u32p), ctypes.c_size_t(a.shape[0]), ctypes.c_size_t(a.shape[1]),
+                                    e.ctypes.data_as(u32p), ctypes.c_size_t(nat), out.ctypes.data_as(u32p))
+    assert got == N_CONSTRAINTS[comp], lib.orc_last_error()
+    return [tuple(int(x) for x in row) for row in out]
+
+
+N_MAIN = [8, 8, 4, 9, 13, 13, 11, 11, 11, 11, 11, 11, 7]
+
+
+@pytest.mark.parametrize("comp", range(13))
+def test_air_matches_the_python_transcription_of_the_reference(orc, comp):
+    """Every constraint of every component, in the reference's order, on RANDOM tables (which violate the AIR, so that each
+    value depends on the exact formula), at the first row (is_first = 1), the last row and rows in between.  This is the
+    only check of csrc/host/air.hpp that does not go through air.hpp: the kernels and the oracle both instantiate it."""
+    import air_model as A
+    rng = np.random.default_rng(0xA1B + comp)
+    el = random_elements(0xA1B0 + comp)
+    for n_rows in (1, 4):
+        rows = [[int(x) for x in rng.integers(0, M.P, size=N_MAIN[comp])] for _ in range(n_rows)]
+        n = 16 * n_rows
+        for nat in sorted({0, 1, n // 2 - 1, n // 2, n - 1, int(rng.integers(0, n))}):
+            want = A.constraint_values(comp, rows, el, nat)
+            assert len(want) == N_CONSTRAINTS[comp]
+            assert oracle_constraint_values(orc, comp, rows, el, nat) == want, (n_rows, nat)
+
+
+def test_honest_tables_satisfy_the_python_air(orc):
+    """and on the tables of a real execution the transcription evaluates to zero everywhere (assert_constraints, in Python)"""
+    import air_model as A
+    code, stdin = PROGRAMS[0]
+    el = random_elements(7)
+    for comp in range(13):
+        rows = table(orc, code, stdin, comp)
+        if len(rows) > 8:
+            continue                      # Python speed: the small tables are enough here, the oracle covers the rest
+        for nat in range(16 * len(rows)):
+            assert all(v == (0, 0, 0, 0) for v in A.constraint_values(comp, rows, el, nat)), (comp, nat)
