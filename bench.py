@@ -401,7 +401,7 @@ def bench_prove(args):
             "warmup": args.warmup, "ms_per_step": dev_s * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32 (M31)", "data": "fib19.bf (reference example program), 199246 VM steps",
             "config": {"workload": "fib19_prove", "log_max_rows": lmr, "pcs": "pow 5, blowup 2x, 3 queries",
-                       "twiddles": "tree of half_odds(26) cached per context (program-independent); preprocessed tree recomputed every proof",
+                       "twiddles": "tree of half_odds(26) cached per context (program-independent; recomputing it in every proof as the reference does adds 3.2 ms, profiles/r1_twiddle_cost.json); preprocessed tree recomputed every proof",
                        "columns": 213, "lde_cells": proof_lde_cells(FIB19, lmr), "l2": "working set (>20 GB) exceeds L2",
                        "parallelism": "single GPU (at --gpus N > 1 the same proof is split over N GPUs)",
                        "proof_sha256": __import__("hashlib").sha256(pr.json().encode()).hexdigest()},
