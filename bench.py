@@ -384,6 +384,21 @@ def bench_prove(args):
             pkg.clear_preprocessed_cache(be)
         except Exception as e:  # reported, never hidden: the headline legs above do not depend on this one
             cached = {"error": repr(e)}
+        # (D) the strict reading of the reference's prove_brainfuck: nothing kept between proofs, the twiddle tree of
+        # half_odds(26) recomputed in every proof as well (brainfuck_air/mod.rs:480-484; SBF_NO_TWIDDLE_CACHE).
+        strict = None
+        try:
+            pkg.prove_brainfuck(be, code, b"", lmr, twiddle_cache=False)
+            torch.cuda.synchronize()
+            t0s = time.perf_counter()
+            for _ in range(args.steps):
+                prs = pkg.prove_brainfuck(be, code, b"", lmr, twiddle_cache=False)
+                same_s = prs.json() == pr.json()
+            torch.cuda.synchronize()
+            strict = {"value": (time.perf_counter() - t0s) / args.steps, "unit": "s", "proof_identical": bool(same_s),
+                      "note": "end to end as e2e with the twiddle tree recomputed in every proof, as the reference does"}
+        except Exception as e:
+            strict = {"error": repr(e)}
     if world > 1:
         dist.barrier()
     pr.verify()                              # the host verifier accepts the last proof
@@ -408,7 +423,7 @@ def bench_prove(args):
             "e2e": {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": proof_len,
                     "includes": "VM run, host table building, uploads, proof, proof readback"},
             "gpu_launches": int(launches // args.steps), "stages_ms": stages, "kernel_ms_per_proof": kern, "roofline": roof,
-            "roofline_fft": roof_fft, "clocks": clocks, "verified": True, "e2e_preprocessed_cache": cached}
+            "roofline_fft": roof_fft, "clocks": clocks, "verified": True, "e2e_preprocessed_cache": cached, "e2e_no_twiddle_cache": strict}
     if rank == 0 and not args.no_cpu_baseline:
         scaled, dt, thr, desc = cpu_prove_sample()
         line["cpu_baseline"] = {"value": scaled, "unit": "s", "cores": thr, "kind": "port", "sample": desc}

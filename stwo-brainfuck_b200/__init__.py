@@ -452,16 +452,17 @@ class Proof:
 
 
 def prove_brainfuck(backend: CudaBackend, code: str, stdin: bytes = b"", log_max_rows: int = 24, overlap_host: bool = True,
-                    cache_preprocessed: bool = False) -> Proof:
+                    cache_preprocessed: bool = False, twiddle_cache: bool = True) -> Proof:
     """prove_brainfuck(&Machine) of crates/brainfuck_prover/src/brainfuck_air/mod.rs:471-735: runs the VM on the host and the
     whole proof on the device behind `backend`.  overlap_host=False builds the host tables before any device work (used by
     bench.py to time the device path alone); cache_preprocessed=True keeps the program-independent preprocessed tree on
-    the backend's context between proofs (SBF_CACHE_PREPROCESSED; the reference rebuilds it every time).  The proof is
-    identical in every case."""
+    the backend's context between proofs (SBF_CACHE_PREPROCESSED; the reference rebuilds it every time);
+    twiddle_cache=False recomputes the twiddle tree in every proof as the reference does (SBF_NO_TWIDDLE_CACHE).  The proof
+    is identical in every case."""
     lib = backend._lib
     h = _vp()
     code_b = code.encode() if isinstance(code, str) else code
-    flags = (0 if overlap_host else 1) | (8 if cache_preprocessed else 0)
+    flags = (0 if overlap_host else 1) | (8 if cache_preprocessed else 0) | (0 if twiddle_cache else 2)
     rc = lib.sbf_prove(backend._ctx, ctypes.c_char_p(code_b), ctypes.c_char_p(stdin), ctypes.c_size_t(len(stdin)),
                        ctypes.c_uint32(log_max_rows), ctypes.c_uint32(flags), ctypes.byref(h))
     if rc != 0:
