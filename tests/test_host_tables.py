@@ -255,3 +255,63 @@ def test_memory_component_valid_table_passes(orc):
     lib.orc_assert_table.restype = ctypes.c_void_p
     flat = np.ascontiguousarray(_t, dtype=np.uint32)
     assert not lib.orc_assert_table(MEMORY, flat.ctypes.data_as(u32p), ctypes.c_size_t(2), ctypes.c_size_t(8), 0)
+
+
+# ------------------------------------------------------------------------------------------------ random programs
+def random_program(rng, depth=0):
+    """Half of the programs are unstructured (balanced brackets only); the other half is built from counted loops
+    `[` > body < `-]` whose body restores the pointer, so that they terminate and run for hundreds of steps."""
+    if depth == 0 and rng.integers(0, 2) == 0:
+        out, d = [], 0
+        for _ in range(int(rng.integers(1, 40))):
+            c = "+-<>.,[]"[int(rng.integers(0, 8))]
+            if c == "]" and d == 0:
+                c = "+"
+            d += (c == "[") - (c == "]")
+            out.append(c)
+        return ("".join(out) + "]" * d).encode()
+    out = []
+    for _ in range(int(rng.integers(1, 5))):
+        kind = int(rng.integers(0, 4))
+        if kind == 0:
+            out.append("+" * int(rng.integers(1, 6)))
+        elif kind == 1:
+            out.append(",." if rng.integers(0, 2) else ".")
+        elif kind == 2 and depth < 2:
+            k = int(rng.integers(1, 3))
+            out.append("+" * int(rng.integers(0, 4)) + "[" + ">" * k + random_program(rng, depth + 1).decode() + "<" * k + "-]")
+        else:
+            out.append(">" + "+" * int(rng.integers(0, 3)) + "<" if rng.integers(0, 2) else "-" * int(rng.integers(1, 3)) + "+" * 3)
+    return "".join(out).encode()
+
+
+def test_vm_and_tables_match_the_python_transcription_on_random_programs(orc):
+    """tests/host_model.py restates the reference's VM and its 13 table builders; the C++ host code must produce the same
+    output, step count and table rows on random programs (including empty sub-tables, single-step programs, loops that never
+    run and loops entered with a non-zero cell)."""
+    import host_model as H
+    rng = np.random.default_rng(0xB7A1)
+    done = longest = 0
+    kinds = set()
+    for _ in range(400):
+        code = random_program(rng)
+        stdin = bytes(int(x) for x in rng.integers(0, 6, size=64))
+        prog = H.compile_bf(code)
+        try:
+            regs, out = H.execute(prog, stdin, max_steps=3000)
+        except (H.VmError, IndexError):
+            continue
+        if any(r["mp"] > 1000 for r in regs):
+            continue
+        steps, got_out, logs, got_prog, _ = vm_summary(orc, code, stdin)
+        assert (steps, got_out, got_prog) == (len(regs), out, prog), code
+        for comp in range(13):
+            want = H.build_table(comp, regs, prog)
+            assert table(orc, code, stdin, comp) == want, (code, comp)
+            assert logs[comp] == (len(want) - 1).bit_length() + 4
+        kinds |= {chr(r["ci"]) for r in regs[:-1]}
+        longest = max(longest, len(regs))
+        done += 1
+        if done >= 60:
+            break
+    assert done >= 40 and kinds == set("+-<>.,[]") and longest >= 500
