@@ -103,3 +103,22 @@ def constraint_values(comp, rows, el, nat):
     n_ext = len(cols) // 4
     ext = lambda b, i: tuple(cols[4 * b + k][i] for k in range(4))
     return constraints(comp, rows[s // 16], 1 if nat == 0 else 0, el, [ext(b, s) for b in range(n_ext)], ext(n_ext - 1, prev), total)
+
+
+def first_violation(comp, rows, el):
+    """assert_constraints in Python: (natural row, constraint index, value) of the first non-zero constraint, or None.
+    Returns also the claimed sum."""
+    cols, total = M.logup_columns(comp, rows, el)
+    log = (len(rows) * 16).bit_length() - 1
+    order = M.coset_order_storage_indices(log)
+    coset_of = {s: k for k, s in enumerate(order)}
+    n_ext = len(cols) // 4
+    ext = lambda b, i: tuple(cols[4 * b + k][i] for k in range(4))
+    for nat in range(1 << log):
+        s = M.bit_reverse(nat, log)
+        prev = order[(coset_of[s] - 1) % len(order)]
+        vals = constraints(comp, rows[s // 16], 1 if nat == 0 else 0, el, [ext(b, s) for b in range(n_ext)], ext(n_ext - 1, prev), total)
+        for k, v in enumerate(vals):
+            if v != (0, 0, 0, 0):
+                return (nat, k, v), total
+    return None, total

@@ -218,3 +218,27 @@ def test_honest_tables_satisfy_the_python_air(orc):
             continue                      # Python speed: the small tables are enough here, the oracle covers the rest
         for nat in range(16 * len(rows)):
             assert all(v == (0, 0, 0, 0) for v in A.constraint_values(comp, rows, el, nat)), (comp, nat)
+
+
+def test_python_models_are_consistent_with_each_other():
+    """VM -> tables -> LogUp -> AIR entirely in Python (tests/host_model.py, logup_model.py, air_model.py), no C++ involved: on
+    real executions every constraint of every component vanishes on every row and the claimed sums cancel
+    (`lookup_sum_valid`, brainfuck_air/mod.rs:187-227).  The three transcriptions were written from different files of the
+    reference; that they fit together is the check that they were transcribed correctly."""
+    import air_model as A
+    import host_model as H
+    el = random_elements(0x5E1F)
+    for code, stdin in ((b"+>,<[>+.<-]", b"\x01"), (b"++[>+<-]>[-]<", b""), (b",[.-]+[[-]>+<]>.", b"\x03"), (b"+", b"")):
+        prog = H.compile_bf(code)
+        regs, _ = H.execute(prog, stdin)
+        total = (0, 0, 0, 0)
+        for comp in range(13):
+            bad, s = A.first_violation(comp, H.build_table(comp, regs, prog), el)
+            assert bad is None, (code, comp, bad)
+            total = M.q_add(total, s)
+        assert total == (0, 0, 0, 0), code
+    # and a forged execution does not pass: the VM claims a cell went 1 -> 3 on a single `+`
+    prog = H.compile_bf(b"++")
+    regs, _ = H.execute(prog, b"")
+    regs[2]["mv"], regs[2]["mvi"] = 3, pow(3, M.P - 2, M.P)
+    assert A.first_violation(10, H.build_table(10, regs, prog), el)[0] is not None          # the `+` component objects
