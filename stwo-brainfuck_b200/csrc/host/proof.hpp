@@ -166,18 +166,22 @@ inline std::vector<size_t> decommitment_positions(const std::vector<size_t>& que
   return out;
 }
 
-// ---- JSON (serde shapes: M31 -> number, CM31 -> [a,b], QM31 -> [[a,b],[c,d]], hash -> hex string)
-inline std::string hex(const Hash& h) {
-  static const char* d = "0123456789abcdef";
-  std::string s;
+// ---- JSON in the shape serde_json gives the reference's `BrainfuckProof` (bin/brainfuck_prover.rs:127-131 writes it, :145-152
+// reads it back for `verify`).  In-tree part: `Claim { log_size, _marker: PhantomData }` derives Serialize without a skip
+// attribute (components/mod.rs:85-93), so every claim carries `"_marker":null` and the reference's Deserialize REQUIRES it;
+// `InteractionClaim { claimed_sum }` (:70-76).  Upstream part [U]: M31 -> number, CM31 -> [a,b], QM31 -> [[a,b],[c,d]] (tuple
+// structs); `Blake2sHash(pub [u8; 32])` derives Serialize on a newtype over a byte array -> an array of 32 numbers.
+inline std::string hex(const Hash& h) {   // the same digest as `[b0,b1,...,b31]`
+  std::string s = "[";
   const uint8_t* b = (const uint8_t*)h.data();
-  for (int i = 0; i < 32; i++) { s.push_back(d[b[i] >> 4]); s.push_back(d[b[i] & 15]); }
+  for (int i = 0; i < 32; i++) { if (i) s.push_back(','); s += std::to_string((unsigned)b[i]); }
+  s.push_back(']');
   return s;
 }
 inline void jq(std::ostringstream& o, const QM31& q) { o << "[[" << q.a.a << "," << q.a.b << "],[" << q.b.a << "," << q.b.b << "]]"; }
 inline void jdec(std::ostringstream& o, const MerkleDecommitment& d) {
   o << "{\"hash_witness\":[";
-  for (size_t i = 0; i < d.hash_witness.size(); i++) o << (i ? "," : "") << "\"" << hex(d.hash_witness[i]) << "\"";
+  for (size_t i = 0; i < d.hash_witness.size(); i++) o << (i ? "," : "") << hex(d.hash_witness[i]);
   o << "],\"column_witness\":[";
   for (size_t i = 0; i < d.column_witness.size(); i++) o << (i ? "," : "") << d.column_witness[i];
   o << "]}";
@@ -187,17 +191,17 @@ inline void jlayer(std::ostringstream& o, const FriLayerProof& l) {
   for (size_t i = 0; i < l.fri_witness.size(); i++) { if (i) o << ","; jq(o, l.fri_witness[i]); }
   o << "],\"decommitment\":";
   jdec(o, l.decommitment);
-  o << ",\"commitment\":\"" << hex(l.commitment) << "\"}";
+  o << ",\"commitment\":" << hex(l.commitment) << "}";
 }
 inline std::string proof_to_json(const BrainfuckProof& p) {
   std::ostringstream o;
   o << "{\"claim\":{";
-  for (int c = 0; c < N_COMPONENTS; c++) o << (c ? "," : "") << "\"" << COMPONENT_NAMES[c] << "\":{\"log_size\":" << p.log_size[c] << "}";
+  for (int c = 0; c < N_COMPONENTS; c++) o << (c ? "," : "") << "\"" << COMPONENT_NAMES[c] << "\":{\"log_size\":" << p.log_size[c] << ",\"_marker\":null}";
   o << "},\"interaction_claim\":{";
   for (int c = 0; c < N_COMPONENTS; c++) { o << (c ? "," : "") << "\"" << COMPONENT_NAMES[c] << "\":{\"claimed_sum\":"; jq(o, p.claimed_sum[c]); o << "}"; }
   const CommitmentSchemeProof& s = p.proof;
   o << "},\"proof\":{\"commitments\":[";
-  for (size_t i = 0; i < s.commitments.size(); i++) o << (i ? "," : "") << "\"" << hex(s.commitments[i]) << "\"";
+  for (size_t i = 0; i < s.commitments.size(); i++) o << (i ? "," : "") << hex(s.commitments[i]);
   o << "],\"sampled_values\":[";
   for (size_t t = 0; t < s.sampled_values.size(); t++) {
     o << (t ? "," : "") << "[";

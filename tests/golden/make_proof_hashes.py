@@ -2,9 +2,11 @@
 programs.  These are golden vectors of THIS repository's oracle (the reference holds none); they pin the
 whole transcript (roots, claims, OODS values, FRI layers, decommitments) against regressions on both provers.
 Run here: python tests/golden/make_proof_hashes.py"""
-import ctypes, hashlib, json, os
+import ctypes, hashlib, json, os, sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import proof_canon  # noqa: E402
 L = ctypes.CDLL(os.path.join(ROOT, "oracle", "liborc.so"))
 L.orc_prove_json.restype = ctypes.c_void_p
 L.orc_last_error.restype = ctypes.c_char_p
@@ -31,6 +33,7 @@ for name, code, stdin_hex, lmr in CASES:
     assert p, L.orc_last_error()
     js = ctypes.string_at(p)
     L.orc_free(ctypes.c_void_p(p))
+    js = proof_canon.canonical(js)   # hashes are over the canonical text (tests/proof_canon.py), not the wire spelling
     out[name] = {"code": code, "stdin_hex": stdin_hex, "log_max_rows": lmr, "proof_bytes": len(js), "sha256": hashlib.sha256(js).hexdigest()}
     print(name, out[name]["sha256"][:16], len(js))
 json.dump(out, open(os.path.join(HERE, "proof_hashes.json"), "w"), indent=1)

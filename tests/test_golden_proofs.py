@@ -7,6 +7,8 @@ import os
 
 import pytest
 
+import proof_canon
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "proof_hashes.json")))
 
@@ -25,7 +27,7 @@ def test_oracle_reproduces_golden_proof(orc, name):
     assert p
     js = ctypes.string_at(p)
     lib.orc_free(ctypes.c_void_p(p))
-    assert len(js) == g["proof_bytes"] and hashlib.sha256(js).hexdigest() == g["sha256"]
+    proof_canon.check(js, g)
 
 
 @pytest.mark.gpu
@@ -35,7 +37,36 @@ def test_cuda_prover_reproduces_golden_proof(pkg, be, name):
     proof = pkg.prove_brainfuck(be, source(name, g), bytes.fromhex(g["stdin_hex"]), g["log_max_rows"])
     proof.verify()
     js = proof.json().encode()
-    assert len(js) == g["proof_bytes"] and hashlib.sha256(js).hexdigest() == g["sha256"]
+    proof_canon.check(js, g)
     # the device path with the host tables built first gives the same proof
     js2 = pkg.prove_brainfuck(be, source(name, g), bytes.fromhex(g["stdin_hex"]), g["log_max_rows"], overlap_host=False).json().encode()
     assert js2 == js
+
+
+def test_proof_json_has_the_shape_serde_gives_the_reference_types(orc):
+    """`brainfuck_prover verify` does `serde_json::from_str::<BrainfuckProof<_>>` (bin/brainfuck_prover.rs:145-152).  What the
+    reference's own type definitions fix about that text: the three top-level fields (brainfuck_air/mod.rs:71-76), the 13
+    component names in declaration order (:78-93, :170-184), `Claim { log_size, _marker }` with the PhantomData serialised
+    as null and REQUIRED on the way back (components/mod.rs:85-93), `InteractionClaim { claimed_sum }` (:70-76)."""
+    import json
+    lib = orc.lib
+    lib.orc_prove_json.restype = ctypes.c_void_p
+    p = lib.orc_prove_json(b"+>,<[>+.<-]", b"\x01", ctypes.c_size_t(1), ctypes.c_uint32(10), 0)
+    raw = ctypes.string_at(p)
+    lib.orc_free(ctypes.c_void_p(p))
+    assert b" " not in raw and b"\n" not in raw                      # serde_json::to_string is compact
+    js = json.loads(raw)
+    names = ["memory", "instruction", "program", "processor", "jump_if_not_zero", "jump_if_zero", "input_instruction",
+             "left_instruction", "minus_instruction", "output_instruction", "plus_instruction", "right_instruction", "end_of_execution"]
+    assert list(js) == ["claim", "interaction_claim", "proof"]
+    assert list(js["claim"]) == names and list(js["interaction_claim"]) == names
+    for n in names:
+        assert list(js["claim"][n]) == ["log_size", "_marker"] and js["claim"][n]["_marker"] is None
+        cs = js["interaction_claim"][n]["claimed_sum"]
+        assert list(js["interaction_claim"][n]) == ["claimed_sum"] and [len(cs), len(cs[0]), len(cs[1])] == [2, 2, 2]
+    s = js["proof"]
+    assert list(s) == ["commitments", "sampled_values", "decommitments", "queried_values", "proof_of_work", "fri_proof"]
+    assert len(s["commitments"]) == 4 and all(len(h) == 32 and all(0 <= b < 256 for b in h) for h in s["commitments"])
+    assert list(s["fri_proof"]) == ["first_layer", "inner_layers", "last_layer_poly"]
+    assert list(s["fri_proof"]["first_layer"]) == ["fri_witness", "decommitment", "commitment"]
+    assert list(s["decommitments"][0]) == ["hash_witness", "column_witness"]

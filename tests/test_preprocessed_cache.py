@@ -8,6 +8,8 @@ import os
 
 import pytest
 
+import proof_canon
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "proof_hashes.json")))
 
@@ -19,7 +21,7 @@ def source(name):
 
 def check(name, js: bytes):
     g = GOLD[name]
-    assert len(js) == g["proof_bytes"] and hashlib.sha256(js).hexdigest() == g["sha256"], name
+    proof_canon.check(js, g)
 
 
 def test_oracle_driver_with_cache_reproduces_golden_proofs(orc):

@@ -9,6 +9,8 @@ import os
 
 import pytest
 
+import proof_canon
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "proof_hashes.json")))
 
@@ -29,7 +31,7 @@ def test_sharded_driver_on_thread_ranks(orc, name, world):
     assert p, lib.orc_last_error()
     js = ctypes.string_at(p)
     lib.orc_free(ctypes.c_void_p(p))
-    assert hashlib.sha256(js).hexdigest() == g["sha256"]
+    proof_canon.check(js, g)
 
 
 def test_sharded_driver_eight_thread_ranks(orc):
@@ -43,7 +45,7 @@ def test_sharded_driver_eight_thread_ranks(orc):
     assert p, lib.orc_last_error()
     js = ctypes.string_at(p)
     lib.orc_free(ctypes.c_void_p(p))
-    assert hashlib.sha256(js).hexdigest() == g["sha256"]
+    proof_canon.check(js, g)
 
 
 def test_sharded_driver_hello_kakarot_two_ranks(orc):
@@ -54,7 +56,7 @@ def test_sharded_driver_hello_kakarot_two_ranks(orc):
     assert p
     js = ctypes.string_at(p)
     lib.orc_free(ctypes.c_void_p(p))
-    assert hashlib.sha256(js).hexdigest() == g["sha256"]
+    proof_canon.check(js, g)
 
 
 @pytest.mark.gpu
@@ -64,4 +66,4 @@ def test_cuda_sharded_driver_world1(pkg, be, name):
     proof = pkg.prove_brainfuck_sharded(be, None, source(name, g), bytes.fromhex(g["stdin_hex"]), g["log_max_rows"])
     proof.verify()
     js = proof.json().encode()
-    assert hashlib.sha256(js).hexdigest() == g["sha256"]
+    proof_canon.check(js, g)

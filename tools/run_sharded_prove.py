@@ -12,6 +12,8 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 rank, world = dist.get_rank(), dist.get_world_size()
 be = pkg.CudaBackend(local)
 comm = pkg.Comm.from_torch_distributed(be, dist)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import proof_canon  # noqa: E402
 GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "proof_hashes.json")))
 ok = True
 for name in ["with_input", "a-bc", "hello_kakarot", "collatz"]:
@@ -19,7 +21,7 @@ for name in ["with_input", "a-bc", "hello_kakarot", "collatz"]:
     src = g["code"].encode() if g["code"] else open(os.path.join(ROOT, "tests", "golden", "programs", name + ".bf"), "rb").read()
     proof = pkg.prove_brainfuck_sharded(be, comm, src, bytes.fromhex(g["stdin_hex"]), g["log_max_rows"])
     proof.verify()
-    same = hashlib.sha256(proof.json().encode()).hexdigest() == g["sha256"]
+    same = hashlib.sha256(proof_canon.canonical(proof.json().encode())).hexdigest() == g["sha256"]
     ok &= same
     if rank == 0:
         print(json.dumps({"program": name, "world": world, "matches_golden": same}))
