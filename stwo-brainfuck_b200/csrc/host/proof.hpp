@@ -228,9 +228,12 @@ inline std::string proof_to_json(const BrainfuckProof& p) {
   jlayer(o, s.fri_proof.first_layer);
   o << ",\"inner_layers\":[";
   for (size_t i = 0; i < s.fri_proof.inner_layers.size(); i++) { if (i) o << ","; jlayer(o, s.fri_proof.inner_layers[i]); }
-  o << "],\"last_layer_poly\":[";
+  // LinePoly { coeffs: Vec<SecureField>, log_size: u32 } [U core/poly/line.rs]: a struct with named fields -> an object
+  o << "],\"last_layer_poly\":{\"coeffs\":[";
   for (size_t i = 0; i < s.fri_proof.last_layer_poly.size(); i++) { if (i) o << ","; jq(o, s.fri_proof.last_layer_poly[i]); }
-  o << "]}}}";
+  uint32_t ll_log = 0;
+  while (((size_t)1 << ll_log) < s.fri_proof.last_layer_poly.size()) ll_log++;
+  o << "],\"log_size\":" << ll_log << "}}}}";
   return o.str();
 }
 

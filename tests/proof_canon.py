@@ -1,7 +1,8 @@
 """Golden proof hashes (tests/golden/proof_hashes.json) are taken over a canonical text of the proof that does not depend on
 how the wire format spells two things: the `"_marker":null` field serde adds to every `Claim` (components/mod.rs:85-93) and
 Blake2s digests, which the JSON carries as arrays of 32 byte values (derive(Serialize) on `Blake2sHash(pub [u8; 32])`) and the
-canonical text as 64 hex digits.  The canonical text is what the provers emitted when the hashes were first taken, so a
+canonical text as 64 hex digits; likewise `last_layer_poly`, a `LinePoly { coeffs, log_size }` object on the wire and the bare
+coefficient list in the canonical text.  The canonical text is what the provers emitted when the hashes were first taken, so a
 change of spelling does not cost another 15 minutes of oracle time for the two full-size proofs."""
 import hashlib
 import json
@@ -27,6 +28,9 @@ def canonical(js: bytes) -> bytes:
     for d in s["decommitments"]:
         _dec(d)
     fri = s["fri_proof"]
+    if isinstance(fri["last_layer_poly"], dict):          # LinePoly { coeffs, log_size } on the wire, the bare coefficients here
+        assert len(fri["last_layer_poly"]["coeffs"]) == 1 << fri["last_layer_poly"]["log_size"]
+        fri["last_layer_poly"] = fri["last_layer_poly"]["coeffs"]
     for layer in [fri["first_layer"]] + fri["inner_layers"]:
         layer["commitment"] = _hx(layer["commitment"])
         _dec(layer["decommitment"])

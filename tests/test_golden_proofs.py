@@ -70,3 +70,4 @@ def test_proof_json_has_the_shape_serde_gives_the_reference_types(orc):
     assert list(s["fri_proof"]) == ["first_layer", "inner_layers", "last_layer_poly"]
     assert list(s["fri_proof"]["first_layer"]) == ["fri_witness", "decommitment", "commitment"]
     assert list(s["decommitments"][0]) == ["hash_witness", "column_witness"]
+    assert list(s["fri_proof"]["last_layer_poly"]) == ["coeffs", "log_size"] and s["fri_proof"]["last_layer_poly"]["log_size"] == 0
