@@ -71,3 +71,26 @@ def test_proof_json_has_the_shape_serde_gives_the_reference_types(orc):
     assert list(s["fri_proof"]["first_layer"]) == ["fri_witness", "decommitment", "commitment"]
     assert list(s["decommitments"][0]) == ["hash_witness", "column_witness"]
     assert list(s["fri_proof"]["last_layer_poly"]) == ["coeffs", "log_size"] and s["fri_proof"]["last_layer_poly"]["log_size"] == 0
+
+
+HELLO_WORLD = (b"++++++++++[>+++++++>++++++++++>+++>+<<<<-]>++.>+.+++++++..+++.>++.<<+++++++++++++++.>.+++.------.--------.>+.>.")
+
+
+@pytest.mark.parametrize("code,stdin,out,lmr", [
+    (b"+++>,<[>+.<-]", b"\x01", bytes([2, 3, 4]), 14),            # test_proof
+    (HELLO_WORLD, b"", b"Hello World!\n", 16),                      # test_proof_hello_world
+    (b"+++><[>+<-]", b"", b"", 14),                                 # test_proof_no_input
+    (b"++[-]+.", b"", bytes([1]), 14),                              # test_proof_jump_middle_of_program
+])
+def test_reference_end_to_end_programs(orc, code, stdin, out, lmr):
+    """The four prove -> verify round trips of crates/brainfuck_prover/src/brainfuck_air/mod.rs:804-858, program text and
+    input exactly as there (LOG_MAX_ROWS smaller than the reference's test value of 20 to keep the scalar oracle quick)."""
+    import host_model as H
+    regs, got = H.execute(H.compile_bf(code), stdin, max_steps=20000)
+    assert got == out
+    lib = orc.lib
+    lib.orc_prove_json.restype = ctypes.c_void_p
+    lib.orc_last_error.restype = ctypes.c_char_p
+    p = lib.orc_prove_json(code, stdin, ctypes.c_size_t(len(stdin)), ctypes.c_uint32(lmr), 1)      # 1: also verify
+    assert p, lib.orc_last_error()
+    lib.orc_free(ctypes.c_void_p(p))

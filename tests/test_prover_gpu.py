@@ -22,7 +22,8 @@ def oracle_proof(orc, code: bytes, stdin: bytes, log_max_rows: int) -> str:
     return s
 
 
-CASES = [  # the reference's four end-to-end programs (mod.rs:804-858) + the shipped examples that finish quickly
+CASES = [  # programs of the kind the reference's end-to-end tests use (mod.rs:804-858; the exact four run on the CPU oracle in
+          # tests/test_golden_proofs.py::test_reference_end_to_end_programs) + the shipped examples that finish quickly
     ("with_input", b"+>,<[>+.<-]", b"\x01", 10),
     ("no_input", b"+++>++<[->+<]>.", b"", 10),
     ("jump_mid", b"++[>+<-]>[-]<", b"", 10),
