@@ -133,3 +133,24 @@ def test_reference_patch_applies():
     patch = os.path.join(ROOT, "bindings", "rust", "reference-cuda-feature.patch")
     r = subprocess.run(["patch", "-p1", "--dry-run", "--batch", "-F0", "-d", ref, "-o", "/dev/null", "-i", patch], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_column_counts_match_the_reference_source(pkg):
+    """`TraceColumn::count()` of the seven column enums, read from the reference's source text (only where that tree exists),
+    against the counts the ABI documents (`COMPONENT_COLUMNS`), the C++ constants (air_ids.hpp) and the Rust `ComponentId`."""
+    ref = "/root/reference/crates/brainfuck_prover/src/components"
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not available")
+
+    def count(rel):
+        src = open(os.path.join(ref, rel)).read()
+        m = re.search(r"fn count\(\) -> \(usize, usize\) \{\s*\((\d+), (\d+)\)", src)
+        return int(m.group(1)), int(m.group(2))
+    instr = count("processor/instructions/table.rs")
+    jump = count("processor/instructions/jump/table.rs")
+    want = [count("memory/table.rs"), count("instruction/table.rs"), count("program/table.rs"), count("processor/table.rs"), jump, jump] + \
+        [instr] * 6 + [count("processor/instructions/end_of_execution/table.rs")]
+    assert pkg.CudaBackend.COMPONENT_COLUMNS == want
+    ids = open(os.path.join(ROOT, "stwo-brainfuck_b200", "csrc", "host", "air_ids.hpp")).read()
+    nums = lambda name: [int(x) for x in re.search(name + r"\[N_COMPONENTS\] = \{([^}]*)\}", ids).group(1).split(",")]
+    assert nums("N_MAIN_COLS") == [w[0] for w in want] and nums("N_LOGUP_COLS") == [w[1] for w in want]
