@@ -154,3 +154,27 @@ def test_column_counts_match_the_reference_source(pkg):
     ids = open(os.path.join(ROOT, "stwo-brainfuck_b200", "csrc", "host", "air_ids.hpp")).read()
     nums = lambda name: [int(x) for x in re.search(name + r"\[N_COMPONENTS\] = \{([^}]*)\}", ids).group(1).split(",")]
     assert nums("N_MAIN_COLS") == [w[0] for w in want] and nums("N_LOGUP_COLS") == [w[1] for w in want]
+
+
+def test_constraint_counts_match_the_reference_source():
+    """N_CONSTRAINTS of air_ids.hpp = `eval.add_constraint(` calls + `eval.add_to_relation(` calls (one LogUp constraint per
+    relation entry, no batching) in each component's `evaluate()` body of the reference (only where that tree exists)."""
+    ref = "/root/reference/crates/brainfuck_prover/src/components"
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not available")
+    files = ["memory/component.rs", "instruction/component.rs", "program/component.rs", "processor/component.rs",
+             "processor/instructions/jump/jump_if_not_zero_component.rs", "processor/instructions/jump/jump_if_zero_component.rs",
+             "processor/instructions/input_component.rs", "processor/instructions/left_component.rs",
+             "processor/instructions/minus_component.rs", "processor/instructions/output_component.rs",
+             "processor/instructions/plus_component.rs", "processor/instructions/right_component.rs",
+             "processor/instructions/end_of_execution/component.rs"]
+    want = []
+    for f in files:
+        src = open(os.path.join(ref, f)).read()
+        body = src[src.index("fn evaluate<E: EvalAtRow>"):]
+        body = body[:body.index("\n    }\n")]
+        body = re.sub(r"//[^\n]*", "", body)
+        want.append(body.count("eval.add_constraint(") + body.count("eval.add_to_relation("))
+    ids = open(os.path.join(ROOT, "stwo-brainfuck_b200", "csrc", "host", "air_ids.hpp")).read()
+    got = [int(x) for x in re.search(r"N_CONSTRAINTS\[N_COMPONENTS\] = \{([^}]*)\}", ids).group(1).split(",")]
+    assert got == want and sum(got) == 103
