@@ -11,10 +11,8 @@ import logup_model as M
 P = M.P
 
 
-def constraints(comp, r, is_first, el, ext_cur, ext_prev_last, total_sum):
-    """Values of all constraints of component `comp` on one row.
-    r: main-trace values of the row; is_first: 0/1; ext_cur[b]: value of LogUp column b on this row (QM31 4-tuples);
-    ext_prev_last: last LogUp column on the previous row in coset order; total_sum: the component's claimed sum."""
+def main_and_relations(comp, r, is_first):
+    """The `add_constraint` values of one row (as QM31 tuples) and the `add_to_relation` entries (numerator, relation, values)."""
     out = []
     add = lambda v: out.append((v % P, 0, 0, 0))
     one = 1
@@ -79,6 +77,14 @@ def constraints(comp, r, is_first, el, ext_cur, ext_prev_last, total_sum):
         clk, ip, ci, ni, mp, mv, mvi = r
         add(ci)
         rel = [(-one, M.PROC, [clk, ip, ci, ni, mp, mv, mvi])]
+    return out, rel
+
+
+def constraints(comp, r, is_first, el, ext_cur, ext_prev_last, total_sum):
+    """Values of all constraints of component `comp` on one row.
+    r: main-trace values of the row; is_first: 0/1; ext_cur[b]: value of LogUp column b on this row (QM31 4-tuples);
+    ext_prev_last: last LogUp column on the previous row in coset order; total_sum: the component's claimed sum."""
+    out, rel = main_and_relations(comp, r, is_first)
     # LogupAtRow::finalize
     prev_col = (0, 0, 0, 0)
     for b, (num, relation, vals) in enumerate(rel):

@@ -242,3 +242,25 @@ def test_python_models_are_consistent_with_each_other():
     regs, _ = H.execute(prog, b"")
     regs[2]["mv"], regs[2]["mvi"] = 3, pow(3, M.P - 2, M.P)
     assert A.first_violation(10, H.build_table(10, regs, prog), el)[0] is not None          # the `+` component objects
+
+
+def test_air_transcription_against_the_reference_source_text():
+    """Where the reference tree exists: every `eval.add_constraint(<expr>)` and `eval.add_to_relation(..)` of the 13 `evaluate()`
+    bodies, translated mechanically from the Rust source (tests/ref_air_parser.py) and evaluated on random rows, equals the hand
+    transcription of tests/air_model.py — which the oracle and, through proof equality, the CUDA kernels equal in turn."""
+    import air_model as A
+    import ref_air_parser as R
+    if not R.available():
+        pytest.skip("reference tree not available")
+    rng = np.random.default_rng(0x50C)
+    for comp in range(13):
+        for trial in range(8):
+            row = [int(x) for x in rng.integers(0, M.P, size=N_MAIN[comp])]
+            if trial % 2:
+                row = [v % 3 for v in row]                  # small values: products that vanish, flags that are bits
+            for is_first in (0, 1):
+                got_main, got_rel = R.evaluate(comp, row, is_first)
+                want_main, want_rel = A.main_and_relations(comp, row, is_first)
+                assert [(v, 0, 0, 0) for v in got_main] == want_main, (comp, row)
+                assert got_rel == [(n % M.P, r, v) for n, r, v in want_rel], (comp, row)
+        assert len(got_main) + len(got_rel) == N_CONSTRAINTS[comp]
