@@ -86,3 +86,38 @@ def evaluate(comp: int, row, is_first: int):
         else:
             rels.append((eval(st[2], {"__builtins__": {}}, env) % P, st[1], [env[v] for v in st[3]]))
     return out, rels
+
+
+# ---- the seven interaction_trace_evaluation functions (table.rs): which fraction each LogUp column accumulates
+TABLE_FILES = {0: "memory/table.rs", 1: "instruction/table.rs", 2: "program/table.rs", 3: "processor/table.rs",
+               4: "processor/instructions/jump/table.rs", 5: "processor/instructions/jump/table.rs",
+               **{k: "processor/instructions/table.rs" for k in range(6, 12)}, 12: "processor/instructions/end_of_execution/table.rs"}
+ELEMENT_TYPES = {"MemoryElements": 0, "InstructionElements": 1, "ProcessorElements": 2}
+
+
+def parse_fractions(comp: int):
+    """-> one entry per `col_gen.write_frac(..)`: (numerator at d = 0, numerator at d = 1, dummy-flag column index or None,
+    relation, [main column indices])"""
+    src = open(os.path.join(REF, TABLE_FILES[comp])).read()
+    src = re.sub(r"//[^\n]*", "", src)
+    index_of = {}                                                      # "MemoryColumn::Clk" -> 0
+    for em in re.finditer(r"impl (\w+Column) \{.*?fn index\(self\) -> usize \{\s*match self \{(.*?)\}", src, flags=re.S):
+        for v, i in re.findall(r"Self::(\w+) => (\d+)", em.group(2)):
+            index_of[em.group(1) + "::" + v] = int(i)
+    start = src.index("pub fn interaction_trace_evaluation(")
+    body = src[start:src.index("\n}\n", start)]
+    params = dict(re.findall(r"(\w+): &(\w+Elements)", body[:body.index("{")]))
+    col_var = {v: index_of[e + "::" + c] for v, e, c in re.findall(r"let (\w+) = &main_trace_eval\[(\w+)::(\w+)\.index\(\)\]\.data;", body)}
+    out = []
+    for loop in re.split(r"for vec_row in", body)[1:]:
+        loop = loop[:loop.index("write_frac")]
+        row_var = {v: col_var[c] for v, c in re.findall(r"let (\w+) = (\w+)\[vec_row\];", loop)}
+        num = " ".join(re.search(r"let num\s*=\s*([^;]*);", loop).group(1).split())
+        flag = re.search(r"PackedSecureField::from\((\w+)(?:\[vec_row\])?\)", num)
+        d_idx = None if not flag else (col_var[flag.group(1)] if flag.group(1) in col_var else row_var[flag.group(1)])
+        expr = re.sub(r"PackedSecureField::from\([^)]*\)", "d", num).replace("PackedSecureField::one()", "1")
+        assert re.fullmatch(r"[d1\s+\-]*", expr), expr
+        comb = re.search(r"(\w+)\s*\.combine\(&\[([^\]]*)\]\)", " ".join(loop.split()))
+        vals = [row_var[v.strip()] for v in comb.group(2).split(",") if v.strip()]
+        out.append((eval(expr, {}, {"d": 0}), eval(expr, {}, {"d": 1}), d_idx, ELEMENT_TYPES[params[comb.group(1)]], vals))
+    return out

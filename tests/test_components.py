@@ -264,3 +264,15 @@ def test_air_transcription_against_the_reference_source_text():
                 assert [(v, 0, 0, 0) for v in got_main] == want_main, (comp, row)
                 assert got_rel == [(n % M.P, r, v) for n, r, v in want_rel], (comp, row)
         assert len(got_main) + len(got_rel) == N_CONSTRAINTS[comp]
+
+
+def test_logup_fractions_against_the_reference_source_text():
+    """Where the reference tree exists: numerator, dummy-flag column, relation and value columns of every
+    `col_gen.write_frac(..)` in the seven `interaction_trace_evaluation` functions, read from the Rust source
+    (tests/ref_air_parser.py), equal the table tests/logup_model.py was written from."""
+    import ref_air_parser as R
+    if not R.available():
+        pytest.skip("reference tree not available")
+    for comp in range(13):
+        want = [((1, 0) if sign > 0 else (-1, 0) if d is not None else (-1, -1)) + (d, rel, cols) for sign, d, rel, cols in M.FRACTIONS[comp]]
+        assert [tuple(f) for f in R.parse_fractions(comp)] == want, comp
