@@ -14,6 +14,7 @@
 #include <thread>
 #include "../stwo-brainfuck_b200/csrc/host/prover_sharded.hpp"
 #include "../stwo-brainfuck_b200/csrc/host/verifier.hpp"
+#include <omp.h>
 #include "orc_ops.h"
 
 using namespace sbf;
@@ -151,20 +152,27 @@ struct OrcBackend : Backend {
     return out;
   }
 
+  // Per-column work over columns of very different lengths: long columns one after the other (their transforms split each
+  // layer over the host threads, orc_circle.h), the short ones in parallel over the columns.
+  template <class F>
+  static void for_columns(const std::vector<Col>& v, uint32_t extra_log, F body, bool split = true) {
+    const size_t big = split ? (size_t)1 << 18 : ~(size_t)0;
+    for (size_t i = 0; i < v.size(); i++) if ((H(v[i])->n << extra_log) >= big) body(i);
+#pragma omp parallel for schedule(dynamic)
+    for (size_t i = 0; i < v.size(); i++) if ((H(v[i])->n << extra_log) < big) body(i);
+  }
   void precompute_twiddles(uint32_t root_log) override { orc::precompute_twiddles(orc::coset_half_odds(root_log), tw, itw); }
   void interpolate(const std::vector<Col>& cols) override {
-#pragma omp parallel for schedule(dynamic)
-    for (size_t i = 0; i < cols.size(); i++) orc::interpolate(H(cols[i])->d, lg2(H(cols[i])->n), itw);
+    for_columns(cols, 0, [&](size_t i) { orc::interpolate(H(cols[i])->d, lg2(H(cols[i])->n), itw); });
   }
   std::vector<Col> evaluate(const std::vector<Col>& coeffs, uint32_t log_blowup) override {
     std::vector<Col> out(coeffs.size());
-#pragma omp parallel for schedule(dynamic)
-    for (size_t i = 0; i < coeffs.size(); i++) {
+    for_columns(coeffs, log_blowup, [&](size_t i) {
       HCol* o = new HCol(H(coeffs[i])->n << log_blowup);  // extend(): zero-pad at the end
       memcpy(o->d, H(coeffs[i])->d, H(coeffs[i])->n * 4);
       orc::evaluate(o->d, lg2(o->n), tw);
       out[i] = o;
-    }
+    });
     return out;
   }
   std::vector<sb::QM31> eval_at_point(const std::vector<Col>& polys, const std::vector<QPoint>& pts) override {
@@ -188,8 +196,7 @@ struct OrcBackend : Backend {
   std::vector<Col> interpolate_repeated(const std::vector<Col>& cols, uint32_t rep) override {
     bool bad = false;
     std::vector<Col> out(cols.size());
-#pragma omp parallel for schedule(dynamic)
-    for (size_t i = 0; i < cols.size(); i++) {
+    for_columns(cols, rep, [&](size_t i) {
       HCol* full = expand_values(H(cols[i]), rep);
       orc::interpolate(full->d, lg2(full->n), itw);
       HCol* o = new HCol(H(cols[i])->n);
@@ -199,18 +206,17 @@ struct OrcBackend : Backend {
       }
       delete full;
       out[i] = o;
-    }
+    });
     if (bad) throw std::runtime_error("oracle: a repeated column has a non-zero coefficient off the 2^rep grid");
     return out;
   }
   std::vector<Col> evaluate_repeated(const std::vector<Col>& coeffs, uint32_t rep, uint32_t log_blowup) override {
     std::vector<Col> out(coeffs.size());
-#pragma omp parallel for schedule(dynamic)
-    for (size_t i = 0; i < coeffs.size(); i++) {
+    for_columns(coeffs, rep + log_blowup, [&](size_t i) {
       HCol* o = expand_coeffs(H(coeffs[i]), rep, log_blowup);
       orc::evaluate(o->d, lg2(o->n), tw);
       out[i] = o;
-    }
+    });
     return out;
   }
   std::vector<Col> evaluate_repeated_range(const std::vector<Col>& coeffs, uint32_t rep, uint32_t log_blowup, const std::vector<size_t>& offs,
@@ -221,24 +227,27 @@ struct OrcBackend : Backend {
   }
   std::vector<sb::QM31> eval_at_point_repeated(const std::vector<Col>& polys, const std::vector<uint32_t>& reps, const std::vector<QPoint>& pts) override {
     std::vector<sb::QM31> out(polys.size());
-#pragma omp parallel for schedule(dynamic)
-    for (size_t i = 0; i < polys.size(); i++) {
+    for_columns(polys, 0, [&](size_t i) {
       HCol* full = expand_coeffs(H(polys[i]), reps[i], 0);
       out[i] = sq(orc::eval_at_point(full->d, lg2(full->n), orc::QPt{oq(pts[i].x), oq(pts[i].y)}));
       delete full;
-    }
+    }, false);
     return out;
   }
   std::vector<Col> merkle_commit_repeated(const std::vector<Col>& cols, uint32_t, Hash* root) override { return merkle_commit(cols, root); }
   std::vector<Col> merkle_commit(const std::vector<Col>& cols, Hash* root) override {
-    std::vector<const uint32_t*> p;
-    std::vector<uint32_t> logs;
-    for (Col c : cols) { p.push_back(H(c)->d); logs.push_back(lg2(H(c)->n)); }
-    std::vector<std::vector<uint32_t>> layers;
-    orc::merkle_commit(p.data(), logs.data(), cols.size(), layers);
-    std::vector<Col> out;
-    for (auto& l : layers) out.push_back(new HCol(l.data(), l.size()));
-    if (root) memcpy(root->data(), layers[0].data(), 32);
+    // MerkleProver::commit (orc_blake2s.h merkle_commit), layer by layer straight into the columns that are kept
+    uint32_t max_log = 0;
+    for (Col c : cols) max_log = std::max(max_log, lg2(H(c)->n));
+    std::vector<Col> out(max_log + 1);
+    for (int lg = (int)max_log; lg >= 0; lg--) {
+      std::vector<const uint32_t*> lc;
+      for (Col c : cols) if (lg2(H(c)->n) == (uint32_t)lg) lc.push_back(H(c)->d);  // stable order
+      HCol* o = new HCol((size_t)8 << lg);
+      orc::commit_on_layer(lg, lg == (int)max_log ? nullptr : H(out[lg + 1])->d, lc.data(), lc.size(), o->d);
+      out[lg] = o;
+    }
+    if (root) memcpy(root->data(), H(out[0])->d, 32);
     return out;
   }
   Col commit_layer(uint32_t log, Col prev, const std::vector<Col>& cols) override {
@@ -320,6 +329,7 @@ struct OrcBackend : Backend {
     for (int k = 0; k < 4; k++) out[k] = new HCol(n_out);
     orc::Coset dom = orc::coset_half_odds(log);
     orc::QM31 al = oq(alpha);
+#pragma omp parallel for schedule(static)
     for (size_t i = 0; i < n_out; i++) {
       uint32_t x = dom.at(orc::bit_reverse((uint32_t)(2 * (off + i)), log)).x;
       orc::QM31 a = orc::qfrom(H(src[0])->d[2 * i], H(src[1])->d[2 * i], H(src[2])->d[2 * i], H(src[3])->d[2 * i]);
@@ -333,6 +343,7 @@ struct OrcBackend : Backend {
                                    sb::QM31 alpha) override {
     orc::CircleDomain dom = orc::canonic_domain(log);
     orc::QM31 al = oq(alpha), a2 = orc::qmul(al, al);
+#pragma omp parallel for schedule(static)
     for (size_t i = 0; i < n_out; i++) {
       orc::Pt p = dom.at(orc::bit_reverse((uint32_t)(2 * (off + i)), log));
       orc::QM31 a = orc::qfrom(H(src[0])->d[2 * i], H(src[1])->d[2 * i], H(src[2])->d[2 * i], H(src[3])->d[2 * i]);
@@ -344,41 +355,49 @@ struct OrcBackend : Backend {
     }
   }
   std::array<Col, 4> accumulate_quotients_range(uint32_t log, size_t row_off, size_t n_rows, const std::vector<Col>& cols, sb::QM31 rc,
-                                                const SampleBatchesFlat& b) override {
+                                                const SampleBatchesFlat& f) override {
     std::array<Col, 4> out;
     for (int k = 0; k < 4; k++) out[k] = new HCol(n_rows);
-#pragma omp parallel for schedule(static)
-    for (size_t r = 0; r < n_rows; r++) {
-      std::vector<uint32_t> rowv(cols.size());
-      for (size_t c = 0; c < cols.size(); c++) rowv[c] = H(cols[c])->d[r];
-      orc::Pt p = orc::canonic_domain(log).at(orc::bit_reverse((uint32_t)(row_off + r), log));
-      sb::QM31 v = orc_row_quotient(b, rowv, rc, p);
-      H(out[0])->d[r] = v.a.a; H(out[1])->d[r] = v.a.b; H(out[2])->d[r] = v.b.a; H(out[3])->d[r] = v.b.b;
-    }
-    return out;
-  }
-  // one row of accumulate_quotients with the oracle's own arithmetic (orc_ops.h accumulate_quotients, row form)
-  static sb::QM31 orc_row_quotient(const SampleBatchesFlat& f, const std::vector<uint32_t>& row, sb::QM31 alpha_s, orc::Pt p) {
-    orc::QM31 alpha = oq(alpha_s), acc = orc::qfromm(0);
+    // quotient_constants (pcs/quotients.rs): per sample the line coefficients already multiplied by their power of alpha,
+    // per batch alpha^len — computed once per call, as upstream does, with the oracle's own arithmetic
+    struct LC { orc::QM31 a, b, c; uint32_t col; };
+    struct Batch { orc::CM31 prx, pry, pix, piy; orc::QM31 coef; std::vector<LC> lc; };
+    std::vector<Batch> batches(f.sizes.size());
+    orc::QM31 alpha = oq(rc);
     size_t e = 0;
     for (size_t b = 0; b < f.sizes.size(); b++) {
       const uint32_t* q = &f.points[8 * b];
       orc::QM31 sx = orc::qfrom(q[0], q[1], q[2], q[3]), sy = orc::qfrom(q[4], q[5], q[6], q[7]);
-      orc::CM31 den = orc::csub(orc::cmul(orc::csub(sx.a, orc::CM31{p.x, 0}), sy.b), orc::cmul(orc::csub(sy.a, orc::CM31{p.y, 0}), sx.b));
-      orc::QM31 num = orc::qfromm(0), al = orc::qfromm(1);
-      orc::QM31 c = orc::qsub(orc::qconj(sy), sy);
+      Batch& B = batches[b];
+      B.prx = sx.a; B.pix = sx.b; B.pry = sy.a; B.piy = sy.b;
+      orc::QM31 al = orc::qfromm(1), c = orc::qsub(orc::qconj(sy), sy);
       for (uint32_t j = 0; j < f.sizes[b]; j++, e++) {
         al = orc::qmul(al, alpha);
         orc::QM31 v = orc::qfrom(f.entry_vals[4 * e], f.entry_vals[4 * e + 1], f.entry_vals[4 * e + 2], f.entry_vals[4 * e + 3]);
         orc::QM31 a = orc::qsub(orc::qconj(v), v);
         orc::QM31 bb = orc::qsub(orc::qmul(v, c), orc::qmul(a, sy));
-        orc::QM31 value = orc::qmulm(orc::qmul(al, c), row[f.entry_cols[e]]);
-        orc::QM31 lin = orc::qadd(orc::qmulm(orc::qmul(al, a), p.y), orc::qmul(al, bb));
-        num = orc::qadd(num, orc::qsub(value, lin));
+        B.lc.push_back({orc::qmul(al, a), orc::qmul(al, bb), orc::qmul(al, c), f.entry_cols[e]});
       }
-      acc = orc::qadd(orc::qmul(acc, orc::qpow(alpha, f.sizes[b])), orc::qmulc(num, orc::cinv(den)));
+      B.coef = orc::qpow(alpha, f.sizes[b]);
     }
-    return sq(acc);
+    const orc::CircleDomain dom = orc::canonic_domain(log);
+#pragma omp parallel for schedule(static)
+    for (size_t r = 0; r < n_rows; r++) {
+      orc::Pt p = dom.at(orc::bit_reverse((uint32_t)(row_off + r), log));
+      orc::QM31 acc = orc::qfromm(0);
+      for (const Batch& B : batches) {
+        orc::CM31 den = orc::csub(orc::cmul(orc::csub(B.prx, orc::CM31{p.x, 0}), B.piy), orc::cmul(orc::csub(B.pry, orc::CM31{p.y, 0}), B.pix));
+        orc::QM31 num = orc::qfromm(0);
+        for (const LC& l : B.lc) {
+          orc::QM31 value = orc::qmulm(l.c, H(cols[l.col])->d[r]);
+          orc::QM31 lin = orc::qadd(orc::qmulm(l.a, p.y), l.b);
+          num = orc::qadd(num, orc::qsub(value, lin));
+        }
+        acc = orc::qadd(orc::qmul(acc, B.coef), orc::qmulc(num, orc::cinv(den)));
+      }
+      H(out[0])->d[r] = acc.a.a; H(out[1])->d[r] = acc.a.b; H(out[2])->d[r] = acc.b.a; H(out[3])->d[r] = acc.b.b;
+    }
+    return out;
   }
   Col shift_prev(Col c, uint32_t trace_log) override {
     uint32_t e = trace_log + 1;
@@ -522,6 +541,7 @@ char* orc_prove_json(const char* code, const uint8_t* input, size_t input_len, u
     ProverConfig cfg;
     cfg.log_max_rows = log_max_rows;
     ProveResult r = prove_brainfuck(B, program, vm.trace, cfg);
+    if (getenv("ORC_STAGES")) for (auto& kv : r.times.ms) fprintf(stderr, "orc stage %-28s %10.1f ms\n", kv.first.c_str(), kv.second);
     if (verify) verify_brainfuck(r.proof, cfg);
     return dupstr(proof_to_json(r.proof));
   } catch (const std::exception& e) {

@@ -8,6 +8,7 @@
 // Reference call sites: crates/brainfuck_prover/src/brainfuck_air/mod.rs:500,583,723 (tree_builder.commit).
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -24,25 +25,33 @@ static const uint8_t B2S_SIGMA[10][16] = {
 
 static inline uint32_t rotr32(uint32_t x, int r) { return (x >> r) | (x << (32 - r)); }
 
-// h' = F(h, m, t0, t1, f0, f1)
-static inline void b2s_compress(uint32_t h[8], const uint32_t m[16], uint32_t t0, uint32_t t1, uint32_t f0, uint32_t f1) {
-  uint32_t v[16];
-  for (int i = 0; i < 8; i++) { v[i] = h[i]; v[8 + i] = B2S_IV[i]; }
+// h' = F(h, m, t0, t1, f0, f1).  One definition over the word type W: uint32_t (the scalar form every test pins against
+// RFC 7693 / hashlib) or a vector of 16 u32 lanes hashing 16 independent rows at once, which is how upstream's SimdBackend
+// runs it (`compress16`, core/backend/simd/blake2s.rs).
+template <class W>
+static inline __attribute__((always_inline)) void b2s_compress_t(W h[8], const W m[16], uint32_t t0, uint32_t t1, uint32_t f0, uint32_t f1) {
+  W v[16];
+  for (int i = 0; i < 8; i++) { v[i] = h[i]; v[8 + i] = (h[i] ^ h[i]) + B2S_IV[i]; }
   v[12] ^= t0; v[13] ^= t1; v[14] ^= f0; v[15] ^= f1;
-  auto G = [&](int a, int b, int c, int d, uint32_t x, uint32_t y) {
-    v[a] = v[a] + v[b] + x; v[d] = rotr32(v[d] ^ v[a], 16);
-    v[c] = v[c] + v[d];     v[b] = rotr32(v[b] ^ v[c], 12);
-    v[a] = v[a] + v[b] + y; v[d] = rotr32(v[d] ^ v[a], 8);
-    v[c] = v[c] + v[d];     v[b] = rotr32(v[b] ^ v[c], 7);
-  };
+#define ORC_ROTR(x, r) (((x) >> (r)) | ((x) << (32 - (r))))
+#define ORC_G(a, b, c, d, x, y)                                  \
+  v[a] = v[a] + v[b] + (x); v[d] = ORC_ROTR(v[d] ^ v[a], 16);    \
+  v[c] = v[c] + v[d];       v[b] = ORC_ROTR(v[b] ^ v[c], 12);    \
+  v[a] = v[a] + v[b] + (y); v[d] = ORC_ROTR(v[d] ^ v[a], 8);     \
+  v[c] = v[c] + v[d];       v[b] = ORC_ROTR(v[b] ^ v[c], 7);
   for (int r = 0; r < 10; r++) {
     const uint8_t* s = B2S_SIGMA[r];
-    G(0, 4, 8, 12, m[s[0]], m[s[1]]);   G(1, 5, 9, 13, m[s[2]], m[s[3]]);
-    G(2, 6, 10, 14, m[s[4]], m[s[5]]);  G(3, 7, 11, 15, m[s[6]], m[s[7]]);
-    G(0, 5, 10, 15, m[s[8]], m[s[9]]);  G(1, 6, 11, 12, m[s[10]], m[s[11]]);
-    G(2, 7, 8, 13, m[s[12]], m[s[13]]); G(3, 4, 9, 14, m[s[14]], m[s[15]]);
+    ORC_G(0, 4, 8, 12, m[s[0]], m[s[1]])   ORC_G(1, 5, 9, 13, m[s[2]], m[s[3]])
+    ORC_G(2, 6, 10, 14, m[s[4]], m[s[5]])  ORC_G(3, 7, 11, 15, m[s[6]], m[s[7]])
+    ORC_G(0, 5, 10, 15, m[s[8]], m[s[9]])  ORC_G(1, 6, 11, 12, m[s[10]], m[s[11]])
+    ORC_G(2, 7, 8, 13, m[s[12]], m[s[13]]) ORC_G(3, 4, 9, 14, m[s[14]], m[s[15]])
   }
+#undef ORC_G
+#undef ORC_ROTR
   for (int i = 0; i < 8; i++) h[i] ^= v[i] ^ v[8 + i];
+}
+static inline void b2s_compress(uint32_t h[8], const uint32_t m[16], uint32_t t0, uint32_t t1, uint32_t f0, uint32_t f1) {
+  b2s_compress_t<uint32_t>(h, m, t0, t1, f0, f1);
 }
 
 // Standard unkeyed Blake2s-256 (the `blake2` crate's Blake2s256) — used by the channel.
@@ -80,13 +89,52 @@ static inline void hash_node(const uint32_t* children /*16 words or null*/, cons
 }
 
 // MerkleOps::commit_on_layer: row i hashes children (2i, 2i+1) of prev (if any) then element i of each column.
-static inline void commit_on_layer(uint32_t log_size, const uint32_t* prev, const uint32_t* const* cols, size_t ncols, uint32_t* out) {
-  size_t rows = (size_t)1 << log_size;
-#pragma omp parallel for schedule(static)
-  for (size_t i = 0; i < rows; i++) {
-    std::vector<uint32_t> vals(ncols);
+static inline void commit_on_layer_rows(size_t lo, size_t hi, const uint32_t* prev, const uint32_t* const* cols, size_t ncols, uint32_t* out) {
+  for (size_t i = lo; i < hi; i++) {
+    uint32_t small[64];
+    std::vector<uint32_t> big;
+    uint32_t* vals = small;
+    if (ncols > 64) { big.resize(ncols); vals = big.data(); }
     for (size_t c = 0; c < ncols; c++) vals[c] = cols[c][i];
-    hash_node(prev ? prev + 16 * i : nullptr, vals.data(), ncols, out + 8 * i);
+    hash_node(prev ? prev + 16 * i : nullptr, vals, ncols, out + 8 * i);
+  }
+}
+// The same function on 16 consecutive rows at a time, one row per vector lane (upstream: SimdBackend::commit_on_layer over
+// compress16).  Compiled for AVX-512 and used when the host has it; ORC_SCALAR=1 forces the scalar definition above
+// (tests/test_oracle.py compares the two).
+typedef uint32_t b2s_v16 __attribute__((vector_size(64), aligned(4)));
+__attribute__((target("avx512f"))) static void commit_on_layer_rows16(size_t lo, size_t hi, const uint32_t* prev, const uint32_t* const* cols,
+                                                                      size_t ncols, uint32_t* out) {
+  for (size_t i = lo; i < hi; i += 16) {
+    b2s_v16 st[8], m[16];
+    for (int k = 0; k < 8; k++) st[k] = b2s_v16{};
+    if (prev) {
+      for (int j = 0; j < 16; j++) for (int r = 0; r < 16; r++) m[j][r] = prev[16 * (i + r) + j];
+      b2s_compress_t<b2s_v16>(st, m, 0, 0, 0, 0);
+    }
+    for (size_t o = 0; o < ncols; o += 16) {
+      size_t k = ncols - o < 16 ? ncols - o : 16;
+      for (size_t j = 0; j < 16; j++) {
+        if (j < k) memcpy(&m[j], cols[o + j] + i, 64);
+        else m[j] = b2s_v16{};
+      }
+      b2s_compress_t<b2s_v16>(st, m, 0, 0, 0, 0);
+    }
+    for (int k = 0; k < 8; k++) for (int r = 0; r < 16; r++) out[8 * (i + r) + k] = st[k][r];
+  }
+}
+static inline bool b2s_use_simd() {
+  static const bool on = __builtin_cpu_supports("avx512f") && !getenv("ORC_SCALAR");
+  return on;
+}
+static inline void commit_on_layer(uint32_t log_size, const uint32_t* prev, const uint32_t* const* cols, size_t ncols, uint32_t* out) {
+  const size_t rows = (size_t)1 << log_size, chunk = 256;
+  if (rows < chunk) { commit_on_layer_rows(0, rows, prev, cols, ncols, out); return; }
+  const bool simd = b2s_use_simd();
+#pragma omp parallel for schedule(static)
+  for (size_t c = 0; c < rows / chunk; c++) {
+    if (simd) commit_on_layer_rows16(c * chunk, (c + 1) * chunk, prev, cols, ncols, out);
+    else commit_on_layer_rows(c * chunk, (c + 1) * chunk, prev, cols, ncols, out);
   }
 }
 

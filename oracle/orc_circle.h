@@ -24,12 +24,29 @@ static inline Pt padd(Pt p, Pt q) {
 static inline Pt pconj(Pt p) { return {p.x, mneg(p.y)}; }
 static inline uint32_t double_x(uint32_t x) { return msub(mmul(2, mmul(x, x)), 1); }
 
-// G^idx, idx taken mod 2^31.
-static inline Pt point_at_index(uint32_t idx) {
+// G^idx, idx taken mod 2^31: the plain square-and-multiply ladder (the definition) ...
+static inline Pt point_at_index_ladder(uint32_t idx) {
   idx &= 0x7fffffffu;
   Pt r = {1, 0}, b = CIRCLE_GEN;
   while (idx) { if (idx & 1) r = padd(r, b); b = padd(b, b); idx >>= 1; }
   return r;
+}
+// ... and the same element from four 256-entry tables of G^(d * 256^k) (three group additions instead of up to 61): the
+// row loops below call this once per domain row, as upstream iterates its domains incrementally instead of exponentiating.
+struct PointTables {
+  Pt t[4][256];
+  PointTables() {
+    for (int k = 0; k < 4; k++) {
+      Pt base = point_at_index_ladder(1u << (8 * k));
+      t[k][0] = {1, 0};
+      for (int d = 1; d < 256; d++) t[k][d] = padd(t[k][d - 1], base);
+    }
+  }
+};
+static inline Pt point_at_index(uint32_t idx) {
+  static const PointTables T;  // thread-safe static initialisation
+  idx &= 0x7fffffffu;
+  return padd(padd(T.t[0][idx & 255], T.t[1][(idx >> 8) & 255]), padd(T.t[2][(idx >> 16) & 255], T.t[3][idx >> 24]));
 }
 
 struct Coset {
@@ -104,6 +121,21 @@ static inline void fft_layer(uint32_t* v, uint32_t layer, size_t h, uint32_t t, 
     else { uint32_t m = mmul(b, t); v[i0] = madd(a, m); v[i1] = msub(a, m); }
   }
 }
+// One whole layer: butterfly k pairs (h 2^(layer+1) + l, + 2^layer) with h = k >> layer, l = k mod 2^layer, twiddle tw(h).
+// Large layers are split over the host threads when the caller is not already inside a parallel region (a transform of
+// few long columns, e.g. the four composition coordinates).
+template <class TW>
+static inline void fft_whole_layer(uint32_t* v, uint32_t log, uint32_t layer, bool inverse, TW tw) {
+  const size_t half = (size_t)1 << (log - 1), span = (size_t)1 << layer;
+#pragma omp parallel for schedule(static) if (half >= 32768)
+  for (size_t k = 0; k < half; k++) {
+    size_t h = k >> layer, l = k & (span - 1);
+    size_t i0 = (h << (layer + 1)) + l, i1 = i0 + span;
+    uint32_t a = v[i0], b = v[i1], t = tw(h);
+    if (inverse) { v[i0] = madd(a, b); v[i1] = mmul(msub(a, b), t); }
+    else { uint32_t m = mmul(b, t); v[i0] = madd(a, m); v[i1] = msub(a, m); }
+  }
+}
 
 // Circle-layer twiddles from the first line layer: [x, y] -> [y, -y, -x, x].
 static inline uint32_t circle_twiddle(const uint32_t* line0, size_t h) {
@@ -127,12 +159,13 @@ static inline void interpolate(uint32_t* v, uint32_t log, const std::vector<uint
     uint32_t iy = minv(canonic_domain(2).at(0).y);
     fft_layer(v, 0, 0, iy, true); fft_layer(v, 0, 1, mneg(iy), true);
   } else
-  for (size_t h = 0; h < n / 2; h++) fft_layer(v, 0, h, circle_twiddle(lines[0], h), true);
+  fft_whole_layer(v, log, 0, true, [&](size_t h) { return circle_twiddle(lines[0], h); });
   for (uint32_t layer = 1; layer < log; layer++) {
     const uint32_t* t = lines[layer - 1];
-    for (size_t h = 0; h < (n >> (layer + 1)); h++) fft_layer(v, layer, h, t[h], true);
+    fft_whole_layer(v, log, layer, true, [&](size_t h) { return t[h]; });
   }
   uint32_t ninv = minv(mpow(2, log));
+#pragma omp parallel for schedule(static) if (n >= 65536)
   for (size_t i = 0; i < n; i++) v[i] = mmul(v[i], ninv);
 }
 
@@ -149,14 +182,14 @@ static inline void evaluate(uint32_t* v, uint32_t log, const std::vector<uint32_
   auto lines = domain_line_twiddles(tw, log - 1);
   for (uint32_t layer = log - 1; layer >= 1; layer--) {
     const uint32_t* t = lines[layer - 1];
-    for (size_t h = 0; h < (n >> (layer + 1)); h++) fft_layer(v, layer, h, t[h], false);
+    fft_whole_layer(v, log, layer, false, [&](size_t h) { return t[h]; });
   }
   if (log == 2) {
     uint32_t y = canonic_domain(2).at(0).y;
     fft_layer(v, 0, 0, y, false); fft_layer(v, 0, 1, mneg(y), false);
     return;
   }
-  for (size_t h = 0; h < n / 2; h++) fft_layer(v, 0, h, circle_twiddle(lines[0], h), false);
+  fft_whole_layer(v, log, 0, false, [&](size_t h) { return circle_twiddle(lines[0], h); });
 }
 
 // Secure-field circle point.
