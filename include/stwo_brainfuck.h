@@ -1,7 +1,8 @@
 /* stwo_brainfuck.h — prove / verify entry points of libstwo_cuda.so: the host orchestrator that stands in for
  * `brainfuck_prover prove|verify` (crates/brainfuck_prover/src/bin/brainfuck_prover.rs:79-152) and for
  * prove_brainfuck / verify_brainfuck (crates/brainfuck_prover/src/brainfuck_air/mod.rs:471-797).
- * The VM and the table builders run on the host; every Backend operation goes through the C ABI of stwo_cuda.h. */
+ * The VM runs on the host; the 13 tables are built on the device from the uploaded register rows (sc_trace_*, stwo_cuda.h);
+ * every Backend operation goes through the C ABI of stwo_cuda.h. */
 #ifndef STWO_BRAINFUCK_H
 #define STWO_BRAINFUCK_H
 #include "stwo_cuda.h"
@@ -17,6 +18,9 @@ const char* sbf_last_error(void);
  * same for every program, brainfuck_air/mod.rs:453-464,493-500) on the context between proofs.  The reference rebuilds it
  * in every proof; the proof bytes are the same either way.  sbf_preprocessed_cache_clear drops it (sc_ctx_destroy does too). */
 #define SBF_CACHE_PREPROCESSED 8u
+/* flags: build the 13 tables with the host builders (csrc/host/tables.hpp) and upload the finished columns, as round 1 did,
+ * instead of building them on the device from the register rows; same proof bytes (A/B measurements, parity tests). */
+#define SBF_HOST_TABLES 16u
 int32_t sbf_preprocessed_cache_clear(sc_ctx* ctx);
 int32_t sbf_prove(sc_ctx* ctx, const char* code, const uint8_t* input, size_t input_len, uint32_t log_max_rows, uint32_t flags,
                   sbf_proof** out);

@@ -139,6 +139,34 @@ int32_t sc_secure_powers(const uint32_t felt[4], uint32_t n, uint32_t* out /* n 
 /* ---- GrindOps<Blake2sChannel>::grind: smallest nonce with >= pow_bits trailing zeros (upstream simd/grind.rs) ---- */
 int32_t sc_grind(sc_ctx* ctx, const uint32_t digest[8], uint32_t pow_bits, uint64_t* nonce_out);
 
+/* ---- Device-side table building: the 13 `trace_evaluation`s of crates/brainfuck_prover/src/brainfuck_air/
+ * mod.rs:511-547 (memory/table.rs:85-117,249-318; instruction/table.rs:85-110,250-281; program/table.rs:36-46; processor/
+ * table.rs:117-142,195-207; processor/instructions/table.rs:293-328; .../jump/table.rs:264-297; .../end_of_execution/table.rs:
+ * 71-77) from the VM's register rows, in the lane-compact form the *_repeated entry points take (one word per table row).
+ * regs: n_steps x 7 words {clk, ip, ci, ni, mp, mv, mvi} (crates/brainfuck_vm/src/registers.rs:5-21), in clk order; program:
+ * the compiled program words.  The upload does not wait (host memory must stay valid until the next synchronising call;
+ * pinned memory from sc_host_arena_alloc makes it a DMA beside queued kernels).  fill_mvi != 0: mvi is computed on the
+ * device and the input's seventh word is ignored.
+ * stats (16 words): [0] steps, [1] Memory rows before padding, [2..9] steps per opcode ] [ , < - . + > (with a successor),
+ * [10] rows with ci = 0, [11] index of the first, [12] max mp, [13] max ip — kept by the VM while it runs, or computed by
+ * sc_trace_stats_host.  They fix every table size, so no device round trip is needed before the columns are allocated;
+ * the kernels cross-check them (sc_trace_status).
+ * sc_trace_build_tables: cols_out receives the 128 main-trace columns in (component, column) order, log_sizes_out the 13
+ * column log sizes (rows x 16 lanes).  SC_EINVAL "component too large: <name>" when a table exceeds 2^(log_max_rows-4) rows. ---- */
+typedef struct sc_trace sc_trace;
+int32_t sc_trace_stats_host(const uint32_t* regs, uint64_t n_steps, uint64_t stats_out[16]);
+int32_t sc_trace_upload(sc_ctx* ctx, const uint32_t* regs, uint64_t n_steps, const uint32_t* program, uint64_t program_len,
+                        int32_t fill_mvi, sc_trace** out);
+int32_t sc_trace_build_tables(sc_ctx* ctx, sc_trace* trace, const uint64_t stats[16], uint32_t log_max_rows, sc_col** cols_out,
+                              uint32_t log_sizes_out[13]);
+int32_t sc_trace_status(sc_ctx* ctx, const sc_trace* trace, uint32_t* flags);
+int32_t sc_trace_free(sc_ctx* ctx, sc_trace* trace);
+
+/* ---- measurement only: integer-pipe micro-benchmark, the measured peak of the Blake2s roofline ("INT32 ALU
+ * pipe ... measure").  kind 0 LOP3, 1 SHF, 2 PRMT, 3 IADD3, 4 IMAD, 5 LOP3+IMAD interleaved, 6 the Blake2s G mix.
+ * out = {ALU-pipe lane-ops/clk/SM, FMA-pipe lane-ops/clk/SM, kernel ms, #SMs}. ---- */
+int32_t sc_microbench_int(sc_ctx* ctx, int32_t kind, uint32_t iters, double out[4]);
+
 /* ---- constraint_framework pieces the reference uses concretely at SimdBackend ---- */
 /* gen_is_first::<B>(log_size) — brainfuck_air/mod.rs:497. */
 int32_t sc_gen_is_first(sc_ctx* ctx, uint32_t log_size, sc_col** out);

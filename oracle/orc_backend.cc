@@ -595,7 +595,11 @@ char* orc_prove_sharded_json(const char* code, const uint8_t* input, size_t inpu
           OrcBackend B;
           B.my_rank = r;
           if (world > 1) B.comm = &comm;
-          ProveResult res = prove_brainfuck_sharded(B, program, TraceSource([&]() -> const std::vector<Registers>& { return vm.trace; }), cfg);
+          ProveResult res = prove_brainfuck_sharded(B, program, TraceSource([&] {
+            TraceInput in;
+            in.regs = vm.trace.data(); in.n = vm.trace.size(); in.stats = trace_stats(in.regs, in.n);   // recomputed, not the VM's own
+            return in;
+          }), cfg);
           if (verify) verify_brainfuck(res.proof, cfg);
           json[r] = proof_to_json(res.proof);
         } catch (const std::exception& e) {
@@ -638,6 +642,33 @@ char* orc_vm_summary(const char* code, const uint8_t* input, size_t input_len) {
   } catch (const std::exception& e) {
     g_err = e.what();
     return nullptr;
+  }
+}
+
+// The VM's register rows (n x 7 words, registers.rs order) and two statements of their statistics: the counters the VM keeps
+// while it runs and trace_stats() recomputed from the finished trace (16 words each, layout of sc_trace_stats_host).
+// out == NULL: returns the number of rows only.
+size_t orc_vm_registers(const char* code, const uint8_t* input, size_t input_len, uint32_t* out, uint64_t* stats_vm, uint64_t* stats_recomputed,
+                        uint32_t* program_out, size_t* program_len) {
+  try {
+    std::vector<uint32_t> program = compile(code);
+    Machine vm(program, std::vector<uint8_t>(input, input + input_len));
+    vm.execute();
+    if (program_len) *program_len = program.size();
+    if (program_out) memcpy(program_out, program.data(), program.size() * 4);
+    auto pack = [](const TraceStats& st, uint64_t* w) {
+      memset(w, 0, 16 * sizeof(uint64_t));
+      w[0] = st.steps; w[1] = st.memory_rows;
+      for (int k = 0; k < 8; k++) w[2 + k] = st.op_count[k];
+      w[10] = st.zero_ci; w[11] = st.zero_ci_index; w[12] = st.max_mp; w[13] = st.max_ip;
+    };
+    if (stats_vm) pack(vm.stats, stats_vm);
+    if (stats_recomputed) pack(trace_stats(vm.trace.data(), vm.trace.size()), stats_recomputed);
+    if (out) memcpy(out, vm.trace.data(), vm.trace.size() * sizeof(Registers));
+    return vm.trace.size();
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 0;
   }
 }
 

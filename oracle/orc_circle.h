@@ -171,7 +171,6 @@ static inline void interpolate(uint32_t* v, uint32_t log, const std::vector<uint
 
 // evaluate: coefficients (length 2^log) -> bit-reversed evaluations on canonic_domain(log), in place.
 static inline void evaluate(uint32_t* v, uint32_t log, const std::vector<uint32_t>& tw) {
-  size_t n = (size_t)1 << log;
   if (log == 0) return;
   if (log == 1) {
     Pt p = canonic_domain(1).at(0);

@@ -66,6 +66,7 @@ ABI_SYMBOLS = [
     "sc_fold_circle_into_line", "sc_accumulate_quotients", "sc_accumulate", "sc_secure_powers", "sc_grind",
     "sc_gen_is_first", "sc_is_first_coeffs", "sc_prefix_sum_bitrev", "sc_logup_generate", "sc_eval_constraints", "sc_gather", "sc_ctx_profile", "sc_ctx_profile_report", "sc_ctx_profile_timeline", "sc_ctx_mark", "sc_ctx_release_since", "sc_ctx_live_columns", "sc_event_record", "sc_event_elapsed", "sc_event_free", "sc_interpolate_repeated", "sc_evaluate_repeated", "sc_eval_at_point_repeated",
     "sc_merkle_commit_layer_repeated", "sc_merkle_commit_repeated", "sc_ctx_attach", "sc_ctx_attached",
+    "sc_microbench_int", "sc_trace_stats_host", "sc_trace_upload", "sc_trace_build_tables", "sc_trace_status", "sc_trace_free",
 ]
 PROVER_SYMBOLS = ["sbf_prove", "sbf_verify", "sbf_proof_json", "sbf_proof_report", "sbf_proof_output", "sbf_string_free",
                   "sbf_proof_free", "sbf_proof_tamper", "sbf_last_error", "sbf_preprocessed_cache_clear"]
@@ -118,7 +119,8 @@ class Column:
 
     def free(self) -> None:
         if self._h is not None:
-            self._b._lib.sc_col_free(self._b._ctx, self._h)
+            if self._b._ctx is not None:   # sc_ctx_destroy has already released every column of a closed backend
+                self._b._lib.sc_col_free(self._b._ctx, self._h)
             self._h = None
 
     def __del__(self):
@@ -353,6 +355,48 @@ class CudaBackend:
         self._ck(self._lib.sc_grind(self._ctx, _ptr(d), ctypes.c_uint32(pow_bits), ctypes.byref(nonce)))
         return int(nonce.value)
 
+    # -- device-side table building (the 13 `trace_evaluation`s, brainfuck_air/mod.rs:511-547)
+    def build_tables(self, registers, program, log_max_rows: int = 24, fill_mvi: bool = False, stats=None):
+        """registers: (n, 7) words {clk, ip, ci, ni, mp, mv, mvi} in clk order; program: compiled program words.
+        Returns (tables, log_sizes): tables[c] = list of lane-compact Columns (one word per table row) of component c."""
+        regs = np.ascontiguousarray(registers, dtype=np.uint32).reshape(-1, 7)
+        prog = _np_u32(program)
+        if stats is None:
+            st = (ctypes.c_uint64 * 16)()
+            self._ck(self._lib.sc_trace_stats_host(_ptr(regs), ctypes.c_uint64(regs.shape[0]), st))
+        else:
+            st = (ctypes.c_uint64 * 16)(*[int(x) for x in stats])
+        t = _vp()
+        self._ck(self._lib.sc_trace_upload(self._ctx, _ptr(regs), ctypes.c_uint64(regs.shape[0]), _ptr(prog), ctypes.c_uint64(prog.size),
+                                           ctypes.c_int32(1 if fill_mvi else 0), ctypes.byref(t)))
+        cols = (ctypes.c_void_p * 128)()
+        logs = (ctypes.c_uint32 * 13)()
+        r = self._lib.sc_trace_build_tables(self._ctx, t, st, ctypes.c_uint32(log_max_rows), cols, logs)
+        if r:
+            self._lib.sc_trace_free(self._ctx, t)
+            self._ck(r)
+        flags = ctypes.c_uint32()
+        r = self._lib.sc_trace_status(self._ctx, t, ctypes.byref(flags))
+        self._lib.sc_trace_free(self._ctx, t)
+        self._ck(r)
+        n_main = [8, 8, 4, 9, 13, 13, 11, 11, 11, 11, 11, 11, 7]
+        tables, k = [], 0
+        for c in range(13):
+            tables.append([Column(self, ctypes.c_void_p(cols[k + j])) for j in range(n_main[c])])
+            k += n_main[c]
+        if flags.value:
+            for tb in tables:
+                for col in tb:
+                    col.free()
+            raise BackendError(f"device table building: the trace disagrees with its statistics (flags {flags.value})")
+        return tables, [int(x) for x in logs]
+
+    def microbench_int(self, kind: int, iters: int = 4096) -> dict:
+        """Integer-pipe micro-benchmark (csrc/microbench.cu): lane-operations per clock per SM on the ALU and FMA pipes."""
+        out = (ctypes.c_double * 4)()
+        self._ck(self._lib.sc_microbench_int(self._ctx, ctypes.c_int32(kind), ctypes.c_uint32(iters), out))
+        return {"alu_ops_per_clk_sm": out[0], "fma_ops_per_clk_sm": out[1], "ms": out[2], "n_sm": int(out[3])}
+
     # -- constraint_framework helpers
     def gen_is_first(self, log_size: int) -> Column:
         h = _vp()
@@ -452,7 +496,7 @@ class Proof:
 
 
 def prove_brainfuck(backend: CudaBackend, code: str, stdin: bytes = b"", log_max_rows: int = 24, overlap_host: bool = True,
-                    cache_preprocessed: bool = False, twiddle_cache: bool = True) -> Proof:
+                    cache_preprocessed: bool = False, twiddle_cache: bool = True, host_tables: bool = False) -> Proof:
     """prove_brainfuck(&Machine) of crates/brainfuck_prover/src/brainfuck_air/mod.rs:471-735: runs the VM on the host and the
     whole proof on the device behind `backend`.  overlap_host=False builds the host tables before any device work (used by
     bench.py to time the device path alone); cache_preprocessed=True keeps the program-independent preprocessed tree on
@@ -462,7 +506,7 @@ def prove_brainfuck(backend: CudaBackend, code: str, stdin: bytes = b"", log_max
     lib = backend._lib
     h = _vp()
     code_b = code.encode() if isinstance(code, str) else code
-    flags = (0 if overlap_host else 1) | (8 if cache_preprocessed else 0) | (0 if twiddle_cache else 2)
+    flags = (0 if overlap_host else 1) | (8 if cache_preprocessed else 0) | (0 if twiddle_cache else 2) | (16 if host_tables else 0)
     rc = lib.sbf_prove(backend._ctx, ctypes.c_char_p(code_b), ctypes.c_char_p(stdin), ctypes.c_size_t(len(stdin)),
                        ctypes.c_uint32(log_max_rows), ctypes.c_uint32(flags), ctypes.byref(h))
     if rc != 0:

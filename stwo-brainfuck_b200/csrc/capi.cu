@@ -15,7 +15,10 @@
 
 using namespace sb;
 
-namespace sb { unsigned long long g_launch_count = 0; }
+namespace sb {
+static unsigned long long g_launch_orphans = 0;  // launches made before any context was entered on the thread
+thread_local unsigned long long* g_launch_counter = &g_launch_orphans;
+}
 thread_local std::string g_sc_err;
 
 #include "capi_internal.cuh"
@@ -52,6 +55,11 @@ int32_t sc_ctx_destroy(sc_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->st);
   for (auto& a : ctx->attached) if (a.p && a.dtor) { a.dtor(ctx, a.p); a.p = nullptr; }  // may free columns: the context is still whole
+  {  // columns the caller never freed die with their context (their handles are invalid from here on)
+    std::vector<sc_col*> left;
+    for (auto& kv : ctx->live) left.push_back(kv.second);
+    for (sc_col* c : left) sc_col_free(ctx, c);
+  }
   cudaStreamSynchronize(ctx->st);
   cudaFreeHost(ctx->h_ring);
   for (auto& b : ctx->arena) cudaFreeHost(b.p);
@@ -73,7 +81,7 @@ int32_t sc_ctx_attach(sc_ctx* ctx, uint32_t slot, void* p, sc_attach_dtor dtor) 
   return SC_OK;
 }
 void* sc_ctx_attached(sc_ctx* ctx, uint32_t slot) { return ctx && slot < 4 ? ctx->attached[slot].p : nullptr; }
-uint64_t sc_ctx_launch_count(const sc_ctx*) { return g_launch_count; }
+uint64_t sc_ctx_launch_count(const sc_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int32_t sc_ctx_profile(sc_ctx* ctx, int32_t enable) {
   ENTER();
   ctx->profiling = enable != 0;
@@ -792,6 +800,19 @@ int32_t sc_secure_powers(const uint32_t felt[4], uint32_t n, uint32_t* out) {
     out[4 * i] = acc.a.a; out[4 * i + 1] = acc.a.b; out[4 * i + 2] = acc.b.a; out[4 * i + 3] = acc.b.b;
     acc = q_mul(acc, f);
   }
+  return SC_OK;
+}
+// Integer-pipe micro-benchmark (microbench.cu): the measured peak the Merkle roofline is reported against.
+int32_t sc_microbench_int(sc_ctx* ctx, int32_t kind, uint32_t iters, double out[4]) {
+  ENTER();
+  if (!out || kind < 0 || kind > 6 || iters == 0) return fail(SC_EINVAL, "microbench_int: bad argument");
+  int n_sm = 0;
+  CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
+  void* scratch = nullptr;
+  CK(cudaMalloc(&scratch, 16 * (size_t)n_sm + 64));
+  int e = launch_int_pipe_bench(kind, iters, n_sm, scratch, out, ctx->st);
+  cudaFree(scratch);
+  CKL(e);
   return SC_OK;
 }
 int32_t sc_grind(sc_ctx* ctx, const uint32_t digest[8], uint32_t pow_bits, uint64_t* nonce_out) {

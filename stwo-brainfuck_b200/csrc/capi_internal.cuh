@@ -30,6 +30,7 @@ struct sc_ctx {
   cudaStream_t st;
   bool own_stream;
   bool poisoned;
+  unsigned long long launches = 0;  // kernels launched through this context (sc_ctx_launch_count)
   // staging ring for small host->device tables (pointer arrays, task tables)
   uint8_t* h_ring;
   uint8_t* d_ring;
@@ -97,6 +98,7 @@ static inline int32_t fail(int32_t code, const std::string& m) { g_sc_err = m; r
 #define ENTER_NOJOIN()                                                                             \
   if (!ctx) return fail(SC_EINVAL, "null context");                                                \
   if (ctx->poisoned) return fail(SC_ECUDA, "context unusable after an earlier CUDA error");        \
+  ::sb::g_launch_counter = &ctx->launches;                                                         \
   CK(cudaSetDevice(ctx->device))
 #define ENTER()                                                                                    \
   ENTER_NOJOIN();                                                                                  \

@@ -17,7 +17,7 @@ struct CudaBackendImpl : Backend {
   sc_ctx* ctx;
   const sc_twiddles* tw = nullptr;
   explicit CudaBackendImpl(sc_ctx* c) : ctx(c) {}
-  ~CudaBackendImpl() override { if (own_tw) sc_twiddles_free(ctx, own_tw); }
+  ~CudaBackendImpl() override { if (own_tw) sc_twiddles_free(ctx, own_tw); if (pending_trace) sc_trace_free(ctx, pending_trace); }
   static void ck(int32_t r) { if (r) throw std::runtime_error(std::string("stwo_cuda: ") + sc_last_error()); }
   static sc_col* h(Col c) { return (sc_col*)c; }
   const char* name() const override { return "cuda"; }
@@ -33,6 +33,43 @@ struct CudaBackendImpl : Backend {
     }
   } pinned;
   HostArena* host_arena() override { pinned.ctx = ctx; sc_host_arena_reset(ctx); return &pinned; }
+  // The 13 tables are built on the device from the uploaded register rows (csrc/tables.cu).  host_tables = true falls back
+  // to the host builders of tables.hpp (SBF_HOST_TABLES: A/B measurements and the table parity tests).
+  bool host_tables = false;
+  sc_trace* pending_trace = nullptr;
+  void trace_tables(const TraceInput& in, const std::vector<uint32_t>& code, uint32_t log_max_rows,
+                    std::vector<std::vector<Col>>& compact, uint32_t log_size[N_COMPONENTS]) override {
+    if (host_tables) { Backend::trace_tables(in, code, log_max_rows, compact, log_size); return; }
+    uint64_t rows[N_COMPONENTS];
+    table_rows_from_stats(in.stats, code.size(), rows);   // throws InvalidEndOfExecution / empty trace like the host builders
+    uint64_t w[16] = {0};
+    w[0] = in.stats.steps; w[1] = in.stats.memory_rows;
+    for (int k = 0; k < 8; k++) w[2 + k] = in.stats.op_count[k];
+    w[10] = in.stats.zero_ci; w[11] = in.stats.zero_ci_index; w[12] = in.stats.max_mp; w[13] = in.stats.max_ip;
+    sc_trace* t = nullptr;
+    ck(sc_trace_upload(ctx, (const uint32_t*)in.regs, in.n, code.data(), code.size(), in.mvi_filled ? 0 : 1, &t));
+    std::vector<sc_col*> cols(128, nullptr);
+    if (sc_trace_build_tables(ctx, t, w, log_max_rows, cols.data(), log_size)) {
+      std::string msg = sc_last_error();
+      sc_trace_free(ctx, t);
+      throw std::runtime_error(msg);
+    }
+    if (pending_trace) sc_trace_free(ctx, pending_trace);
+    pending_trace = t;
+    compact.assign(N_COMPONENTS, {});
+    size_t k = 0;
+    for (int c = 0; c < N_COMPONENTS; c++) for (int j = 0; j < N_MAIN_COLS[c]; j++) compact[c].push_back(cols[k++]);
+  }
+  // called by the driver right after a read-back it needs anyway: the flags the table kernels raised
+  void check_tables() override {
+    if (!pending_trace) return;
+    uint32_t flags = 0;
+    int32_t r = sc_trace_status(ctx, pending_trace, &flags);
+    sc_trace_free(ctx, pending_trace);
+    pending_trace = nullptr;
+    ck(r);
+    if (flags) throw std::runtime_error("device table building: the trace disagrees with its statistics (flags " + std::to_string(flags) + ")");
+  }
   Col broadcast16(Col c) override { sc_col* o; ck(sc_col_broadcast16(ctx, h(c), &o)); return o; }
   Col zeros(size_t n) override { sc_col* c; ck(sc_col_zeros(ctx, n, &c)); return c; }
   size_t len(Col c) override { return sc_col_len(h(c)); }
@@ -219,6 +256,27 @@ struct CudaBackendImpl : Backend {
   }
 };
 
+// Runs the VM.  Device-side table building wants the register rows in pinned memory (the upload is then a DMA beside the
+// kernels already queued) and fills mvi itself, so the machine writes straight into the context's host arena and skips its
+// batched inversions.  With host tables the trace stays in the machine's own vector.
+TraceInput run_machine(sc_ctx* ctx, Machine& vm, uint32_t log_max_rows, bool host_tables, double& vm_ms) {
+  auto t0 = std::chrono::steady_clock::now();
+  if (!host_tables) {
+    const uint32_t lg = log_max_rows >= LOG_N_LANES && log_max_rows <= 28 ? log_max_rows - LOG_N_LANES : 24;
+    const size_t cap = ((size_t)1 << lg) + 1;   // one more row than the Processor table can take: the size check reports it
+    void* buf = nullptr;
+    sc_host_arena_reset(ctx);
+    if (sc_host_arena_alloc(ctx, cap * sizeof(Registers), &buf)) throw std::runtime_error(sc_last_error());
+    vm.sink = (Registers*)buf; vm.sink_cap = cap;
+    vm.skip_inverses = true;
+  }
+  vm.execute();
+  vm_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  TraceInput in;
+  in.regs = vm.rows(); in.n = vm.n_rows(); in.stats = vm.stats; in.mvi_filled = !vm.skip_inverses;
+  return in;
+}
+
 thread_local std::string g_sbf_err;
 char* dup_string(const std::string& s) {
   char* p = (char*)malloc(s.size() + 1);
@@ -276,14 +334,11 @@ int32_t sbf_prove(sc_ctx* ctx, const char* code, const uint8_t* input, size_t in
     std::vector<uint32_t> program = compile(code);
     Machine vm(program, std::vector<uint8_t>(input, input + input_len));
     double vm_ms = 0;
+    const bool host_tables = (flags & 16u) != 0;   // SBF_HOST_TABLES
     // the VM runs when the prover asks for the trace: after the preprocessed phase is enqueued unless SBF_NO_OVERLAP
-    TraceSource run_vm = [&]() -> const std::vector<Registers>& {
-      auto t0 = std::chrono::steady_clock::now();
-      vm.execute();
-      vm_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-      return vm.trace;
-    };
+    TraceSource run_vm = [&]() { return run_machine(ctx, vm, log_max_rows, host_tables, vm_ms); };
     CudaBackendImpl B(ctx);
+    B.host_tables = host_tables;
     ProverConfig cfg;
     cfg.log_max_rows = log_max_rows;
     cfg.overlap_host = !(flags & 1u);  // SBF_NO_OVERLAP: VM run and tables before any device work (bench.py's device-path timing)
@@ -293,7 +348,7 @@ int32_t sbf_prove(sc_ctx* ctx, const char* code, const uint8_t* input, size_t in
     double prove_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
     sbf_proof* p = new sbf_proof{std::move(r.proof), cfg, "", vm.output};
     std::ostringstream o;
-    o << "{\"steps\":" << vm.trace.size() << ",\"vm_ms\":" << vm_ms << ",\"prove_ms\":" << prove_ms << ",\"log_sizes\":[";
+    o << "{\"steps\":" << vm.n_rows() << ",\"vm_ms\":" << vm_ms << ",\"prove_ms\":" << prove_ms << ",\"log_sizes\":[";
     for (int c = 0; c < N_COMPONENTS; c++) o << (c ? "," : "") << p->proof.log_size[c];
     o << "],\"stages_ms\":{";
     for (size_t i = 0; i < r.times.ms.size(); i++) o << (i ? "," : "") << "\"" << r.times.ms[i].first << "\":" << r.times.ms[i].second;
@@ -319,13 +374,11 @@ int32_t sbf_prove_sharded(sc_ctx* ctx, sc_comm* comm, const char* code, const ui
     std::vector<uint32_t> program = compile(code);
     Machine vm(program, std::vector<uint8_t>(input, input + input_len));
     double vm_ms = 0;
-    TraceSource run_vm = [&]() -> const std::vector<Registers>& {  // called on the prover's host thread, beside the preprocessed phase
-      auto t0 = std::chrono::steady_clock::now();
-      vm.execute();
-      vm_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-      return vm.trace;
-    };
+    const bool host_tables = (flags & 16u) != 0;   // SBF_HOST_TABLES
+    // called on the prover's host thread, beside the preprocessed phase
+    TraceSource run_vm = [&]() { return run_machine(ctx, vm, log_max_rows, host_tables, vm_ms); };
     CudaBackendImpl B(ctx);
+    B.host_tables = host_tables;
     B.comm = comm;
     ProverConfig cfg;
     cfg.log_max_rows = log_max_rows;
@@ -335,7 +388,7 @@ int32_t sbf_prove_sharded(sc_ctx* ctx, sc_comm* comm, const char* code, const ui
     double prove_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
     sbf_proof* p = new sbf_proof{std::move(r.proof), cfg, "", vm.output};
     std::ostringstream o;
-    o << "{\"steps\":" << vm.trace.size() << ",\"vm_ms\":" << vm_ms << ",\"prove_ms\":" << prove_ms << ",\"world\":" << B.world() << ",\"log_sizes\":[";
+    o << "{\"steps\":" << vm.n_rows() << ",\"vm_ms\":" << vm_ms << ",\"prove_ms\":" << prove_ms << ",\"world\":" << B.world() << ",\"log_sizes\":[";
     for (int c = 0; c < N_COMPONENTS; c++) o << (c ? "," : "") << p->proof.log_size[c];
     o << "],\"stages_ms\":{";
     for (size_t i = 0; i < r.times.ms.size(); i++) o << (i ? "," : "") << "\"" << r.times.ms[i].first << "\":" << r.times.ms[i].second;

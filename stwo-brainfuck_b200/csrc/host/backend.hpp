@@ -3,6 +3,7 @@
 // ABI (cuda_backend.cu); the CPU oracle implements it with scalar loops (oracle/orc_backend.cc, tests only).
 #pragma once
 #include <array>
+#include <mutex>
 #include <vector>
 #include "air.hpp"
 #include "channel.hpp"
@@ -20,9 +21,57 @@ struct SampleBatchesFlat {   // ColumnSampleBatch list for one LDE size, flatten
   std::vector<uint32_t> entry_vals;  // 4 words per entry
 };
 
+// The VM's output as the table builders see it (crates/brainfuck_vm/src/registers.rs:5-21: seven words per step, in clk
+// order) together with the sizes derived from it (vm.hpp TraceStats).
+struct TraceInput {
+  const Registers* regs = nullptr;
+  size_t n = 0;
+  TraceStats stats;
+  bool mvi_filled = true;   // false: the mvi column is still zero and the table builder computes mv^-1 itself
+};
+// Rows of every table (a power of two) from the trace statistics — what the reference learns by building the tables
+// (memory/table.rs:259-318, instruction/table.rs:250-281, program/table.rs:36-46, processor/table.rs:195-207,
+// instructions/table.rs:293-328, jump/table.rs:264-297, end_of_execution/table.rs:71-77).
+inline void table_rows_from_stats(const TraceStats& st, size_t program_len, uint64_t rows[N_COMPONENTS]) {
+  auto p2 = [](uint64_t n) { uint64_t p = 1; while (p < n) p <<= 1; return p; };
+  if (st.steps == 0) throw std::runtime_error("empty trace");
+  if (program_len == 0) throw std::runtime_error("empty program");
+  if (st.zero_ci != 1) throw std::runtime_error("InvalidEndOfExecution");
+  rows[MEMORY] = p2(st.memory_rows);
+  rows[INSTRUCTION] = p2(program_len + st.steps);
+  rows[PROGRAM] = p2(program_len);
+  rows[PROCESSOR] = p2(st.steps);
+  for (int k = 0; k < 8; k++) rows[JNZ + k] = st.op_count[k] ? p2(2ull * st.op_count[k]) / 2 : 1;
+  rows[EOE] = 1;
+}
+
 struct Backend {
   virtual ~Backend() {}
   virtual const char* name() const = 0;
+  // The 13 `trace_evaluation`s (brainfuck_air/mod.rs:511-547) in lane-compact form: compact[c] receives N_MAIN_COLS[c] columns of
+  // one word per table row and log_size[c] the column log size (rows x 16 lanes).  Default: the host builders of tables.hpp
+  // and one upload per column; the CUDA backend builds the tables on the device from the uploaded registers (csrc/tables.cu).
+  // Throws "component too large: <name>" before anything is allocated when a table exceeds 2^(log_max_rows - 4) rows.
+  virtual void trace_tables(const TraceInput& in, const std::vector<uint32_t>& code, uint32_t log_max_rows,
+                            std::vector<std::vector<Col>>& compact, uint32_t log_size[N_COMPONENTS]) {
+    std::vector<Registers> regs(in.regs, in.regs + in.n);
+    if (!in.mvi_filled) for (auto& r : regs) r.mvi = r.mv ? sb::m_inv(r.mv) : 0;
+    static std::mutex arena_mu;   // current_arena() is process-wide: concurrent proofs take turns building host tables
+    std::lock_guard<std::mutex> lk(arena_mu);
+    struct ArenaGuard {  // tables are built into the backend's host arena (pinned memory on CUDA) and die before it is released
+      HostArena* prev;
+      explicit ArenaGuard(HostArena* a) : prev(current_arena()) { current_arena() = a; }
+      ~ArenaGuard() { current_arena() = prev; }
+    } guard(host_arena());
+    std::vector<Table> tables = build_tables(regs, code, log_max_rows);
+    compact.assign(N_COMPONENTS, {});
+    for (int c = 0; c < N_COMPONENTS; c++) {
+      log_size[c] = tables[c].log_size;
+      if (tables[c].log_size > log_max_rows) throw std::runtime_error(std::string("component too large: ") + COMPONENT_NAMES[c]);
+    }
+    for (int c = 0; c < N_COMPONENTS; c++)
+      for (auto& col : tables[c].cols) compact[c].push_back(from_host(col.data(), col.size()));   // synchronous: the tables die here
+  }
   // Column<T>
   virtual Col from_host(const uint32_t* v, size_t n) = 0;
   // Optional fast upload path: a host arena whose memory the backend can DMA from directly, and an upload that does not
@@ -84,6 +133,9 @@ struct Backend {
   virtual void eval_constraints(int comp, uint32_t log_size, const std::vector<Col>& main_lde, const std::vector<Col>& inter_lde,
                                 Col is_first_lde, const InteractionElements& el, QM31 total_sum, const std::vector<QM31>& coeffs,
                                 const std::array<Col, 4>& accum) = 0;
+
+  // trace_tables may defer its consistency checks to the next point where the driver waits for the device anyway
+  virtual void check_tables() {}
 
   // device-side stopwatch: mark() a point in the queued work; gap_ms(a, b) = device time between two marks (consumes both)
   virtual void* mark() { return nullptr; }

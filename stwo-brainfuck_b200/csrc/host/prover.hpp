@@ -230,7 +230,7 @@ struct ProveResult {
 
 // `run_vm` yields the execution trace.  With cfg.overlap_host it is called only after the (program-independent)
 // preprocessed phase has been enqueued, so the VM run as well as the table building hide behind that device work.
-typedef std::function<const std::vector<Registers>&()> TraceSource;
+typedef std::function<TraceInput()> TraceSource;
 inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code, const TraceSource& run_vm,
                                    const ProverConfig& cfg, const std::function<void()>& sync = nullptr,
                                    PreprocessedCache* pp_cache = nullptr) {
@@ -263,24 +263,14 @@ inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code
   // ---- phase 0: preprocessed trace (mod.rs:493-500).  With cfg.overlap_host the device work of this phase is only
   // enqueued here; the host builds the 13 tables meanwhile and the root is read back (and mixed) afterwards — the
   // transcript order is unchanged.
-  struct ArenaGuard {  // tables are built into the backend's host arena (pinned memory on CUDA) and die before it is released
-    HostArena* prev;
-    explicit ArenaGuard(HostArena* a) : prev(current_arena()) { current_arena() = a; }
-    ~ArenaGuard() { current_arena() = prev; }
-  } arena_guard(B.host_arena());
-  std::vector<Table> tables;
   std::vector<std::vector<Col>> compact(N_COMPONENTS);
-  // One value per table row crosses to the device.  The copies are queued as soon as the tables exist: the backend runs
-  // them beside the preprocessed phase (CUDA: a copy stream), and `tables` outlives them (they are complete by the first
-  // read-back after this point).
-  auto upload_tables = [&] {
-    for (int c = 0; c < N_COMPONENTS; c++) {
-      proof.log_size[c] = tables[c].log_size;
-      if (tables[c].log_size > cfg.log_max_rows) throw std::runtime_error(std::string("component too large: ") + COMPONENT_NAMES[c]);
-      for (auto& col : tables[c].cols) compact[c].push_back(B.from_host_async(col.data(), col.size()));
-    }
+  // The 13 tables in lane-compact form (one word per table row).  The CUDA backend uploads the 7-word register rows and
+  // builds every table on the device (csrc/tables.cu); the copy runs beside the preprocessed phase on the copy stream.
+  auto make_tables = [&] {
+    TraceInput in = run_vm();
+    B.trace_tables(in, code, cfg.log_max_rows, compact, proof.log_size);
   };
-  if (!cfg.overlap_host) { tables = build_tables(run_vm(), code, cfg.log_max_rows); lap("tables(host)"); }
+  if (!cfg.overlap_host) { make_tables(); lap("tables(host)"); }
   {
     CommitTree t;
     const bool hit = pp_cache && pp_cache->matches(cfg);
@@ -293,8 +283,7 @@ inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code
       t.evals = B.evaluate(t.polys, cfg.log_blowup);
       t.layers = B.merkle_commit(t.evals, nullptr);
     }
-    if (cfg.overlap_host) tables = build_tables(run_vm(), code, cfg.log_max_rows);
-    upload_tables();  // queued behind nothing: the copies run while the device is still busy with the phase above
+    if (cfg.overlap_host) make_tables();  // the VM runs on this thread while the device is busy with the phase queued above
     if (cfg.overlap_host) { R.times.ms.push_back({"tables(host)", 0}); lap("tables(host)+preprocessed"); }
     if (!hit) B.read(t.layers[0], 0, 8, t.root.data());
     ch.mix_root(t.root);
@@ -315,7 +304,7 @@ inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code
     CommitTree t;
     std::vector<Col> values;
     for (int c = 0; c < N_COMPONENTS; c++)
-      for (Col cc : compact[c]) { values.push_back(cc); t.logs.push_back(tables[c].log_size); }
+      for (Col cc : compact[c]) { values.push_back(cc); t.logs.push_back(proof.log_size[c]); }
     // a table row fills all 16 lanes of its column (table.rs trace_evaluation): interpolate / extend / hash the distinct values only
     t.rep = LOG_N_LANES;
     t.polys = B.interpolate_repeated(values, t.rep);   // the values themselves are kept for the LogUp generation below
@@ -339,6 +328,7 @@ inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code
     {  // claimed sums (LogupTraceGenerator::finalize_last: the cumulative column at index 1), one read-back for all components
       std::vector<uint32_t> w = B.gather(sum_cols, std::vector<size_t>(sum_cols.size(), 1), 1);
       for (int c = 0; c < N_COMPONENTS; c++) proof.claimed_sum[c] = q_make(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+      B.check_tables();  // the device has just been waited for: collect what the table kernels flagged, if anything
     }
     B.interpolate(t.polys);
     for (int c = 0; c < N_COMPONENTS; c++) ch.mix_felts({proof.claimed_sum[c]});
@@ -556,7 +546,11 @@ inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code
 inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code, const std::vector<Registers>& vm_trace,
                                    const ProverConfig& cfg, const std::function<void()>& sync = nullptr,
                                    PreprocessedCache* pp_cache = nullptr) {
-  return prove_brainfuck(B, code, TraceSource([&]() -> const std::vector<Registers>& { return vm_trace; }), cfg, sync, pp_cache);
+  return prove_brainfuck(B, code, TraceSource([&] {
+    TraceInput in;
+    in.regs = vm_trace.data(); in.n = vm_trace.size(); in.stats = trace_stats(in.regs, in.n);
+    return in;
+  }), cfg, sync, pp_cache);
 }
 
 }  // namespace sbf

@@ -273,12 +273,6 @@ inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_
   std::vector<STree> trees;
   lap("twiddles");
 
-  struct ArenaGuard {
-    HostArena* prev;
-    explicit ArenaGuard(HostArena* a) : prev(current_arena()) { current_arena() = a; }
-    ~ArenaGuard() { current_arena() = prev; }
-  } arena_guard(B.host_arena());
-
   // owned polynomials of a tree: interpolate in place, extend, exchange, commit
   auto lde_owned = [&](STree& t) {
     std::vector<Col> owned;
@@ -295,24 +289,16 @@ inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_
     B.interpolate(owned);
   };
 
-  // The VM run and this rank's tables (table k is built by rank k % N only: host work and PCIe traffic are divided by N)
-  // proceed on a host thread while the program-independent preprocessed phase below keeps the device and this thread busy.
-  std::vector<Table> tables(N_COMPONENTS);
+  // Every rank runs the VM itself (it is deterministic and there is a host core per GPU) on a host thread beside the
+  // program-independent preprocessed phase below, uploads the 7-word register rows and builds all 13 tables on its own
+  // device (Backend::trace_tables; csrc/tables.cu on CUDA): no table crosses NVLink.
+  std::vector<std::vector<Col>> compact(N_COMPONENTS);
+  TraceInput trace_in;
   std::string host_err;
   double host_wait_ms = 0;
-  std::vector<Col> uploaded;   // this rank's compact columns, in (component, column) order
   struct Joiner { std::thread t; ~Joiner() { if (t.joinable()) t.join(); } } host;
   host.t = std::thread([&] {
-    try {
-      const std::vector<Registers>& vm_trace = run_vm();
-      std::vector<std::string> err(N_COMPONENTS);
-      std::vector<std::thread> th;
-      for (int k = 0; k < N_COMPONENTS; k++)
-        if (k % N == me)
-          th.emplace_back([&, k] { try { tables[k] = build_table(k, vm_trace, code); } catch (const std::exception& e) { err[k] = e.what(); } });
-      for (auto& x : th) x.join();
-      for (auto& e : err) if (!e.empty()) { host_err = e; break; }
-    } catch (const std::exception& e) { host_err = e.what(); }
+    try { trace_in = run_vm(); } catch (const std::exception& e) { host_err = e.what(); }
   });
 
   // ---- phase 0: preprocessed trace
@@ -330,8 +316,7 @@ inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_
       host.t.join();
       ev_host = B.mark();     // first moment the device could be given the next phase: the gap is what the host cost it
       if (!host_err.empty()) return;
-      for (int c = 0; c < N_COMPONENTS; c++)
-        if (c % N == me) for (auto& col : tables[c].cols) uploaded.push_back(B.from_host_async(col.data(), col.size()));
+      try { B.trace_tables(trace_in, code, cfg.log_max_rows, compact, proof.log_size); } catch (const std::exception& e) { host_err = e.what(); }
     });
     if (ev_queued && ev_host) host_wait_ms = B.gap_ms(ev_queued, ev_host);
     if (!host_err.empty()) throw std::runtime_error(host_err);
@@ -342,54 +327,15 @@ inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_
   // the part of the VM + table time the DEVICE waited for (the rest hid behind the preprocessed phase)
   R.times.ms.push_back({"tables(host)", host_wait_ms});
 
-  // ---- phase 1: main trace.  The compact columns (one word per table row, 63 MB in total for fib19) are replicated over
-  // NVLink, because LogUp generation and the transforms below need them on every rank.
-  std::vector<std::vector<Col>> compact(N_COMPONENTS);
-  Col compact_recv = nullptr;
+  // ---- phase 1: main trace.  The compact columns (one word per table row, 63 MB in total for fib19) were built on every
+  // rank's own device above, because LogUp generation and the transforms below need them everywhere.
   {
     STree t;
-    std::vector<uint32_t> ls(N_COMPONENTS, 0);
-    for (int c = 0; c < N_COMPONENTS; c++) if (c % N == me) ls[c] = tables[c].log_size;
-    if (N > 1) B.allreduce_host(ls.data(), ls.size());
     for (int c = 0; c < N_COMPONENTS; c++) {
-      proof.log_size[c] = ls[c];
-      if (ls[c] > cfg.log_max_rows) throw std::runtime_error(std::string("component too large: ") + COMPONENT_NAMES[c]);
-      if (ls[c] < LOG_N_LANES) throw std::runtime_error("bad table size");
-      for (int j = 0; j < N_MAIN_COLS[c]; j++) t.logs.push_back(ls[c]);
+      if (proof.log_size[c] < LOG_N_LANES) throw std::runtime_error("bad table size");
+      for (int j = 0; j < N_MAIN_COLS[c]; j++) t.logs.push_back(proof.log_size[c]);
     }
     t.owner = assign_owners(t.logs, N);
-    if (N == 1) {
-      size_t u = 0;
-      for (int c = 0; c < N_COMPONENTS; c++)
-        for (size_t j = 0; j < tables[c].cols.size(); j++) compact[c].push_back(uploaded[u++]);
-    } else {
-      auto rows_of = [&](int c) { return (size_t)1 << (ls[c] - LOG_N_LANES); };
-      auto seg_of = [&](int c) { return std::max<size_t>(rows_of(c), 4); };  // 16-byte aligned slots: the views feed vector loads
-      std::vector<size_t> scount(N, 0), rcount(N, 0);
-      for (int c = 0; c < N_COMPONENTS; c++) {
-        rcount[c % N] += seg_of(c) * N_MAIN_COLS[c];
-        if (c % N == me) for (int d = 0; d < N; d++) scount[d] += seg_of(c) * N_MAIN_COLS[c];
-      }
-      size_t mine = scount[0], rtot = 0;
-      for (int s2 = 0; s2 < N; s2++) rtot += rcount[s2];
-      Col send = B.alloc(std::max<size_t>(mine * N, 4));
-      compact_recv = B.alloc(std::max<size_t>(rtot, 4));
-      size_t so = 0, ui = 0;
-      for (int c = 0; c < N_COMPONENTS; c++)
-        if (c % N == me)
-          for (auto& col : tables[c].cols) {
-            Col u = uploaded[ui++];
-            for (int d = 0; d < N; d++) B.copy(send, (size_t)d * mine + so, u, 0, col.size());
-            so += seg_of(c);
-          }
-      B.all_to_all(send, scount, compact_recv, rcount);
-      B.free_col(send);
-      for (Col u : uploaded) B.free_col(u);
-      std::vector<size_t> roff(N, 0);
-      { size_t o = 0; for (int s2 = 0; s2 < N; s2++) { roff[s2] = o; o += rcount[s2]; } }
-      for (int c = 0; c < N_COMPONENTS; c++)
-        for (int j = 0; j < N_MAIN_COLS[c]; j++) { compact[c].push_back(B.view(compact_recv, roff[c % N], rows_of(c))); roff[c % N] += seg_of(c); }
-    }
     // Every table row fills 16 lanes, so a column's transforms run on its distinct values at 1/16 of the cost; the values
     // are on every rank already, so each rank transforms ALL main columns and expands only its own row range of the LDE:
     // the main tree needs no column->row exchange at all.
@@ -454,13 +400,13 @@ inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_
       for (Col cc : compact[c]) B.free_col(cc);
       base += nout;
     }
-    if (compact_recv) B.free_col(compact_recv);
     if (!sum_cols.empty()) {  // one read-back for every cumulative column this rank owns
       std::vector<uint32_t> wv = B.gather(sum_cols, std::vector<size_t>(sum_cols.size(), 1), 1);
       for (size_t i = 0; i < sum_slots.size(); i++) claimed[sum_slots[i]] = wv[i];
     }
     if (N > 1) B.allreduce_host(claimed.data(), claimed.size());
     for (int c = 0; c < N_COMPONENTS; c++) proof.claimed_sum[c] = q_make(claimed[4 * c], claimed[4 * c + 1], claimed[4 * c + 2], claimed[4 * c + 3]);
+    B.check_tables();
     interpolate_owned(t);
     for (int c = 0; c < N_COMPONENTS; c++) ch.mix_felts({proof.claimed_sum[c]});
     std::vector<Col> lde = lde_owned(t);

@@ -17,6 +17,39 @@ struct Registers {
   uint32_t clk = 0, ip = 0, ci = 0, ni = 0, mp = 0, mv = 0, mvi = 0;
 };
 
+// What the table builders need to know about a trace before they allocate anything: the size of every table follows from
+// these counts (memory/table.rs:259-283: one row per clk of every cell's life-span; instructions/table.rs:293-328: one entry
+// pair per step of the opcode).  The VM keeps them while it runs; trace_stats() recomputes them for a trace that came from
+// elsewhere.  Device-side table building (csrc/tables.cu) takes its sizes from here and cross-checks them.
+struct TraceStats {
+  uint64_t steps = 0;          // trace rows (the last one has ci = 0)
+  uint64_t memory_rows = 0;    // sum over touched cells of (last clk - first clk + 1)
+  uint32_t op_count[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // steps with a successor, by opcode: ] [ , < - . + >
+  uint32_t zero_ci = 0;        // rows with ci == 0 (EndOfExecution needs exactly one)
+  uint64_t zero_ci_index = 0;  // index of the first of them
+  uint32_t max_mp = 0, max_ip = 0;
+};
+inline int op_slot_of(uint32_t ci) {
+  switch (ci) { case ']': return 0; case '[': return 1; case ',': return 2; case '<': return 3; case '-': return 4; case '.': return 5;
+                case '+': return 6; case '>': return 7; default: return -1; }
+}
+inline TraceStats trace_stats(const Registers* regs, size_t n) {
+  TraceStats st;
+  st.steps = n;
+  std::vector<std::pair<uint32_t, uint32_t>> seen;  // mp -> last clk + 1, dense up to the largest mp
+  for (size_t i = 0; i < n; i++) {
+    const Registers& r = regs[i];
+    if (i + 1 < n) { int sl = op_slot_of(r.ci); if (sl >= 0) st.op_count[sl]++; }
+    if (r.ci == 0 && st.zero_ci++ == 0) st.zero_ci_index = i;
+    st.max_mp = std::max(st.max_mp, r.mp); st.max_ip = std::max(st.max_ip, r.ip);
+    if (r.mp >= seen.size()) seen.resize((size_t)r.mp + 1, {0u, 0u});
+    auto& c = seen[r.mp];
+    st.memory_rows += c.first ? (uint64_t)(r.clk - c.second) : 1;   // rows are in clk order
+    c.first = 1; c.second = r.clk;
+  }
+  return st;
+}
+
 // `[` is followed by the index of the matching `]`'s argument slot, `]` by the index after the `[`'s slot.
 inline std::vector<uint32_t> compile(const std::string& code) {
   std::vector<uint32_t> ins;
@@ -45,6 +78,14 @@ struct Machine {
   size_t in_pos = 0;
   std::vector<Registers> trace;
   Registers r;
+  // Optional external trace buffer (the CUDA path hands in pinned memory so that the upload is a plain DMA): when set, rows
+  // go to sink[0 .. sink_len) and `trace` stays empty.  `skip_inverses`: leave mvi = 0 for the device to fill (tables.cu).
+  Registers* sink = nullptr;
+  size_t sink_cap = 0, sink_len = 0;
+  bool skip_inverses = false;
+  TraceStats stats;
+  const Registers* rows() const { return sink ? sink : trace.data(); }
+  size_t n_rows() const { return sink ? sink_len : trace.size(); }
 
   Machine(std::vector<uint32_t> code, std::vector<uint8_t> in, size_t ram_size = 30000)
       : program(std::move(code)), ram(ram_size, 0), input(std::move(in)) {}
@@ -56,9 +97,29 @@ struct Machine {
     // Growing the trace from empty costs more than the run itself (reallocation + a page fault per 4 KB), so the buffer of
     // the previous proof is taken over when there is one; 2^20 + 1 rows is the most the AIR can take at LOG_MAX_ROWS 24
     // (the processor table holds one row per step) and untouched pages cost nothing.
-    recycle(trace, /*take=*/true);
-    trace.clear();
-    trace.reserve(((size_t)1 << 20) + 1);
+    if (!sink) {
+      recycle(trace, /*take=*/true);
+      trace.clear();
+      trace.reserve(((size_t)1 << 20) + 1);
+    }
+    sink_len = 0;
+    stats = TraceStats();
+    std::vector<uint32_t> last_seen(ram.size(), 0);  // clk + 1 of the last access of every cell (0: untouched)
+    uint32_t* seen = last_seen.data();
+    uint64_t mem_rows = 0;
+    uint32_t opc[256] = {0};
+    uint32_t max_mp = 0, max_ip = 0;
+    auto emit = [&](const Registers& x) {
+      if (sink) {
+        if (sink_len == sink_cap) throw std::runtime_error("component too large: processor (the trace does not fit the buffer)");
+        sink[sink_len++] = x;
+      } else trace.push_back(x);
+      const uint32_t l = seen[x.mp];
+      mem_rows += l ? (uint64_t)(x.clk + 1 - l) : 1;
+      seen[x.mp] = x.clk + 1;
+      max_mp = x.mp > max_mp ? x.mp : max_mp;
+      max_ip = x.ip > max_ip ? x.ip : max_ip;
+    };
     const uint32_t* prog = program.data();
     uint32_t* cells = ram.data();
     const uint32_t ram_size = (uint32_t)ram.size();
@@ -67,7 +128,8 @@ struct Machine {
     while (r.ip < n) {
       r.ci = prog[r.ip];
       r.ni = (r.ip == n - 1) ? 0 : prog[r.ip + 1];
-      trace.push_back(r);
+      emit(r);
+      opc[r.ci & 255u]++;
       bool early = false;
       switch (r.ci) {
         case '>': r.mp = sb::m_add(r.mp, 1); if (r.mp >= ram_size) throw std::runtime_error("memory pointer out of range"); break;
@@ -97,8 +159,19 @@ struct Machine {
     }
     r.ci = 0;
     r.ni = 0;
-    trace.push_back(r);
-    fill_inverses();
+    emit(r);
+    stats.steps = n_rows();
+    stats.memory_rows = mem_rows;
+    static const char ops[8] = {']', '[', ',', '<', '-', '.', '+', '>'};
+    for (int k = 0; k < 8; k++) stats.op_count[k] = opc[(unsigned char)ops[k]];   // every counted step has a successor (the final row)
+    stats.zero_ci = 1 + opc[0];          // program words are never 0 (compile() keeps instruction bytes only; jump targets are >= 1)
+    stats.zero_ci_index = n_rows() - 1;
+    if (opc[0]) {                        // cannot happen with compile()'s output; stay exact if it ever does
+      const Registers* p = rows();
+      for (size_t i = 0; i < n_rows(); i++) if (p[i].ci == 0) { stats.zero_ci_index = i; break; }
+    }
+    stats.max_mp = max_mp; stats.max_ip = max_ip;
+    if (!skip_inverses) fill_inverses();
   }
 
   // One spare trace buffer per process: a finished machine leaves its (already faulted-in) buffer for the next one.
@@ -114,7 +187,8 @@ struct Machine {
   // which the pass below reproduces because it inverts whatever mv the row recorded.  Montgomery's trick over chunks of the
   // trace (3 multiplications per row and one inversion per chunk), chunks on a few host threads.
   void fill_inverses() {
-    const size_t n = trace.size(), chunk = (size_t)1 << 14;
+    const size_t n = n_rows(), chunk = (size_t)1 << 14;
+    Registers* const trace = sink ? sink : this->trace.data();
     auto work = [&](size_t lo, size_t hi) {
       std::vector<uint32_t> pre(chunk);
       for (size_t c0 = lo; c0 < hi; c0 += chunk) {

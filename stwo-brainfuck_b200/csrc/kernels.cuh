@@ -7,7 +7,10 @@
 
 namespace sb {
 
-extern unsigned long long g_launch_count;  // kernels launched by this process (bench.py gpu_launches)
+// Kernel-launch counter of the context the calling thread entered last (ENTER in capi_internal.cuh points it at
+// sc_ctx::launches): bench.py's gpu_launches is per context, not per process.
+extern thread_local unsigned long long* g_launch_counter;
+#define g_launch_count (*::sb::g_launch_counter)
 
 // fft.cu
 int launch_twiddle_tree(uint32_t* tw, uint32_t* itw, uint32_t R, cudaStream_t st);
@@ -26,6 +29,9 @@ int launch_commit_top(uint32_t top_log, const uint32_t* prev, const uint32_t* co
 int launch_commit_layer(uint32_t log_size, const uint32_t* prev, const uint32_t* const* cols, uint32_t ncols,
                         uint32_t* out, cudaStream_t st, uint32_t rep_log = 0);
 int launch_grind(const uint32_t digest[8], uint32_t pow_bits, unsigned long long* d_result, cudaStream_t st);
+
+// microbench.cu (measurement only)
+int launch_int_pipe_bench(int kind, uint32_t iters, int n_sm, void* d_scratch, double out[4], cudaStream_t st);
 
 // ops.cu
 int launch_bit_reverse(uint32_t* v, uint32_t log, cudaStream_t st);
@@ -55,6 +61,30 @@ int launch_gather(const uint32_t* const* d_src, uint32_t n, uint32_t words, uint
 int launch_broadcast16(const uint32_t* src, uint32_t* dst, size_t src_len, cudaStream_t st);
 // dst[c][i] = src[c][i >> rep_log] for ncols columns of src_len values (device pointer arrays), 2 <= rep_log <= 8
 int launch_broadcast_cols(const uint32_t* const* src, uint32_t* const* dst, uint32_t ncols, size_t src_len, uint32_t rep_log, cudaStream_t st);
+
+// tables.cu — device-side table building
+struct TraceSoA { uint32_t *clk, *ip, *ci, *ni, *mp, *mv, *mvi; };   // the register rows as seven arrays
+struct ColPtrs { uint32_t* p[13]; };
+struct OpSteps { uint32_t* p[8]; };                                   // step indices per opcode slot: ] [ , < - . + >
+struct OpCounts { uint32_t n[8]; };
+struct OpTables { uint32_t* cols[8][13]; uint32_t rows[8]; };
+int launch_tb_unpack(const uint32_t* d_regs, uint32_t n, bool fill_mvi, const TraceSoA& t, uint32_t* d_status, cudaStream_t st);
+int launch_tb_processor(const TraceSoA& t, uint32_t m, uint32_t n, const ColPtrs& c, cudaStream_t st);
+int launch_tb_program(const uint32_t* d_code, uint32_t np, uint32_t n, const ColPtrs& c, cudaStream_t st);
+int launch_tb_eoe(const TraceSoA& t, uint32_t idx, const ColPtrs& c, uint32_t* d_status, cudaStream_t st);
+size_t tb_opcode_scratch_words(uint32_t m);
+int launch_tb_opcodes(const TraceSoA& t, uint32_t m, const OpCounts& cnt, const OpSteps& steps, const OpTables& tabs, uint32_t* d_cnt,
+                      uint32_t* d_status, cudaStream_t st);
+size_t rs_scratch_words(uint32_t n);
+int launch_radix_sort_index(const uint32_t* keys_in, uint32_t* const kbuf[2], uint32_t* const vbuf[2], uint32_t n, uint32_t key_bits,
+                            uint32_t* d_hist, uint32_t** ord_out, cudaStream_t st);
+size_t scan_scratch_words(uint32_t n);
+int launch_inclusive_scan(uint32_t* v, uint32_t n, uint32_t* d_sums, cudaStream_t st);
+int launch_tb_memory(const TraceSoA& t, const uint32_t* d_ord, uint32_t m, uint32_t rows, uint32_t n, const ColPtrs& c, uint32_t* d_delta,
+                     uint32_t* d_sums, uint32_t* d_status, cudaStream_t st);
+int launch_tb_ins_keys(const uint32_t* d_ip, uint32_t np, uint32_t total, uint32_t* d_keys, cudaStream_t st);
+int launch_tb_instruction(const TraceSoA& t, const uint32_t* d_code, const uint32_t* d_ord, uint32_t np, uint32_t total, uint32_t n,
+                          const ColPtrs& c, cudaStream_t st);
 
 // quotients.cu
 struct QuotEntry { uint32_t col; uint32_t c[4]; };
