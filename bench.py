@@ -2,17 +2,23 @@
 """bench.py — measures the proving hot path on B200.
 
 Workloads (config.workload):
-  fib19_prove   (default) BASELINE.json configs[1]: prove fib19.bf end to end on one B200, LOG_MAX_ROWS = 24, PcsConfig
-                default (pow 5, blowup 2x, 3 queries).  A step = one full proof.  metric = prove time (s), lower is better.
-                value = device path (tables already built on the host; includes the 63 MB compact-column upload);
-                e2e   = the whole `prove` call a user makes: VM run + host table building + uploads + proof + proof readback.
-  fib19_commit  the "LDE + commit GB/s" half of the metric on fib19's main-trace tree shape (128 columns): interpolate ->
-                evaluate(2x) -> Blake2s Merkle commit.  value = algorithmic GB/s.  (--workload commit)
+  fib19_prove          (default) BASELINE.json configs[1]: prove fib19.bf end to end, LOG_MAX_ROWS = 24, PcsConfig default (pow 5,
+                       blowup 2x, 3 queries).  A step = one full proof.  metric = prove time (s), lower is better.
+                       value = device time from "register rows resident in HBM" to "proof complete" (CUDA events on the launch stream);
+                       e2e   = the whole `prove` call a user makes: VM run, upload of the register rows from pinned memory,
+                               device-side table building, proof, proof JSON readback.
+                       The default single-GPU run also proves configs[3] and reports it under `extra.synthetic_2p24`.
+  synthetic_2p24_prove (--workload synthetic) BASELINE.json configs[3]: the looping program whose Processor, Memory and
+                       Instruction tables have 2^20 rows (column length 2^24); golden hash checked in the run; any --gpus.
+  fib19_commit         (--workload commit) the "LDE + commit GB/s" half of the metric on fib19's main-trace tree shape (128
+                       columns): interpolate -> evaluate(2x) -> Blake2s Merkle commit.  value = algorithmic GB/s.
 Contract: one JSON line on stdout from rank 0: metric/value/unit, e2e, roofline of the dominant kernel class (device time
-from CUDA events on the launch stream, recorded by the library's profiling scopes), cpu_baseline, clocks, gpu_launches.
-`--impl reference`: the reference is Rust + an un-vendored git dependency and cannot be built in this image, so this arm
-times the in-repo CPU oracle prover (OpenMP, all host cores) on a bounded sample and scales it to the workload (see
-`cpu_baseline.sample`).
+from CUDA events on the launch stream, recorded by the library's profiling scopes; integer peaks measured in the run by
+csrc/microbench.cu), cpu_baseline, clocks, gpu_launches.
+`--impl reference`: the reference is Rust + an un-vendored git dependency; neither this image nor the GPU box has cargo
+(profiles/r2_gpu_box_probe.txt), so this arm times the in-repo CPU oracle prover (OpenMP on every host core, AVX-512 Blake2s)
+on the SAME program at the SAME size, one full proof per step, and stops when the next step would overrun its time budget
+(`cpu_baseline.kind` = "port").
 """
 import argparse
 import ctypes
@@ -34,9 +40,23 @@ PROGRAMS = os.path.join(ROOT, "tests", "golden", "programs")
 # fib19.bf: (log_size, main columns, LogUp columns) per component in commit order (column fib19)
 FIB19 = [(24, 8, 1), (22, 8, 1), (11, 4, 1), (22, 9, 3), (19, 13, 1), (11, 13, 1), (4, 11, 1), (20, 11, 1), (19, 11, 1),
          (4, 11, 1), (20, 11, 1), (20, 11, 1), (4, 7, 1)]
-COLLATZ = [(21, 8, 1), (17, 8, 1), (13, 4, 1), (17, 9, 3), (14, 13, 1), (13, 13, 1), (5, 11, 1), (15, 11, 1), (14, 11, 1),
-           (6, 11, 1), (14, 11, 1), (15, 11, 1), (4, 7, 1)]
+N_MAIN = [8, 8, 4, 9, 13, 13, 11, 11, 11, 11, 11, 11, 7]
+N_LOGUP = [1, 1, 1, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1]
 ROOT_LOG = 26  # brainfuck_air/mod.rs:480-484: twiddles for CanonicCoset(24+1+2).circle_domain().half_coset
+
+# The proving workloads of BASELINE.json: configs[1] (fib19.bf, the headline) and configs[3] (the synthetic looping program whose
+# Processor, Memory and Instruction tables all have 2^20 rows = column length 2^24; SURVEY.md Table S, tests/golden/programs).
+WORKLOADS = {
+    "prove": {"name": "fib19_prove", "file": "fib19.bf", "stdin": b"", "golden": "fib19", "metric": "fib19.bf prove time",
+              "data": "fib19.bf (reference example program), 199246 VM steps"},
+    "synthetic": {"name": "synthetic_2p24_prove", "file": "synthetic_2p24.bf", "stdin": b"", "golden": "synthetic_2p24",
+                  "metric": "2^24-row synthetic trace prove time",
+                  "data": "synthetic '+'x262000 '[-]' (786002 VM steps; Processor = Memory = Instruction = 2^24-row columns)"},
+}
+
+
+def shape_of(log_sizes):
+    return [(lg, N_MAIN[c], N_LOGUP[c]) for c, lg in enumerate(log_sizes)]
 
 
 def proof_columns(shape, log_max_rows):
@@ -48,16 +68,15 @@ def proof_columns(shape, log_max_rows):
     return pre, main, inter, comp
 
 
-def fft_bytes(logs):
-    """algorithmic bytes of interpolate (8N) + evaluate on the 2x domain (12N) per polynomial of 2^log words"""
-    return sum((8 + 12) * (1 << lg) for lg in logs)
-
-
 def proof_fft_bytes(shape, log_max_rows):
+    """Bytes the transforms of one proof MOVE at their minimum (read once + write once): interpolate 8N and evaluate 12N (N
+    coefficients in, 2N values out) per polynomial of N = 2^log words.  The 128 main-trace columns are lane-repeated: they are
+    transformed on their N/16 distinct values (8N/16 in and out) and only the LDE is written at full length (N/16 in, 2N out).
+    The composition polynomials are interpolated once (accumulator finalize) and evaluated once."""
     pre, main, inter, comp = proof_columns(shape, log_max_rows)
-    # composition polynomials are interpolated once (accumulator finalize) and evaluated once on the 2x domain; the lifts of
-    # the running polynomial between accumulator sizes are small and not counted
-    return fft_bytes(pre) + fft_bytes(main) + fft_bytes(inter) + fft_bytes(comp)
+    full = sum((8 + 12) * (1 << lg) for lg in pre + inter + comp)
+    rep = sum(8 * (1 << (lg - 4)) + 4 * (1 << (lg - 4)) + 8 * (1 << lg) for lg in main)
+    return full + rep
 
 
 def tree_stats(lde_logs, rep=0):
@@ -94,7 +113,8 @@ def proof_merkle_stats(shape, log_max_rows):
     return nbytes, comps, done
 
 
-ALU_OPS_PER_COMPRESSION = 8 * 80 + 24  # per G: 4 XOR + 4 rotates stay on the ALU pipe (the 6 additions run as IMAD); + finalisation
+OPS_PER_COMPRESSION = 1136     # 10 rounds x 8 G x 14 + 16, every add / xor / rotate counted once
+ALU_OPS_PER_COMPRESSION = 648  # of those, the 4 XOR + 4 rotates per G (+ 8 LOP3 of the finalisation) cannot leave the ALU pipe
 
 
 def proof_lde_cells(shape, log_max_rows):
@@ -153,80 +173,131 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def rooflines(kern, shape, lmr, world, clocks):
-    """`roofline`: the dominant kernel class of a proof, commit_layer_kernel (Blake2s Merkle layers, about half of the kernel
-    time), per rank: algorithmic bytes / summed CUDA-event time against the measured HBM peak, as the contract asks, plus the
-    bound that actually binds it (`alu_pipe`: compressions/s against SMs x 4 SMSPs x 16 ALU lanes x SM clock / ALU ops per
-    compression).  `roofline_fft`: the same for the FFT launches (second largest class)."""
+def int_peaks(be):
+    """The measured integer peaks of this GPU, from csrc/microbench.cu (lane-operations per second, CUDA-event timed; two CTAs
+    of 1024 threads per SM, eight independent chains per thread): the ALU pipe alone (LOP3), the FMA pipe alone (IMAD), both
+    fed 1:1, and the Blake2s G mix as merkle.cu issues it (8 ALU + 6 IMAD per G) with no loads or stores."""
+    out = {}
+    iters = 8192
+    for key, kind, ops in (("alu_lop3", 0, 32), ("alu_shf", 1, 32), ("alu_prmt", 2, 32), ("alu_iadd3", 3, 32), ("fma_imad", 4, 32),
+                           ("alu_plus_fma", 5, 32), ("blake2s_g_mix", 6, 56)):
+        r = be.microbench_int(kind, iters)
+        out[key] = r["n_sm"] * 2048 * iters * ops / (r["ms"] * 1e-3) / 1e12    # T lane-ops / s
+    return out
+
+
+def merkle_traffic():
+    """dram bytes (read + write) of all Merkle launches of one fib19 proof from the committed ncu pass, or None."""
+    p = os.path.join(ROOT, "profiles", "r2_merkle_traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p))
+    return None
+
+
+def rooflines(kern, shape, lmr, world, clocks, peaks_int):
+    """`roofline`: the dominant kernel class of a proof, the Blake2s Merkle kernels (more than half of the kernel time), per
+    rank.  Bound: the integer pipes — achieved = compressions executed x 1136 integer operations / the summed
+    CUDA-event time of those launches, peak = the MEASURED rate of the ALU and FMA pipes fed together (csrc/microbench.cu,
+    run inside this bench).  Sub-keys: `alu_pipe` (the 648 XOR / rotate operations per compression that can only run on the
+    ALU pipe, against that pipe's measured rate), `g_mix` (the compression's own instruction mix without loads and stores —
+    the practical ceiling of this formulation) and `hbm` (algorithmic bytes against the measured copy bandwidth).
+    `roofline_fft`: the FFT launches against HBM, bytes counted as moved."""
     peak, peak_src = peaks()
     mb, mc, mx = proof_merkle_stats(shape, lmr)
     m_ms = kern.get("merkle_commit_layer", 0)
     share = m_ms / sum(kern.values()) if kern else None
-    sm_hz = (clocks.get("sm_mhz") or 1965) * 1e6
-    bound = 148 * 4 * 16 * sm_hz / ALU_OPS_PER_COMPRESSION
-    roof = {"bound": "hbm", "kernel": "commit_layer_kernel + commit_top_kernel (every Merkle launch of one proof, this rank's share)",
-            "achieved": mb / world / (m_ms * 1e-3) / 1e9 if m_ms else None, "peak": peak, "unit": "GB/s", "traffic": None,
-            "peak_source": peak_src, "algorithmic_bytes": mb / world, "ms_per_proof": m_ms, "share_of_kernel_time": share,
-            "traffic_note": "ncu --set full on seven launches of a fib19 proof: dram read+write = 0.96-1.00 x the algorithmic bytes "
-                            "of the launch (profiles/r1_final_ncu_full_merkle_*.csv); not summed over the ~170 launches, hence null",
-            "alu_pipe": {"algorithmic_compressions": mc / world, "executed_compressions": mx / world,
-                         "achieved_Gcomp_s": mx / world / (m_ms * 1e-3) / 1e9 if m_ms else None, "bound_Gcomp_s": bound / 1e9,
-                         "frac": (mx / world / (m_ms * 1e-3)) / bound if m_ms else None,
-                         "alu_ops_per_compression": ALU_OPS_PER_COMPRESSION, "ncu_alu_pipe_active_pct": "77-82 (profiles/r1_final_ncu_full_merkle_*.csv)",
-                         "note": "the binding roofline: XOR/rotate run on the 16-lane ALU pipe; executed < algorithmic because "
-                                 "the main-trace tree hashes one node per 16 repeated rows in its four deepest layers"}}
-    roof["frac"] = roof["achieved"] / peak if roof["achieved"] else None
+    rate = mx / world / (m_ms * 1e-3) if m_ms else None        # compressions / s
+    tr = merkle_traffic()
+    roof = {"bound": "int_alu", "kernel": "commit_layer_kernel / commit_subtree_kernel (every Merkle launch of one proof, this rank's share)",
+            "achieved": rate * OPS_PER_COMPRESSION / 1e12 if rate else None, "peak": peaks_int["alu_plus_fma"], "unit": "Tint32op/s",
+            "peak_source": "measured in this run: LOP3 and IMAD streams interleaved 1:1 (csrc/microbench.cu); ALU pipe alone "
+                           f"{peaks_int['alu_lop3']:.2f}, FMA pipe alone {peaks_int['fma_imad']:.2f} T lane-ops/s",
+            "ops_per_compression": OPS_PER_COMPRESSION, "executed_compressions": mx / world, "algorithmic_compressions": mc / world,
+            "achieved_Gcomp_s": rate / 1e9 if rate else None, "ms_per_proof": m_ms, "share_of_kernel_time": share,
+            "traffic": tr["dram_bytes_per_proof"] / world if tr else None,
+            "traffic_note": (tr or {}).get("note", "no ncu pass committed for this build"),
+            "alu_pipe": {"achieved": rate * ALU_OPS_PER_COMPRESSION / 1e12 if rate else None, "peak": peaks_int["alu_lop3"], "unit": "Tint32op/s",
+                         "frac": rate * ALU_OPS_PER_COMPRESSION / 1e12 / peaks_int["alu_lop3"] if rate else None,
+                         "note": "4 XOR + 4 rotates per G must run on the ALU pipe (the additions are issued as IMAD on the FMA pipe)"},
+            "g_mix": {"ceiling_Gcomp_s": peaks_int["blake2s_g_mix"] * 1e12 / (80 * 14) / 1e9,
+                      "frac": rate / (peaks_int["blake2s_g_mix"] * 1e12 / (80 * 14)) if rate else None,
+                      "note": "the 80 G functions of a compression issued back to back with no loads, stores or finalisation"},
+            "hbm": {"achieved": mb / world / (m_ms * 1e-3) / 1e9 if m_ms else None, "peak": peak, "unit": "GB/s", "peak_source": peak_src,
+                    "algorithmic_bytes": mb / world, "frac": mb / world / (m_ms * 1e-3) / 1e9 / peak if m_ms else None}}
+    roof["frac"] = roof["achieved"] / roof["peak"] if roof["achieved"] else None
     fft_ms = kern.get("fft_interpolate", 0) + kern.get("fft_evaluate", 0)
     fb = proof_fft_bytes(shape, lmr) / world
     roof_fft = {"bound": "hbm", "kernel": "fft_kernel (every interpolate + evaluate launch of one proof, this rank's share)",
                 "achieved": fb / (fft_ms * 1e-3) / 1e9 if fft_ms else None, "peak": peak, "unit": "GB/s", "traffic": None,
                 "algorithmic_bytes": fb, "ms_per_proof": fft_ms,
-                "note": "algorithmic bytes count every column at full length (8N + 12N); main-trace columns are transformed on "
-                        "their 2^-4 distinct values",
-                "binding_limit": "integer issue: ncu smsp__issue_active 59-72 %, ALU pipe 47-61 %, DRAM 11-39 % on the passes of a "
-                                 "fib19 proof (profiles/r1_final_ncu_full_fft_a.csv); >= 10 integer instructions per butterfly"}
+                "note": "bytes as moved: 8N + 12N per polynomial; the lane-repeated main-trace columns at their compact size "
+                        "(N/16 in and out for the transforms, the LDE written at full length)"}
     roof_fft["frac"] = roof_fft["achieved"] / peak if roof_fft["achieved"] else None
     return roof, roof_fft
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline (oracle port)
 def oracle():
+    # torchrun exports OMP_NUM_THREADS=1: the CPU arm must use the host's cores whatever launched it
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "liborc.so"))
     lib.orc_prove_json.restype = ctypes.c_void_p
     lib.orc_last_error.restype = ctypes.c_char_p
+    try:
+        lib.orc_set_num_threads(ctypes.c_int(os.cpu_count() or 1))
+    except AttributeError:
+        pass
     return lib
 
 
-def cpu_prove_sample():
-    """CPU oracle prover (all host threads) on collatz.bf (stdin '7\\n') at LOG_MAX_ROWS 21, scaled to fib19 by committed LDE
-    cells.  Returns (scaled seconds, measured seconds, threads, description)."""
+def cpu_prove(workload, lmr=24):
+    """One proof of the workload's own program at its own size by the CPU oracle prover (a scalar/OpenMP port — the Rust
+    reference cannot be built here or on the GPU box: no cargo, profiles/r2_gpu_box_probe.txt).  Returns (seconds, threads)."""
     lib = oracle()
-    code = open(os.path.join(PROGRAMS, "collatz.bf"), "rb").read()
+    w = WORKLOADS[workload]
+    code = open(os.path.join(PROGRAMS, w["file"]), "rb").read()
     t0 = time.perf_counter()
-    p = lib.orc_prove_json(code, b"7\n", ctypes.c_size_t(2), ctypes.c_uint32(21), 0)
+    p = lib.orc_prove_json(code, w["stdin"], ctypes.c_size_t(len(w["stdin"])), ctypes.c_uint32(lmr), 0)
     dt = time.perf_counter() - t0
     if not p:
         raise RuntimeError(lib.orc_last_error())
     lib.orc_free(ctypes.c_void_p(p))
-    scale = proof_lde_cells(FIB19, 24) / proof_lde_cells(COLLATZ, 21)
-    return dt * scale, dt, int(lib.orc_num_threads()), \
-        f"CPU oracle prover (port; the Rust reference is not buildable here) on collatz.bf, LOG_MAX_ROWS 21: {dt:.2f} s measured, " \
-        f"scaled x{scale:.2f} by committed LDE cells to fib19.bf at LOG_MAX_ROWS 24"
+    return dt, int(lib.orc_num_threads())
+
+
+def cpu_baseline_entry(workload, dt, thr, n=1):
+    w = WORKLOADS[workload]
+    return {"value": dt, "unit": "s", "cores": thr, "kind": "port",
+            "sample": f"{n} full proof(s) of {w['file']} at LOG_MAX_ROWS 24 by the in-repo CPU oracle prover (OpenMP, AVX-512 Blake2s; a port — "
+                      "neither this image nor the GPU box has a Rust toolchain to build the reference)"}
 
 
 def run_reference(args):
+    """`--impl reference`: the CPU arm on the same workload and config.  A step is one full proof; the run stops early when
+    the next proof would overrun the time budget (each takes about a minute on 16 cores) and reports the steps it did."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    vals = []
-    for i in range(max(1, min(args.steps, 2))):  # each sample is ~15-30 s of CPU work
-        scaled, dt, thr, desc = cpu_prove_sample()
-        vals.append(scaled)
+    workload = args.workload if args.workload in WORKLOADS else "prove"
+    w = WORKLOADS[workload]
+    budget = float(os.environ.get("SBF_REFERENCE_BUDGET_S", "300"))
+    t_start = time.perf_counter()
+    vals, thr = [], 1
+    for i in range(max(1, args.warmup + args.steps)):
+        dt, thr = cpu_prove(workload)
+        if i >= args.warmup or args.warmup + args.steps <= 1:
+            vals.append(dt)
+        elapsed = time.perf_counter() - t_start
+        if len(vals) >= args.steps or elapsed + dt > budget:
+            if not vals:
+                vals.append(dt)      # the budget ended inside the warm-up: the one proof that was run is the sample
+            break
     v = float(np.mean(vals))
-    line = {"impl": "reference", "metric": "fib19.bf prove time", "value": v, "unit": "s", "n_gpus": args.gpus,
-            "steps": len(vals), "warmup": 0, "ms_per_step": 1e3 * v, "higher_is_better": False, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u32 (M31)", "data": "fib19.bf (reference example program)",
-            "config": {"workload": "fib19_prove", "log_max_rows": 24, "pcs": "pow 5, blowup 2x, 3 queries"},
-            "cpu_baseline": {"value": v, "unit": "s", "cores": thr, "kind": "port", "sample": desc},
+    line = {"impl": "reference", "metric": w["metric"], "value": v, "unit": "s", "n_gpus": args.gpus,
+            "steps": len(vals), "warmup": min(args.warmup, max(0, i + 1 - len(vals))), "ms_per_step": 1e3 * v, "higher_is_better": False, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u32 (M31)", "data": w["data"],
+            "config": {"workload": w["name"], "log_max_rows": 24, "pcs": "pow 5, blowup 2x, 3 queries",
+                       "steps_requested": args.steps, "time_budget_s": budget},
+            "cpu_baseline": cpu_baseline_entry(workload, v, thr, len(vals)),
             "e2e": {"value": v, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -258,178 +329,172 @@ def max_over_ranks(torch, dist, world, x):
     return float(t.item())
 
 
-def bench_prove_sharded(args, torch, dist, rank, world, local, pkg, stream, be):
-    """N > 1: ONE fib19 proof split over the N GPUs (strong scaling) by the sharded prover: column-sharded FFTs, one NCCL
-    all-to-all per commitment tree, row-sharded hashing / constraints / quotients / FRI (csrc/host/prover_sharded.hpp)."""
+def golden_check(workload, js):
+    """sha256 of the canonical proof text against tests/golden/proof_hashes.json (the CPU oracle's proof of the same program)."""
     import hashlib
-    code = open(os.path.join(PROGRAMS, "fib19.bf"), "rb").read()
-    lmr = 24
-    comm = pkg.Comm.from_torch_distributed(be, dist)
-    for _ in range(args.warmup):
-        pkg.prove_brainfuck_sharded(be, comm, code, b"", lmr)
-    dist.barrier()
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import proof_canon
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "proof_hashes.json"))).get(WORKLOADS[workload]["golden"])
+    if not gold:
+        return None
+    c = proof_canon.canonical(js.encode())
+    return bool(len(c) == gold["proof_bytes"] and hashlib.sha256(c).hexdigest() == gold["sha256"])
+
+
+def timed_proofs(torch, dist, world, stream, steps, prove):
+    """K proofs bracketed by barrier + synchronize; wall clock and CUDA events on the launch stream; max over ranks."""
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize()
-    be.profile(True)
-    be.profile_report()
-    l0 = be.launch_count()
-    reports = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as cs:
-        t0 = time.perf_counter()
-        e0.record(stream)
-        for _ in range(args.steps):
-            pr = pkg.prove_brainfuck_sharded(be, comm, code, b"", lmr)
-            reports.append(pr.report())
-            js = pr.json()                  # proof readback inside the timed region
-        e1.record(stream)
-        torch.cuda.synchronize()
-        wall = time.perf_counter() - t0
-    dist.barrier()
-    launches = be.launch_count() - l0
-    prof = be.profile_report()
-    be.profile(False)
-    pr.verify()
-    digest = hashlib.sha256(js.encode()).hexdigest()
-    digests = [None] * world
-    dist.all_gather_object(digests, digest)
-    assert len(set(digests)) == 1, "ranks disagree on the proof"
-    e2e_s = max_over_ranks(torch, dist, world, max(wall / args.steps, e0.elapsed_time(e1) * 1e-3 / args.steps))
-    # each table is built by one rank; the others wait for the slowest builder at the first collective, so the host share of
-    # a proof is the MAX over ranks of the table-building time (rank 0 builds the Memory table, the longest one)
-    host_tables = max_over_ranks(torch, dist, world, float(np.mean([r["stages_ms"]["tables(host)"] for r in reports])) * 1e-3)
-    dev_s = max_over_ranks(torch, dist, world, float(np.mean([r["prove_ms"] for r in reports])) * 1e-3) - host_tables
-    stages = {k: float(np.mean([r["stages_ms"][k] for r in reports])) for k in reports[0]["stages_ms"]}
-    kern = {k: v[0] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
-    clocks = cs.summary()
-    roof, roof_fft = rooflines(kern, FIB19, lmr, world, clocks)
-    h2d = sum(n * (1 << (lg - 4)) * 4 for lg, n, _ in FIB19)
-    line = {"metric": "fib19.bf prove time", "value": dev_s, "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_s * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "u32 (M31)",
-            "data": "fib19.bf (reference example program), 199246 VM steps",
-            "config": {"workload": "fib19_prove", "log_max_rows": lmr, "pcs": "pow 5, blowup 2x, 3 queries", "columns": 213,
-                       "lde_cells": proof_lde_cells(FIB19, lmr),
-                       "parallelism": f"one proof over {world} GPUs: column-sharded FFT -> all_to_all per tree -> row-sharded "
-                                      "Merkle / constraints / quotients / FRI; sub-roots all-gathered; main-trace tree from "
-                                      "local transforms of the replicated compact columns (no exchange)",
-                       "proof_sha256": digest},
-            "e2e": {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": len(js),
-                    "includes": "VM run and host table building on every rank, uploads, proof, proof readback"},
-            "gpu_launches": int(launches // args.steps), "stages_ms": stages, "kernel_ms_per_proof": kern, "roofline": roof,
-            "roofline_fft": roof_fft, "clocks": clocks, "verified": True}
-    if args.timeline:  # one more proof with the scopes kept in launch order: where this rank's device sits idle
-        dist.barrier()
-        be.profile(True); be.profile_report()
-        pr = pkg.prove_brainfuck_sharded(be, comm, code, b"", lmr)
-        tl = be.profile_timeline()
-        be.profile_report(); be.profile(False)
-        json.dump({"rank": rank, "world": world, "timeline": tl, "stages_ms": pr.report()["stages_ms"]},
-                  open(f"{args.timeline}.rank{rank}.json", "w"))
-    if rank == 0:
-        print(json.dumps(line))
-    comm.close()
-    be.close()
-    dist.destroy_process_group()
-
-
-def bench_prove(args):
-    torch, dist, rank, world, local, pkg, stream, be = setup(args)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    out = None
+    for _ in range(steps):
+        out = prove()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
     if world > 1:
-        return bench_prove_sharded(args, torch, dist, rank, world, local, pkg, stream, be)
-    code = open(os.path.join(PROGRAMS, "fib19.bf"), "rb").read()
-    lmr = 24
+        dist.barrier()
+    return max_over_ranks(torch, dist, world, max(wall, e0.elapsed_time(e1) * 1e-3) / steps), out
 
+
+def bench_prove(args, workload="prove", extra_only=False):
+    """One step = one full proof of the workload's program at LOG_MAX_ROWS 24.  N > 1: the SAME proof split over the N GPUs
+    (strong scaling) by the sharded prover: every rank runs the VM and builds the tables on its device, column-sharded FFTs,
+    one NCCL all-to-all per commitment tree, row-sharded hashing / constraints / quotients / FRI (csrc/host/prover_sharded.hpp).
+      value : device time from "register rows resident in HBM" to "proof complete" (two CUDA events on the launch stream,
+              recorded by the library: behind the upload, and after the last kernel), VM run before the timed region;
+      e2e   : the call a user makes — VM on the host, 28 B per step uploaded from pinned memory, tables built on the device,
+              proof, proof JSON read back — wall clock and CUDA events around K calls, max over ranks."""
+    torch, dist, rank, world, local, pkg, stream, be = setup(args)
+    w = WORKLOADS[workload]
+    code = open(os.path.join(PROGRAMS, w["file"]), "rb").read()
+    stdin, lmr = w["stdin"], 24
+    comm = pkg.Comm.from_torch_distributed(be, dist) if world > 1 else None
+    if world > 1:
+        prove = lambda **kw: pkg.prove_brainfuck_sharded(be, comm, code, stdin, lmr)
+    else:
+        prove = lambda **kw: pkg.prove_brainfuck(be, code, stdin, lmr, **kw)
     for _ in range(args.warmup):
-        pkg.prove_brainfuck(be, code, b"", lmr)
+        prove()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    # (A) device path: host tables built first (no overlap), value = prove time minus the host table building
+    # (A) device path: VM first, then everything on the device; per-kernel-class CUDA-event scopes on
     be.profile(True)
     be.profile_report()
     l0 = be.launch_count()
     reports = []
     with ClockSampler(local) as cs:
         for _ in range(args.steps):
-            reports.append(pkg.prove_brainfuck(be, code, b"", lmr, overlap_host=False).report())
+            reports.append((prove(overlap_host=False) if world == 1 else prove()).report())
         launches = be.launch_count() - l0
         prof = be.profile_report()
         be.profile(False)
-        # (B) end to end, the call a user makes: VM + tables (overlapped with phase 0) + uploads + proof + proof readback
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        e0.record(stream)
-        for _ in range(args.steps):
-            pr = pkg.prove_brainfuck(be, code, b"", lmr)
-            proof_len = len(pr.json())      # proof readback (D2H of the result) is inside the timed region
-        e1.record(stream)
-        torch.cuda.synchronize()
-        wall = time.perf_counter() - t0
-        # (C) not the headline: the same end-to-end call with the program-independent preprocessed tree kept on the context
-        # between proofs (SBF_CACHE_PREPROCESSED; SURVEY.md §8f rank 2).  The reference rebuilds that tree in every proof,
-        # so `value` and `e2e` above do too; this leg only reports what a server proving many programs would see.
-        cached = None
-        try:
-            pkg.prove_brainfuck(be, code, b"", lmr, cache_preprocessed=True)   # fills the cache
-            torch.cuda.synchronize()
-            t0c = time.perf_counter()
-            for _ in range(args.steps):
-                prc = pkg.prove_brainfuck(be, code, b"", lmr, cache_preprocessed=True)
-                same = prc.json() == pr.json()
-            torch.cuda.synchronize()
-            cached = {"value": (time.perf_counter() - t0c) / args.steps, "unit": "s", "proof_identical": bool(same),
-                      "note": "end to end as e2e, preprocessed tree reused across proofs; not the headline"}
-            pkg.clear_preprocessed_cache(be)
-        except Exception as e:  # reported, never hidden: the headline legs above do not depend on this one
-            cached = {"error": repr(e)}
-        # (D) the strict reading of the reference's prove_brainfuck: nothing kept between proofs, the twiddle tree of
-        # half_odds(26) recomputed in every proof as well (brainfuck_air/mod.rs:480-484; SBF_NO_TWIDDLE_CACHE).
-        strict = None
-        try:
-            pkg.prove_brainfuck(be, code, b"", lmr, twiddle_cache=False)
-            torch.cuda.synchronize()
-            t0s = time.perf_counter()
-            for _ in range(args.steps):
-                prs = pkg.prove_brainfuck(be, code, b"", lmr, twiddle_cache=False)
-                same_s = prs.json() == pr.json()
-            torch.cuda.synchronize()
-            strict = {"value": (time.perf_counter() - t0s) / args.steps, "unit": "s", "proof_identical": bool(same_s),
-                      "note": "end to end as e2e with the twiddle tree recomputed in every proof, as the reference does"}
-        except Exception as e:
-            strict = {"error": repr(e)}
-    if world > 1:
-        dist.barrier()
+        # (B) end to end, the call a user makes
+        state = {}
+
+        def user_call():
+            pr = prove()
+            state["js"] = pr.json()            # proof readback (D2H of the result) is inside the timed region
+            return pr
+        e2e_s, pr = timed_proofs(torch, dist, world, stream, args.steps, user_call)
+        js = state["js"]
+        legs = {}
+        if world == 1 and not extra_only:
+            # (C) not the headline: the program-independent preprocessed tree kept on the context between proofs
+            # (SBF_CACHE_PREPROCESSED; SURVEY.md 8f rank 2).  The reference rebuilds that tree in every proof, so `value` and
+            # `e2e` do too; this leg reports what a server proving many programs would see.
+            try:
+                prove(cache_preprocessed=True)
+                t, prc = timed_proofs(torch, dist, world, stream, args.steps, lambda: prove(cache_preprocessed=True))
+                legs["e2e_preprocessed_cache"] = {"value": t, "unit": "s", "proof_identical": bool(prc.json() == js),
+                                                  "note": "end to end as e2e, preprocessed tree reused across proofs; not the headline"}
+                pkg.clear_preprocessed_cache(be)
+            except Exception as e:  # reported, never hidden: the headline legs above do not depend on this one
+                legs["e2e_preprocessed_cache"] = {"error": repr(e)}
+            # (D) the strict reading of the reference: the twiddle tree of half_odds(26) recomputed in every proof as well
+            # (brainfuck_air/mod.rs:480-484; SBF_NO_TWIDDLE_CACHE)
+            try:
+                prove(twiddle_cache=False)
+                t, prs = timed_proofs(torch, dist, world, stream, args.steps, lambda: prove(twiddle_cache=False))
+                legs["e2e_no_twiddle_cache"] = {"value": t, "unit": "s", "proof_identical": bool(prs.json() == js),
+                                                "note": "end to end as e2e with the twiddle tree recomputed in every proof, as the reference does"}
+            except Exception as e:
+                legs["e2e_no_twiddle_cache"] = {"error": repr(e)}
+            # (E) round 1's input path for comparison: tables built by host threads, finished columns uploaded
+            try:
+                prove(host_tables=True)
+                t, prh = timed_proofs(torch, dist, world, stream, args.steps, lambda: prove(host_tables=True))
+                legs["e2e_host_tables"] = {"value": t, "unit": "s", "proof_identical": bool(prh.json() == js),
+                                           "note": "end to end with the 13 tables built on the host and their columns uploaded (SBF_HOST_TABLES)"}
+            except Exception as e:
+                legs["e2e_host_tables"] = {"error": repr(e)}
+        peaks_int = int_peaks(be)
     pr.verify()                              # the host verifier accepts the last proof
-    ev_s = e0.elapsed_time(e1) * 1e-3 / args.steps
-    e2e_s = max_over_ranks(torch, dist, world, max(wall / args.steps, ev_s))
-    host_tables = float(np.mean([r["stages_ms"]["tables(host)"] for r in reports])) * 1e-3
-    dev_s = max_over_ranks(torch, dist, world, float(np.mean([r["prove_ms"] for r in reports])) * 1e-3 - host_tables)
+    import hashlib
+    digest = hashlib.sha256(js.encode()).hexdigest()
+    if world > 1:
+        digests = [None] * world
+        dist.all_gather_object(digests, digest)
+        assert len(set(digests)) == 1, "ranks disagree on the proof"
+    rep = pr.report()
+    dev_s = max_over_ranks(torch, dist, world, float(np.mean([r["device_ms"] for r in reports])) * 1e-3)
     stages = {k: float(np.mean([r["stages_ms"][k] for r in reports])) for k in reports[0]["stages_ms"]}
     kern = {k: v[0] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
-    peak, peak_src = peaks()
     clocks = cs.summary()
-    roof, roof_fft = rooflines(kern, FIB19, lmr, 1, clocks)
-    h2d = sum(n * (1 << (lg - 4)) * 4 for lg, n, _ in FIB19)
-    line = {"metric": "fib19.bf prove time", "value": dev_s, "unit": "s", "n_gpus": world, "steps": args.steps,
+    shape = shape_of(rep["log_sizes"])
+    roof, roof_fft = rooflines(kern, shape, lmr, world, clocks, peaks_int)
+    par = "single GPU (at --gpus N > 1 the same proof is split over N GPUs)" if world == 1 else \
+        f"one proof over {world} GPUs: VM + device-built tables on every rank, column-sharded FFT -> all_to_all per tree -> " \
+        "row-sharded Merkle / constraints / quotients / FRI; sub-roots all-gathered; main-trace tree without exchange"
+    line = {"metric": w["metric"], "value": dev_s, "unit": "s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_s * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
-            "dtype": "u32 (M31)", "data": "fib19.bf (reference example program), 199246 VM steps",
-            "config": {"workload": "fib19_prove", "log_max_rows": lmr, "pcs": "pow 5, blowup 2x, 3 queries",
-                       "twiddles": "tree of half_odds(26) cached per context (program-independent; recomputing it in every proof as the reference does adds 3.2 ms, profiles/r1_twiddle_cost.json); preprocessed tree recomputed every proof",
-                       "columns": 213, "lde_cells": proof_lde_cells(FIB19, lmr), "l2": "working set (>20 GB) exceeds L2",
-                       "parallelism": "single GPU (at --gpus N > 1 the same proof is split over N GPUs)",
-                       "proof_sha256": __import__("hashlib").sha256(pr.json().encode()).hexdigest()},
-            "e2e": {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": proof_len,
-                    "includes": "VM run, host table building, uploads, proof, proof readback"},
-            "gpu_launches": int(launches // args.steps), "stages_ms": stages, "kernel_ms_per_proof": kern, "roofline": roof,
-            "roofline_fft": roof_fft, "clocks": clocks, "verified": True, "e2e_preprocessed_cache": cached, "e2e_no_twiddle_cache": strict}
-    if rank == 0 and not args.no_cpu_baseline:
-        scaled, dt, thr, desc = cpu_prove_sample()
-        line["cpu_baseline"] = {"value": scaled, "unit": "s", "cores": thr, "kind": "port", "sample": desc}
+            "dtype": "u32 (M31)", "data": w["data"],
+            "config": {"workload": w["name"], "log_max_rows": lmr, "pcs": "pow 5, blowup 2x, 3 queries",
+                       "twiddles": "tree of half_odds(26) cached per context (program-independent; see e2e_no_twiddle_cache); "
+                                   "preprocessed tree recomputed every proof",
+                       "columns": 213, "lde_cells": proof_lde_cells(shape, lmr), "log_sizes": rep["log_sizes"],
+                       "l2": "working set (>20 GB) exceeds L2", "parallelism": par, "proof_sha256": digest,
+                       "golden_match": golden_check(workload, js),
+                       "value_timing": "CUDA events on the launch stream: register rows resident -> proof complete; VM outside"},
+            "e2e": {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": int(rep["h2d_bytes"]), "d2h_bytes_per_step": len(js),
+                    "includes": "VM run (host), register rows + program uploaded from pinned memory, device-side table building, "
+                                "proof, proof JSON read back"},
+            "gpu_launches": int(launches // args.steps), "stages_ms": stages, "vm_ms": float(np.mean([r["vm_ms"] for r in reports])),
+            "kernel_ms_per_proof": kern, "roofline": roof, "roofline_fft": roof_fft, "int_peaks_Tops": peaks_int, "clocks": clocks,
+            "verified": True}
+    line.update(legs)
+    if args.timeline and world > 1:  # one more proof with the scopes kept in launch order: where this rank's device sits idle
+        dist.barrier()
+        be.profile(True); be.profile_report()
+        prt = prove()
+        tl = be.profile_timeline()
+        be.profile_report(); be.profile(False)
+        json.dump({"rank": rank, "world": world, "timeline": tl, "stages_ms": prt.report()["stages_ms"]},
+                  open(f"{args.timeline}.rank{rank}.json", "w"))
+    if comm is not None:
+        comm.close()
+    be.close()
+    if extra_only:
+        return {k: line[k] for k in ("metric", "value", "unit", "e2e", "gpu_launches", "stages_ms", "vm_ms", "kernel_ms_per_proof")} | \
+            {"workload": w["name"], "golden_match": line["config"]["golden_match"], "proof_sha256": digest, "steps": args.steps}
+    if rank == 0 and workload == "prove" and world == 1 and not args.no_extra:
+        # configs[3] beside the headline so that the driver's default run records it (bench.py --workload synthetic runs it
+        # alone, at any --gpus)
+        try:
+            sub = argparse.Namespace(**vars(args))
+            sub.steps, sub.warmup = max(2, min(args.steps, 5)), 2
+            line["extra"] = {"synthetic_2p24": bench_prove(sub, "synthetic", extra_only=True)}
+        except Exception as e:
+            line["extra"] = {"synthetic_2p24": {"error": repr(e)}}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        dt, thr = cpu_prove(workload)
+        line["cpu_baseline"] = cpu_baseline_entry(workload, dt, thr)
     if rank == 0:
         print(json.dumps(line))
-    be.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -569,7 +634,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda")
-    ap.add_argument("--workload", default="prove", choices=["prove", "commit"])
+    ap.add_argument("--workload", default="prove", choices=["prove", "synthetic", "commit"])
+    ap.add_argument("--no-extra", action="store_true", help="prove workload: skip the synthetic 2^24 leg reported under `extra`")
     ap.add_argument("--scale-down", type=int, default=0, help="commit workload only: shrink every column by 2^k rows")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--timeline", default=None, help="N > 1 prove workload: also dump every rank's profiling-scope timeline to <path>.rank<r>.json")
@@ -578,7 +644,7 @@ def main():
         return run_reference(args)
     if args.workload == "commit":
         return bench_commit(args)
-    return bench_prove(args)
+    return bench_prove(args, args.workload)
 
 
 if __name__ == "__main__":

@@ -37,6 +37,8 @@ int32_t sc_version(void);
 int32_t sc_ctx_create(int32_t device, void* stream, sc_ctx** out);
 int32_t sc_ctx_destroy(sc_ctx* ctx);
 int32_t sc_ctx_sync(sc_ctx* ctx);
+/* The compute stream waits for the asynchronous uploads issued so far (every other entry point does this first, too). */
+int32_t sc_ctx_join_uploads(sc_ctx* ctx);
 /* Number of kernels launched through this context so far (bench.py's gpu_launches). */
 uint64_t sc_ctx_launch_count(const sc_ctx* ctx);
 /* Per-kernel-class device timing: when enabled every entry point brackets its launches with CUDA events on the launch

@@ -36,6 +36,14 @@ int orc_num_threads() {
 #endif
 }
 
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);   // a launcher may have exported OMP_NUM_THREADS=1 (torchrun does)
+#else
+  (void)n;
+#endif
+}
+
 void orc_precompute_twiddles(uint32_t root_log, uint32_t* tw, uint32_t* itw) {
   const Tree& t = tree_for(root_log);
   memcpy(tw, t.tw.data(), t.tw.size() * 4);

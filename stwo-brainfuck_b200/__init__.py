@@ -58,7 +58,7 @@ def load_library() -> ctypes.CDLL:
 
 # Every symbol include/stwo_cuda.h declares (checked by tests/test_abi.py without a GPU).
 ABI_SYMBOLS = [
-    "sc_last_error", "sc_version", "sc_ctx_create", "sc_ctx_destroy", "sc_ctx_sync", "sc_ctx_launch_count",
+    "sc_last_error", "sc_version", "sc_ctx_create", "sc_ctx_destroy", "sc_ctx_sync", "sc_ctx_join_uploads", "sc_ctx_launch_count",
     "sc_col_zeros", "sc_col_uninit", "sc_col_from_host", "sc_col_from_host_async", "sc_host_arena_alloc", "sc_host_arena_reset", "sc_col_to_host", "sc_col_read", "sc_col_write", "sc_col_clone",
     "sc_col_free", "sc_col_len", "sc_col_device_ptr", "sc_col_wrap", "sc_col_broadcast16", "sc_bit_reverse", "sc_batch_inverse_m31",
     "sc_batch_inverse_qm31", "sc_precompute_twiddles", "sc_twiddles_free", "sc_twiddles_cached", "sc_twiddles_to_host", "sc_interpolate",
@@ -388,7 +388,7 @@ class CudaBackend:
             for tb in tables:
                 for col in tb:
                     col.free()
-            raise BackendError(f"device table building: the trace disagrees with its statistics (flags {flags.value})")
+            raise BackendError(-1, f"device table building: the trace disagrees with its statistics (flags {flags.value})")
         return tables, [int(x) for x in logs]
 
     def microbench_int(self, kind: int, iters: int = 4096) -> dict:

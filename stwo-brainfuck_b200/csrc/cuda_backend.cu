@@ -17,7 +17,7 @@ struct CudaBackendImpl : Backend {
   sc_ctx* ctx;
   const sc_twiddles* tw = nullptr;
   explicit CudaBackendImpl(sc_ctx* c) : ctx(c) {}
-  ~CudaBackendImpl() override { if (own_tw) sc_twiddles_free(ctx, own_tw); if (pending_trace) sc_trace_free(ctx, pending_trace); }
+  ~CudaBackendImpl() override { if (own_tw) sc_twiddles_free(ctx, own_tw); if (pending_trace) sc_trace_free(ctx, pending_trace); if (ev_resident) sc_event_free(ctx, ev_resident); }
   static void ck(int32_t r) { if (r) throw std::runtime_error(std::string("stwo_cuda: ") + sc_last_error()); }
   static sc_col* h(Col c) { return (sc_col*)c; }
   const char* name() const override { return "cuda"; }
@@ -37,6 +37,19 @@ struct CudaBackendImpl : Backend {
   // to the host builders of tables.hpp (SBF_HOST_TABLES: A/B measurements and the table parity tests).
   bool host_tables = false;
   sc_trace* pending_trace = nullptr;
+  sc_event* ev_resident = nullptr;   // recorded when the register rows have arrived (bench.py's device-timed `value`)
+  uint64_t h2d_bytes = 0;
+  // milliseconds of device time from that mark to now (waits for the queued work); -1 without a mark
+  double ms_since_resident() {
+    if (!ev_resident) return -1;
+    sc_event* e = nullptr;
+    ck(sc_event_record(ctx, &e));
+    float ms = 0;
+    int32_t r = sc_event_elapsed(ctx, ev_resident, e, &ms);
+    sc_event_free(ctx, e); sc_event_free(ctx, ev_resident); ev_resident = nullptr;
+    ck(r);
+    return ms;
+  }
   void trace_tables(const TraceInput& in, const std::vector<uint32_t>& code, uint32_t log_max_rows,
                     std::vector<std::vector<Col>>& compact, uint32_t log_size[N_COMPONENTS]) override {
     if (host_tables) { Backend::trace_tables(in, code, log_max_rows, compact, log_size); return; }
@@ -48,6 +61,12 @@ struct CudaBackendImpl : Backend {
     w[10] = in.stats.zero_ci; w[11] = in.stats.zero_ci_index; w[12] = in.stats.max_mp; w[13] = in.stats.max_ip;
     sc_trace* t = nullptr;
     ck(sc_trace_upload(ctx, (const uint32_t*)in.regs, in.n, code.data(), code.size(), in.mvi_filled ? 0 : 1, &t));
+    // "inputs resident in HBM": a mark on the compute stream right behind the upload, in front of the first table kernel
+    ck(sc_ctx_join_uploads(ctx));
+    if (ev_resident) sc_event_free(ctx, ev_resident);
+    ev_resident = nullptr;
+    ck(sc_event_record(ctx, &ev_resident));
+    h2d_bytes = (in.n * 7 + code.size()) * 4;
     std::vector<sc_col*> cols(128, nullptr);
     if (sc_trace_build_tables(ctx, t, w, log_max_rows, cols.data(), log_size)) {
       std::string msg = sc_last_error();
@@ -345,10 +364,12 @@ int32_t sbf_prove(sc_ctx* ctx, const char* code, const uint8_t* input, size_t in
     B.cache_twiddles = !(flags & 2u);  // SBF_NO_TWIDDLE_CACHE: recompute the twiddle tree in every proof, as the reference does
     auto t1 = std::chrono::steady_clock::now();
     ProveResult r = prove_brainfuck(B, program, run_vm, cfg, [&] { sc_ctx_sync(ctx); }, pp);
+    const double device_ms = B.ms_since_resident();
     double prove_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
     sbf_proof* p = new sbf_proof{std::move(r.proof), cfg, "", vm.output};
     std::ostringstream o;
-    o << "{\"steps\":" << vm.n_rows() << ",\"vm_ms\":" << vm_ms << ",\"prove_ms\":" << prove_ms << ",\"log_sizes\":[";
+    o << "{\"steps\":" << vm.n_rows() << ",\"vm_ms\":" << vm_ms << ",\"prove_ms\":" << prove_ms << ",\"device_ms\":" << device_ms << ",\"h2d_bytes\":" << B.h2d_bytes
+      << ",\"program_words\":" << program.size() << ",\"log_sizes\":[";
     for (int c = 0; c < N_COMPONENTS; c++) o << (c ? "," : "") << p->proof.log_size[c];
     o << "],\"stages_ms\":{";
     for (size_t i = 0; i < r.times.ms.size(); i++) o << (i ? "," : "") << "\"" << r.times.ms[i].first << "\":" << r.times.ms[i].second;
@@ -385,10 +406,12 @@ int32_t sbf_prove_sharded(sc_ctx* ctx, sc_comm* comm, const char* code, const ui
     B.cache_twiddles = !(flags & 2u);
     auto t1 = std::chrono::steady_clock::now();
     ProveResult r = prove_brainfuck_sharded(B, program, run_vm, cfg, [&] { sc_ctx_sync(ctx); });
+    const double device_ms = B.ms_since_resident();
     double prove_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
     sbf_proof* p = new sbf_proof{std::move(r.proof), cfg, "", vm.output};
     std::ostringstream o;
-    o << "{\"steps\":" << vm.n_rows() << ",\"vm_ms\":" << vm_ms << ",\"prove_ms\":" << prove_ms << ",\"world\":" << B.world() << ",\"log_sizes\":[";
+    o << "{\"steps\":" << vm.n_rows() << ",\"vm_ms\":" << vm_ms << ",\"prove_ms\":" << prove_ms << ",\"device_ms\":" << device_ms << ",\"h2d_bytes\":" << B.h2d_bytes
+      << ",\"program_words\":" << program.size() << ",\"world\":" << B.world() << ",\"log_sizes\":[";
     for (int c = 0; c < N_COMPONENTS; c++) o << (c ? "," : "") << p->proof.log_size[c];
     o << "],\"stages_ms\":{";
     for (size_t i = 0; i < r.times.ms.size(); i++) o << (i ? "," : "") << "\"" << r.times.ms[i].first << "\":" << r.times.ms[i].second;
