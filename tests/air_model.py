@@ -14,7 +14,7 @@ P = M.P
 def main_and_relations(comp, r, is_first):
     """The `add_constraint` values of one row (as QM31 tuples) and the `add_to_relation` entries (numerator, relation, values)."""
     out = []
-    add = lambda v: out.append((v % P, 0, 0, 0))
+    add = lambda v: out.append(M.q_from(v))   # ints (trace rows) or M.Q values (mask values at the out-of-domain point)
     one = 1
     if comp == 0:                                                   # memory/component.rs:62-137
         clk, mp, mv, d, nclk, nmp, nmv, nd = r

@@ -46,7 +46,34 @@ def q_inv(x):
     return (ra[0], ra[1], (-rb[0]) % P, (-rb[1]) % P)
 
 
+class Q:
+    """A QM31 value with Python operators, so that the integer formulas of tests/air_model.py can be evaluated on secure-field
+    mask values as well (tests/py_verifier.py evaluates the constraints at the out-of-domain point)."""
+    __slots__ = ("t",)
+
+    def __init__(self, t):
+        self.t = tuple(x % P for x in t)
+
+    @staticmethod
+    def of(v):
+        return v if isinstance(v, Q) else Q((v, 0, 0, 0))
+
+    def __add__(self, o): return Q(q_add(self.t, Q.of(o).t))
+    __radd__ = __add__
+    def __sub__(self, o): return Q(q_sub(self.t, Q.of(o).t))
+    def __rsub__(self, o): return Q(q_sub(Q.of(o).t, self.t))
+    def __mul__(self, o): return Q(q_mul(self.t, Q.of(o).t))
+    __rmul__ = __mul__
+    def __neg__(self): return Q(q_sub((0, 0, 0, 0), self.t))
+    def __eq__(self, o): return self.t == Q.of(o).t
+    def __hash__(self): return hash(self.t)
+    def inv(self): return Q(q_inv(self.t))
+    def __repr__(self): return "Q%r" % (self.t,)
+
+
 def q_from(v):
+    if isinstance(v, Q):
+        return v.t
     return (v % P, 0, 0, 0)
 
 
