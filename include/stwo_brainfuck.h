@@ -21,6 +21,9 @@ const char* sbf_last_error(void);
 /* flags: build the 13 tables with the host builders (csrc/host/tables.hpp) and upload the finished columns, as round 1 did,
  * instead of building them on the device from the register rows; same proof bytes (A/B measurements, parity tests). */
 #define SBF_HOST_TABLES 16u
+/* flags: run the FRI commit phase layer by layer with the host channel (one root read-back per layer) instead of
+ * sc_fri_commit's device-side channel; same proof bytes (A/B measurements). */
+#define SBF_NO_FUSED_FRI 32u
 int32_t sbf_preprocessed_cache_clear(sc_ctx* ctx);
 int32_t sbf_prove(sc_ctx* ctx, const char* code, const uint8_t* input, size_t input_len, uint32_t log_max_rows, uint32_t flags,
                   sbf_proof** out);

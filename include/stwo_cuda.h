@@ -126,6 +126,22 @@ int32_t sc_fold_line(sc_ctx* ctx, sc_col* const src[4], uint32_t log, const uint
 /* dst (length 2^(log-1), 4 coords) <- dst*alpha^2 + fold(src on CanonicCoset(log)). */
 int32_t sc_fold_circle_into_line(sc_ctx* ctx, sc_col* const src[4], uint32_t log, const uint32_t alpha[4], const sc_twiddles* tw, sc_col* const dst[4]);
 
+/* FriProver::commit (upstream core/fri.rs) as ONE call: first-layer tree over all quotient columns, then per line layer
+ * fold_circle_into_line of the columns that join it, Merkle tree, channel.mix_root + channel.draw_felt, fold_line — with the
+ * Blake2s channel state in device memory, so no layer waits for a host round trip (upstream reads every root back before it
+ * can draw the next folding coefficient).  The caller replays its own channel from roots_out afterwards: mix_root(roots[0]),
+ * draw_felt() (the circle fold's coefficient), then mix_root / draw_felt per inner layer — the digests and coefficients are
+ * the same, so the transcript and the proof are unchanged.
+ * quot_cols: nq secure columns (4 coordinate columns each) of strictly descending log sizes quot_logs; channel_digest: the
+ * channel's digest before the phase; last_log = log_last_layer_degree_bound + log_blowup.  With top = quot_logs[0] and
+ * n_inner = top - 1 - last_log:  first_layers_out: top + 1 slots (layer k = log size k);  inner_evals_out: 4 * n_inner
+ * columns (the committed evaluation of line log top-1, top-2, ...);  inner_layers_out: for each inner layer of line log lg,
+ * lg + 1 slots (layer k at slot k), concatenated in layer order;  roots_out: 8 * (1 + n_inner) words;  last_values_out:
+ * 4 * 2^last_log words, coordinate-major. */
+int32_t sc_fri_commit(sc_ctx* ctx, const sc_twiddles* tw, sc_col* const* quot_cols, const uint32_t* quot_logs, uint32_t nq,
+                      const uint32_t channel_digest[8], uint32_t last_log, sc_col** first_layers_out, sc_col** inner_evals_out,
+                      sc_col** inner_layers_out, uint32_t* roots_out, uint32_t* last_values_out);
+
 /* ---- QuotientOps::accumulate_quotients (upstream core/backend/simd/quotients.rs, core/pcs/quotients.rs) ----
  * cols: the n columns of one LDE size 2^log; batches: nb sample batches; batch b has point batch_points[8b..8b+8) and
  * batch_sizes[b] entries; entries (column index, value[4]) are concatenated in entry_cols / entry_vals.

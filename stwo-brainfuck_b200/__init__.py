@@ -66,7 +66,7 @@ ABI_SYMBOLS = [
     "sc_fold_circle_into_line", "sc_accumulate_quotients", "sc_accumulate", "sc_secure_powers", "sc_grind",
     "sc_gen_is_first", "sc_is_first_coeffs", "sc_prefix_sum_bitrev", "sc_logup_generate", "sc_eval_constraints", "sc_gather", "sc_ctx_profile", "sc_ctx_profile_report", "sc_ctx_profile_timeline", "sc_ctx_mark", "sc_ctx_release_since", "sc_ctx_live_columns", "sc_event_record", "sc_event_elapsed", "sc_event_free", "sc_interpolate_repeated", "sc_evaluate_repeated", "sc_eval_at_point_repeated",
     "sc_merkle_commit_layer_repeated", "sc_merkle_commit_repeated", "sc_ctx_attach", "sc_ctx_attached",
-    "sc_microbench_int", "sc_trace_stats_host", "sc_trace_upload", "sc_trace_build_tables", "sc_trace_status", "sc_trace_free",
+    "sc_microbench_int", "sc_fri_commit", "sc_trace_stats_host", "sc_trace_upload", "sc_trace_build_tables", "sc_trace_status", "sc_trace_free",
 ]
 PROVER_SYMBOLS = ["sbf_prove", "sbf_verify", "sbf_proof_json", "sbf_proof_report", "sbf_proof_output", "sbf_string_free",
                   "sbf_proof_free", "sbf_proof_tamper", "sbf_last_error", "sbf_preprocessed_cache_clear"]
@@ -496,7 +496,8 @@ class Proof:
 
 
 def prove_brainfuck(backend: CudaBackend, code: str, stdin: bytes = b"", log_max_rows: int = 24, overlap_host: bool = True,
-                    cache_preprocessed: bool = False, twiddle_cache: bool = True, host_tables: bool = False) -> Proof:
+                    cache_preprocessed: bool = False, twiddle_cache: bool = True, host_tables: bool = False,
+                    fused_fri: bool = True) -> Proof:
     """prove_brainfuck(&Machine) of crates/brainfuck_prover/src/brainfuck_air/mod.rs:471-735: runs the VM on the host and the
     whole proof on the device behind `backend`.  overlap_host=False builds the host tables before any device work (used by
     bench.py to time the device path alone); cache_preprocessed=True keeps the program-independent preprocessed tree on
@@ -506,7 +507,7 @@ def prove_brainfuck(backend: CudaBackend, code: str, stdin: bytes = b"", log_max
     lib = backend._lib
     h = _vp()
     code_b = code.encode() if isinstance(code, str) else code
-    flags = (0 if overlap_host else 1) | (8 if cache_preprocessed else 0) | (0 if twiddle_cache else 2) | (16 if host_tables else 0)
+    flags = (0 if overlap_host else 1) | (8 if cache_preprocessed else 0) | (0 if twiddle_cache else 2) | (16 if host_tables else 0) | (0 if fused_fri else 32)
     rc = lib.sbf_prove(backend._ctx, ctypes.c_char_p(code_b), ctypes.c_char_p(stdin), ctypes.c_size_t(len(stdin)),
                        ctypes.c_uint32(log_max_rows), ctypes.c_uint32(flags), ctypes.byref(h))
     if rc != 0:

@@ -636,7 +636,6 @@ static int32_t commit_layer_impl(sc_ctx* ctx, uint32_t log_size, const sc_col* p
   return SC_OK;
 }
 
-static int32_t merkle_commit_impl(sc_ctx* ctx, sc_col* const* cols, uint32_t n, uint32_t log_repeat, sc_col** layers_out, uint32_t* max_log_out, uint32_t root_out[8]);
 int32_t sc_merkle_commit(sc_ctx* ctx, sc_col* const* cols, uint32_t n, sc_col** layers_out, uint32_t* max_log_out, uint32_t root_out[8]) {
   return merkle_commit_impl(ctx, cols, n, 0, layers_out, max_log_out, root_out);
 }
@@ -646,7 +645,7 @@ int32_t sc_merkle_commit_repeated(sc_ctx* ctx, sc_col* const* cols, uint32_t n, 
   if (log_repeat > 8) return fail(SC_EINVAL, "merkle_commit: log_repeat > 8");
   return merkle_commit_impl(ctx, cols, n, log_repeat, layers_out, max_log_out, root_out);
 }
-static int32_t merkle_commit_impl(sc_ctx* ctx, sc_col* const* cols, uint32_t n, uint32_t log_repeat, sc_col** layers_out, uint32_t* max_log_out, uint32_t root_out[8]) {
+int32_t merkle_commit_impl(sc_ctx* ctx, sc_col* const* cols, uint32_t n, uint32_t log_repeat, sc_col** layers_out, uint32_t* max_log_out, uint32_t root_out[8]) {
   ENTER();
   if (!layers_out || (!cols && n)) return fail(SC_EINVAL, "null argument");
   uint32_t max_log = 0;

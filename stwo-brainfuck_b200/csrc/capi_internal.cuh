@@ -136,3 +136,7 @@ static inline int32_t new_col(sc_ctx* ctx, uint64_t len, sc_col** out) {
   return SC_OK;
 }
 
+
+// MerkleProver::commit over mixed-size columns (capi.cu): layers_out[k] = layer of log size k; root_out may be NULL (no read-back).
+extern "C" int32_t merkle_commit_impl(sc_ctx* ctx, sc_col* const* cols, uint32_t n, uint32_t log_repeat, sc_col** layers_out,
+                                        uint32_t* max_log_out, uint32_t root_out[8]);

@@ -175,6 +175,39 @@ struct CudaBackendImpl : Backend {
   void fold_circle_into_line(const std::array<Col, 4>& dst, const std::array<Col, 4>& src, uint32_t log, QM31 alpha) override {
     ck(sc_fold_circle_into_line(ctx, (sc_col* const*)src.data(), log, (const uint32_t*)&alpha, tw, (sc_col* const*)dst.data()));
   }
+  bool fused_fri = true;   // SBF_NO_FUSED_FRI clears it (A/B measurements)
+  bool fri_commit(const std::vector<std::pair<uint32_t, std::array<Col, 4>>>& quotients, const Hash& digest, uint32_t last_log,
+                  FriCommitResult& out) override {
+    if (!fused_fri || quotients.empty()) return false;
+    const uint32_t top = quotients[0].first;
+    if (last_log + 1 >= top || last_log > 10) return false;
+    std::vector<sc_col*> qc;
+    std::vector<uint32_t> ql;
+    for (auto& q : quotients) { ql.push_back(q.first); for (Col c : q.second) qc.push_back(h(c)); }
+    const uint32_t n_inner = top - 1 - last_log;
+    size_t n_layers = 0;
+    for (uint32_t lg = top - 1; lg > last_log; lg--) n_layers += lg + 1;
+    std::vector<sc_col*> first(top + 1, nullptr), evals(4 * (size_t)n_inner, nullptr), layers(n_layers, nullptr);
+    std::vector<uint32_t> roots(8 * (size_t)(n_inner + 1)), last((size_t)4 << last_log);
+    ck(sc_fri_commit(ctx, tw, qc.data(), ql.data(), (uint32_t)ql.size(), digest.data(), last_log, first.data(), evals.data(), layers.data(),
+                     roots.data(), last.data()));
+    out.first_layers.assign(first.begin(), first.end());
+    memcpy(out.first_root.data(), roots.data(), 32);
+    out.inner.resize(n_inner);
+    size_t off = 0;
+    for (uint32_t i = 0; i < n_inner; i++) {
+      auto& L = out.inner[i];
+      L.log = top - 1 - i;
+      for (int k = 0; k < 4; k++) L.eval[k] = evals[4 * i + k];
+      L.layers.assign(layers.begin() + off, layers.begin() + off + L.log + 1);
+      off += L.log + 1;
+      memcpy(L.root.data(), roots.data() + 8 * (i + 1), 32);
+    }
+    const size_t n = (size_t)1 << last_log;
+    out.last_layer.resize(n);
+    for (size_t i = 0; i < n; i++) out.last_layer[i] = sb::q_make(last[i], last[n + i], last[2 * n + i], last[3 * n + i]);
+    return true;
+  }
   std::array<Col, 4> accumulate_quotients(uint32_t log, const std::vector<Col>& cols, QM31 rc, const SampleBatchesFlat& b) override {
     std::array<Col, 4> out;
     ck(sc_accumulate_quotients(ctx, log, (sc_col* const*)cols.data(), (uint32_t)cols.size(), (const uint32_t*)&rc, b.points.data(),
@@ -358,6 +391,7 @@ int32_t sbf_prove(sc_ctx* ctx, const char* code, const uint8_t* input, size_t in
     TraceSource run_vm = [&]() { return run_machine(ctx, vm, log_max_rows, host_tables, vm_ms); };
     CudaBackendImpl B(ctx);
     B.host_tables = host_tables;
+    B.fused_fri = !(flags & 32u);   // SBF_NO_FUSED_FRI
     ProverConfig cfg;
     cfg.log_max_rows = log_max_rows;
     cfg.overlap_host = !(flags & 1u);  // SBF_NO_OVERLAP: VM run and tables before any device work (bench.py's device-path timing)

@@ -113,6 +113,16 @@ struct Backend {
   // FriOps
   virtual std::array<Col, 4> fold_line(const std::array<Col, 4>& src, uint32_t log, QM31 alpha) = 0;
   virtual void fold_circle_into_line(const std::array<Col, 4>& dst, const std::array<Col, 4>& src, uint32_t log, QM31 alpha) = 0;
+  // FriProver::commit as one backend call with the channel on the device (optional; csrc/fri.cu).  Returns false when the
+  // backend has no fused path — the driver then runs the layer-by-layer loop over fold_* / merkle_commit with its own channel.
+  struct FriCommitResult {
+    std::vector<Col> first_layers; Hash first_root;
+    struct Inner { std::array<Col, 4> eval; uint32_t log; std::vector<Col> layers; Hash root; };
+    std::vector<Inner> inner;
+    std::vector<QM31> last_layer;   // 2^last_log values
+  };
+  virtual bool fri_commit(const std::vector<std::pair<uint32_t, std::array<Col, 4>>>& quotients, const Hash& channel_digest, uint32_t last_log,
+                          FriCommitResult& out) { (void)quotients; (void)channel_digest; (void)last_log; (void)out; return false; }
   // QuotientOps
   virtual std::array<Col, 4> accumulate_quotients(uint32_t log, const std::vector<Col>& cols, QM31 random_coeff,
                                                   const SampleBatchesFlat& b) = 0;

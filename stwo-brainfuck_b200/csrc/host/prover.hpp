@@ -440,35 +440,56 @@ inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code
   CommitTree fri_first;
   std::vector<Col> first_cols;
   for (auto& q : quotients) for (Col x : q.second) first_cols.push_back(x);
-  fri_first.layers = B.merkle_commit(first_cols, &fri_first.root);
-  ch.mix_root(fri_first.root);
-  QM31 circle_alpha = ch.draw_felt();
   struct InnerLayer { std::array<Col, 4> eval; uint32_t log; CommitTree tree; };
   std::vector<InnerLayer> inner;
-  uint32_t line_log = quotients[0].first - 1;
-  std::array<Col, 4> layer = {B.zeros((size_t)1 << line_log), B.zeros((size_t)1 << line_log), B.zeros((size_t)1 << line_log), B.zeros((size_t)1 << line_log)};
-  size_t qi = 0;
   const uint32_t last_log = cfg.log_last_layer_degree_bound + cfg.log_blowup;
-  while (line_log > last_log) {
-    while (qi < quotients.size() && quotients[qi].first - 1 == line_log) { B.fold_circle_into_line(layer, quotients[qi].second, quotients[qi].first, circle_alpha); qi++; }
-    InnerLayer L{layer, line_log, {}};
-    L.tree.layers = B.merkle_commit({layer[0], layer[1], layer[2], layer[3]}, &L.tree.root);
-    ch.mix_root(L.tree.root);
-    QM31 alpha = ch.draw_felt();
-    layer = B.fold_line(layer, line_log, alpha);
-    line_log--;
-    inner.push_back(std::move(L));
-  }
-  if (qi != quotients.size()) throw std::runtime_error("FRI: not all columns consumed");
-  // last layer: interpolate on the host (LineEvaluation::interpolate), degree bound 2^log_last_layer_degree_bound
-  {
+  if (cfg.log_last_layer_degree_bound != 0) throw std::runtime_error("only log_last_layer_degree_bound = 0 is supported");
+  std::vector<QM31> last_values;   // the last layer's evaluation
+  std::array<Col, 4> layer = {nullptr, nullptr, nullptr, nullptr};
+  Backend::FriCommitResult fused;
+  if (B.fri_commit(quotients, ch.digest, last_log, fused)) {
+    // The whole phase ran on the device with its own copy of the channel; replay the transcript from the roots it returned.
+    fri_first.layers = fused.first_layers;
+    fri_first.root = fused.first_root;
+    ch.mix_root(fri_first.root);
+    ch.draw_felt();                      // the circle fold's coefficient
+    for (auto& L : fused.inner) {
+      InnerLayer I{L.eval, L.log, {}};
+      I.tree.layers = L.layers;
+      I.tree.root = L.root;
+      ch.mix_root(L.root);
+      ch.draw_felt();                    // this layer's folding coefficient
+      inner.push_back(std::move(I));
+    }
+    last_values = fused.last_layer;
+  } else {
+    fri_first.layers = B.merkle_commit(first_cols, &fri_first.root);
+    ch.mix_root(fri_first.root);
+    QM31 circle_alpha = ch.draw_felt();
+    uint32_t line_log = quotients[0].first - 1;
+    layer = {B.zeros((size_t)1 << line_log), B.zeros((size_t)1 << line_log), B.zeros((size_t)1 << line_log), B.zeros((size_t)1 << line_log)};
+    size_t qi = 0;
+    while (line_log > last_log) {
+      while (qi < quotients.size() && quotients[qi].first - 1 == line_log) { B.fold_circle_into_line(layer, quotients[qi].second, quotients[qi].first, circle_alpha); qi++; }
+      InnerLayer L{layer, line_log, {}};
+      L.tree.layers = B.merkle_commit({layer[0], layer[1], layer[2], layer[3]}, &L.tree.root);
+      ch.mix_root(L.tree.root);
+      QM31 alpha = ch.draw_felt();
+      layer = B.fold_line(layer, line_log, alpha);
+      line_log--;
+      inner.push_back(std::move(L));
+    }
+    if (qi != quotients.size()) throw std::runtime_error("FRI: not all columns consumed");
     size_t n = (size_t)1 << line_log;
     std::vector<std::vector<uint32_t>> cv(4, std::vector<uint32_t>(n));
     for (int k = 0; k < 4; k++) B.read(layer[k], 0, n, cv[k].data());
-    if (cfg.log_last_layer_degree_bound != 0) throw std::runtime_error("only log_last_layer_degree_bound = 0 is supported");
-    QM31 v0 = q_make(cv[0][0], cv[1][0], cv[2][0], cv[3][0]);
-    for (size_t i = 1; i < n; i++)
-      if (!q_eq(v0, q_make(cv[0][i], cv[1][i], cv[2][i], cv[3][i]))) throw std::runtime_error("FRI: invalid degree (last layer not constant)");
+    for (size_t i = 0; i < n; i++) last_values.push_back(q_make(cv[0][i], cv[1][i], cv[2][i], cv[3][i]));
+  }
+  // last layer: interpolate on the host (LineEvaluation::interpolate), degree bound 2^log_last_layer_degree_bound = 1
+  {
+    QM31 v0 = last_values[0];
+    for (size_t i = 1; i < last_values.size(); i++)
+      if (!q_eq(v0, last_values[i])) throw std::runtime_error("FRI: invalid degree (last layer not constant)");
     P.fri_proof.last_layer_poly = {v0};
     ch.mix_felts(P.fri_proof.last_layer_poly);
   }
@@ -538,7 +559,7 @@ inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code
   for (auto& q : quotients) for (Col x : q.second) B.free_col(x);
   for (Col x : fri_first.layers) B.free_col(x);
   for (auto& L : inner) { for (Col x : L.eval) B.free_col(x); for (Col x : L.tree.layers) B.free_col(x); }
-  for (Col x : layer) B.free_col(x);
+  for (Col x : layer) if (x) B.free_col(x);
   lap("check+free");
   return R;
 }

@@ -62,6 +62,27 @@ int launch_broadcast16(const uint32_t* src, uint32_t* dst, size_t src_len, cudaS
 // dst[c][i] = src[c][i >> rep_log] for ncols columns of src_len values (device pointer arrays), 2 <= rep_log <= 8
 int launch_broadcast_cols(const uint32_t* const* src, uint32_t* const* dst, uint32_t ncols, size_t src_len, uint32_t rep_log, cudaStream_t st);
 
+// fri.cu — FRI commit phase with the channel on the device
+constexpr uint32_t FRI_TAIL_LOG = 10;   // line evaluations of <= 2^10 values are folded, hashed and mixed by one persistent CTA
+struct FriTailArgs {
+  uint32_t start_log, last_log, one;
+  const uint32_t* layer_in[4];       // evaluation of line log start_log before its circle fold (all NULL: zeros)
+  const uint32_t* itw_end;           // end of the plain inverse twiddle buffer
+  uint32_t* digest;                  // channel digest, 8 words, in/out
+  const uint32_t* circle_alpha;      // the first layer's folding coefficient, 4 words
+  uint32_t* const* eval_out;         // [layer * 4 + k]: the committed evaluation of each layer (2^lg words per coordinate)
+  uint32_t* const* tree_out;         // per layer lg: its Merkle layers of log lg, lg-1, ..., 0, concatenated over the layers
+  const uint32_t* const* quot;       // [layer * 4 + k]: the quotient column of log lg + 1 that folds into layer lg, or NULL
+  uint32_t* roots_out;               // 8 words per layer
+  uint32_t* last_out[4];             // the last layer's evaluation (2^last_log words per coordinate)
+};
+int launch_fri_channel(uint32_t* d_digest, const uint32_t* d_root, uint32_t* d_alpha_out, uint32_t* d_root_copy, cudaStream_t st);
+int launch_fold_line_dev(const uint32_t* const src[4], uint32_t log, const uint32_t* d_alpha, uint32_t* const dst[4], const uint32_t* itw_end,
+                         cudaStream_t st);
+int launch_fold_circle_dev(const uint32_t* const src[4], uint32_t log, const uint32_t* d_alpha, uint32_t* const dst[4], const uint32_t* itw_end,
+                           bool first, cudaStream_t st);
+int launch_fri_tail(const FriTailArgs& a, cudaStream_t st);
+
 // tables.cu — device-side table building
 struct TraceSoA { uint32_t *clk, *ip, *ci, *ni, *mp, *mv, *mvi; };   // the register rows as seven arrays
 struct ColPtrs { uint32_t* p[13]; };

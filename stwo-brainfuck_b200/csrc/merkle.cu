@@ -10,70 +10,16 @@
 // load is one coalesced 128-byte line and the 32-byte digest store fills whole sectors.  The whole compression is
 // unrolled with compile-time sigma so message and state words live in registers (no local memory).
 #include "kernels.cuh"
+#include "blake2s.cuh"
+#include <cstdlib>
 
 namespace sb {
 
-__device__ __forceinline__ uint32_t rotr16(uint32_t x) { return __byte_perm(x, x, 0x1032); }
-__device__ __forceinline__ uint32_t rotr8(uint32_t x) { return __byte_perm(x, x, 0x0321); }
-__device__ __forceinline__ uint32_t rotr12(uint32_t x) { return __funnelshift_r(x, x, 12); }
-__device__ __forceinline__ uint32_t rotr7(uint32_t x) { return __funnelshift_r(x, x, 7); }
-
-// Pipe balance (ncu, round 1): with plain adds the compression is 12 ALU-pipe ops per G (IADD3, LOP3, SHF, PRMT) and the
-// ALU pipe sits at 93-97 % while the FMA pipe idles at 10 %.  The additions are therefore issued as IMAD (x*1+y, `one` is a
-// runtime 1 so ptxas keeps the multiply): 8 ALU + 6 FMA ops per G, which lowers the pipe bound from 12/16 to 8/16 cycles.
-__device__ __forceinline__ uint32_t fadd(uint32_t x, uint32_t y, uint32_t one) {
-  uint32_t r;
-  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(one), "r"(y));
-  return r;
-}
-// Tried and rejected (tools/merkle_bench.py, B200): rotating by 16 on the FMA pipe as x*2^16 -> lo+hi (IMAD.WIDE + IMAD) to take
-// one of the eight ALU ops per G off the ALU pipe: 17.8-20.0 G compressions/s against 19.8-22.3 with the PRMT below.
-#define B2S_G(a, b, c, d, x, y)      \
-  do {                               \
-    a = fadd(b, a, one);             \
-    a = fadd((x), a, one);           \
-    d = rotr16(d ^ a);               \
-    c = fadd(d, c, one);             \
-    b = rotr12(b ^ c);               \
-    a = fadd(b, a, one);             \
-    a = fadd((y), a, one);           \
-    d = rotr8(d ^ a);                \
-    c = fadd(d, c, one);             \
-    b = rotr7(b ^ c);                \
-  } while (0)
-
-#define B2S_ROUND(s0, s1, s2, s3, s4, s5, s6, s7, s8, s9, s10, s11, s12, s13, s14, s15) \
-  B2S_G(v0, v4, v8, v12, m[s0], m[s1]);                                                  \
-  B2S_G(v1, v5, v9, v13, m[s2], m[s3]);                                                  \
-  B2S_G(v2, v6, v10, v14, m[s4], m[s5]);                                                 \
-  B2S_G(v3, v7, v11, v15, m[s6], m[s7]);                                                 \
-  B2S_G(v0, v5, v10, v15, m[s8], m[s9]);                                                 \
-  B2S_G(v1, v6, v11, v12, m[s10], m[s11]);                                               \
-  B2S_G(v2, v7, v8, v13, m[s12], m[s13]);                                                \
-  B2S_G(v3, v4, v9, v14, m[s14], m[s15]);
-
-// h <- F(h, m, 0, 0, 0, 0)
-__device__ __forceinline__ void b2s_compress(uint32_t h[8], const uint32_t m[16], uint32_t one) {
-  uint32_t v0 = h[0], v1 = h[1], v2 = h[2], v3 = h[3], v4 = h[4], v5 = h[5], v6 = h[6], v7 = h[7];
-  uint32_t v8 = 0x6A09E667u, v9 = 0xBB67AE85u, v10 = 0x3C6EF372u, v11 = 0xA54FF53Au;
-  uint32_t v12 = 0x510E527Fu, v13 = 0x9B05688Cu, v14 = 0x1F83D9ABu, v15 = 0x5BE0CD19u;
-  B2S_ROUND(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15)
-  B2S_ROUND(14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3)
-  B2S_ROUND(11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4)
-  B2S_ROUND(7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8)
-  B2S_ROUND(9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13)
-  B2S_ROUND(2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9)
-  B2S_ROUND(12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11)
-  B2S_ROUND(13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10)
-  B2S_ROUND(6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5)
-  B2S_ROUND(10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0)
-  h[0] ^= v0 ^ v8;  h[1] ^= v1 ^ v9;  h[2] ^= v2 ^ v10; h[3] ^= v3 ^ v11;
-  h[4] ^= v4 ^ v12; h[5] ^= v5 ^ v13; h[6] ^= v6 ^ v14; h[7] ^= v7 ^ v15;
-}
-
 // rep_log > 0: every column repeats each value 2^rep_log times and so do the children, hence so do the nodes of this layer;
 // a thread hashes the first node of its group and stores the digest 2^rep_log times (rows = number of groups).
-template <bool HAS_PREV>
+// NC4: the layer injects at most four columns (every FRI layer, the composition tree, one IsFirst column per preprocessed
+// layer, most interaction layers): one column block whose message words 4..15 are compile-time zeros.
+template <bool HAS_PREV, bool NC4>
 __global__ void __launch_bounds__(256) commit_layer_kernel(uint32_t rows, const uint32_t* __restrict__ prev,
                                                            const uint32_t* const* __restrict__ cols, uint32_t ncols,
                                                            uint32_t* __restrict__ out, uint32_t one, uint32_t rep_log) {
@@ -89,10 +35,18 @@ __global__ void __launch_bounds__(256) commit_layer_kernel(uint32_t rows, const 
     m[8] = c.x; m[9] = c.y; m[10] = c.z; m[11] = c.w; m[12] = d.x; m[13] = d.y; m[14] = d.z; m[15] = d.w;
     b2s_compress(h, m, one);
   }
-  for (uint32_t c0 = 0; c0 < ncols; c0 += 16) {
+  if (NC4) {
+    if (ncols) {
 #pragma unroll
-    for (uint32_t j = 0; j < 16; j++) m[j] = (c0 + j < ncols) ? __ldg(cols[c0 + j] + i) : 0u;
-    b2s_compress(h, m, one);
+      for (uint32_t j = 0; j < 4; j++) m[j] = (j < ncols) ? __ldg(cols[j] + i) : 0u;
+      b2s_compress<4>(h, m, one);
+    }
+  } else {
+    for (uint32_t c0 = 0; c0 < ncols; c0 += 16) {
+#pragma unroll
+      for (uint32_t j = 0; j < 16; j++) m[j] = (c0 + j < ncols) ? __ldg(cols[c0 + j] + i) : 0u;
+      b2s_compress(h, m, one);
+    }
   }
   uint4* o = reinterpret_cast<uint4*>(out) + (size_t)i * 2;
   const uint4 lo = make_uint4(h[0], h[1], h[2], h[3]), hi = make_uint4(h[4], h[5], h[6], h[7]);
@@ -105,8 +59,15 @@ int launch_commit_layer(uint32_t log_size, const uint32_t* prev, const uint32_t*
   uint32_t rows = 1u << (log_size - rep_log);
   uint32_t threads = rows < 256 ? (rows < 32 ? 32 : rows) : 256;
   uint32_t blocks = (rows + threads - 1) / threads;
-  if (prev) commit_layer_kernel<true><<<blocks, threads, 0, st>>>(rows, prev, cols, ncols, out, 1u, rep_log);
-  else commit_layer_kernel<false><<<blocks, threads, 0, st>>>(rows, prev, cols, ncols, out, 1u, rep_log);
+  static const bool generic_only = getenv("SC_MERKLE_GENERIC") != nullptr;   // A/B switch for tools/merkle_bench.py
+  const bool nc4 = ncols <= 4 && !generic_only;
+  if (prev) {
+    if (nc4) commit_layer_kernel<true, true><<<blocks, threads, 0, st>>>(rows, prev, cols, ncols, out, 1u, rep_log);
+    else commit_layer_kernel<true, false><<<blocks, threads, 0, st>>>(rows, prev, cols, ncols, out, 1u, rep_log);
+  } else {
+    if (nc4) commit_layer_kernel<false, true><<<blocks, threads, 0, st>>>(rows, prev, cols, ncols, out, 1u, rep_log);
+    else commit_layer_kernel<false, false><<<blocks, threads, 0, st>>>(rows, prev, cols, ncols, out, 1u, rep_log);
+  }
   g_launch_count++;
   return (int)cudaGetLastError();
 }
