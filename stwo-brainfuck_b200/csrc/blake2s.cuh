@@ -47,11 +47,12 @@ __device__ __forceinline__ uint32_t fadd(uint32_t x, uint32_t y, uint32_t one) {
   B2S_G(v3, v4, v9, v14, s14, s15);
 
 // h <- F(h, m, 0, 0, 0, 0)
+// t0 / f0: byte counter and final-block flag of the real Blake2s hash (the channel); zero — and folded away — for Merkle nodes
 template <int NZ = 16>
-__device__ __forceinline__ void b2s_compress(uint32_t h[8], const uint32_t m[16], uint32_t one) {
+__device__ __forceinline__ void b2s_compress(uint32_t h[8], const uint32_t m[16], uint32_t one, uint32_t t0 = 0, uint32_t f0 = 0) {
   uint32_t v0 = h[0], v1 = h[1], v2 = h[2], v3 = h[3], v4 = h[4], v5 = h[5], v6 = h[6], v7 = h[7];
   uint32_t v8 = 0x6A09E667u, v9 = 0xBB67AE85u, v10 = 0x3C6EF372u, v11 = 0xA54FF53Au;
-  uint32_t v12 = 0x510E527Fu, v13 = 0x9B05688Cu, v14 = 0x1F83D9ABu, v15 = 0x5BE0CD19u;
+  uint32_t v12 = 0x510E527Fu ^ t0, v13 = 0x9B05688Cu, v14 = 0x1F83D9ABu ^ f0, v15 = 0x5BE0CD19u;
   B2S_ROUND(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15)
   B2S_ROUND(14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3)
   B2S_ROUND(11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4)

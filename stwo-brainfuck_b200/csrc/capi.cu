@@ -667,7 +667,32 @@ int32_t merkle_commit_impl(sc_ctx* ctx, sc_col* const* cols, uint32_t n, uint32_
   first[0] = (uint32_t)cp.size();
   const uint32_t* const* dp = nullptr;
   if (!cp.empty()) { void* d; int32_t r = stage(ctx, cp.data(), cp.size() * sizeof(void*), &d); if (r) return r; dp = (const uint32_t* const*)d; }
+  // layers top+1 .. sub_from (at most 2^MERKLE_SUB_FROM nodes, none of them in the repeated region): one sub-tree launch
+  int sub_from = -1;
+  if (top == (int)MERKLE_TOP_LOG && !getenv("SC_MERKLE_NO_SUBTREE")) {
+    sub_from = (int)std::min<uint32_t>(max_log > log_repeat ? max_log - log_repeat : 0, MERKLE_SUB_FROM);
+    if (log_repeat == 0) sub_from = (int)std::min<uint32_t>(max_log, MERKLE_SUB_FROM);
+    if (sub_from - top < 2) sub_from = -1;   // nothing to gain over one or two plain launches
+  }
   for (int lg = (int)max_log; lg > top; lg--) {
+    if (lg == sub_from) {
+      const uint32_t S = (uint32_t)(sub_from - top - 1);
+      uint32_t col_off[MERKLE_SUB_MAX + 2];
+      uint32_t* outp[MERKLE_SUB_MAX + 1];
+      for (uint32_t k = 0; k <= S; k++) {
+        int l2 = sub_from - (int)k;
+        col_off[k] = first[l2 + 1] - first[sub_from + 1];
+        int32_t r = new_col(ctx, 8ull << l2, &layers_out[l2]);
+        if (r) return r;
+        outp[k] = layers_out[l2]->d;
+      }
+      col_off[S + 1] = first[sub_from - (int)S] - first[sub_from + 1];
+      ProfScope ps_(ctx, "merkle_commit_layer");
+      CKL(launch_commit_subtree((uint32_t)sub_from, S, sub_from == (int)max_log ? nullptr : layers_out[sub_from + 1]->d, dp + first[sub_from + 1],
+                                col_off, outp, ctx->st));
+      lg = top + 1;   // the loop's decrement leaves the walk at `top`
+      continue;
+    }
     uint32_t depth = max_log - (uint32_t)lg, rep = log_repeat > depth ? log_repeat - depth : 0;
     int32_t r = new_col(ctx, 8ull << lg, &layers_out[lg]);
     if (r) return r;

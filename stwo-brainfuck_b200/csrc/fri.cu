@@ -14,35 +14,11 @@
 namespace sb {
 
 // ---------------------------------------------------------------- Blake2s-256 (the real hash: IV, parameter block, counter, final flag)
-__constant__ uint8_t c_b2s_sigma[10][16] = {
-    {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3},
-    {11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4}, {7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8},
-    {9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13}, {2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9},
-    {12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11}, {13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10},
-    {6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5}, {10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0}};
-__device__ __forceinline__ uint32_t ch_ror(uint32_t x, int r) { return (x >> r) | (x << (32 - r)); }
-// out = Blake2s-256 of the 64-byte message m (one final block: t = 64, f0 = ~0).  Not performance relevant (one thread).
+// out = Blake2s-256 of the 64-byte message m (one final block: t = 64, f0 = ~0) on the unrolled compression of blake2s.cuh
 __device__ __noinline__ void chan_hash64(const uint32_t m[16], uint32_t out[8]) {
-  const uint32_t iv[8] = {0x6A09E667u, 0xBB67AE85u, 0x3C6EF372u, 0xA54FF53Au, 0x510E527Fu, 0x9B05688Cu, 0x1F83D9ABu, 0x5BE0CD19u};
-  uint32_t h[8], v[16];
-  for (int i = 0; i < 8; i++) { h[i] = iv[i]; v[8 + i] = iv[i]; }
-  h[0] ^= 0x01010020u;
-  for (int i = 0; i < 8; i++) v[i] = h[i];
-  v[12] ^= 64u; v[14] ^= 0xFFFFFFFFu;
-  for (int r = 0; r < 10; r++) {
-    const uint8_t* s = c_b2s_sigma[r];
-#pragma unroll 1
-    for (int g = 0; g < 8; g++) {
-      const int a = g & 3, col = g < 4;
-      const int b = 4 + ((a + (col ? 0 : 1)) & 3), c = 8 + ((a + (col ? 0 : 2)) & 3), d = 12 + ((a + (col ? 0 : 3)) & 3);
-      const uint32_t x = m[s[2 * g]], y = m[s[2 * g + 1]];
-      v[a] = v[a] + v[b] + x; v[d] = ch_ror(v[d] ^ v[a], 16);
-      v[c] = v[c] + v[d];     v[b] = ch_ror(v[b] ^ v[c], 12);
-      v[a] = v[a] + v[b] + y; v[d] = ch_ror(v[d] ^ v[a], 8);
-      v[c] = v[c] + v[d];     v[b] = ch_ror(v[b] ^ v[c], 7);
-    }
-  }
-  for (int i = 0; i < 8; i++) out[i] = h[i] ^ v[i] ^ v[8 + i];
+  uint32_t h[8] = {0x6A09E667u ^ 0x01010020u, 0xBB67AE85u, 0x3C6EF372u, 0xA54FF53Au, 0x510E527Fu, 0x9B05688Cu, 0x1F83D9ABu, 0x5BE0CD19u};
+  b2s_compress(h, m, 1u, 64u, 0xFFFFFFFFu);
+  for (int i = 0; i < 8; i++) out[i] = h[i];
 }
 // Blake2sMerkleChannel::mix_root followed by Blake2sChannel::draw_felt: digest <- H(digest || root); then H(digest || counter)
 // with counter 0, 1, ... until all eight words are < 2P; the first four, reduced, are the felt.

@@ -24,6 +24,10 @@ int launch_evaluate(const uint32_t* const* coeffs, uint32_t* const* out, uint32_
 
 // merkle.cu
 constexpr uint32_t MERKLE_TOP_LOG = 9;  // layers of <= 2^9 nodes are hashed by one CTA in a single launch (merkle.cu)
+constexpr uint32_t MERKLE_SUB_MAX = 9;   // a CTA of the sub-tree kernel owns up to 2^9 nodes of its first layer (16 KB + 8 KB of digests)
+constexpr uint32_t MERKLE_SUB_FROM = 19; // layers of more than 2^19 nodes keep one launch each: they fill the machine on their own
+int launch_commit_subtree(uint32_t L, uint32_t S, const uint32_t* prev, const uint32_t* const* cols, const uint32_t* col_off,
+                          uint32_t* const* out, cudaStream_t st);
 int launch_commit_top(uint32_t top_log, const uint32_t* prev, const uint32_t* const* cols, const uint32_t* col_off,
                       uint32_t* const* out, cudaStream_t st);
 int launch_commit_layer(uint32_t log_size, const uint32_t* prev, const uint32_t* const* cols, uint32_t ncols,

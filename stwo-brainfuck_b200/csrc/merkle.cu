@@ -113,6 +113,75 @@ __global__ void __launch_bounds__(1 << MERKLE_TOP_LOG) commit_top_kernel(TopArgs
     prev = a.out[k];
   }
 }
+// The middle of a tree in one launch: CTA b owns nodes [b << S, (b + 1) << S) of layer L and walks its sub-tree up to the one
+// node of layer L - S, handing digests from layer to layer through shared memory (every layer is also written to global
+// memory: decommitment reads them).  Layers of 2^10 .. 2^19 nodes cost a launch each otherwise — 5-6 us apiece against
+// 0.7 us of hashing once they stop filling the machine — and a proof has some thirty trees.
+struct SubtreeArgs {
+  const uint32_t* prev;                     // layer L + 1 (NULL when L is the deepest layer)
+  const uint32_t* const* cols;              // column pointers of layers L, L-1, ..., L-S, concatenated
+  uint32_t col_off[MERKLE_SUB_MAX + 2];     // columns of layer L - k are cols[col_off[k] .. col_off[k+1])
+  uint32_t* out[MERKLE_SUB_MAX + 1];        // out[k] = layer L - k
+  uint32_t L, S, one;
+};
+__device__ __forceinline__ void subtree_columns(uint32_t h[8], uint32_t m[16], const uint32_t* const* cols, uint32_t c_lo, uint32_t c_hi,
+                                                uint32_t node, uint32_t one) {
+  if (c_hi - c_lo <= 4) {
+    if (c_hi > c_lo) {
+#pragma unroll
+      for (uint32_t j = 0; j < 4; j++) m[j] = (c_lo + j < c_hi) ? __ldg(cols[c_lo + j] + node) : 0u;
+      b2s_compress<4>(h, m, one);
+    }
+    return;
+  }
+  for (uint32_t c0 = c_lo; c0 < c_hi; c0 += 16) {
+#pragma unroll
+    for (uint32_t j = 0; j < 16; j++) m[j] = (c0 + j < c_hi) ? __ldg(cols[c0 + j] + node) : 0u;
+    b2s_compress(h, m, one);
+  }
+}
+__global__ void __launch_bounds__(256) commit_subtree_kernel(SubtreeArgs a) {
+  extern __shared__ uint4 sub_sm[];
+  uint4* cur = sub_sm;                       // digests of the layer below: two uint4 per node
+  uint4* nxt = sub_sm + (2u << a.S);
+  for (uint32_t k = 0; k <= a.S; k++) {
+    const uint32_t cnt = 1u << (a.S - k), base = blockIdx.x << (a.S - k);
+    for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) {
+      const uint32_t node = base + j;
+      uint32_t h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      uint32_t m[16];
+      if (k > 0 || a.prev) {
+        uint4 x, y, z, w;
+        if (k == 0) { const uint4* pc = reinterpret_cast<const uint4*>(a.prev) + (size_t)node * 4; x = __ldg(pc); y = __ldg(pc + 1); z = __ldg(pc + 2); w = __ldg(pc + 3); }
+        else { const uint4* pc = cur + (size_t)j * 4; x = pc[0]; y = pc[1]; z = pc[2]; w = pc[3]; }
+        m[0] = x.x; m[1] = x.y; m[2] = x.z; m[3] = x.w; m[4] = y.x; m[5] = y.y; m[6] = y.z; m[7] = y.w;
+        m[8] = z.x; m[9] = z.y; m[10] = z.z; m[11] = z.w; m[12] = w.x; m[13] = w.y; m[14] = w.z; m[15] = w.w;
+        b2s_compress(h, m, a.one);
+      }
+      subtree_columns(h, m, a.cols, a.col_off[k], a.col_off[k + 1], node, a.one);
+      const uint4 lo = make_uint4(h[0], h[1], h[2], h[3]), hi = make_uint4(h[4], h[5], h[6], h[7]);
+      uint4* o = reinterpret_cast<uint4*>(a.out[k]) + (size_t)node * 2;
+      o[0] = lo; o[1] = hi;
+      nxt[2 * j] = lo; nxt[2 * j + 1] = hi;
+    }
+    __syncthreads();
+    uint4* t = cur; cur = nxt; nxt = t;
+  }
+}
+// layers L, L-1, ..., L-S (S <= MERKLE_SUB_MAX); cols / col_off / out as in SubtreeArgs (col_off and out are host arrays)
+int launch_commit_subtree(uint32_t L, uint32_t S, const uint32_t* prev, const uint32_t* const* cols, const uint32_t* col_off,
+                          uint32_t* const* out, cudaStream_t st) {
+  if (S > MERKLE_SUB_MAX || S > L) return -1;
+  SubtreeArgs a;
+  a.prev = prev; a.cols = cols; a.L = L; a.S = S; a.one = 1u;
+  for (uint32_t k = 0; k <= S + 1; k++) a.col_off[k] = col_off[k];
+  for (uint32_t k = 0; k <= S; k++) a.out[k] = out[k];
+  const uint32_t per_cta = 1u << S, threads = per_cta < 256 ? (per_cta < 32 ? 32 : per_cta) : 256;
+  const size_t smem = (size_t)(4u << S) * sizeof(uint4);   // two buffers of 2^S nodes (the second needs half of it)
+  commit_subtree_kernel<<<1u << (L - S), threads, smem, st>>>(a); g_launch_count++;
+  return (int)cudaGetLastError();
+}
+
 // cols: device array of the column pointers (layer top_log first); col_off / out as in TopArgs (host arrays).
 int launch_commit_top(uint32_t top_log, const uint32_t* prev, const uint32_t* const* cols, const uint32_t* col_off,
                       uint32_t* const* out, cudaStream_t st) {
