@@ -25,6 +25,9 @@ int32_t sc_all_to_all(sc_ctx* ctx, sc_comm* comm, const sc_col* send, const uint
 int32_t sc_all_gather(sc_ctx* ctx, sc_comm* comm, const sc_col* send, sc_col* recv, uint64_t n);   /* Merkle sub-roots */
 int32_t sc_allreduce_host_u32(sc_ctx* ctx, sc_comm* comm, uint32_t* buf, uint64_t n);              /* tiny host tables */
 
+/* the send buffer of sc_all_to_all in one launch: for every destination d, block d = the rows [d*seg_j, (d+1)*seg_j) of each
+ * owned column j in order (the whole column when sharded[j] == 0) */
+int32_t sc_pack_exchange(sc_ctx* ctx, sc_col* const* cols, const uint64_t* segs, const uint8_t* sharded, uint32_t n, uint32_t world, sc_col* send);
 int32_t sc_col_copy(sc_ctx* ctx, sc_col* dst, uint64_t dst_off, const sc_col* src, uint64_t src_off, uint64_t n);
 int32_t sc_col_view(sc_ctx* ctx, sc_col* col, uint64_t off, uint64_t n, sc_col** out);   /* non-owning slice, off % 4 == 0 */
 
@@ -33,6 +36,20 @@ int32_t sc_fold_line_range(sc_ctx* ctx, sc_col* const src[4], uint32_t log, uint
                            const sc_twiddles* tw, sc_col* dst_out[4]);
 int32_t sc_fold_circle_into_line_range(sc_ctx* ctx, sc_col* const src[4], uint32_t log, uint64_t out_off, uint64_t n_out,
                                        const uint32_t alpha[4], const sc_twiddles* tw, sc_col* const dst[4]);
+/* The FRI transcript as a device object, for callers that drive the commit loop layer by layer (the sharded prover): the
+ * channel digest, one folding coefficient per mixed root and a copy of every root live in device memory, so a layer never
+ * waits for a host round trip; the host reads the roots once (sc_dchan_finish, which also frees the object) and replays its
+ * own channel.  Same arithmetic as Blake2sMerkleChannel::mix_root + Blake2sChannel::draw_felt (upstream core/vcs/
+ * blake2_merkle.rs, core/channel/blake2s.rs).  The *_dc folds take coefficient #k of the object. */
+typedef struct sc_dchan sc_dchan;
+int32_t sc_dchan_create(sc_ctx* ctx, const uint32_t digest[8], uint32_t max_mixes, sc_dchan** out);
+int32_t sc_dchan_mix_root_draw(sc_ctx* ctx, sc_dchan* dc, const sc_col* root_col);
+int32_t sc_dchan_finish(sc_ctx* ctx, sc_dchan* dc, uint32_t* roots_out);
+const uint32_t* sc_dchan_coeff_ptr(const sc_dchan* dc, uint32_t k);   /* device address of coefficient #k (4 words), NULL if not drawn yet */
+int32_t sc_fold_line_range_dc(sc_ctx* ctx, sc_col* const src[4], uint32_t log, uint64_t out_off, uint64_t n_out, const sc_dchan* dc, uint32_t k,
+                              const sc_twiddles* tw, sc_col* dst_out[4]);
+int32_t sc_fold_circle_into_line_range_dc(sc_ctx* ctx, sc_col* const src[4], uint32_t log, uint64_t out_off, uint64_t n_out, const sc_dchan* dc,
+                                          uint32_t k, const sc_twiddles* tw, sc_col* const dst[4]);
 /* QuotientOps on a row range (row_off, n_rows multiples of 4) */
 int32_t sc_accumulate_quotients_range(sc_ctx* ctx, uint32_t log, uint64_t row_off, uint64_t n_rows, sc_col* const* cols, uint32_t n,
                                       const uint32_t random_coeff[4], const uint32_t* batch_points, const uint32_t* batch_sizes,

@@ -140,3 +140,10 @@ static inline int32_t new_col(sc_ctx* ctx, uint64_t len, sc_col** out) {
 // MerkleProver::commit over mixed-size columns (capi.cu): layers_out[k] = layer of log size k; root_out may be NULL (no read-back).
 extern "C" int32_t merkle_commit_impl(sc_ctx* ctx, sc_col* const* cols, uint32_t n, uint32_t log_repeat, sc_col** layers_out,
                                         uint32_t* max_log_out, uint32_t root_out[8]);
+
+// Device-resident transcript for the FRI commit loop (fri_capi.cu): digest, one coefficient per mix, a copy of every root.
+struct sc_dchan {
+  sc_col* buf = nullptr;     // 8 (digest) + 4 * max (coefficients) + 8 * max (roots) words
+  uint32_t max = 0, n = 0;   // mixes allowed / done
+};
+extern "C" const uint32_t* sc_dchan_coeff_ptr(const sc_dchan* dc, uint32_t k);

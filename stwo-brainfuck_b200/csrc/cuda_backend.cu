@@ -176,6 +176,29 @@ struct CudaBackendImpl : Backend {
     ck(sc_fold_circle_into_line(ctx, (sc_col* const*)src.data(), log, (const uint32_t*)&alpha, tw, (sc_col* const*)dst.data()));
   }
   bool fused_fri = true;   // SBF_NO_FUSED_FRI clears it (A/B measurements)
+  void* dchan_begin(const Hash& digest, uint32_t max_mixes) override {
+    if (!fused_fri) return nullptr;
+    sc_dchan* dc = nullptr;
+    ck(sc_dchan_create(ctx, digest.data(), max_mixes, &dc));
+    return dc;
+  }
+  void dchan_mix_root_draw(void* dc, Col root_col) override { ck(sc_dchan_mix_root_draw(ctx, (sc_dchan*)dc, h(root_col))); }
+  std::vector<Hash> dchan_finish(void* dc, uint32_t n_mixes) override {
+    std::vector<uint32_t> w(8 * (size_t)n_mixes);
+    ck(sc_dchan_finish(ctx, (sc_dchan*)dc, w.data()));
+    std::vector<Hash> out(n_mixes);
+    for (uint32_t i = 0; i < n_mixes; i++) memcpy(out[i].data(), &w[8 * i], 32);
+    return out;
+  }
+  std::array<Col, 4> fold_line_range_dc(const std::array<Col, 4>& src, uint32_t log, size_t off, size_t n_out, void* dc, uint32_t k) override {
+    std::array<Col, 4> out;
+    ck(sc_fold_line_range_dc(ctx, (sc_col* const*)src.data(), log, off, n_out, (sc_dchan*)dc, k, tw, (sc_col**)out.data()));
+    return out;
+  }
+  void fold_circle_into_line_range_dc(const std::array<Col, 4>& dst, const std::array<Col, 4>& src, uint32_t log, size_t off, size_t n_out, void* dc,
+                                      uint32_t k) override {
+    ck(sc_fold_circle_into_line_range_dc(ctx, (sc_col* const*)src.data(), log, off, n_out, (sc_dchan*)dc, k, tw, (sc_col* const*)dst.data()));
+  }
   bool fri_commit(const std::vector<std::pair<uint32_t, std::array<Col, 4>>>& quotients, const Hash& digest, uint32_t last_log,
                   FriCommitResult& out) override {
     if (!fused_fri || quotients.empty()) return false;
@@ -261,6 +284,10 @@ struct CudaBackendImpl : Backend {
     sc_col* o;
     ck(sc_merkle_commit_layer_repeated(ctx, log, h(prev), (sc_col* const*)cols.data(), (uint32_t)cols.size(), rep, &o));
     return o;
+  }
+  void pack_exchange(Col send, const std::vector<Col>& cols, const std::vector<size_t>& segs, const std::vector<uint8_t>& sharded) override {
+    std::vector<uint64_t> sg(segs.begin(), segs.end());
+    ck(sc_pack_exchange(ctx, (sc_col* const*)cols.data(), sg.data(), sharded.data(), (uint32_t)cols.size(), (uint32_t)world(), h(send)));
   }
   void all_to_all(Col send, const std::vector<size_t>& sc, Col recv, const std::vector<size_t>& rc) override {
     if (!comm) { copy(recv, 0, send, 0, sc[0]); return; }
@@ -434,6 +461,7 @@ int32_t sbf_prove_sharded(sc_ctx* ctx, sc_comm* comm, const char* code, const ui
     TraceSource run_vm = [&]() { return run_machine(ctx, vm, log_max_rows, host_tables, vm_ms); };
     CudaBackendImpl B(ctx);
     B.host_tables = host_tables;
+    B.fused_fri = !(flags & 32u);   // SBF_NO_FUSED_FRI
     B.comm = comm;
     ProverConfig cfg;
     cfg.log_max_rows = log_max_rows;

@@ -3,6 +3,44 @@
 
 extern "C" {
 
+// ---------------------------------------------------------------- the transcript as a device object (layer-by-layer callers)
+int32_t sc_dchan_create(sc_ctx* ctx, const uint32_t digest[8], uint32_t max_mixes, sc_dchan** out) {
+  ENTER();
+  if (!digest || !out || !max_mixes || max_mixes > 4096) return fail(SC_EINVAL, "dchan_create: bad argument");
+  sc_dchan* dc = new sc_dchan;
+  dc->max = max_mixes;
+  int32_t r = new_col(ctx, 8 + 12 * (uint64_t)max_mixes, &dc->buf);
+  if (r) { delete dc; return r; }
+  void* st = nullptr;
+  r = stage(ctx, digest, 32, &st);
+  if (r) { sc_col_free(ctx, dc->buf); delete dc; return r; }
+  CK(cudaMemcpyAsync(dc->buf->d, st, 32, cudaMemcpyDeviceToDevice, ctx->st));
+  *out = dc;
+  return SC_OK;
+}
+const uint32_t* sc_dchan_coeff_ptr(const sc_dchan* dc, uint32_t k) { return dc && k < dc->n ? dc->buf->d + 8 + 4 * (size_t)k : nullptr; }
+// Blake2sMerkleChannel::mix_root(root_col[0..8)) then Blake2sChannel::draw_felt -> coefficient #n (n = mixes so far), on the stream
+int32_t sc_dchan_mix_root_draw(sc_ctx* ctx, sc_dchan* dc, const sc_col* root_col) {
+  ENTER();
+  if (!dc || !root_col || root_col->len < 8) return fail(SC_EINVAL, "dchan_mix_root_draw: bad argument");
+  if (dc->n >= dc->max) return fail(SC_EINVAL, "dchan_mix_root_draw: more mixes than the channel was created for");
+  uint32_t* base = dc->buf->d;
+  { ProfScope ps(ctx, "fri_channel");
+    CKL(launch_fri_channel(base, root_col->d, base + 8 + 4 * (size_t)dc->n, base + 8 + 4 * (size_t)dc->max + 8 * (size_t)dc->n, ctx->st)); }
+  dc->n++;
+  return SC_OK;
+}
+// Waits for the stream and returns the roots mixed so far (8 words each); frees the channel.
+int32_t sc_dchan_finish(sc_ctx* ctx, sc_dchan* dc, uint32_t* roots_out) {
+  if (!dc) return SC_OK;
+  ENTER();
+  int32_t r = SC_OK;
+  if (roots_out && dc->n) r = sc_col_read(ctx, dc->buf, 8 + 4 * (uint64_t)dc->max, 8 * (uint64_t)dc->n, roots_out);
+  sc_col_free(ctx, dc->buf);
+  delete dc;
+  return r;
+}
+
 // FriProver::commit (stwo-prover 0.1.1 @ 31e8dbc core/fri.rs; reached from prover::prove, crates/brainfuck_prover/src/
 // brainfuck_air/mod.rs:732) with the transcript kept on the device — see fri.cu.
 int32_t sc_fri_commit(sc_ctx* ctx, const sc_twiddles* tw, sc_col* const* quot_cols, const uint32_t* quot_logs, uint32_t nq,

@@ -123,6 +123,18 @@ struct Backend {
   };
   virtual bool fri_commit(const std::vector<std::pair<uint32_t, std::array<Col, 4>>>& quotients, const Hash& channel_digest, uint32_t last_log,
                           FriCommitResult& out) { (void)quotients; (void)channel_digest; (void)last_log; (void)out; return false; }
+  // The same idea for drivers that walk the layers themselves (prover_sharded.hpp): a device-resident transcript.  dchan_begin
+  // returns NULL when the backend has none.  Coefficient #k is the one drawn after the k-th mix (k = 0: the circle fold's).
+  virtual void* dchan_begin(const Hash& channel_digest, uint32_t max_mixes) { (void)channel_digest; (void)max_mixes; return nullptr; }
+  virtual void dchan_mix_root_draw(void* dc, Col root_col) { (void)dc; (void)root_col; }
+  virtual std::vector<Hash> dchan_finish(void* dc, uint32_t n_mixes) { (void)dc; (void)n_mixes; return {}; }   // waits; frees dc
+  virtual std::array<Col, 4> fold_line_range_dc(const std::array<Col, 4>& src, uint32_t log, size_t out_off, size_t n_out, void* dc, uint32_t k) {
+    (void)src; (void)log; (void)out_off; (void)n_out; (void)dc; (void)k; throw std::runtime_error("no device channel");
+  }
+  virtual void fold_circle_into_line_range_dc(const std::array<Col, 4>& dst, const std::array<Col, 4>& src, uint32_t log, size_t out_off, size_t n_out,
+                                              void* dc, uint32_t k) {
+    (void)dst; (void)src; (void)log; (void)out_off; (void)n_out; (void)dc; (void)k; throw std::runtime_error("no device channel");
+  }
   // QuotientOps
   virtual std::array<Col, 4> accumulate_quotients(uint32_t log, const std::vector<Col>& cols, QM31 random_coeff,
                                                   const SampleBatchesFlat& b) = 0;
@@ -157,6 +169,15 @@ struct Backend {
   virtual Col alloc(size_t n) = 0;                                            // uninitialised
   virtual Col view(Col c, size_t off, size_t n) = 0;                          // non-owning slice (free_col drops the handle)
   virtual void copy(Col dst, size_t dst_off, Col src, size_t src_off, size_t n) = 0;
+  // send[d * per_dest + off_j ..) = rows [d * seg_j, (d+1) * seg_j) of cols[j] (the whole column when !sharded[j]), per_dest = sum of segs
+  virtual void pack_exchange(Col send, const std::vector<Col>& cols, const std::vector<size_t>& segs, const std::vector<uint8_t>& sharded) {
+    size_t per = 0;
+    for (size_t x : segs) per += x;
+    for (int d = 0; d < world(); d++) {
+      size_t o = 0;
+      for (size_t j = 0; j < cols.size(); j++) { copy(send, (size_t)d * per + o, cols[j], sharded[j] ? (size_t)d * segs[j] : 0, segs[j]); o += segs[j]; }
+    }
+  }
   virtual void all_to_all(Col send, const std::vector<size_t>& send_counts, Col recv, const std::vector<size_t>& recv_counts) = 0;
   virtual void all_gather(Col send, Col recv, size_t n) = 0;
   virtual void allreduce_host(uint32_t* buf, size_t n) = 0;                   // sum; exactly one contributor per slot

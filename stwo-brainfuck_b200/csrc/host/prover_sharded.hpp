@@ -86,7 +86,7 @@ struct SMerkle {
 // rep: every column repeats each value 2^rep times (main trace); the deepest `rep` layers then hash one node per group.
 // before_root_read: called when all device work is queued, just before the blocking read of the root.
 inline SMerkle merkle_sharded(Backend& B, const ShardLayout& sl, const std::vector<RowCol>& cols, uint32_t rep = 0,
-                              const std::function<void()>& before_root_read = nullptr) {
+                              const std::function<void()>& before_root_read = nullptr, bool read_root = true) {
   SMerkle m;
   uint32_t maxL = 0;
   for (auto& c : cols) maxL = std::max(maxL, c.L);
@@ -120,7 +120,7 @@ inline SMerkle merkle_sharded(Backend& B, const ShardLayout& sl, const std::vect
     prev = layer;
   }
   if (before_root_read) before_root_read();
-  B.read(m.layers[0], 0, 8, m.root.data());
+  if (read_root) B.read(m.layers[0], 0, 8, m.root.data());   // otherwise the caller mixes it on the device (Backend::dchan_*)
   return m;
 }
 
@@ -160,10 +160,13 @@ inline void exchange_and_commit(Backend& B, const ShardLayout& sl, uint32_t log_
     size_t stot = 0, rtot = 0;
     for (int d = 0; d < N; d++) { stot += scount[d]; rtot += rcount[d]; }
     Col send = B.alloc(std::max<size_t>(stot, 4)), recv = B.alloc(std::max<size_t>(rtot, 4));
-    size_t so = 0;
-    for (int d = 0; d < N; d++)
-      for (auto& e : es)
-        if (e.owner == me) { B.copy(send, so, e.full, e.sharded ? (size_t)d * e.seg : 0, e.seg); so += e.seg; }
+    {
+      std::vector<Col> pc;
+      std::vector<size_t> ps;
+      std::vector<uint8_t> psh;
+      for (auto& e : es) if (e.owner == me) { pc.push_back(e.full); ps.push_back(e.seg); psh.push_back(e.sharded ? 1 : 0); }
+      B.pack_exchange(send, pc, ps, psh);   // one launch on CUDA instead of world x columns copies
+    }
     B.all_to_all(send, scount, recv, rcount);
     B.free_col(send);
     for (auto& e : es) if (e.owner == me) B.free_col(e.full);
@@ -612,9 +615,17 @@ inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_
   // ---- FRI commit
   std::vector<RowCol> first_cols;
   for (auto& q : quotients) for (auto& x : q.second) first_cols.push_back(x);
-  SMerkle fri_first = merkle_sharded(B, sl, first_cols);
-  ch.mix_root(fri_first.root);
-  QM31 circle_alpha = ch.draw_felt();
+  // The transcript of this phase runs on the device when the backend has a device channel (Backend::dchan_*): every rank
+  // mixes the (replicated) root of each layer and draws the folding coefficient in a one-thread kernel, the folds read it
+  // from device memory, and no layer waits for a read-back; the host replays its channel from the roots afterwards.
+  const uint32_t last_log = cfg.log_last_layer_degree_bound + cfg.log_blowup;
+  const uint32_t n_mixes = quotients[0].first - last_log;   // first layer + one per inner layer
+  void* dc = B.dchan_begin(ch.digest, n_mixes);
+  uint32_t mixes = 0;
+  SMerkle fri_first = merkle_sharded(B, sl, first_cols, 0, nullptr, dc == nullptr);
+  QM31 circle_alpha = q_zero();
+  if (dc) { B.dchan_mix_root_draw(dc, fri_first.layers[0]); mixes++; }
+  else { ch.mix_root(fri_first.root); circle_alpha = ch.draw_felt(); }
   struct InnerLayer { std::array<RowCol, 4> eval; uint32_t log; SMerkle tree; };
   std::vector<InnerLayer> inner;
   uint32_t line_log = quotients[0].first - 1;
@@ -632,23 +643,26 @@ inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_
     layer = line_cols(line_log, {B.zeros(len), B.zeros(len), B.zeros(len), B.zeros(len)});
   }
   size_t qi = 0;
-  const uint32_t last_log = cfg.log_last_layer_degree_bound + cfg.log_blowup;
   auto cols_of = [](const std::array<RowCol, 4>& r) { return std::array<Col, 4>{r[0].rows, r[1].rows, r[2].rows, r[3].rows}; };
   while (line_log > last_log) {
     while (qi < quotients.size() && quotients[qi].first - 1 == line_log) {
-      if (layer[0].sharded) B.fold_circle_into_line_range(cols_of(layer), cols_of(quotients[qi].second), quotients[qi].first,
-                                                          (size_t)me * layer[0].rows_len, layer[0].rows_len, circle_alpha);
+      const size_t off = layer[0].sharded ? (size_t)me * layer[0].rows_len : 0;
+      if (dc) B.fold_circle_into_line_range_dc(cols_of(layer), cols_of(quotients[qi].second), quotients[qi].first, off, layer[0].rows_len, dc, 0);
+      else if (layer[0].sharded) B.fold_circle_into_line_range(cols_of(layer), cols_of(quotients[qi].second), quotients[qi].first, off,
+                                                               layer[0].rows_len, circle_alpha);
       else B.fold_circle_into_line(cols_of(layer), cols_of(quotients[qi].second), quotients[qi].first, circle_alpha);
       qi++;
     }
     InnerLayer Lr{layer, line_log, {}};
-    Lr.tree = merkle_sharded(B, sl, std::vector<RowCol>(layer.begin(), layer.end()));
-    ch.mix_root(Lr.tree.root);
-    QM31 alpha = ch.draw_felt();
+    Lr.tree = merkle_sharded(B, sl, std::vector<RowCol>(layer.begin(), layer.end()), 0, nullptr, dc == nullptr);
+    QM31 alpha = q_zero();
+    if (dc) { B.dchan_mix_root_draw(dc, Lr.tree.layers[0]); mixes++; }
+    else { ch.mix_root(Lr.tree.root); alpha = ch.draw_felt(); }
     std::array<Col, 4> next;
     if (layer[0].sharded) {
       size_t n_out = layer[0].rows_len / 2;
-      next = B.fold_line_range(cols_of(layer), line_log, (size_t)me * n_out, n_out, alpha);
+      next = dc ? B.fold_line_range_dc(cols_of(layer), line_log, (size_t)me * n_out, n_out, dc, mixes - 1)
+                : B.fold_line_range(cols_of(layer), line_log, (size_t)me * n_out, n_out, alpha);
       if (!sl.line_sharded(line_log - 1)) {  // the layer becomes too small to shard: replicate it
         for (int k = 0; k < 4; k++) {
           Col fullc = B.alloc((size_t)1 << (line_log - 1));
@@ -658,11 +672,23 @@ inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_
         }
       }
     } else {
-      next = B.fold_line(cols_of(layer), line_log, alpha);
+      next = dc ? B.fold_line_range_dc(cols_of(layer), line_log, 0, (size_t)1 << (line_log - 1), dc, mixes - 1)
+                : B.fold_line(cols_of(layer), line_log, alpha);
     }
     line_log--;
     layer = line_cols(line_log, next);
     inner.push_back(std::move(Lr));
+  }
+  if (dc) {   // one read-back for the whole phase, then the host transcript catches up
+    std::vector<Hash> roots = B.dchan_finish(dc, mixes);
+    fri_first.root = roots[0];
+    ch.mix_root(roots[0]);
+    ch.draw_felt();
+    for (size_t i = 0; i < inner.size(); i++) {
+      inner[i].tree.root = roots[i + 1];
+      ch.mix_root(roots[i + 1]);
+      ch.draw_felt();
+    }
   }
   if (qi != quotients.size()) throw std::runtime_error("FRI: not all columns consumed");
   {

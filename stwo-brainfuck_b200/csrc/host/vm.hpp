@@ -93,7 +93,6 @@ struct Machine {
   ~Machine() { recycle(trace); }
 
   void execute() {
-    const size_t n = program.size();
     // Growing the trace from empty costs more than the run itself (reallocation + a page fault per 4 KB), so the buffer of
     // the previous proof is taken over when there is one; 2^20 + 1 rows is the most the AIR can take at LOG_MAX_ROWS 24
     // (the processor table holds one row per step) and untouched pages cost nothing.
@@ -104,62 +103,85 @@ struct Machine {
     }
     sink_len = 0;
     stats = TraceStats();
-    std::vector<uint32_t> last_seen(ram.size(), 0);  // clk + 1 of the last access of every cell (0: untouched)
-    uint32_t* seen = last_seen.data();
-    uint64_t mem_rows = 0;
-    uint32_t opc[256] = {0};
-    uint32_t max_mp = 0, max_ip = 0;
-    auto emit = [&](const Registers& x) {
-      if (sink) {
-        if (sink_len == sink_cap) throw std::runtime_error("component too large: processor (the trace does not fit the buffer)");
-        sink[sink_len++] = x;
-      } else trace.push_back(x);
-      const uint32_t l = seen[x.mp];
-      mem_rows += l ? (uint64_t)(x.clk + 1 - l) : 1;
-      seen[x.mp] = x.clk + 1;
-      max_mp = x.mp > max_mp ? x.mp : max_mp;
-      max_ip = x.ip > max_ip ? x.ip : max_ip;
-    };
+    if (sink) run<true>(); else run<false>();
+    if (!skip_inverses) fill_inverses();
+  }
+
+  // The interpreter loop.  Every register lives in a local for the whole run (the loop is the critical path of a proof on
+  // eight GPUs: the device waits for the trace once the program-independent phase is done); the statistics the table
+  // builders need (TraceStats) are kept on the way instead of in a second pass over the trace.
+  template <bool SINK>
+  void run() {
+    const size_t n = program.size();
     const uint32_t* prog = program.data();
     uint32_t* cells = ram.data();
     const uint32_t ram_size = (uint32_t)ram.size();
     if (r.mp >= ram_size) throw std::runtime_error("memory pointer out of range");
+    std::vector<uint32_t> last_seen(ram.size(), 0);  // clk + 1 of the last access of every cell (0: untouched)
+    uint32_t* seen = last_seen.data();
+    uint64_t mem_rows = 0;
+    uint32_t opc[256] = {0};
+    uint32_t clk = r.clk, ip = r.ip, mp = r.mp, mv = r.mv, max_mp = r.mp, max_ip = 0;
+    const uint32_t mvi0 = r.mvi;
+    Registers* out = sink;
+    size_t len = 0;
+    const size_t cap = sink_cap;
     // the pointer is range-checked when it moves; every access in between is to a checked cell
-    while (r.ip < n) {
-      r.ci = prog[r.ip];
-      r.ni = (r.ip == n - 1) ? 0 : prog[r.ip + 1];
-      emit(r);
-      opc[r.ci & 255u]++;
+    while (ip < n) {
+      const uint32_t ci = prog[ip], ni = (ip == n - 1) ? 0 : prog[ip + 1];
+      if (SINK) {
+        if (len == cap) throw std::runtime_error("component too large: processor (the trace does not fit the buffer)");
+        out[len++] = Registers{clk, ip, ci, ni, mp, mv, mvi0};
+      } else {
+        trace.push_back(Registers{clk, ip, ci, ni, mp, mv, mvi0});
+      }
+      const uint32_t l = seen[mp];
+      mem_rows += l ? (uint64_t)(clk + 1 - l) : 1;
+      seen[mp] = clk + 1;
+      max_ip = ip > max_ip ? ip : max_ip;
+      opc[ci & 255u]++;
       bool early = false;
-      switch (r.ci) {
-        case '>': r.mp = sb::m_add(r.mp, 1); if (r.mp >= ram_size) throw std::runtime_error("memory pointer out of range"); break;
-        case '<': r.mp = sb::m_sub(r.mp, 1); if (r.mp >= ram_size) throw std::runtime_error("memory pointer out of range"); break;
-        case '+': cells[r.mp] = sb::m_add(cells[r.mp], 1); break;
-        case '-': cells[r.mp] = sb::m_sub(cells[r.mp], 1); break;
+      switch (ci) {
+        case '>': mp = sb::m_add(mp, 1); if (mp >= ram_size) throw std::runtime_error("memory pointer out of range"); max_mp = mp > max_mp ? mp : max_mp; break;
+        case '<': mp = sb::m_sub(mp, 1); if (mp >= ram_size) throw std::runtime_error("memory pointer out of range"); max_mp = mp > max_mp ? mp : max_mp; break;
+        case '+': cells[mp] = sb::m_add(cells[mp], 1); break;
+        case '-': cells[mp] = sb::m_sub(cells[mp], 1); break;
         case ',':
           if (in_pos >= input.size()) throw std::runtime_error("input exhausted");
-          cells[r.mp] = input[in_pos++];
+          cells[mp] = input[in_pos++];
           break;
-        case '.': output.push_back((uint8_t)cells[r.mp]); break;
+        case '.': output.push_back((uint8_t)cells[mp]); break;
         case '[': {
-          uint32_t arg = program.at(r.ip + 1);
-          if (cells[r.mp] == 0) { r.ip = arg; early = true; } else r.ip += 1;
+          if (ip + 1 >= n) throw std::out_of_range("jump without an argument");
+          const uint32_t arg = prog[ip + 1];
+          if (cells[mp] == 0) { ip = arg; early = true; } else ip += 1;
           break;
         }
         case ']': {
-          uint32_t arg = program.at(r.ip + 1);
-          if (cells[r.mp] != 0) { r.ip = arg - 1; early = true; } else r.ip += 1;
+          if (ip + 1 >= n) throw std::out_of_range("jump without an argument");
+          const uint32_t arg = prog[ip + 1];
+          if (cells[mp] != 0) { ip = arg - 1; early = true; } else ip += 1;
           break;
         }
         default: throw std::runtime_error("invalid instruction");
       }
-      if (!early) r.mv = cells[r.mp];  // mvi is filled in afterwards (fill_inverses): it does not influence execution
-      r.clk += 1;
-      r.ip += 1;
+      if (!early) mv = cells[mp];  // mvi is filled in afterwards (fill_inverses): it does not influence execution
+      clk += 1;
+      ip += 1;
     }
-    r.ci = 0;
-    r.ni = 0;
-    emit(r);
+    // the final row: ci = ni = 0
+    {
+      const Registers last{clk, ip, 0, 0, mp, mv, mvi0};
+      if (SINK) {
+        if (len == cap) throw std::runtime_error("component too large: processor (the trace does not fit the buffer)");
+        out[len++] = last;
+      } else trace.push_back(last);
+      const uint32_t l = seen[mp];
+      mem_rows += l ? (uint64_t)(clk + 1 - l) : 1;
+      max_ip = ip > max_ip ? ip : max_ip;
+    }
+    if (SINK) sink_len = len;
+    r.clk = clk; r.ip = ip; r.ci = 0; r.ni = 0; r.mp = mp; r.mv = mv;
     stats.steps = n_rows();
     stats.memory_rows = mem_rows;
     static const char ops[8] = {']', '[', ',', '<', '-', '.', '+', '>'};
@@ -171,7 +193,6 @@ struct Machine {
       for (size_t i = 0; i < n_rows(); i++) if (p[i].ci == 0) { stats.zero_ci_index = i; break; }
     }
     stats.max_mp = max_mp; stats.max_ip = max_ip;
-    if (!skip_inverses) fill_inverses();
   }
 
   // One spare trace buffer per process: a finished machine leaves its (already faulted-in) buffer for the next one.

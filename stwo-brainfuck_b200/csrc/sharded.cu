@@ -17,8 +17,11 @@ struct Ptr4 { uint32_t* p[4]; };
 struct CPtr4 { const uint32_t* p[4]; };
 
 // ---- FRI folds on a row range: outputs [off, off + n) of the folded layer (twiddles are indexed by the global row)
-__global__ void fold_line_range_kernel(CPtr4 s, Ptr4 d, uint32_t log, QM31 alpha, const uint32_t* __restrict__ itw_end, size_t off, size_t n) {
+// alpha_p != NULL: the coefficient is read from device memory (sc_dchan: the transcript runs on the device)
+__global__ void fold_line_range_kernel(CPtr4 s, Ptr4 d, uint32_t log, QM31 alpha, const uint32_t* __restrict__ itw_end, size_t off, size_t n,
+                                       const uint32_t* __restrict__ alpha_p = nullptr) {
   const uint32_t* itw = itw_end - ((size_t)1 << log);
+  if (alpha_p) alpha = q_make(alpha_p[0], alpha_p[1], alpha_p[2], alpha_p[3]);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     uint2 c0 = reinterpret_cast<const uint2*>(s.p[0])[i], c1 = reinterpret_cast<const uint2*>(s.p[1])[i];
     uint2 c2 = reinterpret_cast<const uint2*>(s.p[2])[i], c3 = reinterpret_cast<const uint2*>(s.p[3])[i];
@@ -29,8 +32,9 @@ __global__ void fold_line_range_kernel(CPtr4 s, Ptr4 d, uint32_t log, QM31 alpha
   }
 }
 __global__ void fold_circle_range_kernel(CPtr4 s, Ptr4 d, uint32_t log, QM31 alpha, QM31 alpha_sq, const uint32_t* __restrict__ itw_end,
-                                         size_t off, size_t n) {
+                                         size_t off, size_t n, const uint32_t* __restrict__ alpha_p = nullptr) {
   const uint32_t* l1 = itw_end - ((size_t)1 << (log - 1));
+  if (alpha_p) { alpha = q_make(alpha_p[0], alpha_p[1], alpha_p[2], alpha_p[3]); alpha_sq = q_mul(alpha, alpha); }
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     size_t gi = off + i;
     size_t pair = (gi >> 2) * 2;
@@ -45,6 +49,23 @@ __global__ void fold_circle_range_kernel(CPtr4 s, Ptr4 d, uint32_t log, QM31 alp
     QM31 acc = q_make(d.p[0][i], d.p[1][i], d.p[2][i], d.p[3][i]);
     QM31 r = q_add(q_mul(acc, alpha_sq), q_add(f0, q_mul(alpha, f1)));
     d.p[0][i] = r.a.a; d.p[1][i] = r.a.b; d.p[2][i] = r.b.a; d.p[3][i] = r.b.b;
+  }
+}
+// Send buffer of a column->row exchange in ONE launch: block (d, j) of the buffer = rows [d * seg_j, (d + 1) * seg_j) of owned
+// column j (the whole column when it is replicated), blocks laid out destination-major.  Replaces world x columns small copies.
+struct PackCol { const uint32_t* src; uint32_t seg; uint32_t sharded; uint64_t off; };   // off: word offset inside a destination's block
+__global__ void __launch_bounds__(256) pack_exchange_kernel(const PackCol* __restrict__ cols, uint32_t ncols, uint64_t per_dest,
+                                                            uint32_t* __restrict__ send) {
+  const PackCol c = cols[blockIdx.y];
+  const uint32_t d = blockIdx.z;
+  const uint32_t* src = c.src + (c.sharded ? (size_t)d * c.seg : 0);
+  uint32_t* dst = send + (size_t)d * per_dest + c.off;
+  if (((c.seg | c.off | per_dest) & 3u) == 0) {   // everything 16-byte aligned: vector copies
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < c.seg / 4; i += gridDim.x * blockDim.x) d4[i] = s4[i];
+  } else {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < c.seg; i += gridDim.x * blockDim.x) dst[i] = src[i];
   }
 }
 // out[row] = col[storage index of the coset-order predecessor of row]  (offset_bit_reversed_circle_domain_index(.., -1))
@@ -126,6 +147,30 @@ int32_t sc_col_view(sc_ctx* ctx, sc_col* col, uint64_t off, uint64_t n, sc_col**
   return SC_OK;
 }
 
+// send[d * per_dest + off_j .. + seg_j) = cols[j][(sharded_j ? d * seg_j : 0) .. + seg_j) for every destination d < world
+int32_t sc_pack_exchange(sc_ctx* ctx, sc_col* const* cols, const uint64_t* segs, const uint8_t* sharded, uint32_t n, uint32_t world, sc_col* send) {
+  ENTER();
+  if (!send || (n && (!cols || !segs || !sharded)) || !world) return fail(SC_EINVAL, "pack_exchange: null argument");
+  if (!n) return SC_OK;
+  std::vector<PackCol> pc(n);
+  uint64_t off = 0;
+  uint32_t max_seg = 1;
+  for (uint32_t j = 0; j < n; j++) {
+    if (!cols[j] || segs[j] > 0xffffffffull || cols[j]->len < (sharded[j] ? segs[j] * world : segs[j])) return fail(SC_EINVAL, "pack_exchange: bad column");
+    pc[j] = {cols[j]->d, (uint32_t)segs[j], sharded[j] ? 1u : 0u, off};
+    off += segs[j];
+    max_seg = std::max<uint32_t>(max_seg, (uint32_t)segs[j]);
+  }
+  if (send->len < off * world) return fail(SC_EINVAL, "pack_exchange: send buffer too small");
+  void* d_pc = nullptr;
+  { int32_t r = stage(ctx, pc.data(), pc.size() * sizeof(PackCol), &d_pc); if (r) return r; }
+  const uint32_t bx = std::max(1u, std::min(64u, (max_seg / 4 + 255) / 256));
+  { ProfScope ps_(ctx, "pack_exchange");
+    pack_exchange_kernel<<<dim3(bx, n, world), 256, 0, ctx->st>>>((const PackCol*)d_pc, n, off, send->d);
+    g_launch_count++; CK(cudaGetLastError()); }
+  return SC_OK;
+}
+
 // ------------------------------------------------------------------ row-range FRI folds
 int32_t sc_fold_line_range(sc_ctx* ctx, sc_col* const src[4], uint32_t log, uint64_t out_off, uint64_t n_out, const uint32_t alpha[4],
                            const sc_twiddles* tw, sc_col* dst_out[4]) {
@@ -152,6 +197,37 @@ int32_t sc_fold_circle_into_line_range(sc_ctx* ctx, sc_col* const src[4], uint32
   QM31 a = q_make(alpha[0], alpha[1], alpha[2], alpha[3]);
   { ProfScope ps_(ctx, "fold_circle_into_line");
     fold_circle_range_kernel<<<grid_for(n_out), 256, 0, ctx->st>>>(s, d, log, a, q_mul(a, a), tw->itw + ((size_t)1 << tw->root_log), out_off, n_out);
+    g_launch_count++; CK(cudaGetLastError()); }
+  return SC_OK;
+}
+
+// The same folds with the coefficient taken from a device-resident transcript (sc_dchan): coefficient #k of `dc`.
+int32_t sc_fold_line_range_dc(sc_ctx* ctx, sc_col* const src[4], uint32_t log, uint64_t out_off, uint64_t n_out, const sc_dchan* dc, uint32_t k,
+                              const sc_twiddles* tw, sc_col* dst_out[4]) {
+  ENTER();
+  const uint32_t* ap = sc_dchan_coeff_ptr(dc, k);
+  if (!tw || !ap || log < 1 || log > tw->root_log || out_off + n_out > (1ull << (log - 1))) return fail(SC_EINVAL, "fold_line_range_dc: bad argument");
+  CPtr4 s; Ptr4 d;
+  for (int j = 0; j < 4; j++) { if (!src[j] || src[j]->len != 2 * n_out) return fail(SC_EINVAL, "fold_line_range_dc: bad source"); s.p[j] = src[j]->d; }
+  for (int j = 0; j < 4; j++) { int32_t r = new_col(ctx, n_out, &dst_out[j]); if (r) return r; d.p[j] = dst_out[j]->d; }
+  { ProfScope ps_(ctx, "fold_line");
+    fold_line_range_kernel<<<grid_for(n_out), 256, 0, ctx->st>>>(s, d, log, q_make(0, 0, 0, 0), tw->itw + ((size_t)1 << tw->root_log), out_off, n_out, ap);
+    g_launch_count++; CK(cudaGetLastError()); }
+  return SC_OK;
+}
+int32_t sc_fold_circle_into_line_range_dc(sc_ctx* ctx, sc_col* const src[4], uint32_t log, uint64_t out_off, uint64_t n_out, const sc_dchan* dc,
+                                          uint32_t k, const sc_twiddles* tw, sc_col* const dst[4]) {
+  ENTER();
+  const uint32_t* ap = sc_dchan_coeff_ptr(dc, k);
+  if (!tw || !ap || log < 3 || log > tw->root_log + 1 || out_off + n_out > (1ull << (log - 1))) return fail(SC_EINVAL, "fold_circle_range_dc: bad argument");
+  CPtr4 s; Ptr4 d;
+  for (int j = 0; j < 4; j++) {
+    if (!src[j] || !dst[j] || src[j]->len != 2 * n_out || dst[j]->len != n_out) return fail(SC_EINVAL, "fold_circle_range_dc: bad columns");
+    s.p[j] = src[j]->d; d.p[j] = dst[j]->d;
+  }
+  { ProfScope ps_(ctx, "fold_circle_into_line");
+    fold_circle_range_kernel<<<grid_for(n_out), 256, 0, ctx->st>>>(s, d, log, q_make(0, 0, 0, 0), q_make(0, 0, 0, 0), tw->itw + ((size_t)1 << tw->root_log),
+                                                                  out_off, n_out, ap);
     g_launch_count++; CK(cudaGetLastError()); }
   return SC_OK;
 }

@@ -26,7 +26,8 @@ for name in ["with_input", "a-bc", "hello_kakarot", "collatz"]:
     if rank == 0:
         print(json.dumps({"program": name, "world": world, "matches_golden": same}))
 code = open(os.path.join(ROOT, "tests", "golden", "programs", "fib19.bf"), "rb").read()
-for it in range(4):
+n_fib = int(sys.argv[sys.argv.index("--fib19-proofs") + 1]) if "--fib19-proofs" in sys.argv else 4
+for it in range(n_fib):
     dist.barrier()
     t = time.time()
     proof = pkg.prove_brainfuck_sharded(be, comm, code, b"", 24)
