@@ -465,6 +465,7 @@ int32_t sbf_prove_sharded(sc_ctx* ctx, sc_comm* comm, const char* code, const ui
     B.comm = comm;
     ProverConfig cfg;
     cfg.log_max_rows = log_max_rows;
+    cfg.shard_min_log = getenv("SBF_SHARD_MIN_LOG") ? (uint32_t)atoi(getenv("SBF_SHARD_MIN_LOG")) : 16;
     B.cache_twiddles = !(flags & 2u);
     auto t1 = std::chrono::steady_clock::now();
     ProveResult r = prove_brainfuck_sharded(B, program, run_vm, cfg, [&] { sc_ctx_sync(ctx); });

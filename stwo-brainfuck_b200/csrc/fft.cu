@@ -23,6 +23,7 @@
 //  * columns of one size are batched through blockIdx.y, so concurrent CTAs share twiddle lines in L1/L2;
 //  * the blow-up layers of an LDE (zero high coefficients) are not computed: the first pass reads index & (2^src-1).
 // All values canonical in [0,P) at kernel boundaries.
+#include <cstdlib>
 #include <mutex>
 #include "kernels.cuh"
 
@@ -261,8 +262,12 @@ struct Rounds<INV, K, LOW, LINE, SC, NR, NR> {
 // transform of a column whose evaluations repeat each value 2^r times, restricted to its 2^n distinct values: the first r
 // layers of the circle transform of log n+r only scale (inverse) or replicate (forward), see launch_interpolate_repeated.
 // (256, 4): 64 registers, four CTAs per SM; the forward low pass otherwise takes 80 and runs three (LDE 6-7 % slower, measured)
+// K = 15: the one strided pass that finishes a transform of log 24..26 after the 13-layer low pass (two HBM round trips instead
+// of three): 2^(15-SC) rows x 2^SC contiguous words = 128 KB of shared memory, one CTA of 1024 threads per SM (the same 32 warps
+// per SM as four 256-thread CTAs).  Rows are only 16..64 bytes long; the rest of each DRAM sector is consumed by the CTA that
+// owns the neighbouring tile, which runs at the same time, so the sector is served from L2.
 template <bool INV, int K, bool LOW, bool LINE = false, int SC = STRIDED_C>
-__global__ void __launch_bounds__(256, 4) fft_kernel(FftArgs a) {
+__global__ void __launch_bounds__(K >= 14 ? 1024 : 256, K >= 14 ? 1 : 4) fft_kernel(FftArgs a) {
   extern __shared__ uint32_t sm[];
   constexpr int C = LOW ? K : SC;
   const uint32_t L0 = LOW ? (uint32_t)K : a.L0;
@@ -306,9 +311,13 @@ static int plan_passes(uint32_t n, PassDesc* out) {  // ascending layer order
   uint32_t K0 = n < KMAX ? n : KMAX;
   out[np++] = {K0, K0, true, 0};
   uint32_t rem = n - K0;
+  static const bool three_pass = getenv("SC_FFT_THREE_PASS") != nullptr;   // A/B switch (tools/fft_bench.py)
   if (rem == KSTRIDE_MAX + 1) {
     // ten layers left (log 23): one strided pass of 2^10 rows x 8 words instead of two passes of 16-word rows
     out[np++] = {rem + 3, K0, false, 3};
+  } else if (rem >= 11 && rem <= 13 && !three_pass) {
+    // log 24..26: ONE strided pass over a 2^15-word tile (2^rem rows x 2^(15-rem) words) instead of two
+    out[np++] = {15, K0, false, 15 - rem};
   } else if (rem) {
     uint32_t ns = (rem + KSTRIDE_MAX - 1) / KSTRIDE_MAX;
     uint32_t L = K0;
@@ -322,6 +331,7 @@ static int plan_passes(uint32_t n, PassDesc* out) {  // ascending layer order
 }
 
 static uint32_t threads_for(uint32_t K) {
+  if (K >= 14) return 1024u;
   uint32_t t = K >= 12 ? 256u : (K >= 4 ? (1u << (K - 4)) : 1u);
   if (t < 32) t = 32;
   return t;
@@ -330,6 +340,14 @@ static uint32_t threads_for(uint32_t K) {
 template <bool INV, int K, bool LOW, bool LINE = false, int SC = STRIDED_C>
 static int launch_one(const FftArgs& a, dim3 grid, cudaStream_t st) {
   size_t smem = ((size_t)(1u << K) + ((1u << K) >> 5) + 4) * 4;
+  if (K >= 14) {   // above the 48 KB default: opt in once per instantiation
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(fft_kernel<INV, K, LOW, LINE, SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      configured = true;
+    }
+  }
   fft_kernel<INV, K, LOW, LINE, SC><<<grid, threads_for(K), smem, st>>>(a); g_launch_count++;
   return (int)cudaGetLastError();
 }
@@ -352,6 +370,14 @@ static int run_pass(const PassDesc& d, const uint32_t* const* src, uint32_t* con
       case 11: return launch_one<INV, 11, true, true>(a, grid, st);
       case 12: return launch_one<INV, 12, true, true>(a, grid, st);
       case 13: return launch_one<INV, 13, true, true>(a, grid, st);
+    }
+    return -1;
+  }
+  if (!d.low && d.K == 15) {
+    switch (d.sc) {
+      case 2: return launch_one<INV, 15, false, false, 2>(a, grid, st);
+      case 3: return launch_one<INV, 15, false, false, 3>(a, grid, st);
+      case 4: return launch_one<INV, 15, false, false, 4>(a, grid, st);
     }
     return -1;
   }

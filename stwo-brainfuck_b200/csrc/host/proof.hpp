@@ -17,6 +17,7 @@ struct ProverConfig {          // PcsConfig::default() + LOG_MAX_ROWS (brainfuck
   uint32_t log_blowup = 1;
   uint32_t n_queries = 3;
   uint32_t log_last_layer_degree_bound = 0;
+  uint32_t shard_min_log = 0;  // sharded driver: columns below 2^shard_min_log rows are replicated on every rank (0: shard whatever can be)
   bool overlap_host = true;    // build the tables on the host while the device commits the preprocessed tree
 };
 

@@ -21,8 +21,12 @@ namespace sbf {
 
 struct ShardLayout {
   int w = 0, rank = 0, world = 1;
-  bool circle_sharded(uint32_t L) const { return L >= (uint32_t)w + 5; }  // LDE / circle-domain columns of log L
-  bool line_sharded(uint32_t l) const { return l >= (uint32_t)w + 4; }    // FRI line layers of log l
+  // Columns of fewer than 2^min_log rows are replicated instead of sharded (ProverConfig::shard_min_log): below ~2^16 rows a
+  // rank's share is a handful of thread blocks, and every sharded layer costs an all-gather of sub-roots plus three launches
+  // for the replicated top of its tree — more than hashing the whole small tree on every rank.
+  uint32_t min_log = 0;
+  bool circle_sharded(uint32_t L) const { return L >= std::max<uint32_t>((uint32_t)w + 5, min_log + 1); }  // LDE / circle-domain columns of log L
+  bool line_sharded(uint32_t l) const { return l >= std::max<uint32_t>((uint32_t)w + 4, min_log); }        // FRI line layers of log l
 };
 
 // A column as this rank sees it after re-sharding: its rows [rank*seg, (rank+1)*seg) if sharded, else the whole column.
@@ -258,7 +262,7 @@ inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_
   ProveResult R;
   BrainfuckProof& proof = R.proof;
   ShardLayout sl;
-  sl.rank = B.rank(); sl.world = B.world();
+  sl.rank = B.rank(); sl.world = B.world(); sl.min_log = cfg.shard_min_log;
   while ((1 << sl.w) < sl.world) sl.w++;
   if ((1 << sl.w) != sl.world) throw std::runtime_error("world size must be a power of two");
   const int N = sl.world, me = sl.rank;
