@@ -311,7 +311,11 @@ static int plan_passes(uint32_t n, PassDesc* out) {  // ascending layer order
   uint32_t K0 = n < KMAX ? n : KMAX;
   out[np++] = {K0, K0, true, 0};
   uint32_t rem = n - K0;
-  static const bool three_pass = getenv("SC_FFT_THREE_PASS") != nullptr;   // A/B switch (tools/fft_bench.py)
+  // Measured on B200 (tools/fft_bench.py, profiles/r2_fft_two_pass_ab.json): the single 2^15-word strided pass LOSES to two
+  // 2^10..2^11-word passes — log 25: interpolate 1.16 vs 1.06 ms, LDE 2.94 vs 2.26 ms — because one 1024-thread CTA per SM
+  // serialises its load, butterfly and store phases where four small CTAs overlap them, and the transform is bound by integer
+  // issue (about 5 instructions per element and layer), not by the third HBM round trip.  Kept behind SC_FFT_TWO_PASS=1.
+  static const bool three_pass = getenv("SC_FFT_TWO_PASS") == nullptr;
   if (rem == KSTRIDE_MAX + 1) {
     // ten layers left (log 23): one strided pass of 2^10 rows x 8 words instead of two passes of 16-word rows
     out[np++] = {rem + 3, K0, false, 3};
