@@ -34,13 +34,16 @@ int32_t sbf_prove(sc_ctx* ctx, const char* code, const uint8_t* input, size_t in
 struct sc_comm;
 int32_t sbf_prove_sharded(sc_ctx* ctx, struct sc_comm* comm, const char* code, const uint8_t* input, size_t input_len,
                           uint32_t log_max_rows, uint32_t flags, sbf_proof** out);
-int32_t sbf_verify(const sbf_proof* proof);
+int32_t sbf_verify(const sbf_proof* proof);   /* with the LOG_MAX_ROWS the proof object was made with */
 char* sbf_proof_json(const sbf_proof* proof);    /* serde-shaped JSON of the proof; free with sbf_string_free */
 char* sbf_proof_report(const sbf_proof* proof);  /* steps, log sizes, per-stage milliseconds */
 size_t sbf_proof_output(const sbf_proof* proof, uint8_t* buf, size_t cap); /* program stdout */
 void sbf_string_free(char* s);
 void sbf_proof_free(sbf_proof* proof);
-int32_t sbf_proof_tamper(sbf_proof* proof, int32_t what); /* test hook: corrupt one field */
+/* `brainfuck_prover verify <file>`: the serde JSON text of a proof (what sbf_proof_json / the reference's `prove --output`
+ * write) checked with the verifier's own LOG_MAX_ROWS and the default PcsConfig; 0 or SC_EVERIFY.  Pure host code. */
+int32_t sbf_verify_json(const char* json, uint32_t log_max_rows);
+int32_t sbf_proof_from_json(const char* json, uint32_t log_max_rows, sbf_proof** out);
 #ifdef __cplusplus
 }
 #endif

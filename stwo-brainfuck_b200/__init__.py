@@ -69,7 +69,7 @@ ABI_SYMBOLS = [
     "sc_microbench_int", "sc_fri_commit", "sc_trace_stats_host", "sc_trace_upload", "sc_trace_build_tables", "sc_trace_status", "sc_trace_free",
 ]
 PROVER_SYMBOLS = ["sbf_prove", "sbf_verify", "sbf_proof_json", "sbf_proof_report", "sbf_proof_output", "sbf_string_free",
-                  "sbf_proof_free", "sbf_proof_tamper", "sbf_last_error", "sbf_preprocessed_cache_clear"]
+                  "sbf_proof_free", "sbf_verify_json", "sbf_proof_from_json", "sbf_last_error", "sbf_preprocessed_cache_clear"]
 
 
 def _np_u32(a) -> np.ndarray:
@@ -452,8 +452,8 @@ class ProvingError(RuntimeError):
 class Proof:
     """BrainfuckProof handle (claim, interaction_claim, StarkProof) living on the C++ side."""
 
-    def __init__(self, lib, handle):
-        self._lib, self._h = lib, handle
+    def __init__(self, lib, handle, log_max_rows: int = 24):
+        self._lib, self._h, self._lmr = lib, handle, log_max_rows
 
     def _str(self, fn) -> str:
         fn.restype = _vp
@@ -476,15 +476,42 @@ class Proof:
         self._lib.sbf_proof_output(self._h, buf, ctypes.c_size_t(n))
         return bytes(buf[:n])
 
+    def verify_json(self, log_max_rows: Optional[int] = None) -> None:
+        """`brainfuck_prover verify`: the wire text parsed back and checked with the verifier's own LOG_MAX_ROWS."""
+        lmr = self._lmr if log_max_rows is None else log_max_rows
+        if self._lib.sbf_verify_json(ctypes.c_char_p(self.json().encode()), ctypes.c_uint32(lmr)) != 0:
+            raise VerificationError(self._lib.sbf_last_error().decode())
+
     def verify(self) -> None:
         """verify_brainfuck (host only).  Raises VerificationError."""
         if self._lib.sbf_verify(self._h) != 0:
             self._lib.sbf_last_error.restype = ctypes.c_char_p
             raise VerificationError(self._lib.sbf_last_error().decode())
 
-    def tamper(self, what: int) -> None:
-        if self._lib.sbf_proof_tamper(self._h, ctypes.c_int32(what)) != 0:
-            raise ValueError("bad tamper selector")
+    def tamper(self, what: int) -> "Proof":
+        """A copy of this proof with one field corrupted (tests): 0 claimed_sum, 1 sampled value, 2 queried value, 3 FRI witness,
+        4 proof_of_work, 5 Merkle hash witness, 6 last-layer polynomial, 7 commitment.  Done on the wire text and read back
+        through sbf_proof_from_json, so the library exports no test hook."""
+        import json as _json
+        p = _json.loads(self.json())
+        s = p["proof"]
+        if what == 0: p["interaction_claim"]["memory"]["claimed_sum"][0][0] ^= 1
+        elif what == 1: s["sampled_values"][1][0][0][0][0] ^= 1
+        elif what == 2: s["queried_values"][1][0][0] ^= 1
+        elif what == 3: s["fri_proof"]["first_layer"]["fri_witness"][0][0][0] ^= 1
+        elif what == 4: s["proof_of_work"] += 1
+        elif what == 5: s["decommitments"][1]["hash_witness"][0][0] ^= 1
+        elif what == 6: s["fri_proof"]["last_layer_poly"]["coeffs"][0][0][0] ^= 1
+        elif what == 7: s["commitments"][2][0] ^= 1
+        else: raise ValueError("bad tamper selector")
+        return Proof.from_json(self._lib, _json.dumps(p, separators=(",", ":")), self._lmr)
+
+    @staticmethod
+    def from_json(lib, text: str, log_max_rows: int) -> "Proof":
+        h = _vp()
+        if lib.sbf_proof_from_json(ctypes.c_char_p(text.encode()), ctypes.c_uint32(log_max_rows), ctypes.byref(h)) != 0:
+            raise VerificationError(lib.sbf_last_error().decode())
+        return Proof(lib, h, log_max_rows)
 
     def __del__(self):
         try:
@@ -513,7 +540,7 @@ def prove_brainfuck(backend: CudaBackend, code: str, stdin: bytes = b"", log_max
     if rc != 0:
         lib.sbf_last_error.restype = ctypes.c_char_p
         raise ProvingError(lib.sbf_last_error().decode())
-    return Proof(lib, h)
+    return Proof(lib, h, log_max_rows)
 
 
 def clear_preprocessed_cache(backend: CudaBackend) -> None:
@@ -572,4 +599,4 @@ def prove_brainfuck_sharded(backend: CudaBackend, comm: Optional[Comm], code, st
     if rc != 0:
         lib.sbf_last_error.restype = ctypes.c_char_p
         raise ProvingError(lib.sbf_last_error().decode())
-    return Proof(lib, h)
+    return Proof(lib, h, log_max_rows)

@@ -166,10 +166,10 @@ int32_t sc_col_from_host_async(sc_ctx* ctx, const uint32_t* host, uint64_t len, 
   ctx->slab_high = std::max(ctx->slab_high, ctx->slab_used + bytes);
   if (ctx->slab_used + bytes > ctx->slab_cap) {
     // no room (first proof on this context, or a larger program): ordinary pool column, copied on the compute stream
+    int32_t r = new_col(ctx, len, out);
+    if (r) return r;          // nothing was counted yet: a failed allocation leaves the slab bookkeeping untouched
     ctx->slab_used += bytes;  // keep counting so that slab_high sees the whole round
     ctx->slab_live++;
-    int32_t r = new_col(ctx, len, out);
-    if (r) return r;
     (*out)->slab = true;      // only for the live count; `owned` stays true, so the memory goes back to the pool
     CK(cudaMemcpyAsync((*out)->d, host, len * 4, cudaMemcpyHostToDevice, ctx->st));
     return SC_OK;

@@ -453,6 +453,9 @@ int32_t sbf_prove_sharded(sc_ctx* ctx, sc_comm* comm, const char* code, const ui
   const uint64_t mark = sc_ctx_mark(ctx);
   try {
     if (!ctx || !code || !out) throw std::runtime_error("null argument");
+    // the sharded driver always overlaps the VM with phase 0 and has no preprocessed-tree cache: say so instead of ignoring the flags
+    if (flags & 1u) throw std::runtime_error("SBF_NO_OVERLAP is not supported by the sharded driver");
+    if (flags & 8u) throw std::runtime_error("SBF_CACHE_PREPROCESSED is not supported by the sharded driver");
     std::vector<uint32_t> program = compile(code);
     Machine vm(program, std::vector<uint8_t>(input, input + input_len));
     double vm_ms = 0;
@@ -511,24 +514,33 @@ size_t sbf_proof_output(const sbf_proof* p, uint8_t* buf, size_t cap) {
 void sbf_string_free(char* s) { free(s); }
 void sbf_proof_free(sbf_proof* p) { delete p; }
 
-// Test hook: corrupt one field of a proof so that the verifier's rejection paths can be exercised.
-// what: 0 claimed_sum, 1 sampled value, 2 queried value, 3 FRI witness, 4 proof_of_work, 5 Merkle hash witness,
-//       6 last-layer polynomial, 7 commitment.
-int32_t sbf_proof_tamper(sbf_proof* p, int32_t what) {
-  if (!p) return SC_EINVAL;
-  CommitmentSchemeProof& s = p->proof.proof;
-  switch (what) {
-    case 0: p->proof.claimed_sum[0].a.a ^= 1; break;
-    case 1: s.sampled_values[1][0][0].a.a ^= 1; break;
-    case 2: s.queried_values[1][0][0] ^= 1; break;
-    case 3: s.fri_proof.first_layer.fri_witness[0].a.a ^= 1; break;
-    case 4: s.proof_of_work += 1; break;
-    case 5: s.decommitments[1].hash_witness[0][0] ^= 1; break;
-    case 6: s.fri_proof.last_layer_poly[0].a.a ^= 1; break;
-    case 7: s.commitments[2][0] ^= 1; break;
-    default: return SC_EINVAL;
+// `brainfuck_prover verify <file>` (bin/brainfuck_prover.rs:145-152): deserialise the serde JSON text and verify it with the
+// VERIFIER's own parameters — its LOG_MAX_ROWS and the default PcsConfig — not with anything the prover recorded.
+int32_t sbf_verify_json(const char* json, uint32_t log_max_rows) {
+  try {
+    if (!json) throw std::runtime_error("null proof");
+    BrainfuckProof p = proof_from_json(json);
+    ProverConfig cfg;
+    cfg.log_max_rows = log_max_rows;
+    verify_brainfuck(p, cfg);
+    return SC_OK;
+  } catch (const std::exception& e) {
+    g_sbf_err = e.what();
+    return SC_EVERIFY;
   }
-  return SC_OK;
+}
+// The same text as a proof object (sbf_proof_json o sbf_proof_from_json is the identity on well-formed proofs).
+int32_t sbf_proof_from_json(const char* json, uint32_t log_max_rows, sbf_proof** out) {
+  try {
+    if (!json || !out) throw std::runtime_error("null argument");
+    ProverConfig cfg;
+    cfg.log_max_rows = log_max_rows;
+    *out = new sbf_proof{proof_from_json(json), cfg, "{}", {}};
+    return SC_OK;
+  } catch (const std::exception& e) {
+    g_sbf_err = e.what();
+    return SC_EVERIFY;
+  }
 }
 
 }  // extern "C"

@@ -238,4 +238,102 @@ inline std::string proof_to_json(const BrainfuckProof& p) {
   return o.str();
 }
 
+// ---- The way back: serde_json text -> BrainfuckProof (what `brainfuck_prover verify` does with `serde_json::from_str`,
+// bin/brainfuck_prover.rs:145-152).  A small recursive-descent reader for exactly the shapes proof_to_json writes; every
+// structural surprise is an error, never a guess.
+struct JsonReader {
+  const char* p; const char* end;
+  explicit JsonReader(const std::string& s) : p(s.data()), end(s.data() + s.size()) {}
+  [[noreturn]] void bad(const char* what) const { throw std::runtime_error(std::string("proof JSON: ") + what); }
+  void ws() { while (p < end && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) p++; }
+  bool peek(char c) { ws(); return p < end && *p == c; }
+  void expect(char c) { ws(); if (p >= end || *p != c) bad("unexpected character"); p++; }
+  bool maybe(char c) { ws(); if (p < end && *p == c) { p++; return true; } return false; }
+  uint64_t number() {
+    ws();
+    if (p >= end || *p < '0' || *p > '9') bad("number expected");
+    uint64_t v = 0;
+    while (p < end && *p >= '0' && *p <= '9') { if (v > (UINT64_MAX - 9) / 10) bad("number too large"); v = v * 10 + (uint64_t)(*p - '0'); p++; }
+    return v;
+  }
+  uint32_t m31() { uint64_t v = number(); if (v >= sb::P) bad("field element out of range"); return (uint32_t)v; }
+  void key(const char* name) {
+    expect('"');
+    size_t n = strlen(name);
+    if ((size_t)(end - p) < n + 1 || memcmp(p, name, n) != 0 || p[n] != '"') bad("unexpected field name");
+    p += n + 1;
+    expect(':');
+  }
+  void null() { ws(); if (end - p < 4 || memcmp(p, "null", 4) != 0) bad("null expected"); p += 4; }
+  template <class F> void array(F item) {   // item() reads one element
+    expect('[');
+    if (maybe(']')) return;
+    do { item(); } while (maybe(','));
+    expect(']');
+  }
+  QM31 qm31() {
+    expect('['); expect('['); uint32_t a = m31(); expect(','); uint32_t b = m31(); expect(']'); expect(',');
+    expect('['); uint32_t c = m31(); expect(','); uint32_t d = m31(); expect(']'); expect(']');
+    return q_make(a, b, c, d);
+  }
+  Hash hash() {
+    uint8_t b[32]; size_t n = 0;
+    array([&] { uint64_t v = number(); if (v > 255 || n >= 32) bad("digest byte"); b[n++] = (uint8_t)v; });
+    if (n != 32) bad("digest length");
+    Hash h; memcpy(h.data(), b, 32); return h;
+  }
+  MerkleDecommitment decommitment() {
+    MerkleDecommitment d;
+    expect('{'); key("hash_witness"); array([&] { d.hash_witness.push_back(hash()); });
+    expect(','); key("column_witness"); array([&] { d.column_witness.push_back(m31()); });
+    expect('}');
+    return d;
+  }
+  FriLayerProof layer() {
+    FriLayerProof l;
+    expect('{'); key("fri_witness"); array([&] { l.fri_witness.push_back(qm31()); });
+    expect(','); key("decommitment"); l.decommitment = decommitment();
+    expect(','); key("commitment"); l.commitment = hash();
+    expect('}');
+    return l;
+  }
+};
+inline BrainfuckProof proof_from_json(const std::string& text) {
+  JsonReader r(text);
+  BrainfuckProof p;
+  r.expect('{'); r.key("claim"); r.expect('{');
+  for (int c = 0; c < N_COMPONENTS; c++) {
+    if (c) r.expect(',');
+    r.key(COMPONENT_NAMES[c]); r.expect('{'); r.key("log_size");
+    uint64_t v = r.number(); if (v > 31) r.bad("log_size");
+    p.log_size[c] = (uint32_t)v;
+    r.expect(','); r.key("_marker"); r.null(); r.expect('}');
+  }
+  r.expect('}'); r.expect(','); r.key("interaction_claim"); r.expect('{');
+  for (int c = 0; c < N_COMPONENTS; c++) {
+    if (c) r.expect(',');
+    r.key(COMPONENT_NAMES[c]); r.expect('{'); r.key("claimed_sum"); p.claimed_sum[c] = r.qm31(); r.expect('}');
+  }
+  r.expect('}'); r.expect(','); r.key("proof"); r.expect('{');
+  CommitmentSchemeProof& s = p.proof;
+  r.key("commitments"); r.array([&] { s.commitments.push_back(r.hash()); });
+  r.expect(','); r.key("sampled_values");
+  r.array([&] { s.sampled_values.emplace_back(); r.array([&] { s.sampled_values.back().emplace_back(); r.array([&] { s.sampled_values.back().back().push_back(r.qm31()); }); }); });
+  r.expect(','); r.key("decommitments"); r.array([&] { s.decommitments.push_back(r.decommitment()); });
+  r.expect(','); r.key("queried_values");
+  r.array([&] { s.queried_values.emplace_back(); r.array([&] { s.queried_values.back().emplace_back(); r.array([&] { s.queried_values.back().back().push_back(r.m31()); }); }); });
+  r.expect(','); r.key("proof_of_work"); s.proof_of_work = r.number();
+  r.expect(','); r.key("fri_proof"); r.expect('{');
+  r.key("first_layer"); s.fri_proof.first_layer = r.layer();
+  r.expect(','); r.key("inner_layers"); r.array([&] { s.fri_proof.inner_layers.push_back(r.layer()); });
+  r.expect(','); r.key("last_layer_poly"); r.expect('{'); r.key("coeffs"); r.array([&] { s.fri_proof.last_layer_poly.push_back(r.qm31()); });
+  r.expect(','); r.key("log_size");
+  uint64_t ll = r.number();
+  if (ll > 20 || s.fri_proof.last_layer_poly.size() != ((size_t)1 << ll)) r.bad("last_layer_poly size");
+  r.expect('}'); r.expect('}'); r.expect('}'); r.expect('}');
+  r.ws();
+  if (r.p != r.end) r.bad("trailing characters");
+  return p;
+}
+
 }  // namespace sbf

@@ -138,8 +138,11 @@ inline void verify_brainfuck(const BrainfuckProof& proof, const ProverConfig& cf
   uint32_t max_log = col_logs[0];
   std::vector<QM31> layer_alphas;
   uint32_t line_log = max_log - 1;
+  // the last-layer check below compares evaluations with coefficient 0 only: a non-constant last layer is not supported
+  // (the prover refuses it too), so it must not be accepted as if it were constant
+  if (cfg.log_last_layer_degree_bound != 0) throw VerifyError("only log_last_layer_degree_bound = 0 is supported");
   const uint32_t last_log = cfg.log_last_layer_degree_bound + cfg.log_blowup;
-  if (F.inner_layers.size() != line_log - last_log) throw VerifyError("FRI: InvalidNumFriLayers");
+  if (line_log < last_log || F.inner_layers.size() != line_log - last_log) throw VerifyError("FRI: InvalidNumFriLayers");
   for (auto& L : F.inner_layers) { ch.mix_root(L.commitment); layer_alphas.push_back(ch.draw_felt()); }
   if (F.last_layer_poly.size() > ((size_t)1 << cfg.log_last_layer_degree_bound)) throw VerifyError("FRI: LastLayerDegreeInvalid");
   ch.mix_felts(F.last_layer_poly);
@@ -248,8 +251,8 @@ inline void verify_brainfuck(const BrainfuckProof& proof, const ProverConfig& cf
     merkle_verify(L.commitment, std::vector<uint32_t>(4, line_log), {{line_log, pos}}, dvals, L.decommitment);
     Queries nq = lq.fold(1);
     std::vector<QM31> next(nq.positions.size());
+    if (s.subsets.size() != nq.positions.size()) throw VerifyError("FRI: fold mismatch");   // before anything is written through k
     for (size_t k = 0; k < s.subsets.size(); k++) next[k] = fold_line_pair(line_log, s.subset_start[k], s.subsets[k], layer_alphas[li]);
-    if (s.subsets.size() != nq.positions.size()) throw VerifyError("FRI: fold mismatch");
     lq = nq;
     layer_evals = next;
     line_log--;

@@ -14,7 +14,7 @@ GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "proof_hashes.json")
 
 
 def source(name, g):
-    return g["code"].encode() if g["code"] else open(os.path.join(ROOT, "tests", "golden", "programs", name + ".bf"), "rb").read()
+    return g["code"].encode() if g["code"] else open(os.path.join(ROOT, "tests", "golden", "programs", name.split("@")[0] + ".bf"), "rb").read()
 
 
 @pytest.mark.parametrize("name", ["with_input", "no_input", "jump_mid", "a-bc", "hello_kakarot"])
@@ -94,3 +94,22 @@ def test_reference_end_to_end_programs(orc, code, stdin, out, lmr):
     p = lib.orc_prove_json(code, stdin, ctypes.c_size_t(len(stdin)), ctypes.c_uint32(lmr), 1)      # 1: also verify
     assert p, lib.orc_last_error()
     lib.orc_free(ctypes.c_void_p(p))
+
+
+def test_proof_json_round_trips_through_the_parser(orc, pkg):
+    """sbf_proof_from_json o sbf_proof_json is the identity, and sbf_verify_json accepts the oracle's proof text with the right
+    LOG_MAX_ROWS and rejects it with another one or when it is malformed (host code: no GPU needed)."""
+    lib = pkg.load_library()
+    olib = orc.lib
+    olib.orc_prove_json.restype = ctypes.c_void_p
+    p = olib.orc_prove_json(b"+>,<[>+.<-]", b"\x01", ctypes.c_size_t(1), ctypes.c_uint32(10), 0)
+    raw = ctypes.string_at(p)
+    olib.orc_free(ctypes.c_void_p(p))
+    assert lib.sbf_verify_json(raw, ctypes.c_uint32(10)) == 0
+    assert lib.sbf_verify_json(raw, ctypes.c_uint32(11)) != 0
+    pr = pkg.Proof.from_json(lib, raw.decode(), 10)
+    assert pr.json().encode() == raw
+    pr.verify()
+    for bad in (raw[:-1], raw.replace(b'"claim"', b'"clam"', 1), raw.replace(b'"_marker":null', b'"_marker":0', 1), raw + b" x",
+                raw.replace(b'"proof_of_work":', b'"proof_of_work":-', 1)):
+        assert lib.sbf_verify_json(bad, ctypes.c_uint32(10)) != 0

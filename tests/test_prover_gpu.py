@@ -58,9 +58,14 @@ def test_hello_kakarot_at_reference_test_size(pkg, be):
 def test_verifier_rejects_tampered_proof(pkg, be, what):
     proof = pkg.prove_brainfuck(be, b"+>,<[>+.<-]", b"\x03", 10)
     proof.verify()
-    proof.tamper(what)
+    proof.verify_json()                      # the wire text, parsed back and verified with the verifier's own LOG_MAX_ROWS
+    bad = proof.tamper(what)                 # corrupted on the wire text, read back through sbf_proof_from_json
     with pytest.raises(pkg.VerificationError):
-        proof.verify()
+        bad.verify()
+    with pytest.raises(pkg.VerificationError):
+        bad.verify_json()
+    with pytest.raises(pkg.VerificationError):
+        proof.verify_json(11)                # a verifier with another LOG_MAX_ROWS expects another preprocessed tree
 
 
 def test_component_too_large_is_an_error(pkg, be):

@@ -27,7 +27,7 @@ def oracle_proof(orc, code, stdin, lmr):
 
 def case(name):
     g = GOLD[name]
-    code = g["code"].encode() if g["code"] else load(name + ".bf")
+    code = g["code"].encode() if g["code"] else load(name.split("@")[0] + ".bf")
     return code, bytes.fromhex(g["stdin_hex"]), g["log_max_rows"]
 
 
@@ -89,7 +89,6 @@ def test_cuda_proofs_are_accepted_by_the_independent_verifier(pkg, be, name):
     pr = pkg.prove_brainfuck(be, code, stdin, lmr)
     assert py_verifier.verify(pr.json(), lmr)
     for what in range(8):   # the library's own tamper hook: every case must be rejected here as well
-        bad = pkg.prove_brainfuck(be, code, stdin, lmr)
-        bad.tamper(what)
+        bad = pr.tamper(what)
         with pytest.raises(py_verifier.Reject):
             py_verifier.verify(bad.json(), lmr)

@@ -16,7 +16,7 @@ GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "proof_hashes.json")
 
 
 def source(name, g):
-    return g["code"].encode() if g["code"] else open(os.path.join(ROOT, "tests", "golden", "programs", name + ".bf"), "rb").read()
+    return g["code"].encode() if g["code"] else open(os.path.join(ROOT, "tests", "golden", "programs", name.split("@")[0] + ".bf"), "rb").read()
 
 
 @pytest.mark.parametrize("world", [1, 2, 4])
