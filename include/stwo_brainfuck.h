@@ -24,6 +24,8 @@ const char* sbf_last_error(void);
 /* flags: run the FRI commit phase layer by layer with the host channel (one root read-back per layer) instead of
  * sc_fri_commit's device-side channel; same proof bytes (A/B measurements). */
 #define SBF_NO_FUSED_FRI 32u
+/* flags: allocate the proof's columns from the stream-ordered pool one by one instead of the per-proof arena (sc_ctx_arena_*) */
+#define SBF_NO_ARENA 64u
 int32_t sbf_preprocessed_cache_clear(sc_ctx* ctx);
 int32_t sbf_prove(sc_ctx* ctx, const char* code, const uint8_t* input, size_t input_len, uint32_t log_max_rows, uint32_t flags,
                   sbf_proof** out);

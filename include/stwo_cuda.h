@@ -37,6 +37,12 @@ int32_t sc_version(void);
 int32_t sc_ctx_create(int32_t device, void* stream, sc_ctx** out);
 int32_t sc_ctx_destroy(sc_ctx* ctx);
 int32_t sc_ctx_sync(sc_ctx* ctx);
+/* Proof arena: between begin and end every new column is a slice of one persistent device slab (bump allocation; sc_col_free
+ * of such a column only drops the handle).  The caller promises that every column made inside the bracket is dead before the
+ * next sc_ctx_arena_begin.  The slab is sized from the previous bracket's total and reallocated, if it has to grow, in begin;
+ * what does not fit falls back to the stream-ordered pool.  sbf_prove brackets every proof with it. */
+int32_t sc_ctx_arena_begin(sc_ctx* ctx);
+int32_t sc_ctx_arena_end(sc_ctx* ctx);
 /* The compute stream waits for the asynchronous uploads issued so far (every other entry point does this first, too). */
 int32_t sc_ctx_join_uploads(sc_ctx* ctx);
 /* Number of kernels launched through this context so far (bench.py's gpu_launches). */

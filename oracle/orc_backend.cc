@@ -586,6 +586,7 @@ char* orc_prove_sharded_json(const char* code, const uint8_t* input, size_t inpu
     vm.execute();
     ProverConfig cfg;
     cfg.log_max_rows = log_max_rows;
+    if (getenv("ORC_SHARD_MIN_LOG")) cfg.shard_min_log = (uint32_t)atoi(getenv("ORC_SHARD_MIN_LOG"));   // tests: replicate small columns
     ThreadComm comm(world);
     std::vector<std::string> json(world), err(world);
     std::vector<std::thread> th;

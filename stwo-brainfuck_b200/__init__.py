@@ -58,7 +58,7 @@ def load_library() -> ctypes.CDLL:
 
 # Every symbol include/stwo_cuda.h declares (checked by tests/test_abi.py without a GPU).
 ABI_SYMBOLS = [
-    "sc_last_error", "sc_version", "sc_ctx_create", "sc_ctx_destroy", "sc_ctx_sync", "sc_ctx_join_uploads", "sc_ctx_launch_count",
+    "sc_last_error", "sc_version", "sc_ctx_create", "sc_ctx_destroy", "sc_ctx_sync", "sc_ctx_arena_begin", "sc_ctx_arena_end", "sc_ctx_join_uploads", "sc_ctx_launch_count",
     "sc_col_zeros", "sc_col_uninit", "sc_col_from_host", "sc_col_from_host_async", "sc_host_arena_alloc", "sc_host_arena_reset", "sc_col_to_host", "sc_col_read", "sc_col_write", "sc_col_clone",
     "sc_col_free", "sc_col_len", "sc_col_device_ptr", "sc_col_wrap", "sc_col_broadcast16", "sc_bit_reverse", "sc_batch_inverse_m31",
     "sc_batch_inverse_qm31", "sc_precompute_twiddles", "sc_twiddles_free", "sc_twiddles_cached", "sc_twiddles_to_host", "sc_interpolate",
@@ -524,7 +524,7 @@ class Proof:
 
 def prove_brainfuck(backend: CudaBackend, code: str, stdin: bytes = b"", log_max_rows: int = 24, overlap_host: bool = True,
                     cache_preprocessed: bool = False, twiddle_cache: bool = True, host_tables: bool = False,
-                    fused_fri: bool = True) -> Proof:
+                    fused_fri: bool = True, arena: bool = True) -> Proof:
     """prove_brainfuck(&Machine) of crates/brainfuck_prover/src/brainfuck_air/mod.rs:471-735: runs the VM on the host and the
     whole proof on the device behind `backend`.  overlap_host=False builds the host tables before any device work (used by
     bench.py to time the device path alone); cache_preprocessed=True keeps the program-independent preprocessed tree on
@@ -534,7 +534,8 @@ def prove_brainfuck(backend: CudaBackend, code: str, stdin: bytes = b"", log_max
     lib = backend._lib
     h = _vp()
     code_b = code.encode() if isinstance(code, str) else code
-    flags = (0 if overlap_host else 1) | (8 if cache_preprocessed else 0) | (0 if twiddle_cache else 2) | (16 if host_tables else 0) | (0 if fused_fri else 32)
+    flags = (0 if overlap_host else 1) | (8 if cache_preprocessed else 0) | (0 if twiddle_cache else 2) | (16 if host_tables else 0) | (0 if fused_fri else 32) | \
+        (0 if arena else 64)
     rc = lib.sbf_prove(backend._ctx, ctypes.c_char_p(code_b), ctypes.c_char_p(stdin), ctypes.c_size_t(len(stdin)),
                        ctypes.c_uint32(log_max_rows), ctypes.c_uint32(flags), ctypes.byref(h))
     if rc != 0:

@@ -67,11 +67,35 @@ int32_t sc_ctx_destroy(sc_ctx* ctx) {
   cudaFree(ctx->d_ring);
   if (ctx->copy_st) { cudaStreamSynchronize(ctx->copy_st); cudaStreamDestroy(ctx->copy_st); cudaEventDestroy(ctx->copy_ev); cudaEventDestroy(ctx->slab_ev); }
   if (ctx->slab) cudaFree(ctx->slab);
+  if (ctx->parena) cudaFree(ctx->parena);
   if (ctx->own_stream) cudaStreamDestroy(ctx->st);
   delete ctx;
   return SC_OK;
 }
 int32_t sc_ctx_sync(sc_ctx* ctx) { ENTER(); CK(cudaStreamSynchronize(ctx->st)); return SC_OK; }
+// Proof arena: see sc_ctx::parena.  begin: (re)size the slab to what the previous bracket asked for (a growing slab is
+// reallocated here, while nothing of the arena is alive) and start bump allocation; end: stop and remember the total.
+int32_t sc_ctx_arena_begin(sc_ctx* ctx) {
+  ENTER();
+  if (ctx->parena_on) return fail(SC_EINVAL, "arena_begin: already inside a bracket");
+  if (ctx->parena_want > ctx->parena_cap) {
+    CK(cudaStreamSynchronize(ctx->st));
+    if (ctx->parena) CK(cudaFree(ctx->parena));
+    ctx->parena = nullptr; ctx->parena_cap = 0;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);   // the pool's cached blocks make room
+    const size_t want = ctx->parena_want + ctx->parena_want / 16 + ((size_t)64 << 20);
+    if (cudaMalloc((void**)&ctx->parena, want) == cudaSuccess) ctx->parena_cap = want;
+    else { cudaGetLastError(); ctx->parena = nullptr; }   // no room: stay on the pool
+  }
+  ctx->parena_off = 0; ctx->parena_need = 0; ctx->parena_on = true;
+  return SC_OK;
+}
+int32_t sc_ctx_arena_end(sc_ctx* ctx) {
+  if (!ctx) return fail(SC_EINVAL, "null context");
+  if (ctx->parena_on) { ctx->parena_on = false; ctx->parena_want = std::max(ctx->parena_want, ctx->parena_need); }
+  return SC_OK;
+}
 // Makes the compute stream wait for every upload issued so far (sc_col_from_host_async, sc_trace_upload) without blocking the host.
 int32_t sc_ctx_join_uploads(sc_ctx* ctx) { ENTER(); return SC_OK; }
 int32_t sc_ctx_attach(sc_ctx* ctx, uint32_t slot, void* p, sc_attach_dtor dtor) {

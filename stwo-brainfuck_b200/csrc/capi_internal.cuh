@@ -16,7 +16,7 @@ using namespace sb;
 struct sc_col {
   uint32_t* d;
   uint64_t len;
-  bool owned = true;  // false: a view over caller-owned device memory (sc_col_wrap)
+  bool owned = true;  // false: a view over caller-owned device memory (sc_col_wrap) or a slice of the proof arena
   bool slab = false;  // lives in the context's upload slab (sc_col_from_host_async)
   uint64_t id = 0;    // creation order within the context (sc_ctx_mark / sc_ctx_release_since)
 };
@@ -62,6 +62,13 @@ struct sc_ctx {
   size_t slab_cap = 0, slab_used = 0, slab_high = 0;
   int slab_live = 0;
   bool slab_fence = false;
+  // Proof arena (sc_ctx_arena_begin/end): between the two calls new columns are bump-allocated from one persistent slab and
+  // freeing them is a host-side no-op — a proof makes ~1200 columns, and at eight GPUs its kernels are short enough that the
+  // 2400 cudaMallocAsync / cudaFreeAsync calls were a visible part of the (host-bound) critical path.  Nothing is reused inside
+  // a proof, so there is no ordering hazard; the slab is sized from the previous proof's total and grows between proofs.
+  uint8_t* parena = nullptr;
+  size_t parena_cap = 0, parena_off = 0, parena_need = 0, parena_want = 0;
+  bool parena_on = false;
   // sc_ctx_attach: caller-owned objects whose life ends with the context (e.g. the prover's preprocessed-tree cache)
   struct Attached { void* p = nullptr; void (*dtor)(sc_ctx*, void*) = nullptr; } attached[4];
 };
@@ -128,6 +135,17 @@ static inline int32_t stage(sc_ctx* ctx, const void* host, size_t bytes, void** 
 
 static inline void track(sc_ctx* ctx, sc_col* c) { c->id = ctx->next_id++; ctx->live[c->id] = c; }
 static inline int32_t new_col(sc_ctx* ctx, uint64_t len, sc_col** out) {
+  if (ctx->parena_on) {
+    const size_t bytes = ((size_t)std::max<uint64_t>(len, 4) * 4 + 255) & ~(size_t)255;
+    ctx->parena_need += bytes;
+    if (ctx->parena && ctx->parena_off + bytes <= ctx->parena_cap) {
+      *out = new sc_col{reinterpret_cast<uint32_t*>(ctx->parena + ctx->parena_off), len};
+      (*out)->owned = false;
+      ctx->parena_off += bytes;
+      track(ctx, *out);
+      return SC_OK;
+    }
+  }
   uint32_t* d = nullptr;
   cudaError_t e = cudaMallocAsync((void**)&d, std::max<uint64_t>(len, 4) * 4, ctx->st);
   if (e != cudaSuccess) { cudaGetLastError(); return fail(SC_ENOMEM, std::string("cudaMallocAsync: ") + cudaGetErrorString(e)); }

@@ -356,6 +356,13 @@ TraceInput run_machine(sc_ctx* ctx, Machine& vm, uint32_t log_max_rows, bool hos
   return in;
 }
 
+// sc_ctx_arena_begin / _end around one proof (also when the proof throws)
+struct ArenaBracket {
+  sc_ctx* ctx; bool on;
+  ArenaBracket(sc_ctx* c, bool enable) : ctx(c), on(enable && sc_ctx_arena_begin(c) == SC_OK) {}
+  ~ArenaBracket() { if (on) sc_ctx_arena_end(ctx); }
+};
+
 thread_local std::string g_sbf_err;
 char* dup_string(const std::string& s) {
   char* p = (char*)malloc(s.size() + 1);
@@ -419,6 +426,8 @@ int32_t sbf_prove(sc_ctx* ctx, const char* code, const uint8_t* input, size_t in
     CudaBackendImpl B(ctx);
     B.host_tables = host_tables;
     B.fused_fri = !(flags & 32u);   // SBF_NO_FUSED_FRI
+    // every column of the proof from one slab (not with the preprocessed-tree cache, whose columns outlive the proof)
+    ArenaBracket arena(ctx, !(flags & 64u) && !(flags & 8u));
     ProverConfig cfg;
     cfg.log_max_rows = log_max_rows;
     cfg.overlap_host = !(flags & 1u);  // SBF_NO_OVERLAP: VM run and tables before any device work (bench.py's device-path timing)
@@ -465,6 +474,7 @@ int32_t sbf_prove_sharded(sc_ctx* ctx, sc_comm* comm, const char* code, const ui
     CudaBackendImpl B(ctx);
     B.host_tables = host_tables;
     B.fused_fri = !(flags & 32u);   // SBF_NO_FUSED_FRI
+    ArenaBracket arena(ctx, !(flags & 64u));
     B.comm = comm;
     ProverConfig cfg;
     cfg.log_max_rows = log_max_rows;

@@ -82,6 +82,7 @@ inline std::vector<int> assign_owners(const std::vector<uint32_t>& logs, int wor
 struct SMerkle {
   std::vector<Col> layers;  // [k]: k > w: this rank's sub-layer (2^(k-w) nodes); k <= w: the whole layer (replicated)
   Hash root;
+  bool whole = false;       // no column of the tree is sharded: every rank hashed the whole tree, every layer is complete
 };
 // Row-sharded MerkleProver::commit over columns that are either row ranges (sharded) or whole (replicated).  The node
 // function is local to a row, so the layers with more than `world` nodes are an ordinary Merkle tree over this rank's row
@@ -96,6 +97,19 @@ inline SMerkle merkle_sharded(Backend& B, const ShardLayout& sl, const std::vect
   for (auto& c : cols) maxL = std::max(maxL, c.L);
   m.layers.assign(maxL + 1, nullptr);
   const uint32_t w = (uint32_t)sl.w;
+  bool any_sharded = false;
+  for (auto& c : cols) any_sharded |= c.sharded;
+  if (!any_sharded) {
+    // Every column is replicated (a small tree, ShardLayout::min_log): hash the whole tree here, like every other rank —
+    // one fused backend call, no sub-root all-gather and no separate launches for the top layers.
+    std::vector<Col> all;
+    for (auto& c : cols) all.push_back(c.rows);
+    m.layers = rep ? B.merkle_commit_repeated(all, rep, nullptr) : B.merkle_commit(all, nullptr);
+    m.whole = true;
+    if (before_root_read) before_root_read();
+    if (read_root) B.read(m.layers[0], 0, 8, m.root.data());
+    return m;
+  }
   Col prev = nullptr;
   int k = (int)maxL;
   if (maxL >= w) {
@@ -216,7 +230,7 @@ inline void merkle_decommit_sharded(FetchBatch& fb, const ShardLayout& sl, const
         int k = lg + 1;
         for (size_t child = 2 * node; child <= 2 * node + 1; child++) {
           if (pi < last_queries.size() && last_queries[pi] == child) { pi++; continue; }
-          if (k > sl.w) {
+          if (k > sl.w && !m.whole) {
             size_t n = (size_t)1 << (k - sl.w);
             hslots->push_back(fb.add_hash({m.layers[k], 8 * (child % n), (int)(child / n) == sl.rank}));
           } else {

@@ -91,3 +91,20 @@ def test_cuda_sharded_driver_over_nccl(world):
     fib = [l for l in lines if l["program"] == "fib19"]
     assert fib and all(l["ranks_agree"] for l in fib)
     assert fib[0]["sha256"] == json.load(open(os.path.join(ROOT, "tests", "golden", "fib19_wire_sha256.json")))["sha256"]
+
+
+@pytest.mark.parametrize("min_log", [7, 9, 30])
+def test_sharded_driver_with_small_columns_replicated(orc, min_log, monkeypatch):
+    """ProverConfig::shard_min_log: columns below 2^min_log rows are replicated and their trees hashed whole on every rank
+    (what the CUDA path does below 2^16 rows); 30 replicates everything.  The proof must not change."""
+    monkeypatch.setenv("ORC_SHARD_MIN_LOG", str(min_log))
+    g = GOLD["a-bc"]
+    lib = orc.lib
+    lib.orc_prove_sharded_json.restype = ctypes.c_void_p
+    lib.orc_last_error.restype = ctypes.c_char_p
+    stdin = bytes.fromhex(g["stdin_hex"])
+    p = lib.orc_prove_sharded_json(source("a-bc", g), stdin, ctypes.c_size_t(len(stdin)), ctypes.c_uint32(g["log_max_rows"]), 4, 1)
+    assert p, lib.orc_last_error()
+    js = ctypes.string_at(p)
+    lib.orc_free(ctypes.c_void_p(p))
+    proof_canon.check(js, g)
