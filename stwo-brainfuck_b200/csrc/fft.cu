@@ -106,35 +106,40 @@ __device__ __forceinline__ uint32_t fsub(uint32_t y, uint32_t x, uint32_t mone) 
   asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(mone), "r"(y));
   return r;
 }
+// The IMAD forms matter (measured on the Blake2s G mix, tools/exp/gmix.cu: 96.5 % of the pipe with the multiplicand in a
+// UNIFORM register, 88 % with three vector-register operands).  An IMAD takes one non-vector operand only, so the runtime
+// +-1 can live in a uniform register only if no IMAD pairs it with an immediate addend: the constants P and 2^32 - P are
+// therefore kept in vector registers too (FK, built once per thread from `one`, opaque to ptxas).
+struct FK { uint32_t one, mone, p, np; };
+static const FK FK_HOST{1u, 0xffffffffu, P, 0x80000001u};
+// all four arrive as kernel arguments (FftArgs): computing them from `one` in the kernel would put `one` into a vector register again
 // canonical reduction of s in [0, 2P): min(s, s-P)
-__device__ __forceinline__ uint32_t cred(uint32_t s, uint32_t one) { return min(s, fadd(s, 0x80000001u, one)); }  // s + (2^32 - P)
+__device__ __forceinline__ uint32_t cred(uint32_t s, const FK& k) { return min(s, fadd(s, k.np, k.one)); }  // s + (2^32 - P)
 // b*t mod P for b in [0,P], t in [0,P) given as t2 = 2t: the 64-bit product 2bt has (bt >> 31) in its high word and
 // (bt & P) << 1 in its low word, so bt = hi + (lo >> 1) (mod P) — one IMAD.WIDE and one IMAD.HI, no shifts or masks.
-__device__ __forceinline__ uint32_t mulred(uint32_t b, uint32_t t2, uint32_t one) {
+__device__ __forceinline__ uint32_t mulred(uint32_t b, uint32_t t2, const FK& k) {
   const uint64_t pr = (uint64_t)b * t2;
   const uint32_t lo = (uint32_t)pr, hi = (uint32_t)(pr >> 32);
   uint32_t s;
 #ifdef SB_FFT_IMADHI
-  asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(s) : "r"(lo), "r"(one << 31), "r"(hi));   // runtime 2^31: stays an IMAD.HI (FMA pipe)
+  asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(s) : "r"(lo), "r"(k.one << 31), "r"(hi));   // runtime 2^31: stays an IMAD.HI (FMA pipe)
 #else
   asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(s) : "r"(lo), "r"(0x80000000u), "r"(hi));  // ptxas turns this into LEA.HI (ALU pipe)
 #endif
-  return cred(s, one);
+  return cred(s, k);
 }
-__device__ __forceinline__ void bfly_fwd(uint32_t& a, uint32_t& b, uint32_t t2, uint32_t one) {
-  const uint32_t mone = 0u - one;
-  uint32_t m = mulred(b, t2, one);
+__device__ __forceinline__ void bfly_fwd(uint32_t& a, uint32_t& b, uint32_t t2, const FK& k) {
+  uint32_t m = mulred(b, t2, k);
   uint32_t a0 = a;
-  a = cred(fadd(a0, m, one), one);
-  uint32_t d = fsub(a0, m, mone);                       // wraps when a0 < m
-  b = min(d, fadd(d, P, one));
+  a = cred(fadd(a0, m, k.one), k);
+  uint32_t d = fsub(a0, m, k.mone);                       // wraps when a0 < m
+  b = min(d, fadd(d, k.p, k.one));
 }
-__device__ __forceinline__ void bfly_inv(uint32_t& a, uint32_t& b, uint32_t t2, uint32_t one) {
-  const uint32_t mone = 0u - one;
+__device__ __forceinline__ void bfly_inv(uint32_t& a, uint32_t& b, uint32_t t2, const FK& k) {
   uint32_t a0 = a;
-  a = cred(fadd(a0, b, one), one);
-  uint32_t d = fsub(a0, b, mone);
-  b = mulred(min(d, fadd(d, P, one)), t2, one);
+  a = cred(fadd(a0, b, k.one), k);
+  uint32_t d = fsub(a0, b, k.mone);
+  b = mulred(min(d, fadd(d, k.p, k.one)), t2, k);
 }
 
 // ---------------------------------------------------------------- compile-time round partition
@@ -156,7 +161,7 @@ struct FftArgs {
   uint32_t src_log;       // loads read index & (2^src_log - 1); forward layers >= src_log are copies (zero-padded coeffs)
   uint32_t L0;            // strided pass: global bit of local bit STRIDED_C
   uint32_t scale;         // multiply on store (inverse normalisation), 1 = none
-  uint32_t one;           // runtime 1 (see fadd)
+  FK k;                   // runtime 1, -1, P, 2^32 - P (see fadd, FK)
 };
 
 // One register round over local bits [B, B+R) of a 2^K tile.  gb = global bit of local bit B; T = tile index bits above the tile.
@@ -164,7 +169,7 @@ template <bool INV, int K, int B, int R, bool CIRCLE>
 __device__ __forceinline__ void fft_round(uint32_t* __restrict__ sm, const FftArgs& a, uint32_t T, uint32_t gb) {
   constexpr int M = 1 << R;
   constexpr int NG = 1 << (K - R);
-  const uint32_t one = a.one;
+  const FK one = a.k;
   for (int q = threadIdx.x; q < NG; q += blockDim.x) {
     const uint32_t low = q & ((1u << B) - 1u), high = (uint32_t)q >> B;
     const uint32_t li0 = low | (high << (B + R));
@@ -359,7 +364,7 @@ static int launch_one(const FftArgs& a, dim3 grid, cudaStream_t st) {
 template <bool INV>
 static int run_pass(const PassDesc& d, const uint32_t* const* src, uint32_t* const* dst, uint32_t ncols, uint32_t n,
                     uint32_t src_log, const uint32_t* twend, uint32_t scale, cudaStream_t st, bool line = false) {
-  FftArgs a{src, dst, twend, n, src_log, d.L0, scale, 1u};
+  FftArgs a{src, dst, twend, n, src_log, d.L0, scale, FK_HOST};
   dim3 grid(1u << (n - d.K), ncols);
   if (d.low && line) {
     switch (d.K) {
@@ -452,6 +457,7 @@ __global__ void line_fft_small_kernel(FftArgs a, uint32_t ncols) {
   if (c >= ncols) return;
   const uint32_t n = a.n, size = 1u << n;
   const uint32_t smask = (a.src_log >= 32) ? 0xffffffffu : ((1u << a.src_log) - 1u);
+  const FK fk = a.k;
   uint32_t v[4];
   for (uint32_t i = 0; i < size; i++) v[i] = a.src[c][i & smask];
   for (uint32_t ss = 0; ss < n; ss++) {
@@ -460,7 +466,7 @@ __global__ void line_fft_small_kernel(FftArgs a, uint32_t ncols) {
     const uint32_t* tw = a.twend - ((size_t)1 << (n - s));
     for (uint32_t i = 0; i < size; i++) {
       if ((i >> s) & 1u) continue;
-      if (INV) bfly_inv(v[i], v[i + (1u << s)], tw[i >> (s + 1)], a.one); else bfly_fwd(v[i], v[i + (1u << s)], tw[i >> (s + 1)], a.one);
+      if (INV) bfly_inv(v[i], v[i + (1u << s)], tw[i >> (s + 1)], fk); else bfly_fwd(v[i], v[i + (1u << s)], tw[i >> (s + 1)], fk);
     }
   }
   for (uint32_t i = 0; i < size; i++) a.dst[c][i] = a.scale != 1u ? m_mul(v[i], a.scale) : v[i];
@@ -474,7 +480,7 @@ int launch_interpolate_repeated(const uint32_t* const* src, uint32_t* const* col
   if (ncols == 0) return 0;
   uint32_t ninv = m_inv(m_pow(2, n));
   if (n < 3) {
-    FftArgs a{src, cols, itw_end, n, 32, 0, ninv, 1u};
+    FftArgs a{src, cols, itw_end, n, 32, 0, ninv, FK_HOST};
     line_fft_small_kernel<true><<<(ncols + 63) / 64, 64, 0, st>>>(a, ncols); g_launch_count++;
     return (int)cudaGetLastError();
   }
@@ -494,7 +500,7 @@ int launch_evaluate_repeated(const uint32_t* const* coeffs, uint32_t* const* out
   if (ncols == 0) return 0;
   if (n - src_log > 1) return -1;
   if (n < 3) {
-    FftArgs a{coeffs, out, tw_end, n, src_log, 0, 1u, 1u};
+    FftArgs a{coeffs, out, tw_end, n, src_log, 0, 1u, FK_HOST};
     line_fft_small_kernel<false><<<(ncols + 63) / 64, 64, 0, st>>>(a, ncols); g_launch_count++;
     return (int)cudaGetLastError();
   }
