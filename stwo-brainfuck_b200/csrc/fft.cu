@@ -106,40 +106,38 @@ __device__ __forceinline__ uint32_t fsub(uint32_t y, uint32_t x, uint32_t mone) 
   asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(mone), "r"(y));
   return r;
 }
-// The IMAD forms matter (measured on the Blake2s G mix, tools/exp/gmix.cu: 96.5 % of the pipe with the multiplicand in a
-// UNIFORM register, 88 % with three vector-register operands).  An IMAD takes one non-vector operand only, so the runtime
-// +-1 can live in a uniform register only if no IMAD pairs it with an immediate addend: the constants P and 2^32 - P are
-// therefore kept in vector registers too (FK, built once per thread from `one`, opaque to ptxas).
-struct FK { uint32_t one, mone, p, np; };
-static const FK FK_HOST{1u, 0xffffffffu, P, 0x80000001u};
-// all four arrive as kernel arguments (FftArgs): computing them from `one` in the kernel would put `one` into a vector register again
-// canonical reduction of s in [0, 2P): min(s, s-P)
-__device__ __forceinline__ uint32_t cred(uint32_t s, const FK& k) { return min(s, fadd(s, k.np, k.one)); }  // s + (2^32 - P)
+// Butterfly = 7 instructions.  sm_100a has VIADDMNMX (min(s, s + imm) in ONE ALU-pipe instruction), which is what a
+// conditional subtraction of P is; with it a butterfly is IMAD.WIDE + LEA.HI + VIADDMNMX (b*t), IMAD + VIADDMNMX (a + bt),
+// IMAD + VIADDMNMX (a - bt): 4 ALU-pipe and 3 FMA-pipe instructions.  (Round 1/2 spelled the reduction as IMAD + VIMNMX to
+// keep the ALU pipe free: 10 instructions, 6 of them on the FMA pipe, whose IMAD rate — one warp instruction every two
+// cycles per sub-partition — then bounded the kernel at 12 cycles per butterfly; now the ALU pipe bounds it at 8.)
+// The two remaining additions stay IMADs with the +-1 multiplicand in a UNIFORM register (tools/exp/gmix.cu: the
+// three-vector-register form costs 9 % of the pipe); FK arrives as kernel arguments so that `one` never needs a vector register.
+struct FK { uint32_t one, mone; };
+static const FK FK_HOST{1u, 0xffffffffu};
+// canonical reduction of s in [0, 2P): min(s, s - P) as unsigned
+__device__ __forceinline__ uint32_t cred(uint32_t s) { return min(s, s + 0x80000001u); }
 // b*t mod P for b in [0,P], t in [0,P) given as t2 = 2t: the 64-bit product 2bt has (bt >> 31) in its high word and
-// (bt & P) << 1 in its low word, so bt = hi + (lo >> 1) (mod P) — one IMAD.WIDE and one IMAD.HI, no shifts or masks.
-__device__ __forceinline__ uint32_t mulred(uint32_t b, uint32_t t2, const FK& k) {
+// (bt & P) << 1 in its low word, so bt = hi + (lo >> 1) (mod P): LEA.HI, no shifts or masks.
+__device__ __forceinline__ uint32_t mulred(uint32_t b, uint32_t t2) {
   const uint64_t pr = (uint64_t)b * t2;
   const uint32_t lo = (uint32_t)pr, hi = (uint32_t)(pr >> 32);
   uint32_t s;
-#ifdef SB_FFT_IMADHI
-  asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(s) : "r"(lo), "r"(k.one << 31), "r"(hi));   // runtime 2^31: stays an IMAD.HI (FMA pipe)
-#else
   asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(s) : "r"(lo), "r"(0x80000000u), "r"(hi));  // ptxas turns this into LEA.HI (ALU pipe)
-#endif
-  return cred(s, k);
+  return cred(s);
 }
 __device__ __forceinline__ void bfly_fwd(uint32_t& a, uint32_t& b, uint32_t t2, const FK& k) {
-  uint32_t m = mulred(b, t2, k);
-  uint32_t a0 = a;
-  a = cred(fadd(a0, m, k.one), k);
-  uint32_t d = fsub(a0, m, k.mone);                       // wraps when a0 < m
-  b = min(d, fadd(d, k.p, k.one));
+  const uint32_t m = mulred(b, t2);
+  const uint32_t a0 = a;
+  a = cred(fadd(a0, m, k.one));
+  const uint32_t d = fsub(a0, m, k.mone);                 // wraps when a0 < m
+  b = min(d, d + P);
 }
 __device__ __forceinline__ void bfly_inv(uint32_t& a, uint32_t& b, uint32_t t2, const FK& k) {
-  uint32_t a0 = a;
-  a = cred(fadd(a0, b, k.one), k);
-  uint32_t d = fsub(a0, b, k.mone);
-  b = mulred(min(d, fadd(d, k.p, k.one)), t2, k);
+  const uint32_t a0 = a;
+  a = cred(fadd(a0, b, k.one));
+  const uint32_t d = fsub(a0, b, k.mone);
+  b = mulred(min(d, d + P), t2);
 }
 
 // ---------------------------------------------------------------- compile-time round partition
