@@ -62,7 +62,8 @@ struct DomainEval {
   uint32_t row, prev_row;
   int col = 0, k = 0, pending = 0;
   // sum_k coeff_k * constraint_k in four 64-bit lanes: one IMAD.WIDE per coordinate and base-field constraint, a partial
-  // fold after every second product (2 * 2^62 + the folded rest stays below 2^64), one full reduction at the end
+  // fold after every third product (high word back in with weight 2^32 == 2: one IMAD.WIDE, result < 3 * 2^32, and
+  // 3 * 2^62 + that stays below 2^64), one full reduction at the end
   unsigned long long acc[4] = {0, 0, 0, 0};
   LogupState<DomainEval> lg;
   __device__ DomainEval(const AirParams& pp, uint32_t r, uint32_t pr) : p(pp), row(r), prev_row(pr) {}
@@ -77,10 +78,10 @@ struct DomainEval {
     const QM31 q = p.coeff[k++];
     acc[0] += (unsigned long long)q.a.a * c.v; acc[1] += (unsigned long long)q.a.b * c.v;
     acc[2] += (unsigned long long)q.b.a * c.v; acc[3] += (unsigned long long)q.b.b * c.v;
-    if (++pending == 2) {
+    if (++pending == 3) {
       pending = 0;
 #pragma unroll
-      for (int j = 0; j < 4; j++) acc[j] = (acc[j] >> 31) + (acc[j] & P);
+      for (int j = 0; j < 4; j++) acc[j] = (unsigned long long)(uint32_t)(acc[j] >> 32) * 2u + (uint32_t)acc[j];
     }
   }
   __device__ void add(EF c) {

@@ -158,7 +158,7 @@ struct FftArgs {
   uint32_t n;             // transform log size
   uint32_t src_log;       // loads read index & (2^src_log - 1); forward layers >= src_log are copies (zero-padded coeffs)
   uint32_t L0;            // strided pass: global bit of local bit STRIDED_C
-  uint32_t scale;         // multiply on store (inverse normalisation), 1 = none
+  uint32_t scale;         // multiply on store (inverse normalisation), 1 = none; the kernels multiply by 2*scale (mulred)
   FK k;                   // runtime 1, -1, P, 2^32 - P (see fadd, FK)
 };
 
@@ -293,12 +293,12 @@ __global__ void __launch_bounds__(K >= 14 ? 1024 : 256, K >= 14 ? 1 : 4) fft_ker
 
   Rounds<INV, K, LOW, LINE, SC, 0, n_rounds(LOW ? K : K - SC)>::run(sm, a, T);
 
-  const uint32_t scale = a.scale;
+  const uint32_t scale = a.scale, scale2 = a.scale << 1;
   for (uint32_t li = threadIdx.x * 4; li < (1u << K); li += blockDim.x * 4) {
     uint32_t g = gbase | (li & cm) | ((li >> C) << L0);
     uint32_t o = li + (li >> 5);
     uint4 x = make_uint4(sm[o], sm[o + 1], sm[o + 2], sm[o + 3]);
-    if (scale != 1u) { x.x = m_mul(x.x, scale); x.y = m_mul(x.y, scale); x.z = m_mul(x.z, scale); x.w = m_mul(x.w, scale); }
+    if (scale != 1u) { x.x = mulred(x.x, scale2); x.y = mulred(x.y, scale2); x.z = mulred(x.z, scale2); x.w = mulred(x.w, scale2); }
     *reinterpret_cast<uint4*>(dst + g) = x;
   }
 }

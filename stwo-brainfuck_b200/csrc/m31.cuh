@@ -32,9 +32,25 @@ SB_HD uint32_t m_reduce64(uint64_t v) {
   uint32_t t = s - P;
   return t < s ? t : s;  // note: s == 2P -> t == P -> handled below
 }
+// Device form (sm_100a, 4 instructions: SHL/IADD, IMAD.WIDE, LEA.HI, VIADDMNMX): the 64-bit product a * 2b has
+// (ab >> 31) in its high word and (ab & P) << 1 in its low word, so ab = hi + (lo >> 1) (mod P), at most 2P - 2, and one
+// conditional subtraction — min(s, s - P) as unsigned, a single VIADDMNMX — makes it canonical.  a, b in [0, P].
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ uint32_t m_hl(uint32_t hi, uint32_t lo) {   // hi + (lo >> 1) as LEA.HI
+  uint32_t s;
+  asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(s) : "r"(lo), "r"(0x80000000u), "r"(hi));
+  return s;
+}
+#endif
 SB_HD uint32_t m_mul(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  const uint64_t pr = (uint64_t)a * (b << 1);
+  const uint32_t s = m_hl((uint32_t)(pr >> 32), (uint32_t)pr);
+  return min(s, s - P);
+#else
   uint32_t r = m_reduce64((uint64_t)a * b);
   return r == P ? 0 : r;
+#endif
 }
 SB_HD uint32_t m_sqr(uint32_t a) { return m_mul(a, a); }
 SB_HD uint32_t m_pow(uint32_t a, uint32_t e) {
@@ -68,17 +84,40 @@ struct CM31 {
 SB_HD CM31 c_add(CM31 x, CM31 y) { return {m_add(x.a, y.a), m_add(x.b, y.b)}; }
 SB_HD CM31 c_sub(CM31 x, CM31 y) { return {m_sub(x.a, y.a), m_sub(x.b, y.b)}; }
 SB_HD CM31 c_neg(CM31 x) { return {m_neg(x.a), m_neg(x.b)}; }
-// Any 64-bit value -> canonical [0,P): two folds by 2^31 == 1 (mod P) and one conditional subtraction.
+// Any 64-bit value -> canonical [0,P).  Host: two folds by 2^31 == 1 (mod P) and one conditional subtraction.  Device: the
+// high word folds in with weight 2^32 == 2 (one IMAD.WIDE), what is left is below 2^34: one fold and one VIADDMNMX.
 SB_HD uint32_t m_red_wide(uint64_t v) {
+#if defined(__CUDA_ARCH__)
+  const uint64_t t = (uint64_t)(uint32_t)(v >> 32) * 2u + (uint32_t)v;   // < 3 * 2^32
+  const uint32_t s = (uint32_t)(t >> 31) + ((uint32_t)t & P);            // <= P + 5
+  return min(s, s - P);
+#else
   v = (v >> 31) + (v & P);                               // < 2^33 + 2^31
   uint32_t s = (uint32_t)(v >> 31) + ((uint32_t)v & P);  // < P + 8
   return s >= P ? s - P : s;
+#endif
 }
+#if defined(__CUDA_ARCH__)
+// x*y2 + z*w2 for DOUBLED second factors (y2 = 2y, w2 = 2w; x, y, z, w in [0,P]): the sum is 2T with T < 2^63, its high
+// word T >> 31 is below 2P, so: conditional subtraction, LEA.HI with the low word, conditional subtraction — 2 IMAD.WIDE + 3.
+__device__ __forceinline__ uint32_t m_dot2(uint32_t x, uint32_t y2, uint32_t z, uint32_t w2) {
+  const uint64_t pr = (uint64_t)x * y2 + (uint64_t)z * w2;
+  uint32_t hi = (uint32_t)(pr >> 32);
+  hi = min(hi, hi - P);
+  const uint32_t s = m_hl(hi, (uint32_t)pr);
+  return min(s, s - P);
+}
+#endif
 SB_HD CM31 c_mul(CM31 x, CM31 y) {
+#if defined(__CUDA_ARCH__)
+  const uint32_t ya2 = y.a << 1, yb2 = y.b << 1, nyb2 = (P - y.b) << 1;
+  return {m_dot2(x.a, ya2, x.b, nyb2), m_dot2(x.a, yb2, x.b, ya2)};
+#else
   // (a+bi)(c+di) = (ac - bd) + (ad + bc)i; each coordinate is ONE 64-bit sum of two products (-bd as b(P-d)), reduced once
   uint64_t re = (uint64_t)x.a * y.a + (uint64_t)x.b * (P - y.b);
   uint64_t im = (uint64_t)x.a * y.b + (uint64_t)x.b * y.a;
   return {m_red_wide(re), m_red_wide(im)};
+#endif
 }
 SB_HD CM31 c_mulm(CM31 x, uint32_t m) { return {m_mul(x.a, m), m_mul(x.b, m)}; }
 SB_HD CM31 c_inv(CM31 x) {
@@ -99,14 +138,26 @@ SB_HD CM31 c_mulR(CM31 x) {  // * (2 + i)
   return {m_sub(m_add(x.a, x.a), x.b), m_add(m_add(x.b, x.b), x.a)};
 }
 SB_HD QM31 q_mul(QM31 x, QM31 y) {
-  // x = A + Bu, y = C + Du, u^2 = 2 + i:  (AC + (2+i)BD) + (AD + BC)u.  BD is reduced first; every other coordinate is one
-  // 64-bit sum (at most four products, 4P^2 < 2^64) and one reduction: 16 multiplications and 6 reductions in all.
+  // x = A + Bu, y = C + Du, u^2 = 2 + i:  (AC + (2+i)BD) + (AD + BC)u.
+#if defined(__CUDA_ARCH__)
+  // AC and BD as two-product sums with doubled factors (m_dot2: 2 IMAD.WIDE + 3 each), AD + BC as four-product 64-bit sums
+  const uint32_t c02 = y.a.a << 1, c12 = y.a.b << 1, nc12 = (P - y.a.b) << 1;
+  const CM31 ac = {m_dot2(x.a.a, c02, x.a.b, nc12), m_dot2(x.a.a, c12, x.a.b, c02)};
+  const CM31 bd = c_mul(x.b, y.b);
+  const uint32_t nc1 = P - y.a.b, nd1 = P - y.b.b;
+  const uint64_t ure = (uint64_t)x.a.a * y.b.a + (uint64_t)x.a.b * nd1 + (uint64_t)x.b.a * y.a.a + (uint64_t)x.b.b * nc1;
+  const uint64_t uim = (uint64_t)x.a.a * y.b.b + (uint64_t)x.a.b * y.b.a + (uint64_t)x.b.a * y.a.b + (uint64_t)x.b.b * y.a.a;
+  return {c_add(ac, c_mulR(bd)), {m_red_wide(ure), m_red_wide(uim)}};
+#else
+  // BD is reduced first; every other coordinate is one 64-bit sum (at most four products, 4P^2 < 2^64) and one reduction:
+  // 16 multiplications and 6 reductions in all.
   const CM31 bd = c_mul(x.b, y.b);
   uint64_t re = (uint64_t)x.a.a * y.a.a + (uint64_t)x.a.b * (P - y.a.b) + 2ull * bd.a + (P - bd.b);
   uint64_t im = (uint64_t)x.a.a * y.a.b + (uint64_t)x.a.b * y.a.a + bd.a + 2ull * bd.b;
   uint64_t ure = (uint64_t)x.a.a * y.b.a + (uint64_t)x.a.b * (P - y.b.b) + (uint64_t)x.b.a * y.a.a + (uint64_t)x.b.b * (P - y.a.b);
   uint64_t uim = (uint64_t)x.a.a * y.b.b + (uint64_t)x.a.b * y.b.a + (uint64_t)x.b.a * y.a.b + (uint64_t)x.b.b * y.a.a;
   return {{m_red_wide(re), m_red_wide(im)}, {m_red_wide(ure), m_red_wide(uim)}};
+#endif
 }
 SB_HD QM31 q_mulm(QM31 x, uint32_t m) { return {c_mulm(x.a, m), c_mulm(x.b, m)}; }
 SB_HD QM31 q_mulc(QM31 x, CM31 c) { return {c_mul(x.a, c), c_mul(x.b, c)}; }

@@ -491,13 +491,9 @@ int launch_prefix_sum_bitrev_tiled(uint32_t* const* v, uint32_t ncols, uint32_t 
 typedef EvalTaskHost EvalTask;  // {coeffs, log, first_block (prefix of stage-1 blocks), f[28]}
 constexpr uint32_t EV_CHUNK_LOG = 13;
 
-__device__ __forceinline__ uint64_t ev_fold(uint64_t v) { return (v >> 31) + (v & P); }
-__device__ __forceinline__ uint32_t ev_red(uint64_t v) {
-  v = (v >> 31) + (v & P);
-  v = (v >> 31) + (v & P);
-  uint32_t s = (uint32_t)v;
-  return s >= P ? s - P : s;
-}
+// high word back in with weight 2^32 == 2 (mod P): one IMAD.WIDE, result < 3 * 2^32 (three more products fit below 2^64)
+__device__ __forceinline__ uint64_t ev_fold(uint64_t v) { return (uint64_t)(uint32_t)(v >> 32) * 2u + (uint32_t)v; }
+__device__ __forceinline__ uint32_t ev_red(uint64_t v) { return m_red_wide(v); }
 
 __global__ void __launch_bounds__(256) eval_stage1_kernel(const EvalTask* __restrict__ tasks, uint32_t ntasks, QM31* __restrict__ partials) {
   // locate task by binary search over first_block

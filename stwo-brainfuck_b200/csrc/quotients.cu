@@ -12,7 +12,7 @@
 // kernel evaluates directly.  HBM-bound: every column word is read once (128-bit loads, 4 consecutive rows per thread),
 // 16 bytes per row are written.  Four consecutive bit-reversed rows are (x,y),(x,-y),(-x,-y),(-x,y): one point per thread.
 // The numerator is split as sum_j C_j*col_j - (py*A + B) with A = sum a_j, B = sum b_j folded on the host, and the
-// sum of products is carried in 64-bit lanes with one partial reduction every two terms.
+// sum of products is carried in 64-bit lanes with one partial reduction (a single IMAD.WIDE) every three terms.
 #include <mutex>
 #include "kernels.cuh"
 
@@ -28,13 +28,10 @@ __device__ __forceinline__ Pt q_point_at_index(uint32_t idx) {
   return r;
 }
 
-__device__ __forceinline__ uint64_t fold64(uint64_t v) { return (v >> 31) + (v & P); }
-__device__ __forceinline__ uint32_t red64(uint64_t v) {  // full reduction of any 64-bit value
-  v = (v >> 31) + (v & P);  // < 2^34
-  v = (v >> 31) + (v & P);  // < 2^31 + 8
-  uint32_t s = (uint32_t)v;
-  return s >= P ? s - P : s;
-}
+// partial fold of a 64-bit lane: the high word re-enters with weight 2^32 == 2 (mod P) — one IMAD.WIDE; the result is below
+// 3 * 2^32, so three more products of two 31-bit factors fit before the next fold (3 * 2^62 + 3 * 2^32 < 2^64)
+__device__ __forceinline__ uint64_t fold64(uint64_t v) { return (uint64_t)(uint32_t)(v >> 32) * 2u + (uint32_t)v; }
+__device__ __forceinline__ uint32_t red64(uint64_t v) { return m_red_wide(v); }  // full reduction of any 64-bit value
 
 __global__ void __launch_bounds__(128) quotients_kernel(uint32_t log, const uint32_t* const* __restrict__ cols,
                                                         const QuotBatch* __restrict__ batches, uint32_t nb,
@@ -70,6 +67,7 @@ __global__ void __launch_bounds__(128) quotients_kernel(uint32_t log, const uint
       uint64_t s[4][4];
 #pragma unroll
       for (int r = 0; r < 4; r++) { s[r][0] = s[r][1] = s[r][2] = s[r][3] = 0; }
+      uint32_t pend = 0;
       for (uint32_t e = qb.first; e < qb.first + qb.count; e++) {
         const QuotEntry en = entries[e];
         uint4 v = __ldg(reinterpret_cast<const uint4*>(cols[en.col]) + k);
@@ -79,7 +77,8 @@ __global__ void __launch_bounds__(128) quotients_kernel(uint32_t log, const uint
           s[r][0] += (uint64_t)en.c[0] * vv[r]; s[r][1] += (uint64_t)en.c[1] * vv[r];
           s[r][2] += (uint64_t)en.c[2] * vv[r]; s[r][3] += (uint64_t)en.c[3] * vv[r];
         }
-        if ((e - qb.first) & 1u) {
+        if (++pend == 3u) {
+          pend = 0;
 #pragma unroll
           for (int r = 0; r < 4; r++) { s[r][0] = fold64(s[r][0]); s[r][1] = fold64(s[r][1]); s[r][2] = fold64(s[r][2]); s[r][3] = fold64(s[r][3]); }
         }
@@ -175,6 +174,7 @@ __global__ void __launch_bounds__(128, 8) quotients_kernel2(const uint32_t* cons
 #pragma unroll
           for (int r = 0; r < 4; r++) { s[r][0] = s[r][1] = s[r][2] = s[r][3] = 0; }
           const uint32_t e0 = qb.first, e1 = qb.first + qb.count;
+          uint32_t pend = 0;
           for (uint32_t e = e0; e < e1; e++) {
             const QuotEntry en = entries[e];
             uint4 v = __ldg(reinterpret_cast<const uint4*>(cols[en.col]) + k);
@@ -184,7 +184,8 @@ __global__ void __launch_bounds__(128, 8) quotients_kernel2(const uint32_t* cons
               s[r][0] += (uint64_t)en.c[0] * vv[r]; s[r][1] += (uint64_t)en.c[1] * vv[r];
               s[r][2] += (uint64_t)en.c[2] * vv[r]; s[r][3] += (uint64_t)en.c[3] * vv[r];
             }
-            if ((e - e0) & 1u) {
+            if (++pend == 3u) {
+              pend = 0;
 #pragma unroll
               for (int r = 0; r < 4; r++) { s[r][0] = fold64(s[r][0]); s[r][1] = fold64(s[r][1]); s[r][2] = fold64(s[r][2]); s[r][3] = fold64(s[r][3]); }
             }
