@@ -74,9 +74,19 @@ def proof_fft_bytes(shape, log_max_rows):
     transformed on their N/16 distinct values (8N/16 in and out) and only the LDE is written at full length (N/16 in, 2N out).
     The composition polynomials are interpolated once (accumulator finalize) and evaluated once."""
     pre, main, inter, comp = proof_columns(shape, log_max_rows)
-    full = sum((8 + 12) * (1 << lg) for lg in pre + inter + comp)
+    full = sum((8 + 12) * (1 << lg) for lg in inter + comp) + sum(12 * (1 << lg) for lg in pre)   # IsFirst polynomials are closed-form
     rep = sum(8 * (1 << (lg - 4)) + 4 * (1 << (lg - 4)) + 8 * (1 << lg) for lg in main)
     return full + rep
+
+
+def proof_fft_butterflies(shape, log_max_rows):
+    """Butterflies the transforms of one proof execute: interpolate of 2^lg values = lg layers of 2^(lg-1); the 2x evaluation =
+    lg layers of 2^lg (the blow-up layer is a copy and is not computed).  Main-trace columns at their compact size lg - 4;
+    the IsFirst polynomials are written in closed form (evaluation only)."""
+    pre, main, inter, comp = proof_columns(shape, log_max_rows)
+    n = sum(lg * (1 << (lg - 1)) + lg * (1 << lg) for lg in inter + comp) + sum(lg * (1 << lg) for lg in pre)
+    n += sum((lg - 4) * (1 << (lg - 5)) + (lg - 4) * (1 << (lg - 4)) for lg in main if lg > 4)
+    return n
 
 
 def tree_stats(lde_logs, rep=0):
@@ -233,6 +243,14 @@ def rooflines(kern, shape, lmr, world, clocks, peaks_int):
                 "note": "bytes as moved: 8N + 12N per polynomial; the lane-repeated main-trace columns at their compact size "
                         "(N/16 in and out for the transforms, the LDE written at full length)"}
     roof_fft["frac"] = roof_fft["achieved"] / peak if roof_fft["achieved"] else None
+    # the transform's own bound is the integer pipes: a butterfly is 7 instructions, 4 of them (LEA.HI + three
+    # VIADDMNMX) on the ALU pipe, and 25 layers of them stand against 8 bytes moved per element and pass
+    nbf = proof_fft_butterflies(shape, lmr) / world
+    roof_fft["int_alu"] = {"butterflies": nbf, "alu_ops_per_butterfly": 4, "ops_per_butterfly": 7,
+                           "achieved": nbf * 4 / (fft_ms * 1e-3) / 1e12 if fft_ms else None, "peak": peaks_int["alu_lop3"], "unit": "Tint32op/s",
+                           "frac": nbf * 4 / (fft_ms * 1e-3) / 1e12 / peaks_int["alu_lop3"] if fft_ms else None,
+                           "note": "ALGORITHMIC ALU-pipe operations (4 per butterfly; addressing, shared-memory and twiddle traffic not "
+                                   "counted) against the measured ALU-pipe rate"}
     return roof, roof_fft
 
 
@@ -382,14 +400,18 @@ def bench_prove(args, workload="prove", extra_only=False):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    # (A) device path: VM first, then everything on the device; per-kernel-class CUDA-event scopes on
-    be.profile(True)
-    be.profile_report()
-    l0 = be.launch_count()
+    # (A) device path: VM first, then everything on the device.  `value` comes from K proofs WITHOUT the per-kernel-class
+    # CUDA-event scopes (two event records per launch cost the host about a millisecond per proof); the kernel breakdown and
+    # the launch count come from K more proofs with the scopes on.
     reports = []
     with ClockSampler(local) as cs:
         for _ in range(args.steps):
             reports.append((prove(overlap_host=False) if world == 1 else prove()).report())
+        be.profile(True)
+        be.profile_report()
+        l0 = be.launch_count()
+        for _ in range(args.steps):
+            (prove(overlap_host=False) if world == 1 else prove())
         launches = be.launch_count() - l0
         prof = be.profile_report()
         be.profile(False)

@@ -176,27 +176,27 @@ __device__ __forceinline__ void fft_round(uint32_t* __restrict__ sm, const FftAr
 #pragma unroll
     for (int m = 0; m < M; m++) v[m] = p[(m << B) + ((m << B) >> 5)];
     const uint32_t H = (T << (K - B - R)) | high;
-    // CIRCLE (low pass, B == 0): line layer 1's 2^(R-2) twiddles also define the 2^(R-1) circle twiddles: [x,y] -> [y,-y,-x,x]
+    // CIRCLE (low pass, B == 0): line layer 1's 2^(R-2) twiddles also define the 2^(R-1) circle twiddles: [x,y] -> [y,-y,-x,x];
+    // fetched right before the first layer that needs them (the forward round walks s = R-1 .. 0: live for two layers only)
     uint32_t w1[CIRCLE ? (M / 4) : 1];
-    if (CIRCLE) {
-      const uint32_t* l1 = a.twend - ((size_t)1 << (a.n - 1)) + ((size_t)H << (R - 2));
-      if (R >= 4) {
-#pragma unroll
-        for (int i = 0; i < M / 16; i++) {
-          uint4 x = __ldg(reinterpret_cast<const uint4*>(l1) + i);
-          w1[4 * i] = x.x; w1[4 * i + 1] = x.y; w1[4 * i + 2] = x.z; w1[4 * i + 3] = x.w;
-        }
-      } else {
-        uint2 x = __ldg(reinterpret_cast<const uint2*>(l1));
-        w1[0] = x.x; w1[1] = x.y;
-      }
-    }
 #pragma unroll
     for (int ss = 0; ss < R; ss++) {
       const int s = INV ? ss : (R - 1 - ss);
       const uint32_t l = gb + s;
+      if (CIRCLE && s == (INV ? 0 : 1)) {
+        const uint32_t* l1 = a.twend - ((size_t)1 << (a.n - 1)) + ((size_t)H << (R - 2));
+        if (R >= 4) {
+#pragma unroll
+          for (int i = 0; i < M / 16; i++) {
+            uint4 x = __ldg(reinterpret_cast<const uint4*>(l1) + i);
+            w1[4 * i] = x.x; w1[4 * i + 1] = x.y; w1[4 * i + 2] = x.z; w1[4 * i + 3] = x.w;
+          }
+        } else {
+          uint2 x = __ldg(reinterpret_cast<const uint2*>(l1));
+          w1[0] = x.x; w1[1] = x.y;
+        }
+      }
       if (!INV && l >= a.src_log) continue;  // (v0, 0) -> (v0, v0): already done by the masked load
-      constexpr int dummy = 0; (void)dummy;
       const int NT = M >> (s + 1);           // distinct twiddles of this layer in the group
       uint32_t tw[M / 2];
       if (CIRCLE && s == 0) {

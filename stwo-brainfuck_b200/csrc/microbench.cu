@@ -6,8 +6,9 @@
 //   kind 0  LOP3   (xor3)                 ALU pipe        kind 3  IADD3 (add.u32 x2 -> one IADD3)   ALU pipe
 //   kind 1  SHF    (rotate by 12)         ALU pipe        kind 4  IMAD  (mad.lo.u32)                FMA pipe
 //   kind 2  PRMT   (rotate by 16)         ALU pipe        kind 5  ALU+IMAD 1:1 interleaved          both pipes
-//   kind 6  the Blake2s G mix exactly as merkle.cu issues it: per G 4 LOP3 + 2 SHF + 2 PRMT (ALU) and 6 IMAD (FMA),
-//           four independent G columns per thread, i.e. the compression without its loads and stores.
+//   kind 6  the Blake2s G mix exactly as merkle.cu issues it: per G 4 LOP3 + 2 SHF + 2 PRMT (ALU) and 6 IMAD (FMA, the
+//           multiplicand in a uniform register), four independent G columns per thread, i.e. the compression without its
+//           loads and stores.
 // The instruction classes are fixed with inline PTX; `cuobjdump -sass` of this file shows the SASS each one became
 // (profiles/r2_microbench_sass.txt).  Not on the proving path.
 #include "kernels.cuh"
@@ -20,6 +21,9 @@ __global__ void __launch_bounds__(1024) int_pipe_kernel(uint32_t iters, uint32_t
   uint32_t x0 = seed + threadIdx.x, x1 = x0 * 3u + 1u, x2 = x0 * 5u + 2u, x3 = x0 * 7u + 3u;
   uint32_t x4 = x0 * 11u + 4u, x5 = x0 * 13u + 5u, x6 = x0 * 17u + 6u, x7 = x0 * 19u + 7u;
   const uint32_t k0 = seed ^ 0x9E3779B9u, k1 = seed * 0x85EBCA6Bu + 1u;
+  uint32_t y0 = x0 ^ 0x243F6A88u, y1 = x1 ^ 0x85A308D3u, y2 = x2 ^ 0x13198A2Eu, y3 = x3 ^ 0x03707344u;   // KIND 6: four G columns
+  uint32_t y4 = x4 ^ 0xA4093822u, y5 = x5 ^ 0x299F31D0u, y6 = x6 ^ 0x082EFA98u, y7 = x7 ^ 0xEC4E6C89u;
+  const uint32_t m0 = k0 + threadIdx.x, m1 = k1 ^ threadIdx.x;                                          // message words: vector registers
   __syncthreads();
   const long long t0 = clock64();
 #define OP8(INS)                                                                                      \
@@ -42,20 +46,23 @@ __global__ void __launch_bounds__(1024) int_pipe_kernel(uint32_t iters, uint32_t
       I_IMAD(x0) I_LOP3(x1) I_IMAD(x2) I_LOP3(x3) I_IMAD(x4) I_LOP3(x5) I_IMAD(x6) I_LOP3(x7)
     }
     if (KIND == 6) {
-      // two G columns on (x0..x3) and (x4..x7) as (a, b, c, d), message words k0 / k1: 14 instructions each, issued twice
+      // four G columns on (x0..x3), (x4..x7), (y0..y3), (y4..y7) as (a, b, c, d), message words in vector registers, the
+      // IMAD multiplicand `one` in a UNIFORM register (a kernel argument, never paired with an immediate addend): the form
+      // blake2s.cuh compiles to.  With `one` in a vector register (three vector operands per IMAD, the round-1 form) the
+      // same mix reaches 88 % of the ALU pipe instead of 96 %.
 #define FADD(r, p, q) asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(p), "r"(one), "r"(q));
 #define XROT_P(r, p, q, sel) asm volatile("{ .reg .u32 t; xor.b32 t, %1, %2; prmt.b32 %0, t, t, " #sel "; }" : "=r"(r) : "r"(p), "r"(q));
 #define XROT_S(r, p, q, n) asm volatile("{ .reg .u32 t; xor.b32 t, %1, %2; shf.r.wrap.b32 %0, t, t, " #n "; }" : "=r"(r) : "r"(p), "r"(q));
 #define GMIX(a, b, c, d)                                                       \
-  FADD(a, b, a) FADD(a, k0, a) XROT_P(d, d, a, 0x1032) FADD(c, d, c) XROT_S(b, b, c, 12) \
-  FADD(a, b, a) FADD(a, k1, a) XROT_P(d, d, a, 0x0321) FADD(c, d, c) XROT_S(b, b, c, 7)
-      GMIX(x0, x1, x2, x3) GMIX(x4, x5, x6, x7)
-      GMIX(x0, x1, x2, x3) GMIX(x4, x5, x6, x7)
+  FADD(a, b, a) FADD(a, m0, a) XROT_P(d, d, a, 0x1032) FADD(c, d, c) XROT_S(b, b, c, 12) \
+  FADD(a, b, a) FADD(a, m1, a) XROT_P(d, d, a, 0x0321) FADD(c, d, c) XROT_S(b, b, c, 7)
+      GMIX(x0, x1, x2, x3) GMIX(x4, x5, x6, x7) GMIX(y0, y1, y2, y3) GMIX(y4, y5, y6, y7)
     }
   }
   const long long t1 = clock64();
   if (threadIdx.x == 0) cycles[blockIdx.x] = (unsigned long long)(t1 - t0);
   uint32_t r = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7;
+  if (KIND == 6) r ^= y0 ^ y1 ^ y2 ^ y3 ^ y4 ^ y5 ^ y6 ^ y7;
   if (r == 0x12345678u) sink[0] = r;  // keeps the chains alive; practically never taken
 }
 
@@ -65,7 +72,7 @@ static void ops_per_iter(int kind, uint32_t* alu, uint32_t* fma) {
   if (kind <= 3) *alu = 32;
   else if (kind == 4) *fma = 32;
   else if (kind == 5) { *alu = 16; *fma = 16; }
-  else { *alu = 4 * 8; *fma = 4 * 6; }
+  else { *alu = 4 * 8; *fma = 4 * 6; }   // four G per iteration
 }
 
 // Runs `kind` on every SM at full occupancy (2 CTAs x 1024 threads per SM, one wave).  out[0] = ALU-pipe lane-ops per clock
