@@ -50,6 +50,7 @@ uint64_t sc_ctx_launch_count(const sc_ctx* ctx);
 /* Per-kernel-class device timing: when enabled every entry point brackets its launches with CUDA events on the launch
  * stream; the report is "tag:milliseconds:count;..." (sum per tag since the last report) and clears the records. */
 int32_t sc_ctx_profile(sc_ctx* ctx, int32_t enable);
+int32_t sc_ctx_profiling(const sc_ctx* ctx);   /* 1 while enabled (sbf_prove then also waits at its stage boundaries, so that stages_ms are device-complete) */
 /* Device-side stopwatch on the compute stream: sc_event_elapsed waits for `b` and returns the milliseconds between the marks. */
 typedef struct sc_event sc_event;
 int32_t sc_event_record(sc_ctx* ctx, sc_event** out);

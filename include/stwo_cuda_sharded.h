@@ -22,6 +22,17 @@ int32_t sc_comm_rank(const sc_comm* comm);
 int32_t sc_comm_world(const sc_comm* comm);
 /* column-shard -> row-shard exchange: per-peer counts in words, blocks laid out in rank order in both buffers */
 int32_t sc_all_to_all(sc_ctx* ctx, sc_comm* comm, const sc_col* send, const uint64_t* send_counts, sc_col* recv, const uint64_t* recv_counts);
+/* Direct column->row exchange: instead of packing a send buffer and handing it to NCCL's send/recv all-to-all, every rank
+ * owns a receive WINDOW (cudaMalloc + CUDA IPC, mapped by all peers) and one kernel of a sending rank writes every
+ * destination's block straight into that rank's window over NVLink; a one-word all-reduce behind it is the completion
+ * barrier.  sc_exchange_begin: collective, once per proof (sizes / maps the windows, one small all-reduce in steady state).
+ * sc_exchange_push: arguments as sc_pack_exchange + the per-source receive counts of sc_all_to_all; *recv_out = the receive
+ * buffer (a region of the window), or NULL when the direct path is unavailable on this box / the window is still too small:
+ * the caller then falls back to sc_pack_exchange + sc_all_to_all (every rank takes the same branch).  SC_NO_PUSH_EXCHANGE=1
+ * disables it (A/B measurements). */
+int32_t sc_exchange_begin(sc_ctx* ctx, sc_comm* comm);
+int32_t sc_exchange_push(sc_ctx* ctx, sc_comm* comm, sc_col* const* cols, const uint64_t* segs, const uint8_t* sharded, uint32_t n,
+                         const uint64_t* recv_counts, sc_col** recv_out);
 int32_t sc_all_gather(sc_ctx* ctx, sc_comm* comm, const sc_col* send, sc_col* recv, uint64_t n);   /* Merkle sub-roots */
 int32_t sc_allreduce_host_u32(sc_ctx* ctx, sc_comm* comm, uint32_t* buf, uint64_t n);              /* tiny host tables */
 
@@ -50,6 +61,13 @@ int32_t sc_fold_line_range_dc(sc_ctx* ctx, sc_col* const src[4], uint32_t log, u
                               const sc_twiddles* tw, sc_col* dst_out[4]);
 int32_t sc_fold_circle_into_line_range_dc(sc_ctx* ctx, sc_col* const src[4], uint32_t log, uint64_t out_off, uint64_t n_out, const sc_dchan* dc,
                                           uint32_t k, const sc_twiddles* tw, sc_col* const dst[4]);
+/* Every remaining FRI layer in one launch once the line evaluation is replicated and has <= 2^10 values (the sharded
+ * driver's counterpart of sc_fri_commit's tail): for lg = start_log .. last_log + 1 fold quot_cols[4t..4t+3] (the quotient
+ * column of log lg + 1; four NULLs when there is none) into the evaluation with coefficient #0, commit it (evals_out[4t..],
+ * layers_out: lg + 1 layers per tree, root at index 0 of each tree's block), mix the root, draw, fold_line (FriProver::
+ * commit_inner_layers, stwo core/fri.rs).  last_out: the 2^last_log values left.  dc advances by start_log - last_log mixes. */
+int32_t sc_dchan_fri_tail(sc_ctx* ctx, sc_dchan* dc, const sc_twiddles* tw, sc_col* const layer_in[4], uint32_t start_log, uint32_t last_log,
+                          sc_col* const* quot_cols, sc_col** evals_out, sc_col** layers_out, sc_col* last_out[4]);
 /* QuotientOps on a row range (row_off, n_rows multiples of 4) */
 int32_t sc_accumulate_quotients_range(sc_ctx* ctx, uint32_t log, uint64_t row_off, uint64_t n_rows, sc_col* const* cols, uint32_t n,
                                       const uint32_t random_coeff[4], const uint32_t* batch_points, const uint32_t* batch_sizes,

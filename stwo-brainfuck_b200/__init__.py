@@ -64,7 +64,7 @@ ABI_SYMBOLS = [
     "sc_batch_inverse_qm31", "sc_precompute_twiddles", "sc_twiddles_free", "sc_twiddles_cached", "sc_twiddles_to_host", "sc_interpolate",
     "sc_evaluate", "sc_eval_at_point", "sc_merkle_commit_layer", "sc_merkle_commit", "sc_fold_line",
     "sc_fold_circle_into_line", "sc_accumulate_quotients", "sc_accumulate", "sc_secure_powers", "sc_grind",
-    "sc_gen_is_first", "sc_is_first_coeffs", "sc_prefix_sum_bitrev", "sc_logup_generate", "sc_eval_constraints", "sc_gather", "sc_ctx_profile", "sc_ctx_profile_report", "sc_ctx_profile_timeline", "sc_ctx_mark", "sc_ctx_release_since", "sc_ctx_live_columns", "sc_event_record", "sc_event_elapsed", "sc_event_free", "sc_interpolate_repeated", "sc_evaluate_repeated", "sc_eval_at_point_repeated",
+    "sc_gen_is_first", "sc_is_first_coeffs", "sc_prefix_sum_bitrev", "sc_logup_generate", "sc_eval_constraints", "sc_gather", "sc_ctx_profile", "sc_ctx_profiling", "sc_ctx_profile_report", "sc_ctx_profile_timeline", "sc_ctx_mark", "sc_ctx_release_since", "sc_ctx_live_columns", "sc_event_record", "sc_event_elapsed", "sc_event_free", "sc_interpolate_repeated", "sc_evaluate_repeated", "sc_eval_at_point_repeated",
     "sc_merkle_commit_layer_repeated", "sc_merkle_commit_repeated", "sc_ctx_attach", "sc_ctx_attached",
     "sc_microbench_int", "sc_fri_commit", "sc_trace_stats_host", "sc_trace_upload", "sc_trace_build_tables", "sc_trace_status", "sc_trace_free",
 ]
@@ -552,7 +552,7 @@ def clear_preprocessed_cache(backend: CudaBackend) -> None:
 # ---------------------------------------------------------------------------------------------------------------------
 # multi-GPU: one process per GPU, NCCL communicator created from an id that the launcher broadcasts (torch.distributed)
 SHARDED_SYMBOLS = ["sc_comm_unique_id", "sc_comm_init", "sc_comm_destroy", "sc_comm_rank", "sc_comm_world", "sc_all_to_all",
-                   "sc_all_gather", "sc_allreduce_host_u32", "sc_pack_exchange", "sc_dchan_create", "sc_dchan_mix_root_draw", "sc_dchan_finish", "sc_dchan_coeff_ptr",
+                   "sc_all_gather", "sc_allreduce_host_u32", "sc_pack_exchange", "sc_exchange_begin", "sc_exchange_push", "sc_dchan_create", "sc_dchan_mix_root_draw", "sc_dchan_finish", "sc_dchan_coeff_ptr", "sc_dchan_fri_tail",
                    "sc_fold_line_range_dc", "sc_fold_circle_into_line_range_dc", "sc_col_copy", "sc_col_view", "sc_fold_line_range",
                    "sc_fold_circle_into_line_range", "sc_accumulate_quotients_range", "sc_shift_prev", "sc_accumulate_col",
                    "sc_logup_generate_sel", "sc_eval_constraints_range", "sc_evaluate_repeated_range", "sbf_prove_sharded"]

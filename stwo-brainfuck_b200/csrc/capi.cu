@@ -113,6 +113,7 @@ int32_t sc_ctx_profile(sc_ctx* ctx, int32_t enable) {
   ctx->profiling = enable != 0;
   return SC_OK;
 }
+int32_t sc_ctx_profiling(const sc_ctx* ctx) { return ctx && ctx->profiling ? 1 : 0; }
 // Sums the recorded scopes per tag into "tag:ms:count;..." and clears them.  Returns the needed length.
 size_t sc_ctx_profile_report(sc_ctx* ctx, char* buf, size_t cap) {
   if (!ctx) return 0;

@@ -190,6 +190,31 @@ struct CudaBackendImpl : Backend {
     for (uint32_t i = 0; i < n_mixes; i++) memcpy(out[i].data(), &w[8 * i], 32);
     return out;
   }
+  uint32_t fri_tail_max_log() const override { return fused_fri ? 10u : 0u; }
+  bool fri_tail_dc(void* dc, const std::array<Col, 4>& layer, uint32_t start_log, uint32_t last_log, const std::vector<std::array<Col, 4>>& quot,
+                   FriTailResult& out) override {
+    if (!dc || !fused_fri || start_log > 10 || start_log <= last_log || quot.size() != start_log - last_log) return false;
+    const uint32_t n_tail = start_log - last_log;
+    std::vector<sc_col*> qc;
+    for (auto& q : quot) for (Col c : q) qc.push_back(c ? h(c) : nullptr);
+    size_t n_layers = 0;
+    for (uint32_t lg = start_log; lg > last_log; lg--) n_layers += lg + 1;
+    std::vector<sc_col*> evals(4 * (size_t)n_tail, nullptr), layers(n_layers, nullptr);
+    sc_col* last[4] = {nullptr, nullptr, nullptr, nullptr};
+    sc_col* in[4] = {h(layer[0]), h(layer[1]), h(layer[2]), h(layer[3])};
+    ck(sc_dchan_fri_tail(ctx, (sc_dchan*)dc, tw, in, start_log, last_log, qc.data(), evals.data(), layers.data(), last));
+    out.evals.clear(); out.trees.clear();
+    size_t loff = 0;
+    for (uint32_t lg = start_log, t = 0; lg > last_log; lg--, t++) {
+      out.evals.push_back({(Col)evals[4 * t], (Col)evals[4 * t + 1], (Col)evals[4 * t + 2], (Col)evals[4 * t + 3]});
+      std::vector<Col> tr(lg + 1);
+      for (uint32_t k = 0; k <= lg; k++) tr[k] = (Col)layers[loff + k];
+      out.trees.push_back(std::move(tr));
+      loff += lg + 1;
+    }
+    out.last = {(Col)last[0], (Col)last[1], (Col)last[2], (Col)last[3]};
+    return true;
+  }
   std::array<Col, 4> fold_line_range_dc(const std::array<Col, 4>& src, uint32_t log, size_t off, size_t n_out, void* dc, uint32_t k) override {
     std::array<Col, 4> out;
     ck(sc_fold_line_range_dc(ctx, (sc_col* const*)src.data(), log, off, n_out, (sc_dchan*)dc, k, tw, (sc_col**)out.data()));
@@ -288,6 +313,15 @@ struct CudaBackendImpl : Backend {
   void pack_exchange(Col send, const std::vector<Col>& cols, const std::vector<size_t>& segs, const std::vector<uint8_t>& sharded) override {
     std::vector<uint64_t> sg(segs.begin(), segs.end());
     ck(sc_pack_exchange(ctx, (sc_col* const*)cols.data(), sg.data(), sharded.data(), (uint32_t)cols.size(), (uint32_t)world(), h(send)));
+  }
+  void exchange_begin() override { if (comm) ck(sc_exchange_begin(ctx, comm)); }
+  Col exchange_push(const std::vector<Col>& cols, const std::vector<size_t>& segs, const std::vector<uint8_t>& sharded,
+                    const std::vector<size_t>& recv_counts) override {
+    if (!comm) return nullptr;
+    std::vector<uint64_t> sg(segs.begin(), segs.end()), rc(recv_counts.begin(), recv_counts.end());
+    sc_col* out = nullptr;
+    ck(sc_exchange_push(ctx, comm, (sc_col* const*)cols.data(), sg.data(), sharded.data(), (uint32_t)cols.size(), rc.data(), &out));
+    return out;
   }
   void all_to_all(Col send, const std::vector<size_t>& sc, Col recv, const std::vector<size_t>& rc) override {
     if (!comm) { copy(recv, 0, send, 0, sc[0]); return; }
@@ -433,13 +467,15 @@ int32_t sbf_prove(sc_ctx* ctx, const char* code, const uint8_t* input, size_t in
     cfg.overlap_host = !(flags & 1u);  // SBF_NO_OVERLAP: VM run and tables before any device work (bench.py's device-path timing)
     B.cache_twiddles = !(flags & 2u);  // SBF_NO_TWIDDLE_CACHE: recompute the twiddle tree in every proof, as the reference does
     auto t1 = std::chrono::steady_clock::now();
-    ProveResult r = prove_brainfuck(B, program, run_vm, cfg, [&] { sc_ctx_sync(ctx); }, pp);
+    // stage boundaries wait for the device only while the profiling scopes are on (sc_ctx_profile): stages_ms are then device-complete
+    // times; otherwise they are the host's enqueue times and the stages overlap as the stream allows
+    ProveResult r = prove_brainfuck(B, program, run_vm, cfg, [&] { if (sc_ctx_profiling(ctx)) sc_ctx_sync(ctx); }, pp);
     const double device_ms = B.ms_since_resident();
     double prove_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
     sbf_proof* p = new sbf_proof{std::move(r.proof), cfg, "", vm.output};
     std::ostringstream o;
     o << "{\"steps\":" << vm.n_rows() << ",\"vm_ms\":" << vm_ms << ",\"prove_ms\":" << prove_ms << ",\"device_ms\":" << device_ms << ",\"h2d_bytes\":" << B.h2d_bytes
-      << ",\"program_words\":" << program.size() << ",\"log_sizes\":[";
+      << ",\"stages_synced\":" << (sc_ctx_profiling(ctx) ? "true" : "false") << ",\"program_words\":" << program.size() << ",\"log_sizes\":[";
     for (int c = 0; c < N_COMPONENTS; c++) o << (c ? "," : "") << p->proof.log_size[c];
     o << "],\"stages_ms\":{";
     for (size_t i = 0; i < r.times.ms.size(); i++) o << (i ? "," : "") << "\"" << r.times.ms[i].first << "\":" << r.times.ms[i].second;
@@ -481,13 +517,13 @@ int32_t sbf_prove_sharded(sc_ctx* ctx, sc_comm* comm, const char* code, const ui
     cfg.shard_min_log = getenv("SBF_SHARD_MIN_LOG") ? (uint32_t)atoi(getenv("SBF_SHARD_MIN_LOG")) : 16;
     B.cache_twiddles = !(flags & 2u);
     auto t1 = std::chrono::steady_clock::now();
-    ProveResult r = prove_brainfuck_sharded(B, program, run_vm, cfg, [&] { sc_ctx_sync(ctx); });
+    ProveResult r = prove_brainfuck_sharded(B, program, run_vm, cfg, [&] { if (sc_ctx_profiling(ctx)) sc_ctx_sync(ctx); });
     const double device_ms = B.ms_since_resident();
     double prove_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
     sbf_proof* p = new sbf_proof{std::move(r.proof), cfg, "", vm.output};
     std::ostringstream o;
     o << "{\"steps\":" << vm.n_rows() << ",\"vm_ms\":" << vm_ms << ",\"prove_ms\":" << prove_ms << ",\"device_ms\":" << device_ms << ",\"h2d_bytes\":" << B.h2d_bytes
-      << ",\"program_words\":" << program.size() << ",\"world\":" << B.world() << ",\"log_sizes\":[";
+      << ",\"stages_synced\":" << (sc_ctx_profiling(ctx) ? "true" : "false") << ",\"program_words\":" << program.size() << ",\"world\":" << B.world() << ",\"log_sizes\":[";
     for (int c = 0; c < N_COMPONENTS; c++) o << (c ? "," : "") << p->proof.log_size[c];
     o << "],\"stages_ms\":{";
     for (size_t i = 0; i < r.times.ms.size(); i++) o << (i ? "," : "") << "\"" << r.times.ms[i].first << "\":" << r.times.ms[i].second;

@@ -41,6 +41,62 @@ int32_t sc_dchan_finish(sc_ctx* ctx, sc_dchan* dc, uint32_t* roots_out) {
   return r;
 }
 
+// The FRI layers of <= 2^FRI_TAIL_LOG values on a device transcript, in ONE launch (fri_tail_kernel): for lg = start_log ..
+// last_log + 1: circle-fold quot_cols[4 * t ..] (the quotient column of log lg + 1, NULL entries when there is none) into the
+// line evaluation with coefficient #0, commit the evaluation (evals_out, layers_out: lg + 1 layers per tree, leaves first
+// at index lg ... root at 0 within each tree's block), mix the root, draw, fold_line.  last_out: the 2^last_log values left.
+// The layer-by-layer driver of the sharded prover calls this once its line evaluation is replicated and small: ten launches
+// per layer (fold, tree, top, channel, fold) become one for the whole tail.  dc advances by start_log - last_log mixes.
+int32_t sc_dchan_fri_tail(sc_ctx* ctx, sc_dchan* dc, const sc_twiddles* tw, sc_col* const layer_in[4], uint32_t start_log, uint32_t last_log,
+                          sc_col* const* quot_cols, sc_col** evals_out, sc_col** layers_out, sc_col* last_out[4]) {
+  ENTER();
+  if (!dc || !tw || !layer_in || !quot_cols || !evals_out || !layers_out || !last_out) return fail(SC_EINVAL, "dchan_fri_tail: null argument");
+  if (start_log > FRI_TAIL_LOG || start_log <= last_log || start_log > tw->root_log) return fail(SC_EINVAL, "dchan_fri_tail: bad log sizes");
+  const uint32_t n_tail = start_log - last_log;
+  if (!dc->n || dc->n + n_tail > dc->max) return fail(SC_EINVAL, "dchan_fri_tail: channel too short (or the first layer was not mixed)");
+  for (int k = 0; k < 4; k++)
+    if (!layer_in[k] || layer_in[k]->len != (1ull << start_log)) return fail(SC_EINVAL, "dchan_fri_tail: bad input layer");
+  const uint32_t* itw_end = tw->itw + ((size_t)1 << tw->root_log);
+  std::vector<sc_col*> made;
+  auto undo = [&](int32_t r) { for (sc_col* c : made) sc_col_free(ctx, c); return r; };
+  std::vector<uint32_t*> evp, trp;
+  std::vector<const uint32_t*> qp;
+  size_t loff = 0;
+  for (uint32_t lg = start_log, t = 0; lg > last_log; lg--, t++) {
+    for (int k = 0; k < 4; k++) {
+      sc_col* c = nullptr; int32_t r = new_col(ctx, 1ull << lg, &c); if (r) return undo(r);
+      made.push_back(c); evals_out[4 * t + k] = c; evp.push_back(c->d);
+    }
+    for (int kk = (int)lg; kk >= 0; kk--) {
+      sc_col* c = nullptr; int32_t r = new_col(ctx, 8ull << kk, &c); if (r) return undo(r);
+      made.push_back(c); layers_out[loff + kk] = c;
+    }
+    for (int kk = (int)lg; kk >= 0; kk--) trp.push_back(layers_out[loff + kk]->d);
+    loff += lg + 1;
+    for (int k = 0; k < 4; k++) {
+      const sc_col* q = quot_cols[4 * t + k];
+      if (q && q->len != (2ull << lg)) return undo(fail(SC_EINVAL, "dchan_fri_tail: bad quotient column"));
+      if ((q == nullptr) != (quot_cols[4 * t] == nullptr)) return undo(fail(SC_EINVAL, "dchan_fri_tail: quotient coordinates must come in fours"));
+      qp.push_back(q ? q->d : nullptr);
+    }
+  }
+  for (int k = 0; k < 4; k++) { sc_col* c = nullptr; int32_t r = new_col(ctx, 1ull << last_log, &c); if (r) return undo(r); made.push_back(c); last_out[k] = c; }
+  void *d_evp, *d_trp, *d_qp;
+  { int32_t r = stage(ctx, evp.data(), evp.size() * sizeof(void*), &d_evp); if (r) return undo(r); }
+  { int32_t r = stage(ctx, trp.data(), trp.size() * sizeof(void*), &d_trp); if (r) return undo(r); }
+  { int32_t r = stage(ctx, qp.data(), qp.size() * sizeof(void*), &d_qp); if (r) return undo(r); }
+  uint32_t* base = dc->buf->d;
+  FriTailArgs a;
+  a.start_log = start_log; a.last_log = last_log; a.one = 1u;
+  for (int k = 0; k < 4; k++) { a.layer_in[k] = layer_in[k]->d; a.last_out[k] = last_out[k]->d; }
+  a.itw_end = itw_end; a.digest = base; a.circle_alpha = base + 8;
+  a.eval_out = (uint32_t* const*)d_evp; a.tree_out = (uint32_t* const*)d_trp; a.quot = (const uint32_t* const*)d_qp;
+  a.roots_out = base + 8 + 4 * (size_t)dc->max + 8 * (size_t)dc->n;
+  { ProfScope ps(ctx, "fri_tail"); int e = launch_fri_tail(a, ctx->st); if (e) { undo(0); CKL(e); } }
+  dc->n += n_tail;
+  return SC_OK;
+}
+
 // FriProver::commit (stwo-prover 0.1.1 @ 31e8dbc core/fri.rs; reached from prover::prove, crates/brainfuck_prover/src/
 // brainfuck_air/mod.rs:732) with the transcript kept on the device — see fri.cu.
 int32_t sc_fri_commit(sc_ctx* ctx, const sc_twiddles* tw, sc_col* const* quot_cols, const uint32_t* quot_logs, uint32_t nq,

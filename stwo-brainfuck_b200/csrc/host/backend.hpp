@@ -128,6 +128,16 @@ struct Backend {
   virtual void* dchan_begin(const Hash& channel_digest, uint32_t max_mixes) { (void)channel_digest; (void)max_mixes; return nullptr; }
   virtual void dchan_mix_root_draw(void* dc, Col root_col) { (void)dc; (void)root_col; }
   virtual std::vector<Hash> dchan_finish(void* dc, uint32_t n_mixes) { (void)dc; (void)n_mixes; return {}; }   // waits; frees dc
+  // All FRI layers from `start_log` down to last_log + 1 on the device transcript in one call (optional; false = not
+  // available, the caller walks the layers).  `layer`: the replicated line evaluation of log start_log BEFORE the quotient of
+  // that size is folded in; quot[t]: the quotient columns of log start_log - t + 1 (nullptr entries when there are none).
+  // Out, per layer t: the committed evaluation, its tree (layers[k] = 2^k nodes); `last`: the 2^last_log values left.
+  struct FriTailResult { std::vector<std::array<Col, 4>> evals; std::vector<std::vector<Col>> trees; std::array<Col, 4> last; };
+  virtual uint32_t fri_tail_max_log() const { return 0; }
+  virtual bool fri_tail_dc(void* dc, const std::array<Col, 4>& layer, uint32_t start_log, uint32_t last_log,
+                           const std::vector<std::array<Col, 4>>& quot, FriTailResult& out) {
+    (void)dc; (void)layer; (void)start_log; (void)last_log; (void)quot; (void)out; return false;
+  }
   virtual std::array<Col, 4> fold_line_range_dc(const std::array<Col, 4>& src, uint32_t log, size_t out_off, size_t n_out, void* dc, uint32_t k) {
     (void)src; (void)log; (void)out_off; (void)n_out; (void)dc; (void)k; throw std::runtime_error("no device channel");
   }
@@ -179,6 +189,14 @@ struct Backend {
     }
   }
   virtual void all_to_all(Col send, const std::vector<size_t>& send_counts, Col recv, const std::vector<size_t>& recv_counts) = 0;
+  // Optional direct exchange (CUDA: peer stores into the destination's receive window, csrc/sharded.cu): exchange_begin once per
+  // proof (collective); exchange_push = pack_exchange + all_to_all in one step, returning the receive buffer, or nullptr when
+  // the backend has no such path (the caller then packs and calls all_to_all).  Every rank gets the same answer.
+  virtual void exchange_begin() {}
+  virtual Col exchange_push(const std::vector<Col>& cols, const std::vector<size_t>& segs, const std::vector<uint8_t>& sharded,
+                            const std::vector<size_t>& recv_counts) {
+    (void)cols; (void)segs; (void)sharded; (void)recv_counts; return nullptr;
+  }
   virtual void all_gather(Col send, Col recv, size_t n) = 0;
   virtual void allreduce_host(uint32_t* buf, size_t n) = 0;                   // sum; exactly one contributor per slot
   virtual std::array<Col, 4> fold_line_range(const std::array<Col, 4>& src, uint32_t log, size_t out_off, size_t n_out, QM31 alpha) = 0;

@@ -70,12 +70,22 @@ struct FetchBatch {
   }
 };
 
+// Owner of every column of a tree: longest-processing-time-first over the transform cost (2^log words): columns in
+// descending size, each to the rank with the least work so far (ties: the lowest rank), so that four 2^24-word columns and
+// sixteen 2^22-word columns on eight ranks come out as 4 x (one large) + 4 x (four small) instead of the 6 : 3 split a plain
+// round-robin over the sorted list gives.  Every rank computes the same assignment.
 inline std::vector<int> assign_owners(const std::vector<uint32_t>& logs, int world) {
   std::vector<size_t> order(logs.size());
   for (size_t i = 0; i < order.size(); i++) order[i] = i;
   std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return logs[a] > logs[b]; });
   std::vector<int> owner(logs.size());
-  for (size_t k = 0; k < order.size(); k++) owner[order[k]] = (int)(k % world);
+  std::vector<uint64_t> load((size_t)world, 0);
+  for (size_t k = 0; k < order.size(); k++) {
+    int best = 0;
+    for (int r = 1; r < world; r++) if (load[(size_t)r] < load[(size_t)best]) best = r;
+    owner[order[k]] = best;
+    load[(size_t)best] += (uint64_t)1 << logs[order[k]];
+  }
   return owner;
 }
 
@@ -177,16 +187,20 @@ inline void exchange_and_commit(Backend& B, const ShardLayout& sl, uint32_t log_
     for (auto& e : es) { rcount[e.owner] += e.seg; if (e.owner == me) for (int d = 0; d < N; d++) scount[d] += e.seg; }
     size_t stot = 0, rtot = 0;
     for (int d = 0; d < N; d++) { stot += scount[d]; rtot += rcount[d]; }
-    Col send = B.alloc(std::max<size_t>(stot, 4)), recv = B.alloc(std::max<size_t>(rtot, 4));
-    {
-      std::vector<Col> pc;
-      std::vector<size_t> ps;
-      std::vector<uint8_t> psh;
-      for (auto& e : es) if (e.owner == me) { pc.push_back(e.full); ps.push_back(e.seg); psh.push_back(e.sharded ? 1 : 0); }
+    std::vector<Col> pc;
+    std::vector<size_t> ps;
+    std::vector<uint8_t> psh;
+    for (auto& e : es) if (e.owner == me) { pc.push_back(e.full); ps.push_back(e.seg); psh.push_back(e.sharded ? 1 : 0); }
+    // CUDA: one kernel writes every destination's block into that rank's receive window over NVLink (Backend::exchange_push);
+    // otherwise (no peer mapping, window still growing, CPU backends) pack a send buffer and hand it to the all-to-all
+    Col recv = B.exchange_push(pc, ps, psh, rcount);
+    if (!recv) {
+      Col send = B.alloc(std::max<size_t>(stot, 4));
+      recv = B.alloc(std::max<size_t>(rtot, 4));
       B.pack_exchange(send, pc, ps, psh);   // one launch on CUDA instead of world x columns copies
+      B.all_to_all(send, scount, recv, rcount);
+      B.free_col(send);
     }
-    B.all_to_all(send, scount, recv, rcount);
-    B.free_col(send);
     for (auto& e : es) if (e.owner == me) B.free_col(e.full);
     std::vector<size_t> roff(N, 0);
     { size_t o = 0; for (int s = 0; s < N; s++) { roff[s] = o; o += rcount[s]; } }
@@ -290,6 +304,7 @@ inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_
   auto row_off = [&](const RowCol& c) { return c.sharded ? (size_t)me * c.rows_len : (size_t)0; };
 
   B.precompute_twiddles(cfg.log_max_rows + cfg.log_blowup + 1);
+  if (N > 1) B.exchange_begin();   // collective: the receive windows of the direct column->row exchange (Backend::exchange_push)
   Channel ch;
   std::vector<STree> trees;
   lap("twiddles");
@@ -663,6 +678,33 @@ inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_
   size_t qi = 0;
   auto cols_of = [](const std::array<RowCol, 4>& r) { return std::array<Col, 4>{r[0].rows, r[1].rows, r[2].rows, r[3].rows}; };
   while (line_log > last_log) {
+    if (dc && !layer[0].sharded && line_log <= B.fri_tail_max_log()) {
+      // The line evaluation is replicated and small: every remaining layer (circle fold, commit, channel, fold_line) in one
+      // backend call on the device transcript (Backend::fri_tail_dc; csrc/fri.cu fri_tail_kernel) instead of ~10 launches each.
+      std::vector<std::array<Col, 4>> tq;
+      size_t qj = qi;
+      for (uint32_t lg = line_log; lg > last_log; lg--) {
+        if (qj < quotients.size() && quotients[qj].first - 1 == lg) { tq.push_back(cols_of(quotients[qj].second)); qj++; }
+        else tq.push_back({nullptr, nullptr, nullptr, nullptr});
+      }
+      bool whole = true;   // the quotient columns of these sizes are replicated too (below ShardLayout::min_log)
+      for (size_t j = qi; j < qj; j++) whole &= !quotients[j].second[0].sharded;
+      Backend::FriTailResult tr;
+      if (whole && B.fri_tail_dc(dc, cols_of(layer), line_log, last_log, tq, tr)) {
+        for (int k = 0; k < 4; k++) B.free_col(layer[k].rows);
+        for (size_t t = 0; t < tr.evals.size(); t++) {
+          InnerLayer Lr{line_cols(line_log, tr.evals[t]), line_log, {}};
+          Lr.tree.layers = tr.trees[t];
+          Lr.tree.whole = true;
+          inner.push_back(std::move(Lr));
+          mixes++;
+          line_log--;
+        }
+        layer = line_cols(line_log, tr.last);
+        qi = qj;
+        break;
+      }
+    }
     while (qi < quotients.size() && quotients[qi].first - 1 == line_log) {
       const size_t off = layer[0].sharded ? (size_t)me * layer[0].rows_len : 0;
       if (dc) B.fold_circle_into_line_range_dc(cols_of(layer), cols_of(quotients[qi].second), quotients[qi].first, off, layer[0].rows_len, dc, 0);

@@ -5,6 +5,7 @@
 // column for interpolation and extension, then re-sharded by row range over NVLink (NCCL all-to-all) for Merkle leaf
 // hashing, quotient evaluation and FRI folding".  NCCL is resolved with dlopen so that the library also loads on a box
 // without it (single-GPU use); the soname is the one torch ships, so both share one copy.
+#include <cstdlib>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -68,6 +69,24 @@ __global__ void __launch_bounds__(256) pack_exchange_kernel(const PackCol* __res
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < c.seg; i += gridDim.x * blockDim.x) dst[i] = src[i];
   }
 }
+// The same blocks written where they are needed: block (d, j) goes straight into rank d's receive window over NVLink
+// (peer-mapped device memory, sc_exchange_begin), at the offset this rank's contribution has in every rank's window.  The
+// pack pass, the send buffer and NCCL's send/recv all-to-all (243 GB/s per direction between two B200s, measured) collapse
+// into one kernel of peer stores; a one-word all-reduce behind it tells every rank that its window is complete.
+__global__ void __launch_bounds__(256) push_exchange_kernel(const PackCol* __restrict__ cols, uint32_t ncols, uint32_t* const* __restrict__ peer,
+                                                            uint64_t win_off) {
+  const PackCol c = cols[blockIdx.y];
+  const uint32_t d = blockIdx.z;
+  const uint32_t* src = c.src + (c.sharded ? (size_t)d * c.seg : 0);
+  uint32_t* dst = peer[d] + win_off + c.off;
+  if (((c.seg | c.off | win_off) & 3u) == 0) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < c.seg / 4; i += gridDim.x * blockDim.x) d4[i] = s4[i];
+  } else {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < c.seg; i += gridDim.x * blockDim.x) dst[i] = src[i];
+  }
+}
 // out[row] = col[storage index of the coset-order predecessor of row]  (offset_bit_reversed_circle_domain_index(.., -1))
 __global__ void shift_prev_kernel(const uint32_t* __restrict__ col, uint32_t* __restrict__ out, uint32_t e) {
   uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
@@ -119,6 +138,15 @@ static NcclApi* nccl() {
 struct sc_comm {
   ncclComm_t comm;
   int rank, world;
+  // receive window of the direct (peer-store) column->row exchange: one cudaMalloc'ed buffer per rank, exported with CUDA IPC
+  // and mapped by every other rank; regions are bump-allocated per proof in the same order on every rank (the sizes are the
+  // same everywhere), so a region has the same offset in every window.
+  uint32_t* win = nullptr;
+  size_t win_cap = 0, win_off = 0, win_need = 0, win_want = 0;   // words
+  std::vector<uint32_t*> peer;      // peer[d] = rank d's window as mapped here (peer[rank] = win)
+  uint32_t** d_peer = nullptr;      // the same table on the device
+  uint32_t* d_flag = nullptr;       // one word for the completion all-reduce
+  bool mapped = false, push_ok = false;
 };
 #define CKN(call)                                                                                                   \
   do {                                                                                                              \
@@ -336,7 +364,11 @@ int32_t sc_comm_init(sc_ctx* ctx, int32_t rank, int32_t world, const uint8_t id[
 int32_t sc_comm_destroy(sc_ctx* ctx, sc_comm* c) {
   if (!c) return SC_OK;
   if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->st); }
-  if (nccl()) nccl()->CommDestroy(c->comm);
+  for (int d = 0; d < (int)c->peer.size(); d++) if (d != c->rank && c->peer[d]) cudaIpcCloseMemHandle(c->peer[d]);
+  if (nccl()) nccl()->CommDestroy(c->comm);   // after every rank's unmapping was issued; the windows are freed below
+  if (c->win) cudaFree(c->win);
+  if (c->d_peer) cudaFree(c->d_peer);
+  if (c->d_flag) cudaFree(c->d_flag);
   delete c;
   return SC_OK;
 }
@@ -383,6 +415,114 @@ int32_t sc_allreduce_host_u32(sc_ctx* ctx, sc_comm* c, uint32_t* buf, uint64_t n
   CK(cudaMemcpyAsync(buf, d, n * 4, cudaMemcpyDeviceToHost, ctx->st));
   CK(cudaStreamSynchronize(ctx->st));
   CK(cudaFreeAsync(d, ctx->st));
+  return SC_OK;
+}
+// ---- direct exchange (peer stores over NVLink), see push_exchange_kernel
+// Once per proof, collective: start bump allocation in the window; when a rank wants a larger window than it has (the previous
+// proof recorded what it would have needed) or nothing is mapped yet, every rank unmaps, reallocates, exports and re-maps.
+// A steady-state call is one one-word all-reduce (which is also the guarantee that no rank still reads the previous proof's
+// regions when the first peer store of this proof arrives: a rank enters it only after its previous proof has drained).
+int32_t sc_exchange_begin(sc_ctx* ctx, sc_comm* c) {
+  ENTER();
+  if (!c) return fail(SC_EINVAL, "exchange_begin: null communicator");
+  static const bool disabled = getenv("SC_NO_PUSH_EXCHANGE") != nullptr;
+  c->win_off = 0;
+  c->win_want = std::max(c->win_want, c->win_need);
+  c->win_need = 0;
+  if (disabled || c->world < 2) { c->push_ok = false; return SC_OK; }
+  uint32_t flag = (!c->mapped || c->win_want > c->win_cap) ? 1u : 0u;
+  { int32_t r = sc_allreduce_host_u32(ctx, c, &flag, 1); if (r) return r; }
+  if (!flag) return SC_OK;
+  // ---- (re)map: nobody may free a window that a peer still has mapped
+  for (int d = 0; d < (int)c->peer.size(); d++) if (d != c->rank && c->peer[d]) cudaIpcCloseMemHandle(c->peer[d]);
+  c->peer.assign((size_t)c->world, nullptr);
+  c->mapped = false; c->push_ok = false;
+  { uint32_t z = 0; int32_t r = sc_allreduce_host_u32(ctx, c, &z, 1); if (r) return r; }   // every rank has unmapped
+  if (c->win_want > c->win_cap || !c->win) {
+    if (c->win) CK(cudaFree(c->win));
+    c->win = nullptr; c->win_cap = 0;
+    const size_t want = std::max<size_t>(c->win_want + c->win_want / 16, (size_t)1 << 20);
+    if (cudaMalloc((void**)&c->win, want * 4) == cudaSuccess) c->win_cap = want;
+    else { cudaGetLastError(); c->win = nullptr; }
+  }
+  if (!c->d_peer) CK(cudaMalloc((void**)&c->d_peer, sizeof(uint32_t*) * (size_t)c->world));
+  if (!c->d_flag) { CK(cudaMalloc((void**)&c->d_flag, 4)); CK(cudaMemsetAsync(c->d_flag, 0, 4, ctx->st)); }
+  // handle (64 bytes) + capacity, all-gathered through device memory
+  constexpr size_t REC = 20;   // words per rank: 16 (handle) + 2 (capacity) + 2 (padding)
+  std::vector<uint32_t> mine(REC, 0), all(REC * (size_t)c->world, 0);
+  uint32_t fails = 0;
+  if (c->win) {
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, c->win) == cudaSuccess) { static_assert(sizeof(h) == 64, "IPC handle size"); memcpy(mine.data(), &h, 64); }
+    else { cudaGetLastError(); fails = 1; }
+    const uint64_t cap = c->win_cap;
+    memcpy(mine.data() + 16, &cap, 8);
+  } else fails = 1;
+  {
+    uint32_t* d;
+    CK(cudaMallocAsync((void**)&d, (REC + REC * (size_t)c->world) * 4, ctx->st));
+    CK(cudaMemcpyAsync(d, mine.data(), REC * 4, cudaMemcpyHostToDevice, ctx->st));
+    CKN(nccl()->AllGather(d, d + REC, REC, ncclUint32, c->comm, ctx->st));
+    CK(cudaMemcpyAsync(all.data(), d + REC, REC * (size_t)c->world * 4, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    CK(cudaFreeAsync(d, ctx->st));
+  }
+  for (int d = 0; d < c->world && !fails; d++) {
+    uint64_t cap;
+    memcpy(&cap, all.data() + REC * (size_t)d + 16, 8);
+    if (cap != c->win_cap) { fails = 1; break; }   // every rank sizes its window by the same rule; anything else: no direct exchange
+    if (d == c->rank) { c->peer[(size_t)d] = c->win; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, all.data() + REC * (size_t)d, 64);
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); fails = 1; break; }
+    c->peer[(size_t)d] = (uint32_t*)p;
+  }
+  c->mapped = true;
+  { int32_t r = sc_allreduce_host_u32(ctx, c, &fails, 1); if (r) return r; }   // all or nothing
+  c->push_ok = fails == 0;
+  if (c->push_ok) CK(cudaMemcpyAsync(c->d_peer, c->peer.data(), sizeof(uint32_t*) * (size_t)c->world, cudaMemcpyHostToDevice, ctx->st));
+  return SC_OK;
+}
+// One column->row exchange by peer stores.  cols / segs / sharded: the columns this rank owns, as in sc_pack_exchange;
+// recv_counts[s]: words rank s contributes to every rank's receive buffer (its block starts at sum(recv_counts[0..s))).
+// *recv_out: the receive buffer (a region of this rank's window; freeing the handle releases nothing), or NULL when the
+// direct path is not available (no window, window too small — it grows at the next sc_exchange_begin): the caller then uses
+// sc_pack_exchange + sc_all_to_all.  Every rank takes the same branch (the sizes are the same on every rank).
+int32_t sc_exchange_push(sc_ctx* ctx, sc_comm* c, sc_col* const* cols, const uint64_t* segs, const uint8_t* sharded, uint32_t n,
+                         const uint64_t* recv_counts, sc_col** recv_out) {
+  ENTER();
+  if (!c || !recv_counts || !recv_out || (n && (!cols || !segs || !sharded))) return fail(SC_EINVAL, "exchange_push: null argument");
+  *recv_out = nullptr;
+  uint64_t rtot = 0, roff_me = 0;
+  for (int s = 0; s < c->world; s++) { if (s < c->rank) roff_me += recv_counts[s]; rtot += recv_counts[s]; }
+  const uint64_t region = (rtot + 63) & ~63ull;
+  c->win_need += region;
+  if (!c->push_ok || c->win_off + region > c->win_cap) return SC_OK;
+  std::vector<PackCol> pc(n);
+  uint64_t off = 0;
+  uint32_t max_seg = 1;
+  for (uint32_t j = 0; j < n; j++) {
+    if (!cols[j] || segs[j] > 0xffffffffull || cols[j]->len < (sharded[j] ? segs[j] * c->world : segs[j])) return fail(SC_EINVAL, "exchange_push: bad column");
+    pc[j] = {cols[j]->d, (uint32_t)segs[j], sharded[j] ? 1u : 0u, roff_me + off};
+    off += segs[j];
+    max_seg = std::max<uint32_t>(max_seg, (uint32_t)segs[j]);
+  }
+  if (off != recv_counts[c->rank]) return fail(SC_EINVAL, "exchange_push: this rank's columns do not add up to its receive count");
+  if (n) {
+    void* d_pc = nullptr;
+    { int32_t r = stage(ctx, pc.data(), pc.size() * sizeof(PackCol), &d_pc); if (r) return r; }
+    const uint32_t bx = std::max(1u, std::min(64u, (max_seg / 4 + 255) / 256));
+    ProfScope ps_(ctx, "push_exchange");
+    push_exchange_kernel<<<dim3(bx, n, (unsigned)c->world), 256, 0, ctx->st>>>((const PackCol*)d_pc, n, c->d_peer, c->win_off);
+    g_launch_count++; CK(cudaGetLastError());
+  }
+  { ProfScope ps_(ctx, "nccl_all_reduce"); CKN(nccl()->AllReduce(c->d_flag, c->d_flag, 1, ncclUint32, ncclSum, c->comm, ctx->st)); }
+  sc_col* r = new sc_col{c->win + c->win_off, rtot};
+  r->owned = false;
+  track(ctx, r);
+  *recv_out = r;
+  c->win_off += region;
   return SC_OK;
 }
 int32_t sc_comm_rank(const sc_comm* c) { return c ? c->rank : 0; }
