@@ -151,6 +151,22 @@ __host__ __device__ constexpr int round_start(int nbits, int i) {
 }
 constexpr int STRIDED_C = 4;  // log2 of the contiguous words per row of a strided tile (64-byte runs); 3 for the 10-layer pass
 
+// Shared-memory index of local element i (padding against bank conflicts).
+//  * low pass: i + i / 32 — the first round's threads own 32 consecutive words each (stride 33: conflict-free), later rounds
+//    read 32 consecutive words per warp;
+//  * strided pass: a warp of the first round (local bits [SC, SC + R0)) touches 2^(5-SC) runs of 2^SC words that lie
+//    2^(SC+R0) words apart; 2^SC words of padding per 2^(SC+R0)-word block puts consecutive runs 2^SC banks apart, so the
+//    runs of a warp tile the 32 banks (ncu on the i + i/32 padding of round 1: 9.0 M conflicts in 34.8 M shared wavefronts on
+//    fft_kernel<1,10,0,0,4>).  The padding is a multiple of four words, so the load / store phases use 128-bit accesses.
+// PAD is additive over the disjoint bit fields the rounds use (a thread's base + a compile-time offset per element).
+template <bool LOW, int K, int SC>
+struct Pad {
+  static constexpr int BLK = LOW ? 5 : SC + round_size(K - SC, 0);   // log2 of the block that is followed by padding
+  static constexpr int PW = LOW ? 0 : SC;                            // log2 of the padding words per block
+  static __host__ __device__ constexpr uint32_t at(uint32_t i) { return i + ((i >> BLK) << PW); }
+  static constexpr uint32_t words = (1u << K) + (((1u << K) >> BLK) << PW);
+};
+
 struct FftArgs {
   const uint32_t* const* src;
   uint32_t* const* dst;
@@ -163,18 +179,19 @@ struct FftArgs {
 };
 
 // One register round over local bits [B, B+R) of a 2^K tile.  gb = global bit of local bit B; T = tile index bits above the tile.
-template <bool INV, int K, int B, int R, bool CIRCLE>
+template <bool INV, int K, int B, int R, bool CIRCLE, bool LOW, int SC>
 __device__ __forceinline__ void fft_round(uint32_t* __restrict__ sm, const FftArgs& a, uint32_t T, uint32_t gb) {
+  typedef Pad<LOW, K, SC> PD;
   constexpr int M = 1 << R;
   constexpr int NG = 1 << (K - R);
   const FK one = a.k;
   for (int q = threadIdx.x; q < NG; q += blockDim.x) {
     const uint32_t low = q & ((1u << B) - 1u), high = (uint32_t)q >> B;
     const uint32_t li0 = low | (high << (B + R));
-    uint32_t* p = sm + li0 + (li0 >> 5);
+    uint32_t* p = sm + PD::at(li0);
     uint32_t v[M];
 #pragma unroll
-    for (int m = 0; m < M; m++) v[m] = p[(m << B) + ((m << B) >> 5)];
+    for (int m = 0; m < M; m++) v[m] = p[PD::at((uint32_t)m << B)];
     const uint32_t H = (T << (K - B - R)) | high;
     // CIRCLE (low pass, B == 0): line layer 1's 2^(R-2) twiddles also define the 2^(R-1) circle twiddles: [x,y] -> [y,-y,-x,x];
     // fetched right before the first layer that needs them (the forward round walks s = R-1 .. 0: live for two layers only)
@@ -234,7 +251,7 @@ __device__ __forceinline__ void fft_round(uint32_t* __restrict__ sm, const FftAr
       }
     }
 #pragma unroll
-    for (int m = 0; m < M; m++) p[(m << B) + ((m << B) >> 5)] = v[m];
+    for (int m = 0; m < M; m++) p[PD::at((uint32_t)m << B)] = v[m];
   }
 }
 
@@ -246,7 +263,7 @@ __device__ __forceinline__ void run_round(uint32_t* sm, const FftArgs& a, uint32
   constexpr int R = round_size(NB, I);
   constexpr int B = C0 + round_start(NB, I);
   const uint32_t gb = LOW ? (uint32_t)B : a.L0 + (uint32_t)(B - SC);
-  fft_round<INV, K, B, R, (LOW && B == 0 && !LINE)>(sm, a, T, gb);
+  fft_round<INV, K, B, R, (LOW && B == 0 && !LINE), LOW, SC>(sm, a, T, gb);
   __syncthreads();
 }
 template <bool INV, int K, bool LOW, bool LINE, int SC, int I, int NR>
@@ -271,7 +288,7 @@ struct Rounds<INV, K, LOW, LINE, SC, NR, NR> {
 // owns the neighbouring tile, which runs at the same time, so the sector is served from L2.
 template <bool INV, int K, bool LOW, bool LINE = false, int SC = STRIDED_C>
 __global__ void __launch_bounds__(K >= 14 ? 1024 : 256, K >= 14 ? 1 : 4) fft_kernel(FftArgs a) {
-  extern __shared__ uint32_t sm[];
+  extern __shared__ __align__(16) uint32_t sm[];
   constexpr int C = LOW ? K : SC;
   const uint32_t L0 = LOW ? (uint32_t)K : a.L0;
   const uint32_t tile = blockIdx.x;
@@ -283,11 +300,13 @@ __global__ void __launch_bounds__(K >= 14 ? 1024 : 256, K >= 14 ? 1 : 4) fft_ker
   const uint32_t smask = (a.src_log >= 32) ? 0xffffffffu : ((1u << a.src_log) - 1u);
   constexpr uint32_t cm = (1u << C) - 1u;
 
+  typedef Pad<LOW, K, SC> PD;
   for (uint32_t li = threadIdx.x * 4; li < (1u << K); li += blockDim.x * 4) {
     uint32_t g = (gbase | (li & cm) | ((li >> C) << L0)) & smask;
     uint4 x = __ldg(reinterpret_cast<const uint4*>(src + g));
-    uint32_t o = li + (li >> 5);
-    sm[o] = x.x; sm[o + 1] = x.y; sm[o + 2] = x.z; sm[o + 3] = x.w;
+    uint32_t o = PD::at(li);
+    if (PD::PW >= 2) *reinterpret_cast<uint4*>(sm + o) = x;   // padding in multiples of four words: the quad stays aligned
+    else { sm[o] = x.x; sm[o + 1] = x.y; sm[o + 2] = x.z; sm[o + 3] = x.w; }
   }
   __syncthreads();
 
@@ -296,8 +315,8 @@ __global__ void __launch_bounds__(K >= 14 ? 1024 : 256, K >= 14 ? 1 : 4) fft_ker
   const uint32_t scale = a.scale, scale2 = a.scale << 1;
   for (uint32_t li = threadIdx.x * 4; li < (1u << K); li += blockDim.x * 4) {
     uint32_t g = gbase | (li & cm) | ((li >> C) << L0);
-    uint32_t o = li + (li >> 5);
-    uint4 x = make_uint4(sm[o], sm[o + 1], sm[o + 2], sm[o + 3]);
+    uint32_t o = PD::at(li);
+    uint4 x = PD::PW >= 2 ? *reinterpret_cast<const uint4*>(sm + o) : make_uint4(sm[o], sm[o + 1], sm[o + 2], sm[o + 3]);
     if (scale != 1u) { x.x = mulred(x.x, scale2); x.y = mulred(x.y, scale2); x.z = mulred(x.z, scale2); x.w = mulred(x.w, scale2); }
     *reinterpret_cast<uint4*>(dst + g) = x;
   }
@@ -346,7 +365,7 @@ static uint32_t threads_for(uint32_t K) {
 
 template <bool INV, int K, bool LOW, bool LINE = false, int SC = STRIDED_C>
 static int launch_one(const FftArgs& a, dim3 grid, cudaStream_t st) {
-  size_t smem = ((size_t)(1u << K) + ((1u << K) >> 5) + 4) * 4;
+  size_t smem = ((size_t)Pad<LOW, K, SC>::words + 4) * 4;
   if (K >= 14) {   // above the 48 KB default: opt in once per instantiation
     static bool configured = false;
     if (!configured) {
