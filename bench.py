@@ -392,7 +392,7 @@ def bench_prove(args, workload="prove", extra_only=False):
     stdin, lmr = w["stdin"], 24
     comm = pkg.Comm.from_torch_distributed(be, dist) if world > 1 else None
     if world > 1:
-        prove = lambda **kw: pkg.prove_brainfuck_sharded(be, comm, code, stdin, lmr)
+        prove = lambda **kw: pkg.prove_brainfuck_sharded(be, comm, code, stdin, lmr, overlap_host=kw.get("overlap_host", True))
     else:
         prove = lambda **kw: pkg.prove_brainfuck(be, code, stdin, lmr, **kw)
     for _ in range(args.warmup):
@@ -406,13 +406,13 @@ def bench_prove(args, workload="prove", extra_only=False):
     reports = []
     with ClockSampler(local) as cs:
         for _ in range(args.steps):
-            reports.append((prove(overlap_host=False) if world == 1 else prove()).report())
+            reports.append(prove(overlap_host=False).report())
         be.profile(True)
         be.profile_report()
         l0 = be.launch_count()
         prof_reports = []
         for _ in range(args.steps):
-            prof_reports.append((prove(overlap_host=False) if world == 1 else prove()).report())
+            prof_reports.append(prove(overlap_host=False).report())
         launches = be.launch_count() - l0
         prof = be.profile_report()
         be.profile(False)

@@ -588,15 +588,17 @@ class Comm:
             self._h = None
 
 
-def prove_brainfuck_sharded(backend: CudaBackend, comm: Optional[Comm], code, stdin: bytes = b"", log_max_rows: int = 24) -> Proof:
+def prove_brainfuck_sharded(backend: CudaBackend, comm: Optional[Comm], code, stdin: bytes = b"", log_max_rows: int = 24,
+                            overlap_host: bool = True) -> Proof:
     """One proof split over the ranks of `comm` (column-sharded FFTs, all-to-all, row-sharded hashing / constraints /
     quotients / FRI — csrc/host/prover_sharded.hpp).  Every rank calls this with the same inputs and gets the same proof.
-    comm=None runs the sharded driver on one GPU."""
+    comm=None runs the sharded driver on one GPU.  overlap_host=False runs the VM and builds the tables before any other device
+    work of the proof (SBF_NO_OVERLAP: bench.py's device-timed value then covers the whole proof)."""
     lib = backend._lib
     h = _vp()
     code_b = code.encode() if isinstance(code, str) else code
     rc = lib.sbf_prove_sharded(backend._ctx, comm._h if comm else None, ctypes.c_char_p(code_b), ctypes.c_char_p(stdin),
-                               ctypes.c_size_t(len(stdin)), ctypes.c_uint32(log_max_rows), ctypes.c_uint32(0), ctypes.byref(h))
+                               ctypes.c_size_t(len(stdin)), ctypes.c_uint32(log_max_rows), ctypes.c_uint32(0 if overlap_host else 1), ctypes.byref(h))
     if rc != 0:
         lib.sbf_last_error.restype = ctypes.c_char_p
         raise ProvingError(lib.sbf_last_error().decode())

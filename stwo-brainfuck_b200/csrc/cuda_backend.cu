@@ -498,8 +498,7 @@ int32_t sbf_prove_sharded(sc_ctx* ctx, sc_comm* comm, const char* code, const ui
   const uint64_t mark = sc_ctx_mark(ctx);
   try {
     if (!ctx || !code || !out) throw std::runtime_error("null argument");
-    // the sharded driver always overlaps the VM with phase 0 and has no preprocessed-tree cache: say so instead of ignoring the flags
-    if (flags & 1u) throw std::runtime_error("SBF_NO_OVERLAP is not supported by the sharded driver");
+    // the sharded driver has no preprocessed-tree cache: say so instead of ignoring the flag
     if (flags & 8u) throw std::runtime_error("SBF_CACHE_PREPROCESSED is not supported by the sharded driver");
     std::vector<uint32_t> program = compile(code);
     Machine vm(program, std::vector<uint8_t>(input, input + input_len));
@@ -515,6 +514,7 @@ int32_t sbf_prove_sharded(sc_ctx* ctx, sc_comm* comm, const char* code, const ui
     ProverConfig cfg;
     cfg.log_max_rows = log_max_rows;
     cfg.shard_min_log = getenv("SBF_SHARD_MIN_LOG") ? (uint32_t)atoi(getenv("SBF_SHARD_MIN_LOG")) : 16;
+    cfg.overlap_host = !(flags & 1u);  // SBF_NO_OVERLAP: VM run and tables before any device work (bench.py's device-path timing)
     B.cache_twiddles = !(flags & 2u);
     auto t1 = std::chrono::steady_clock::now();
     ProveResult r = prove_brainfuck_sharded(B, program, run_vm, cfg, [&] { if (sc_ctx_profiling(ctx)) sc_ctx_sync(ctx); });
