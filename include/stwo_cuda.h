@@ -197,6 +197,12 @@ int32_t sc_microbench_int(sc_ctx* ctx, int32_t kind, uint32_t iters, double out[
 int32_t sc_gen_is_first(sc_ctx* ctx, uint32_t log_size, sc_col** out);
 /* coefficients of that column's polynomial in closed form (= sc_gen_is_first + sc_interpolate, without the transform) */
 int32_t sc_is_first_coeffs(sc_ctx* ctx, uint32_t log_size, const sc_twiddles* tw, sc_col** out);
+/* The low-degree extension of that column — rows [row_off, row_off + n_rows) (multiples of 4) of its evaluation on
+ * CanonicCoset(log_size + log_blowup).circle_domain(), bit-reversed — written in closed form: the polynomial is the rank-one
+ * product 2^-L (1 + t_0 y)(1 + t_1 x) prod_l (1 + t_l pi^(l-1)(x)), so the extension of the preprocessed trace
+ * (brainfuck_air/mod.rs:493-500: gen_is_first -> interpolate -> commit's evaluate) needs no transform and, row range by row
+ * range, no exchange between GPUs.  Same values as sc_evaluate(sc_is_first_coeffs(..)). */
+int32_t sc_is_first_lde(sc_ctx* ctx, uint32_t log_size, uint32_t log_blowup, const sc_twiddles* tw, uint64_t row_off, uint64_t n_rows, sc_col** out);
 /* simd/prefix_sum.rs inclusive_prefix_sum: in-place inclusive prefix sum in trace-coset order of a bit-reversed
  * column (LogupTraceGenerator::finalize_last, e.g. crates/brainfuck_prover/src/components/processor/table.rs:530). */
 int32_t sc_prefix_sum_bitrev(sc_ctx* ctx, sc_col* col);

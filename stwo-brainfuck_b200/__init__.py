@@ -64,7 +64,7 @@ ABI_SYMBOLS = [
     "sc_batch_inverse_qm31", "sc_precompute_twiddles", "sc_twiddles_free", "sc_twiddles_cached", "sc_twiddles_to_host", "sc_interpolate",
     "sc_evaluate", "sc_eval_at_point", "sc_merkle_commit_layer", "sc_merkle_commit", "sc_fold_line",
     "sc_fold_circle_into_line", "sc_accumulate_quotients", "sc_accumulate", "sc_secure_powers", "sc_grind",
-    "sc_gen_is_first", "sc_is_first_coeffs", "sc_prefix_sum_bitrev", "sc_logup_generate", "sc_eval_constraints", "sc_gather", "sc_ctx_profile", "sc_ctx_profiling", "sc_ctx_profile_report", "sc_ctx_profile_timeline", "sc_ctx_mark", "sc_ctx_release_since", "sc_ctx_live_columns", "sc_event_record", "sc_event_elapsed", "sc_event_free", "sc_interpolate_repeated", "sc_evaluate_repeated", "sc_eval_at_point_repeated",
+    "sc_gen_is_first", "sc_is_first_coeffs", "sc_is_first_lde", "sc_prefix_sum_bitrev", "sc_logup_generate", "sc_eval_constraints", "sc_gather", "sc_ctx_profile", "sc_ctx_profiling", "sc_ctx_profile_report", "sc_ctx_profile_timeline", "sc_ctx_mark", "sc_ctx_release_since", "sc_ctx_live_columns", "sc_event_record", "sc_event_elapsed", "sc_event_free", "sc_interpolate_repeated", "sc_evaluate_repeated", "sc_eval_at_point_repeated",
     "sc_merkle_commit_layer_repeated", "sc_merkle_commit_repeated", "sc_ctx_attach", "sc_ctx_attached",
     "sc_microbench_int", "sc_fri_commit", "sc_trace_stats_host", "sc_trace_upload", "sc_trace_build_tables", "sc_trace_status", "sc_trace_free",
 ]
@@ -401,6 +401,14 @@ class CudaBackend:
     def gen_is_first(self, log_size: int) -> Column:
         h = _vp()
         self._ck(self._lib.sc_gen_is_first(self._ctx, ctypes.c_uint32(log_size), ctypes.byref(h)))
+        return Column(self, h)
+
+    def is_first_lde(self, log_size: int, log_blowup: int, twiddles: Twiddles, row_off: int = 0, n_rows: Optional[int] = None) -> Column:
+        """Rows [row_off, row_off + n_rows) of gen_is_first(log_size) extended by 2^log_blowup, in closed form (no transform)."""
+        h = _vp()
+        n = (1 << (log_size + log_blowup)) - row_off if n_rows is None else n_rows
+        self._ck(self._lib.sc_is_first_lde(self._ctx, ctypes.c_uint32(log_size), ctypes.c_uint32(log_blowup), twiddles._h,
+                                           ctypes.c_uint64(row_off), ctypes.c_uint64(n), ctypes.byref(h)))
         return Column(self, h)
 
     def is_first_coeffs(self, log_size: int, twiddles: Twiddles) -> Column:

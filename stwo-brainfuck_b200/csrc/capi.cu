@@ -900,6 +900,23 @@ int32_t sc_is_first_coeffs(sc_ctx* ctx, uint32_t log_size, const sc_twiddles* tw
   { ProfScope ps_(ctx, "gen_is_first"); CKL(launch_is_first_coeffs((*out)->d, log_size, tw->itw + ((size_t)1 << tw->root_log), ctx->st)); }
   return SC_OK;
 }
+// Rows [row_off, row_off + n_rows) of the IsFirst column of log_size extended to log_size + log_blowup, written in closed form
+// (quotients.cu is_first_lde_kernel): what sc_evaluate gives for sc_is_first_coeffs, without the transform.
+int32_t sc_is_first_lde(sc_ctx* ctx, uint32_t log_size, uint32_t log_blowup, const sc_twiddles* tw, uint64_t row_off, uint64_t n_rows, sc_col** out) {
+  ENTER();
+  const uint32_t dom = log_size + log_blowup;
+  if (!out || !tw || log_size < 3 || dom > 30 || (row_off & 3) || (n_rows & 3) || !n_rows || row_off + n_rows > (1ull << dom))
+    return fail(SC_EINVAL, "is_first_lde: bad argument");
+  if (log_size > tw->root_log + 1) return fail(SC_EINVAL, "is_first_lde: twiddle tree too small for this domain");
+  int32_t r = new_col(ctx, n_rows, out);
+  if (r) return r;
+  uint32_t* scratch = nullptr;
+  const size_t sw = quotients_scratch_words(dom, row_off, n_rows);
+  if (sw) CK(cudaMallocAsync((void**)&scratch, sw * 4, ctx->st));
+  { ProfScope ps_(ctx, "gen_is_first"); CKL(launch_is_first_lde((*out)->d, log_size, dom, row_off, n_rows, tw->itw + ((size_t)1 << tw->root_log), ctx->st, scratch)); }
+  if (scratch) CK(cudaFreeAsync(scratch, ctx->st));
+  return SC_OK;
+}
 static inline size_t prefix_scratch_words(uint64_t len) { return ((len + 2 * ((len >> 11) + 2) + 8) + 3) & ~(size_t)3; }
 int32_t sc_prefix_sum_bitrev(sc_ctx* ctx, sc_col* col) {
   ENTER();

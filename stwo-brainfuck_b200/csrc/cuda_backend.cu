@@ -268,6 +268,9 @@ struct CudaBackendImpl : Backend {
   uint64_t grind(const Hash& digest, uint32_t pow_bits) override { uint64_t n; ck(sc_grind(ctx, digest.data(), pow_bits, &n)); return n; }
   Col gen_is_first(uint32_t log_size) override { sc_col* c; ck(sc_gen_is_first(ctx, log_size, &c)); return c; }
   Col is_first_poly(uint32_t log_size) override { sc_col* c; ck(sc_is_first_coeffs(ctx, log_size, tw, &c)); return c; }
+  Col is_first_lde(uint32_t log_size, uint32_t log_blowup, size_t row_off, size_t n_rows) override {
+    sc_col* c; ck(sc_is_first_lde(ctx, log_size, log_blowup, tw, row_off, n_rows, &c)); return c;
+  }
   std::vector<Col> logup_generate(int comp, const std::vector<Col>& main, const InteractionElements& el, QM31& claimed) override {
     std::vector<Col> out(4 * N_LOGUP_COLS[comp]);
     ck(sc_logup_generate(ctx, comp, (sc_col* const*)main.data(), (uint32_t)main.size(), LOG_N_LANES, (const uint32_t*)&el,

@@ -156,6 +156,18 @@ struct Backend {
   virtual Col gen_is_first(uint32_t log_size) = 0;
   // the interpolated IsFirst column (backends may have a closed form)
   virtual Col is_first_poly(uint32_t log_size) { Col c = gen_is_first(log_size); interpolate({c}); return c; }
+  // rows [row_off, row_off + n_rows) of the evaluation of that polynomial on the domain of log_size + log_blowup.  CUDA writes
+  // them in closed form (csrc/quotients.cu is_first_lde_kernel); the default transforms the polynomial and slices.
+  virtual Col is_first_lde(uint32_t log_size, uint32_t log_blowup, size_t row_off, size_t n_rows) {
+    Col p = is_first_poly(log_size);
+    std::vector<Col> e = evaluate({p}, log_blowup);
+    free_col(p);
+    if (row_off == 0 && n_rows == ((size_t)1 << (log_size + log_blowup))) return e[0];
+    Col out = alloc(n_rows);
+    copy(out, 0, e[0], row_off, n_rows);
+    free_col(e[0]);
+    return out;
+  }
   virtual std::vector<Col> logup_generate(int comp, const std::vector<Col>& main, const InteractionElements& el, QM31& claimed_sum) = 0;
   // same without the read-back: the claimed sum is element 1 of each of the last four returned columns (fetch them with one gather)
   virtual std::vector<Col> logup_generate_deferred(int comp, const std::vector<Col>& main, const InteractionElements& el) {

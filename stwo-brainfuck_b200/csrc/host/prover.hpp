@@ -279,8 +279,12 @@ inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code
       pp_cache->hits++;
     } else {
       if (pp_cache && pp_cache->valid) pp_cache->release(B);  // built for another LOG_MAX_ROWS / blowup
-      for (uint32_t lg = cfg.log_max_rows; lg >= LOG_N_LANES; lg--) { t.polys.push_back(B.is_first_poly(lg)); t.logs.push_back(lg); }
-      t.evals = B.evaluate(t.polys, cfg.log_blowup);
+      // the polynomials (closed-form coefficients) are kept for the OODS samples; the extension is written directly
+      // (Backend::is_first_lde: the polynomial is a rank-one product, no transform on CUDA)
+      for (uint32_t lg = cfg.log_max_rows; lg >= LOG_N_LANES; lg--) {
+        t.polys.push_back(B.is_first_poly(lg)); t.logs.push_back(lg);
+        t.evals.push_back(B.is_first_lde(lg, cfg.log_blowup, 0, (size_t)1 << (lg + cfg.log_blowup)));
+      }
       t.layers = B.merkle_commit(t.evals, nullptr);
     }
     if (cfg.overlap_host) make_tables();  // the VM runs on this thread while the device is busy with the phase queued above

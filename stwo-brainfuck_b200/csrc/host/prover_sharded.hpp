@@ -350,11 +350,21 @@ inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_
     for (uint32_t lg = cfg.log_max_rows; lg >= LOG_N_LANES; lg--) t.logs.push_back(lg);
     t.owner = assign_owners(t.logs, N);
     for (size_t c = 0; c < t.logs.size(); c++) t.polys.push_back(t.owner[c] == me ? B.is_first_poly(t.logs[c]) : nullptr);
-    std::vector<Col> lde = lde_owned(t);
+    // The extension of an IsFirst column is a row-local closed form (Backend::is_first_lde): every rank writes its own row
+    // range of every column, so this tree needs neither transforms nor a column->row exchange; the polynomials stay with
+    // their owners for the OODS samples.
+    for (size_t c = 0; c < t.logs.size(); c++) {
+      const uint32_t L = t.logs[c] + cfg.log_blowup;
+      const bool sh = sl.circle_sharded(L);
+      const size_t seg = sh ? ((size_t)1 << (L - sl.w)) : ((size_t)1 << L);
+      Col r = B.is_first_lde(t.logs[c], cfg.log_blowup, sh ? (size_t)me * seg : 0, seg);
+      t.rows.push_back({r, L, sh, seg});
+      t.bufs.push_back(r);
+    }
     // With every kernel of this phase queued, wait for the host thread and queue the uploads of this rank's tables: they
     // run on the copy stream beside the tail of the phase instead of in front of the main-trace exchange.
     void *ev_queued = nullptr, *ev_host = nullptr;
-    exchange_and_commit(B, sl, cfg.log_blowup, t, lde, {}, nullptr, [&] {
+    t.merkle = merkle_sharded(B, sl, t.rows, 0, [&] {
       if (!cfg.overlap_host) return;
       ev_queued = B.mark();   // end of this phase's kernels
       host.t.join();

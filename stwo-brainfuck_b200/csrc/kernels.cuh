@@ -118,5 +118,7 @@ int launch_accumulate_quotients(uint32_t log, uint64_t row_off, uint64_t nrows, 
                                 const QuotBatch* d_batches, uint32_t nb, const QuotEntry* d_entries, uint32_t* const out[4],
                                 cudaStream_t st, uint32_t* d_scratch = nullptr);
 size_t quotients_scratch_words(uint32_t log, uint64_t row_off, uint64_t nrows);
+int launch_is_first_lde(uint32_t* out, uint32_t L, uint32_t dom_log, uint64_t row_off, uint64_t nrows, const uint32_t* itw_plain_end,
+                        cudaStream_t st, uint32_t* d_scratch);
 
 }  // namespace sb

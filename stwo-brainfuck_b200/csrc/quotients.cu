@@ -209,6 +209,80 @@ __global__ void __launch_bounds__(128, 8) quotients_kernel2(const uint32_t* cons
   }
 }
 
+size_t quotients_scratch_words(uint32_t log, uint64_t row_off, uint64_t nrows);
+// ---------------------------------------------------------------- IsFirst on the extended domain, in closed form
+// The inverse transform of e_0 (1 at row 0) only ever meets twiddle index 0, so coefficient i of the IsFirst polynomial of log
+// size L is 2^-L * prod_{l in bits(i)} t_l (is_first_coeffs_kernel, ops.cu) — a rank-one tensor — and the polynomial is
+//   f(p) = 2^-L * (1 + t_0 y)(1 + t_1 x) * prod_{l >= 2} (1 + t_l pi^(l-1)(x)),   pi(x) = 2x^2 - 1.
+// Its low-degree extension is therefore a row-local function: no transform, no HBM pass beside the store, and on several GPUs no
+// column->row exchange for the preprocessed tree — every rank writes its own row range.  The four rows of a quad
+// (x,y) (x,-y) (-x,-y) (-x,y) share the factors l >= 2: about 3 L multiplications per quad.  Points as in quotients_kernel2.
+__global__ void __launch_bounds__(128) is_first_lde_kernel(uint32_t* __restrict__ out, uint32_t L, uint32_t dom_log, const uint32_t* __restrict__ itw_end,
+                                                           uint32_t ninv, uint32_t k_off, uint32_t nq, const Pt* __restrict__ Q,
+                                                           const Pt* __restrict__ Rt, uint32_t kb0) {
+  __shared__ uint32_t t[32];
+  if (threadIdx.x < L) {
+    const uint32_t l = threadIdx.x;
+    const uint32_t* l1 = itw_end - ((size_t)1 << (L - 1));
+    t[l] = l == 0 ? l1[1] : (l == 1 ? l1[0] : *(itw_end - ((size_t)1 << (L - l))));
+  }
+  __syncthreads();
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < nq; k += gridDim.x * blockDim.x) {
+    const uint32_t kg = k + k_off;
+    Pt bp;
+    if (Q) bp = p_add(Q[kg & ((1u << QV2_TLOG) - 1u)], Rt[(kg >> QV2_TLOG) - kb0]);
+    else {
+      const uint32_t j0 = (dom_log > 2) ? (__brev(kg) >> (34 - dom_log)) : 0;
+      bp = q_point_at_index(((1u << (30 - dom_log)) + (uint32_t)(((uint64_t)j0 << (32 - dom_log)) & 0x7fffffffu)) & 0x7fffffffu);
+    }
+    uint32_t c = ninv, z = bp.x;
+    for (uint32_t l = 2; l < L; l++) {
+      z = m_sub(m_mul(m_add(z, z), z), 1u);          // pi^(l-1)(x)
+      c = m_mul(c, m_add(1u, m_mul(t[l], z)));
+    }
+    const uint32_t ux = m_mul(t[1], bp.x), uy = m_mul(t[0], bp.y);
+    const uint32_t ap = m_mul(c, m_add(1u, ux)), am = m_mul(c, m_sub(1u, ux));   // x, -x
+    const uint32_t bpv = m_add(1u, uy), bm = m_sub(1u, uy);                      // y, -y
+    reinterpret_cast<uint4*>(out)[k] = make_uint4(m_mul(ap, bpv), m_mul(ap, bm), m_mul(am, bm), m_mul(am, bpv));
+  }
+}
+// rows [row_off, row_off + nrows) of IsFirst(log L) on CanonicCoset(dom_log).circle_domain(), bit-reversed; d_scratch as in
+// launch_accumulate_quotients (quotients_scratch_words(dom_log, row_off, nrows) words, may be NULL for small domains)
+int launch_is_first_lde(uint32_t* out, uint32_t L, uint32_t dom_log, uint64_t row_off, uint64_t nrows, const uint32_t* itw_plain_end,
+                        cudaStream_t st, uint32_t* d_scratch) {
+  if (L < 3 || L > 31 || dom_log < L || dom_log > 30 || (row_off & 3) || (nrows & 3) || row_off + nrows > ((uint64_t)1 << dom_log)) return -1;
+  {
+    static std::mutex mu;
+    static bool init[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev >= 0 && dev < 64 && !init[dev]) {
+      Pt g[31];
+      g[0] = {GEN_X, GEN_Y};
+      for (int k = 1; k < 31; k++) g[k] = p_dbl(g[k - 1]);
+      cudaError_t e = cudaMemcpyToSymbol(c_qgen_pow, g, sizeof(g));
+      if (e != cudaSuccess) return (int)e;
+      init[dev] = true;
+    }
+  }
+  const uint32_t nq = (uint32_t)(nrows >> 2), k0 = (uint32_t)(row_off >> 2);
+  if (!nq) return 0;
+  uint32_t blocks = (nq + 127) / 128;
+  if (blocks > 148u * 16u) blocks = 148u * 16u;
+  const uint32_t ninv = m_inv(m_pow(2, L));
+  if (d_scratch && quotients_scratch_words(dom_log, row_off, nrows)) {
+    const uint32_t kb0 = k0 >> QV2_TLOG, nkb = ((k0 + nq + 127) >> QV2_TLOG) - kb0;
+    Pt* Q = reinterpret_cast<Pt*>(d_scratch);
+    Pt* Rt = Q + 128;
+    quot_points_kernel<<<(128 + nkb + 127) / 128, 128, 0, st>>>(dom_log, kb0, nkb, Q, Rt); g_launch_count++;
+    is_first_lde_kernel<<<blocks, 128, 0, st>>>(out, L, dom_log, itw_plain_end, ninv, k0, nq, Q, Rt, kb0); g_launch_count++;
+  } else {
+    is_first_lde_kernel<<<blocks, 128, 0, st>>>(out, L, dom_log, itw_plain_end, ninv, k0, nq, nullptr, nullptr, 0); g_launch_count++;
+  }
+  return (int)cudaGetLastError();
+}
+
 // words of device scratch launch_accumulate_quotients needs for its point tables (0: the small-domain kernel is used)
 size_t quotients_scratch_words(uint32_t log, uint64_t row_off, uint64_t nrows) {
   if (log < 2 + QV2_TLOG + 1 || nrows == 0) return 0;

@@ -292,3 +292,27 @@ def test_error_paths_return_status_not_crash(be, tw, pkg):
     c = be.column(rnd(8, 1 << 8))
     be.interpolate_columns([c], tw)
     assert len(c.to_cpu()) == 256
+
+
+@pytest.mark.parametrize("log", [3, 4, 5, 7, 8, 9, 12, 13, 16, 19])
+def test_is_first_lde_closed_form(be, orc, tw, log):
+    """sc_is_first_lde writes the 2x extension of gen_is_first without a transform (the polynomial is a rank-one product):
+    same values as evaluate(interpolate(e_0)) on the device and through the oracle's plain FFT, whole columns and row ranges
+    (the ranges a rank of the sharded prover asks for)."""
+    e0 = np.eye(1, 1 << log, 0, dtype=np.uint32)[0]
+    ref = orc.evaluate(orc.interpolate(e0, ROOT_LOG), 1, ROOT_LOG)
+    poly = be.is_first_coeffs(log, tw)
+    dev = be.evaluate_polynomials([poly], 1, tw)[0].to_cpu()
+    assert (dev == ref).all()
+    got = be.is_first_lde(log, 1, tw).to_cpu()
+    assert (got == ref).all()
+    n = 2 << log
+    for parts in (2, 4, 8):
+        seg = n // parts
+        if seg < 4:
+            continue
+        for r in (0, parts - 1, parts // 2):
+            part = be.is_first_lde(log, 1, tw, r * seg, seg).to_cpu()
+            assert (part == ref[r * seg:(r + 1) * seg]).all()
+    same = be.is_first_lde(log, 0, tw).to_cpu()   # no blow-up: the indicator itself
+    assert (same == e0).all()
