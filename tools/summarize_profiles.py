@@ -95,19 +95,21 @@ KEEP = ["gpu__time_duration.sum", "smsp__inst_executed.sum", "sm__inst_executed_
 
 
 def full_reports():
+    """r2_ncu_full_<name>.raw.csv (the raw page of a --set full capture, written on the GPU box by tools/profile_r2.sh) ->
+    profiles/r2_ncu_full_<name>.csv with the judged metrics of every captured launch."""
     for rep in sorted(os.listdir(G)):
-        if not (rep.startswith("r2_ncu_full_") and rep.endswith(".ncu-rep")):
+        if not (rep.startswith("r2_ncu_full_") and rep.endswith(".raw.csv")):
             continue
-        raw = subprocess.run(["ncu", "-i", os.path.join(G, rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-        rows = list(csv.reader(raw.splitlines()))
+        rows = list(csv.reader(open(os.path.join(G, rep))))
         if len(rows) < 3:
             continue
         hdr = rows[0]
         idx = {n: i for i, n in enumerate(hdr)}
         cols = [c for c in KEEP if c in idx]
-        out = os.path.join(PR, rep.replace(".ncu-rep", ".csv"))
+        out = os.path.join(PR, rep.replace(".raw.csv", ".csv"))
         with open(out, "w") as f:
             f.write("# ncu --set full --clock-control none; one row per captured launch\n")
+            f.write("# units: " + ", ".join("%s [%s]" % (c, rows[1][idx[c]]) for c in cols if rows[1][idx[c]]) + "\n")
             f.write(",".join(["kernel", "grid", "block"] + cols) + "\n")
             for r in rows[2:]:
                 if len(r) != len(hdr):
