@@ -72,9 +72,10 @@ def proof_fft_bytes(shape, log_max_rows):
     """Bytes the transforms of one proof MOVE at their minimum (read once + write once): interpolate 8N and evaluate 12N (N
     coefficients in, 2N values out) per polynomial of N = 2^log words.  The 128 main-trace columns are lane-repeated: they are
     transformed on their N/16 distinct values (8N/16 in and out) and only the LDE is written at full length (N/16 in, 2N out).
-    The composition polynomials are interpolated once (accumulator finalize) and evaluated once."""
+    The composition polynomials are interpolated once (accumulator finalize) and evaluated once; the IsFirst columns of the
+    preprocessed tree never pass through a transform (csrc/quotients.cu is_first_lde_kernel)."""
     pre, main, inter, comp = proof_columns(shape, log_max_rows)
-    full = sum((8 + 12) * (1 << lg) for lg in inter + comp) + sum(12 * (1 << lg) for lg in pre)   # IsFirst polynomials are closed-form
+    full = sum((8 + 12) * (1 << lg) for lg in inter + comp)   # the IsFirst columns are written in closed form: no transform (pre unused)
     rep = sum(8 * (1 << (lg - 4)) + 4 * (1 << (lg - 4)) + 8 * (1 << lg) for lg in main)
     return full + rep
 
@@ -82,9 +83,9 @@ def proof_fft_bytes(shape, log_max_rows):
 def proof_fft_butterflies(shape, log_max_rows):
     """Butterflies the transforms of one proof execute: interpolate of 2^lg values = lg layers of 2^(lg-1); the 2x evaluation =
     lg layers of 2^lg (the blow-up layer is a copy and is not computed).  Main-trace columns at their compact size lg - 4;
-    the IsFirst polynomials are written in closed form (evaluation only)."""
+    the IsFirst columns of the preprocessed tree are extended in closed form (no transform at all)."""
     pre, main, inter, comp = proof_columns(shape, log_max_rows)
-    n = sum(lg * (1 << (lg - 1)) + lg * (1 << lg) for lg in inter + comp) + sum(lg * (1 << lg) for lg in pre)
+    n = sum(lg * (1 << (lg - 1)) + lg * (1 << lg) for lg in inter + comp)
     n += sum((lg - 4) * (1 << (lg - 5)) + (lg - 4) * (1 << (lg - 4)) for lg in main if lg > 4)
     return n
 
