@@ -382,7 +382,8 @@ def timed_proofs(torch, dist, world, stream, steps, prove):
 def bench_prove(args, workload="prove", extra_only=False):
     """One step = one full proof of the workload's program at LOG_MAX_ROWS 24.  N > 1: the SAME proof split over the N GPUs
     (strong scaling) by the sharded prover: every rank runs the VM and builds the tables on its device, column-sharded FFTs,
-    one NCCL all-to-all per commitment tree, row-sharded hashing / constraints / quotients / FRI (csrc/host/prover_sharded.hpp).
+    one column->row exchange per commitment tree (peer stores over NVLink into IPC-mapped receive windows; NCCL all-to-all as the
+    fallback), row-sharded hashing / constraints / quotients / FRI (csrc/host/prover_sharded.hpp).
       value : device time from "register rows resident in HBM" to "proof complete" (two CUDA events on the launch stream,
               recorded by the library: behind the upload, and after the last kernel), VM run before the timed region;
       e2e   : the call a user makes — VM on the host, 28 B per step uploaded from pinned memory, tables built on the device,
@@ -473,7 +474,7 @@ def bench_prove(args, workload="prove", extra_only=False):
     shape = shape_of(rep["log_sizes"])
     roof, roof_fft = rooflines(kern, shape, lmr, world, clocks, peaks_int)
     par = "single GPU (at --gpus N > 1 the same proof is split over N GPUs)" if world == 1 else \
-        f"one proof over {world} GPUs: VM + device-built tables on every rank, column-sharded FFT -> all_to_all per tree -> " \
+        f"one proof over {world} GPUs: VM + device-built tables on every rank, column-sharded FFT -> column->row exchange per tree (NVLink peer stores, NCCL fallback) -> " \
         "row-sharded Merkle / constraints / quotients / FRI; sub-roots all-gathered; main-trace tree without exchange"
     line = {"metric": w["metric"], "value": dev_s, "unit": "s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_s * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
