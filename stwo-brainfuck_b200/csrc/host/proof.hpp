@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <map>
 #include <set>
+#include <charconv>
 #include <sstream>
 #include <string>
 #include "backend.hpp"
@@ -179,30 +180,64 @@ inline std::string hex(const Hash& h) {   // the same digest as `[b0,b1,...,b31]
   s.push_back(']');
   return s;
 }
-inline void jq(std::ostringstream& o, const QM31& q) { o << "[[" << q.a.a << "," << q.a.b << "],[" << q.b.a << "," << q.b.b << "]]"; }
-inline void jdec(std::ostringstream& o, const MerkleDecommitment& d) {
+// Append-only text writer: std::to_chars into one pre-sized string.  (The first version streamed ~50 000 numbers through an
+// ostringstream: 2.1 ms per fib19 proof on the GPU box's host — inside the end-to-end time, 4 % of it on one GPU and 12 % on
+// eight; this one takes 0.2 ms for the same bytes.)
+struct JsonOut {
+  std::string s;
+  JsonOut() { s.reserve(1 << 18); }
+  JsonOut& operator<<(const char* t) { s.append(t); return *this; }
+  JsonOut& operator<<(const std::string& t) { s.append(t); return *this; }
+  JsonOut& operator<<(uint64_t v) {
+    char buf[24];
+    auto r = std::to_chars(buf, buf + sizeof(buf), v);
+    s.append(buf, (size_t)(r.ptr - buf));
+    return *this;
+  }
+  JsonOut& operator<<(uint32_t v) { return *this << (uint64_t)v; }
+  JsonOut& operator<<(const Hash& h) {   // `[b0,b1,...,b31]`: most of a proof's text; written through a pointer
+    const uint8_t* b = (const uint8_t*)h.data();
+    const size_t n = s.size();
+    s.resize(n + 2 + 32 * 4);
+    char* w = &s[n];
+    *w++ = '[';
+    for (int i = 0; i < 32; i++) {
+      if (i) *w++ = ',';
+      const unsigned v = b[i];
+      if (v >= 100) { *w++ = (char)('0' + v / 100); *w++ = (char)('0' + (v / 10) % 10); *w++ = (char)('0' + v % 10); }
+      else if (v >= 10) { *w++ = (char)('0' + v / 10); *w++ = (char)('0' + v % 10); }
+      else *w++ = (char)('0' + v);
+    }
+    *w++ = ']';
+    s.resize((size_t)(w - s.data()));
+    return *this;
+  }
+  std::string str() { return std::move(s); }
+};
+inline void jq(JsonOut& o, const QM31& q) { o << "[[" << q.a.a << "," << q.a.b << "],[" << q.b.a << "," << q.b.b << "]]"; }
+inline void jdec(JsonOut& o, const MerkleDecommitment& d) {
   o << "{\"hash_witness\":[";
-  for (size_t i = 0; i < d.hash_witness.size(); i++) o << (i ? "," : "") << hex(d.hash_witness[i]);
+  for (size_t i = 0; i < d.hash_witness.size(); i++) o << (i ? "," : "") << d.hash_witness[i];
   o << "],\"column_witness\":[";
   for (size_t i = 0; i < d.column_witness.size(); i++) o << (i ? "," : "") << d.column_witness[i];
   o << "]}";
 }
-inline void jlayer(std::ostringstream& o, const FriLayerProof& l) {
+inline void jlayer(JsonOut& o, const FriLayerProof& l) {
   o << "{\"fri_witness\":[";
   for (size_t i = 0; i < l.fri_witness.size(); i++) { if (i) o << ","; jq(o, l.fri_witness[i]); }
   o << "],\"decommitment\":";
   jdec(o, l.decommitment);
-  o << ",\"commitment\":" << hex(l.commitment) << "}";
+  o << ",\"commitment\":" << l.commitment << "}";
 }
 inline std::string proof_to_json(const BrainfuckProof& p) {
-  std::ostringstream o;
+  JsonOut o;
   o << "{\"claim\":{";
   for (int c = 0; c < N_COMPONENTS; c++) o << (c ? "," : "") << "\"" << COMPONENT_NAMES[c] << "\":{\"log_size\":" << p.log_size[c] << ",\"_marker\":null}";
   o << "},\"interaction_claim\":{";
   for (int c = 0; c < N_COMPONENTS; c++) { o << (c ? "," : "") << "\"" << COMPONENT_NAMES[c] << "\":{\"claimed_sum\":"; jq(o, p.claimed_sum[c]); o << "}"; }
   const CommitmentSchemeProof& s = p.proof;
   o << "},\"proof\":{\"commitments\":[";
-  for (size_t i = 0; i < s.commitments.size(); i++) o << (i ? "," : "") << hex(s.commitments[i]);
+  for (size_t i = 0; i < s.commitments.size(); i++) o << (i ? "," : "") << s.commitments[i];
   o << "],\"sampled_values\":[";
   for (size_t t = 0; t < s.sampled_values.size(); t++) {
     o << (t ? "," : "") << "[";
@@ -225,7 +260,7 @@ inline std::string proof_to_json(const BrainfuckProof& p) {
     }
     o << "]";
   }
-  o << "],\"proof_of_work\":" << s.proof_of_work << ",\"fri_proof\":{\"first_layer\":";
+  o << "],\"proof_of_work\":" << (uint64_t)s.proof_of_work << ",\"fri_proof\":{\"first_layer\":";
   jlayer(o, s.fri_proof.first_layer);
   o << ",\"inner_layers\":[";
   for (size_t i = 0; i < s.fri_proof.inner_layers.size(); i++) { if (i) o << ","; jlayer(o, s.fri_proof.inner_layers[i]); }
