@@ -438,6 +438,17 @@ inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code
     for (auto* f : kv.second) { cols.push_back(f->eval); samples.push_back(&f->samples); }
     quotients.push_back({kv.first, B.accumulate_quotients(kv.first, cols, quot_coeff, batch_samples(samples))});
   }
+  // ---- sanity check (ProvingError::ConstraintsNotSatisfied).  Host arithmetic on the sampled values: done here, while the
+  // device works through the quotient kernels queued above, instead of at the end of the proof where it is pure latency
+  {
+    const auto& cs = P.sampled_values[3];
+    QM31 comp = cs[0][0];
+    comp = q_add(comp, q_mul(cs[1][0], q_make(0, 1, 0, 0)));
+    comp = q_add(comp, q_mul(cs[2][0], q_make(0, 0, 1, 0)));
+    comp = q_add(comp, q_mul(cs[3][0], q_make(0, 0, 0, 1)));
+    QM31 want = eval_composition_at_point(cfg, proof.log_size, proof.claimed_sum, el, oods, P.sampled_values, random_coeff);
+    if (!q_eq(comp, want)) throw std::runtime_error("ConstraintsNotSatisfied");
+  }
   lap("quotients");
 
   // ---- FRI commit (FriProver::commit)
@@ -543,16 +554,6 @@ inline ProveResult prove_brainfuck(Backend& B, const std::vector<uint32_t>& code
   G.flush();
   lap("decommit");
 
-  // ---- sanity check (ProvingError::ConstraintsNotSatisfied)
-  {
-    const auto& cs = P.sampled_values[3];
-    QM31 comp = cs[0][0];
-    comp = q_add(comp, q_mul(cs[1][0], q_make(0, 1, 0, 0)));
-    comp = q_add(comp, q_mul(cs[2][0], q_make(0, 0, 1, 0)));
-    comp = q_add(comp, q_mul(cs[3][0], q_make(0, 0, 0, 1)));
-    QM31 want = eval_composition_at_point(cfg, proof.log_size, proof.claimed_sum, el, oods, P.sampled_values, random_coeff);
-    if (!q_eq(comp, want)) throw std::runtime_error("ConstraintsNotSatisfied");
-  }
   // ---- release device memory
   for (auto& t : trees) {
     if (t.borrowed) continue;  // the preprocessed tree stays with its cache

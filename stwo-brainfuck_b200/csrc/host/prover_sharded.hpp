@@ -661,6 +661,17 @@ inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_
     for (int k = 0; k < 4; k++) rq[k] = {q[k], kv.first, r0.sharded, r0.rows_len};
     quotients.push_back({kv.first, rq});
   }
+  // ---- sanity check (ProvingError::ConstraintsNotSatisfied): host arithmetic on the sampled values, done while the device works
+  // through the quotient kernels queued above instead of at the end of the proof
+  {
+    const auto& cs = P.sampled_values[3];
+    QM31 comp = cs[0][0];
+    comp = q_add(comp, q_mul(cs[1][0], q_make(0, 1, 0, 0)));
+    comp = q_add(comp, q_mul(cs[2][0], q_make(0, 0, 1, 0)));
+    comp = q_add(comp, q_mul(cs[3][0], q_make(0, 0, 0, 1)));
+    QM31 want = eval_composition_at_point(cfg, proof.log_size, proof.claimed_sum, el, oods, P.sampled_values, random_coeff);
+    if (!q_eq(comp, want)) throw std::runtime_error("ConstraintsNotSatisfied");
+  }
   lap("quotients");
 
   // ---- FRI commit
@@ -827,15 +838,6 @@ inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_
   }
   lap("decommit");
 
-  {
-    const auto& cs = P.sampled_values[3];
-    QM31 comp = cs[0][0];
-    comp = q_add(comp, q_mul(cs[1][0], q_make(0, 1, 0, 0)));
-    comp = q_add(comp, q_mul(cs[2][0], q_make(0, 0, 1, 0)));
-    comp = q_add(comp, q_mul(cs[3][0], q_make(0, 0, 0, 1)));
-    QM31 want = eval_composition_at_point(cfg, proof.log_size, proof.claimed_sum, el, oods, P.sampled_values, random_coeff);
-    if (!q_eq(comp, want)) throw std::runtime_error("ConstraintsNotSatisfied");
-  }
   // ---- release
   for (auto& t : trees) {
     for (Col x : t.polys) if (x) B.free_col(x);
