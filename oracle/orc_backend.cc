@@ -577,6 +577,13 @@ char* orc_prove_sequence_cached_json(int n, const char* const* codes, const uint
   }
 }
 
+// Test hook: the column -> owner-rank assignment of the sharded driver (prover_sharded.hpp assign_owners), so that its balance
+// and determinism can be pinned from Python (tests/test_sharded_prover.py).
+void orc_assign_owners(const uint32_t* logs, size_t n, int world, int32_t* out) {
+  std::vector<int> o = assign_owners(std::vector<uint32_t>(logs, logs + n), world);
+  for (size_t i = 0; i < n; i++) out[i] = o[i];
+}
+
 // The sharded driver on `world` in-process ranks (threads).  Every rank must produce the same proof; returns rank 0's JSON,
 // or NULL if any rank failed or the ranks disagree.
 char* orc_prove_sharded_json(const char* code, const uint8_t* input, size_t input_len, uint32_t log_max_rows, int world, int verify) {

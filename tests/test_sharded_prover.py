@@ -111,3 +111,29 @@ def test_sharded_driver_with_small_columns_replicated(orc, min_log, monkeypatch)
     js = ctypes.string_at(p)
     lib.orc_free(ctypes.c_void_p(p))
     proof_canon.check(js, g)
+
+
+def test_columns_are_dealt_longest_first(orc):
+    """assign_owners (prover_sharded.hpp): columns in descending size, each to the least-loaded rank.  The interaction tree of
+    fib19 — 4 coordinate columns of 2^24 words, 16 of 2^22, 16 of 2^20, 8 of 2^19, 8 of 2^11, 12 of 2^4 — must come out balanced
+    on 2, 4 and 8 ranks (a round-robin over the sorted list gives 6 : 3 on eight ranks), every rank must compute the same
+    assignment, and one rank owns everything at world 1."""
+    import numpy as np
+    lib = orc.lib
+    logs = np.array([24] * 4 + [22] * 16 + [11] * 4 + [19] * 8 + [4] * 12 + [20] * 16 + [11] * 4, dtype=np.uint32)
+    for world in (1, 2, 4, 8):
+        out = np.zeros(len(logs), dtype=np.int32)
+        lib.orc_assign_owners(logs.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), ctypes.c_size_t(len(logs)), world,
+                              out.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
+        again = np.zeros_like(out)
+        lib.orc_assign_owners(logs.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), ctypes.c_size_t(len(logs)), world,
+                              again.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
+        assert (out == again).all() and out.min() >= 0 and out.max() < world
+        load = np.zeros(world)
+        for lg, o in zip(logs, out):
+            load[o] += 2.0 ** int(lg)
+        assert load.max() / load.mean() < 1.02, (world, load)
+    rr = np.zeros(8)   # what the round-robin of round 1 did on eight ranks
+    for k, i in enumerate(np.argsort(-logs.astype(np.int64), kind="stable")):
+        rr[k % 8] += 2.0 ** int(logs[i])
+    assert rr.max() / rr.mean() > 1.3
