@@ -33,6 +33,11 @@ int32_t sc_all_to_all(sc_ctx* ctx, sc_comm* comm, const sc_col* send, const uint
 int32_t sc_exchange_begin(sc_ctx* ctx, sc_comm* comm);
 int32_t sc_exchange_push(sc_ctx* ctx, sc_comm* comm, sc_col* const* cols, const uint64_t* segs, const uint8_t* sharded, uint32_t n,
                          const uint64_t* recv_counts, sc_col** recv_out);
+/* The same windows for the opposite direction (row ranges -> whole columns on an owner: the composition accumulators before
+ * the accumulator-finalize transforms): piece j of this rank lands, whole, at word dst_offs[j] of rank dest_ranks[j]'s region.
+ * Every rank passes the same region_words; *recv_out = this rank's region or NULL (fall back to sc_all_to_all). */
+int32_t sc_exchange_scatter(sc_ctx* ctx, sc_comm* comm, sc_col* const* cols, const uint32_t* dest_ranks, const uint64_t* dst_offs, uint32_t n,
+                            uint64_t region_words, sc_col** recv_out);
 int32_t sc_all_gather(sc_ctx* ctx, sc_comm* comm, const sc_col* send, sc_col* recv, uint64_t n);   /* Merkle sub-roots */
 int32_t sc_allreduce_host_u32(sc_ctx* ctx, sc_comm* comm, uint32_t* buf, uint64_t n);              /* tiny host tables */
 

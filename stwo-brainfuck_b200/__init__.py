@@ -560,7 +560,7 @@ def clear_preprocessed_cache(backend: CudaBackend) -> None:
 # ---------------------------------------------------------------------------------------------------------------------
 # multi-GPU: one process per GPU, NCCL communicator created from an id that the launcher broadcasts (torch.distributed)
 SHARDED_SYMBOLS = ["sc_comm_unique_id", "sc_comm_init", "sc_comm_destroy", "sc_comm_rank", "sc_comm_world", "sc_all_to_all",
-                   "sc_all_gather", "sc_allreduce_host_u32", "sc_pack_exchange", "sc_exchange_begin", "sc_exchange_push", "sc_dchan_create", "sc_dchan_mix_root_draw", "sc_dchan_finish", "sc_dchan_coeff_ptr", "sc_dchan_fri_tail",
+                   "sc_all_gather", "sc_allreduce_host_u32", "sc_pack_exchange", "sc_exchange_begin", "sc_exchange_push", "sc_exchange_scatter", "sc_dchan_create", "sc_dchan_mix_root_draw", "sc_dchan_finish", "sc_dchan_coeff_ptr", "sc_dchan_fri_tail",
                    "sc_fold_line_range_dc", "sc_fold_circle_into_line_range_dc", "sc_col_copy", "sc_col_view", "sc_fold_line_range",
                    "sc_fold_circle_into_line_range", "sc_accumulate_quotients_range", "sc_shift_prev", "sc_accumulate_col",
                    "sc_logup_generate_sel", "sc_eval_constraints_range", "sc_evaluate_repeated_range", "sbf_prove_sharded"]

@@ -318,6 +318,16 @@ struct CudaBackendImpl : Backend {
     ck(sc_pack_exchange(ctx, (sc_col* const*)cols.data(), sg.data(), sharded.data(), (uint32_t)cols.size(), (uint32_t)world(), h(send)));
   }
   void exchange_begin() override { if (comm) ck(sc_exchange_begin(ctx, comm)); }
+  Col exchange_scatter(const std::vector<Col>& pieces, const std::vector<uint32_t>& dest, const std::vector<size_t>& dst_off,
+                       size_t region_words) override {
+    if (!comm) return nullptr;
+    static const bool enabled = getenv("SC_SCATTER_EXCHANGE") != nullptr;   // opt-in until it has run on a multi-GPU box
+    if (!enabled) return nullptr;
+    std::vector<uint64_t> off(dst_off.begin(), dst_off.end());
+    sc_col* out = nullptr;
+    ck(sc_exchange_scatter(ctx, comm, (sc_col* const*)pieces.data(), dest.data(), off.data(), (uint32_t)pieces.size(), region_words, &out));
+    return out;
+  }
   Col exchange_push(const std::vector<Col>& cols, const std::vector<size_t>& segs, const std::vector<uint8_t>& sharded,
                     const std::vector<size_t>& recv_counts) override {
     if (!comm) return nullptr;

@@ -204,6 +204,12 @@ struct Backend {
   // Optional direct exchange (CUDA: peer stores into the destination's receive window, csrc/sharded.cu): exchange_begin once per
   // proof (collective); exchange_push = pack_exchange + all_to_all in one step, returning the receive buffer, or nullptr when
   // the backend has no such path (the caller then packs and calls all_to_all).  Every rank gets the same answer.
+  // the same windows, pieces -> arbitrary (rank, offset): piece j goes whole to word dst_off[j] of rank dest[j]'s region of
+  // region_words words (the same number on every rank); returns this rank's region or nullptr (no direct path)
+  virtual Col exchange_scatter(const std::vector<Col>& pieces, const std::vector<uint32_t>& dest, const std::vector<size_t>& dst_off,
+                               size_t region_words) {
+    (void)pieces; (void)dest; (void)dst_off; (void)region_words; return nullptr;
+  }
   virtual void exchange_begin() {}
   virtual Col exchange_push(const std::vector<Col>& cols, const std::vector<size_t>& segs, const std::vector<uint8_t>& sharded,
                             const std::vector<size_t>& recv_counts) {

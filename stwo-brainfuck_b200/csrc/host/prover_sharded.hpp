@@ -528,35 +528,68 @@ inline ProveResult prove_brainfuck_sharded(Backend& B, const std::vector<uint32_
     if (N == 1) {
       for (auto& kv : sub) full[kv.first] = kv.second.cols;
     } else {
+      // Direct path (CUDA): every rank writes its row range of coordinate k straight into the whole column inside owner k % N's
+      // receive window (Backend::exchange_scatter) — no send buffer, no all-to-all, no reassembly copies.  The layout of an
+      // owner's region: its coordinates of every sharded size, ascending, each a whole column of len * N words.
+      for (auto& kv : sub) full[kv.first] = {nullptr, nullptr, nullptr, nullptr};
+      Col region = nullptr;
+      {
+        std::vector<size_t> tot(N, 0);
+        std::map<std::pair<uint32_t, int>, size_t> off;   // (size, coordinate) -> offset in its owner's region
+        for (auto& kv : sub)
+          if (kv.second.sharded)
+            for (int k = 0; k < 4; k++) { off[{kv.first, k}] = tot[owner_of(k)]; tot[owner_of(k)] += kv.second.len * (size_t)N; }
+        size_t region_words = 4;
+        for (int d = 0; d < N; d++) region_words = std::max(region_words, tot[d]);
+        std::vector<Col> pieces;
+        std::vector<uint32_t> dest;
+        std::vector<size_t> doff;
+        for (auto& kv : sub)
+          if (kv.second.sharded)
+            for (int k = 0; k < 4; k++) {
+              pieces.push_back(kv.second.cols[k]); dest.push_back((uint32_t)owner_of(k));
+              doff.push_back(off[{kv.first, k}] + (size_t)me * kv.second.len);
+            }
+        region = B.exchange_scatter(pieces, dest, doff, region_words);
+        if (region) {
+          for (auto& kv : sub)
+            if (kv.second.sharded)
+              for (int k = 0; k < 4; k++)
+                if (owner_of(k) == me) full[kv.first][k] = B.view(region, off[{kv.first, k}], kv.second.len * (size_t)N);
+          B.free_col(region);   // a handle on window memory: the views stay valid for the proof
+        }
+      }
       std::vector<size_t> scount(N, 0), rcount(N, 0);
+      if (!region)
       for (auto& kv : sub) {
         if (!kv.second.sharded) continue;
         for (int k = 0; k < 4; k++) { scount[owner_of(k)] += kv.second.len; if (owner_of(k) == me) for (int s = 0; s < N; s++) rcount[s] += kv.second.len; }
       }
-      size_t stot = 0, rtot = 0;
-      for (int d = 0; d < N; d++) { stot += scount[d]; rtot += rcount[d]; }
-      Col send = B.alloc(std::max<size_t>(stot, 4)), recv = B.alloc(std::max<size_t>(rtot, 4));
-      size_t so = 0;
-      for (int d = 0; d < N; d++)
-        for (auto& kv : sub)
-          if (kv.second.sharded)
-            for (int k = 0; k < 4; k++)
-              if (owner_of(k) == d) { B.copy(send, so, kv.second.cols[k], 0, kv.second.len); so += kv.second.len; }
-      B.all_to_all(send, scount, recv, rcount);
-      B.free_col(send);
-      size_t ro = 0;
-      for (auto& kv : sub) full[kv.first] = {nullptr, nullptr, nullptr, nullptr};
-      for (int s = 0; s < N; s++)
-        for (auto& kv : sub)
-          if (kv.second.sharded)
-            for (int k = 0; k < 4; k++)
-              if (owner_of(k) == me) {
-                Col& dst = full[kv.first][k];
-                if (!dst) dst = B.alloc(kv.second.len * N);
-                B.copy(dst, (size_t)s * kv.second.len, recv, ro, kv.second.len);
-                ro += kv.second.len;
-              }
-      B.free_col(recv);
+      if (!region) {   // packed send buffer -> all-to-all -> reassembly
+        size_t stot = 0, rtot = 0;
+        for (int d = 0; d < N; d++) { stot += scount[d]; rtot += rcount[d]; }
+        Col send = B.alloc(std::max<size_t>(stot, 4)), recv = B.alloc(std::max<size_t>(rtot, 4));
+        size_t so = 0;
+        for (int d = 0; d < N; d++)
+          for (auto& kv : sub)
+            if (kv.second.sharded)
+              for (int k = 0; k < 4; k++)
+                if (owner_of(k) == d) { B.copy(send, so, kv.second.cols[k], 0, kv.second.len); so += kv.second.len; }
+        B.all_to_all(send, scount, recv, rcount);
+        B.free_col(send);
+        size_t ro = 0;
+        for (int s = 0; s < N; s++)
+          for (auto& kv : sub)
+            if (kv.second.sharded)
+              for (int k = 0; k < 4; k++)
+                if (owner_of(k) == me) {
+                  Col& dst = full[kv.first][k];
+                  if (!dst) dst = B.alloc(kv.second.len * N);
+                  B.copy(dst, (size_t)s * kv.second.len, recv, ro, kv.second.len);
+                  ro += kv.second.len;
+                }
+        B.free_col(recv);
+      }
       for (auto& kv : sub)
         for (int k = 0; k < 4; k++) {
           if (kv.second.sharded) B.free_col(kv.second.cols[k]);

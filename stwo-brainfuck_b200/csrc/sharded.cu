@@ -87,6 +87,20 @@ __global__ void __launch_bounds__(256) push_exchange_kernel(const PackCol* __res
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < c.seg; i += gridDim.x * blockDim.x) dst[i] = src[i];
   }
 }
+// Row ranges -> whole columns on their owners (the composition accumulators): piece j of this rank goes, whole, to ONE rank's
+// window at a caller-given offset.  Same windows, same completion barrier as push_exchange_kernel.
+struct ScatterCol { const uint32_t* src; uint32_t len; uint32_t dest; uint64_t off; };
+__global__ void __launch_bounds__(256) scatter_exchange_kernel(const ScatterCol* __restrict__ cols, uint32_t* const* __restrict__ peer, uint64_t win_off) {
+  const ScatterCol c = cols[blockIdx.y];
+  uint32_t* dst = peer[c.dest] + win_off + c.off;
+  if (((c.len | c.off | win_off) & 3u) == 0) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(c.src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < c.len / 4; i += gridDim.x * blockDim.x) d4[i] = s4[i];
+  } else {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < c.len; i += gridDim.x * blockDim.x) dst[i] = c.src[i];
+  }
+}
 // out[row] = col[storage index of the coset-order predecessor of row]  (offset_bit_reversed_circle_domain_index(.., -1))
 __global__ void shift_prev_kernel(const uint32_t* __restrict__ col, uint32_t* __restrict__ out, uint32_t e) {
   uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
@@ -519,6 +533,43 @@ int32_t sc_exchange_push(sc_ctx* ctx, sc_comm* c, sc_col* const* cols, const uin
   }
   { ProfScope ps_(ctx, "nccl_all_reduce"); CKN(nccl()->AllReduce(c->d_flag, c->d_flag, 1, ncclUint32, ncclSum, c->comm, ctx->st)); }
   sc_col* r = new sc_col{c->win + c->win_off, rtot};
+  r->owned = false;
+  track(ctx, r);
+  *recv_out = r;
+  c->win_off += region;
+  return SC_OK;
+}
+// Pieces of this rank to arbitrary places in arbitrary ranks' windows: piece j (cols[j], whole) lands at word dst_offs[j] of
+// rank dest_ranks[j]'s region.  Every rank calls this with the same region_words (the windows advance together); the caller's
+// layout must make the pieces of all ranks disjoint.  *recv_out: this rank's region, or NULL when the direct path is not
+// available (the caller then falls back to its all-to-all).  Used for the composition accumulators: row ranges -> whole
+// coordinate columns on their owner ranks.
+int32_t sc_exchange_scatter(sc_ctx* ctx, sc_comm* c, sc_col* const* cols, const uint32_t* dest_ranks, const uint64_t* dst_offs, uint32_t n,
+                            uint64_t region_words, sc_col** recv_out) {
+  ENTER();
+  if (!c || !recv_out || (n && (!cols || !dest_ranks || !dst_offs))) return fail(SC_EINVAL, "exchange_scatter: null argument");
+  *recv_out = nullptr;
+  const uint64_t region = (region_words + 63) & ~63ull;
+  c->win_need += region;
+  if (!c->push_ok || c->win_off + region > c->win_cap) return SC_OK;
+  std::vector<ScatterCol> sc(n);
+  uint32_t max_len = 1;
+  for (uint32_t j = 0; j < n; j++) {
+    if (!cols[j] || cols[j]->len > 0xffffffffull || (int)dest_ranks[j] >= c->world || dst_offs[j] + cols[j]->len > region_words)
+      return fail(SC_EINVAL, "exchange_scatter: bad piece");
+    sc[j] = {cols[j]->d, (uint32_t)cols[j]->len, dest_ranks[j], dst_offs[j]};
+    max_len = std::max<uint32_t>(max_len, (uint32_t)cols[j]->len);
+  }
+  if (n) {
+    void* d_sc = nullptr;
+    { int32_t r = stage(ctx, sc.data(), sc.size() * sizeof(ScatterCol), &d_sc); if (r) return r; }
+    const uint32_t bx = std::max(1u, std::min(128u, (max_len / 4 + 255) / 256));
+    ProfScope ps_(ctx, "push_exchange");
+    scatter_exchange_kernel<<<dim3(bx, n), 256, 0, ctx->st>>>((const ScatterCol*)d_sc, c->d_peer, c->win_off);
+    g_launch_count++; CK(cudaGetLastError());
+  }
+  { ProfScope ps_(ctx, "nccl_all_reduce"); CKN(nccl()->AllReduce(c->d_flag, c->d_flag, 1, ncclUint32, ncclSum, c->comm, ctx->st)); }
+  sc_col* r = new sc_col{c->win + c->win_off, region_words};
   r->owned = false;
   track(ctx, r);
   *recv_out = r;
