@@ -14,10 +14,13 @@
 //  * everything that shapes addressing (K, round start, radix) is a template parameter: shared-memory accesses are
 //    [base + immediate], twiddles of a round are fetched with 128/64-bit loads (one load serves the circle layer and line
 //    layer 1), and ncu showed the round-1 version spending 13.9 instructions per element-layer against ~6 for the math;
-//  * butterflies are balanced across the two integer pipes: twiddles are stored doubled so that the 64-bit product 2bt
-//    splits into (bt >> 31, (bt & P) << 1) without a mask, additions and subtractions are IMADs with a runtime +-1 (FMA
-//    pipe), only LEA.HI and the three min() of the conditional subtractions stay on the ALU pipe: 10 integer instructions
-//    per butterfly (ncu: first version ALU 77 % / FMA 22 %, now 47-61 % / 31-38 %, issue 59-72 %);
+//  * a butterfly is 7 integer instructions: twiddles are stored doubled so that the 64-bit product 2bt splits into
+//    (bt >> 31, (bt & P) << 1) without a mask (IMAD.WIDE + LEA.HI), every conditional subtraction of P is ONE VIADDMNMX
+//    (min(s, s + imm)), the two additions are IMADs with a runtime +-1 held in a uniform register (FMA pipe): 4 ALU-pipe +
+//    3 FMA-pipe instructions (ncu: ALU 51-62 %, FMA 21-25 %, issue 58-68 %; the 10-instruction form of round 1 was bound by
+//    the FMA pipe's IMAD rate);
+//  * shared memory is padded per pass so that every round is bank-conflict-free (struct Pad) and the load / store phases of
+//    the strided passes use 128-bit accesses;
 //  * columns that repeat every value 2^r times (the whole main trace, r = 4) are transformed on their distinct values: the
 //    LINE variants at the end of this file;
 //  * columns of one size are batched through blockIdx.y, so concurrent CTAs share twiddle lines in L1/L2;
