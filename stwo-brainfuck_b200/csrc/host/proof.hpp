@@ -6,6 +6,7 @@
 #include <map>
 #include <set>
 #include <charconv>
+#include <cstring>
 #include <sstream>
 #include <string>
 #include "backend.hpp"
@@ -184,22 +185,17 @@ inline std::string hex(const Hash& h) {   // the same digest as `[b0,b1,...,b31]
 // ostringstream: 2.1 ms per fib19 proof on the GPU box's host — inside the end-to-end time, 4 % of it on one GPU and 12 % on
 // eight; this one takes 0.2 ms for the same bytes.)
 struct JsonOut {
-  std::string s;
-  JsonOut() { s.reserve(1 << 18); }
-  JsonOut& operator<<(const char* t) { s.append(t); return *this; }
-  JsonOut& operator<<(const std::string& t) { s.append(t); return *this; }
-  JsonOut& operator<<(uint64_t v) {
-    char buf[24];
-    auto r = std::to_chars(buf, buf + sizeof(buf), v);
-    s.append(buf, (size_t)(r.ptr - buf));
-    return *this;
-  }
-  JsonOut& operator<<(uint32_t v) { return *this << (uint64_t)v; }
-  JsonOut& operator<<(const Hash& h) {   // `[b0,b1,...,b31]`: most of a proof's text; written through a pointer
+  std::string s;   // s[0 .. n) is the text so far; the rest is spare room that every writer checks before it writes
+  size_t n = 0;
+  JsonOut() { s.resize(1 << 18); }
+  char* room(size_t k) { if (n + k > s.size()) s.resize(std::max(s.size() * 2, n + k)); return &s[n]; }
+  JsonOut& operator<<(const char* t) { const size_t k = strlen(t); memcpy(room(k), t, k); n += k; return *this; }
+  JsonOut& operator<<(uint64_t v) { char* w = room(24); n += (size_t)(std::to_chars(w, w + 24, v).ptr - w); return *this; }
+  JsonOut& operator<<(uint32_t v) { char* w = room(12); n += (size_t)(std::to_chars(w, w + 12, v).ptr - w); return *this; }
+  JsonOut& operator<<(const Hash& h) {   // `[b0,b1,...,b31]`: most of a proof's text
     const uint8_t* b = (const uint8_t*)h.data();
-    const size_t n = s.size();
-    s.resize(n + 2 + 32 * 4);
-    char* w = &s[n];
+    char* const w0 = room(2 + 32 * 4);
+    char* w = w0;
     *w++ = '[';
     for (int i = 0; i < 32; i++) {
       if (i) *w++ = ',';
@@ -209,10 +205,10 @@ struct JsonOut {
       else *w++ = (char)('0' + v);
     }
     *w++ = ']';
-    s.resize((size_t)(w - s.data()));
+    n += (size_t)(w - w0);
     return *this;
   }
-  std::string str() { return std::move(s); }
+  std::string str() { s.resize(n); return std::move(s); }
 };
 inline void jq(JsonOut& o, const QM31& q) { o << "[[" << q.a.a << "," << q.a.b << "],[" << q.b.a << "," << q.b.b << "]]"; }
 inline void jdec(JsonOut& o, const MerkleDecommitment& d) {
